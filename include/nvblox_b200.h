@@ -1,0 +1,252 @@
+/*
+ * nvblox_b200.h -- C-ABI of the B200-native depth-integration hot path.
+ *
+ * This is the drop-in boundary for ONE path of nvblox_core:
+ *   ViewCalculator::getBlocksInImageViewRaycast  ->
+ *   ProjectiveTsdfIntegrator::integrateFrame     ->
+ *   EsdfIntegrator::integrateBlocks
+ * as driven by nvblox::Mapper::integrateDepth / Mapper::updateEsdf.
+ *
+ * The reference exposes this path as a C++ ABI (libnvblox_lib.so + Eigen-typed
+ * headers). The library below is the C core a source-compatible `nvblox/...`
+ * header set forwards to (see INTEGRATION.md and include/nvblox/): plain
+ * pointers and sizes only, no Eigen / torch / STL types in any signature.
+ *
+ * Citations: paths are relative to
+ *   /root/reference/nvblox_ros/nvblox_core/nvblox/   ("C/" in SURVEY.md)
+ *
+ * Conventions
+ *   - Every function returns NVB_OK (0) or a negative NvbStatus; the message of
+ *     the last failure on the calling thread is nvb_last_error(). (The reference
+ *     aborts the process through glog CHECK on the same conditions,
+ *     C/include/nvblox/core/internal/error_check.h:28-65; the C++ mirror in
+ *     include/nvblox/ turns a non-zero status back into an abort.)
+ *   - Transforms are 16 floats, 4x4 column-major = Eigen::Isometry3f::data()
+ *     (C/include/nvblox/core/types.h:141-153).
+ *   - Block indices are int32 triples (Index3D = Eigen::Vector3i).
+ *   - Voxel layouts in device memory are the reference's
+ *     (C/include/nvblox/map/voxels.h:28-74, blox.h:28-67): a block is
+ *     voxels[8][8][8], z fastest; TsdfVoxel 8 B, EsdfVoxel 20 B.
+ *   - Functions without the _async suffix are synchronous at return, like the
+ *     reference (projective_integrator_impl.cuh:305, esdf_integrator.cu:258).
+ *   - One NvbMapper is driven from one host thread (same as nvblox::Mapper).
+ */
+#ifndef NVBLOX_B200_H_
+#define NVBLOX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define NVB_API
+#else
+#define NVB_API __attribute__((visibility("default")))
+#endif
+
+typedef enum {
+  NVB_OK = 0,
+  NVB_ERR_INVALID_ARGUMENT = -1,
+  NVB_ERR_CUDA = -2,
+  NVB_ERR_CAPACITY = -3,      /* a slab / hash could not be grown */
+  NVB_ERR_INDEX_RANGE = -4,   /* a block index does not fit the 21-bit hash key */
+  NVB_ERR_NO_DEVICE = -5
+} NvbStatus;
+
+/* Where a caller buffer lives. */
+typedef enum { NVB_MEM_HOST = 0, NVB_MEM_DEVICE = 1 } NvbMemory;
+
+/* Layers of the map (C/include/nvblox/map/common_names.h TsdfLayer / EsdfLayer). */
+typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1 } NvbLayer;
+
+/* nvblox::Camera without distortion (C/include/nvblox/sensors/camera.h:193-203). */
+typedef struct {
+  float fu, fv, cu, cv;
+  int32_t width, height;
+} NvbCamera;
+
+/* WeightingFunctionType (C/include/nvblox/integrators/weighting_function.h:11-18). */
+typedef enum {
+  NVB_WEIGHT_CONSTANT = 0,
+  NVB_WEIGHT_CONSTANT_DROPOFF = 1,
+  NVB_WEIGHT_INVERSE_SQUARE = 2,
+  NVB_WEIGHT_INVERSE_SQUARE_DROPOFF = 3,
+  NVB_WEIGHT_INVERSE_SQUARE_TSDF_DISTANCE_PENALTY = 4,
+  NVB_WEIGHT_LINEAR_WITH_MAX = 5
+} NvbWeighting;
+
+/* WorkspaceBoundsType (C/include/nvblox/geometry/workspace_bounds.h:24). */
+typedef enum { NVB_WS_UNBOUNDED = 0, NVB_WS_HEIGHT_BOUNDS = 1, NVB_WS_BOUNDING_BOX = 2 } NvbWorkspaceBounds;
+
+/* MaskMode (C/include/nvblox/sensors/image.h:383). */
+typedef enum { NVB_MASK_NON_INVERTED = 0, NVB_MASK_INVERTED = 1 } NvbMaskMode;
+
+/* ProjectiveIntegrator / ProjectiveTsdfIntegrator / ViewCalculator parameters
+ * (C/include/nvblox/integrators/projective_integrator_params.h:24-63,
+ *  view_calculator_params.h:22-60). */
+typedef struct {
+  float truncation_distance_vox;    /* 4   */
+  float max_integration_distance_m; /* 7   */
+  float max_weight;                 /* 5   */
+  float invalid_depth_decay_factor; /* -1 (off) */
+  int32_t weighting_type;           /* NVB_WEIGHT_INVERSE_SQUARE */
+  int32_t raycast_subsampling;      /* 4   */
+  int32_t workspace_bounds_type;    /* NVB_WS_UNBOUNDED */
+  float workspace_min[3];
+  float workspace_max[3];
+} NvbTsdfParams;
+
+/* EsdfIntegrator parameters (C/include/nvblox/integrators/esdf_integrator_params.h:22-31). */
+typedef struct {
+  float max_esdf_distance_m;   /* 2    */
+  float max_site_distance_vox; /* 1    */
+  float min_weight;            /* 1e-4 */
+} NvbEsdfParams;
+
+/* TsdfVoxel / EsdfVoxel as stored in HBM (C/include/nvblox/map/voxels.h:28-34,55-74). */
+typedef struct {
+  float distance;
+  float weight;
+} NvbTsdfVoxel;
+
+typedef struct {
+  float squared_distance_vox;
+  int32_t parent_direction[3];
+  uint8_t is_inside, observed, is_site, pad_;
+} NvbEsdfVoxel;
+
+/* Construction options. capacity = number of 8x8x8 blocks each layer's slab is
+ * sized for up front (it grows by doubling, which is a synchronising event;
+ * BlockMemoryPool does the same, C/include/nvblox/map/internal/impl/
+ * block_memory_pool_impl.h:30-73). 0 selects the default (65536). */
+typedef struct {
+  float voxel_size_m;
+  int32_t device;                /* CUDA device ordinal */
+  int32_t tsdf_capacity_blocks;
+  int32_t esdf_capacity_blocks;
+  int32_t esdf_persistent;       /* 1: whole ESDF wavefront in one cooperative launch (default);
+                                    0: one launch per ring with a host-read counter, like the reference */
+} NvbMapperOptions;
+
+/* = nvblox::Mapper restricted to {TsdfLayer, EsdfLayer, ProjectiveTsdfIntegrator,
+ * EsdfIntegrator, BlocksToUpdateTracker(kEsdf)} (C/include/nvblox/mapper/mapper.h:107-836). */
+typedef struct NvbMapper NvbMapper;
+
+NVB_API const char* nvb_last_error(void);
+NVB_API const char* nvb_version(void);
+/* Number of CUDA devices visible (0 if none / no driver). */
+NVB_API int32_t nvb_device_count(void);
+
+NVB_API void nvb_default_mapper_options(NvbMapperOptions* opts);
+NVB_API void nvb_default_tsdf_params(NvbTsdfParams* p);
+NVB_API void nvb_default_esdf_params(NvbEsdfParams* p);
+
+/* Mapper::Mapper(voxel_size_m, ...) (mapper.h:119-124). */
+NVB_API int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out);
+NVB_API void nvb_mapper_destroy(NvbMapper* m);
+/* LayerCake::clear + tracker reset. */
+NVB_API int32_t nvb_mapper_clear(NvbMapper* m);
+/* Mapper::tsdf_integrator().<setters> (projective_tsdf_integrator.h:59-121,
+ * projective_integrator.h:56-85, view_calculator.h:88-145). */
+NVB_API int32_t nvb_mapper_set_tsdf_params(NvbMapper* m, const NvbTsdfParams* p);
+NVB_API int32_t nvb_mapper_get_tsdf_params(const NvbMapper* m, NvbTsdfParams* p);
+/* Mapper::esdf_integrator().<setters> (esdf_integrator.h:178-283). */
+NVB_API int32_t nvb_mapper_set_esdf_params(NvbMapper* m, const NvbEsdfParams* p);
+NVB_API int32_t nvb_mapper_get_esdf_params(const NvbMapper* m, NvbEsdfParams* p);
+NVB_API float nvb_mapper_voxel_size(const NvbMapper* m);
+NVB_API float nvb_mapper_block_size(const NvbMapper* m);
+
+/* ViewCalculator::getBlocksInImageViewRaycast<Camera> (view_calculator.h:75-80,
+ * view_calculator_impl.cuh:117-198). Does not touch the map. Writes up to
+ * cap triples to out_xyz_host (x-fastest order inside the view AABB) and the
+ * full count to *out_count. */
+NVB_API int32_t nvb_view_raycast(NvbMapper* m, const float* depth, int32_t depth_memory,
+                                 int32_t rows, int32_t cols, const float* T_L_C,
+                                 const NvbCamera* cam, float block_size,
+                                 float max_integration_distance_behind_surface_m,
+                                 float max_integration_distance_m, int32_t* out_xyz_host,
+                                 int32_t cap, int32_t* out_count);
+
+/* Mapper::integrateDepth(MaskedDepthImageConstView, T_L_C, Camera)
+ * (mapper.h:167-172, mapper_impl.h:28-81) =
+ * ProjectiveTsdfIntegrator::integrateFrame (projective_tsdf_integrator.h:48-52)
+ * + BlocksToUpdateTracker::addBlocksToUpdate. mask may be NULL
+ * (kMaskActiveEverywhere). updated_xyz_host may be NULL; otherwise it receives
+ * up to cap triples of `updated_blocks` and *out_count the full count. */
+NVB_API int32_t nvb_mapper_integrate_depth(NvbMapper* m, const float* depth, const uint8_t* mask,
+                                           int32_t mask_mode, int32_t memory, int32_t rows,
+                                           int32_t cols, const float* T_L_C, const NvbCamera* cam,
+                                           int32_t* updated_xyz_host, int32_t cap,
+                                           int32_t* out_count);
+
+/* Same work, enqueued on the mapper's stream; returns without synchronising.
+ * Host depth/mask buffers must stay valid (and should be pinned) until
+ * nvb_mapper_synchronize. The per-frame block count can be read afterwards with
+ * nvb_mapper_last_frame_block_count. */
+NVB_API int32_t nvb_mapper_integrate_depth_async(NvbMapper* m, const float* depth,
+                                                 const uint8_t* mask, int32_t mask_mode,
+                                                 int32_t memory, int32_t rows, int32_t cols,
+                                                 const float* T_L_C, const NvbCamera* cam);
+
+/* Mapper::updateEsdf(UpdateFullLayer) (mapper.h:326, src/mapper/mapper.cpp:408-430):
+ * EsdfIntegrator::integrateBlocks over the blocks touched since the last call
+ * (all TSDF blocks on the first call or when update_full_layer != 0). */
+NVB_API int32_t nvb_mapper_update_esdf(NvbMapper* m, int32_t update_full_layer);
+NVB_API int32_t nvb_mapper_update_esdf_async(NvbMapper* m, int32_t update_full_layer);
+
+/* EsdfIntegrator::integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
+ * (esdf_integrator.h:56-58, src/integrators/esdf_integrator.cu:220-266) on an
+ * explicit block list; does not consult or reset the tracker. */
+NVB_API int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host,
+                                          int32_t num_blocks);
+
+/* cudaStreamSynchronize on the mapper's stream + deferred error check. */
+NVB_API int32_t nvb_mapper_synchronize(NvbMapper* m);
+NVB_API int32_t nvb_mapper_last_frame_block_count(NvbMapper* m, int32_t* out_count);
+/* The CUDA stream (cudaStream_t) all of the mapper's work is enqueued on
+ * (Mapper's shared CudaStream, src/mapper/mapper.cpp:28-46). */
+NVB_API void* nvb_mapper_stream(NvbMapper* m);
+
+/* BlockLayer queries (C/include/nvblox/map/layer.h:76-311). All synchronising. */
+NVB_API int32_t nvb_layer_num_blocks(NvbMapper* m, int32_t layer, int32_t* out_count);      /* numBlocks        */
+NVB_API int32_t nvb_layer_block_indices(NvbMapper* m, int32_t layer, int32_t* out_xyz_host,
+                                        int32_t cap, int32_t* out_count);                    /* getAllBlockIndices */
+/* getBlockAtIndex(...)->voxels copied to host: out_host receives n blocks of
+ * block_bytes (4096 TSDF / 10240 ESDF); found[i] = 0 for unallocated indices
+ * (their output bytes are zero). */
+NVB_API int32_t nvb_layer_get_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_host,
+                                     int32_t n, void* out_host, uint8_t* found_host);
+/* allocateBlockAtIndex + host->device copy of the voxels (tests, map loading). */
+NVB_API int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_host,
+                                     int32_t n, const void* in_host);
+/* getBlockAtIndex(index).get(): raw device pointer of a block, NULL if absent.
+ * Valid until the layer's slab grows or the map is cleared. */
+NVB_API int32_t nvb_layer_block_device_ptr(NvbMapper* m, int32_t layer, const int32_t xyz[3],
+                                           void** out_ptr);
+NVB_API int32_t nvb_layer_block_bytes(int32_t layer);
+
+/* Counters of the last ESDF update (for the roofline's algorithmic bytes):
+ * [0] blocks marked, [1] blocks with sites, [2] blocks to clear, [3] clear-pass
+ * candidate blocks, [4] blocks cleared, [5] swept blocks, [6] (block,direction)
+ * face passes, [7] rings. Synchronising. */
+NVB_API int32_t nvb_mapper_last_esdf_stats(NvbMapper* m, int64_t out[8]);
+
+/* Per-stage device time of the frames since the last reset, measured with CUDA
+ * events on the mapper's stream when profiling is enabled (same names as the
+ * reference's timers: "tsdf/integrate", "esdf/integrate", ...;
+ * projective_integrator_impl.cuh:230-270, esdf_integrator.cu:224-252).
+ * stage ids: 0 view raycast, 1 block compaction+allocation, 2 tsdf update,
+ * 3 esdf allocate+mark, 4 esdf clear, 5 esdf compute. out_ms / out_calls have 6 entries. */
+NVB_API int32_t nvb_mapper_enable_profiling(NvbMapper* m, int32_t enable);
+NVB_API int32_t nvb_mapper_stage_times(NvbMapper* m, double* out_ms, int64_t* out_calls,
+                                       int32_t reset);
+/* Number of kernels this library launched on behalf of the mapper since creation. */
+NVB_API int64_t nvb_mapper_kernel_launches(const NvbMapper* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVBLOX_B200_H_ */

@@ -1,0 +1,1046 @@
+// nvb_api.cu -- the C-ABI (include/nvblox_b200.h) and the host-side orchestration.
+//
+// Host responsibilities are reduced to what the reference also does on the host
+// for this path and cannot be avoided: the view AABB from the camera pose
+// (Camera::getViewAABB, nvblox/src/sensors/camera.cpp:31-83; ViewCalculator setup,
+// view_calculator_impl.cuh:137-156), T_C_L = T_L_C^-1
+// (projective_integrator_impl.cuh:268), and capacity bookkeeping. Block lists,
+// allocation, the update tracker and the ESDF wavefront stay on the device.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nvb_internal.cuh"
+
+using namespace nvb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define NVB_CUDA(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t e_ = (expr);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(NVB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                 \
+  } while (0)
+
+constexpr int kDefaultCapacity = 1 << 18;
+constexpr int kStagingBuffers = 3;
+constexpr int kCountRing = 8;
+constexpr int kNumStages = 6;
+
+struct StageEvent {
+  cudaEvent_t start, stop;
+  int stage;
+};
+
+}  // namespace
+
+struct NvbMapper {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  float voxel_size = 0.05f, block_size = 0.4f;
+  NvbTsdfParams tp;
+  NvbEsdfParams ep;
+  int esdf_persistent = 1;
+
+  DevLayer tsdf{}, esdf{};
+  int tsdf_count_ub = 0;   // host-side upper bound of *tsdf.count
+  int esdf_extra_ub = 0;   // blocks submitted to the ESDF through explicit lists
+
+  // per-frame scratch
+  unsigned int* bits = nullptr;
+  size_t bits_words_cap = 0;
+  int4* frame_blocks = nullptr;
+  int frame_cap = 0;
+  int* frame_count = nullptr;
+  unsigned long long* tile_state = nullptr;
+  int tile_cap = 0;
+  unsigned int* ticket = nullptr;
+  unsigned int ticket_base = 0;
+  unsigned int epoch = 0;
+  int* error_dev = nullptr;
+
+  // depth / mask staging for host inputs
+  float* depth_stage[kStagingBuffers] = {nullptr, nullptr, nullptr};
+  unsigned char* mask_stage[kStagingBuffers] = {nullptr, nullptr, nullptr};
+  size_t stage_pixels = 0;
+  cudaEvent_t stage_copied[kStagingBuffers];
+  cudaEvent_t stage_consumed[kStagingBuffers];
+  bool stage_used[kStagingBuffers] = {false, false, false};
+  unsigned long long frame_seq = 0;
+
+  // tracker
+  int* dirty = nullptr;
+  int* todo_slots = nullptr;
+  int* todo_count = nullptr;
+  bool tracker_initialized = false;
+
+  // esdf scratch
+  int2* work = nullptr;
+  int* esdf_ints = nullptr;  // small counters block
+  int* upd_list = nullptr;
+  int* clr_list = nullptr;
+  int* cleared_list = nullptr;
+  int* ring_a = nullptr;
+  int* ring_b = nullptr;
+  int* stamp_a = nullptr;
+  int* stamp_b = nullptr;
+  long long* stats = nullptr;
+  unsigned int* barrier = nullptr;
+  int* xyz_upload = nullptr;
+  int xyz_upload_cap = 0;
+
+  // pinned host scratch
+  int* h_ints = nullptr;  // [0] frame count, [1] error, [2..] misc
+  int* h_count_ring = nullptr;
+  cudaEvent_t count_events[kCountRing];
+  bool count_pending[kCountRing];
+  long long count_cum_at[kCountRing];  // cells_cum when the read-back was enqueued
+  int count_ring_head = 0;
+  int tsdf_count_confirmed = 0;        // last *tsdf.count seen by the host ...
+  long long confirmed_cum = 0;         // ... and cells_cum at that moment
+  long long cells_cum = 0;             // sum of the view-AABB cells of every frame enqueued so far
+
+  long long launches = 0;
+  bool profiling = false;
+  std::vector<StageEvent> stage_events;
+  double stage_ms[kNumStages] = {0, 0, 0, 0, 0, 0};
+  long long stage_calls[kNumStages] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int nextPow2(long long v) {
+  long long p = 1;
+  while (p < v) p <<= 1;
+  return (int)p;
+}
+
+int allocLayer(DevLayer* L, int capacity, int block_bytes, cudaStream_t stream) {
+  L->capacity = capacity;
+  L->block_bytes = block_bytes;
+  NVB_CUDA(cudaMalloc(&L->blocks, (size_t)capacity * block_bytes));
+  NVB_CUDA(cudaMemsetAsync(L->blocks, 0, (size_t)capacity * block_bytes, stream));
+  NVB_CUDA(cudaMalloc(&L->block_index, (size_t)capacity * 3 * sizeof(int)));
+  NVB_CUDA(cudaMalloc(&L->count, sizeof(int)));
+  NVB_CUDA(cudaMemsetAsync(L->count, 0, sizeof(int), stream));
+  const int hcap = nextPow2(2ll * capacity);
+  L->hash.mask = (unsigned int)hcap - 1;
+  NVB_CUDA(cudaMalloc(&L->hash.keys, (size_t)hcap * sizeof(unsigned long long)));
+  NVB_CUDA(cudaMalloc(&L->hash.vals, (size_t)hcap * sizeof(int)));
+  launchFillU64(L->hash.keys, kEmptyKey, (size_t)hcap, stream);
+  return NVB_OK;
+}
+
+void freeLayer(DevLayer* L) {
+  cudaFree(L->blocks), cudaFree(L->block_index), cudaFree(L->count), cudaFree(L->hash.keys), cudaFree(L->hash.vals);
+  *L = DevLayer{};
+}
+
+template <typename T>
+int reallocCopy(T** p, size_t old_n, size_t new_n, bool zero_rest, cudaStream_t stream) {
+  T* q = nullptr;
+  NVB_CUDA(cudaMalloc(&q, new_n * sizeof(T)));
+  if (zero_rest) NVB_CUDA(cudaMemsetAsync(q, 0, new_n * sizeof(T), stream));
+  if (*p && old_n) NVB_CUDA(cudaMemcpyAsync(q, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+  NVB_CUDA(cudaStreamSynchronize(stream));
+  if (*p) cudaFree(*p);
+  *p = q;
+  return NVB_OK;
+}
+
+// Doubling growth of a layer slab (BlockMemoryPool expansion,
+// map/internal/impl/block_memory_pool_impl.h:54-73). Synchronising and rare.
+int growLayer(NvbMapper* m, DevLayer* L, int new_capacity) {
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int count = 0;
+  NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
+  count = std::min(count, L->capacity);
+  DevLayer N{};
+  N.count = L->count;
+  N.capacity = new_capacity;
+  N.block_bytes = L->block_bytes;
+  NVB_CUDA(cudaMalloc(&N.blocks, (size_t)new_capacity * L->block_bytes));
+  NVB_CUDA(cudaMemsetAsync(N.blocks, 0, (size_t)new_capacity * L->block_bytes, m->stream));
+  NVB_CUDA(cudaMemcpyAsync(N.blocks, L->blocks, (size_t)count * L->block_bytes, cudaMemcpyDeviceToDevice, m->stream));
+  NVB_CUDA(cudaMalloc(&N.block_index, (size_t)new_capacity * 3 * sizeof(int)));
+  NVB_CUDA(cudaMemcpyAsync(N.block_index, L->block_index, (size_t)count * 3 * sizeof(int), cudaMemcpyDeviceToDevice,
+                           m->stream));
+  const int hcap = nextPow2(2ll * new_capacity);
+  N.hash.mask = (unsigned int)hcap - 1;
+  NVB_CUDA(cudaMalloc(&N.hash.keys, (size_t)hcap * sizeof(unsigned long long)));
+  NVB_CUDA(cudaMalloc(&N.hash.vals, (size_t)hcap * sizeof(int)));
+  launchFillU64(N.hash.keys, kEmptyKey, (size_t)hcap, m->stream);
+  launchRehash(N, count, m->stream);
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(L->blocks), cudaFree(L->block_index), cudaFree(L->hash.keys), cudaFree(L->hash.vals);
+  *L = N;
+  return NVB_OK;
+}
+
+int allocEsdfScratch(NvbMapper* m, int old_cap, int cap) {
+  int rc;
+  if ((rc = reallocCopy(&m->work, 0, (size_t)cap, false, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->upd_list, 0, (size_t)cap, false, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->clr_list, 0, (size_t)cap, false, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->cleared_list, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->ring_a, 0, (size_t)cap, false, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->ring_b, 0, (size_t)cap, false, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->stamp_a, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->stamp_b, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  return NVB_OK;
+}
+
+int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
+  int rc;
+  if ((rc = reallocCopy(&m->dirty, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->todo_slots, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  return NVB_OK;
+}
+
+// esdf_ints layout
+enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kNumInts = 32 };
+
+EsdfCtx makeEsdfCtx(NvbMapper* m) {
+  EsdfCtx c{};
+  c.tsdf = m->tsdf, c.esdf = m->esdf;
+  c.work = m->work;
+  c.work_count = m->esdf_ints + kWorkCount;
+  c.upd_list = m->upd_list, c.upd_count = m->esdf_ints + kUpdCount;
+  c.clr_list = m->clr_list, c.clr_count = m->esdf_ints + kClrCount;
+  c.clr_aabb = m->esdf_ints + kClrAabb;
+  c.cleared_list = m->cleared_list, c.cleared_count = m->esdf_ints + kClearedCount;
+  c.ring_a = m->ring_a, c.ring_b = m->ring_b;
+  c.ring_count = m->esdf_ints + kRingCount;
+  c.stamp_a = m->stamp_a, c.stamp_b = m->stamp_b;
+  c.ring_id = m->esdf_ints + kRingId;
+  c.barrier = m->barrier;
+  c.stats = m->stats;
+  c.error = m->error_dev;
+  // esdf_integrator.cu:693-696, 672-676
+  const float max_esdf_distance_vox = m->ep.max_esdf_distance_m / m->voxel_size;
+  c.max_sq = max_esdf_distance_vox * max_esdf_distance_vox;
+  c.max_esdf_distance_m = m->ep.max_esdf_distance_m;
+  c.max_site_distance_m = m->ep.max_site_distance_vox * m->voxel_size;
+  c.min_weight = m->ep.min_weight;
+  c.block_size = m->block_size;
+  return c;
+}
+
+Rigid rigidFromColMajor(const float* T) {
+  Rigid r;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) r.r[i][j] = T[j * 4 + i];
+    r.t[i] = T[12 + i];
+  }
+  return r;
+}
+
+// Transform::inverse() for an isometry: R' = R^T, t' = -(R^T t).
+Rigid invertRigid(const Rigid& T) {
+  Rigid o;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) o.r[i][j] = T.r[j][i];
+  for (int i = 0; i < 3; i++) o.t[i] = -sum3(o.r[i][0] * T.t[0], o.r[i][1] * T.t[1], o.r[i][2] * T.t[2]);
+  return o;
+}
+
+// Camera::getViewAABB (src/sensors/camera.cpp:31-83) + applyWorkspaceBounds
+// (src/geometry/workspace_bounds.cpp:20-61) + the block-index AABB of
+// getBlocksInImageViewRaycast (view_calculator_impl.cuh:137-156).
+// Returns false when the workspace-clipped AABB is empty.
+bool computeViewGrid(const NvbCamera& cam, const Rigid& T_L_C, float block_size, float max_dist,
+                     const NvbTsdfParams& P, ViewGrid* g, long long* cells) {
+  const float w = (float)cam.width, h = (float)cam.height;
+  const float ux[4] = {0.0f, w, w, 0.0f};
+  const float vy[4] = {0.0f, 0.0f, h, h};
+  Vec3 ray[4];
+  for (int k = 0; k < 4; k++) ray[k] = Vec3{(ux[k] - cam.cu) / cam.fu, (vy[k] - cam.cv) / cam.fv, 1.0f};
+  const int order[4] = {2, 1, 0, 3};
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int k = 0; k < 8; k++) {
+    const float d = (k < 4) ? 0.0f : max_dist;
+    const Vec3 r = ray[order[k & 3]];
+    const Vec3 c = transformPoint(T_L_C, Vec3{d * r.x, d * r.y, d * r.z});
+    const float cl[3] = {c.x, c.y, c.z};
+    for (int i = 0; i < 3; i++) {
+      lo[i] = std::min(lo[i], cl[i]);
+      hi[i] = std::max(hi[i], cl[i]);
+    }
+  }
+  if (P.workspace_bounds_type == NVB_WS_HEIGHT_BOUNDS) {
+    lo[2] = std::max(lo[2], P.workspace_min[2]);
+    hi[2] = std::min(hi[2], P.workspace_max[2]);
+  } else if (P.workspace_bounds_type == NVB_WS_BOUNDING_BOX) {
+    for (int i = 0; i < 3; i++) {
+      lo[i] = std::max(P.workspace_min[i], lo[i]);
+      hi[i] = std::min(P.workspace_max[i], hi[i]);
+    }
+  }
+  if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) return false;
+  const int3 mn = blockIndexFromPosition(block_size, Vec3{lo[0], lo[1], lo[2]});
+  const int3 mx = blockIndexFromPosition(block_size, Vec3{hi[0], hi[1], hi[2]});
+  g->min_index = mn;
+  g->size = make_int3(mx.x - mn.x + 1, mx.y - mn.y + 1, mx.z - mn.z + 1);
+  *cells = (long long)g->size.x * g->size.y * g->size.z;
+  if (*cells <= 0 || *cells > 0x7fffffffll) {
+    *cells = -1;
+    return false;
+  }
+  g->linear_size = (int)*cells;
+  g->num_words = (g->linear_size + 31) / 32;
+  return true;
+}
+
+void beginStage(NvbMapper* m, int stage) {
+  if (!m->profiling) return;
+  StageEvent ev;
+  ev.stage = stage;
+  cudaEventCreate(&ev.start), cudaEventCreate(&ev.stop);
+  cudaEventRecord(ev.start, m->stream);
+  m->stage_events.push_back(ev);
+}
+void endStage(NvbMapper* m) {
+  if (!m->profiling) return;
+  cudaEventRecord(m->stage_events.back().stop, m->stream);
+}
+void collectStages(NvbMapper* m) {
+  for (auto& ev : m->stage_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.start, ev.stop) == cudaSuccess) {
+      m->stage_ms[ev.stage] += ms;
+      m->stage_calls[ev.stage]++;
+    }
+    cudaEventDestroy(ev.start), cudaEventDestroy(ev.stop);
+  }
+  m->stage_events.clear();
+}
+
+// Poll the asynchronous read-backs of *tsdf.count to tighten the host-side bound.
+// count <= confirmed + (cells enqueued since the confirmed read-back).
+void pollCounts(NvbMapper* m) {
+  for (int k = 0; k < kCountRing; k++) {
+    if (m->count_pending[k] && cudaEventQuery(m->count_events[k]) == cudaSuccess) {
+      m->count_pending[k] = false;
+      if (m->count_cum_at[k] > m->confirmed_cum) {
+        m->confirmed_cum = m->count_cum_at[k];
+        m->tsdf_count_confirmed = m->h_count_ring[k];
+      }
+    }
+  }
+  const long long ub = (long long)m->tsdf_count_confirmed + (m->cells_cum - m->confirmed_cum);
+  m->tsdf_count_ub = (int)std::min<long long>(ub, 0x7fffffff);
+}
+
+int ensureTsdfCapacity(NvbMapper* m, long long new_cells) {
+  pollCounts(m);
+  if ((long long)m->tsdf_count_ub + new_cells <= m->tsdf.capacity) return NVB_OK;
+  // refine the bound with a synchronous read
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int count = 0;
+  NVB_CUDA(cudaMemcpy(&count, m->tsdf.count, sizeof(int), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < kCountRing; k++) m->count_pending[k] = false;
+  m->tsdf_count_confirmed = count;
+  m->confirmed_cum = m->cells_cum;
+  m->tsdf_count_ub = count;
+  if ((long long)count + new_cells <= m->tsdf.capacity) return NVB_OK;
+  long long cap = m->tsdf.capacity;
+  while (cap < (long long)count + new_cells) cap *= 2;
+  if (cap > (1ll << 28)) return fail(NVB_ERR_CAPACITY, "TSDF layer would exceed 2^28 blocks");
+  const int old = m->tsdf.capacity;
+  int rc = growLayer(m, &m->tsdf, (int)cap);
+  if (rc) return rc;
+  return allocTsdfSide(m, old, (int)cap);
+}
+
+int ensureEsdfCapacity(NvbMapper* m, long long needed_total) {
+  if (needed_total <= m->esdf.capacity) return NVB_OK;
+  long long cap = m->esdf.capacity;
+  while (cap < needed_total) cap *= 2;
+  if (cap > (1ll << 28)) return fail(NVB_ERR_CAPACITY, "ESDF layer would exceed 2^28 blocks");
+  const int old = m->esdf.capacity;
+  int rc = growLayer(m, &m->esdf, (int)cap);
+  if (rc) return rc;
+  return allocEsdfScratch(m, old, (int)cap);
+}
+
+int ensureFrameScratch(NvbMapper* m, const ViewGrid& g) {
+  if ((size_t)g.num_words > m->bits_words_cap) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    const size_t cap = (size_t)(1.5 * g.num_words) + 64;  // kBufferExpansionFactor, view_calculator_impl.cuh:159
+    if (m->bits) cudaFree(m->bits);
+    NVB_CUDA(cudaMalloc(&m->bits, cap * sizeof(unsigned int)));
+    NVB_CUDA(cudaMemsetAsync(m->bits, 0, cap * sizeof(unsigned int), m->stream));
+    m->bits_words_cap = cap;
+  }
+  if (g.linear_size > m->frame_cap) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    const int cap = (int)std::min<long long>((long long)(1.5 * g.linear_size) + 64, 0x7fffffff);
+    if (m->frame_blocks) cudaFree(m->frame_blocks);
+    NVB_CUDA(cudaMalloc(&m->frame_blocks, (size_t)cap * sizeof(int4)));
+    m->frame_cap = cap;
+  }
+  const int tiles = compactNumTiles(g);
+  if (tiles > m->tile_cap) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    const int cap = tiles * 2;
+    if (m->tile_state) cudaFree(m->tile_state);
+    NVB_CUDA(cudaMalloc(&m->tile_state, (size_t)cap * sizeof(unsigned long long)));
+    NVB_CUDA(cudaMemsetAsync(m->tile_state, 0, (size_t)cap * sizeof(unsigned long long), m->stream));
+    m->tile_cap = cap;
+  }
+  return NVB_OK;
+}
+
+int ensureStaging(NvbMapper* m, size_t pixels) {
+  if (pixels <= m->stage_pixels) return NVB_OK;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->copy_stream));
+  for (int k = 0; k < kStagingBuffers; k++) {
+    if (m->depth_stage[k]) cudaFree(m->depth_stage[k]);
+    if (m->mask_stage[k]) cudaFree(m->mask_stage[k]);
+    NVB_CUDA(cudaMalloc(&m->depth_stage[k], pixels * sizeof(float)));
+    NVB_CUDA(cudaMalloc(&m->mask_stage[k], pixels));
+    m->stage_used[k] = false;
+  }
+  m->stage_pixels = pixels;
+  return NVB_OK;
+}
+
+int checkDeviceError(NvbMapper* m) {
+  int err = 0;
+  NVB_CUDA(cudaMemcpy(&err, m->error_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    cudaMemset(m->error_dev, 0, sizeof(int));
+    if (err & 2) return fail(NVB_ERR_INDEX_RANGE, "a block index does not fit the 21-bit hash key");
+    return fail(NVB_ERR_CAPACITY, "a layer slab overflowed on the device");
+  }
+  return NVB_OK;
+}
+
+int validateFrameArgs(const NvbMapper* m, const float* depth, int rows, int cols, const float* T, const NvbCamera* cam) {
+  if (!m || !depth || !T || !cam) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (rows <= 0 || cols <= 0) return fail(NVB_ERR_INVALID_ARGUMENT, "image must have positive size");
+  if (!(cam->fu != 0.0f) || !(cam->fv != 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "camera focal length is zero");
+  return NVB_OK;
+}
+
+// The depth-integration chain for one frame, enqueued on m->stream.
+int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, int mask_mode, int memory, int rows,
+                 int cols, const float* T_L_C_cm, const NvbCamera* cam, float block_size, float trunc_m,
+                 float max_dist, bool integrate) {
+  const Rigid T_L_C = rigidFromColMajor(T_L_C_cm);
+  ViewGrid grid{};
+  long long cells = 0;
+  const bool visible = computeViewGrid(*cam, T_L_C, block_size, max_dist, m->tp, &grid, &cells);
+  if (!visible) {
+    if (cells < 0) return fail(NVB_ERR_CAPACITY, "view AABB has more than 2^31 blocks");
+    NVB_CUDA(cudaMemsetAsync(m->frame_count, 0, sizeof(int), m->stream));  // empty workspace -> empty list
+    return NVB_OK;
+  }
+  int rc;
+  if ((rc = ensureFrameScratch(m, grid))) return rc;
+  if (integrate && (rc = ensureTsdfCapacity(m, cells))) return rc;
+
+  // Inputs: device pointers are used in place; host buffers go through a small
+  // ring of staging buffers on a copy stream so the upload of frame k+1 overlaps
+  // the kernels of frame k.
+  const float* depth_dev = depth;
+  const unsigned char* mask_dev = mask;
+  int stage_slot = -1;
+  if (memory == NVB_MEM_HOST) {
+    const size_t pixels = (size_t)rows * cols;
+    if ((rc = ensureStaging(m, pixels))) return rc;
+    stage_slot = (int)(m->frame_seq % kStagingBuffers);
+    if (m->stage_used[stage_slot]) NVB_CUDA(cudaStreamWaitEvent(m->copy_stream, m->stage_consumed[stage_slot], 0));
+    NVB_CUDA(cudaMemcpyAsync(m->depth_stage[stage_slot], depth, pixels * sizeof(float), cudaMemcpyHostToDevice,
+                             m->copy_stream));
+    if (mask)
+      NVB_CUDA(cudaMemcpyAsync(m->mask_stage[stage_slot], mask, pixels, cudaMemcpyHostToDevice, m->copy_stream));
+    NVB_CUDA(cudaEventRecord(m->stage_copied[stage_slot], m->copy_stream));
+    NVB_CUDA(cudaStreamWaitEvent(m->stream, m->stage_copied[stage_slot], 0));
+    depth_dev = m->depth_stage[stage_slot];
+    mask_dev = mask ? m->mask_stage[stage_slot] : nullptr;
+  }
+  m->frame_seq++;
+
+  beginStage(m, 0);
+  launchViewRaycast(depth_dev, rows, cols, T_L_C, *cam, block_size, trunc_m, max_dist, m->tp.raycast_subsampling,
+                    grid, m->bits, m->stream);
+  endStage(m);
+  m->launches++;
+
+  beginStage(m, 1);
+  CompactArgs ca{};
+  ca.bits = m->bits;
+  ca.grid = grid;
+  ca.frame_blocks = m->frame_blocks;
+  ca.frame_count = m->frame_count;
+  ca.tile_state = m->tile_state;
+  ca.ticket = m->ticket;
+  ca.ticket_base = m->ticket_base;
+  ca.epoch = ++m->epoch;
+  ca.allocate = integrate ? 1 : 0;
+  ca.layer = m->tsdf;
+  ca.error = m->error_dev;
+  ca.dirty = (integrate && m->tracker_initialized) ? m->dirty : nullptr;
+  ca.todo_slots = m->todo_slots;
+  ca.todo_count = m->todo_count;
+  launchCompactAllocate(ca, m->stream);
+  m->ticket_base += (unsigned int)compactNumTiles(grid);
+  endStage(m);
+  m->launches++;
+
+  if (integrate) {
+    beginStage(m, 2);
+    TsdfKernelParams p;
+    p.block_size = block_size;
+    p.voxel_size = block_size * (1.0f / kVps);       // blockSizeToVoxelSize, indexing_impl.h:26-29
+    p.half_voxel_size = block_size * (0.5f / kVps);  // indexing_impl.h:75-77
+    p.truncation_distance_m = trunc_m;
+    p.max_integration_distance_m = max_dist;
+    p.max_weight = m->tp.max_weight;
+    p.invalid_depth_decay_factor = m->tp.invalid_depth_decay_factor;
+    p.weighting_type = m->tp.weighting_type;
+    const Rigid T_C_L = invertRigid(T_L_C);
+    launchTsdfIntegrate(m->frame_blocks, m->frame_count, m->tsdf.blocks, depth_dev, mask_dev, mask_mode, rows, cols,
+                        T_C_L, *cam, p, m->num_sms, m->stream);
+    endStage(m);
+    m->launches++;
+    // asynchronous read-back of the slab fill level for the host-side capacity bound
+    m->cells_cum += cells;
+    const int k = m->count_ring_head;
+    if (!m->count_pending[k]) {
+      m->count_ring_head = (k + 1) % kCountRing;
+      NVB_CUDA(cudaMemcpyAsync(m->h_count_ring + k, m->tsdf.count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+      NVB_CUDA(cudaEventRecord(m->count_events[k], m->stream));
+      m->count_pending[k] = true;
+      m->count_cum_at[k] = m->cells_cum;
+    }
+    m->tsdf_count_ub = (int)std::min<long long>((long long)m->tsdf_count_ub + cells, 0x7fffffff);
+  }
+  if (stage_slot >= 0) {
+    NVB_CUDA(cudaEventRecord(m->stage_consumed[stage_slot], m->stream));
+    m->stage_used[stage_slot] = true;
+  }
+  return NVB_OK;
+}
+
+int readFrameList(NvbMapper* m, int32_t* out_xyz, int32_t cap, int32_t* out_count) {
+  NVB_CUDA(cudaMemcpyAsync(m->h_ints, m->frame_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  const int n = m->h_ints[0];
+  if (out_count) *out_count = n;
+  if (out_xyz && cap > 0 && n > 0) {
+    const int k = std::min(n, cap);
+    std::vector<int4> tmp((size_t)k);
+    NVB_CUDA(cudaMemcpy(tmp.data(), m->frame_blocks, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < k; i++) out_xyz[3 * i] = tmp[i].x, out_xyz[3 * i + 1] = tmp[i].y, out_xyz[3 * i + 2] = tmp[i].z;
+  }
+  return NVB_OK;
+}
+
+int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_tracker) {
+  int rc;
+  int upper;
+  if (from_tracker) {
+    pollCounts(m);
+    upper = std::min(m->tsdf_count_ub, m->tsdf.capacity);
+  } else {
+    upper = n_explicit;
+    m->esdf_extra_ub += n_explicit;
+  }
+  if (upper <= 0) upper = 1;
+  if ((rc = ensureEsdfCapacity(m, (long long)std::min(m->tsdf_count_ub, m->tsdf.capacity) + m->esdf_extra_ub))) return rc;
+  EsdfCtx c = makeEsdfCtx(m);
+  beginStage(m, 3);
+  if (from_tracker) {
+    launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, m->stream);
+    launchTodoConsume(m->todo_slots, m->todo_count, m->dirty, m->stream);
+    NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
+    m->launches += 2;
+  } else {
+    launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, m->stream);
+    m->launches += 1;
+  }
+  launchEsdfMark(c, upper, m->num_sms, m->stream);
+  m->launches++;
+  endStage(m);
+  beginStage(m, 4);
+  launchEsdfClear(c, m->esdf.capacity, m->num_sms, m->stream);
+  m->launches++;
+  endStage(m);
+  beginStage(m, 5);
+  int launches = 0;
+  cudaError_t e;
+  if (m->esdf_persistent) {
+    e = launchEsdfComputePersistent(c, m->num_sms, m->stream, &launches);
+  } else {
+    e = runEsdfComputeHostLoop(c, m->num_sms, m->stream, &launches);
+  }
+  m->launches += launches;
+  if (e != cudaSuccess) return fail(NVB_ERR_CUDA, std::string("ESDF compute launch: ") + cudaGetErrorString(e));
+  endStage(m);
+  return NVB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* nvb_last_error(void) { return g_last_error.c_str(); }
+const char* nvb_version(void) { return "nvblox_b200 0.1 (sm_100a)"; }
+
+int32_t nvb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void nvb_default_mapper_options(NvbMapperOptions* o) {
+  if (!o) return;
+  o->voxel_size_m = 0.05f;
+  o->device = 0;
+  o->tsdf_capacity_blocks = kDefaultCapacity;
+  o->esdf_capacity_blocks = kDefaultCapacity;
+  o->esdf_persistent = 1;
+}
+void nvb_default_tsdf_params(NvbTsdfParams* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->truncation_distance_vox = 4.0f;
+  p->max_integration_distance_m = 7.0f;
+  p->max_weight = 5.0f;
+  p->invalid_depth_decay_factor = -1.0f;
+  p->weighting_type = NVB_WEIGHT_INVERSE_SQUARE;
+  p->raycast_subsampling = 4;
+  p->workspace_bounds_type = NVB_WS_UNBOUNDED;
+}
+void nvb_default_esdf_params(NvbEsdfParams* p) {
+  if (!p) return;
+  p->max_esdf_distance_m = 2.0f;
+  p->max_site_distance_vox = 1.0f;
+  p->min_weight = 1e-4f;
+}
+
+int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
+  if (!opts || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (!(opts->voxel_size_m > 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "voxel_size_m must be > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(NVB_ERR_NO_DEVICE, "no CUDA device: the depth-integration path has no CPU fallback");
+  }
+  if (opts->device < 0 || opts->device >= ndev) return fail(NVB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+  NVB_CUDA(cudaSetDevice(opts->device));
+  NvbMapper* m = new NvbMapper();
+  m->device = opts->device;
+  cudaDeviceProp prop;
+  NVB_CUDA(cudaGetDeviceProperties(&prop, opts->device));
+  m->num_sms = prop.multiProcessorCount;
+  m->voxel_size = opts->voxel_size_m;
+  m->block_size = opts->voxel_size_m * (float)kVps;  // voxelSizeToBlockSize (indexing_impl.h:22-24)
+  nvb_default_tsdf_params(&m->tp);
+  nvb_default_esdf_params(&m->ep);
+  m->esdf_persistent = opts->esdf_persistent;
+  NVB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  NVB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  const int tcap = opts->tsdf_capacity_blocks > 0 ? opts->tsdf_capacity_blocks : kDefaultCapacity;
+  const int ecap = std::max(opts->esdf_capacity_blocks > 0 ? opts->esdf_capacity_blocks : kDefaultCapacity, tcap);
+  int rc;
+  if ((rc = allocLayer(&m->tsdf, tcap, kTsdfBlockBytes, m->stream))) return rc;
+  if ((rc = allocLayer(&m->esdf, ecap, kEsdfBlockBytes, m->stream))) return rc;
+  if ((rc = allocTsdfSide(m, 0, tcap))) return rc;
+  if ((rc = allocEsdfScratch(m, 0, ecap))) return rc;
+  NVB_CUDA(cudaMalloc(&m->esdf_ints, kNumInts * sizeof(int)));
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints, 0, kNumInts * sizeof(int), m->stream));
+  const int one = 1;
+  NVB_CUDA(cudaMemcpyAsync(m->esdf_ints + kRingId, &one, sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  m->todo_count = m->esdf_ints + kTodoCount;
+  m->frame_count = m->esdf_ints + kFrameCount;
+  m->error_dev = m->esdf_ints + kError;
+  NVB_CUDA(cudaMalloc(&m->stats, 8 * sizeof(long long)));
+  NVB_CUDA(cudaMemsetAsync(m->stats, 0, 8 * sizeof(long long), m->stream));
+  NVB_CUDA(cudaMalloc(&m->barrier, 64));
+  NVB_CUDA(cudaMemsetAsync(m->barrier, 0, 64, m->stream));
+  NVB_CUDA(cudaMalloc(&m->ticket, 64));
+  NVB_CUDA(cudaMemsetAsync(m->ticket, 0, 64, m->stream));
+  NVB_CUDA(cudaMallocHost(&m->h_ints, 64 * sizeof(int)));
+  NVB_CUDA(cudaMallocHost(&m->h_count_ring, kCountRing * sizeof(int)));
+  for (int k = 0; k < kCountRing; k++) {
+    NVB_CUDA(cudaEventCreateWithFlags(&m->count_events[k], cudaEventDisableTiming));
+    m->count_pending[k] = false;
+    m->count_cum_at[k] = 0;
+  }
+  for (int k = 0; k < kStagingBuffers; k++) {
+    NVB_CUDA(cudaEventCreateWithFlags(&m->stage_copied[k], cudaEventDisableTiming));
+    NVB_CUDA(cudaEventCreateWithFlags(&m->stage_consumed[k], cudaEventDisableTiming));
+  }
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return NVB_OK;
+}
+
+void nvb_mapper_destroy(NvbMapper* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  cudaStreamSynchronize(m->copy_stream);
+  collectStages(m);
+  freeLayer(&m->tsdf), freeLayer(&m->esdf);
+  cudaFree(m->bits), cudaFree(m->frame_blocks), cudaFree(m->tile_state), cudaFree(m->ticket);
+  for (int k = 0; k < kStagingBuffers; k++) {
+    cudaFree(m->depth_stage[k]), cudaFree(m->mask_stage[k]);
+    cudaEventDestroy(m->stage_copied[k]), cudaEventDestroy(m->stage_consumed[k]);
+  }
+  cudaFree(m->dirty), cudaFree(m->todo_slots);
+  cudaFree(m->work), cudaFree(m->esdf_ints), cudaFree(m->upd_list), cudaFree(m->clr_list), cudaFree(m->cleared_list);
+  cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
+  cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->xyz_upload);
+  cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
+  for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
+  cudaStreamDestroy(m->stream), cudaStreamDestroy(m->copy_stream);
+  delete m;
+}
+
+int32_t nvb_mapper_clear(NvbMapper* m) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  DevLayer* layers[2] = {&m->tsdf, &m->esdf};
+  for (DevLayer* L : layers) {
+    int count = 0;
+    NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
+    count = std::min(count, L->capacity);
+    // re-zero only the slots that were handed out: the slab invariant is "free slots are zero"
+    NVB_CUDA(cudaMemsetAsync(L->blocks, 0, (size_t)count * L->block_bytes, m->stream));
+    NVB_CUDA(cudaMemsetAsync(L->count, 0, sizeof(int), m->stream));
+    launchFillU64(L->hash.keys, kEmptyKey, (size_t)L->hash.mask + 1, m->stream);
+  }
+  NVB_CUDA(cudaMemsetAsync(m->dirty, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kClearedCount, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
+  m->tracker_initialized = false;
+  m->tsdf_count_ub = 0, m->tsdf_count_confirmed = 0, m->esdf_extra_ub = 0;
+  m->cells_cum = 0, m->confirmed_cum = 0;
+  for (int k = 0; k < kCountRing; k++) m->count_pending[k] = false;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_set_tsdf_params(NvbMapper* m, const NvbTsdfParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  // CHECK_GT(max_weight, 0) etc. (src/integrators/projective_tsdf_integrator.cu:61-64)
+  if (!(p->max_weight > 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "max_weight must be > 0");
+  if (!(p->truncation_distance_vox > 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "truncation_distance_vox must be > 0");
+  if (p->raycast_subsampling < 1) return fail(NVB_ERR_INVALID_ARGUMENT, "raycast_subsampling must be >= 1");
+  if (p->weighting_type < 0 || p->weighting_type > NVB_WEIGHT_LINEAR_WITH_MAX)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "unknown weighting_type");
+  if (p->workspace_bounds_type < 0 || p->workspace_bounds_type > NVB_WS_BOUNDING_BOX)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "unknown workspace_bounds_type");
+  m->tp = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_tsdf_params(const NvbMapper* m, NvbTsdfParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->tp;
+  return NVB_OK;
+}
+int32_t nvb_mapper_set_esdf_params(NvbMapper* m, const NvbEsdfParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  // CHECK_GT in the setters (src/integrators/esdf_integrator.cu:55-68)
+  if (!(p->max_esdf_distance_m > 0.0f) || !(p->max_site_distance_vox > 0.0f) || !(p->min_weight > 0.0f))
+    return fail(NVB_ERR_INVALID_ARGUMENT, "ESDF parameters must be > 0");
+  m->ep = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_esdf_params(const NvbMapper* m, NvbEsdfParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->ep;
+  return NVB_OK;
+}
+float nvb_mapper_voxel_size(const NvbMapper* m) { return m ? m->voxel_size : 0.0f; }
+float nvb_mapper_block_size(const NvbMapper* m) { return m ? m->block_size : 0.0f; }
+
+int32_t nvb_view_raycast(NvbMapper* m, const float* depth, int32_t depth_memory, int32_t rows, int32_t cols,
+                         const float* T_L_C, const NvbCamera* cam, float block_size,
+                         float max_integration_distance_behind_surface_m, float max_integration_distance_m,
+                         int32_t* out_xyz_host, int32_t cap, int32_t* out_count) {
+  int rc = validateFrameArgs(m, depth, rows, cols, T_L_C, cam);
+  if (rc) return rc;
+  if (!(block_size > 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "block_size must be > 0");
+  NVB_CUDA(cudaSetDevice(m->device));
+  if ((rc = enqueueFrame(m, depth, nullptr, 0, depth_memory, rows, cols, T_L_C, cam, block_size,
+                         max_integration_distance_behind_surface_m, max_integration_distance_m, false)))
+    return rc;
+  return readFrameList(m, out_xyz_host, cap, out_count);
+}
+
+int32_t nvb_mapper_integrate_depth_async(NvbMapper* m, const float* depth, const uint8_t* mask, int32_t mask_mode,
+                                         int32_t memory, int32_t rows, int32_t cols, const float* T_L_C,
+                                         const NvbCamera* cam) {
+  int rc = validateFrameArgs(m, depth, rows, cols, T_L_C, cam);
+  if (rc) return rc;
+  NVB_CUDA(cudaSetDevice(m->device));
+  // max_integration_distance_behind_surface_m = truncation_distance_vox * voxel_size
+  // (projective_integrator_impl.cuh:234-235)
+  const float trunc_m = m->tp.truncation_distance_vox * m->voxel_size;
+  return enqueueFrame(m, depth, mask, mask_mode, memory, rows, cols, T_L_C, cam, m->block_size, trunc_m,
+                      m->tp.max_integration_distance_m, true);
+}
+
+int32_t nvb_mapper_integrate_depth(NvbMapper* m, const float* depth, const uint8_t* mask, int32_t mask_mode,
+                                   int32_t memory, int32_t rows, int32_t cols, const float* T_L_C,
+                                   const NvbCamera* cam, int32_t* updated_xyz_host, int32_t cap, int32_t* out_count) {
+  int rc = nvb_mapper_integrate_depth_async(m, depth, mask, mask_mode, memory, rows, cols, T_L_C, cam);
+  if (rc) return rc;
+  if ((rc = readFrameList(m, updated_xyz_host, cap, out_count))) return rc;
+  return checkDeviceError(m);
+}
+
+int32_t nvb_mapper_update_esdf_async(NvbMapper* m, int32_t update_full_layer) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  if (!m->tracker_initialized || update_full_layer) {
+    // First query of the tracker, or UpdateFullLayer::kYes: every TSDF block
+    // (map/blocks_to_update_tracker.cpp:107-124, src/mapper/mapper.cpp:523-537).
+    launchTodoAll(m->tsdf, m->dirty, m->todo_slots, m->todo_count, m->stream);
+    m->launches++;
+    m->tracker_initialized = true;
+  }
+  return enqueueEsdf(m, nullptr, 0, true);
+}
+
+int32_t nvb_mapper_update_esdf(NvbMapper* m, int32_t update_full_layer) {
+  int rc = nvb_mapper_update_esdf_async(m, update_full_layer);
+  if (rc) return rc;
+  return nvb_mapper_synchronize(m);
+}
+
+int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (num_blocks < 0 || (num_blocks > 0 && !blocks_xyz_host)) return fail(NVB_ERR_INVALID_ARGUMENT, "bad block list");
+  if (num_blocks == 0) return NVB_OK;  // early return, esdf_integrator.cu:226-228
+  NVB_CUDA(cudaSetDevice(m->device));
+  // The list is a set for every caller of the reference (Mapper::getBlocksToUpdate); make it one.
+  struct K {
+    int x, y, z;
+  };
+  std::vector<K> v((size_t)num_blocks);
+  memcpy(v.data(), blocks_xyz_host, (size_t)num_blocks * sizeof(K));
+  std::sort(v.begin(), v.end(), [](const K& a, const K& b) {
+    if (a.x != b.x) return a.x < b.x;
+    if (a.y != b.y) return a.y < b.y;
+    return a.z < b.z;
+  });
+  v.erase(std::unique(v.begin(), v.end(), [](const K& a, const K& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }),
+          v.end());
+  for (const K& k : v)
+    if (!indexInRange(k.x, k.y, k.z)) return fail(NVB_ERR_INDEX_RANGE, "block index outside +-2^20");
+  const int n = (int)v.size();
+  if (n > m->xyz_upload_cap) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->xyz_upload) cudaFree(m->xyz_upload);
+    NVB_CUDA(cudaMalloc(&m->xyz_upload, (size_t)n * 2 * 3 * sizeof(int)));
+    m->xyz_upload_cap = n * 2;
+  }
+  NVB_CUDA(cudaStreamSynchronize(m->stream));  // v is pageable: order the copy before it goes out of scope
+  NVB_CUDA(cudaMemcpy(m->xyz_upload, v.data(), (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  int rc = enqueueEsdf(m, m->xyz_upload, n, false);
+  if (rc) return rc;
+  return nvb_mapper_synchronize(m);
+}
+
+int32_t nvb_mapper_synchronize(NvbMapper* m) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(cudaGetLastError());
+  collectStages(m);
+  return checkDeviceError(m);
+}
+
+int32_t nvb_mapper_last_frame_block_count(NvbMapper* m, int32_t* out_count) {
+  if (!m || !out_count) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  return readFrameList(m, nullptr, 0, out_count);
+}
+
+void* nvb_mapper_stream(NvbMapper* m) { return m ? (void*)m->stream : nullptr; }
+
+static DevLayer* layerOf(NvbMapper* m, int layer) {
+  if (layer == NVB_LAYER_TSDF) return &m->tsdf;
+  if (layer == NVB_LAYER_ESDF) return &m->esdf;
+  return nullptr;
+}
+
+int32_t nvb_layer_block_bytes(int32_t layer) {
+  return layer == NVB_LAYER_TSDF ? kTsdfBlockBytes : (layer == NVB_LAYER_ESDF ? kEsdfBlockBytes : 0);
+}
+
+int32_t nvb_layer_num_blocks(NvbMapper* m, int32_t layer, int32_t* out_count) {
+  if (!m || !out_count) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  DevLayer* L = layerOf(m, layer);
+  if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int count = 0;
+  NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
+  *out_count = std::min(count, L->capacity);
+  return NVB_OK;
+}
+
+int32_t nvb_layer_block_indices(NvbMapper* m, int32_t layer, int32_t* out_xyz_host, int32_t cap, int32_t* out_count) {
+  int n = 0;
+  int rc = nvb_layer_num_blocks(m, layer, &n);
+  if (rc) return rc;
+  if (out_count) *out_count = n;
+  DevLayer* L = layerOf(m, layer);
+  const int k = std::min(n, cap);
+  if (out_xyz_host && k > 0)
+    NVB_CUDA(cudaMemcpy(out_xyz_host, L->block_index, (size_t)k * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  return NVB_OK;
+}
+
+int32_t nvb_layer_get_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_host, int32_t n, void* out_host,
+                             uint8_t* found_host) {
+  if (!m || (n > 0 && (!xyz_host || !out_host))) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  DevLayer* L = layerOf(m, layer);
+  if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
+  if (n <= 0) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int* xyz_dev = nullptr;
+  unsigned char *out_dev = nullptr, *found_dev = nullptr;
+  NVB_CUDA(cudaMalloc(&xyz_dev, (size_t)n * 3 * sizeof(int)));
+  NVB_CUDA(cudaMalloc(&out_dev, (size_t)n * L->block_bytes));
+  NVB_CUDA(cudaMalloc(&found_dev, (size_t)n));
+  NVB_CUDA(cudaMemcpy(xyz_dev, xyz_host, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  launchGatherBlocks(*L, xyz_dev, n, out_dev, found_dev, m->stream);
+  m->launches++;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(cudaMemcpy(out_host, out_dev, (size_t)n * L->block_bytes, cudaMemcpyDeviceToHost));
+  if (found_host) NVB_CUDA(cudaMemcpy(found_host, found_dev, (size_t)n, cudaMemcpyDeviceToHost));
+  cudaFree(xyz_dev), cudaFree(out_dev), cudaFree(found_dev);
+  return NVB_OK;
+}
+
+int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_host, int32_t n, const void* in_host) {
+  if (!m || (n > 0 && (!xyz_host || !in_host))) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  DevLayer* L = layerOf(m, layer);
+  if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
+  if (n <= 0) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
+  for (int i = 0; i < n; i++)
+    if (!indexInRange(xyz_host[3 * i], xyz_host[3 * i + 1], xyz_host[3 * i + 2]))
+      return fail(NVB_ERR_INDEX_RANGE, "block index outside +-2^20");
+  int rc;
+  if (layer == NVB_LAYER_TSDF) {
+    if ((rc = ensureTsdfCapacity(m, n))) return rc;
+    m->cells_cum += n;
+    m->tsdf_count_ub += n;
+  } else {
+    m->esdf_extra_ub += n;
+    if ((rc = ensureEsdfCapacity(m, (long long)std::min(m->tsdf_count_ub, m->tsdf.capacity) + m->esdf_extra_ub))) return rc;
+  }
+  L = layerOf(m, layer);
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int* xyz_dev = nullptr;
+  unsigned char* in_dev = nullptr;
+  NVB_CUDA(cudaMalloc(&xyz_dev, (size_t)n * 3 * sizeof(int)));
+  NVB_CUDA(cudaMalloc(&in_dev, (size_t)n * L->block_bytes));
+  NVB_CUDA(cudaMemcpy(xyz_dev, xyz_host, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  NVB_CUDA(cudaMemcpy(in_dev, in_host, (size_t)n * L->block_bytes, cudaMemcpyHostToDevice));
+  launchScatterBlocks(*L, xyz_dev, n, in_dev, m->error_dev, m->stream);
+  m->launches++;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(xyz_dev), cudaFree(in_dev);
+  if (layer == NVB_LAYER_TSDF) {
+    // the tracker is told like after an integration: a later updateEsdf must see these blocks
+    m->tracker_initialized = false;
+  }
+  return checkDeviceError(m);
+}
+
+int32_t nvb_layer_block_device_ptr(NvbMapper* m, int32_t layer, const int32_t xyz[3], void** out_ptr) {
+  if (!m || !xyz || !out_ptr) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  DevLayer* L = layerOf(m, layer);
+  if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  // host-side probe of the device hash (small, synchronous): copy the probe window
+  *out_ptr = nullptr;
+  if (!indexInRange(xyz[0], xyz[1], xyz[2])) return NVB_OK;
+  const unsigned long long key = packIndex(xyz[0], xyz[1], xyz[2]);
+  unsigned int p = hashKey(key) & L->hash.mask;
+  for (unsigned int probes = 0; probes <= L->hash.mask; probes++) {
+    unsigned long long k = 0;
+    NVB_CUDA(cudaMemcpy(&k, L->hash.keys + p, sizeof(k), cudaMemcpyDeviceToHost));
+    if (k == key) {
+      int slot = -1;
+      NVB_CUDA(cudaMemcpy(&slot, L->hash.vals + p, sizeof(int), cudaMemcpyDeviceToHost));
+      if (slot >= 0) *out_ptr = L->blocks + (size_t)slot * L->block_bytes;
+      return NVB_OK;
+    }
+    if (k == kEmptyKey) return NVB_OK;
+    p = (p + 1) & L->hash.mask;
+  }
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_last_esdf_stats(NvbMapper* m, int64_t out[8]) {
+  if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  long long tmp[8];
+  NVB_CUDA(cudaMemcpy(tmp, m->stats, sizeof(tmp), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; i++) out[i] = tmp[i];
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_enable_profiling(NvbMapper* m, int32_t enable) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  collectStages(m);
+  m->profiling = enable != 0;
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_stage_times(NvbMapper* m, double* out_ms, int64_t* out_calls, int32_t reset) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  collectStages(m);
+  for (int i = 0; i < kNumStages; i++) {
+    if (out_ms) out_ms[i] = m->stage_ms[i];
+    if (out_calls) out_calls[i] = m->stage_calls[i];
+    if (reset) m->stage_ms[i] = 0, m->stage_calls[i] = 0;
+  }
+  return NVB_OK;
+}
+
+int64_t nvb_mapper_kernel_launches(const NvbMapper* m) { return m ? m->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,682 @@
+// nvb_esdf.cu -- incremental ESDF update from the TSDF layer.
+//
+// Replaces EsdfIntegrator::integrateBlocks(TsdfLayer, blocks, EsdfLayer*)
+// (nvblox/src/integrators/esdf_integrator.cu:220-266) and its kernels
+// markAllSitesKernel (:467-540), clearAllInvalidKernel (:1522-1585),
+// sweepBlockBandKernel (:1390-1431), getBlockPtr/updateNeighborBandsKernel
+// (:1100-1183) and sortUniqueKernel (:1187-1280).
+//
+// The reference's result depends on the ORDER of its passes (in-block x->y->z
+// sweeps; face propagation +x,-x,+y,-y,+z,-z, each pass seeing the previous
+// ones; repeat until no block changes), so that order is kept. What changes:
+//   * everything is driven from device-side lists and counters: no host hash,
+//     no D2H of counters per ring, no host scan of all block indices;
+//   * blocks move through shared memory with 128-bit coalesced accesses (the
+//     reference walks 20-byte AoS voxels straight in global memory);
+//   * the +dir / -dir passes of one axis are fused per block INTERFACE: the two
+//     operations on an interface only touch that interface's two faces and keep
+//     their relative order inside one thread, so the six passes need three
+//     grid-wide phases instead of six launches;
+//   * the "updated blocks" list of a ring is built unique with a per-slot stamp
+//     (atomicExch), which replaces the sort + unique launch;
+//   * the whole wavefront (both computeEsdf calls) runs in ONE cooperative
+//     persistent launch with a grid barrier between phases.
+#include <cooperative_groups.h>
+
+#include "nvb_internal.cuh"
+
+namespace nvb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kGroups = kThreads / 64;  // 64-thread groups, one ESDF block each
+constexpr int kBlockWords = kEsdfBlockBytes / 4;  // 2560
+
+__device__ __forceinline__ unsigned int* esdfBlockPtr(const DevLayer& L, int slot) {
+  return reinterpret_cast<unsigned int*>(L.blocks + (size_t)slot * kEsdfBlockBytes);
+}
+
+// EsdfVoxel words: [0] squared_distance_vox, [1..3] parent_direction, [4] flags
+// (byte0 is_inside, byte1 observed, byte2 is_site) -- map/voxels.h:55-74.
+__device__ __forceinline__ bool flagInside(unsigned int f) { return (f & 0xffu) != 0; }
+__device__ __forceinline__ bool flagObserved(unsigned int f) { return (f & 0xff00u) != 0; }
+__device__ __forceinline__ bool flagSite(unsigned int f) { return (f & 0xff0000u) != 0; }
+
+// ---------------------------------------------------------------------------
+// Allocation of the ESDF blocks + per-update counter reset
+// (EsdfIntegrator::allocateBlocksOnCPU, esdf_integrator.cu:391-397).
+// ---------------------------------------------------------------------------
+__global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
+                                   int in_count_host) {
+  const int n = in_count_dev ? *in_count_dev : in_count_host;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    *c.work_count = n;
+    *c.upd_count = 0;
+    *c.clr_count = 0;
+    c.clr_aabb[0] = c.clr_aabb[1] = c.clr_aabb[2] = INT32_MAX;
+    c.clr_aabb[3] = c.clr_aabb[4] = c.clr_aabb[5] = INT32_MIN;
+    c.ring_count[0] = c.ring_count[1] = 0;
+    c.ring_count[2] = 0;  // mark-kernel "CTAs done" counter
+    *c.barrier = 0;
+    for (int k = 0; k < 8; k++) c.stats[k] = 0;
+    c.stats[0] = n;
+  }
+  if (i >= n) return;
+  int x, y, z, tslot;
+  if (in_slots) {
+    tslot = in_slots[i];
+    x = c.tsdf.block_index[3 * tslot], y = c.tsdf.block_index[3 * tslot + 1], z = c.tsdf.block_index[3 * tslot + 2];
+  } else {
+    x = in_xyz[3 * i], y = in_xyz[3 * i + 1], z = in_xyz[3 * i + 2];
+    tslot = hashFind(c.tsdf.hash, x, y, z);
+  }
+  bool was_new;
+  const int eslot = hashFindOrInsert(c.esdf, x, y, z, c.error, &was_new);
+  c.work[i] = make_int2(eslot, tslot);
+}
+
+// ---------------------------------------------------------------------------
+// markAllSitesKernel + updateEsdfVoxelToChanges with TsdfSiteFunctor
+// (esdf_integrator.cu:113-138, 401-540).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
+  __shared__ __align__(16) unsigned int s[kBlockWords];
+  __shared__ int s_flags[3];  // updated, cleared, changed
+  const int tid = threadIdx.x;
+  const int n = *c.work_count;
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    const int2 w = c.work[item];
+    if (w.x < 0 || w.y < 0) continue;  // block_ptr == nullptr || esdf_block == nullptr (:513-517)
+    if (tid < 3) s_flags[tid] = 0;
+    uint4* gblk = reinterpret_cast<uint4*>(esdfBlockPtr(c.esdf, w.x));
+    for (int k = tid; k < kBlockWords / 4; k += kThreads) reinterpret_cast<uint4*>(s)[k] = gblk[k];
+    const float2* tsdf = reinterpret_cast<const float2*>(c.tsdf.blocks + (size_t)w.y * kTsdfBlockBytes);
+    const float2 t0 = tsdf[tid], t1 = tsdf[tid + kThreads];
+    __syncthreads();
+    bool updated = false, cleared = false, changed = false;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float2 t = h ? t1 : t0;
+      unsigned int* e = s + (tid + h * kThreads) * kEsdfVoxelWords;
+      float sq = __uint_as_float(e[0]);
+      int p0 = (int)e[1], p1 = (int)e[2], p2 = (int)e[3];
+      const unsigned int fl = e[4];
+      bool e_inside = flagInside(fl), e_observed = flagObserved(fl), e_site = flagSite(fl);
+      const bool is_observed = t.y >= c.min_weight;
+      if (is_observed) {
+        const bool is_inside = t.x <= 0.0f;
+        const bool is_site = is_inside && (fabsf(t.x) <= c.max_site_distance_m);
+        if (e_inside && !is_inside) {
+          p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+          cleared = true;
+        }
+        e_inside = is_inside;
+        if (is_site) {
+          if (!e_site) {
+            e_site = true, sq = 0.0f, p0 = p1 = p2 = 0;
+          }
+          updated = true;
+        } else {
+          if (e_site) {
+            p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+            cleared = true;
+          } else if (!e_observed) {
+            p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+          } else if ((double)sq <= 1e-4) {
+            p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+            cleared = true;
+          }
+        }
+        e_observed = true;
+      } else {
+        p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+        cleared = true;
+        e_observed = false;
+      }
+      const unsigned int nfl = (fl & 0xff000000u) | (e_inside ? 1u : 0u) | (e_observed ? 0x100u : 0u) |
+                               (e_site ? 0x10000u : 0u);
+      const unsigned int nsq = __float_as_uint(sq);
+      if (nsq != e[0] || (unsigned)p0 != e[1] || (unsigned)p1 != e[2] || (unsigned)p2 != e[3] || nfl != fl) {
+        e[0] = nsq, e[1] = (unsigned)p0, e[2] = (unsigned)p1, e[3] = (unsigned)p2, e[4] = nfl;
+        changed = true;
+      }
+    }
+    if (updated) s_flags[0] = 1;
+    if (cleared) s_flags[1] = 1;
+    if (changed) s_flags[2] = 1;
+    __syncthreads();
+    if (s_flags[2]) {
+      for (int k = tid; k < kBlockWords / 4; k += kThreads) gblk[k] = reinterpret_cast<uint4*>(s)[k];
+    }
+    if (tid == 0) {
+      if (s_flags[0]) c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
+      if (s_flags[1]) {
+        c.clr_list[atomicAdd(c.clr_count, 1)] = w.x;
+        const int* bi = c.esdf.block_index + 3 * w.x;
+        atomicMin(c.clr_aabb + 0, bi[0]), atomicMin(c.clr_aabb + 1, bi[1]), atomicMin(c.clr_aabb + 2, bi[2]);
+        atomicMax(c.clr_aabb + 3, bi[0]), atomicMax(c.clr_aabb + 4, bi[1]), atomicMax(c.clr_aabb + 5, bi[2]);
+      }
+    }
+    __syncthreads();
+  }
+  // Last CTA out: if this update has blocks to clear, the persistent "cleared"
+  // list is about to be rewritten (clearAllInvalid resizes it, :1620); otherwise it
+  // keeps the previous call's content (:242-257).
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      const int nclr = *(volatile int*)c.clr_count;
+      const int nupd = *(volatile int*)c.upd_count;
+      if (nclr > 0) *c.cleared_count = 0;
+      c.stats[1] = nupd, c.stats[2] = nclr;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// clearAllInvalid (:1587-1647): candidate = every ESDF block whose box is within
+// max_esdf_distance of the AABB of the to-clear blocks
+// (geometry/bounding_spheres.cpp:76-91, bounding_boxes.cpp:20-27);
+// clearAllInvalidKernel (:1522-1585) per candidate.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
+  __shared__ __align__(16) unsigned int s[kBlockWords];
+  __shared__ int s_any;
+  const int nclr = *c.clr_count;
+  if (nclr == 0) return;
+  const int tid = threadIdx.x;
+  const int nblocks = *c.esdf.count < c.esdf.capacity ? *c.esdf.count : c.esdf.capacity;
+  const float bs = c.block_size;
+  float amin[3], amax[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    amin[a] = (float)c.clr_aabb[a] * bs;
+    amax[a] = ((float)c.clr_aabb[3 + a] + 1.0f) * bs;
+  }
+  for (int slot = blockIdx.x; slot < nblocks; slot += gridDim.x) {
+    const int bx = c.esdf.block_index[3 * slot], by = c.esdf.block_index[3 * slot + 1],
+              bz = c.esdf.block_index[3 * slot + 2];
+    const int bi[3] = {bx, by, bz};
+    // AlignedBox::exteriorDistance(box) > radius -> skip
+    float d2 = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float lo = (float)bi[a] * bs, hi = ((float)bi[a] + 1.0f) * bs;
+      if (amin[a] > hi) {
+        const float aux = amin[a] - hi;
+        d2 += aux * aux;
+      } else if (lo > amax[a]) {
+        const float aux = lo - amax[a];
+        d2 += aux * aux;
+      }
+    }
+    if (sqrtf(d2) > c.max_esdf_distance_m) continue;
+    if (tid == 0) {
+      s_any = 0;
+      atomicAdd((unsigned long long*)&c.stats[3], 1ull);
+    }
+    unsigned int* gw = esdfBlockPtr(c.esdf, slot);
+    const uint4* gblk = reinterpret_cast<const uint4*>(gw);
+    for (int k = tid; k < kBlockWords / 4; k += kThreads) reinterpret_cast<uint4*>(s)[k] = gblk[k];
+    __syncthreads();
+    bool any = false;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int v = tid + h * kThreads;
+      const unsigned int* e = s + v * kEsdfVoxelWords;
+      const unsigned int fl = e[4];
+      const int p[3] = {(int)e[1], (int)e[2], (int)e[3]};
+      if (flagObserved(fl) && !flagSite(fl) && (p[0] != 0 || p[1] != 0 || p[2] != 0)) {
+        // getBlockAndVoxelIndexFromOffset (:1498-1520): C++ '/' and '%' truncate toward zero.
+        const int vi[3] = {v >> 6, (v >> 3) & 7, v & 7};
+        int nb[3], nv[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          nb[a] = bi[a] + p[a] / kVps;
+          nv[a] = vi[a] + p[a] % kVps;
+          if (nv[a] >= kVps) {
+            nv[a] -= kVps;
+            nb[a]++;
+          } else if (nv[a] < 0) {
+            nv[a] += kVps;
+            nb[a]--;
+          }
+        }
+        const int pv = (nv[0] * kVps + nv[1]) * kVps + nv[2];
+        bool parent_is_site = false;
+        if (nb[0] == bx && nb[1] == by && nb[2] == bz) {
+          parent_is_site = flagSite(s[pv * kEsdfVoxelWords + 4]);
+        } else {
+          const int ps = hashFind(c.esdf.hash, nb[0], nb[1], nb[2]);
+          // is_site is never written by this kernel: reading it from a block another
+          // CTA is processing is race-free.
+          if (ps >= 0) parent_is_site = flagSite(esdfBlockPtr(c.esdf, ps)[pv * kEsdfVoxelWords + 4]);
+        }
+        if (!parent_is_site) {
+          unsigned int* g = gw + v * kEsdfVoxelWords;
+          g[0] = __float_as_uint(c.max_sq), g[1] = 0u, g[2] = 0u, g[3] = 0u;
+          any = true;
+        }
+      }
+    }
+    if (any) s_any = 1;
+    __syncthreads();
+    if (tid == 0 && s_any) c.cleared_list[atomicAdd(c.cleared_count, 1)] = slot;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Phases of computeEsdf (:1465-1496), written as device functions over
+// (cta, num_ctas) so the persistent kernel and the per-phase kernels share them.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ void loadBlockGroup(unsigned int* sm, const unsigned int* g, int lane64) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(sm);
+#pragma unroll
+  for (int k = 0; k < kBlockWords / 4 / 64; k++) dst[lane64 + k * 64] = __ldcg(src + lane64 + k * 64);
+}
+__device__ __forceinline__ void storeBlockGroup(unsigned int* g, const unsigned int* sm, int lane64) {
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  const uint4* src = reinterpret_cast<const uint4*>(sm);
+#pragma unroll
+  for (int k = 0; k < kBlockWords / 4 / 64; k++) __stcg(dst + lane64 + k * 64, src[lane64 + k * 64]);
+}
+
+// sweepSingleBand (:542-600): forward then backward along one line of 8 voxels.
+__device__ __forceinline__ bool sweepLine(unsigned int* s, int c0, int c1, int c2, int axis, float max_sq) {
+  const int stride = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
+  const int basev = c0 * 64 + c1 * 8 + c2;  // coordinate along `axis` is 0 on entry
+  bool changed = false;
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    int l0 = 0, l1 = 0, l2 = 0;
+    bool found = false;
+#pragma unroll
+    for (int k = 0; k < kVps; k++) {
+      const int cc = pass ? (kVps - 1 - k) : k;
+      unsigned int* e = s + (basev + cc * stride) * kEsdfVoxelWords;
+      const unsigned int fl = e[4];
+      if (!flagObserved(fl)) continue;
+      const int v0 = (axis == 0) ? cc : c0, v1 = (axis == 1) ? cc : c1, v2 = (axis == 2) ? cc : c2;
+      if (flagSite(fl)) {
+        l0 = v0, l1 = v1, l2 = v2;
+        found = true;
+      } else if (!found) {
+        if (__uint_as_float(e[0]) < max_sq) {
+          found = true;
+          l0 = (int)e[1] + v0, l1 = (int)e[2] + v1, l2 = (int)e[3] + v2;
+        }
+      } else {
+        const int d0 = l0 - v0, d1 = l1 - v1, d2 = l2 - v2;
+        const float pdist = (float)(d0 * d0 + (d1 * d1 + d2 * d2));
+        const float sq = __uint_as_float(e[0]);
+        if (sq > pdist) {
+          e[1] = (unsigned)d0, e[2] = (unsigned)d1, e[3] = (unsigned)d2;
+          e[0] = __float_as_uint(pdist);
+          changed = true;
+        } else if (sq < max_sq) {
+          l0 = (int)e[1] + v0, l1 = (int)e[2] + v1, l2 = (int)e[3] + v2;
+        }
+      }
+    }
+  }
+  return changed;
+}
+
+// sweepBlockBandKernel (:1390-1431) for up to kGroups blocks per CTA iteration.
+// If `src` is non-null this is the initial sweep of a computeEsdf call: the source
+// list is also copied into `list` and stamped as the members of ring `ring`.
+__device__ void phaseSweep(const EsdfCtx& c, const int* src, int* list, int n, int* stamp, int ring,
+                           unsigned int* smem, int* s_changed, int cta, int nctas) {
+  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
+  unsigned int* sm = smem + group * kBlockWords;
+  const int a = lane64 >> 3, b = lane64 & 7;
+  for (int base = cta * kGroups; base < n; base += nctas * kGroups) {
+    const int item = base + group;
+    int slot = -1;
+    if (item < n) {
+      slot = src ? __ldcg(src + item) : __ldcg(list + item);
+      if (src && lane64 == 0) {
+        list[item] = slot;
+        stamp[slot] = ring;
+      }
+    }
+    if (lane64 == 0) s_changed[group] = 0;
+    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
+    __syncthreads();
+    bool ch = false;
+    if (slot >= 0) ch |= sweepLine(sm, 0, a, b, 0, c.max_sq);
+    __syncthreads();
+    if (slot >= 0) ch |= sweepLine(sm, a, 0, b, 1, c.max_sq);
+    __syncthreads();
+    if (slot >= 0) ch |= sweepLine(sm, a, b, 0, 2, c.max_sq);
+    if (ch) s_changed[group] = 1;
+    __syncthreads();
+    if (slot >= 0 && s_changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
+    __syncthreads();
+  }
+}
+
+struct VoxelRegs {
+  float sq;
+  int p0, p1, p2;
+  unsigned int fl;
+};
+__device__ __forceinline__ VoxelRegs loadVoxel(const unsigned int* g) {
+  VoxelRegs v;
+  v.sq = __uint_as_float(__ldcg(g + 0));
+  v.p0 = (int)__ldcg(g + 1), v.p1 = (int)__ldcg(g + 2), v.p2 = (int)__ldcg(g + 3);
+  v.fl = __ldcg(g + 4);
+  return v;
+}
+// updateSingleNeighbor (:602-633): src -> dst across a face; `direction` is the
+// block direction from src to dst along `axis`.
+__device__ __forceinline__ bool updateSingleNeighbor(const VoxelRegs& e, VoxelRegs& nb, unsigned int* g_nb, int axis,
+                                                     int direction, float max_sq) {
+  if (!flagObserved(e.fl) || !flagObserved(nb.fl) || flagSite(nb.fl) || e.sq >= max_sq) return false;
+  int d0 = e.p0, d1 = e.p1, d2 = e.p2;
+  if (axis == 0) d0 -= direction;
+  else if (axis == 1) d1 -= direction;
+  else d2 -= direction;
+  const float pdist = (float)(d0 * d0 + (d1 * d1 + d2 * d2));
+  if (nb.sq > pdist) {
+    nb.p0 = d0, nb.p1 = d1, nb.p2 = d2, nb.sq = pdist;
+    __stcg(g_nb + 1, (unsigned)d0), __stcg(g_nb + 2, (unsigned)d1), __stcg(g_nb + 3, (unsigned)d2);
+    __stcg(g_nb + 0, __float_as_uint(pdist));
+    return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void appendUnique(int slot, int* nxt, int* nxt_count, int* stamp_nxt, int ring_next) {
+  if (atomicExch(stamp_nxt + slot, ring_next) != ring_next) nxt[atomicAdd(nxt_count, 1)] = slot;
+}
+
+// The two passes of one axis of updateNeighborBands (:1323-1386,
+// getDirectionAndVoxelIndicesFromThread :1062-1091), fused per interface.
+// For a list member b:
+//   group "hi": interface (b, b+d): P = b -> b+d (pass +dir); then, if b+d is a
+//               list member too, Q = b+d -> b (pass -dir).
+//   group "lo": interface (b-d, b), only when b-d is NOT a list member (otherwise
+//               b-d's "hi" group owns it): Q = b -> b-d.
+// P precedes Q on every interface, different interfaces touch disjoint faces, so
+// this equals running pass +dir over the whole list and then pass -dir.
+__device__ void phaseNeighbors(const EsdfCtx& c, int axis, const int* cur, int n, const int* stamp_cur, int ring,
+                               int* nxt, int* nxt_count, int* stamp_nxt, int* s_slot, int* s_upd, int cta,
+                               int nctas) {
+  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
+  const int entry_in_cta = group >> 1, side = group & 1;  // side 0 = hi, 1 = lo
+  const int u = lane64 >> 3, w = lane64 & 7;
+  // voxel offset of this thread's face voxel at coordinate `cc` along `axis`
+  const int strideA = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
+  const int faceBase = (axis == 0) ? (u * 8 + w) : ((axis == 1) ? (u * 64 + w) : (u * 64 + w * 8));
+  const int vHi = faceBase + (kVps - 1) * strideA, vLo = faceBase;
+  for (int base = cta * (kGroups / 2); base < n; base += nctas * (kGroups / 2)) {
+    const int item = base + entry_in_cta;
+    if (lane64 == 0) {
+      int other = -1;
+      int mine = -1;
+      if (item < n) {
+        mine = __ldcg(cur + item);
+        const int* bi = c.esdf.block_index + 3 * mine;
+        int x = bi[0], y = bi[1], z = bi[2];
+        const int d = side ? -1 : 1;
+        if (axis == 0) x += d;
+        else if (axis == 1) y += d;
+        else z += d;
+        other = hashFind(c.esdf.hash, x, y, z);
+      }
+      s_slot[group * 2] = mine;
+      s_slot[group * 2 + 1] = other;
+      s_upd[group * 2] = 0;
+      s_upd[group * 2 + 1] = 0;
+    }
+    __syncthreads();
+    const int mine = s_slot[group * 2], other = s_slot[group * 2 + 1];
+    if (mine >= 0 && other >= 0) {
+      const bool other_member = (__ldcg(stamp_cur + other) == ring);
+      if (side == 0) {
+        // interface (A = mine, B = other = mine + d)
+        unsigned int* gA = esdfBlockPtr(c.esdf, mine) + vHi * kEsdfVoxelWords;
+        unsigned int* gB = esdfBlockPtr(c.esdf, other) + vLo * kEsdfVoxelWords;
+        VoxelRegs A = loadVoxel(gA), B = loadVoxel(gB);
+        if (updateSingleNeighbor(A, B, gB, axis, +1, c.max_sq)) s_upd[group * 2 + 1] = 1;  // B updated
+        if (other_member) {
+          if (updateSingleNeighbor(B, A, gA, axis, -1, c.max_sq)) s_upd[group * 2] = 1;  // A updated
+        }
+      } else if (!other_member) {
+        // interface (A = other = mine - d, B = mine): only Q = B -> A
+        unsigned int* gA = esdfBlockPtr(c.esdf, other) + vHi * kEsdfVoxelWords;
+        unsigned int* gB = esdfBlockPtr(c.esdf, mine) + vLo * kEsdfVoxelWords;
+        VoxelRegs A = loadVoxel(gA), B = loadVoxel(gB);
+        if (updateSingleNeighbor(B, A, gA, axis, -1, c.max_sq)) s_upd[group * 2 + 1] = 1;  // A (= other) updated
+      }
+    }
+    __syncthreads();
+    if (lane64 == 0 && mine >= 0 && other >= 0) {
+      if (s_upd[group * 2]) appendUnique(mine, nxt, nxt_count, stamp_nxt, ring + 1);
+      if (s_upd[group * 2 + 1]) appendUnique(other, nxt, nxt_count, stamp_nxt, ring + 1);
+    }
+    __syncthreads();
+  }
+}
+
+// Grid-wide barrier for the cooperative launch: monotonically increasing arrival
+// counter in L2 (reset by esdfAllocateKernel before every update).
+__device__ __forceinline__ void gridBarrier(unsigned int* bar, unsigned int& generation, unsigned int nctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    generation++;
+    const unsigned int target = generation * nctas;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*(volatile unsigned int*)bar < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct RingBufs {
+  int* list[2];
+  int* stamp[2];
+};
+
+// computeEsdf (:1465-1496) twice -- updated blocks, then the persistent cleared
+// list (:254-257) -- in one cooperative launch.
+__global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx c) {
+  extern __shared__ __align__(16) unsigned int smem[];
+  __shared__ int s_changed[kGroups];
+  __shared__ int s_slot[kGroups * 2];
+  __shared__ int s_upd[kGroups * 2];
+  const int cta = blockIdx.x, nctas = gridDim.x;
+  // Empty block list: integrateBlocksTemplate returns before touching anything (:226-228).
+  if (*(volatile int*)c.work_count == 0) return;
+  unsigned int generation = 0;
+  int ring = *(volatile int*)c.ring_id;
+  long long swept = 0, faces = 0, rings = 0;
+  RingBufs rb;
+  rb.list[0] = c.ring_a, rb.list[1] = c.ring_b;
+  rb.stamp[0] = c.stamp_a, rb.stamp[1] = c.stamp_b;
+  for (int pass = 0; pass < 2; pass++) {
+    const int* src = pass ? c.cleared_list : c.upd_list;
+    int n = pass ? *(volatile int*)c.cleared_count : *(volatile int*)c.upd_count;
+    if (n == 0) continue;
+    int ci = ring & 1;
+    // Initial sweep of the source list; members of ring `ring` get stamped.
+    phaseSweep(c, src, rb.list[ci], n, rb.stamp[ci], ring, smem, s_changed, cta, nctas);
+    if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
+    swept += n;
+    gridBarrier(c.barrier, generation, nctas);
+    while (n > 0) {
+      const int ni = ci ^ 1;
+      for (int axis = 0; axis < 3; axis++) {
+        phaseNeighbors(c, axis, rb.list[ci], n, rb.stamp[ci], ring, rb.list[ni], c.ring_count + ni, rb.stamp[ni],
+                       s_slot, s_upd, cta, nctas);
+        gridBarrier(c.barrier, generation, nctas);
+      }
+      faces += 6ll * n;
+      const int n_next = *(volatile int*)(c.ring_count + ni);
+      phaseSweep(c, nullptr, rb.list[ni], n_next, nullptr, 0, smem, s_changed, cta, nctas);
+      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the next ring's append counter
+      swept += n_next;
+      rings++;
+      gridBarrier(c.barrier, generation, nctas);
+      ring++;
+      ci = ni;
+      n = n_next;
+    }
+    ring++;
+  }
+  if (cta == 0 && threadIdx.x == 0) {
+    *c.ring_id = ring + 1;
+    c.stats[4] = *(volatile int*)c.cleared_count;
+    c.stats[5] = swept, c.stats[6] = faces, c.stats[7] = rings;
+  }
+}
+
+// Per-phase kernels for the host-driven loop (reference-like orchestration).
+__global__ void __launch_bounds__(kThreads) esdfSweepKernel(EsdfCtx c, const int* src, int* list, const int* n_dev,
+                                                            int* stamp, int ring) {
+  extern __shared__ __align__(16) unsigned int smem[];
+  __shared__ int s_changed[kGroups];
+  phaseSweep(c, src, list, *n_dev, stamp, ring, smem, s_changed, blockIdx.x, gridDim.x);
+}
+__global__ void __launch_bounds__(kThreads) esdfNeighborKernel(EsdfCtx c, int axis, const int* cur, const int* n_dev,
+                                                               const int* stamp_cur, int ring, int* nxt,
+                                                               int* nxt_count, int* stamp_nxt) {
+  __shared__ int s_slot[kGroups * 2];
+  __shared__ int s_upd[kGroups * 2];
+  phaseNeighbors(c, axis, cur, *n_dev, stamp_cur, ring, nxt, nxt_count, stamp_nxt, s_slot, s_upd, blockIdx.x,
+                 gridDim.x);
+}
+__global__ void esdfSetIntKernel(int* p, int v) { *p = v; }
+
+constexpr size_t kSweepSmemBytes = (size_t)kGroups * kEsdfBlockBytes;  // 40 KiB
+
+}  // namespace
+
+void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
+                        int in_count_upper, cudaStream_t stream) {
+  const int threads = 256;
+  const int blocks = (in_count_upper + threads - 1) / threads;
+  esdfAllocateKernel<<<blocks < 1 ? 1 : blocks, threads, 0, stream>>>(c, in_xyz, in_slots, in_count_dev,
+                                                                       in_count_upper);
+}
+
+void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream) {
+  int grid = num_sms * 4;
+  if (count_upper < grid) grid = count_upper;
+  if (grid < 1) grid = 1;
+  esdfMarkKernel<<<grid, kThreads, 0, stream>>>(c);
+}
+
+void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream) {
+  int grid = num_sms * 4;
+  if (esdf_count_upper < grid) grid = esdf_count_upper;
+  if (grid < 1) grid = 1;
+  esdfClearKernel<<<grid, kThreads, 0, stream>>>(c);
+}
+
+int esdfPersistentMaxCtas(int num_sms) {
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    cudaFuncSetAttribute(esdfComputePersistentKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kSweepSmemBytes);
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, esdfComputePersistentKernel, kThreads,
+                                                      kSweepSmemBytes) != cudaSuccess)
+      v = 0;
+    per_sm = v;
+  }
+  return per_sm * num_sms;
+}
+
+cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches) {
+  const int max_ctas = esdfPersistentMaxCtas(num_sms);
+  if (max_ctas <= 0) return cudaErrorLaunchOutOfResources;
+  // One CTA per SM: the wavefront is latency-bound, more CTAs only make the barrier slower.
+  int grid = num_sms < max_ctas ? num_sms : max_ctas;
+  EsdfCtx cc = c;
+  void* args[] = {&cc};
+  (*launches)++;
+  return cudaLaunchCooperativeKernel((const void*)esdfComputePersistentKernel, dim3(grid), dim3(kThreads), args,
+                                     kSweepSmemBytes, stream);
+}
+
+// One launch per phase; the host reads the ring's block count after every ring,
+// like the reference does (sortAndTakeUniqueIndices, :1296-1297).
+cudaError_t runEsdfComputeHostLoop(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(esdfSweepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmemBytes);
+    attr_set = true;
+  }
+  int h_ring = 0, h_counts[2] = {0, 0}, h_work = 0;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(&h_ring, c.ring_id, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(&h_work, c.work_count, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+  if (h_work == 0) return cudaSuccess;  // empty block list: nothing to do (:226-228)
+  int ring = h_ring;
+  int* lists[2] = {c.ring_a, c.ring_b};
+  int* stamps[2] = {c.stamp_a, c.stamp_b};
+  long long swept = 0, faces = 0, rings = 0;
+  const int grid = num_sms * 2;
+  for (int pass = 0; pass < 2; pass++) {
+    const int* src = pass ? c.cleared_list : c.upd_list;
+    const int* src_count = pass ? c.cleared_count : c.upd_count;
+    int n = 0;
+    if ((e = cudaMemcpyAsync(&n, src_count, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    if (n == 0) continue;
+    int ci = ring & 1;
+    esdfSweepKernel<<<grid, kThreads, kSweepSmemBytes, stream>>>(c, src, lists[ci], src_count, stamps[ci], ring);
+    esdfSetIntKernel<<<1, 1, 0, stream>>>(c.ring_count + ci, n);
+    esdfSetIntKernel<<<1, 1, 0, stream>>>(c.ring_count + (ci ^ 1), 0);
+    (*launches) += 3;
+    swept += n;
+    while (n > 0) {
+      const int ni = ci ^ 1;
+      for (int axis = 0; axis < 3; axis++) {
+        esdfNeighborKernel<<<grid, kThreads, 0, stream>>>(c, axis, lists[ci], c.ring_count + ci, stamps[ci], ring,
+                                                          lists[ni], c.ring_count + ni, stamps[ni]);
+      }
+      esdfSweepKernel<<<grid, kThreads, kSweepSmemBytes, stream>>>(c, nullptr, lists[ni], c.ring_count + ni, nullptr,
+                                                                   0);
+      (*launches) += 4;
+      faces += 6ll * n;
+      if ((e = cudaMemcpyAsync(h_counts, c.ring_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream)) !=
+          cudaSuccess)
+        return e;
+      if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+      const int n_next = h_counts[ni];
+      esdfSetIntKernel<<<1, 1, 0, stream>>>(c.ring_count + ci, 0);
+      (*launches)++;
+      swept += n_next;
+      rings++;
+      ring++;
+      ci = ni;
+      n = n_next;
+    }
+    ring++;
+  }
+  ring++;
+  long long h_stats[3] = {swept, faces, rings};
+  int h_cleared = 0;
+  if ((e = cudaMemcpyAsync(&h_cleared, c.cleared_count, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+    return e;
+  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+  long long h_cl = h_cleared;
+  cudaMemcpyAsync(c.stats + 4, &h_cl, sizeof(long long), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(c.stats + 5, h_stats, 3 * sizeof(long long), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(c.ring_id, &ring, sizeof(int), cudaMemcpyHostToDevice, stream);
+  return cudaStreamSynchronize(stream);
+}
+
+}  // namespace nvb

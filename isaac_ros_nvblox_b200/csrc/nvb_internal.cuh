@@ -1,0 +1,271 @@
+// nvb_internal.cuh -- shared declarations of the B200-native depth-integration core.
+//
+// Everything in csrc/ is compiled for sm_100a with -fmad=false: one IEEE
+// rounding per floating-point operation, so that block-index sets are
+// reproducible bit-for-bit and do not depend on the compiler's contraction
+// choices (the reference's nvcc build contracts at the compiler's discretion,
+// nvblox_core/cmake/nvblox_targets.cmake:120-171 -- see DESIGN.md "Numerics").
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nvblox_b200.h"
+
+namespace nvb {
+
+constexpr int kVps = 8;                 // VoxelBlock::kVoxelsPerSide (map/blox.h:36)
+constexpr int kVpb = kVps * kVps * kVps;
+constexpr int kTsdfBlockBytes = kVpb * 8;   // 4096
+constexpr int kEsdfBlockBytes = kVpb * 20;  // 10240
+constexpr int kEsdfVoxelWords = 5;
+
+struct Vec3 {
+  float x, y, z;
+};
+
+// Rigid transform handed to kernels by value (12 floats; Eigen Isometry3f without
+// the constant bottom row).
+struct Rigid {
+  float r[3][3];
+  float t[3];
+};
+
+// ---------------------------------------------------------------------------
+// Arithmetic with the evaluation order of the reference's Eigen expressions.
+// ---------------------------------------------------------------------------
+
+// Fixed-size-3 reductions in Eigen evaluate a0 + (a1 + a2).
+__host__ __device__ __forceinline__ float sum3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
+
+// Isometry3f * Vector3f : translation + linear * p.
+__host__ __device__ __forceinline__ Vec3 transformPoint(const Rigid& T, const Vec3& p) {
+  Vec3 o;
+  o.x = T.t[0] + sum3(T.r[0][0] * p.x, T.r[0][1] * p.y, T.r[0][2] * p.z);
+  o.y = T.t[1] + sum3(T.r[1][0] * p.x, T.r[1][1] * p.y, T.r[1][2] * p.z);
+  o.z = T.t[2] + sum3(T.r[2][0] * p.x, T.r[2][1] * p.y, T.r[2][2] * p.z);
+  return o;
+}
+
+// float -> int with device semantics on both host and device (NaN -> 0, saturating).
+__host__ __device__ __forceinline__ int floatToIntRz(float f) {
+#ifdef __CUDA_ARCH__
+  return __float2int_rz(f);
+#else
+  if (f != f) return 0;
+  if (f >= 2147483648.0f) return INT32_MAX;
+  if (f <= -2147483648.0f) return INT32_MIN;
+  return (int)f;
+#endif
+}
+
+// getBlockIndexFromPositionInLayer (core/internal/impl/indexing_impl.h:31-35).
+__host__ __device__ __forceinline__ int3 blockIndexFromPosition(float block_size, const Vec3& p) {
+  return make_int3(floatToIntRz(floorf(p.x / block_size)), floatToIntRz(floorf(p.y / block_size)),
+                   floatToIntRz(floorf(p.z / block_size)));
+}
+
+// ---------------------------------------------------------------------------
+// Device-resident block hash: packed Index3D -> slot in the layer's slab.
+// Open addressing, linear probing, 64-bit keys (3 x 21 bit, biased).
+// Replaces the host unordered_map + stdgpu mirror of the reference
+// (map/layer.h:48-217, gpu_hash/gpu_layer_view.h:48-141).
+// ---------------------------------------------------------------------------
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kIndexBias = 1 << 20;
+
+__host__ __device__ __forceinline__ bool indexInRange(int x, int y, int z) {
+  return x >= -kIndexBias && x < kIndexBias && y >= -kIndexBias && y < kIndexBias && z >= -kIndexBias &&
+         z < kIndexBias;
+}
+
+__host__ __device__ __forceinline__ unsigned long long packIndex(int x, int y, int z) {
+  return ((unsigned long long)(unsigned)(x + kIndexBias) << 42) |
+         ((unsigned long long)(unsigned)(y + kIndexBias) << 21) | (unsigned long long)(unsigned)(z + kIndexBias);
+}
+
+__host__ __device__ __forceinline__ unsigned int hashKey(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (unsigned int)k;
+}
+
+struct DevHash {
+  unsigned long long* keys;
+  int* vals;
+  unsigned int mask;  // capacity - 1 (capacity is a power of two)
+};
+
+// One layer = one contiguous slab of fixed-size blocks + the hash + the reverse map.
+struct DevLayer {
+  unsigned char* blocks;  // capacity * block_bytes, zero-initialised
+  int* block_index;       // 3 ints per slot (Index3D of the block living in that slot)
+  int* count;             // device counter: slots handed out so far
+  int capacity;
+  int block_bytes;
+  DevHash hash;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int hashFind(const DevHash& h, int x, int y, int z) {
+  if (!indexInRange(x, y, z)) return -1;
+  const unsigned long long key = packIndex(x, y, z);
+  unsigned int p = hashKey(key) & h.mask;
+  while (true) {
+    const unsigned long long k = h.keys[p];
+    if (k == key) return h.vals[p];
+    if (k == kEmptyKey) return -1;
+    p = (p + 1) & h.mask;
+  }
+}
+
+// Find-or-insert. Keys inserted by one kernel launch must be unique within that
+// launch (callers guarantee it), so a key that is already present was inserted
+// by an earlier launch and its value is visible. Returns the slot, or -1 when
+// the slab is exhausted / the index does not fit (flagged in *error).
+__device__ __forceinline__ int hashFindOrInsert(const DevLayer& L, int x, int y, int z, int* error, bool* was_new) {
+  *was_new = false;
+  if (!indexInRange(x, y, z)) {
+    atomicOr(error, 2);
+    return -1;
+  }
+  const unsigned long long key = packIndex(x, y, z);
+  unsigned int p = hashKey(key) & L.hash.mask;
+  while (true) {
+    const unsigned long long k = L.hash.keys[p];
+    if (k == key) return L.hash.vals[p];
+    if (k == kEmptyKey) {
+      const unsigned long long old = atomicCAS(&L.hash.keys[p], kEmptyKey, key);
+      if (old == kEmptyKey) {
+        const int slot = atomicAdd(L.count, 1);
+        if (slot >= L.capacity) {
+          atomicOr(error, 1);
+          L.hash.vals[p] = -1;
+          return -1;
+        }
+        L.hash.vals[p] = slot;
+        L.block_index[3 * slot + 0] = x;
+        L.block_index[3 * slot + 1] = y;
+        L.block_index[3 * slot + 2] = z;
+        *was_new = true;
+        return slot;
+      }
+      if (old == key) return L.hash.vals[p];
+    }
+    p = (p + 1) & L.hash.mask;
+  }
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------
+// Per-frame view description computed on the host (ViewCalculator setup,
+// view_calculator_impl.cuh:137-156).
+// ---------------------------------------------------------------------------
+struct ViewGrid {
+  int3 min_index;
+  int3 size;
+  int linear_size;  // size.x * size.y * size.z
+  int num_words;    // bitset words
+};
+
+struct TsdfKernelParams {
+  float block_size;
+  float voxel_size;       // block_size * (1/8)
+  float half_voxel_size;  // block_size * (0.5/8)
+  float truncation_distance_m;
+  float max_integration_distance_m;
+  float max_weight;
+  float invalid_depth_decay_factor;
+  int weighting_type;
+};
+
+// ---------------------------------------------------------------------------
+// Kernel launchers (implemented in the .cu files; all enqueue on `stream`).
+// ---------------------------------------------------------------------------
+
+// nvb_view.cu
+void launchViewRaycast(const float* depth, int rows, int cols, const Rigid& T_L_C, const NvbCamera& cam,
+                       float block_size, float trunc_m, float max_dist, int subsample, const ViewGrid& grid,
+                       unsigned int* bits, cudaStream_t stream);
+// Ordered compaction of the bitset into the frame list (+ optional allocation in `layer`
+// and tracker update). frame_blocks: int4 {x,y,z,slot}. Clears the bitset words it reads.
+struct CompactArgs {
+  unsigned int* bits;
+  ViewGrid grid;
+  int4* frame_blocks;
+  int* frame_count;
+  unsigned long long* tile_state;  // chained-scan state, one per tile
+  unsigned int* ticket;            // monotonically increasing ticket counter
+  unsigned int ticket_base;
+  unsigned int epoch;
+  int allocate;                    // 1: find-or-insert into layer
+  DevLayer layer;
+  int* error;
+  int* dirty;                      // per-slot dirty flag for the ESDF tracker (may be null)
+  int* todo_slots;
+  int* todo_count;
+};
+int compactNumTiles(const ViewGrid& grid);
+void launchCompactAllocate(const CompactArgs& args, cudaStream_t stream);
+
+// nvb_tsdf.cu
+void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* tsdf_blocks,
+                         const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
+                         const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p, int num_sms,
+                         cudaStream_t stream);
+
+// nvb_esdf.cu
+struct EsdfCtx {
+  DevLayer tsdf;
+  DevLayer esdf;
+  // work list of this update: {esdf_slot, tsdf_slot}
+  int2* work;
+  int* work_count;
+  // lists of ESDF slots
+  int* upd_list;
+  int* upd_count;
+  int* clr_list;   // to-clear blocks
+  int* clr_count;
+  int* clr_aabb;   // 6 ints: min xyz, max xyz (block indices) of the to-clear blocks
+  int* cleared_list;  // persistent across calls, like EsdfIntegrator::cleared_block_indices_device_
+  int* cleared_count;
+  int* ring_a;
+  int* ring_b;
+  int* ring_count;     // 2 ints
+  int* stamp_a;        // per ESDF slot
+  int* stamp_b;
+  int* ring_id;        // device: monotonically increasing ring id
+  unsigned int* barrier;  // grid barrier counter
+  long long* stats;    // 8 counters
+  int* error;
+  float max_sq;
+  float max_esdf_distance_m;
+  float max_site_distance_m;
+  float min_weight;
+  float block_size;
+};
+void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
+                        int in_count_upper, cudaStream_t stream);
+void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream);
+void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream);
+// Whole wavefront (both computeEsdf calls) in one cooperative launch. Returns cudaError.
+cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
+// Reference-like driver: one launch per phase, host reads the ring counter.
+cudaError_t runEsdfComputeHostLoop(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
+int esdfPersistentMaxCtas(int num_sms);
+
+// nvb_util.cu
+void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsigned char* out, unsigned char* found,
+                        cudaStream_t stream);
+void launchScatterBlocks(const DevLayer& layer, const int* xyz_dev, int n, const unsigned char* in, int* error,
+                         cudaStream_t stream);
+void launchFillU64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t stream);
+void launchRehash(const DevLayer& layer, int count, cudaStream_t stream);
+void launchTodoAll(const DevLayer& tsdf, int* dirty, int* todo_slots, int* todo_count, cudaStream_t stream);
+void launchTodoConsume(const int* todo_slots, const int* todo_count, int* dirty, cudaStream_t stream);
+
+}  // namespace nvb

@@ -1,0 +1,175 @@
+// nvb_tsdf.cu -- projective TSDF update of the frame's VoxelBlocks.
+//
+// Replaces integrateBlocksKernel<TsdfVoxel, UpdateTsdfVoxelFunctor, Camera>
+// (nvblox/include/nvblox/integrators/internal/cuda/impl/projective_integrator_impl.cuh:59-114)
+// with its functor (projective_tsdf_integrator_impl.cuh:30-90) and weighting
+// function (internal/impl/weighting_function_impl.h:29-117).
+//
+// B200 shape: a persistent grid (multiple of the SM count) walks the device-side
+// block list -- the host never learns the block count. A 256-thread CTA owns one
+// 4 KiB VoxelBlock per iteration; every thread owns two z-adjacent voxels = one
+// 128-bit word, so a warp moves 512 contiguous bytes per LDG.128/STG.128 and a
+// block is exactly 256 vector accesses each way. The next block's word is
+// prefetched before the current one is processed. Blocks are addressed by slot in
+// the layer slab (no pointer table). Update parameters arrive as __grid_constant__
+// kernel arguments (the reference dereferences a device pointer to a functor it
+// re-uploads every frame). Unchanged words are not written back.
+#include "nvb_internal.cuh"
+
+namespace nvb {
+
+namespace {
+
+struct TsdfArgs {
+  const int4* frame_blocks;
+  const int* frame_count;
+  unsigned char* tsdf_blocks;
+  const float* depth;
+  const unsigned char* mask;
+  int mask_mode;
+  int rows, cols;
+  Rigid T_C_L;
+  NvbCamera cam;
+  TsdfKernelParams p;
+};
+
+// WeightingFunction (weighting_function_impl.h:29-117)
+__device__ __forceinline__ float dropoff(float measured, float voxel_depth, float trunc) {
+  if (trunc <= 1e-2f) return 0.0f;
+  if (voxel_depth > measured) {
+    const float behind = voxel_depth - measured;
+    if (behind > trunc) return 0.0f;
+    return (trunc - behind) / trunc;
+  }
+  return 1.0f;
+}
+__device__ __forceinline__ float inverseSquare(float measured, float voxel_depth, float trunc) {
+  if (voxel_depth <= 1e-2f) return 1.0f;
+  if (voxel_depth - measured >= trunc) return 0.0f;
+  return 1.0f / (voxel_depth * voxel_depth);
+}
+__device__ __forceinline__ float tsdfDistancePenalty(float measured, float voxel_depth, float trunc) {
+  return (fabsf(measured - voxel_depth) >= trunc) ? 0.1f : 1.0f;
+}
+__device__ __forceinline__ float weighting(int type, float measured, float voxel_depth, float trunc) {
+  switch (type) {
+    case NVB_WEIGHT_CONSTANT:
+      return 1.0f;
+    case NVB_WEIGHT_CONSTANT_DROPOFF:
+      return 1.0f * dropoff(measured, voxel_depth, trunc);
+    case NVB_WEIGHT_INVERSE_SQUARE:
+      return inverseSquare(measured, voxel_depth, trunc);
+    case NVB_WEIGHT_INVERSE_SQUARE_DROPOFF:
+      return inverseSquare(measured, voxel_depth, trunc) * dropoff(measured, voxel_depth, trunc);
+    case NVB_WEIGHT_INVERSE_SQUARE_TSDF_DISTANCE_PENALTY:
+      return inverseSquare(measured, voxel_depth, trunc) * tsdfDistancePenalty(measured, voxel_depth, trunc);
+    default:  // NVB_WEIGHT_LINEAR_WITH_MAX
+      return (voxel_depth > 1.0f) ? 1.0f / voxel_depth : 1.0f;
+  }
+}
+
+// One voxel: project, look the depth up, fuse. Returns true if (dist, weight) changed.
+__device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, int vx, int vy, int vz, float& dist,
+                                            float& wgt) {
+  // getCenterPositionFromBlockIndexAndVoxelIndex (core/internal/impl/indexing_impl.h:51-81)
+  Vec3 p_L;
+  p_L.x = (a.p.block_size * (float)blk.x + a.p.voxel_size * (float)vx) + a.p.half_voxel_size;
+  p_L.y = (a.p.block_size * (float)blk.y + a.p.voxel_size * (float)vy) + a.p.half_voxel_size;
+  p_L.z = (a.p.block_size * (float)blk.z + a.p.voxel_size * (float)vz) + a.p.half_voxel_size;
+  const Vec3 p_C = transformPoint(a.T_C_L, p_L);
+  // Camera::project (sensors/internal/impl/camera_impl.h:37-76)
+  if (!(isfinite(p_C.x) && isfinite(p_C.y) && isfinite(p_C.z))) return false;
+  if (!(p_C.z >= 1e-6f)) return false;
+  const float u = (p_C.x / p_C.z) * a.cam.fu + a.cam.cu;
+  const float v = (p_C.y / p_C.z) * a.cam.fv + a.cam.cv;
+  if (u > (float)a.cam.width || v > (float)a.cam.height || u < 0.0f || v < 0.0f) return false;
+  const float voxel_depth = p_C.z;
+  // projectThreadVoxel max-depth test (projective_integrators_common_impl.cuh:42-45)
+  if (a.p.max_integration_distance_m > 0.0f && voxel_depth > a.p.max_integration_distance_m) return false;
+  // interpolate2DClosest (interpolation/internal/impl/interpolation_2d_impl.h:125-150)
+  const int ux = floatToIntRz(floorf(u)), uy = floatToIntRz(floorf(v));
+  if (ux < 0 || uy < 0 || ux >= a.cols || uy >= a.rows) return false;
+  const size_t pix = (size_t)uy * a.cols + ux;
+  float d = __ldg(a.depth + pix);
+  if (!(isfinite(d) && d > 1e-6f)) d = 0.0f;  // PixelIsValidDepth (interpolation_2d_impl.h:99-104)
+  bool is_active = true;  // MaskedImageView::isMasked (sensors/internal/impl/image_impl.h:250-259)
+  if (a.mask != nullptr) {
+    const unsigned char mv = __ldg(a.mask + pix);
+    is_active = (a.mask_mode == NVB_MASK_NON_INVERTED) ? (mv != 0) : (mv == 0);
+  }
+  // UpdateTsdfVoxelFunctor (projective_tsdf_integrator_impl.cuh:30-90)
+  const float trunc = a.p.truncation_distance_m;
+  if (d <= 0.0f) {
+    if (a.p.invalid_depth_decay_factor >= 0.0f) {
+      wgt = wgt * a.p.invalid_depth_decay_factor;
+      return true;
+    }
+    return false;
+  }
+  const float sdf = d - voxel_depth;
+  if (sdf < -trunc) return false;
+  if (!is_active && sdf < trunc) return false;
+  const float w = weighting(a.p.weighting_type, d, voxel_depth, trunc);
+  float fused = (sdf * w + dist * wgt) / (w + wgt);
+  if (fused > 0.0f) {
+    fused = fminf(trunc, fused);
+  } else {
+    fused = fmaxf(-trunc, fused);
+  }
+  dist = fused;
+  wgt = fminf(w + wgt, a.p.max_weight);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant__ TsdfArgs a) {
+  const int n = *a.frame_count;
+  const int tid = threadIdx.x;
+  // voxel pair owned by this thread: linear voxel offset 2*tid = x*64 + y*8 + z
+  const int vx = tid >> 5, vy = (tid >> 2) & 7, vz = (tid & 3) * 2;
+  int i = blockIdx.x;
+  if (i >= n) return;
+  int4 blk = a.frame_blocks[i];
+  float4 word = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blk.w >= 0) word = __ldcs(reinterpret_cast<const float4*>(a.tsdf_blocks + (size_t)blk.w * kTsdfBlockBytes) + tid);
+  while (true) {
+    // prefetch the next block's word before working on this one
+    const int inext = i + gridDim.x;
+    int4 nblk = make_int4(0, 0, 0, -1);
+    float4 nword = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inext < n) {
+      nblk = a.frame_blocks[inext];
+      if (nblk.w >= 0)
+        nword = __ldcs(reinterpret_cast<const float4*>(a.tsdf_blocks + (size_t)nblk.w * kTsdfBlockBytes) + tid);
+    }
+    if (blk.w >= 0) {
+      const bool c0 = updateVoxel(a, blk, vx, vy, vz, word.x, word.y);
+      const bool c1 = updateVoxel(a, blk, vx, vy, vz + 1, word.z, word.w);
+      if (c0 || c1) *(reinterpret_cast<float4*>(a.tsdf_blocks + (size_t)blk.w * kTsdfBlockBytes) + tid) = word;
+    }
+    if (inext >= n) break;
+    i = inext, blk = nblk, word = nword;
+  }
+}
+
+}  // namespace
+
+void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* tsdf_blocks,
+                         const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
+                         const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p, int num_sms,
+                         cudaStream_t stream) {
+  TsdfArgs a;
+  a.frame_blocks = frame_blocks;
+  a.frame_count = frame_count;
+  a.tsdf_blocks = tsdf_blocks;
+  a.depth = depth;
+  a.mask = mask;
+  a.mask_mode = mask_mode;
+  a.rows = rows, a.cols = cols;
+  a.T_C_L = T_C_L;
+  a.cam = cam;
+  a.p = p;
+  // 8 resident 256-thread CTAs per SM (2048 threads): one full wave.
+  tsdfIntegrateKernel<<<num_sms * 8, 256, 0, stream>>>(a);
+}
+
+}  // namespace nvb

@@ -1,0 +1,115 @@
+// nvb_util.cu -- small service kernels of the layer storage (gather / scatter of
+// blocks for host access, hash maintenance, ESDF "blocks to update" tracker).
+//
+// These back the BlockLayer queries the reference answers from its host-side
+// unordered_map (nvblox/include/nvblox/map/layer.h:76-217): here the map lives in
+// HBM, so host access is an explicit gather.
+#include "nvb_internal.cuh"
+
+namespace nvb {
+
+namespace {
+
+__global__ void gatherBlocksKernel(DevLayer L, const int* xyz, int n, unsigned char* out, unsigned char* found) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  __shared__ int s_slot;
+  if (threadIdx.x == 0) {
+    s_slot = hashFind(L.hash, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    found[i] = s_slot >= 0 ? 1 : 0;
+  }
+  __syncthreads();
+  const int slot = s_slot;
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * L.block_bytes);
+  const int nvec = L.block_bytes / 16;
+  if (slot >= 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(L.blocks + (size_t)slot * L.block_bytes);
+    for (int k = threadIdx.x; k < nvec; k += blockDim.x) dst[k] = src[k];
+  } else {
+    for (int k = threadIdx.x; k < nvec; k += blockDim.x) dst[k] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+__global__ void scatterBlocksKernel(DevLayer L, const int* xyz, int n, const unsigned char* in, int* error) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  __shared__ int s_slot;
+  if (threadIdx.x == 0) {
+    bool was_new;
+    s_slot = hashFindOrInsert(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], error, &was_new);
+  }
+  __syncthreads();
+  const int slot = s_slot;
+  if (slot < 0) return;
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)i * L.block_bytes);
+  uint4* dst = reinterpret_cast<uint4*>(L.blocks + (size_t)slot * L.block_bytes);
+  const int nvec = L.block_bytes / 16;
+  for (int k = threadIdx.x; k < nvec; k += blockDim.x) dst[k] = src[k];
+}
+
+__global__ void fillU64Kernel(unsigned long long* p, unsigned long long v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// Re-insert every live slot into a freshly emptied hash (after a capacity change).
+__global__ void rehashKernel(DevLayer L, int count) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= count) return;
+  const unsigned long long key = packIndex(L.block_index[3 * slot], L.block_index[3 * slot + 1],
+                                           L.block_index[3 * slot + 2]);
+  unsigned int p = hashKey(key) & L.hash.mask;
+  while (true) {
+    const unsigned long long old = atomicCAS(&L.hash.keys[p], kEmptyKey, key);
+    if (old == kEmptyKey) {
+      L.hash.vals[p] = slot;
+      return;
+    }
+    p = (p + 1) & L.hash.mask;
+  }
+}
+
+// BlocksToUpdateState::setUpdateAllBlocks (map/blocks_to_update_tracker.h): the todo
+// list becomes every allocated TSDF slot.
+__global__ void todoAllKernel(DevLayer tsdf, int* dirty, int* todo_slots, int* todo_count) {
+  const int n = *tsdf.count < tsdf.capacity ? *tsdf.count : tsdf.capacity;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *todo_count = n;
+  for (; i < n; i += gridDim.x * blockDim.x) {
+    todo_slots[i] = i;
+    dirty[i] = 1;
+  }
+}
+
+// BlocksToUpdateState::markBlocksAsUpdated: clear the dirty flags of the consumed list
+// (the count itself is zeroed by a memset that follows in the stream).
+__global__ void todoConsumeKernel(const int* todo_slots, const int* todo_count, int* dirty) {
+  const int n = *todo_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dirty[todo_slots[i]] = 0;
+}
+
+}  // namespace
+
+void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsigned char* out, unsigned char* found,
+                        cudaStream_t stream) {
+  if (n > 0) gatherBlocksKernel<<<n, 128, 0, stream>>>(layer, xyz_dev, n, out, found);
+}
+void launchScatterBlocks(const DevLayer& layer, const int* xyz_dev, int n, const unsigned char* in, int* error,
+                         cudaStream_t stream) {
+  if (n > 0) scatterBlocksKernel<<<n, 128, 0, stream>>>(layer, xyz_dev, n, in, error);
+}
+void launchFillU64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t stream) {
+  if (n > 0) fillU64Kernel<<<1184, 256, 0, stream>>>(p, v, n);
+}
+void launchRehash(const DevLayer& layer, int count, cudaStream_t stream) {
+  if (count > 0) rehashKernel<<<(count + 255) / 256, 256, 0, stream>>>(layer, count);
+}
+void launchTodoAll(const DevLayer& tsdf, int* dirty, int* todo_slots, int* todo_count, cudaStream_t stream) {
+  todoAllKernel<<<296, 256, 0, stream>>>(tsdf, dirty, todo_slots, todo_count);
+}
+void launchTodoConsume(const int* todo_slots, const int* todo_count, int* dirty, cudaStream_t stream) {
+  todoConsumeKernel<<<148, 256, 0, stream>>>(todo_slots, todo_count, dirty);
+}
+
+}  // namespace nvb

@@ -1,0 +1,222 @@
+// nvb_view.cu -- which VoxelBlocks does a depth frame touch?
+//
+// Replaces ViewCalculator::getBlocksInImageViewRaycast
+// (nvblox/include/nvblox/integrators/internal/cuda/impl/view_calculator_impl.cuh:62-233,
+//  nvblox/src/integrators/view_calculator.cu:157-195) with a device-only chain:
+//   viewRaycastKernel      one thread per subsampled pixel, Amanatides-Woo walk over
+//                          the block grid, marks a BITSET (1 bit per AABB cell; the
+//                          reference marks one byte per cell and copies it to the host)
+//   compactAllocateKernel  ordered (x-fastest) compaction of the bitset into the frame's
+//                          block list with warp ballots/popc + a chained tile scan, fused
+//                          with allocate-if-absent in the TSDF layer's device hash and the
+//                          ESDF "blocks to update" tracker. The reference does this part on
+//                          the host (D2H copy, sync, host loop, unordered_map inserts).
+// Nothing returns to the host; the list and its count stay in HBM for the TSDF kernel.
+#include "nvb_internal.cuh"
+
+namespace nvb {
+
+namespace {
+
+__device__ __forceinline__ int signum(float x) { return (x > 0.0f) ? 1 : ((x < 0.0f) ? -1 : 0); }
+
+// setIndexUpdated (view_calculator_impl.cuh:46-56): the linear index is computed in
+// int arithmetic and only guarded by lin < linear_size (negative values fail the
+// guard; out-of-AABB cells whose linear index lands in range alias, as in the reference).
+__device__ __forceinline__ void markCell(int x, int y, int z, const ViewGrid& g, unsigned int* bits) {
+  const unsigned int sx = (unsigned int)x - (unsigned int)g.min_index.x;
+  const unsigned int sy = (unsigned int)y - (unsigned int)g.min_index.y;
+  const unsigned int sz = (unsigned int)z - (unsigned int)g.min_index.z;
+  const unsigned int lin = sx + sy * (unsigned int)g.size.x + sz * (unsigned int)g.size.x * (unsigned int)g.size.y;
+  if ((int)lin >= 0 && lin < (unsigned int)g.linear_size) {
+    const unsigned int bit = 1u << (lin & 31);
+    unsigned int* w = bits + (lin >> 5);
+    // Many rays cross the same cells: test first (a stale read only costs an extra atomic).
+    if (!(*(volatile unsigned int*)w & bit)) atomicOr(w, bit);
+  }
+}
+
+// combinedBlockIndicesInImageKernel (view_calculator_impl.cuh:62-115) + RayCaster
+// (rays/internal/impl/ray_caster_impl.h:26-72).
+__global__ void __launch_bounds__(128) viewRaycastKernel(const float* __restrict__ depth, int rows, int cols,
+                                                         Rigid T_L_C, NvbCamera cam, float block_size,
+                                                         float trunc_m, float max_dist, int f, int ray_rows,
+                                                         int ray_cols, ViewGrid g, unsigned int* bits) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= ray_rows * ray_cols) return;
+  const int rr = ray / ray_cols, rc = ray - rr * ray_cols;
+  int pixel_row = rr * f, pixel_col = rc * f;
+  if (pixel_row >= rows) pixel_row = rows - 1;  // overhanging rays are pulled back to the border
+  if (pixel_col >= cols) pixel_col = cols - 1;
+
+  float d = __ldg(depth + (size_t)pixel_row * cols + pixel_col);
+  if (d <= 0.0f) return;  // NaN passes this test, exactly like the reference
+  if (max_dist > 0.0f && d > max_dist) d = max_dist;
+
+  // Camera::vectorFromPixelIndices (sensors/internal/impl/camera_impl.h:89-112)
+  const float vx = (((float)pixel_col + 0.5f) - cam.cu) / cam.fu;
+  const float vy = (((float)pixel_row + 0.5f) - cam.cv) / cam.fv;
+  const float s = d + trunc_m;
+  Vec3 p_C = {s * vx, s * vy, s * 1.0f};
+  const Vec3 p_L = transformPoint(T_L_C, p_C);
+
+  const int3 b = blockIndexFromPosition(block_size, p_L);
+  markCell(b.x, b.y, b.z, g, bits);
+
+  // RayCaster(T_L_C.translation() / block_size, p_L / block_size), scale 1.
+  const float o[3] = {T_L_C.t[0] / block_size, T_L_C.t[1] / block_size, T_L_C.t[2] / block_size};
+  const float e[3] = {p_L.x / block_size, p_L.y / block_size, p_L.z / block_size};
+  int cur[3], sgn[3];
+  float t_next[3], t_step[3];
+  unsigned int length = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    cur[i] = floatToIntRz(floorf(o[i] / 1.0f));
+    const int end = floatToIntRz(floorf(e[i] / 1.0f));
+    const int diff = (int)((unsigned int)end - (unsigned int)cur[i]);
+    length += (diff < 0) ? (0u - (unsigned int)diff) : (unsigned int)diff;
+    const float ray_i = e[i] - o[i];
+    sgn[i] = signum(ray_i);
+    const int corrected = sgn[i] > 0 ? sgn[i] : 0;
+    const float shifted = o[i] - (float)cur[i];
+    t_next[i] = ((float)corrected - shifted) / ray_i;  // NaN / inf allowed
+    t_step[i] = (float)sgn[i] / ray_i;
+  }
+  // nextRayIndex returns length+1 cells.
+  for (int step = 0; step <= (int)length; step++) {
+    markCell(cur[0], cur[1], cur[2], g, bits);
+    // Eigen minCoeff: start at element 0, replace on strict '<'.
+    float best = t_next[0];
+    int k = 0;
+    if (t_next[1] < best) best = t_next[1], k = 1;
+    if (t_next[2] < best) k = 2;
+    if (k == 0) {
+      cur[0] = (int)((unsigned int)cur[0] + (unsigned int)sgn[0]);
+      t_next[0] = t_next[0] + t_step[0];
+    } else if (k == 1) {
+      cur[1] = (int)((unsigned int)cur[1] + (unsigned int)sgn[1]);
+      t_next[1] = t_next[1] + t_step[1];
+    } else {
+      cur[2] = (int)((unsigned int)cur[2] + (unsigned int)sgn[2]);
+      t_next[2] = t_next[2] + t_step[2];
+    }
+  }
+}
+
+constexpr int kCompactThreads = 512;  // one bitset word per thread -> 16384 cells per tile
+
+// Ordered compaction + allocation. Tiles take tickets in order and chain their
+// prefix through tile_state (epoch in the high word), so the emitted list is in
+// ascending linear-index order = the order convertAabbUpdatedToVector produces
+// (view_calculator.cu:185-195): x fastest, then y, then z.
+__global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(CompactArgs a) {
+  __shared__ unsigned int s_tile;
+  __shared__ int s_warp_sums[kCompactThreads / 32];
+  __shared__ int s_prefix;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const int num_tiles = (a.grid.num_words + kCompactThreads - 1) / kCompactThreads;
+
+  const int w = (int)tile * kCompactThreads + tid;
+  unsigned int word = 0;
+  if (w < a.grid.num_words) {
+    word = a.bits[w];
+    if (word) a.bits[w] = 0;  // self-cleaning: the next frame starts from a zero bitset
+  }
+  const int cnt = __popc(word);
+  // block-wide exclusive scan of cnt
+  int incl = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((tid & 31) >= off) incl += n;
+  }
+  if ((tid & 31) == 31) s_warp_sums[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int v = (tid < kCompactThreads / 32) ? s_warp_sums[tid] : 0;
+    int vi = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, vi, off);
+      if (tid >= off) vi += n;
+    }
+    if (tid < kCompactThreads / 32) s_warp_sums[tid] = vi - v;  // exclusive warp offsets
+    if (tid == kCompactThreads / 32 - 1) {
+      const int tile_total = vi;
+      // chained scan: wait for the predecessor tile of this launch
+      int prefix = 0;
+      if (tile > 0) {
+        volatile unsigned long long* prev = a.tile_state + (tile - 1);
+        unsigned long long st;
+        do {
+          st = *prev;
+        } while ((unsigned int)(st >> 32) != a.epoch);
+        prefix = (int)(unsigned int)st;
+      }
+      __threadfence();
+      atomicExch(a.tile_state + tile, ((unsigned long long)a.epoch << 32) | (unsigned int)(prefix + tile_total));
+      if ((int)tile == num_tiles - 1) *a.frame_count = prefix + tile_total;
+      s_prefix = prefix;
+    }
+  }
+  __syncthreads();
+  if (word == 0) return;
+  int out = s_prefix + s_warp_sums[tid >> 5] + (incl - cnt);
+  const int sx = a.grid.size.x, sxy = a.grid.size.x * a.grid.size.y;
+  while (word) {
+    const int bit = __ffs(word) - 1;
+    word &= word - 1;
+    const int lin = w * 32 + bit;
+    // aabbLinearIndexToLayerIndex (view_calculator_impl.cuh:38-44)
+    const int x = lin % sx + a.grid.min_index.x;
+    const int y = (lin / sx) % a.grid.size.y + a.grid.min_index.y;
+    const int z = lin / sxy + a.grid.min_index.z;
+    int slot = -1;
+    if (a.allocate) {
+      bool was_new;
+      slot = hashFindOrInsert(a.layer, x, y, z, a.error, &was_new);
+      if (slot >= 0 && a.dirty != nullptr) {
+        // BlocksToUpdateTracker::addBlocksToUpdate (map/blocks_to_update_tracker.cpp:33-63),
+        // kept on the device: unique append of the slot.
+        if (atomicExch(a.dirty + slot, 1) == 0) a.todo_slots[atomicAdd(a.todo_count, 1)] = slot;
+      }
+    }
+    a.frame_blocks[out++] = make_int4(x, y, z, slot);
+  }
+}
+
+}  // namespace
+
+int compactNumTiles(const ViewGrid& grid) {
+  const int t = (grid.num_words + kCompactThreads - 1) / kCompactThreads;
+  return t < 1 ? 1 : t;
+}
+
+void launchViewRaycast(const float* depth, int rows, int cols, const Rigid& T_L_C, const NvbCamera& cam,
+                       float block_size, float trunc_m, float max_dist, int f, const ViewGrid& grid,
+                       unsigned int* bits, cudaStream_t stream) {
+  // Launch shape of getBlocksByRaycastingPixelsAsync (view_calculator_impl.cuh:200-233):
+  // ceil((dim + 1) / f) rays rounded up to 16-thread tiles, then the in-kernel guard
+  // pixel < dim + f - 1 decides which of those threads cast a ray.
+  const int rows_s = (int)ceilf((float)(rows + 1) / (float)f);
+  const int cols_s = (int)ceilf((float)(cols + 1) / (float)f);
+  const int thr_rows = ((rows_s + 15) / 16) * 16;
+  const int thr_cols = ((cols_s + 15) / 16) * 16;
+  int ray_rows = (rows + f - 2) / f + 1;
+  int ray_cols = (cols + f - 2) / f + 1;
+  if (ray_rows > thr_rows) ray_rows = thr_rows;
+  if (ray_cols > thr_cols) ray_cols = thr_cols;
+  const int n = ray_rows * ray_cols;
+  if (n <= 0) return;
+  viewRaycastKernel<<<(n + 127) / 128, 128, 0, stream>>>(depth, rows, cols, T_L_C, cam, block_size, trunc_m,
+                                                         max_dist, f, ray_rows, ray_cols, grid, bits);
+}
+
+void launchCompactAllocate(const CompactArgs& args, cudaStream_t stream) {
+  compactAllocateKernel<<<compactNumTiles(args.grid), kCompactThreads, 0, stream>>>(args);
+}
+
+}  // namespace nvb

@@ -1,0 +1,1066 @@
+/*
+ * nvblox_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see nvblox_oracle.h).
+ *
+ * CPU restatement of the reference's depth-integration hot path. Citations are
+ * relative to /root/reference/nvblox_ros/nvblox_core/nvblox/ ("C/" in SURVEY.md).
+ * Parity: pinned against the reference's known-answer tests only (the reference
+ * itself cannot be built in this environment) -- see tests/test_oracle_kat.py.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared
+ */
+#include "nvblox_oracle.h"
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define VPS 8 /* VoxelBlock::kVoxelsPerSide, include/nvblox/map/blox.h:36 */
+#define VPB (VPS * VPS * VPS)
+
+typedef struct {
+  float x, y, z;
+} v3;
+typedef struct {
+  int32_t x, y, z;
+} i3;
+
+/* ------------------------------------------------------------------------- */
+/* Scalar helpers                                                            */
+/* ------------------------------------------------------------------------- */
+
+/* float -> int with the CUDA device semantics (cvt.rzi.s32.f32): NaN -> 0,
+ * saturating. The reference performs these casts in device code. */
+static int32_t f2i(float f) {
+  if (f != f) return 0;
+  if (f >= 2147483648.0f) return INT32_MAX;
+  if (f <= -2147483648.0f) return INT32_MIN;
+  return (int32_t)f;
+}
+
+/* Eigen fixed-size-3 reduction order: a0 + (a1 + a2)
+ * (Eigen/src/Core/Redux.h redux_novec_unroller, Length=3 -> {1, 2}). */
+static float sum3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
+
+static int signum(float x) { /* ray_caster_impl.h:22-24 */
+  return (x > 0.0f) ? 1 : ((x < 0.0f) ? -1 : 0);
+}
+
+/* Transform = Eigen::Isometry3f, 4x4 column-major (core/types.h:141-153). */
+static float Rm(const float* T, int i, int j) { return T[j * 4 + i]; }
+static float Tt(const float* T, int i) { return T[12 + i]; }
+
+/* Isometry * point: res = translation; res += linear * p (lazy coefficient
+ * product; Eigen/src/Geometry/Transform.h transform_right_product_impl). */
+static v3 transform_point(const float* T, v3 p) {
+  v3 r;
+  r.x = Tt(T, 0) + sum3(Rm(T, 0, 0) * p.x, Rm(T, 0, 1) * p.y, Rm(T, 0, 2) * p.z);
+  r.y = Tt(T, 1) + sum3(Rm(T, 1, 0) * p.x, Rm(T, 1, 1) * p.y, Rm(T, 1, 2) * p.z);
+  r.z = Tt(T, 2) + sum3(Rm(T, 2, 0) * p.x, Rm(T, 2, 1) * p.y, Rm(T, 2, 2) * p.z);
+  return r;
+}
+
+/* Isometry inverse: R' = R^T, t' = -(R^T t) (Transform::inverse, Isometry). */
+static void invert_isometry(const float* T, float* out) {
+  memset(out, 0, 16 * sizeof(float));
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) out[j * 4 + i] = Rm(T, j, i);
+  for (int i = 0; i < 3; i++) {
+    out[12 + i] = -sum3(out[0 * 4 + i] * Tt(T, 0), out[1 * 4 + i] * Tt(T, 1),
+                        out[2 * 4 + i] * Tt(T, 2));
+  }
+  out[15] = 1.0f;
+}
+
+/* getBlockIndexFromPositionInLayer (core/internal/impl/indexing_impl.h:31-35). */
+static i3 block_index_from_position(float block_size, v3 p) {
+  i3 r;
+  r.x = f2i(floorf(p.x / block_size));
+  r.y = f2i(floorf(p.y / block_size));
+  r.z = f2i(floorf(p.z / block_size));
+  return r;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Camera (sensors/internal/impl/camera_impl.h)                              */
+/* ------------------------------------------------------------------------- */
+
+/* vectorFromImagePlaneCoordinates (camera_impl.h:89-104), no distortion. */
+static v3 cam_vector_from_image_plane(const OrCamera* c, float u, float v) {
+  v3 r;
+  r.x = (u - c->cu) / c->fu;
+  r.y = (v - c->cv) / c->fv;
+  r.z = 1.0f;
+  return r;
+}
+
+/* vectorFromPixelIndices (camera_impl.h:106-112): pixel centre = index + 0.5. */
+static v3 cam_vector_from_pixel(const OrCamera* c, int col, int row) {
+  return cam_vector_from_image_plane(c, (float)col + 0.5f, (float)row + 0.5f);
+}
+
+/* Camera::project (camera_impl.h:37-63, 65-76), min_depth = 1e-6, viewport
+ * check on. Returns 0 if rejected. */
+static int cam_project(const OrCamera* c, v3 p, float* u, float* v) {
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) return 0;
+  const float min_depth = 1e-6f;
+  if (!(p.z >= min_depth)) return 0;
+  float un = p.x / p.z;
+  float vn = p.y / p.z;
+  *u = un * c->fu + c->cu;
+  *v = vn * c->fv + c->cv;
+  if (*u > (float)c->width || *v > (float)c->height || *u < 0.0f || *v < 0.0f)
+    return 0;
+  return 1;
+}
+
+/* Camera::getViewAABB (src/sensors/camera.cpp:31-83): 4 image-corner rays at
+ * min and max depth, transformed into the layer frame. */
+static void cam_view_aabb(const OrCamera* c, const float* T_L_C, float min_depth,
+                          float max_depth, v3* mn, v3* mx) {
+  const float w = (float)c->width, h = (float)c->height;
+  v3 ray[4];
+  ray[0] = cam_vector_from_image_plane(c, 0.0f, 0.0f);
+  ray[1] = cam_vector_from_image_plane(c, w, 0.0f);
+  ray[2] = cam_vector_from_image_plane(c, w, h);
+  ray[3] = cam_vector_from_image_plane(c, 0.0f, h);
+  const int order[4] = {2, 1, 0, 3};
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+  float hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int k = 0; k < 8; k++) {
+    const float d = (k < 4) ? min_depth : max_depth;
+    const v3 r = ray[order[k & 3]];
+    v3 corner_C = {d * r.x, d * r.y, d * r.z};
+    v3 corner_L = transform_point(T_L_C, corner_C);
+    const float cl[3] = {corner_L.x, corner_L.y, corner_L.z};
+    for (int i = 0; i < 3; i++) {
+      /* std::min(a, b) = (b < a) ? b : a ; std::max(a, b) = (a < b) ? b : a */
+      lo[i] = (cl[i] < lo[i]) ? cl[i] : lo[i];
+      hi[i] = (hi[i] < cl[i]) ? cl[i] : hi[i];
+    }
+  }
+  mn->x = lo[0], mn->y = lo[1], mn->z = lo[2];
+  mx->x = hi[0], mx->y = hi[1], mx->z = hi[2];
+}
+
+/* applyWorkspaceBounds (src/geometry/workspace_bounds.cpp:20-61). Returns 0 if
+ * the resulting AABB is empty (Eigen AlignedBox::isEmpty = any(min > max)). */
+static int apply_workspace_bounds(const OrTsdfParams* p, v3* mn, v3* mx) {
+  if (p->workspace_bounds_type == OR_WS_HEIGHT_BOUNDS) {
+    mn->z = (mn->z < p->workspace_min[2]) ? p->workspace_min[2] : mn->z;
+    mx->z = (p->workspace_max[2] < mx->z) ? p->workspace_max[2] : mx->z;
+  } else if (p->workspace_bounds_type == OR_WS_BOUNDING_BOX) {
+    /* AlignedBox::intersection = (cwiseMax(mins), cwiseMin(maxs)) with the
+     * workspace box as *this. */
+    float* a[3] = {&mn->x, &mn->y, &mn->z};
+    float* b[3] = {&mx->x, &mx->y, &mx->z};
+    for (int i = 0; i < 3; i++) {
+      *a[i] = (p->workspace_min[i] < *a[i]) ? *a[i] : p->workspace_min[i];
+      *b[i] = (*b[i] < p->workspace_max[i]) ? *b[i] : p->workspace_max[i];
+    }
+  }
+  if (mn->x > mx->x || mn->y > mx->y || mn->z > mx->z) return 0;
+  return 1;
+}
+
+/* ------------------------------------------------------------------------- */
+/* RayCaster (rays/internal/impl/ray_caster_impl.h:26-75)                    */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+  int32_t cur[3];
+  int32_t sign[3];
+  float t_next[3];
+  float t_step[3];
+  uint32_t step, length;
+} RayCaster;
+
+static void raycaster_init(RayCaster* rc, v3 origin, v3 dest, float scale) {
+  const float o[3] = {origin.x / scale, origin.y / scale, origin.z / scale};
+  const float e[3] = {dest.x / scale, dest.y / scale, dest.z / scale};
+  const i3 ci = block_index_from_position(scale, origin);
+  const i3 ei = block_index_from_position(scale, dest);
+  rc->cur[0] = ci.x, rc->cur[1] = ci.y, rc->cur[2] = ci.z;
+  const int32_t end[3] = {ei.x, ei.y, ei.z};
+  rc->step = 0;
+  /* diff_index.cwiseAbs().sum(): int arithmetic (wraps like the device). */
+  uint32_t len = 0;
+  for (int i = 0; i < 3; i++) {
+    uint32_t d = (uint32_t)end[i] - (uint32_t)rc->cur[i];
+    int32_t di = (int32_t)d;
+    uint32_t ad = (di < 0) ? (0u - (uint32_t)di) : (uint32_t)di;
+    len += ad;
+  }
+  rc->length = len;
+  for (int i = 0; i < 3; i++) {
+    const float ray = e[i] - o[i];
+    rc->sign[i] = signum(ray);
+    const int corrected = rc->sign[i] > 0 ? rc->sign[i] : 0; /* cwiseMax(0) */
+    const float shifted = o[i] - (float)rc->cur[i];
+    const float dist = (float)corrected - shifted;
+    rc->t_next[i] = dist / ray;                 /* NaN/inf allowed */
+    rc->t_step[i] = (float)rc->sign[i] / ray;   /* NaN/inf allowed */
+  }
+}
+
+/* nextRayIndex (ray_caster_impl.h:56-72): returns steps+1 cells. minCoeff is
+ * Eigen's visitor: start at element 0, replace on strict '<'. */
+static int raycaster_next(RayCaster* rc, int32_t out[3]) {
+  /* current_step_++ > ray_length_in_steps_ compares ints in the reference;
+   * lengths are far below 2^31 for finite inputs. */
+  if ((int32_t)(rc->step++) > (int32_t)rc->length) return 0;
+  out[0] = rc->cur[0], out[1] = rc->cur[1], out[2] = rc->cur[2];
+  int k = 0;
+  float best = rc->t_next[0];
+  if (rc->t_next[1] < best) best = rc->t_next[1], k = 1;
+  if (rc->t_next[2] < best) best = rc->t_next[2], k = 2;
+  rc->cur[k] = (int32_t)((uint32_t)rc->cur[k] + (uint32_t)rc->sign[k]);
+  rc->t_next[k] = rc->t_next[k] + rc->t_step[k];
+  return 1;
+}
+
+int32_t or_raycast_cells(const float origin[3], const float dest[3], float scale,
+                         int32_t* out_xyz, int32_t cap) {
+  RayCaster rc;
+  v3 o = {origin[0], origin[1], origin[2]}, d = {dest[0], dest[1], dest[2]};
+  raycaster_init(&rc, o, d, scale);
+  int32_t n = 0, c[3];
+  while (raycaster_next(&rc, c)) {
+    if (n < cap) out_xyz[3 * n] = c[0], out_xyz[3 * n + 1] = c[1], out_xyz[3 * n + 2] = c[2];
+    n++;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Block storage: index -> slot hash + dense block arrays                    */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+  int32_t cap; /* power of two */
+  int32_t n;
+  i3* keys;
+  int32_t* vals; /* -1 = empty */
+} Hash;
+
+static uint32_t hash_i3(i3 k) {
+  uint64_t h = (uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ull;
+  h ^= (uint64_t)(uint32_t)k.y * 0xC2B2AE3D27D4EB4Full;
+  h ^= (uint64_t)(uint32_t)k.z * 0x165667B19E3779F9ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return (uint32_t)h;
+}
+
+static void hash_init(Hash* h, int32_t cap) {
+  h->cap = cap, h->n = 0;
+  h->keys = (i3*)malloc(sizeof(i3) * (size_t)cap);
+  h->vals = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+  for (int32_t i = 0; i < cap; i++) h->vals[i] = -1;
+}
+static void hash_free(Hash* h) {
+  free(h->keys), free(h->vals);
+  h->keys = NULL, h->vals = NULL;
+}
+static int32_t hash_find(const Hash* h, i3 k) {
+  uint32_t m = (uint32_t)h->cap - 1, p = hash_i3(k) & m;
+  while (h->vals[p] >= 0) {
+    if (h->keys[p].x == k.x && h->keys[p].y == k.y && h->keys[p].z == k.z) return h->vals[p];
+    p = (p + 1) & m;
+  }
+  return -1;
+}
+static void hash_put_raw(Hash* h, i3 k, int32_t v) {
+  uint32_t m = (uint32_t)h->cap - 1, p = hash_i3(k) & m;
+  while (h->vals[p] >= 0) p = (p + 1) & m;
+  h->keys[p] = k, h->vals[p] = v, h->n++;
+}
+static void hash_put(Hash* h, i3 k, int32_t v) {
+  if ((h->n + 1) * 2 > h->cap) {
+    Hash g;
+    hash_init(&g, h->cap * 2);
+    for (int32_t i = 0; i < h->cap; i++)
+      if (h->vals[i] >= 0) hash_put_raw(&g, h->keys[i], h->vals[i]);
+    hash_free(h);
+    *h = g;
+  }
+  hash_put_raw(h, k, v);
+}
+
+typedef struct {
+  Hash hash;
+  int32_t n, cap;
+  size_t block_bytes;
+  i3* index;
+  uint8_t* data;
+} Layer;
+
+static void layer_init(Layer* l, size_t block_bytes) {
+  hash_init(&l->hash, 1024);
+  l->n = 0, l->cap = 256, l->block_bytes = block_bytes;
+  l->index = (i3*)malloc(sizeof(i3) * (size_t)l->cap);
+  l->data = (uint8_t*)malloc(block_bytes * (size_t)l->cap);
+}
+static void layer_free(Layer* l) {
+  hash_free(&l->hash);
+  free(l->index), free(l->data);
+}
+static void layer_clear(Layer* l) {
+  size_t bb = l->block_bytes;
+  layer_free(l);
+  layer_init(l, bb);
+}
+/* BlockLayer::allocateBlockAtIndex (map/internal/impl/layer_impl.h:106-128):
+ * new blocks are zero bytes (map/internal/impl/blox_impl.h:37-45,92-97). */
+static int32_t layer_allocate(Layer* l, i3 k) {
+  int32_t s = hash_find(&l->hash, k);
+  if (s >= 0) return s;
+  if (l->n == l->cap) {
+    l->cap *= 2;
+    l->index = (i3*)realloc(l->index, sizeof(i3) * (size_t)l->cap);
+    l->data = (uint8_t*)realloc(l->data, l->block_bytes * (size_t)l->cap);
+  }
+  s = l->n++;
+  l->index[s] = k;
+  memset(l->data + l->block_bytes * (size_t)s, 0, l->block_bytes);
+  hash_put(&l->hash, k, s);
+  return s;
+}
+static void* layer_block(const Layer* l, int32_t slot) {
+  return l->data + l->block_bytes * (size_t)slot;
+}
+
+/* Growable list of block indices. */
+typedef struct {
+  i3* v;
+  int32_t n, cap;
+} List;
+static void list_push(List* l, i3 k) {
+  if (l->n == l->cap) {
+    l->cap = l->cap ? l->cap * 2 : 256;
+    l->v = (i3*)realloc(l->v, sizeof(i3) * (size_t)l->cap);
+  }
+  l->v[l->n++] = k;
+}
+static void list_free(List* l) {
+  free(l->v);
+  l->v = NULL, l->n = l->cap = 0;
+}
+static int cmp_i3(const void* a, const void* b) {
+  const i3 *p = (const i3*)a, *q = (const i3*)b;
+  if (p->x != q->x) return p->x < q->x ? -1 : 1;
+  if (p->y != q->y) return p->y < q->y ? -1 : 1;
+  if (p->z != q->z) return p->z < q->z ? -1 : 1;
+  return 0;
+}
+/* sortAndTakeUniqueIndices (src/integrators/esdf_integrator.cu:1282-1321): only
+ * the resulting SET matters downstream. */
+static void list_sort_unique(List* l) {
+  if (l->n == 0) return;
+  qsort(l->v, (size_t)l->n, sizeof(i3), cmp_i3);
+  int32_t w = 1;
+  for (int32_t i = 1; i < l->n; i++)
+    if (cmp_i3(&l->v[i], &l->v[w - 1]) != 0) l->v[w++] = l->v[i];
+  l->n = w;
+}
+
+struct OrMap {
+  float voxel_size, block_size;
+  Layer tsdf, esdf;
+  /* EsdfIntegrator::cleared_block_indices_device_ (integrators/esdf_integrator.h:389)
+   * is a member that is only overwritten when a call has blocks to clear
+   * (esdf_integrator.cu:242-257), so its content carries over between calls. */
+  List esdf_cleared_persistent;
+  int64_t stats[8];
+};
+
+void or_default_tsdf_params(OrTsdfParams* p) {
+  /* integrators/projective_integrator_params.h:24-63, view_calculator_params.h:22-25 */
+  memset(p, 0, sizeof(*p));
+  p->truncation_distance_vox = 4.0f;
+  p->max_integration_distance_m = 7.0f;
+  p->max_weight = 5.0f;
+  p->invalid_depth_decay_factor = -1.0f;
+  p->weighting_type = OR_WEIGHT_INVERSE_SQUARE;
+  p->raycast_subsampling = 4;
+  p->workspace_bounds_type = OR_WS_UNBOUNDED;
+}
+void or_default_esdf_params(OrEsdfParams* p) {
+  /* integrators/esdf_integrator_params.h:22-31 */
+  p->max_esdf_distance_m = 2.0f;
+  p->max_site_distance_vox = 1.0f;
+  p->min_weight = 1e-4f;
+}
+
+OrMap* or_map_create(float voxel_size_m) {
+  OrMap* m = (OrMap*)calloc(1, sizeof(OrMap));
+  m->voxel_size = voxel_size_m;
+  m->block_size = voxel_size_m * (float)VPS; /* voxelSizeToBlockSize, indexing_impl.h:22 */
+  layer_init(&m->tsdf, sizeof(OrTsdfVoxel) * VPB);
+  layer_init(&m->esdf, sizeof(OrEsdfVoxel) * VPB);
+  return m;
+}
+void or_map_destroy(OrMap* m) {
+  if (!m) return;
+  layer_free(&m->tsdf), layer_free(&m->esdf);
+  list_free(&m->esdf_cleared_persistent);
+  free(m);
+}
+void or_map_clear(OrMap* m) {
+  layer_clear(&m->tsdf), layer_clear(&m->esdf);
+  m->esdf_cleared_persistent.n = 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* View calculation                                                          */
+/* ------------------------------------------------------------------------- */
+
+/* layerIndexToAabbLinearIndex + setIndexUpdated (view_calculator_impl.cuh:30-56):
+ * int arithmetic, converted to size_t, guarded only by lin < linear_size. */
+static void set_index_updated(i3 idx, i3 mn, i3 sz, uint8_t* grid) {
+  const size_t linear_size = (size_t)(int64_t)(int32_t)((uint32_t)sz.x * (uint32_t)sz.y * (uint32_t)sz.z);
+  const int32_t sx = (int32_t)((uint32_t)idx.x - (uint32_t)mn.x);
+  const int32_t sy = (int32_t)((uint32_t)idx.y - (uint32_t)mn.y);
+  const int32_t szz = (int32_t)((uint32_t)idx.z - (uint32_t)mn.z);
+  const int32_t lin32 = (int32_t)((uint32_t)sx + (uint32_t)sy * (uint32_t)sz.x +
+                                  (uint32_t)szz * (uint32_t)sz.x * (uint32_t)sz.y);
+  const size_t lin = (size_t)(int64_t)lin32; /* negative -> huge */
+  if (lin < linear_size) __atomic_store_n(&grid[lin], (uint8_t)1, __ATOMIC_RELAXED);
+}
+
+/* Returns a malloc'ed list of block indices in x-fastest order. */
+static List view_raycast(const float* depth, int rows, int cols, const float* T_L_C,
+                         const OrCamera* cam, float block_size, float trunc_m,
+                         const OrTsdfParams* P) {
+  List out = {0};
+  const float max_dist = P->max_integration_distance_m;
+  const int f = P->raycast_subsampling;
+  /* view_calculator_impl.cuh:137-156 */
+  v3 mn, mx;
+  cam_view_aabb(cam, T_L_C, 0.0f, max_dist, &mn, &mx);
+  if (!apply_workspace_bounds(P, &mn, &mx)) return out;
+  const i3 min_index = block_index_from_position(block_size, mn);
+  const i3 max_index = block_index_from_position(block_size, mx);
+  const i3 size = {max_index.x - min_index.x + 1, max_index.y - min_index.y + 1,
+                   max_index.z - min_index.z + 1};
+  const int64_t lin_size = (int64_t)size.x * size.y * size.z;
+  if (lin_size <= 0) return out;
+  uint8_t* grid = (uint8_t*)calloc((size_t)lin_size, 1);
+
+  /* getBlocksByRaycastingPixelsAsync launch shape (view_calculator_impl.cuh:200-233). */
+  const int rows_s = (int)ceilf((float)(rows + 1) / (float)f);
+  const int cols_s = (int)ceilf((float)(cols + 1) / (float)f);
+  const int thr_rows = ((rows_s + 15) / 16) * 16;
+  const int thr_cols = ((cols_s + 15) / 16) * 16;
+  const v3 origin = {Tt(T_L_C, 0), Tt(T_L_C, 1), Tt(T_L_C, 2)};
+  const v3 origin_s = {origin.x / block_size, origin.y / block_size, origin.z / block_size};
+
+  /* combinedBlockIndicesInImageKernel (view_calculator_impl.cuh:62-115). */
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int rr = 0; rr < thr_rows; rr++) {
+    for (int rc_ = 0; rc_ < thr_cols; rc_++) {
+      int pixel_row = rr * f, pixel_col = rc_ * f;
+      if (pixel_row >= rows + f - 1 || pixel_col >= cols + f - 1) continue;
+      if (pixel_row >= rows) pixel_row = rows - 1;
+      if (pixel_col >= cols) pixel_col = cols - 1;
+      float d = depth[(size_t)pixel_row * cols + pixel_col];
+      if (d <= 0.0f) continue; /* NaN passes, as in the reference */
+      if (max_dist > 0.0f && d > max_dist) d = max_dist;
+      const v3 vec = cam_vector_from_pixel(cam, pixel_col, pixel_row);
+      const float s = d + trunc_m;
+      const v3 p_C = {s * vec.x, s * vec.y, s * vec.z};
+      const v3 p_L = transform_point(T_L_C, p_C);
+      set_index_updated(block_index_from_position(block_size, p_L), min_index, size, grid);
+      const v3 dest_s = {p_L.x / block_size, p_L.y / block_size, p_L.z / block_size};
+      RayCaster rc;
+      raycaster_init(&rc, origin_s, dest_s, 1.0f);
+      int32_t c[3];
+      while (raycaster_next(&rc, c)) {
+        i3 ci = {c[0], c[1], c[2]};
+        set_index_updated(ci, min_index, size, grid);
+      }
+    }
+  }
+  /* convertAabbUpdatedToVector (src/integrators/view_calculator.cu:157-195). */
+  for (int64_t lin = 0; lin < lin_size; lin++) {
+    if (grid[lin]) {
+      i3 k = {(int32_t)(lin % size.x) + min_index.x,
+              (int32_t)((lin / size.x) % size.y) + min_index.y,
+              (int32_t)(lin / ((int64_t)size.x * size.y)) + min_index.z};
+      list_push(&out, k);
+    }
+  }
+  free(grid);
+  return out;
+}
+
+static int32_t copy_out(const List* l, int32_t* out_xyz, int32_t cap) {
+  for (int32_t i = 0; i < l->n && i < cap; i++)
+    out_xyz[3 * i] = l->v[i].x, out_xyz[3 * i + 1] = l->v[i].y, out_xyz[3 * i + 2] = l->v[i].z;
+  return l->n;
+}
+
+int32_t or_view_raycast(const float* depth, int32_t rows, int32_t cols,
+                        const float* T_L_C, const OrCamera* cam, float block_size,
+                        float truncation_distance_m, const OrTsdfParams* params,
+                        int32_t* out_xyz, int32_t cap) {
+  List l = view_raycast(depth, rows, cols, T_L_C, cam, block_size, truncation_distance_m, params);
+  int32_t n = copy_out(&l, out_xyz, cap);
+  list_free(&l);
+  return n;
+}
+
+/* ------------------------------------------------------------------------- */
+/* TSDF                                                                      */
+/* ------------------------------------------------------------------------- */
+
+/* WeightingFunction (integrators/internal/impl/weighting_function_impl.h:20-117). */
+static float w_dropoff(float measured, float voxel_depth, float trunc) {
+  if (trunc <= 1e-2f) return 0.0f;
+  if (voxel_depth > measured) {
+    const float behind = voxel_depth - measured;
+    if (behind > trunc) return 0.0f;
+    return (trunc - behind) / trunc;
+  }
+  return 1.0f;
+}
+static float w_inverse_square(float measured, float voxel_depth, float trunc) {
+  if (voxel_depth <= 1e-2f) return 1.0f;
+  if (voxel_depth - measured >= trunc) return 0.0f;
+  return 1.0f / (voxel_depth * voxel_depth);
+}
+static float w_tsdf_penalty(float measured, float voxel_depth, float trunc) {
+  const float d = measured - voxel_depth;
+  if (fabsf(d) >= trunc) return 0.1f;
+  return 1.0f;
+}
+static float weighting(int type, float measured, float voxel_depth, float trunc) {
+  switch (type) {
+    case OR_WEIGHT_CONSTANT:
+      return 1.0f;
+    case OR_WEIGHT_CONSTANT_DROPOFF:
+      return 1.0f * w_dropoff(measured, voxel_depth, trunc);
+    case OR_WEIGHT_INVERSE_SQUARE:
+      return w_inverse_square(measured, voxel_depth, trunc);
+    case OR_WEIGHT_INVERSE_SQUARE_DROPOFF:
+      return w_inverse_square(measured, voxel_depth, trunc) * w_dropoff(measured, voxel_depth, trunc);
+    case OR_WEIGHT_INVERSE_SQUARE_TSDF_DISTANCE_PENALTY:
+      return w_inverse_square(measured, voxel_depth, trunc) * w_tsdf_penalty(measured, voxel_depth, trunc);
+    case OR_WEIGHT_LINEAR_WITH_MAX:
+      return (voxel_depth > 1.0f) ? 1.0f / voxel_depth : 1.0f;
+    default:
+      abort();
+  }
+}
+
+/* UpdateTsdfVoxelFunctor::operator() (integrators/internal/cuda/impl/
+ * projective_tsdf_integrator_impl.cuh:30-90). */
+static void tsdf_update_voxel(float surface_depth, float voxel_depth, int is_active,
+                              float trunc, float max_weight, float decay, int wtype,
+                              OrTsdfVoxel* v) {
+  if (surface_depth <= 0.0f) {
+    if (decay >= 0.0f) v->weight = v->weight * decay;
+    return;
+  }
+  const float sdf = surface_depth - voxel_depth;
+  if (sdf < -trunc) return;
+  if (!is_active && sdf < trunc) return;
+  const float dist_cur = v->distance, w_cur = v->weight;
+  const float w = weighting(wtype, surface_depth, voxel_depth, trunc);
+  float fused = (sdf * w + dist_cur * w_cur) / (w + w_cur);
+  if (fused > 0.0f) {
+    fused = fminf(trunc, fused);
+  } else {
+    fused = fmaxf(-trunc, fused);
+  }
+  const float weight = fminf(w + w_cur, max_weight);
+  v->distance = fused;
+  v->weight = weight;
+}
+
+/* integrateBlocksKernel for one block (integrators/internal/cuda/impl/
+ * projective_integrator_impl.cuh:59-114, projective_integrators_common_impl.cuh:21-55,
+ * interpolation/internal/impl/interpolation_2d_impl.h:99-150,
+ * sensors/internal/impl/image_impl.h:250-259). */
+static void tsdf_integrate_block(OrTsdfVoxel* blk, i3 bi, const float* depth,
+                                 const uint8_t* mask, int mask_mode, int rows, int cols,
+                                 const float* T_C_L, const OrCamera* cam, float block_size,
+                                 float trunc, const OrTsdfParams* P) {
+  const float voxel_size = block_size * (1.0f / VPS);      /* indexing_impl.h:26-29 */
+  const float half_voxel = block_size * (0.5f / VPS);      /* indexing_impl.h:75-77 */
+  const float max_depth = P->max_integration_distance_m;
+  for (int vx = 0; vx < VPS; vx++)
+    for (int vy = 0; vy < VPS; vy++)
+      for (int vz = 0; vz < VPS; vz++) {
+        /* getCenterPositionFromBlockIndexAndVoxelIndex (indexing_impl.h:51-81) */
+        v3 p_L;
+        p_L.x = (block_size * (float)bi.x + voxel_size * (float)vx) + half_voxel;
+        p_L.y = (block_size * (float)bi.y + voxel_size * (float)vy) + half_voxel;
+        p_L.z = (block_size * (float)bi.z + voxel_size * (float)vz) + half_voxel;
+        const v3 p_C = transform_point(T_C_L, p_L);
+        float u, v;
+        if (!cam_project(cam, p_C, &u, &v)) continue;
+        const float voxel_depth = p_C.z;
+        if (max_depth > 0.0f && voxel_depth > max_depth) continue;
+        /* interpolate2DClosest<float, PixelAlwaysValid> */
+        const int ux = f2i(floorf(u)), uy = f2i(floorf(v));
+        if (ux < 0 || uy < 0 || ux >= cols || uy >= rows) continue;
+        float d = depth[(size_t)uy * cols + ux];
+        /* PixelIsValidDepth (interpolation_2d_impl.h:99-104) */
+        if (!(isfinite(d) && d > 1e-6f)) d = 0.0f;
+        /* MaskedImageView::isMasked (image_impl.h:250-259) */
+        int is_active = 1;
+        if (mask != NULL) {
+          const uint8_t mv = mask[(size_t)uy * cols + ux];
+          is_active = (mask_mode == OR_MASK_NON_INVERTED) ? (mv != 0) : (mv == 0);
+        }
+        tsdf_update_voxel(d, voxel_depth, is_active, trunc, P->max_weight,
+                          P->invalid_depth_decay_factor, P->weighting_type,
+                          &blk[(vx * VPS + vy) * VPS + vz]);
+      }
+}
+
+static void tsdf_integrate_list(OrMap* map, const List* blocks, const float* depth,
+                                const uint8_t* mask, int mask_mode, int rows, int cols,
+                                const float* T_L_C, const OrCamera* cam,
+                                const OrTsdfParams* P) {
+  const float trunc = P->truncation_distance_vox * map->voxel_size;
+  /* allocateBlocksWhereRequired (integrators/internal/impl/integrators_common_impl.h:52-58) */
+  int32_t* slots = (int32_t*)malloc(sizeof(int32_t) * (size_t)(blocks->n + 1));
+  for (int32_t i = 0; i < blocks->n; i++) slots[i] = layer_allocate(&map->tsdf, blocks->v[i]);
+  float T_C_L[16];
+  invert_isometry(T_L_C, T_C_L); /* projective_integrator_impl.cuh:268 */
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < blocks->n; i++) {
+    tsdf_integrate_block((OrTsdfVoxel*)layer_block(&map->tsdf, slots[i]), blocks->v[i], depth,
+                         mask, mask_mode, rows, cols, T_C_L, cam, map->block_size, trunc, P);
+  }
+  free(slots);
+}
+
+/* ProjectiveIntegrator::integrateFrameTemplate (projective_integrator_impl.cuh:211-275). */
+int32_t or_tsdf_integrate(OrMap* map, const float* depth, const uint8_t* mask,
+                          int32_t mask_mode, int32_t rows, int32_t cols,
+                          const float* T_L_C, const OrCamera* cam,
+                          const OrTsdfParams* P, int32_t* out_xyz, int32_t cap) {
+  const float trunc = P->truncation_distance_vox * map->voxel_size;
+  List blocks = view_raycast(depth, rows, cols, T_L_C, cam, map->block_size, trunc, P);
+  if (blocks.n == 0) {
+    list_free(&blocks);
+    return 0;
+  }
+  tsdf_integrate_list(map, &blocks, depth, mask, mask_mode, rows, cols, T_L_C, cam, P);
+  int32_t n = copy_out(&blocks, out_xyz, cap);
+  list_free(&blocks);
+  return n;
+}
+
+void or_tsdf_integrate_blocks(OrMap* map, const float* depth, const uint8_t* mask,
+                              int32_t mask_mode, int32_t rows, int32_t cols,
+                              const float* T_L_C, const OrCamera* cam,
+                              const OrTsdfParams* P, const int32_t* blocks_xyz,
+                              int32_t num_blocks) {
+  List l = {0};
+  for (int32_t i = 0; i < num_blocks; i++) {
+    i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], blocks_xyz[3 * i + 2]};
+    list_push(&l, k);
+  }
+  tsdf_integrate_list(map, &l, depth, mask, mask_mode, rows, cols, T_L_C, cam, P);
+  list_free(&l);
+}
+
+/* ------------------------------------------------------------------------- */
+/* ESDF (src/integrators/esdf_integrator.cu)                                 */
+/* ------------------------------------------------------------------------- */
+
+#define EV(blk, x, y, z) (&(blk)[((x) * VPS + (y)) * VPS + (z)])
+
+static void esdf_clear_voxel(OrEsdfVoxel* v, float max_sq) { /* :152-157 */
+  v->parent_direction[0] = v->parent_direction[1] = v->parent_direction[2] = 0;
+  v->squared_distance_vox = max_sq;
+  v->is_site = 0;
+}
+
+/* updateEsdfVoxelToChanges with TsdfSiteFunctor (:113-138, :401-458). */
+static void esdf_update_voxel_to_changes(const OrTsdfVoxel* t, float min_weight,
+                                         float max_site_distance_m, float max_sq,
+                                         OrEsdfVoxel* e, int* cleared, int* updated) {
+  const int is_observed = t->weight >= min_weight;
+  if (is_observed) {
+    const int is_inside = t->distance <= 0.0f; /* no freespace layer */
+    const int is_site = is_inside && (fabsf(t->distance) <= max_site_distance_m);
+    if (e->is_inside && !is_inside) {
+      esdf_clear_voxel(e, max_sq);
+      *cleared = 1;
+    }
+    e->is_inside = (uint8_t)is_inside;
+    if (is_site) {
+      if (e->is_site) {
+        *updated = 1;
+      } else {
+        e->is_site = 1;
+        e->squared_distance_vox = 0.0f;
+        e->parent_direction[0] = e->parent_direction[1] = e->parent_direction[2] = 0;
+        *updated = 1;
+      }
+    } else {
+      if (e->is_site) {
+        esdf_clear_voxel(e, max_sq);
+        *cleared = 1;
+      } else if (!e->observed) {
+        esdf_clear_voxel(e, max_sq);
+      } else if ((double)e->squared_distance_vox <= 1e-4) { /* double literal, as in :447 */
+        esdf_clear_voxel(e, max_sq);
+        *cleared = 1;
+      }
+    }
+    e->observed = 1;
+  } else {
+    esdf_clear_voxel(e, max_sq);
+    *cleared = 1;
+    e->observed = 0;
+  }
+}
+
+/* sweepSingleBand (:542-600): forward then backward pass along one line. */
+static void esdf_sweep_line(OrEsdfVoxel* blk, int vi[3], int axis, float max_sq) {
+  for (int pass = 0; pass < 2; pass++) {
+    int last_site[3] = {0, 0, 0};
+    int site_found = 0;
+    const int direction = pass ? -1 : 1;
+    const int start = pass ? VPS - 1 : 0;
+    const int end = pass ? -1 : VPS;
+    for (vi[axis] = start; vi[axis] != end; vi[axis] += direction) {
+      OrEsdfVoxel* e = EV(blk, vi[0], vi[1], vi[2]);
+      if (!e->observed) continue;
+      if (e->is_site) {
+        last_site[0] = vi[0], last_site[1] = vi[1], last_site[2] = vi[2];
+        site_found = 1;
+      } else if (!site_found) {
+        if (e->squared_distance_vox < max_sq) {
+          site_found = 1;
+          for (int k = 0; k < 3; k++) last_site[k] = e->parent_direction[k] + vi[k];
+        }
+      } else {
+        int pd[3];
+        for (int k = 0; k < 3; k++) pd[k] = last_site[k] - vi[k];
+        /* Vector3i::squaredNorm() -> int, then converted to float. */
+        const float pdist = (float)(pd[0] * pd[0] + (pd[1] * pd[1] + pd[2] * pd[2]));
+        if (e->squared_distance_vox > pdist) {
+          for (int k = 0; k < 3; k++) e->parent_direction[k] = pd[k];
+          e->squared_distance_vox = pdist;
+        } else if (e->squared_distance_vox < max_sq) {
+          for (int k = 0; k < 3; k++) last_site[k] = e->parent_direction[k] + vi[k];
+        }
+      }
+    }
+  }
+}
+
+/* sweepBlockBandKernel (:1390-1431): x lines, then y lines, then z lines. */
+static void esdf_sweep_block(OrEsdfVoxel* blk, float max_sq) {
+  for (int axis = 0; axis < 3; axis++)
+    for (int a = 0; a < VPS; a++)
+      for (int b = 0; b < VPS; b++) {
+        int vi[3];
+        if (axis == 0) vi[0] = 0, vi[1] = a, vi[2] = b;
+        else if (axis == 1) vi[0] = a, vi[1] = 0, vi[2] = b;
+        else vi[0] = a, vi[1] = b, vi[2] = 0;
+        esdf_sweep_line(blk, vi, axis, max_sq);
+      }
+}
+
+static void esdf_sweep_list(OrMap* map, const List* l, float max_sq) {
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < l->n; i++) {
+    const int32_t s = hash_find(&map->esdf.hash, l->v[i]);
+    if (s < 0) continue;
+    esdf_sweep_block((OrEsdfVoxel*)layer_block(&map->esdf, s), max_sq);
+  }
+  map->stats[5] += l->n;
+}
+
+/* updateSingleNeighbor (:602-633). */
+static int esdf_update_single_neighbor(const OrEsdfVoxel* e, OrEsdfVoxel* n, int axis,
+                                       int direction, float max_sq) {
+  if (!e->observed || !n->observed || n->is_site || e->squared_distance_vox >= max_sq) return 0;
+  int pd[3] = {e->parent_direction[0], e->parent_direction[1], e->parent_direction[2]};
+  pd[axis] -= direction;
+  const float pdist = (float)(pd[0] * pd[0] + (pd[1] * pd[1] + pd[2] * pd[2]));
+  if (n->squared_distance_vox > pdist) {
+    n->parent_direction[0] = pd[0], n->parent_direction[1] = pd[1], n->parent_direction[2] = pd[2];
+    n->squared_distance_vox = pdist;
+    return 1;
+  }
+  return 0;
+}
+
+/* updateNeighborBands (:1323-1386): six sequential passes over the whole list
+ * (+x,-x,+y,-y,+z,-z; getDirectionAndVoxelIndicesFromThread :1062-1091), each
+ * seeing the writes of the previous ones; then sort-unique of the touched
+ * neighbours. */
+static List esdf_update_neighbor_bands(OrMap* map, const List* l, float max_sq) {
+  List out = {0};
+  uint8_t* flag = (uint8_t*)malloc((size_t)l->n + 1);
+  for (int i = 0; i < 6; i++) {
+    const int axis = i / 2, direction = (i % 2) ? -1 : 1;
+    memset(flag, 0, (size_t)l->n + 1);
+#pragma omp parallel for schedule(static)
+    for (int32_t b = 0; b < l->n; b++) {
+      const int32_t s = hash_find(&map->esdf.hash, l->v[b]);
+      i3 nk = l->v[b];
+      if (axis == 0) nk.x += direction;
+      else if (axis == 1) nk.y += direction;
+      else nk.z += direction;
+      const int32_t ns = hash_find(&map->esdf.hash, nk);
+      if (s < 0 || ns < 0) continue;
+      const OrEsdfVoxel* blk = (const OrEsdfVoxel*)layer_block(&map->esdf, s);
+      OrEsdfVoxel* nblk = (OrEsdfVoxel*)layer_block(&map->esdf, ns);
+      int any = 0;
+      for (int tx = 0; tx < VPS; tx++)
+        for (int ty = 0; ty < VPS; ty++) {
+          int vi[3], ni[3];
+          if (axis == 0) vi[0] = 0, vi[1] = tx, vi[2] = ty;
+          else if (axis == 1) vi[0] = tx, vi[1] = 0, vi[2] = ty;
+          else vi[0] = tx, vi[1] = ty, vi[2] = 0;
+          ni[0] = vi[0], ni[1] = vi[1], ni[2] = vi[2];
+          if (direction < 0) vi[axis] = 0, ni[axis] = VPS - 1;
+          else vi[axis] = VPS - 1, ni[axis] = 0;
+          any |= esdf_update_single_neighbor(EV(blk, vi[0], vi[1], vi[2]),
+                                             EV(nblk, ni[0], ni[1], ni[2]), axis, direction, max_sq);
+        }
+      flag[b] = (uint8_t)any;
+    }
+    for (int32_t b = 0; b < l->n; b++)
+      if (flag[b]) {
+        i3 nk = l->v[b];
+        if (axis == 0) nk.x += direction;
+        else if (axis == 1) nk.y += direction;
+        else nk.z += direction;
+        list_push(&out, nk);
+      }
+    map->stats[6] += l->n;
+  }
+  free(flag);
+  list_sort_unique(&out);
+  return out;
+}
+
+/* computeEsdf (:1465-1496). */
+static void esdf_compute(OrMap* map, const List* blocks_with_sites, float max_sq) {
+  if (blocks_with_sites->n == 0) return;
+  List cur = {0};
+  for (int32_t i = 0; i < blocks_with_sites->n; i++) list_push(&cur, blocks_with_sites->v[i]);
+  esdf_sweep_list(map, &cur, max_sq);
+  while (cur.n > 0) {
+    List upd = esdf_update_neighbor_bands(map, &cur, max_sq);
+    esdf_sweep_list(map, &upd, max_sq);
+    list_free(&cur);
+    cur = upd;
+    map->stats[7]++;
+  }
+  list_free(&cur);
+}
+
+/* getBlockAndVoxelIndexFromOffset (:1498-1520): C++ '/' and '%' truncate. */
+static void block_and_voxel_from_offset(i3 bi, const int vi[3], const int32_t off[3],
+                                        i3* nb, int nv[3]) {
+  int32_t b[3] = {bi.x, bi.y, bi.z};
+  for (int i = 0; i < 3; i++) {
+    b[i] = b[i] + off[i] / VPS;
+    nv[i] = vi[i] + off[i] % VPS;
+    if (nv[i] >= VPS) {
+      nv[i] -= VPS;
+      b[i]++;
+    } else if (nv[i] < 0) {
+      nv[i] += VPS;
+      b[i]--;
+    }
+  }
+  nb->x = b[0], nb->y = b[1], nb->z = b[2];
+}
+
+/* clearAllInvalid + clearAllInvalidKernel (:1522-1647); candidate selection by
+ * getBlocksWithinRadiusOfAABB (src/geometry/bounding_spheres.cpp:76-91),
+ * getAABBOfBlocks (src/geometry/bounding_boxes.cpp:20-27). */
+static void esdf_clear_all_invalid(OrMap* map, const List* to_clear, float max_esdf_distance_m,
+                                   float max_sq, List* cleared_out) {
+  if (to_clear->n == 0) return;
+  const float bs = map->block_size;
+  /* Merged AABB of the to-clear blocks. */
+  float amin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, amax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int32_t i = 0; i < to_clear->n; i++) {
+    const int32_t k[3] = {to_clear->v[i].x, to_clear->v[i].y, to_clear->v[i].z};
+    for (int a = 0; a < 3; a++) {
+      const float lo = (float)k[a] * bs, hi = ((float)k[a] + 1.0f) * bs;
+      amin[a] = (lo < amin[a]) ? lo : amin[a];
+      amax[a] = (amax[a] < hi) ? hi : amax[a];
+    }
+  }
+  cleared_out->n = 0; /* resizeAsync + overwrite */
+  const int32_t nb = map->esdf.n;
+  uint8_t* flag = (uint8_t*)calloc((size_t)nb + 1, 1);
+  int64_t candidates = 0;
+#pragma omp parallel for schedule(static) reduction(+ : candidates)
+  for (int32_t s = 0; s < nb; s++) {
+    const i3 bi = map->esdf.index[s];
+    const int32_t k[3] = {bi.x, bi.y, bi.z};
+    /* AlignedBox::exteriorDistance = sqrt(squaredExteriorDistance) */
+    float d2 = 0.0f;
+    for (int a = 0; a < 3; a++) {
+      const float lo = (float)k[a] * bs, hi = ((float)k[a] + 1.0f) * bs;
+      if (amin[a] > hi) {
+        const float aux = amin[a] - hi;
+        d2 += aux * aux;
+      } else if (lo > amax[a]) {
+        const float aux = lo - amax[a];
+        d2 += aux * aux;
+      }
+    }
+    if (sqrtf(d2) > max_esdf_distance_m) continue;
+    candidates++;
+    OrEsdfVoxel* blk = (OrEsdfVoxel*)layer_block(&map->esdf, s);
+    int any = 0;
+    for (int x = 0; x < VPS; x++)
+      for (int y = 0; y < VPS; y++)
+        for (int z = 0; z < VPS; z++) {
+          OrEsdfVoxel* e = EV(blk, x, y, z);
+          const int32_t* pd = e->parent_direction;
+          if (e->observed && !e->is_site && (pd[0] != 0 || pd[1] != 0 || pd[2] != 0)) {
+            const int vi[3] = {x, y, z};
+            i3 nbk;
+            int nv[3];
+            block_and_voxel_from_offset(bi, vi, pd, &nbk, nv);
+            const OrEsdfVoxel* parent = NULL;
+            if (nbk.x == bi.x && nbk.y == bi.y && nbk.z == bi.z) {
+              parent = EV(blk, nv[0], nv[1], nv[2]);
+            } else {
+              const int32_t ps = hash_find(&map->esdf.hash, nbk);
+              if (ps >= 0) parent = EV((const OrEsdfVoxel*)layer_block(&map->esdf, ps), nv[0], nv[1], nv[2]);
+            }
+            /* is_site is never written by this kernel, so reading it from another
+             * block while that block is being processed is race-free. */
+            if (parent == NULL || !parent->is_site) {
+              e->parent_direction[0] = e->parent_direction[1] = e->parent_direction[2] = 0;
+              e->squared_distance_vox = max_sq;
+              any = 1;
+            }
+          }
+        }
+    flag[s] = (uint8_t)any;
+  }
+  for (int32_t s = 0; s < nb; s++)
+    if (flag[s]) list_push(cleared_out, map->esdf.index[s]);
+  free(flag);
+  map->stats[3] += candidates;
+}
+
+/* EsdfIntegrator::integrateBlocksTemplate<TsdfLayer> (:220-260) with
+ * markAllSites (:678-747) / markAllSitesKernel (:467-540). */
+void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,
+                       const OrEsdfParams* P) {
+  memset(map->stats, 0, sizeof(map->stats));
+  if (num_blocks == 0) return;
+  /* allocateBlocksOnCPU (:391-397) */
+  List blocks = {0};
+  for (int32_t i = 0; i < num_blocks; i++) {
+    i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], blocks_xyz[3 * i + 2]};
+    list_push(&blocks, k);
+    layer_allocate(&map->esdf, k);
+  }
+  /* Real callers pass a set (Mapper::getBlocksToUpdate, src/mapper/mapper.cpp:523-537);
+   * a duplicated entry would make two CTAs race on one block in the reference. */
+  list_sort_unique(&blocks);
+  num_blocks = blocks.n;
+  /* :693-696 */
+  const float max_esdf_distance_vox = P->max_esdf_distance_m / map->voxel_size;
+  const float max_sq = max_esdf_distance_vox * max_esdf_distance_vox;
+  const float max_site_distance_m = P->max_site_distance_vox * map->voxel_size; /* :672-676 */
+
+  uint8_t* upd = (uint8_t*)calloc((size_t)num_blocks, 1);
+  uint8_t* clr = (uint8_t*)calloc((size_t)num_blocks, 1);
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < num_blocks; i++) {
+    const int32_t ts = hash_find(&map->tsdf.hash, blocks.v[i]);
+    const int32_t es = hash_find(&map->esdf.hash, blocks.v[i]);
+    if (ts < 0 || es < 0) continue;
+    const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(&map->tsdf, ts);
+    OrEsdfVoxel* e = (OrEsdfVoxel*)layer_block(&map->esdf, es);
+    int cleared = 0, updated = 0;
+    for (int v = 0; v < VPB; v++)
+      esdf_update_voxel_to_changes(&t[v], P->min_weight, max_site_distance_m, max_sq, &e[v],
+                                   &cleared, &updated);
+    upd[i] = (uint8_t)updated, clr[i] = (uint8_t)cleared;
+  }
+  List updated = {0}, to_clear = {0};
+  for (int32_t i = 0; i < num_blocks; i++) {
+    if (upd[i]) list_push(&updated, blocks.v[i]);
+    if (clr[i]) list_push(&to_clear, blocks.v[i]);
+  }
+  free(upd), free(clr);
+  map->stats[0] = num_blocks, map->stats[1] = updated.n, map->stats[2] = to_clear.n;
+
+  if (to_clear.n > 0) {
+    esdf_clear_all_invalid(map, &to_clear, P->max_esdf_distance_m, max_sq,
+                           &map->esdf_cleared_persistent);
+  }
+  map->stats[4] = map->esdf_cleared_persistent.n;
+  esdf_compute(map, &updated, max_sq);
+  if (map->esdf_cleared_persistent.n > 0) esdf_compute(map, &map->esdf_cleared_persistent, max_sq);
+  list_free(&blocks), list_free(&updated), list_free(&to_clear);
+}
+
+void or_esdf_last_stats(const OrMap* map, int64_t out[8]) { memcpy(out, map->stats, sizeof(map->stats)); }
+
+/* ------------------------------------------------------------------------- */
+/* Read-back                                                                 */
+/* ------------------------------------------------------------------------- */
+
+int32_t or_tsdf_num_blocks(const OrMap* m) { return m->tsdf.n; }
+int32_t or_esdf_num_blocks(const OrMap* m) { return m->esdf.n; }
+static int32_t layer_indices(const Layer* l, int32_t* out, int32_t cap) {
+  for (int32_t i = 0; i < l->n && i < cap; i++)
+    out[3 * i] = l->index[i].x, out[3 * i + 1] = l->index[i].y, out[3 * i + 2] = l->index[i].z;
+  return l->n;
+}
+int32_t or_tsdf_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->tsdf, out, cap); }
+int32_t or_esdf_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->esdf, out, cap); }
+int32_t or_tsdf_get_block(const OrMap* m, const int32_t xyz[3], OrTsdfVoxel* out) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = hash_find(&m->tsdf.hash, k);
+  if (s < 0) return 0;
+  memcpy(out, layer_block(&m->tsdf, s), m->tsdf.block_bytes);
+  return 1;
+}
+int32_t or_esdf_get_block(const OrMap* m, const int32_t xyz[3], OrEsdfVoxel* out) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = hash_find(&m->esdf.hash, k);
+  if (s < 0) return 0;
+  memcpy(out, layer_block(&m->esdf, s), m->esdf.block_bytes);
+  return 1;
+}
+void or_tsdf_set_block(OrMap* m, const int32_t xyz[3], const OrTsdfVoxel* in) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = layer_allocate(&m->tsdf, k);
+  memcpy(layer_block(&m->tsdf, s), in, m->tsdf.block_bytes);
+}
+
+int32_t or_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void or_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

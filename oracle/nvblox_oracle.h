@@ -1,0 +1,151 @@
+/*
+ * nvblox_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C CPU restatement of the nvblox_core depth-integration hot path
+ * (view raycast -> projective TSDF integration -> incremental ESDF), written
+ * from the reference's behaviour (file:line citations are on every function in
+ * nvblox_oracle.c; paths are relative to
+ * /root/reference/nvblox_ros/nvblox_core/nvblox/).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library. The product path
+ * (isaac_ros_nvblox_b200/) never does.
+ *
+ * Parity status: the reference cannot be built here (Eigen/stdgpu/glog/... are
+ * un-vendored network fetches and there is no GPU), so this oracle is pinned
+ * against the reference's own known-answer tests (tests/test_oracle_kat.py)
+ * and NOT against a reference binary.
+ *
+ * Arithmetic: IEEE binary32, one rounding per operation, no FMA contraction
+ * (compile with -ffp-contract=off). 3-term sums use Eigen's unrolled
+ * reduction order a0 + (a1 + a2). float->int casts follow the CUDA device
+ * semantics (NaN -> 0, saturating), because the reference runs these casts on
+ * the GPU.
+ */
+#ifndef NVBLOX_ORACLE_H_
+#define NVBLOX_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Pinhole camera. (include/nvblox/sensors/camera.h:193-203, no distortion) */
+typedef struct {
+  float fu, fv, cu, cv;
+  int32_t width, height;
+} OrCamera;
+
+/* Weighting modes (include/nvblox/integrators/weighting_function.h:11-18). */
+enum {
+  OR_WEIGHT_CONSTANT = 0,
+  OR_WEIGHT_CONSTANT_DROPOFF = 1,
+  OR_WEIGHT_INVERSE_SQUARE = 2,
+  OR_WEIGHT_INVERSE_SQUARE_DROPOFF = 3,
+  OR_WEIGHT_INVERSE_SQUARE_TSDF_DISTANCE_PENALTY = 4,
+  OR_WEIGHT_LINEAR_WITH_MAX = 5
+};
+
+/* Workspace bounds (include/nvblox/geometry/workspace_bounds.h:24). */
+enum { OR_WS_UNBOUNDED = 0, OR_WS_HEIGHT_BOUNDS = 1, OR_WS_BOUNDING_BOX = 2 };
+
+/* Mask modes (include/nvblox/sensors/image.h:383). */
+enum { OR_MASK_NON_INVERTED = 0, OR_MASK_INVERTED = 1 };
+
+typedef struct {
+  float truncation_distance_vox;    /* default 4   */
+  float max_integration_distance_m; /* default 7   */
+  float max_weight;                 /* default 5   */
+  float invalid_depth_decay_factor; /* default -1  */
+  int32_t weighting_type;           /* default OR_WEIGHT_INVERSE_SQUARE */
+  int32_t raycast_subsampling;      /* default 4   */
+  int32_t workspace_bounds_type;    /* default OR_WS_UNBOUNDED */
+  float workspace_min[3];
+  float workspace_max[3];
+} OrTsdfParams;
+
+typedef struct {
+  float max_esdf_distance_m;   /* default 2    */
+  float max_site_distance_vox; /* default 1    */
+  float min_weight;            /* default 1e-4 */
+} OrEsdfParams;
+
+/* Voxel layouts = the reference's (include/nvblox/map/voxels.h:28-74). */
+typedef struct {
+  float distance;
+  float weight;
+} OrTsdfVoxel; /* 8 B */
+
+typedef struct {
+  float squared_distance_vox;
+  int32_t parent_direction[3];
+  uint8_t is_inside, observed, is_site, pad_;
+} OrEsdfVoxel; /* 20 B */
+
+typedef struct OrMap OrMap;
+
+void or_default_tsdf_params(OrTsdfParams* p);
+void or_default_esdf_params(OrEsdfParams* p);
+
+OrMap* or_map_create(float voxel_size_m);
+void or_map_destroy(OrMap* map);
+void or_map_clear(OrMap* map);
+
+/* RayCaster (rays/internal/impl/ray_caster_impl.h:26-90). Returns the number
+ * of cells, writing up to cap triples to out_xyz. */
+int32_t or_raycast_cells(const float origin[3], const float dest[3], float scale,
+                         int32_t* out_xyz, int32_t cap);
+
+/* ViewCalculator::getBlocksInImageViewRaycast (view_calculator_impl.cuh:117-198).
+ * T_L_C: 4x4 column-major (Eigen Isometry3f::data()). Returns count (x-fastest
+ * order inside the view AABB), writes up to cap triples. */
+int32_t or_view_raycast(const float* depth, int32_t rows, int32_t cols,
+                        const float* T_L_C, const OrCamera* cam, float block_size,
+                        float truncation_distance_m, const OrTsdfParams* params,
+                        int32_t* out_xyz, int32_t cap);
+
+/* ProjectiveTsdfIntegrator::integrateFrame. mask may be NULL. Returns the
+ * number of updated blocks (== raycast blocks), writes up to cap triples. */
+int32_t or_tsdf_integrate(OrMap* map, const float* depth, const uint8_t* mask,
+                          int32_t mask_mode, int32_t rows, int32_t cols,
+                          const float* T_L_C, const OrCamera* cam,
+                          const OrTsdfParams* params, int32_t* out_xyz,
+                          int32_t cap);
+
+/* Same update but on a caller-given block list (bench split timing). */
+void or_tsdf_integrate_blocks(OrMap* map, const float* depth, const uint8_t* mask,
+                              int32_t mask_mode, int32_t rows, int32_t cols,
+                              const float* T_L_C, const OrCamera* cam,
+                              const OrTsdfParams* params, const int32_t* blocks_xyz,
+                              int32_t num_blocks);
+
+/* EsdfIntegrator::integrateBlocks(TsdfLayer, blocks, EsdfLayer*). */
+void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,
+                       const OrEsdfParams* params);
+
+/* Statistics of the last or_esdf_integrate call: [0] blocks marked, [1] blocks
+ * with sites, [2] blocks to clear, [3] candidate blocks scanned by the clear
+ * pass, [4] blocks cleared, [5] total swept blocks, [6] total (block,direction)
+ * face passes, [7] rings. */
+void or_esdf_last_stats(const OrMap* map, int64_t out[8]);
+
+/* Read-back. */
+int32_t or_tsdf_num_blocks(const OrMap* map);
+int32_t or_esdf_num_blocks(const OrMap* map);
+int32_t or_tsdf_block_indices(const OrMap* map, int32_t* out_xyz, int32_t cap);
+int32_t or_esdf_block_indices(const OrMap* map, int32_t* out_xyz, int32_t cap);
+/* Copies the 512 voxels of a block ([x][y][z] order). Returns 0 if absent. */
+int32_t or_tsdf_get_block(const OrMap* map, const int32_t xyz[3], OrTsdfVoxel* out);
+int32_t or_esdf_get_block(const OrMap* map, const int32_t xyz[3], OrEsdfVoxel* out);
+/* Test helper: overwrite / create a TSDF block. */
+void or_tsdf_set_block(OrMap* map, const int32_t xyz[3], const OrTsdfVoxel* in);
+
+/* Number of OpenMP threads the oracle will use (1 if built without OpenMP). */
+int32_t or_num_threads(void);
+void or_set_num_threads(int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVBLOX_ORACLE_H_ */

@@ -1,0 +1,263 @@
+"""ctypes loader for the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module (see oracle/nvblox_oracle.h).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libnvblox_oracle.so")
+
+TSDF_VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4")])
+ESDF_VOXEL_DTYPE = np.dtype(
+    [
+        ("squared_distance_vox", "<f4"),
+        ("parent_direction", "<i4", (3,)),
+        ("is_inside", "u1"),
+        ("observed", "u1"),
+        ("is_site", "u1"),
+        ("pad", "u1"),
+    ]
+)
+assert TSDF_VOXEL_DTYPE.itemsize == 8 and ESDF_VOXEL_DTYPE.itemsize == 20
+
+WEIGHT_CONSTANT = 0
+WEIGHT_CONSTANT_DROPOFF = 1
+WEIGHT_INVERSE_SQUARE = 2
+WEIGHT_INVERSE_SQUARE_DROPOFF = 3
+WEIGHT_INVERSE_SQUARE_TSDF_DISTANCE_PENALTY = 4
+WEIGHT_LINEAR_WITH_MAX = 5
+
+
+class Camera(C.Structure):
+    _fields_ = [("fu", C.c_float), ("fv", C.c_float), ("cu", C.c_float), ("cv", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class TsdfParams(C.Structure):
+    _fields_ = [("truncation_distance_vox", C.c_float),
+                ("max_integration_distance_m", C.c_float),
+                ("max_weight", C.c_float),
+                ("invalid_depth_decay_factor", C.c_float),
+                ("weighting_type", C.c_int32),
+                ("raycast_subsampling", C.c_int32),
+                ("workspace_bounds_type", C.c_int32),
+                ("workspace_min", C.c_float * 3),
+                ("workspace_max", C.c_float * 3)]
+
+
+class EsdfParams(C.Structure):
+    _fields_ = [("max_esdf_distance_m", C.c_float),
+                ("max_site_distance_vox", C.c_float),
+                ("min_weight", C.c_float)]
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
+    if force or not os.path.exists(_LIB_PATH) or (
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "nvblox_oracle.c"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB_PATH)
+    fp = C.POINTER(C.c_float)
+    ip = C.POINTER(C.c_int32)
+    u8p = C.POINTER(C.c_uint8)
+    vp = C.c_void_p
+    L.or_default_tsdf_params.argtypes = [C.POINTER(TsdfParams)]
+    L.or_default_esdf_params.argtypes = [C.POINTER(EsdfParams)]
+    L.or_map_create.argtypes = [C.c_float]
+    L.or_map_create.restype = vp
+    L.or_map_destroy.argtypes = [vp]
+    L.or_map_clear.argtypes = [vp]
+    L.or_raycast_cells.argtypes = [fp, fp, C.c_float, ip, C.c_int32]
+    L.or_raycast_cells.restype = C.c_int32
+    L.or_view_raycast.argtypes = [fp, C.c_int32, C.c_int32, fp, C.POINTER(Camera), C.c_float,
+                                  C.c_float, C.POINTER(TsdfParams), ip, C.c_int32]
+    L.or_view_raycast.restype = C.c_int32
+    L.or_tsdf_integrate.argtypes = [vp, fp, u8p, C.c_int32, C.c_int32, C.c_int32, fp,
+                                    C.POINTER(Camera), C.POINTER(TsdfParams), ip, C.c_int32]
+    L.or_tsdf_integrate.restype = C.c_int32
+    L.or_tsdf_integrate_blocks.argtypes = [vp, fp, u8p, C.c_int32, C.c_int32, C.c_int32, fp,
+                                           C.POINTER(Camera), C.POINTER(TsdfParams), ip, C.c_int32]
+    L.or_esdf_integrate.argtypes = [vp, ip, C.c_int32, C.POINTER(EsdfParams)]
+    L.or_esdf_last_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    for name in ("or_tsdf_num_blocks", "or_esdf_num_blocks"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = C.c_int32
+    for name in ("or_tsdf_block_indices", "or_esdf_block_indices"):
+        getattr(L, name).argtypes = [vp, ip, C.c_int32]
+        getattr(L, name).restype = C.c_int32
+    L.or_tsdf_get_block.argtypes = [vp, ip, vp]
+    L.or_tsdf_get_block.restype = C.c_int32
+    L.or_esdf_get_block.argtypes = [vp, ip, vp]
+    L.or_esdf_get_block.restype = C.c_int32
+    L.or_tsdf_set_block.argtypes = [vp, ip, vp]
+    L.or_num_threads.restype = C.c_int32
+    L.or_set_num_threads.argtypes = [C.c_int32]
+    _lib = L
+    return L
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def colmajor(T):
+    """4x4 numpy transform -> 16 float32 in Eigen (column-major) order."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T).reshape(16)
+
+
+def default_tsdf_params(**kw):
+    p = TsdfParams()
+    lib().or_default_tsdf_params(C.byref(p))
+    for k, v in kw.items():
+        if k in ("workspace_min", "workspace_max"):
+            setattr(p, k, (C.c_float * 3)(*v))
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def default_esdf_params(**kw):
+    p = EsdfParams()
+    lib().or_default_esdf_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def raycast_cells(origin, dest, scale=1.0, cap=1 << 16):
+    o = np.asarray(origin, dtype=np.float32)
+    d = np.asarray(dest, dtype=np.float32)
+    out = np.zeros((cap, 3), dtype=np.int32)
+    n = lib().or_raycast_cells(_fp(o), _fp(d), scale, _ip(out), cap)
+    return out[:n].copy()
+
+
+def view_raycast(depth, T_L_C, cam, block_size, truncation_distance_m, params=None, cap=1 << 20):
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    params = params or default_tsdf_params()
+    T = colmajor(T_L_C)
+    out = np.zeros((cap, 3), dtype=np.int32)
+    n = lib().or_view_raycast(_fp(depth), depth.shape[0], depth.shape[1], _fp(T), C.byref(cam),
+                              block_size, truncation_distance_m, C.byref(params), _ip(out), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+class OracleMap:
+    """One TSDF layer + one ESDF layer + the EsdfIntegrator's carried-over state."""
+
+    def __init__(self, voxel_size):
+        self.voxel_size = float(voxel_size)
+        self._h = lib().or_map_create(voxel_size)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().or_map_destroy(self._h)
+            self._h = None
+
+    def clear(self):
+        lib().or_map_clear(self._h)
+
+    def integrate_depth(self, depth, T_L_C, cam, params=None, mask=None, mask_mode=0, cap=1 << 20):
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        params = params or default_tsdf_params()
+        T = colmajor(T_L_C)
+        out = np.zeros((cap, 3), dtype=np.int32)
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            mp = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+        n = lib().or_tsdf_integrate(self._h, _fp(depth), mp, mask_mode, depth.shape[0],
+                                    depth.shape[1], _fp(T), C.byref(cam), C.byref(params),
+                                    _ip(out), cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def integrate_depth_blocks(self, depth, T_L_C, cam, blocks, params=None, mask=None, mask_mode=0):
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        params = params or default_tsdf_params()
+        T = colmajor(T_L_C)
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            mp = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+        lib().or_tsdf_integrate_blocks(self._h, _fp(depth), mp, mask_mode, depth.shape[0],
+                                       depth.shape[1], _fp(T), C.byref(cam), C.byref(params),
+                                       _ip(blocks), blocks.shape[0])
+
+    def integrate_esdf(self, blocks, params=None):
+        params = params or default_esdf_params()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        lib().or_esdf_integrate(self._h, _ip(blocks), blocks.shape[0], C.byref(params))
+
+    def esdf_stats(self):
+        out = (C.c_int64 * 8)()
+        lib().or_esdf_last_stats(self._h, out)
+        keys = ("marked", "with_sites", "to_clear", "clear_candidates", "cleared", "swept",
+                "face_passes", "rings")
+        return dict(zip(keys, list(out)))
+
+    def tsdf_block_indices(self):
+        n = lib().or_tsdf_num_blocks(self._h)
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        lib().or_tsdf_block_indices(self._h, _ip(out), n)
+        return out[:n].copy()
+
+    def esdf_block_indices(self):
+        n = lib().or_esdf_num_blocks(self._h)
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        lib().or_esdf_block_indices(self._h, _ip(out), n)
+        return out[:n].copy()
+
+    def tsdf_block(self, idx):
+        k = np.asarray(idx, dtype=np.int32)
+        out = np.zeros((8, 8, 8), dtype=TSDF_VOXEL_DTYPE)
+        ok = lib().or_tsdf_get_block(self._h, _ip(k), out.ctypes.data)
+        return out if ok else None
+
+    def esdf_block(self, idx):
+        k = np.asarray(idx, dtype=np.int32)
+        out = np.zeros((8, 8, 8), dtype=ESDF_VOXEL_DTYPE)
+        ok = lib().or_esdf_get_block(self._h, _ip(k), out.ctypes.data)
+        return out if ok else None
+
+    def set_tsdf_block(self, idx, voxels):
+        k = np.asarray(idx, dtype=np.int32)
+        v = np.ascontiguousarray(voxels, dtype=TSDF_VOXEL_DTYPE).reshape(8, 8, 8)
+        lib().or_tsdf_set_block(self._h, _ip(k), v.ctypes.data)
+
+    def tsdf_layer(self):
+        """{(x,y,z): (8,8,8) structured array} for every allocated TSDF block."""
+        return {tuple(int(c) for c in k): self.tsdf_block(k) for k in self.tsdf_block_indices()}
+
+    def esdf_layer(self):
+        return {tuple(int(c) for c in k): self.esdf_block(k) for k in self.esdf_block_indices()}
+
+
+def num_threads():
+    return lib().or_num_threads()
+
+
+def set_num_threads(n):
+    lib().or_set_num_threads(int(n))
