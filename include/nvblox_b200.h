@@ -206,6 +206,9 @@ NVB_API int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xy
 /* cudaStreamSynchronize on the mapper's stream + deferred error check. */
 NVB_API int32_t nvb_mapper_synchronize(NvbMapper* m);
 NVB_API int32_t nvb_mapper_last_frame_block_count(NvbMapper* m, int32_t* out_count);
+/* `updated_blocks` of the most recent frame again (e.g. after a too-small buffer). */
+NVB_API int32_t nvb_mapper_last_frame_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_t cap,
+                                             int32_t* out_count);
 /* The CUDA stream (cudaStream_t) all of the mapper's work is enqueued on
  * (Mapper's shared CudaStream, src/mapper/mapper.cpp:28-46). */
 NVB_API void* nvb_mapper_stream(NvbMapper* m);

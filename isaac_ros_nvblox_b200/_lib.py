@@ -1,0 +1,137 @@
+"""ctypes binding of the C-ABI (include/nvblox_b200.h -> libnvblox_b200.so).
+
+The product path has no CPU fallback: if the CUDA library is missing this module
+raises at load() time, and nvb_mapper_create fails with NVB_ERR_NO_DEVICE when no
+GPU is visible.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnvblox_b200.so")
+
+NVB_OK = 0
+NVB_MEM_HOST, NVB_MEM_DEVICE = 0, 1
+NVB_LAYER_TSDF, NVB_LAYER_ESDF = 0, 1
+
+# Every symbol include/nvblox_b200.h declares (checked by tests/test_cabi_symbols.py).
+EXPORTED_SYMBOLS = [
+    "nvb_last_error", "nvb_version", "nvb_device_count",
+    "nvb_default_mapper_options", "nvb_default_tsdf_params", "nvb_default_esdf_params",
+    "nvb_mapper_create", "nvb_mapper_destroy", "nvb_mapper_clear",
+    "nvb_mapper_set_tsdf_params", "nvb_mapper_get_tsdf_params",
+    "nvb_mapper_set_esdf_params", "nvb_mapper_get_esdf_params",
+    "nvb_mapper_voxel_size", "nvb_mapper_block_size",
+    "nvb_view_raycast", "nvb_mapper_integrate_depth", "nvb_mapper_integrate_depth_async",
+    "nvb_mapper_update_esdf", "nvb_mapper_update_esdf_async", "nvb_esdf_integrate_blocks",
+    "nvb_mapper_synchronize", "nvb_mapper_last_frame_block_count", "nvb_mapper_last_frame_blocks",
+    "nvb_mapper_stream",
+    "nvb_layer_num_blocks", "nvb_layer_block_indices", "nvb_layer_get_blocks",
+    "nvb_layer_set_blocks", "nvb_layer_block_device_ptr", "nvb_layer_block_bytes",
+    "nvb_mapper_last_esdf_stats", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
+    "nvb_mapper_kernel_launches",
+]
+
+
+class NvbCamera(C.Structure):
+    _fields_ = [("fu", C.c_float), ("fv", C.c_float), ("cu", C.c_float), ("cv", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class NvbTsdfParams(C.Structure):
+    _fields_ = [("truncation_distance_vox", C.c_float),
+                ("max_integration_distance_m", C.c_float),
+                ("max_weight", C.c_float),
+                ("invalid_depth_decay_factor", C.c_float),
+                ("weighting_type", C.c_int32),
+                ("raycast_subsampling", C.c_int32),
+                ("workspace_bounds_type", C.c_int32),
+                ("workspace_min", C.c_float * 3),
+                ("workspace_max", C.c_float * 3)]
+
+
+class NvbEsdfParams(C.Structure):
+    _fields_ = [("max_esdf_distance_m", C.c_float),
+                ("max_site_distance_vox", C.c_float),
+                ("min_weight", C.c_float)]
+
+
+class NvbMapperOptions(C.Structure):
+    _fields_ = [("voxel_size_m", C.c_float), ("device", C.c_int32),
+                ("tsdf_capacity_blocks", C.c_int32), ("esdf_capacity_blocks", C.c_int32),
+                ("esdf_persistent", C.c_int32)]
+
+
+class NvbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("nvblox_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libnvblox_b200.so (build it first with build_ext.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for the depth-integration path." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    fp, ip, u8p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    L.nvb_last_error.restype = C.c_char_p
+    L.nvb_version.restype = C.c_char_p
+    L.nvb_device_count.restype = i32
+    L.nvb_default_mapper_options.argtypes = [C.POINTER(NvbMapperOptions)]
+    L.nvb_default_tsdf_params.argtypes = [C.POINTER(NvbTsdfParams)]
+    L.nvb_default_esdf_params.argtypes = [C.POINTER(NvbEsdfParams)]
+    L.nvb_mapper_create.argtypes = [C.POINTER(NvbMapperOptions), C.POINTER(vp)]
+    L.nvb_mapper_create.restype = i32
+    L.nvb_mapper_destroy.argtypes = [vp]
+    L.nvb_mapper_destroy.restype = None
+    L.nvb_mapper_clear.argtypes = [vp]
+    L.nvb_mapper_set_tsdf_params.argtypes = [vp, C.POINTER(NvbTsdfParams)]
+    L.nvb_mapper_get_tsdf_params.argtypes = [vp, C.POINTER(NvbTsdfParams)]
+    L.nvb_mapper_set_esdf_params.argtypes = [vp, C.POINTER(NvbEsdfParams)]
+    L.nvb_mapper_get_esdf_params.argtypes = [vp, C.POINTER(NvbEsdfParams)]
+    L.nvb_mapper_voxel_size.argtypes = [vp]
+    L.nvb_mapper_voxel_size.restype = f32
+    L.nvb_mapper_block_size.argtypes = [vp]
+    L.nvb_mapper_block_size.restype = f32
+    L.nvb_view_raycast.argtypes = [vp, vp, i32, i32, i32, fp, C.POINTER(NvbCamera), f32, f32, f32, ip, i32, ip]
+    L.nvb_mapper_integrate_depth.argtypes = [vp, vp, vp, i32, i32, i32, i32, fp, C.POINTER(NvbCamera), ip, i32, ip]
+    L.nvb_mapper_integrate_depth_async.argtypes = [vp, vp, vp, i32, i32, i32, i32, fp, C.POINTER(NvbCamera)]
+    L.nvb_mapper_update_esdf.argtypes = [vp, i32]
+    L.nvb_mapper_update_esdf_async.argtypes = [vp, i32]
+    L.nvb_esdf_integrate_blocks.argtypes = [vp, ip, i32]
+    L.nvb_mapper_synchronize.argtypes = [vp]
+    L.nvb_mapper_last_frame_block_count.argtypes = [vp, ip]
+    L.nvb_mapper_last_frame_blocks.argtypes = [vp, ip, i32, ip]
+    L.nvb_mapper_stream.argtypes = [vp]
+    L.nvb_mapper_stream.restype = vp
+    L.nvb_layer_num_blocks.argtypes = [vp, i32, ip]
+    L.nvb_layer_block_indices.argtypes = [vp, i32, ip, i32, ip]
+    L.nvb_layer_get_blocks.argtypes = [vp, i32, ip, i32, vp, u8p]
+    L.nvb_layer_set_blocks.argtypes = [vp, i32, ip, i32, vp]
+    L.nvb_layer_block_device_ptr.argtypes = [vp, i32, ip, C.POINTER(vp)]
+    L.nvb_layer_block_bytes.argtypes = [i32]
+    L.nvb_mapper_last_esdf_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.nvb_mapper_enable_profiling.argtypes = [vp, i32]
+    L.nvb_mapper_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
+    L.nvb_mapper_kernel_launches.argtypes = [vp]
+    L.nvb_mapper_kernel_launches.restype = C.c_int64
+    for name in EXPORTED_SYMBOLS:
+        f = getattr(L, name)
+        if f.restype is C.c_int and name not in ("nvb_device_count", "nvb_layer_block_bytes"):
+            f.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != NVB_OK:
+        raise NvbError(rc, load().nvb_last_error().decode("utf-8", "replace"))

@@ -887,6 +887,12 @@ int32_t nvb_mapper_last_frame_block_count(NvbMapper* m, int32_t* out_count) {
   return readFrameList(m, nullptr, 0, out_count);
 }
 
+int32_t nvb_mapper_last_frame_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_t cap, int32_t* out_count) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  return readFrameList(m, out_xyz_host, cap, out_count);
+}
+
 void* nvb_mapper_stream(NvbMapper* m) { return m ? (void*)m->stream : nullptr; }
 
 static DevLayer* layerOf(NvbMapper* m, int layer) {

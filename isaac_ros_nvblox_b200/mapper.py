@@ -1,0 +1,370 @@
+"""Host-side mirror of nvblox::Mapper for the depth-integration path.
+
+Same names and argument meaning as the reference's C++ classes, restricted to this
+path (nvblox/include/nvblox/mapper/mapper.h:107-836):
+    Mapper(voxel_size_m)                       mapper.h:119-124
+    Mapper.integrate_depth(depth, T_L_C, cam)  mapper.h:167-172  (integrateDepth)
+    Mapper.update_esdf()                       mapper.h:326      (updateEsdf)
+    Mapper.tsdf_layer() / esdf_layer()         mapper.h:372,393
+    Mapper.tsdf_integrator() / esdf_integrator()  parameter setters
+    ViewCalculator.get_blocks_in_image_view_raycast  view_calculator.h:75-80
+Everything forwards to the C-ABI in libnvblox_b200.so through ctypes; numpy arrays
+are host buffers, integers are raw device pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import NvbCamera, NvbEsdfParams, NvbMapperOptions, NvbTsdfParams, check
+
+TSDF_VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4")])
+ESDF_VOXEL_DTYPE = np.dtype(
+    [("squared_distance_vox", "<f4"), ("parent_direction", "<i4", (3,)),
+     ("is_inside", "u1"), ("observed", "u1"), ("is_site", "u1"), ("pad", "u1")])
+
+STAGE_NAMES = ("view_calculator/raycast", "tsdf/integrate/allocate_blocks", "tsdf/integrate/update_blocks",
+               "esdf/integrate/mark_sites", "esdf/integrate/clear", "esdf/integrate/compute")
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def colmajor(T):
+    """4x4 transform -> 16 float32 in Eigen::Isometry3f::data() (column-major) order."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T).reshape(16)
+
+
+class Camera:
+    """nvblox::Camera(fu, fv, cu, cv, width, height) (sensors/camera.h:33-203), no distortion."""
+
+    def __init__(self, fu, fv, cu, cv, width, height):
+        self.c = NvbCamera(float(fu), float(fv), float(cu), float(cv), int(width), int(height))
+
+    fu = property(lambda s: s.c.fu)
+    fv = property(lambda s: s.c.fv)
+    cu = property(lambda s: s.c.cu)
+    cv = property(lambda s: s.c.cv)
+    width = property(lambda s: s.c.width)
+    height = property(lambda s: s.c.height)
+
+
+class _Layer:
+    """BlockLayer queries (map/layer.h:76-311) answered from the device-resident map."""
+
+    def __init__(self, mapper, layer_id, dtype):
+        self._m, self._id, self._dtype = mapper, layer_id, dtype
+
+    def num_blocks(self):
+        n = C.c_int32(0)
+        check(self._m._L.nvb_layer_num_blocks(self._m._h, self._id, C.byref(n)))
+        return n.value
+
+    def get_all_block_indices(self):
+        n = self.num_blocks()
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        cnt = C.c_int32(0)
+        check(self._m._L.nvb_layer_block_indices(self._m._h, self._id, _ip(out), n, C.byref(cnt)))
+        return out[:n].copy()
+
+    def get_blocks(self, indices):
+        """(n,3) int32 -> ((n,8,8,8) voxel array, (n,) found mask)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        n = idx.shape[0]
+        out = np.zeros((max(n, 1), 8, 8, 8), dtype=self._dtype)
+        found = np.zeros(max(n, 1), dtype=np.uint8)
+        check(self._m._L.nvb_layer_get_blocks(self._m._h, self._id, _ip(idx), n, out.ctypes.data,
+                                              found.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out[:n], found[:n].astype(bool)
+
+    def get_block_at_index(self, index):
+        v, f = self.get_blocks(np.asarray(index, dtype=np.int32).reshape(1, 3))
+        return v[0] if f[0] else None
+
+    def is_block_allocated(self, index):
+        return self.get_block_at_index(index) is not None
+
+    def set_blocks(self, indices, voxels):
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        v = np.ascontiguousarray(voxels, dtype=self._dtype).reshape(idx.shape[0], 8, 8, 8)
+        check(self._m._L.nvb_layer_set_blocks(self._m._h, self._id, _ip(idx), idx.shape[0], v.ctypes.data))
+
+    def block_device_ptr(self, index):
+        k = np.asarray(index, dtype=np.int32)
+        p = C.c_void_p(0)
+        check(self._m._L.nvb_layer_block_device_ptr(self._m._h, self._id, _ip(k), C.byref(p)))
+        return p.value or 0
+
+    def as_dict(self):
+        idx = self.get_all_block_indices()
+        if len(idx) == 0:
+            return {}
+        v, _ = self.get_blocks(idx)
+        return {tuple(int(c) for c in k): v[i] for i, k in enumerate(idx)}
+
+
+class _TsdfIntegrator:
+    """ProjectiveTsdfIntegrator parameter surface (projective_tsdf_integrator.h:59-121,
+    projective_integrator.h:56-85, view_calculator.h:88-145)."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def _get(self):
+        p = NvbTsdfParams()
+        check(self._m._L.nvb_mapper_get_tsdf_params(self._m._h, C.byref(p)))
+        return p
+
+    def _set(self, **kw):
+        p = self._get()
+        for k, v in kw.items():
+            if k in ("workspace_min", "workspace_max"):
+                setattr(p, k, (C.c_float * 3)(*v))
+            else:
+                setattr(p, k, v)
+        check(self._m._L.nvb_mapper_set_tsdf_params(self._m._h, C.byref(p)))
+
+    def params(self, **kw):
+        if kw:
+            self._set(**kw)
+        return self._get()
+
+    def truncation_distance_vox(self, v=None):
+        if v is not None:
+            self._set(truncation_distance_vox=float(v))
+        return self._get().truncation_distance_vox
+
+    def max_integration_distance_m(self, v=None):
+        if v is not None:
+            self._set(max_integration_distance_m=float(v))
+        return self._get().max_integration_distance_m
+
+    def max_weight(self, v=None):
+        if v is not None:
+            self._set(max_weight=float(v))
+        return self._get().max_weight
+
+    def invalid_depth_decay_factor(self, v=None):
+        if v is not None:
+            self._set(invalid_depth_decay_factor=float(v))
+        return self._get().invalid_depth_decay_factor
+
+    def weighting_function_type(self, v=None):
+        if v is not None:
+            self._set(weighting_type=int(v))
+        return self._get().weighting_type
+
+    def raycast_subsampling_factor(self, v=None):
+        if v is not None:
+            self._set(raycast_subsampling=int(v))
+        return self._get().raycast_subsampling
+
+
+class _EsdfIntegrator:
+    """EsdfIntegrator parameter surface (esdf_integrator.h:178-283) + integrateBlocks."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def _get(self):
+        p = NvbEsdfParams()
+        check(self._m._L.nvb_mapper_get_esdf_params(self._m._h, C.byref(p)))
+        return p
+
+    def params(self, **kw):
+        p = self._get()
+        for k, v in kw.items():
+            setattr(p, k, v)
+        if kw:
+            check(self._m._L.nvb_mapper_set_esdf_params(self._m._h, C.byref(p)))
+        return p
+
+    def max_esdf_distance_m(self, v=None):
+        return self.params(**({} if v is None else {"max_esdf_distance_m": float(v)})).max_esdf_distance_m
+
+    def max_site_distance_vox(self, v=None):
+        return self.params(**({} if v is None else {"max_site_distance_vox": float(v)})).max_site_distance_vox
+
+    def min_weight(self, v=None):
+        return self.params(**({} if v is None else {"min_weight": float(v)})).min_weight
+
+    def integrate_blocks(self, block_indices):
+        """EsdfIntegrator::integrateBlocks(tsdf_layer, block_indices, esdf_layer)."""
+        idx = np.ascontiguousarray(block_indices, dtype=np.int32).reshape(-1, 3)
+        check(self._m._L.nvb_esdf_integrate_blocks(self._m._h, _ip(idx), idx.shape[0]))
+
+    def last_stats(self):
+        out = (C.c_int64 * 8)()
+        check(self._m._L.nvb_mapper_last_esdf_stats(self._m._h, out))
+        keys = ("marked", "with_sites", "to_clear", "clear_candidates", "cleared", "swept", "face_passes", "rings")
+        return dict(zip(keys, list(out)))
+
+
+class Mapper:
+    """nvblox::Mapper(voxel_size_m, ...) with a TSDF and an ESDF layer."""
+
+    def __init__(self, voxel_size_m, device=0, tsdf_capacity_blocks=0, esdf_capacity_blocks=0,
+                 esdf_persistent=True):
+        self._L = _lib.load()
+        o = NvbMapperOptions()
+        self._L.nvb_default_mapper_options(C.byref(o))
+        o.voxel_size_m = float(voxel_size_m)
+        o.device = int(device)
+        if tsdf_capacity_blocks:
+            o.tsdf_capacity_blocks = int(tsdf_capacity_blocks)
+        if esdf_capacity_blocks:
+            o.esdf_capacity_blocks = int(esdf_capacity_blocks)
+        o.esdf_persistent = 1 if esdf_persistent else 0
+        h = C.c_void_p(0)
+        check(self._L.nvb_mapper_create(C.byref(o), C.byref(h)))
+        self._h = h
+        self._tsdf = _Layer(self, _lib.NVB_LAYER_TSDF, TSDF_VOXEL_DTYPE)
+        self._esdf = _Layer(self, _lib.NVB_LAYER_ESDF, ESDF_VOXEL_DTYPE)
+        self._keep = []  # host buffers of in-flight async frames
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.nvb_mapper_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- accessors -------------------------------------------------------
+    def voxel_size(self):
+        return self._L.nvb_mapper_voxel_size(self._h)
+
+    def block_size(self):
+        return self._L.nvb_mapper_block_size(self._h)
+
+    def tsdf_layer(self):
+        return self._tsdf
+
+    def esdf_layer(self):
+        return self._esdf
+
+    def tsdf_integrator(self):
+        return _TsdfIntegrator(self)
+
+    def esdf_integrator(self):
+        return _EsdfIntegrator(self)
+
+    def cuda_stream(self):
+        return self._L.nvb_mapper_stream(self._h)
+
+    def clear(self):
+        check(self._L.nvb_mapper_clear(self._h))
+
+    # --- the hot path ----------------------------------------------------
+    @staticmethod
+    def _frame_args(depth, mask):
+        if isinstance(depth, (int, np.integer)):
+            raise TypeError("pass device frames through integrate_depth_device")
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        return d, mk
+
+    def integrate_depth(self, depth, T_L_C, camera, mask=None, mask_mode=0, return_blocks=True):
+        """Mapper::integrateDepth. depth: (rows, cols) float32 host array. Returns updated_blocks (n,3)."""
+        d, mk = self._frame_args(depth, mask)
+        T = colmajor(T_L_C)
+        cap = 0
+        out = None
+        if return_blocks:
+            cap = 1 << 16
+            out = np.empty((cap, 3), dtype=np.int32)
+        n = C.c_int32(0)
+        check(self._L.nvb_mapper_integrate_depth(
+            self._h, d.ctypes.data, None if mk is None else mk.ctypes.data, mask_mode, _lib.NVB_MEM_HOST,
+            d.shape[0], d.shape[1], _fp(T), C.byref(camera.c), None if out is None else _ip(out), cap,
+            C.byref(n)))
+        if out is not None and n.value > cap:
+            # list longer than the buffer: the frame IS integrated; read the full list back
+            cap = n.value
+            out = np.empty((cap, 3), dtype=np.int32)
+            check(self._L.nvb_mapper_last_frame_blocks(self._h, _ip(out), cap, C.byref(n)))
+        return None if out is None else out[:n.value].copy()
+
+    def integrate_depth_device(self, depth_ptr, rows, cols, T_L_C, camera, mask_ptr=0, mask_mode=0, sync=False):
+        """Same, for a frame already resident in HBM (raw device pointers). Asynchronous unless sync."""
+        T = colmajor(T_L_C)
+        check(self._L.nvb_mapper_integrate_depth_async(self._h, depth_ptr, mask_ptr or None, mask_mode,
+                                                       _lib.NVB_MEM_DEVICE, rows, cols, _fp(T), C.byref(camera.c)))
+        if sync:
+            self.synchronize()
+
+    def integrate_depth_async(self, depth, T_L_C, camera, mask=None, mask_mode=0):
+        """Host frame, enqueued without synchronising (buffers are kept alive until synchronize())."""
+        d, mk = self._frame_args(depth, mask)
+        T = colmajor(T_L_C)
+        self._keep.append((d, mk))
+        check(self._L.nvb_mapper_integrate_depth_async(self._h, d.ctypes.data, None if mk is None else mk.ctypes.data,
+                                                       mask_mode, _lib.NVB_MEM_HOST, d.shape[0], d.shape[1], _fp(T),
+                                                       C.byref(camera.c)))
+
+    def integrate_depth_host_ptr_async(self, depth_host_ptr, rows, cols, T_L_C, camera):
+        """Host frame given as a raw (ideally pinned) pointer the caller keeps alive."""
+        T = colmajor(T_L_C)
+        check(self._L.nvb_mapper_integrate_depth_async(self._h, depth_host_ptr, None, 0, _lib.NVB_MEM_HOST, rows, cols,
+                                                       _fp(T), C.byref(camera.c)))
+
+    def update_esdf(self, update_full_layer=False, sync=True):
+        """Mapper::updateEsdf."""
+        if sync:
+            check(self._L.nvb_mapper_update_esdf(self._h, 1 if update_full_layer else 0))
+            self._keep.clear()
+        else:
+            check(self._L.nvb_mapper_update_esdf_async(self._h, 1 if update_full_layer else 0))
+
+    def synchronize(self):
+        check(self._L.nvb_mapper_synchronize(self._h))
+        self._keep.clear()
+
+    def last_frame_block_count(self):
+        n = C.c_int32(0)
+        check(self._L.nvb_mapper_last_frame_block_count(self._h, C.byref(n)))
+        return n.value
+
+    # --- instrumentation -------------------------------------------------
+    def enable_profiling(self, on=True):
+        check(self._L.nvb_mapper_enable_profiling(self._h, 1 if on else 0))
+
+    def stage_times(self, reset=False):
+        ms = (C.c_double * 6)()
+        calls = (C.c_int64 * 6)()
+        check(self._L.nvb_mapper_stage_times(self._h, ms, calls, 1 if reset else 0))
+        return {STAGE_NAMES[i]: (ms[i], calls[i]) for i in range(6)}
+
+    def kernel_launches(self):
+        return int(self._L.nvb_mapper_kernel_launches(self._h))
+
+
+class ViewCalculator:
+    """ViewCalculator::getBlocksInImageViewRaycast (view_calculator.h:75-80)."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def get_blocks_in_image_view_raycast(self, depth, T_L_C, camera, block_size,
+                                         max_integration_distance_behind_surface_m, max_integration_distance_m):
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        T = colmajor(T_L_C)
+        cap = 1 << 16
+        while True:
+            out = np.zeros((cap, 3), dtype=np.int32)
+            n = C.c_int32(0)
+            check(self._m._L.nvb_view_raycast(self._m._h, d.ctypes.data, _lib.NVB_MEM_HOST, d.shape[0], d.shape[1],
+                                              _fp(T), C.byref(camera.c), float(block_size),
+                                              float(max_integration_distance_behind_surface_m),
+                                              float(max_integration_distance_m), _ip(out), cap, C.byref(n)))
+            if n.value <= cap:
+                return out[:n.value].copy()
+            cap = n.value

@@ -1,0 +1,408 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): block-index sets/lists bit-exact; float SDF values within
+1e-4 (they are in fact bit-identical: same operation order, no FMA on either side);
+all five EsdfVoxel fields exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ESDF_FIELDS, assert_esdf_equal, assert_tsdf_equal, cameras, layer_checksum, sort_rows
+from isaac_ros_nvblox_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _nvb():
+    import isaac_ros_nvblox_b200 as nvb
+    return nvb
+
+
+def _orc():
+    from oracle import oracle as orc
+    return orc
+
+
+def _set_params(m, o_params, **kw):
+    m.tsdf_integrator().params(**kw)
+    for k, v in kw.items():
+        if k in ("workspace_min", "workspace_max"):
+            import ctypes as C
+            setattr(o_params, k, (C.c_float * 3)(*v))
+        else:
+            setattr(o_params, k, v)
+
+
+# ----------------------------------------------------------------------------------------
+# View calculation
+# ----------------------------------------------------------------------------------------
+def test_view_raycast_matches_oracle_in_content_and_order(gpu):
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras()
+    scene = syn.sphere_in_box()
+    m = nvb.Mapper(0.05)
+    vc = nvb.ViewCalculator(m)
+    for T in syn.circle_trajectory(80)[::9]:
+        depth = syn.render_depth(scene, cs, T)
+        got = vc.get_blocks_in_image_view_raycast(depth, T, cam, 0.4, 0.2, 7.0)
+        want = orc.view_raycast(depth, T, ocam, 0.4, 0.2)
+        assert len(want) > 1000
+        assert np.array_equal(got, want)
+    assert m.tsdf_layer().num_blocks() == 0  # the view calculator does not touch the map
+    m.close()
+
+
+@pytest.mark.parametrize("subsample", [1, 2, 3, 4, 7])
+def test_view_raycast_subsampling_and_frustum_kat(gpu, subsample):
+    """FrustumRayTracingSubsamplingTest.RayTracePixels (tests/test_frustum.cpp:352-416) on the GPU."""
+    nvb, orc = _nvb(), _orc()
+    m = nvb.Mapper(0.125)
+    if subsample <= 2:
+        cam, ocam = nvb.Camera(5.0, 5.0, 1.0, 1.0, 3, 3), orc.Camera(5.0, 5.0, 1.0, 1.0, 3, 3)
+        depth = np.full((3, 3), 2.5, np.float32)
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = [1, 1, 0]
+        m.tsdf_integrator().raycast_subsampling_factor(subsample)
+        got = nvb.ViewCalculator(m).get_blocks_in_image_view_raycast(depth, T, cam, 1.0, 0.0, 3.5)
+        assert len(got) == 12
+        assert set(map(tuple, got)) == {(x, y, z) for x in (0, 1) for y in (0, 1) for z in (0, 1, 2)}
+    cs, cam, ocam = cameras(320, 240)
+    depth = syn.render_depth(syn.box_with_cube(), cs, syn.circle_pose(0.7))
+    m.tsdf_integrator().raycast_subsampling_factor(subsample)
+    got = nvb.ViewCalculator(m).get_blocks_in_image_view_raycast(depth, syn.circle_pose(0.7), cam, 0.4, 0.2, 7.0)
+    want = orc.view_raycast(depth, syn.circle_pose(0.7), ocam, 0.4, 0.2, orc.default_tsdf_params(raycast_subsampling=subsample))
+    assert np.array_equal(got, want)
+    m.close()
+
+
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf, 0.0, -1.0])
+def test_view_raycast_invalid_depth(gpu, bad):
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(160, 120)
+    depth = np.full((120, 160), bad, np.float32)
+    T = syn.circle_pose(0.3)
+    m = nvb.Mapper(0.05)
+    got = nvb.ViewCalculator(m).get_blocks_in_image_view_raycast(depth, T, cam, 0.4, 0.2, 7.0)
+    want = orc.view_raycast(depth, T, ocam, 0.4, 0.2)
+    assert np.array_equal(got, want)
+    m.close()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (7, 2), (33, 17), (121, 161)])
+def test_view_raycast_ragged_images(gpu, shape):
+    nvb, orc = _nvb(), _orc()
+    h, w = shape
+    cam, ocam = nvb.Camera(40.0, 40.0, w / 2.0, h / 2.0, w, h), orc.Camera(40.0, 40.0, w / 2.0, h / 2.0, w, h)
+    rng = np.random.default_rng(h * 100 + w)
+    depth = rng.uniform(0.5, 6.0, size=shape).astype(np.float32)
+    T = syn.circle_pose(1.1)
+    m = nvb.Mapper(0.05)
+    got = nvb.ViewCalculator(m).get_blocks_in_image_view_raycast(depth, T, cam, 0.4, 0.2, 7.0)
+    want = orc.view_raycast(depth, T, ocam, 0.4, 0.2)
+    assert np.array_equal(got, want)
+    m.close()
+
+
+def test_view_raycast_workspace_bounds(gpu):
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    T = syn.circle_pose(2.0)
+    depth = syn.render_depth(syn.sphere_in_box(), cs, T)
+    for kw in (dict(workspace_bounds_type=1, workspace_min=(0, 0, 0.5), workspace_max=(0, 0, 2.5)),
+               dict(workspace_bounds_type=2, workspace_min=(-2, -2, 0), workspace_max=(3, 3, 3)),
+               dict(workspace_bounds_type=2, workspace_min=(50, 50, 50), workspace_max=(60, 60, 60))):
+        m = nvb.Mapper(0.05)
+        p = orc.default_tsdf_params()
+        _set_params(m, p, **kw)
+        got = nvb.ViewCalculator(m).get_blocks_in_image_view_raycast(depth, T, cam, 0.4, 0.2, 7.0)
+        want = orc.view_raycast(depth, T, ocam, 0.4, 0.2, p)
+        assert np.array_equal(got.reshape(-1, 3), want.reshape(-1, 3))
+        m.close()
+
+
+# ----------------------------------------------------------------------------------------
+# TSDF
+# ----------------------------------------------------------------------------------------
+def _run_pair(voxel, frames, cam, ocam, esdf=False, tsdf_kw=None, mapper_kw=None, masks=None, mask_mode=0,
+              check_every_frame=True):
+    nvb, orc = _nvb(), _orc()
+    m = nvb.Mapper(voxel, **(mapper_kw or {}))
+    o = orc.OracleMap(voxel)
+    p = orc.default_tsdf_params()
+    if tsdf_kw:
+        _set_params(m, p, **tsdf_kw)
+    for i, (depth, T) in enumerate(frames):
+        mask = None if masks is None else masks[i]
+        b_gpu = m.integrate_depth(depth, T, cam, mask=mask, mask_mode=mask_mode)
+        b_cpu = o.integrate_depth(depth, T, ocam, p, mask=mask, mask_mode=mask_mode)
+        assert np.array_equal(b_gpu, b_cpu), "updated_blocks of frame %d differ" % i
+        if esdf:
+            m.update_esdf()
+            o.integrate_esdf(b_cpu if i > 0 else o.tsdf_block_indices())
+            if check_every_frame:
+                assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+    if esdf:
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    return m, o
+
+
+def test_tsdf_sequence_640x480_5cm(gpu):
+    cs, cam, ocam = cameras()
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(80)[:6])
+    m, o = _run_pair(0.05, frames, cam, ocam)
+    assert m.tsdf_layer().num_blocks() > 3000
+    m.close()
+
+
+@pytest.mark.parametrize("wtype", [0, 1, 2, 3, 4, 5])
+def test_tsdf_all_weighting_functions(gpu, wtype):
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(40)[:3], noise_sigma_rel=0.01, seed=3)
+    m, _ = _run_pair(0.05, frames, cam, ocam, tsdf_kw=dict(weighting_type=wtype))
+    m.close()
+
+
+def test_tsdf_noise_dropout_and_decay(gpu):
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:4], noise_sigma_rel=0.01,
+                               dropout=0.13, seed=1)
+    m, _ = _run_pair(0.05, frames, cam, ocam, tsdf_kw=dict(invalid_depth_decay_factor=0.8))
+    m.close()
+
+
+@pytest.mark.parametrize("mask_mode", [0, 1])
+def test_tsdf_masked_frames(gpu, mask_mode):
+    cs, cam, ocam = cameras(320, 240)
+    seq = syn.moving_sphere_sequence(cs, syn.circle_trajectory(40)[:3])
+    frames = [(d, T) for d, T, _ in seq]
+    masks = [mk for _, _, mk in seq]
+    m, _ = _run_pair(0.05, frames, cam, ocam, masks=masks, mask_mode=mask_mode)
+    m.close()
+
+
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf, 0.0, -10.0])
+def test_tsdf_invalid_frames_integrate_nothing(gpu, bad):
+    """InvalidDepthHandling (tests/test_tsdf_integrator.cpp:588-722)."""
+    cs, cam, ocam = cameras(160, 120)
+    T = syn.circle_pose(0.0)
+    good = syn.render_depth(syn.sphere_in_box(), cs, T)
+    frames = [(good, T), (np.full_like(good, bad), T)]
+    m, o = _run_pair(0.05, frames, cam, ocam)
+    m.close()
+
+
+def test_tsdf_max_integration_distance_and_truncation(gpu):
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:2])
+    m, _ = _run_pair(0.05, frames, cam, ocam, tsdf_kw=dict(max_integration_distance_m=4.0, truncation_distance_vox=2.0,
+                                                             max_weight=100.0))
+    m.close()
+
+
+def test_tsdf_2cm_voxels(gpu):
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(80)[:2])
+    m, _ = _run_pair(0.02, frames, cam, ocam, tsdf_kw=dict(max_integration_distance_m=4.0))
+    assert m.tsdf_layer().num_blocks() > 10000
+    m.close()
+
+
+def test_layer_grows_past_initial_capacity(gpu):
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:4])
+    m, _ = _run_pair(0.05, frames, cam, ocam, esdf=True, mapper_kw=dict(tsdf_capacity_blocks=512, esdf_capacity_blocks=512),
+                     check_every_frame=False)
+    assert m.tsdf_layer().num_blocks() > 512
+    m.close()
+
+
+def test_async_frames_equal_sync_frames(gpu):
+    nvb = _nvb()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:5])
+    a, b = nvb.Mapper(0.05), nvb.Mapper(0.05)
+    for depth, T in frames:
+        a.integrate_depth(depth, T, cam)
+        a.update_esdf()
+        b.integrate_depth_async(depth, T, cam)
+        b.update_esdf(sync=False)
+    b.synchronize()
+    assert_tsdf_equal(b.tsdf_layer().as_dict(), a.tsdf_layer().as_dict())
+    assert_esdf_equal(b.esdf_layer().as_dict(), a.esdf_layer().as_dict())
+    a.close(), b.close()
+
+
+def test_clear_and_reuse(gpu):
+    nvb = _nvb()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(40)[:3])
+    m = nvb.Mapper(0.05)
+    sums = []
+    for rep in range(2):
+        for depth, T in frames:
+            m.integrate_depth(depth, T, cam)
+            m.update_esdf()
+        sums.append((layer_checksum(m.tsdf_layer().as_dict(), ("distance", "weight")),
+                     layer_checksum(m.esdf_layer().as_dict(), ESDF_FIELDS)))
+        m.clear()
+        assert m.tsdf_layer().num_blocks() == 0 and m.esdf_layer().num_blocks() == 0
+    assert sums[0] == sums[1]
+    m.close()
+
+
+def test_block_round_trip_and_device_pointers(gpu):
+    nvb = _nvb()
+    m = nvb.Mapper(0.05)
+    rng = np.random.default_rng(0)
+    idx = np.array([[0, 0, 0], [-3, 7, 2], [100000, -100000, 5], [-1, -1, -1]], np.int32)
+    vox = np.zeros((4, 8, 8, 8), nvb.TSDF_VOXEL_DTYPE)
+    vox["distance"] = rng.normal(size=(4, 8, 8, 8)).astype(np.float32)
+    vox["weight"] = rng.uniform(size=(4, 8, 8, 8)).astype(np.float32)
+    m.tsdf_layer().set_blocks(idx, vox)
+    got, found = m.tsdf_layer().get_blocks(np.vstack([idx, [[9, 9, 9]]]))
+    assert found.tolist() == [True, True, True, True, False]
+    assert np.array_equal(got[:4], vox) and not got[4]["weight"].any()
+    assert sorted(map(tuple, m.tsdf_layer().get_all_block_indices())) == sorted(map(tuple, idx))
+    p0, p1 = m.tsdf_layer().block_device_ptr(idx[0]), m.tsdf_layer().block_device_ptr(idx[1])
+    assert p0 and p1 and abs(p1 - p0) % 4096 == 0
+    assert m.tsdf_layer().block_device_ptr([9, 9, 9]) == 0
+    with pytest.raises(Exception):
+        m.tsdf_layer().set_blocks(np.array([[1 << 21, 0, 0]], np.int32), vox[:1])
+    m.close()
+
+
+# ----------------------------------------------------------------------------------------
+# ESDF
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("persistent", [True, False])
+def test_esdf_incremental_sequence(gpu, persistent):
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:5])
+    m, o = _run_pair(0.05, frames, cam, ocam, esdf=True, mapper_kw=dict(esdf_persistent=persistent))
+    s_gpu, s_cpu = m.esdf_integrator().last_stats(), o.esdf_stats()
+    for k in ("marked", "with_sites", "to_clear", "clear_candidates", "cleared", "swept", "face_passes", "rings"):
+        assert s_gpu[k] == s_cpu[k], (k, s_gpu, s_cpu)
+    m.close()
+
+
+def test_esdf_640x480_5cm_sequence(gpu):
+    cs, cam, ocam = cameras()
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(80)[:4])
+    m, o = _run_pair(0.05, frames, cam, ocam, esdf=True, check_every_frame=False)
+    m.close()
+
+
+def test_esdf_cube_scene_with_noise(gpu):
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(40)[:4], noise_sigma_rel=0.01,
+                               dropout=0.05, seed=5)
+    m, _ = _run_pair(0.05, frames, cam, ocam, esdf=True)
+    m.close()
+
+
+def test_esdf_explicit_block_lists_and_params(gpu):
+    """EsdfIntegrator::integrateBlocks on caller lists, non-default parameters, duplicate and
+    unallocated indices, empty list."""
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:3])
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    ep = orc.default_esdf_params(max_esdf_distance_m=1.0, max_site_distance_vox=1.5, min_weight=0.01)
+    m.esdf_integrator().params(max_esdf_distance_m=1.0, max_site_distance_vox=1.5, min_weight=0.01)
+    m.esdf_integrator().integrate_blocks(np.zeros((0, 3), np.int32))  # no-op
+    for depth, T in frames:
+        b = m.integrate_depth(depth, T, cam)
+        o.integrate_depth(depth, T, ocam)
+        lst = np.vstack([b, b[:10], [[500, 500, 500]]]).astype(np.int32)  # duplicates + a block without TSDF
+        m.esdf_integrator().integrate_blocks(lst)
+        o.integrate_esdf(lst, ep)
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    m.close()
+
+
+def test_esdf_update_without_new_frames_changes_nothing(gpu):
+    nvb = _nvb()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:2])
+    m = nvb.Mapper(0.05)
+    for depth, T in frames:
+        m.integrate_depth(depth, T, cam)
+        m.update_esdf()
+    before = layer_checksum(m.esdf_layer().as_dict(), ESDF_FIELDS)
+    m.update_esdf()  # tracker is empty: Mapper::updateEsdf hands an empty list -> early return
+    assert layer_checksum(m.esdf_layer().as_dict(), ESDF_FIELDS) == before
+    m.close()
+
+
+def test_esdf_full_layer_update(gpu):
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(40)[:3])
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    for depth, T in frames:
+        m.integrate_depth(depth, T, cam)
+        o.integrate_depth(depth, T, ocam)
+    m.update_esdf()  # first query of the tracker = all blocks
+    o.integrate_esdf(o.tsdf_block_indices())
+    assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    m.update_esdf(update_full_layer=True)
+    o.integrate_esdf(o.tsdf_block_indices())
+    assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    m.close()
+
+
+# ----------------------------------------------------------------------------------------
+# Golden fixtures + size-independent properties at full size
+# ----------------------------------------------------------------------------------------
+def test_golden_fixture(gpu):
+    """tests/golden/c2_small.npz was produced by the oracle (tests/golden/make_golden.py)."""
+    nvb = _nvb()
+    g = np.load(os.path.join(GOLDEN, "c2_small.npz"))
+    cam = nvb.Camera(*[float(v) for v in g["cam"][:4]], int(g["cam"][4]), int(g["cam"][5]))
+    m = nvb.Mapper(float(g["voxel_size"]))
+    for i in range(len(g["depth"])):
+        b = m.integrate_depth(g["depth"][i], g["poses"][i], cam)
+        assert np.array_equal(b, g["blocks_%d" % i])
+        m.update_esdf()
+    assert layer_checksum(m.tsdf_layer().as_dict(), ("distance", "weight")) == int(g["tsdf_checksum"])
+    assert layer_checksum(m.esdf_layer().as_dict(), ESDF_FIELDS) == int(g["esdf_checksum"])
+    m.close()
+
+
+def test_full_sequence_properties(gpu):
+    """80-frame C2 sequence at full size (too long for the oracle in a unit test): properties only."""
+    nvb = _nvb()
+    cs, cam, ocam = cameras()
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(80)[::4])
+    m = nvb.Mapper(0.05)
+    seen = set()
+    for depth, T in frames:
+        b = m.integrate_depth(depth, T, cam)
+        assert len({tuple(r) for r in b}) == len(b)  # unique
+        seen |= {tuple(r) for r in b}
+        m.update_esdf()
+    tsdf = m.tsdf_layer().as_dict()
+    esdf = m.esdf_layer().as_dict()
+    assert set(tsdf) == seen == set(esdf)  # allocated blocks = union of updated_blocks
+    max_sq = (2.0 / 0.05) ** 2
+    for k, blk in esdf.items():
+        obs = blk["observed"].astype(bool)
+        site = blk["is_site"].astype(bool)
+        assert not (site & ~obs).any()
+        assert np.all(blk["squared_distance_vox"][site] == 0)
+        p = blk["parent_direction"].astype(np.int64)
+        has_parent = obs & ~site & (p != 0).any(axis=-1)
+        sq = (p * p).sum(-1).astype(np.float32)
+        assert np.array_equal(blk["squared_distance_vox"][has_parent], sq[has_parent])  # sq == |parent|^2
+        t = tsdf[k]
+        assert np.all(np.abs(t["distance"]) <= 0.2 + 1e-6) and np.all(t["weight"] <= 5.0)
+        # observed <=> tsdf weight >= min_weight, inside <=> distance <= 0 (TsdfSiteFunctor)
+        assert np.array_equal(obs, t["weight"] >= np.float32(1e-4))
+        assert np.array_equal(blk["is_inside"].astype(bool) & obs, (t["distance"] <= 0) & obs)
+        assert np.all(blk["squared_distance_vox"][obs] <= np.float32(max_sq))
+    m.close()
