@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- depth-frames/s of the depth-integration hot path (TSDF + ESDF every frame).
+
+One step = one pass of the hot path over one batch of synthetic input: the 80-frame
+"Replica-shape" sequence C2 of SURVEY.md 8(d) (sphere-in-box room, circular trajectory,
+640x480 depth, 5 cm voxels) integrated into an empty map: per frame
+    Mapper::integrateDepth  (view raycast -> block compaction/allocation -> TSDF update)
+    Mapper::updateEsdf      (allocate/mark -> clear -> wavefront)
+`value`  : frames/s with the depth frames already resident in HBM, device-timed (CUDA events
+           on the mapper's stream), max over ranks.
+`e2e`    : the same sequence through the synchronous reference-facing calls with HOST depth
+           buffers (H2D of every frame and D2H of every frame's updated_blocks inside the
+           timed region).
+Weak scaling: every rank owns one camera stream and one map replica; the only exchange is
+the NCCL merge of the ranks' updated-block lists (isaac_ros_nvblox_b200/multi_gpu.py).
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOXEL = 0.05
+ROWS, COLS = 480, 640
+METRIC = "depth-frames/sec (TSDF+ESDF integrate, 640x480 @ 5 cm voxels)"
+WORKLOAD = ("C2 Replica-shape synthetic sequence: sphere-in-box room, 80-pose circle r=4 m h=2 m, "
+            "640x480 depth, 5 cm voxels, TSDF+ESDF every frame, empty map at step start")
+
+
+def make_frames(num_frames, rank, world):
+    from isaac_ros_nvblox_b200 import synthetic as syn
+    cam = syn.PinholeCamera()
+    # every rank is its own camera stream: same circle, phase-shifted start
+    poses = syn.circle_trajectory(80, yaw_offset=0.0)
+    shift = (rank * 80) // max(world, 1)
+    poses = (poses[shift:] + poses[:shift])[:num_frames]
+    return cam, syn.make_sequence(syn.sphere_in_box(), cam, poses)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(frames_np, cam_s, sample_frames):
+    """The reference's algorithm on the host cores (oracle port, OpenMP where the reference's kernels
+    are race-free): TSDF + ESDF on the first `sample_frames` frames of the same sequence."""
+    from oracle import oracle as orc
+    ocam = orc.Camera(cam_s.fu, cam_s.fv, cam_s.cu, cam_s.cv, cam_s.width, cam_s.height)
+    o = orc.OracleMap(VOXEL)
+    t0 = time.perf_counter()
+    for depth, T in frames_np[:sample_frames]:
+        b = o.integrate_depth(depth, T, ocam)
+        o.integrate_esdf(b)
+    dt = time.perf_counter() - t0
+    return {"value": sample_frames / dt, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": "first %d frames of the same sequence (raycast+TSDF+ESDF), %.1f s" % (sample_frames, dt)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cam_s, frames = make_frames(args.cpu_sample_frames, 0, 1)
+    from oracle import oracle as orc
+    ocam = orc.Camera(cam_s.fu, cam_s.fv, cam_s.cu, cam_s.cv, cam_s.width, cam_s.height)
+
+    def step():
+        o = orc.OracleMap(VOXEL)
+        for depth, T in frames:
+            o.integrate_esdf(o.integrate_depth(depth, T, ocam))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * len(frames) / dt
+    sample = "each step = first %d frames of the sequence on the host cores" % len(frames)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": len(frames)},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=80)
+    ap.add_argument("--cpu-sample-frames", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--esdf-host-loop", action="store_true", help="reference-like per-ring launches")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    import isaac_ros_nvblox_b200 as nvb
+    from isaac_ros_nvblox_b200 import multi_gpu
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the depth-integration path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cam_s, frames = make_frames(args.frames, rank, world)
+    cam = nvb.Camera(cam_s.fu, cam_s.fv, cam_s.cu, cam_s.cv, cam_s.width, cam_s.height)
+    F = len(frames)
+    depth_host = torch.from_numpy(np.stack([d for d, _ in frames])).pin_memory()
+    depth_dev = depth_host.cuda(non_blocking=False)
+    poses = [T for _, T in frames]
+
+    m = nvb.Mapper(VOXEL, device=local_rank, esdf_persistent=not args.esdf_host_loop)
+    stream = torch.cuda.ExternalStream(m.cuda_stream(), device=torch.device("cuda", local_rank))
+    frame_bytes = ROWS * COLS * 4
+
+    def step_device():
+        m.clear()
+        for i in range(F):
+            m.integrate_depth_device(depth_dev[i].data_ptr(), ROWS, COLS, poses[i], cam)
+            m.update_esdf(sync=False)
+        if world > 1:
+            multi_gpu.merge_updated_blocks(m, stream)
+
+    def step_e2e():
+        m.clear()
+        d2h = 0
+        for i in range(F):
+            b = m.integrate_depth(frames[i][0], poses[i], cam)  # host in, updated_blocks out, synchronous
+            m.update_esdf()
+            d2h += b.nbytes
+        return d2h
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    m.synchronize()
+    launches0 = m.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    m.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = m.kernel_launches() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * F * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the synchronous reference-facing calls, host buffers ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        d2h = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * F * args.steps / float(te.item())
+
+    # ---- per-stage device time + algorithmic bytes for the roofline (rank 0, one extra step) ----
+    roofline, stages_out, map_stats = None, None, None
+    if rank == 0:
+        m.clear()
+        m.enable_profiling(True)
+        tot = {"N": 0, "marked": 0, "swept": 0, "face_passes": 0, "clear_candidates": 0, "rings": 0}
+        for i in range(F):
+            m.integrate_depth_device(depth_dev[i].data_ptr(), ROWS, COLS, poses[i], cam)
+            m.update_esdf(sync=False)
+            m.synchronize()
+            tot["N"] += m.last_frame_block_count()
+            s = m.esdf_integrator().last_stats()
+            for k in ("marked", "swept", "face_passes", "clear_candidates", "rings"):
+                tot[k] += s[k]
+        st = m.stage_times(reset=True)
+        m.enable_profiling(False)
+        # algorithmic bytes per stage over the sequence (DESIGN.md "Roofline")
+        raycast_b = F * (4 * 121 * 161) + tot["N"] * 12
+        bytes_by_stage = {
+            "view_calculator/raycast": raycast_b,
+            "tsdf/integrate/allocate_blocks": tot["N"] * 16,
+            "tsdf/integrate/update_blocks": 8192 * tot["N"] + F * frame_bytes,
+            "esdf/integrate/mark_sites": 24576 * tot["marked"],
+            "esdf/integrate/clear": 10240 * tot["clear_candidates"],
+            "esdf/integrate/compute": 20480 * tot["swept"] + 3840 * tot["face_passes"],
+        }
+        stages_out = {}
+        for name, (sms, calls) in st.items():
+            gbs = (bytes_by_stage[name] / (sms * 1e-3)) / 1e9 if sms > 0 else 0.0
+            stages_out[name] = {"ms_per_frame": sms / max(calls, 1), "algorithmic_GBps": gbs}
+        dom = max(st, key=lambda k: st[k][0])
+        peak, peak_src = measured_peak_gbs()
+        dom_ms, dom_calls = st[dom]
+        achieved = (bytes_by_stage[dom] / (dom_ms * 1e-3)) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": bytes_by_stage[dom] / max(dom_calls, 1),
+                    "avg_launch_ms": dom_ms / max(dom_calls, 1)}
+        map_stats = {"tsdf_blocks": m.tsdf_layer().num_blocks(), "esdf_blocks": m.esdf_layer().num_blocks(),
+                     "blocks_per_frame": tot["N"] / F, "esdf_rings_per_frame": tot["rings"] / F,
+                     "esdf_swept_per_frame": tot["swept"] / F, "esdf_face_passes_per_frame": tot["face_passes"] / F,
+                     "esdf_clear_candidates_per_frame": tot["clear_candidates"] / F}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(frames, cam_s, min(args.cpu_sample_frames, F))
+
+    if rank == 0:
+        working_set_mb = (F * frame_bytes + (map_stats["tsdf_blocks"] * 4096 + map_stats["esdf_blocks"] * 10240)) / 1e6
+        out = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": F, "voxel_size_m": VOXEL,
+                       "parallelism": "%d independent camera streams (one map replica per GPU)" % world,
+                       "l2": "no explicit flush: one step touches %.0f MB (depth frames + map), larger than the 126 MB L2"
+                             % working_set_mb,
+                       "esdf_driver": "host loop" if args.esdf_host_loop else "persistent cooperative kernel",
+                       "map": map_stats},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes,
+                    "d2h_bytes_per_step": int(d2h),
+                    "api": "nvb_mapper_integrate_depth (host depth in, updated_blocks out) + nvb_mapper_update_esdf, "
+                           "both synchronous, per frame"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages_out,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
