@@ -89,7 +89,7 @@ struct NvbMapper {
   bool tracker_initialized = false;
 
   // esdf scratch
-  int2* work = nullptr;
+  int4* work = nullptr;
   int* esdf_ints = nullptr;  // small counters block
   int* upd_list = nullptr;
   int* clr_list = nullptr;
@@ -98,6 +98,10 @@ struct NvbMapper {
   int* ring_b = nullptr;
   int* stamp_a = nullptr;
   int* stamp_b = nullptr;
+  int* nbr = nullptr;
+  int* seed_upd = nullptr;
+  int* seed_clr = nullptr;
+  int update_seq = 0;
   long long* stats = nullptr;
   unsigned int* barrier = nullptr;
   int* xyz_upload = nullptr;
@@ -201,6 +205,19 @@ int allocEsdfScratch(NvbMapper* m, int old_cap, int cap) {
   if ((rc = reallocCopy(&m->ring_b, 0, (size_t)cap, false, m->stream))) return rc;
   if ((rc = reallocCopy(&m->stamp_a, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
   if ((rc = reallocCopy(&m->stamp_b, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->seed_upd, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->seed_clr, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  // neighbour table: 0xFE bytes = "unknown" (< -1) for slots that were never linked
+  {
+    int* q = nullptr;
+    NVB_CUDA(cudaMalloc(&q, (size_t)cap * 6 * sizeof(int)));
+    NVB_CUDA(cudaMemsetAsync(q, 0xFE, (size_t)cap * 6 * sizeof(int), m->stream));
+    if (m->nbr && old_cap)
+      NVB_CUDA(cudaMemcpyAsync(q, m->nbr, (size_t)old_cap * 6 * sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->nbr) cudaFree(m->nbr);
+    m->nbr = q;
+  }
   return NVB_OK;
 }
 
@@ -213,7 +230,7 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kNumInts = 32 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kNumInts = 32 };
 
 EsdfCtx makeEsdfCtx(NvbMapper* m) {
   EsdfCtx c{};
@@ -228,6 +245,9 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.ring_count = m->esdf_ints + kRingCount;
   c.stamp_a = m->stamp_a, c.stamp_b = m->stamp_b;
   c.ring_id = m->esdf_ints + kRingId;
+  c.nbr = m->nbr, c.seed_upd = m->seed_upd, c.seed_clr = m->seed_clr;
+  c.cleared_seq = m->esdf_ints + kClearedSeq;
+  c.update_seq = m->update_seq;
   c.barrier = m->barrier;
   c.stats = m->stats;
   c.error = m->error_dev;
@@ -566,6 +586,7 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
   }
   if (upper <= 0) upper = 1;
   if ((rc = ensureEsdfCapacity(m, (long long)std::min(m->tsdf_count_ub, m->tsdf.capacity) + m->esdf_extra_ub))) return rc;
+  m->update_seq++;
   EsdfCtx c = makeEsdfCtx(m);
   beginStage(m, 3);
   if (from_tracker) {
@@ -716,6 +737,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->dirty), cudaFree(m->todo_slots);
   cudaFree(m->work), cudaFree(m->esdf_ints), cudaFree(m->upd_list), cudaFree(m->clr_list), cudaFree(m->cleared_list);
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
+  cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
@@ -740,6 +762,10 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(cudaMemsetAsync(m->dirty, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kClearedCount, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kClearedSeq, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->seed_upd, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->seed_clr, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->nbr, 0xFE, (size_t)m->esdf.capacity * 6 * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
   m->tracker_initialized = false;
   m->tsdf_count_ub = 0, m->tsdf_count_confirmed = 0, m->esdf_extra_ub = 0;
@@ -985,6 +1011,10 @@ int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   if (layer == NVB_LAYER_TSDF) {
     // the tracker is told like after an integration: a later updateEsdf must see these blocks
     m->tracker_initialized = false;
+  } else {
+    // blocks created outside the ESDF update path are not linked: forget the neighbour table,
+    // it is re-resolved lazily through the hash
+    NVB_CUDA(cudaMemset(m->nbr, 0xFE, (size_t)m->esdf.capacity * 6 * sizeof(int)));
   }
   return checkDeviceError(m);
 }

@@ -74,7 +74,7 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
   }
   bool was_new;
   const int eslot = hashFindOrInsert(c.esdf, x, y, z, c.error, &was_new);
-  c.work[i] = make_int2(eslot, tslot);
+  c.work[i] = make_int4(eslot, tslot, was_new ? 1 : 0, 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -87,7 +87,20 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
   const int tid = threadIdx.x;
   const int n = *c.work_count;
   for (int item = blockIdx.x; item < n; item += gridDim.x) {
-    const int2 w = c.work[item];
+    const int4 w = c.work[item];
+    if (w.x >= 0 && w.z && tid < 6) {
+      // Newly allocated ESDF block: link it with its six face neighbours (both directions).
+      // Replaces the per-ring getBlockPtr hash lookups (:1100-1131).
+      const int* bi = c.esdf.block_index + 3 * w.x;
+      int x = bi[0], y = bi[1], z = bi[2];
+      const int d = (tid & 1) ? -1 : 1;
+      if ((tid >> 1) == 0) x += d;
+      else if ((tid >> 1) == 1) y += d;
+      else z += d;
+      const int other = hashFind(c.esdf.hash, x, y, z);
+      c.nbr[6 * w.x + tid] = other;
+      if (other >= 0) c.nbr[6 * other + (tid ^ 1)] = w.x;
+    }
     if (w.x < 0 || w.y < 0) continue;  // block_ptr == nullptr || esdf_block == nullptr (:513-517)
     if (tid < 3) s_flags[tid] = 0;
     uint4* gblk = reinterpret_cast<uint4*>(esdfBlockPtr(c.esdf, w.x));
@@ -151,7 +164,10 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
       for (int k = tid; k < kBlockWords / 4; k += kThreads) gblk[k] = reinterpret_cast<uint4*>(s)[k];
     }
     if (tid == 0) {
-      if (s_flags[0]) c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
+      if (s_flags[0]) {
+        c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
+        c.seed_upd[w.x] = c.update_seq;
+      }
       if (s_flags[1]) {
         c.clr_list[atomicAdd(c.clr_count, 1)] = w.x;
         const int* bi = c.esdf.block_index + 3 * w.x;
@@ -170,7 +186,10 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
       __threadfence();
       const int nclr = *(volatile int*)c.clr_count;
       const int nupd = *(volatile int*)c.upd_count;
-      if (nclr > 0) *c.cleared_count = 0;
+      if (nclr > 0) {
+        *c.cleared_count = 0;
+        *c.cleared_seq = c.update_seq;
+      }
       c.stats[1] = nupd, c.stats[2] = nclr;
     }
   }
@@ -264,7 +283,10 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
     }
     if (any) s_any = 1;
     __syncthreads();
-    if (tid == 0 && s_any) c.cleared_list[atomicAdd(c.cleared_count, 1)] = slot;
+    if (tid == 0 && s_any) {
+      c.cleared_list[atomicAdd(c.cleared_count, 1)] = slot;
+      c.seed_clr[slot] = c.update_seq;
+    }
     __syncthreads();
   }
 }
@@ -482,56 +504,227 @@ __device__ __forceinline__ void gridBarrier(unsigned int* bar, unsigned int& gen
   __syncthreads();
 }
 
-struct RingBufs {
-  int* list[2];
-  int* stamp[2];
-};
+// ---------------------------------------------------------------------------
+// Persistent wavefront, ownership based.
+//
+// CTA c owns the ESDF slots {c, c + G, c + 2G, ...}. Ring membership is a per-slot
+// stamp (stamp[r & 1][slot] == r), so there are no global lists, no list atomics and
+// no sort/unique: a face update marks its destination block with one plain store,
+// and at the start of every sweep phase each CTA scans the stamps of the slots it owns
+// to find its members (they stay in shared memory for the three axis phases of the
+// next ring). Neighbour slots come from the nbr table built at allocation time.
+// Per ring: 3 axis phases + 1 sweep phase, one grid barrier each; the only global
+// atomic is one add per CTA per ring for the ring's block count.
+// ---------------------------------------------------------------------------
+constexpr int kMaxMembers = 1024;  // cached owned members per CTA (maps up to G*1024 blocks scan in one round)
 
-// computeEsdf (:1465-1496) twice -- updated blocks, then the persistent cleared
-// list (:254-257) -- in one cooperative launch.
+__device__ __forceinline__ int neighborSlot(const EsdfCtx& c, int slot, int dir) {
+  int v = __ldcg(c.nbr + 6 * slot + dir);
+  if (v < -1) {  // unknown (block created outside the ESDF update path): resolve through the hash once
+    const int* bi = c.esdf.block_index + 3 * slot;
+    int x = bi[0], y = bi[1], z = bi[2];
+    const int d = (dir & 1) ? -1 : 1;
+    if ((dir >> 1) == 0) x += d;
+    else if ((dir >> 1) == 1) y += d;
+    else z += d;
+    v = hashFind(c.esdf.hash, x, y, z);
+    c.nbr[6 * slot + dir] = v;
+  }
+  return v;
+}
+
+// Scan the owned slots for `tag[slot] == value`; compact the hits into s_members
+// (ascending slot order). Returns the number of members. If stamp_out is non-null
+// the members are also stamped (initial list of a computeEsdf call).
+__device__ int scanOwned(const int* tag, int value, int nslots, int cta, int nctas, int first_candidate,
+                         int num_candidates, int* s_members, int* s_scan, int* stamp_out, int stamp_value) {
+  const int tid = threadIdx.x;
+  __shared__ int s_count;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  for (int base = 0; base < num_candidates; base += kThreads) {
+    const int k = first_candidate + base + tid;
+    const int slot = cta + k * nctas;
+    const bool hit = (base + tid < num_candidates) && slot < nslots && __ldcg(tag + slot) == value;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+    if ((tid & 31) == 0) s_scan[tid >> 5] = __popc(ballot);
+    __syncthreads();
+    int offset = s_count;
+    for (int wq = 0; wq < (tid >> 5); wq++) offset += s_scan[wq];
+    if (hit) {
+      const int pos = offset + __popc(ballot & ((1u << (tid & 31)) - 1u));
+      if (pos < kMaxMembers) s_members[pos] = slot;
+      if (stamp_out) stamp_out[slot] = stamp_value;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int wq = 0; wq < kThreads / 32; wq++) tot += s_scan[wq];
+      s_count += tot;
+    }
+    __syncthreads();
+  }
+  return s_count;
+}
+
+// In-block sweeps of the cached members, kGroups blocks at a time (sweepBlockBandKernel, :1390-1431).
+__device__ void sweepMembers(const EsdfCtx& c, const int* s_members, int k, unsigned int* smem, int* s_changed) {
+  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
+  unsigned int* sm = smem + group * kBlockWords;
+  const int a = lane64 >> 3, b = lane64 & 7;
+  for (int base = 0; base < k; base += kGroups) {
+    const int item = base + group;
+    const int slot = item < k ? s_members[item] : -1;
+    if (lane64 == 0) s_changed[group] = 0;
+    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
+    __syncthreads();
+    bool ch = false;
+    if (slot >= 0) ch |= sweepLine(sm, 0, a, b, 0, c.max_sq);
+    __syncthreads();
+    if (slot >= 0) ch |= sweepLine(sm, a, 0, b, 1, c.max_sq);
+    __syncthreads();
+    if (slot >= 0) ch |= sweepLine(sm, a, b, 0, 2, c.max_sq);
+    if (ch) s_changed[group] = 1;
+    __syncthreads();
+    if (slot >= 0 && s_changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
+    __syncthreads();
+  }
+}
+
+// The two passes of one axis over the cached members (see phaseNeighbors for the
+// interface-ownership rule). Destination blocks are stamped for ring+1 with a plain store.
+__device__ void axisMembers(const EsdfCtx& c, int axis, const int* s_members, int k, const int* stamp_cur, int ring,
+                            int* stamp_nxt, int* s_slot, int* s_upd) {
+  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
+  const int entry_in_cta = group >> 1, side = group & 1;  // side 0 = hi (+dir), 1 = lo (-dir)
+  const int u = lane64 >> 3, w = lane64 & 7;
+  const int strideA = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
+  const int faceBase = (axis == 0) ? (u * 8 + w) : ((axis == 1) ? (u * 64 + w) : (u * 64 + w * 8));
+  const int vHi = faceBase + (kVps - 1) * strideA, vLo = faceBase;
+  for (int base = 0; base < k; base += kGroups / 2) {
+    const int item = base + entry_in_cta;
+    if (lane64 == 0) {
+      int mine = -1, other = -1;
+      if (item < k) {
+        mine = s_members[item];
+        other = neighborSlot(c, mine, axis * 2 + side);
+      }
+      s_slot[group * 2] = mine;
+      s_slot[group * 2 + 1] = other;
+      s_upd[group * 2] = 0;
+      s_upd[group * 2 + 1] = 0;
+    }
+    __syncthreads();
+    const int mine = s_slot[group * 2], other = s_slot[group * 2 + 1];
+    if (mine >= 0 && other >= 0) {
+      if (side == 0) {
+        unsigned int* gA = esdfBlockPtr(c.esdf, mine) + vHi * kEsdfVoxelWords;
+        unsigned int* gB = esdfBlockPtr(c.esdf, other) + vLo * kEsdfVoxelWords;
+        const int other_stamp = __ldcg(stamp_cur + other);
+        VoxelRegs A = loadVoxel(gA), B = loadVoxel(gB);
+        if (updateSingleNeighbor(A, B, gB, axis, +1, c.max_sq)) s_upd[group * 2 + 1] = 1;  // B updated
+        if (other_stamp == ring) {
+          if (updateSingleNeighbor(B, A, gA, axis, -1, c.max_sq)) s_upd[group * 2] = 1;  // A updated
+        }
+      } else {
+        const int other_stamp = __ldcg(stamp_cur + other);
+        if (other_stamp != ring) {
+          unsigned int* gA = esdfBlockPtr(c.esdf, other) + vHi * kEsdfVoxelWords;
+          unsigned int* gB = esdfBlockPtr(c.esdf, mine) + vLo * kEsdfVoxelWords;
+          VoxelRegs A = loadVoxel(gA), B = loadVoxel(gB);
+          if (updateSingleNeighbor(B, A, gA, axis, -1, c.max_sq)) s_upd[group * 2 + 1] = 1;  // A (= other) updated
+        }
+      }
+    }
+    __syncthreads();
+    if (lane64 == 0 && mine >= 0 && other >= 0) {
+      if (s_upd[group * 2]) __stcg(stamp_nxt + mine, ring + 1);
+      if (s_upd[group * 2 + 1]) __stcg(stamp_nxt + other, ring + 1);
+    }
+    __syncthreads();
+  }
+}
+
+// computeEsdf (:1465-1496) twice -- blocks with sites, then the persistent cleared
+// set (:254-257) -- in one cooperative launch.
 __global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx c) {
   extern __shared__ __align__(16) unsigned int smem[];
   __shared__ int s_changed[kGroups];
   __shared__ int s_slot[kGroups * 2];
   __shared__ int s_upd[kGroups * 2];
+  __shared__ int s_scan[kThreads / 32];
+  __shared__ int s_members[kMaxMembers];
   const int cta = blockIdx.x, nctas = gridDim.x;
   // Empty block list: integrateBlocksTemplate returns before touching anything (:226-228).
   if (*(volatile int*)c.work_count == 0) return;
   unsigned int generation = 0;
   int ring = *(volatile int*)c.ring_id;
+  const int nslots = min(*(volatile int*)c.esdf.count, c.esdf.capacity);
+  const int owned = (nslots > cta) ? (nslots - cta + nctas - 1) / nctas : 0;  // candidates of this CTA
+  const int max_owned = (nslots + nctas - 1) / nctas;                         // uniform bound
+  const int rounds = (max_owned + kMaxMembers - 1) / kMaxMembers;              // uniform
+  int* stamp[2] = {c.stamp_a, c.stamp_b};
   long long swept = 0, faces = 0, rings = 0;
-  RingBufs rb;
-  rb.list[0] = c.ring_a, rb.list[1] = c.ring_b;
-  rb.stamp[0] = c.stamp_a, rb.stamp[1] = c.stamp_b;
+  const int cleared_seq = *(volatile int*)c.cleared_seq;
   for (int pass = 0; pass < 2; pass++) {
-    const int* src = pass ? c.cleared_list : c.upd_list;
-    int n = pass ? *(volatile int*)c.cleared_count : *(volatile int*)c.upd_count;
-    if (n == 0) continue;
+    const int* seed = pass ? c.seed_clr : c.seed_upd;
+    const int seed_value = pass ? cleared_seq : c.update_seq;
+    if (pass == 1 && cleared_seq == 0) break;  // the clear pass never ran: the cleared set is empty
     int ci = ring & 1;
-    // Initial sweep of the source list; members of ring `ring` get stamped.
-    phaseSweep(c, src, rb.list[ci], n, rb.stamp[ci], ring, smem, s_changed, cta, nctas);
+    // Initial sweep of the seed set; its members are stamped as ring `ring`.
+    int k_total = 0;
+    for (int r = 0; r < rounds; r++) {
+      const int first = r * kMaxMembers;
+      const int ncand = max(0, min(kMaxMembers, owned - first));
+      const int k = scanOwned(seed, seed_value, nslots, cta, nctas, first, ncand, s_members, s_scan, stamp[ci], ring);
+      sweepMembers(c, s_members, k, smem, s_changed);
+      k_total += k;
+    }
+    if (threadIdx.x == 0 && k_total > 0) atomicAdd(c.ring_count + ci, k_total);
     if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
-    swept += n;
     gridBarrier(c.barrier, generation, nctas);
+    int n = *(volatile int*)(c.ring_count + ci);
+    int k_cached = (rounds == 1) ? k_total : -1;  // s_members holds this CTA's members of ring `ring`
+    swept += n;
     while (n > 0) {
       const int ni = ci ^ 1;
       for (int axis = 0; axis < 3; axis++) {
-        phaseNeighbors(c, axis, rb.list[ci], n, rb.stamp[ci], ring, rb.list[ni], c.ring_count + ni, rb.stamp[ni],
-                       s_slot, s_upd, cta, nctas);
+        for (int r = 0; r < rounds; r++) {
+          int k = k_cached;
+          if (k < 0) {
+            const int first = r * kMaxMembers;
+            const int ncand = max(0, min(kMaxMembers, owned - first));
+            k = scanOwned(stamp[ci], ring, nslots, cta, nctas, first, ncand, s_members, s_scan, nullptr, 0);
+          }
+          axisMembers(c, axis, s_members, k, stamp[ci], ring, stamp[ni], s_slot, s_upd);
+        }
         gridBarrier(c.barrier, generation, nctas);
       }
       faces += 6ll * n;
+      // Members of ring+1 = owned slots stamped during the three axis phases.
+      int k_next = 0;
+      for (int r = 0; r < rounds; r++) {
+        const int first = r * kMaxMembers;
+        const int ncand = max(0, min(kMaxMembers, owned - first));
+        const int k = scanOwned(stamp[ni], ring + 1, nslots, cta, nctas, first, ncand, s_members, s_scan, nullptr, 0);
+        sweepMembers(c, s_members, k, smem, s_changed);
+        k_next += k;
+      }
+      if (threadIdx.x == 0 && k_next > 0) atomicAdd(c.ring_count + ni, k_next);
+      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the counter of ring+2
+      gridBarrier(c.barrier, generation, nctas);
       const int n_next = *(volatile int*)(c.ring_count + ni);
-      phaseSweep(c, nullptr, rb.list[ni], n_next, nullptr, 0, smem, s_changed, cta, nctas);
-      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the next ring's append counter
+      k_cached = (rounds == 1) ? k_next : -1;
       swept += n_next;
       rings++;
-      gridBarrier(c.barrier, generation, nctas);
       ring++;
       ci = ni;
       n = n_next;
     }
+    // both counters must be zero for the next pass; ring_count[ci] held n == 0 already
     ring++;
+    if (cta == 0 && threadIdx.x == 0) c.ring_count[0] = c.ring_count[1] = 0;
+    gridBarrier(c.barrier, generation, nctas);
   }
   if (cta == 0 && threadIdx.x == 0) {
     *c.ring_id = ring + 1;
@@ -570,14 +763,14 @@ void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots
 }
 
 void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream) {
-  int grid = num_sms * 4;
+  int grid = num_sms * 8;  // 8 resident CTAs per SM (10 KiB smem, 256 threads each)
   if (count_upper < grid) grid = count_upper;
   if (grid < 1) grid = 1;
   esdfMarkKernel<<<grid, kThreads, 0, stream>>>(c);
 }
 
 void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream) {
-  int grid = num_sms * 4;
+  int grid = num_sms * 8;
   if (esdf_count_upper < grid) grid = esdf_count_upper;
   if (grid < 1) grid = 1;
   esdfClearKernel<<<grid, kThreads, 0, stream>>>(c);

@@ -222,8 +222,8 @@ void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsig
 struct EsdfCtx {
   DevLayer tsdf;
   DevLayer esdf;
-  // work list of this update: {esdf_slot, tsdf_slot}
-  int2* work;
+  // work list of this update: {esdf_slot, tsdf_slot, is_new, 0}
+  int4* work;
   int* work_count;
   // lists of ESDF slots
   int* upd_list;
@@ -239,6 +239,12 @@ struct EsdfCtx {
   int* stamp_a;        // per ESDF slot
   int* stamp_b;
   int* ring_id;        // device: monotonically increasing ring id
+  // Ownership-based wavefront (persistent kernel): no lists, every CTA scans the slots it owns.
+  int* nbr;           // 6 ints per ESDF slot: slot of the +x,-x,+y,-y,+z,-z neighbour, -1 none, < -1 unknown
+  int* seed_upd;      // per slot: == update_seq  <=> block has sites in this update (computeEsdf #1 seeds)
+  int* seed_clr;      // per slot: == *cleared_seq <=> member of the persistent cleared list (computeEsdf #2 seeds)
+  int* cleared_seq;   // device: update_seq of the last update whose clear pass ran
+  int update_seq;     // host: sequence number of this update (monotone, starts at 1)
   unsigned int* barrier;  // grid barrier counter
   long long* stats;    // 8 counters
   int* error;

@@ -23,6 +23,10 @@ __device__ __forceinline__ int signum(float x) { return (x > 0.0f) ? 1 : ((x < 0
 // setIndexUpdated (view_calculator_impl.cuh:46-56): the linear index is computed in
 // int arithmetic and only guarded by lin < linear_size (negative values fail the
 // guard; out-of-AABB cells whose linear index lands in range alias, as in the reference).
+// The bitset lives in shared memory when it fits (kSmem): a CTA of 16x8 neighbouring rays
+// crosses mostly the same cells, so the marks are shared-memory atomics and each CTA
+// merges only its non-zero words into the global bitset at the end.
+template <bool kSmem>
 __device__ __forceinline__ void markCell(int x, int y, int z, const ViewGrid& g, unsigned int* bits) {
   const unsigned int sx = (unsigned int)x - (unsigned int)g.min_index.x;
   const unsigned int sy = (unsigned int)y - (unsigned int)g.min_index.y;
@@ -36,83 +40,111 @@ __device__ __forceinline__ void markCell(int x, int y, int z, const ViewGrid& g,
   }
 }
 
+constexpr int kRayTileCols = 16, kRayTileRows = 8;  // rays per CTA
+constexpr int kMaxSmemWords = 12288;                 // 48 KiB of bitset (393 216 cells)
+
 // combinedBlockIndicesInImageKernel (view_calculator_impl.cuh:62-115) + RayCaster
 // (rays/internal/impl/ray_caster_impl.h:26-72).
-__global__ void __launch_bounds__(128) viewRaycastKernel(const float* __restrict__ depth, int rows, int cols,
-                                                         Rigid T_L_C, NvbCamera cam, float block_size,
-                                                         float trunc_m, float max_dist, int f, int ray_rows,
-                                                         int ray_cols, ViewGrid g, unsigned int* bits) {
-  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= ray_rows * ray_cols) return;
-  const int rr = ray / ray_cols, rc = ray - rr * ray_cols;
-  int pixel_row = rr * f, pixel_col = rc * f;
-  if (pixel_row >= rows) pixel_row = rows - 1;  // overhanging rays are pulled back to the border
-  if (pixel_col >= cols) pixel_col = cols - 1;
-
-  float d = __ldg(depth + (size_t)pixel_row * cols + pixel_col);
-  if (d <= 0.0f) return;  // NaN passes this test, exactly like the reference
-  if (max_dist > 0.0f && d > max_dist) d = max_dist;
-
-  // Camera::vectorFromPixelIndices (sensors/internal/impl/camera_impl.h:89-112)
-  const float vx = (((float)pixel_col + 0.5f) - cam.cu) / cam.fu;
-  const float vy = (((float)pixel_row + 0.5f) - cam.cv) / cam.fv;
-  const float s = d + trunc_m;
-  Vec3 p_C = {s * vx, s * vy, s * 1.0f};
-  const Vec3 p_L = transformPoint(T_L_C, p_C);
-
-  const int3 b = blockIndexFromPosition(block_size, p_L);
-  markCell(b.x, b.y, b.z, g, bits);
-
-  // RayCaster(T_L_C.translation() / block_size, p_L / block_size), scale 1.
-  const float o[3] = {T_L_C.t[0] / block_size, T_L_C.t[1] / block_size, T_L_C.t[2] / block_size};
-  const float e[3] = {p_L.x / block_size, p_L.y / block_size, p_L.z / block_size};
-  int cur[3], sgn[3];
-  float t_next[3], t_step[3];
-  unsigned int length = 0;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    cur[i] = floatToIntRz(floorf(o[i] / 1.0f));
-    const int end = floatToIntRz(floorf(e[i] / 1.0f));
-    const int diff = (int)((unsigned int)end - (unsigned int)cur[i]);
-    length += (diff < 0) ? (0u - (unsigned int)diff) : (unsigned int)diff;
-    const float ray_i = e[i] - o[i];
-    sgn[i] = signum(ray_i);
-    const int corrected = sgn[i] > 0 ? sgn[i] : 0;
-    const float shifted = o[i] - (float)cur[i];
-    t_next[i] = ((float)corrected - shifted) / ray_i;  // NaN / inf allowed
-    t_step[i] = (float)sgn[i] / ray_i;
+template <bool kSmem>
+__global__ void __launch_bounds__(kRayTileCols* kRayTileRows)
+    viewRaycastKernel(const float* __restrict__ depth, int rows, int cols, Rigid T_L_C, NvbCamera cam,
+                      float block_size, float trunc_m, float max_dist, int f, int ray_rows, int ray_cols,
+                      int tiles_x, ViewGrid g, unsigned int* gbits) {
+  extern __shared__ unsigned int s_bits[];
+  unsigned int* bits = kSmem ? s_bits : gbits;
+  const int tid = threadIdx.x;
+  if (kSmem) {
+    for (int w = tid; w < g.num_words; w += blockDim.x) s_bits[w] = 0;
+    __syncthreads();
   }
-  // nextRayIndex returns length+1 cells.
-  for (int step = 0; step <= (int)length; step++) {
-    markCell(cur[0], cur[1], cur[2], g, bits);
-    // Eigen minCoeff: start at element 0, replace on strict '<'.
-    float best = t_next[0];
-    int k = 0;
-    if (t_next[1] < best) best = t_next[1], k = 1;
-    if (t_next[2] < best) k = 2;
-    if (k == 0) {
-      cur[0] = (int)((unsigned int)cur[0] + (unsigned int)sgn[0]);
-      t_next[0] = t_next[0] + t_step[0];
-    } else if (k == 1) {
-      cur[1] = (int)((unsigned int)cur[1] + (unsigned int)sgn[1]);
-      t_next[1] = t_next[1] + t_step[1];
-    } else {
-      cur[2] = (int)((unsigned int)cur[2] + (unsigned int)sgn[2]);
-      t_next[2] = t_next[2] + t_step[2];
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int rr = tile_y * kRayTileRows + tid / kRayTileCols;
+  const int rc = tile_x * kRayTileCols + tid % kRayTileCols;
+  bool active = rr < ray_rows && rc < ray_cols;
+  float d = 0.0f;
+  int pixel_row = 0, pixel_col = 0;
+  if (active) {
+    pixel_row = rr * f, pixel_col = rc * f;
+    if (pixel_row >= rows) pixel_row = rows - 1;  // overhanging rays are pulled back to the border
+    if (pixel_col >= cols) pixel_col = cols - 1;
+    d = __ldg(depth + (size_t)pixel_row * cols + pixel_col);
+    if (d <= 0.0f) active = false;  // NaN passes this test, exactly like the reference
+  }
+  if (active) {
+    if (max_dist > 0.0f && d > max_dist) d = max_dist;
+    // Camera::vectorFromPixelIndices (sensors/internal/impl/camera_impl.h:89-112)
+    const float vx = (((float)pixel_col + 0.5f) - cam.cu) / cam.fu;
+    const float vy = (((float)pixel_row + 0.5f) - cam.cv) / cam.fv;
+    const float s = d + trunc_m;
+    Vec3 p_C = {s * vx, s * vy, s * 1.0f};
+    const Vec3 p_L = transformPoint(T_L_C, p_C);
+
+    const int3 b = blockIndexFromPosition(block_size, p_L);
+    markCell<kSmem>(b.x, b.y, b.z, g, bits);
+
+    // RayCaster(T_L_C.translation() / block_size, p_L / block_size), scale 1.
+    const float o[3] = {T_L_C.t[0] / block_size, T_L_C.t[1] / block_size, T_L_C.t[2] / block_size};
+    const float e[3] = {p_L.x / block_size, p_L.y / block_size, p_L.z / block_size};
+    int cur[3], sgn[3];
+    float t_next[3], t_step[3];
+    unsigned int length = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      cur[i] = floatToIntRz(floorf(o[i] / 1.0f));
+      const int end = floatToIntRz(floorf(e[i] / 1.0f));
+      const int diff = (int)((unsigned int)end - (unsigned int)cur[i]);
+      length += (diff < 0) ? (0u - (unsigned int)diff) : (unsigned int)diff;
+      const float ray_i = e[i] - o[i];
+      sgn[i] = signum(ray_i);
+      const int corrected = sgn[i] > 0 ? sgn[i] : 0;
+      const float shifted = o[i] - (float)cur[i];
+      t_next[i] = ((float)corrected - shifted) / ray_i;  // NaN / inf allowed
+      t_step[i] = (float)sgn[i] / ray_i;
+    }
+    // nextRayIndex returns length+1 cells.
+    for (int step = 0; step <= (int)length; step++) {
+      markCell<kSmem>(cur[0], cur[1], cur[2], g, bits);
+      // Eigen minCoeff: start at element 0, replace on strict '<'.
+      float best = t_next[0];
+      int k = 0;
+      if (t_next[1] < best) best = t_next[1], k = 1;
+      if (t_next[2] < best) k = 2;
+      if (k == 0) {
+        cur[0] = (int)((unsigned int)cur[0] + (unsigned int)sgn[0]);
+        t_next[0] = t_next[0] + t_step[0];
+      } else if (k == 1) {
+        cur[1] = (int)((unsigned int)cur[1] + (unsigned int)sgn[1]);
+        t_next[1] = t_next[1] + t_step[1];
+      } else {
+        cur[2] = (int)((unsigned int)cur[2] + (unsigned int)sgn[2]);
+        t_next[2] = t_next[2] + t_step[2];
+      }
+    }
+  }
+  if (kSmem) {
+    __syncthreads();
+    for (int w = tid; w < g.num_words; w += blockDim.x) {
+      const unsigned int v = s_bits[w];
+      if (v && (*(volatile unsigned int*)(gbits + w) & v) != v) atomicOr(gbits + w, v);
     }
   }
 }
 
-constexpr int kCompactThreads = 512;  // one bitset word per thread -> 16384 cells per tile
+constexpr int kCompactThreads = 256;  // one bitset word per thread -> 8192 cells per tile
 
 // Ordered compaction + allocation. Tiles take tickets in order and chain their
 // prefix through tile_state (epoch in the high word), so the emitted list is in
 // ascending linear-index order = the order convertAabbUpdatedToVector produces
-// (view_calculator.cu:185-195): x fastest, then y, then z.
+// (view_calculator.cu:185-195): x fastest, then y, then z. Inside a tile the set
+// bits are dealt round-robin to the threads (binary search over the popcount scan +
+// find-n-th-set-bit), so the dependent hash probes of one tile run in parallel
+// instead of up to 32 per thread in sequence.
 __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(CompactArgs a) {
   __shared__ unsigned int s_tile;
   __shared__ int s_warp_sums[kCompactThreads / 32];
-  __shared__ int s_prefix;
+  __shared__ int s_incl[kCompactThreads];
+  __shared__ unsigned int s_word[kCompactThreads];
+  __shared__ int s_prefix, s_total;
   const int tid = threadIdx.x;
   if (tid == 0) s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
   __syncthreads();
@@ -125,8 +157,9 @@ __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(Compact
     word = a.bits[w];
     if (word) a.bits[w] = 0;  // self-cleaning: the next frame starts from a zero bitset
   }
+  s_word[tid] = word;
   const int cnt = __popc(word);
-  // block-wide exclusive scan of cnt
+  // block-wide inclusive scan of cnt
   int incl = cnt;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -160,16 +193,26 @@ __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(Compact
       atomicExch(a.tile_state + tile, ((unsigned long long)a.epoch << 32) | (unsigned int)(prefix + tile_total));
       if ((int)tile == num_tiles - 1) *a.frame_count = prefix + tile_total;
       s_prefix = prefix;
+      s_total = tile_total;
     }
   }
   __syncthreads();
-  if (word == 0) return;
-  int out = s_prefix + s_warp_sums[tid >> 5] + (incl - cnt);
+  s_incl[tid] = s_warp_sums[tid >> 5] + incl;
+  __syncthreads();
+  const int total = s_total, prefix = s_prefix;
   const int sx = a.grid.size.x, sxy = a.grid.size.x * a.grid.size.y;
-  while (word) {
-    const int bit = __ffs(word) - 1;
-    word &= word - 1;
-    const int lin = w * 32 + bit;
+  for (int j = tid; j < total; j += kCompactThreads) {
+    // first word whose inclusive count exceeds j
+    int lo = 0, hi = kCompactThreads - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_incl[mid] > j) hi = mid;
+      else lo = mid + 1;
+    }
+    const unsigned int wv = s_word[lo];
+    const int rank = j - (s_incl[lo] - __popc(wv));            // 0-based rank of the bit inside the word
+    const int bit = (int)__fns(wv, 0, rank + 1);               // position of the (rank+1)-th set bit
+    const int lin = ((int)tile * kCompactThreads + lo) * 32 + bit;
     // aabbLinearIndexToLayerIndex (view_calculator_impl.cuh:38-44)
     const int x = lin % sx + a.grid.min_index.x;
     const int y = (lin / sx) % a.grid.size.y + a.grid.min_index.y;
@@ -184,7 +227,7 @@ __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(Compact
         if (atomicExch(a.dirty + slot, 1) == 0) a.todo_slots[atomicAdd(a.todo_count, 1)] = slot;
       }
     }
-    a.frame_blocks[out++] = make_int4(x, y, z, slot);
+    a.frame_blocks[prefix + j] = make_int4(x, y, z, slot);
   }
 }
 
@@ -209,10 +252,17 @@ void launchViewRaycast(const float* depth, int rows, int cols, const Rigid& T_L_
   int ray_cols = (cols + f - 2) / f + 1;
   if (ray_rows > thr_rows) ray_rows = thr_rows;
   if (ray_cols > thr_cols) ray_cols = thr_cols;
-  const int n = ray_rows * ray_cols;
-  if (n <= 0) return;
-  viewRaycastKernel<<<(n + 127) / 128, 128, 0, stream>>>(depth, rows, cols, T_L_C, cam, block_size, trunc_m,
-                                                         max_dist, f, ray_rows, ray_cols, grid, bits);
+  if (ray_rows <= 0 || ray_cols <= 0) return;
+  const int tiles_x = (ray_cols + kRayTileCols - 1) / kRayTileCols;
+  const int tiles_y = (ray_rows + kRayTileRows - 1) / kRayTileRows;
+  const int threads = kRayTileCols * kRayTileRows;
+  if (grid.num_words <= kMaxSmemWords) {
+    viewRaycastKernel<true><<<tiles_x * tiles_y, threads, (size_t)grid.num_words * sizeof(unsigned int), stream>>>(
+        depth, rows, cols, T_L_C, cam, block_size, trunc_m, max_dist, f, ray_rows, ray_cols, tiles_x, grid, bits);
+  } else {
+    viewRaycastKernel<false><<<tiles_x * tiles_y, threads, 0, stream>>>(
+        depth, rows, cols, T_L_C, cam, block_size, trunc_m, max_dist, f, ray_rows, ray_cols, tiles_x, grid, bits);
+  }
 }
 
 void launchCompactAllocate(const CompactArgs& args, cudaStream_t stream) {
