@@ -223,6 +223,7 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
+    m.join_streams()  # the last ESDF wavefront runs on the mapper's side stream
     ev1.record(stream)
     m.synchronize()
     barrier()

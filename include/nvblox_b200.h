@@ -209,6 +209,10 @@ NVB_API int32_t nvb_mapper_last_frame_block_count(NvbMapper* m, int32_t* out_cou
 /* `updated_blocks` of the most recent frame again (e.g. after a too-small buffer). */
 NVB_API int32_t nvb_mapper_last_frame_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_t cap,
                                              int32_t* out_count);
+/* Device-side join (no host synchronisation): work enqueued on nvb_mapper_stream() after this
+ * call also waits for the ESDF wavefront, which runs on an internal side stream so that it
+ * overlaps the next frame's TSDF chain. Needed before recording an event on the mapper's stream. */
+NVB_API int32_t nvb_mapper_join_streams(NvbMapper* m);
 /* The CUDA stream (cudaStream_t) all of the mapper's work is enqueued on
  * (Mapper's shared CudaStream, src/mapper/mapper.cpp:28-46). */
 NVB_API void* nvb_mapper_stream(NvbMapper* m);
@@ -236,6 +240,10 @@ NVB_API int32_t nvb_layer_block_bytes(int32_t layer);
  * candidate blocks, [4] blocks cleared, [5] swept blocks, [6] (block,direction)
  * face passes, [7] rings. Synchronising. */
 NVB_API int32_t nvb_mapper_last_esdf_stats(NvbMapper* m, int64_t out[8]);
+
+/* Time split of the last ESDF wavefront launch as seen by CTA 0 (ns): [0] grid barriers,
+ * [1] face-propagation phases, [2] scan + sweep phases, [3] number of grid barriers. Synchronising. */
+NVB_API int32_t nvb_mapper_esdf_time_split(NvbMapper* m, int64_t out[4]);
 
 /* Per-stage device time of the frames since the last reset, measured with CUDA
  * events on the mapper's stream when profiling is enabled (same names as the

@@ -25,10 +25,10 @@ EXPORTED_SYMBOLS = [
     "nvb_view_raycast", "nvb_mapper_integrate_depth", "nvb_mapper_integrate_depth_async",
     "nvb_mapper_update_esdf", "nvb_mapper_update_esdf_async", "nvb_esdf_integrate_blocks",
     "nvb_mapper_synchronize", "nvb_mapper_last_frame_block_count", "nvb_mapper_last_frame_blocks",
-    "nvb_mapper_stream",
+    "nvb_mapper_stream", "nvb_mapper_join_streams",
     "nvb_layer_num_blocks", "nvb_layer_block_indices", "nvb_layer_get_blocks",
     "nvb_layer_set_blocks", "nvb_layer_block_device_ptr", "nvb_layer_block_bytes",
-    "nvb_mapper_last_esdf_stats", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
+    "nvb_mapper_last_esdf_stats", "nvb_mapper_esdf_time_split", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
     "nvb_mapper_kernel_launches",
 ]
 
@@ -111,6 +111,7 @@ def load():
     L.nvb_mapper_synchronize.argtypes = [vp]
     L.nvb_mapper_last_frame_block_count.argtypes = [vp, ip]
     L.nvb_mapper_last_frame_blocks.argtypes = [vp, ip, i32, ip]
+    L.nvb_mapper_join_streams.argtypes = [vp]
     L.nvb_mapper_stream.argtypes = [vp]
     L.nvb_mapper_stream.restype = vp
     L.nvb_layer_num_blocks.argtypes = [vp, i32, ip]
@@ -120,6 +121,7 @@ def load():
     L.nvb_layer_block_device_ptr.argtypes = [vp, i32, ip, C.POINTER(vp)]
     L.nvb_layer_block_bytes.argtypes = [i32]
     L.nvb_mapper_last_esdf_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.nvb_mapper_esdf_time_split.argtypes = [vp, C.POINTER(C.c_int64)]
     L.nvb_mapper_enable_profiling.argtypes = [vp, i32]
     L.nvb_mapper_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
     L.nvb_mapper_kernel_launches.argtypes = [vp]

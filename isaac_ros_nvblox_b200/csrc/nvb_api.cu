@@ -51,6 +51,12 @@ struct NvbMapper {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  // The ESDF wavefront only touches the ESDF layer: it runs on its own stream so that the next
+  // frame's raycast / compaction / TSDF update overlaps it.
+  cudaStream_t esdf_stream = nullptr;
+  cudaEvent_t esdf_ready = nullptr;  // mark + clear done on `stream`
+  cudaEvent_t esdf_done = nullptr;   // wavefront done on `esdf_stream`
+  bool esdf_in_flight = false;
   float voxel_size = 0.05f, block_size = 0.4f;
   NvbTsdfParams tp;
   NvbEsdfParams ep;
@@ -127,6 +133,21 @@ struct NvbMapper {
 
 namespace {
 
+cudaError_t syncAll(NvbMapper* m) {
+  cudaError_t e = cudaStreamSynchronize(m->stream);
+  if (e != cudaSuccess) return e;
+  if (m->esdf_stream) e = cudaStreamSynchronize(m->esdf_stream);
+  m->esdf_in_flight = false;
+  return e;
+}
+
+// Device-side join: later work on `stream` waits for the wavefront on `esdf_stream`.
+cudaError_t joinEsdf(NvbMapper* m) {
+  if (!m->esdf_in_flight) return cudaSuccess;
+  m->esdf_in_flight = false;
+  return cudaStreamWaitEvent(m->stream, m->esdf_done, 0);
+}
+
 int nextPow2(long long v) {
   long long p = 1;
   while (p < v) p <<= 1;
@@ -169,7 +190,7 @@ int reallocCopy(T** p, size_t old_n, size_t new_n, bool zero_rest, cudaStream_t 
 // Doubling growth of a layer slab (BlockMemoryPool expansion,
 // map/internal/impl/block_memory_pool_impl.h:54-73). Synchronising and rare.
 int growLayer(NvbMapper* m, DevLayer* L, int new_capacity) {
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   int count = 0;
   NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
   count = std::min(count, L->capacity);
@@ -189,7 +210,7 @@ int growLayer(NvbMapper* m, DevLayer* L, int new_capacity) {
   NVB_CUDA(cudaMalloc(&N.hash.vals, (size_t)hcap * sizeof(int)));
   launchFillU64(N.hash.keys, kEmptyKey, (size_t)hcap, m->stream);
   launchRehash(N, count, m->stream);
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   cudaFree(L->blocks), cudaFree(L->block_index), cudaFree(L->hash.keys), cudaFree(L->hash.vals);
   *L = N;
   return NVB_OK;
@@ -214,7 +235,7 @@ int allocEsdfScratch(NvbMapper* m, int old_cap, int cap) {
     NVB_CUDA(cudaMemsetAsync(q, 0xFE, (size_t)cap * 6 * sizeof(int), m->stream));
     if (m->nbr && old_cap)
       NVB_CUDA(cudaMemcpyAsync(q, m->nbr, (size_t)old_cap * 6 * sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
-    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    NVB_CUDA(syncAll(m));
     if (m->nbr) cudaFree(m->nbr);
     m->nbr = q;
   }
@@ -326,18 +347,20 @@ bool computeViewGrid(const NvbCamera& cam, const Rigid& T_L_C, float block_size,
   return true;
 }
 
-void beginStage(NvbMapper* m, int stage) {
+void beginStageOn(NvbMapper* m, int stage, cudaStream_t st) {
   if (!m->profiling) return;
   StageEvent ev;
   ev.stage = stage;
   cudaEventCreate(&ev.start), cudaEventCreate(&ev.stop);
-  cudaEventRecord(ev.start, m->stream);
+  cudaEventRecord(ev.start, st);
   m->stage_events.push_back(ev);
 }
-void endStage(NvbMapper* m) {
+void endStageOn(NvbMapper* m, cudaStream_t st) {
   if (!m->profiling) return;
-  cudaEventRecord(m->stage_events.back().stop, m->stream);
+  cudaEventRecord(m->stage_events.back().stop, st);
 }
+void beginStage(NvbMapper* m, int stage) { beginStageOn(m, stage, m->stream); }
+void endStage(NvbMapper* m) { endStageOn(m, m->stream); }
 void collectStages(NvbMapper* m) {
   for (auto& ev : m->stage_events) {
     float ms = 0.f;
@@ -370,7 +393,7 @@ int ensureTsdfCapacity(NvbMapper* m, long long new_cells) {
   pollCounts(m);
   if ((long long)m->tsdf_count_ub + new_cells <= m->tsdf.capacity) return NVB_OK;
   // refine the bound with a synchronous read
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   int count = 0;
   NVB_CUDA(cudaMemcpy(&count, m->tsdf.count, sizeof(int), cudaMemcpyDeviceToHost));
   for (int k = 0; k < kCountRing; k++) m->count_pending[k] = false;
@@ -400,7 +423,7 @@ int ensureEsdfCapacity(NvbMapper* m, long long needed_total) {
 
 int ensureFrameScratch(NvbMapper* m, const ViewGrid& g) {
   if ((size_t)g.num_words > m->bits_words_cap) {
-    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    NVB_CUDA(syncAll(m));
     const size_t cap = (size_t)(1.5 * g.num_words) + 64;  // kBufferExpansionFactor, view_calculator_impl.cuh:159
     if (m->bits) cudaFree(m->bits);
     NVB_CUDA(cudaMalloc(&m->bits, cap * sizeof(unsigned int)));
@@ -408,7 +431,7 @@ int ensureFrameScratch(NvbMapper* m, const ViewGrid& g) {
     m->bits_words_cap = cap;
   }
   if (g.linear_size > m->frame_cap) {
-    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    NVB_CUDA(syncAll(m));
     const int cap = (int)std::min<long long>((long long)(1.5 * g.linear_size) + 64, 0x7fffffff);
     if (m->frame_blocks) cudaFree(m->frame_blocks);
     NVB_CUDA(cudaMalloc(&m->frame_blocks, (size_t)cap * sizeof(int4)));
@@ -416,7 +439,7 @@ int ensureFrameScratch(NvbMapper* m, const ViewGrid& g) {
   }
   const int tiles = compactNumTiles(g);
   if (tiles > m->tile_cap) {
-    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    NVB_CUDA(syncAll(m));
     const int cap = tiles * 2;
     if (m->tile_state) cudaFree(m->tile_state);
     NVB_CUDA(cudaMalloc(&m->tile_state, (size_t)cap * sizeof(unsigned long long)));
@@ -428,7 +451,7 @@ int ensureFrameScratch(NvbMapper* m, const ViewGrid& g) {
 
 int ensureStaging(NvbMapper* m, size_t pixels) {
   if (pixels <= m->stage_pixels) return NVB_OK;
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   NVB_CUDA(cudaStreamSynchronize(m->copy_stream));
   for (int k = 0; k < kStagingBuffers; k++) {
     if (m->depth_stage[k]) cudaFree(m->depth_stage[k]);
@@ -562,7 +585,7 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
 
 int readFrameList(NvbMapper* m, int32_t* out_xyz, int32_t cap, int32_t* out_count) {
   NVB_CUDA(cudaMemcpyAsync(m->h_ints, m->frame_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   const int n = m->h_ints[0];
   if (out_count) *out_count = n;
   if (out_xyz && cap > 0 && n > 0) {
@@ -588,6 +611,8 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
   if ((rc = ensureEsdfCapacity(m, (long long)std::min(m->tsdf_count_ub, m->tsdf.capacity) + m->esdf_extra_ub))) return rc;
   m->update_seq++;
   EsdfCtx c = makeEsdfCtx(m);
+  // the previous wavefront still owns the ESDF scratch (counters, stamps, barrier)
+  NVB_CUDA(joinEsdf(m));
   beginStage(m, 3);
   if (from_tracker) {
     launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, m->stream);
@@ -605,17 +630,25 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
   launchEsdfClear(c, m->esdf.capacity, m->num_sms, m->stream);
   m->launches++;
   endStage(m);
-  beginStage(m, 5);
   int launches = 0;
   cudaError_t e;
   if (m->esdf_persistent) {
-    e = launchEsdfComputePersistent(c, m->num_sms, m->stream, &launches);
+    NVB_CUDA(cudaEventRecord(m->esdf_ready, m->stream));
+    NVB_CUDA(cudaStreamWaitEvent(m->esdf_stream, m->esdf_ready, 0));
+    beginStageOn(m, 5, m->esdf_stream);
+    e = launchEsdfComputePersistent(c, m->num_sms, m->esdf_stream, &launches);
+    endStageOn(m, m->esdf_stream);
+    if (e == cudaSuccess) {
+      NVB_CUDA(cudaEventRecord(m->esdf_done, m->esdf_stream));
+      m->esdf_in_flight = true;
+    }
   } else {
+    beginStage(m, 5);
     e = runEsdfComputeHostLoop(c, m->num_sms, m->stream, &launches);
+    endStage(m);
   }
   m->launches += launches;
   if (e != cudaSuccess) return fail(NVB_ERR_CUDA, std::string("ESDF compute launch: ") + cudaGetErrorString(e));
-  endStage(m);
   return NVB_OK;
 }
 
@@ -686,6 +719,9 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   m->esdf_persistent = opts->esdf_persistent;
   NVB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   NVB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  NVB_CUDA(cudaStreamCreateWithFlags(&m->esdf_stream, cudaStreamNonBlocking));
+  NVB_CUDA(cudaEventCreateWithFlags(&m->esdf_ready, cudaEventDisableTiming));
+  NVB_CUDA(cudaEventCreateWithFlags(&m->esdf_done, cudaEventDisableTiming));
   const int tcap = opts->tsdf_capacity_blocks > 0 ? opts->tsdf_capacity_blocks : kDefaultCapacity;
   const int ecap = std::max(opts->esdf_capacity_blocks > 0 ? opts->esdf_capacity_blocks : kDefaultCapacity, tcap);
   int rc;
@@ -700,8 +736,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   m->todo_count = m->esdf_ints + kTodoCount;
   m->frame_count = m->esdf_ints + kFrameCount;
   m->error_dev = m->esdf_ints + kError;
-  NVB_CUDA(cudaMalloc(&m->stats, 8 * sizeof(long long)));
-  NVB_CUDA(cudaMemsetAsync(m->stats, 0, 8 * sizeof(long long), m->stream));
+  NVB_CUDA(cudaMalloc(&m->stats, 16 * sizeof(long long)));
+  NVB_CUDA(cudaMemsetAsync(m->stats, 0, 16 * sizeof(long long), m->stream));
   NVB_CUDA(cudaMalloc(&m->barrier, 64));
   NVB_CUDA(cudaMemsetAsync(m->barrier, 0, 64, m->stream));
   NVB_CUDA(cudaMalloc(&m->ticket, 64));
@@ -717,7 +753,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
     NVB_CUDA(cudaEventCreateWithFlags(&m->stage_copied[k], cudaEventDisableTiming));
     NVB_CUDA(cudaEventCreateWithFlags(&m->stage_consumed[k], cudaEventDisableTiming));
   }
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   *out = m;
   return NVB_OK;
 }
@@ -725,9 +761,11 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
 void nvb_mapper_destroy(NvbMapper* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  cudaStreamSynchronize(m->stream);
+  syncAll(m);
   cudaStreamSynchronize(m->copy_stream);
   collectStages(m);
+  cudaEventDestroy(m->esdf_ready), cudaEventDestroy(m->esdf_done);
+  cudaStreamDestroy(m->esdf_stream);
   freeLayer(&m->tsdf), freeLayer(&m->esdf);
   cudaFree(m->bits), cudaFree(m->frame_blocks), cudaFree(m->tile_state), cudaFree(m->ticket);
   for (int k = 0; k < kStagingBuffers; k++) {
@@ -748,7 +786,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
 int32_t nvb_mapper_clear(NvbMapper* m) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   DevLayer* layers[2] = {&m->tsdf, &m->esdf};
   for (DevLayer* L : layers) {
     int count = 0;
@@ -771,7 +809,7 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   m->tsdf_count_ub = 0, m->tsdf_count_confirmed = 0, m->esdf_extra_ub = 0;
   m->cells_cum = 0, m->confirmed_cum = 0;
   for (int k = 0; k < kCountRing; k++) m->count_pending[k] = false;
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   return NVB_OK;
 }
 
@@ -886,12 +924,12 @@ int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, 
     if (!indexInRange(k.x, k.y, k.z)) return fail(NVB_ERR_INDEX_RANGE, "block index outside +-2^20");
   const int n = (int)v.size();
   if (n > m->xyz_upload_cap) {
-    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    NVB_CUDA(syncAll(m));
     if (m->xyz_upload) cudaFree(m->xyz_upload);
     NVB_CUDA(cudaMalloc(&m->xyz_upload, (size_t)n * 2 * 3 * sizeof(int)));
     m->xyz_upload_cap = n * 2;
   }
-  NVB_CUDA(cudaStreamSynchronize(m->stream));  // v is pageable: order the copy before it goes out of scope
+  NVB_CUDA(syncAll(m));  // v is pageable: order the copy before it goes out of scope
   NVB_CUDA(cudaMemcpy(m->xyz_upload, v.data(), (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
   int rc = enqueueEsdf(m, m->xyz_upload, n, false);
   if (rc) return rc;
@@ -901,7 +939,7 @@ int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, 
 int32_t nvb_mapper_synchronize(NvbMapper* m) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   NVB_CUDA(cudaGetLastError());
   collectStages(m);
   return checkDeviceError(m);
@@ -917,6 +955,13 @@ int32_t nvb_mapper_last_frame_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
   return readFrameList(m, out_xyz_host, cap, out_count);
+}
+
+int32_t nvb_mapper_join_streams(NvbMapper* m) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(joinEsdf(m));
+  return NVB_OK;
 }
 
 void* nvb_mapper_stream(NvbMapper* m) { return m ? (void*)m->stream : nullptr; }
@@ -936,7 +981,7 @@ int32_t nvb_layer_num_blocks(NvbMapper* m, int32_t layer, int32_t* out_count) {
   DevLayer* L = layerOf(m, layer);
   if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   int count = 0;
   NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
   *out_count = std::min(count, L->capacity);
@@ -962,7 +1007,7 @@ int32_t nvb_layer_get_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
   if (n <= 0) return NVB_OK;
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   int* xyz_dev = nullptr;
   unsigned char *out_dev = nullptr, *found_dev = nullptr;
   NVB_CUDA(cudaMalloc(&xyz_dev, (size_t)n * 3 * sizeof(int)));
@@ -971,7 +1016,7 @@ int32_t nvb_layer_get_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   NVB_CUDA(cudaMemcpy(xyz_dev, xyz_host, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
   launchGatherBlocks(*L, xyz_dev, n, out_dev, found_dev, m->stream);
   m->launches++;
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   NVB_CUDA(cudaMemcpy(out_host, out_dev, (size_t)n * L->block_bytes, cudaMemcpyDeviceToHost));
   if (found_host) NVB_CUDA(cudaMemcpy(found_host, found_dev, (size_t)n, cudaMemcpyDeviceToHost));
   cudaFree(xyz_dev), cudaFree(out_dev), cudaFree(found_dev);
@@ -997,7 +1042,7 @@ int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
     if ((rc = ensureEsdfCapacity(m, (long long)std::min(m->tsdf_count_ub, m->tsdf.capacity) + m->esdf_extra_ub))) return rc;
   }
   L = layerOf(m, layer);
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   int* xyz_dev = nullptr;
   unsigned char* in_dev = nullptr;
   NVB_CUDA(cudaMalloc(&xyz_dev, (size_t)n * 3 * sizeof(int)));
@@ -1006,7 +1051,7 @@ int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   NVB_CUDA(cudaMemcpy(in_dev, in_host, (size_t)n * L->block_bytes, cudaMemcpyHostToDevice));
   launchScatterBlocks(*L, xyz_dev, n, in_dev, m->error_dev, m->stream);
   m->launches++;
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   cudaFree(xyz_dev), cudaFree(in_dev);
   if (layer == NVB_LAYER_TSDF) {
     // the tracker is told like after an integration: a later updateEsdf must see these blocks
@@ -1024,7 +1069,7 @@ int32_t nvb_layer_block_device_ptr(NvbMapper* m, int32_t layer, const int32_t xy
   DevLayer* L = layerOf(m, layer);
   if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   // host-side probe of the device hash (small, synchronous): copy the probe window
   *out_ptr = nullptr;
   if (!indexInRange(xyz[0], xyz[1], xyz[2])) return NVB_OK;
@@ -1048,17 +1093,27 @@ int32_t nvb_layer_block_device_ptr(NvbMapper* m, int32_t layer, const int32_t xy
 int32_t nvb_mapper_last_esdf_stats(NvbMapper* m, int64_t out[8]) {
   if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   long long tmp[8];
   NVB_CUDA(cudaMemcpy(tmp, m->stats, sizeof(tmp), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 8; i++) out[i] = tmp[i];
   return NVB_OK;
 }
 
+int32_t nvb_mapper_esdf_time_split(NvbMapper* m, int64_t out[4]) {
+  if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(syncAll(m));
+  long long tmp[4];
+  NVB_CUDA(cudaMemcpy(tmp, m->stats + 8, sizeof(tmp), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; i++) out[i] = tmp[i];
+  return NVB_OK;
+}
+
 int32_t nvb_mapper_enable_profiling(NvbMapper* m, int32_t enable) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   collectStages(m);
   m->profiling = enable != 0;
   return NVB_OK;
@@ -1067,7 +1122,7 @@ int32_t nvb_mapper_enable_profiling(NvbMapper* m, int32_t enable) {
 int32_t nvb_mapper_stage_times(NvbMapper* m, double* out_ms, int64_t* out_calls, int32_t reset) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  NVB_CUDA(syncAll(m));
   collectStages(m);
   for (int i = 0; i < kNumStages; i++) {
     if (out_ms) out_ms[i] = m->stage_ms[i];

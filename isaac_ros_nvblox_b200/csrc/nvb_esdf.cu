@@ -60,7 +60,7 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
     c.ring_count[0] = c.ring_count[1] = 0;
     c.ring_count[2] = 0;  // mark-kernel "CTAs done" counter
     *c.barrier = 0;
-    for (int k = 0; k < 8; k++) c.stats[k] = 0;
+    for (int k = 0; k < 16; k++) c.stats[k] = 0;
     c.stats[0] = n;
   }
   if (i >= n) return;
@@ -490,6 +490,12 @@ __device__ void phaseNeighbors(const EsdfCtx& c, int axis, const int* cur, int n
 
 // Grid-wide barrier for the cooperative launch: monotonically increasing arrival
 // counter in L2 (reset by esdfAllocateKernel before every update).
+__device__ __forceinline__ long long globalTimerNs() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void gridBarrier(unsigned int* bar, unsigned int& generation, unsigned int nctas) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -665,6 +671,12 @@ __global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx 
   const int rounds = (max_owned + kMaxMembers - 1) / kMaxMembers;              // uniform
   int* stamp[2] = {c.stamp_a, c.stamp_b};
   long long swept = 0, faces = 0, rings = 0;
+  // CTA 0 keeps a coarse time split (ns): [8] barriers, [9] axis phases, [10] scan + sweep phases
+  long long t_bar = 0, t_axis = 0, t_sweep = 0, n_bar = 0, t0 = globalTimerNs(), t1;
+#define NVB_TICK(acc)        \
+  t1 = globalTimerNs();      \
+  acc += t1 - t0;            \
+  t0 = t1;
   const int cleared_seq = *(volatile int*)c.cleared_seq;
   for (int pass = 0; pass < 2; pass++) {
     const int* seed = pass ? c.seed_clr : c.seed_upd;
@@ -682,7 +694,10 @@ __global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx 
     }
     if (threadIdx.x == 0 && k_total > 0) atomicAdd(c.ring_count + ci, k_total);
     if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
+    NVB_TICK(t_sweep)
     gridBarrier(c.barrier, generation, nctas);
+    NVB_TICK(t_bar)
+    n_bar++;
     int n = *(volatile int*)(c.ring_count + ci);
     int k_cached = (rounds == 1) ? k_total : -1;  // s_members holds this CTA's members of ring `ring`
     swept += n;
@@ -698,7 +713,10 @@ __global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx 
           }
           axisMembers(c, axis, s_members, k, stamp[ci], ring, stamp[ni], s_slot, s_upd);
         }
+        NVB_TICK(t_axis)
         gridBarrier(c.barrier, generation, nctas);
+        NVB_TICK(t_bar)
+        n_bar++;
       }
       faces += 6ll * n;
       // Members of ring+1 = owned slots stamped during the three axis phases.
@@ -712,7 +730,10 @@ __global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx 
       }
       if (threadIdx.x == 0 && k_next > 0) atomicAdd(c.ring_count + ni, k_next);
       if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the counter of ring+2
+      NVB_TICK(t_sweep)
       gridBarrier(c.barrier, generation, nctas);
+      NVB_TICK(t_bar)
+      n_bar++;
       const int n_next = *(volatile int*)(c.ring_count + ni);
       k_cached = (rounds == 1) ? k_next : -1;
       swept += n_next;
@@ -725,11 +746,15 @@ __global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx 
     ring++;
     if (cta == 0 && threadIdx.x == 0) c.ring_count[0] = c.ring_count[1] = 0;
     gridBarrier(c.barrier, generation, nctas);
+    NVB_TICK(t_bar)
+    n_bar++;
   }
+#undef NVB_TICK
   if (cta == 0 && threadIdx.x == 0) {
     *c.ring_id = ring + 1;
     c.stats[4] = *(volatile int*)c.cleared_count;
     c.stats[5] = swept, c.stats[6] = faces, c.stats[7] = rings;
+    c.stats[8] = t_bar, c.stats[9] = t_axis, c.stats[10] = t_sweep, c.stats[11] = n_bar;
   }
 }
 

@@ -208,6 +208,11 @@ class _EsdfIntegrator:
 class Mapper:
     """nvblox::Mapper(voxel_size_m, ...) with a TSDF and an ESDF layer."""
 
+    def esdf_time_split(self):
+        out = (C.c_int64 * 4)()
+        check(self._L.nvb_mapper_esdf_time_split(self._h, out))
+        return {"barrier_ns": out[0], "axis_ns": out[1], "sweep_ns": out[2], "barriers": out[3]}
+
     def __init__(self, voxel_size_m, device=0, tsdf_capacity_blocks=0, esdf_capacity_blocks=0,
                  esdf_persistent=True):
         self._L = _lib.load()
@@ -327,6 +332,10 @@ class Mapper:
     def synchronize(self):
         check(self._L.nvb_mapper_synchronize(self._h))
         self._keep.clear()
+
+    def join_streams(self):
+        """Make later work on cuda_stream() wait for the ESDF side stream (device-side, no host sync)."""
+        check(self._L.nvb_mapper_join_streams(self._h))
 
     def last_frame_block_count(self):
         n = C.c_int32(0)

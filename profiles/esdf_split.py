@@ -1,0 +1,18 @@
+"""Prints the ESDF wavefront's time split (barrier / axis / sweep) per frame for a few frames."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as g
+g.build()
+import isaac_ros_nvblox_b200 as nvb
+from isaac_ros_nvblox_b200 import synthetic as syn
+cs = syn.PinholeCamera(); cam = nvb.Camera(cs.fu, cs.fv, cs.cu, cs.cv, cs.width, cs.height)
+seq = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(80)[:10])
+depth = torch.from_numpy(np.stack([d for d, _ in seq])).cuda()
+m = nvb.Mapper(0.05)
+for i, (_, T) in enumerate(seq):
+    m.integrate_depth_device(depth[i].data_ptr(), 480, 640, T, cam)
+    m.update_esdf(sync=False)
+    m.synchronize()
+    print(i, m.esdf_integrator().last_stats(), m.esdf_time_split())
