@@ -1,0 +1,14 @@
+// nvblox/map/blox.h -- VoxelBlock<V> (reference: nvblox/include/nvblox/map/blox.h:28-67).
+#pragma once
+#include "nvblox/map/voxels.h"
+namespace nvblox {
+template <typename VoxelType>
+struct VoxelBlock {
+  static constexpr int kVoxelsPerSide = 8;
+  static constexpr int kNumVoxels = 512;
+  VoxelType voxels[kVoxelsPerSide][kVoxelsPerSide][kVoxelsPerSide];
+};
+using TsdfBlock = VoxelBlock<TsdfVoxel>;
+using EsdfBlock = VoxelBlock<EsdfVoxel>;
+static_assert(sizeof(TsdfBlock) == 4096 && sizeof(EsdfBlock) == 10240, "block layout");
+}  // namespace nvblox

@@ -1,0 +1,19 @@
+// nvblox/map/voxels.h -- TsdfVoxel / EsdfVoxel with the reference's layout
+// (nvblox/include/nvblox/map/voxels.h:28-74); these are the bytes stored in HBM.
+#pragma once
+#include "nvblox/core/types.h"
+namespace nvblox {
+struct TsdfVoxel {
+  float distance = 0.0f;
+  float weight = 0.0f;
+};
+struct EsdfVoxel {
+  float squared_distance_vox = 0.0f;
+  Index3D parent_direction = Index3D::Zero();
+  bool is_inside = false;
+  bool observed = false;
+  bool is_site = false;
+};
+static_assert(sizeof(TsdfVoxel) == 8, "TsdfVoxel layout");
+static_assert(sizeof(EsdfVoxel) == 20, "EsdfVoxel layout");
+}  // namespace nvblox

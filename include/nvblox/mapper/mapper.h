@@ -1,0 +1,116 @@
+// nvblox/mapper/mapper.h -- nvblox::Mapper restricted to the depth-integration path
+// (reference: nvblox/include/nvblox/mapper/mapper.h:107-836), forwarding to libnvblox_b200.so.
+//   Mapper(voxel_size_m)                                   mapper.h:119-124
+//   integrateDepth(depth, T_L_C, camera)                   mapper.h:167-172
+//   updateEsdf(UpdateFullLayer)                            mapper.h:326
+//   tsdf_layer() / esdf_layer()                            mapper.h:372,393
+//   tsdf_integrator() / esdf_integrator()                  mapper.h:442,534
+#pragma once
+#include <vector>
+#include "nvblox/integrators/weighting_function.h"
+#include "nvblox/map/layer.h"
+#include "nvblox/sensors/camera.h"
+#include "nvblox/sensors/image.h"
+#include "nvblox_b200.h"
+namespace nvblox {
+
+enum class UpdateFullLayer { kNo, kYes };
+enum class ProjectiveLayerType { kTsdf, kOccupancy, kTsdfWithFreespace, kNone };
+
+// ProjectiveTsdfIntegrator's parameter surface + integrateFrame
+// (integrators/projective_tsdf_integrator.h:48-121, internal/projective_integrator.h:56-85).
+class ProjectiveTsdfIntegrator {
+ public:
+  explicit ProjectiveTsdfIntegrator(NvbMapper* m) : m_(m) {}
+  float truncation_distance_vox() const { return get().truncation_distance_vox; }
+  void truncation_distance_vox(float v) { auto p = get(); p.truncation_distance_vox = v; set(p); }
+  float max_integration_distance_m() const { return get().max_integration_distance_m; }
+  void max_integration_distance_m(float v) { auto p = get(); p.max_integration_distance_m = v; set(p); }
+  float max_weight() const { return get().max_weight; }
+  void max_weight(float v) { auto p = get(); p.max_weight = v; set(p); }
+  float invalid_depth_decay_factor() const { return get().invalid_depth_decay_factor; }
+  void invalid_depth_decay_factor(float v) { auto p = get(); p.invalid_depth_decay_factor = v; set(p); }
+  WeightingFunctionType weighting_function_type() const { return (WeightingFunctionType)get().weighting_type; }
+  void weighting_function_type(WeightingFunctionType t) { auto p = get(); p.weighting_type = (int)t; set(p); }
+  float get_truncation_distance_m(float voxel_size) const { return truncation_distance_vox() * voxel_size; }
+  // integrateFrame(depth_frame, T_L_C, camera, layer, updated_blocks)
+  void integrateFrame(const MaskedDepthImageConstView& depth, const Transform& T_L_C, const Camera& camera,
+                      TsdfLayer* /*layer of this mapper*/, std::vector<Index3D>* updated_blocks = nullptr) {
+    const MonoImageConstView& mk = depth.mask();
+    int32_t n = 0;
+    std::vector<int32_t> raw;
+    int32_t cap = 0;
+    if (updated_blocks) { cap = 1 << 16; raw.resize((size_t)cap * 3); }
+    b200_detail::check(nvb_mapper_integrate_depth(m_, depth.dataConstPtr(), mk.dataConstPtr(), (int)depth.mode(),
+                                                  depth.on_device() ? NVB_MEM_DEVICE : NVB_MEM_HOST, depth.rows(),
+                                                  depth.cols(), T_L_C.data(), camera.c_abi(), cap ? raw.data() : nullptr,
+                                                  cap, &n), "integrateFrame", nvb_last_error());
+    if (updated_blocks) {
+      if (n > cap) {
+        raw.resize((size_t)n * 3);
+        b200_detail::check(nvb_mapper_last_frame_blocks(m_, raw.data(), n, &n), "integrateFrame", nvb_last_error());
+      }
+      updated_blocks->resize((size_t)n);
+      for (int i = 0; i < n; i++) (*updated_blocks)[i] = Index3D(raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]);
+    }
+  }
+ private:
+  NvbTsdfParams get() const { NvbTsdfParams p; b200_detail::check(nvb_mapper_get_tsdf_params(m_, &p), "tsdf params", nvb_last_error()); return p; }
+  void set(const NvbTsdfParams& p) { b200_detail::check(nvb_mapper_set_tsdf_params(m_, &p), "tsdf params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+
+// EsdfIntegrator (integrators/esdf_integrator.h:45-401): parameters + integrateBlocks.
+class EsdfIntegrator {
+ public:
+  explicit EsdfIntegrator(NvbMapper* m) : m_(m) {}
+  float max_esdf_distance_m() const { return get().max_esdf_distance_m; }
+  void max_esdf_distance_m(float v) { auto p = get(); p.max_esdf_distance_m = v; set(p); }
+  float max_site_distance_vox() const { return get().max_site_distance_vox; }
+  void max_site_distance_vox(float v) { auto p = get(); p.max_site_distance_vox = v; set(p); }
+  float min_weight() const { return get().min_weight; }
+  void min_weight(float v) { auto p = get(); p.min_weight = v; set(p); }
+  // integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
+  void integrateBlocks(const TsdfLayer&, const std::vector<Index3D>& block_indices, EsdfLayer*) {
+    std::vector<int32_t> raw(block_indices.size() * 3 + 3);
+    for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
+    b200_detail::check(nvb_esdf_integrate_blocks(m_, raw.data(), (int32_t)block_indices.size()), "integrateBlocks", nvb_last_error());
+  }
+ private:
+  NvbEsdfParams get() const { NvbEsdfParams p; b200_detail::check(nvb_mapper_get_esdf_params(m_, &p), "esdf params", nvb_last_error()); return p; }
+  void set(const NvbEsdfParams& p) { b200_detail::check(nvb_mapper_set_esdf_params(m_, &p), "esdf params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+
+class Mapper {
+ public:
+  explicit Mapper(float voxel_size_m, MemoryType = MemoryType::kDevice, ProjectiveLayerType = ProjectiveLayerType::kTsdf) {
+    NvbMapperOptions o;
+    nvb_default_mapper_options(&o);
+    o.voxel_size_m = voxel_size_m;
+    b200_detail::check(nvb_mapper_create(&o, &m_), "Mapper", nvb_last_error());
+  }
+  ~Mapper() { nvb_mapper_destroy(m_); }
+  Mapper(const Mapper&) = delete;
+  Mapper& operator=(const Mapper&) = delete;
+
+  void integrateDepth(const DepthImage& depth_frame, const Transform& T_L_C, const Camera& camera) {
+    integrateDepth(MaskedDepthImageConstView(depth_frame, kMaskActiveEverywhere), T_L_C, camera);
+  }
+  void integrateDepth(const MaskedDepthImageConstView& depth_frame, const Transform& T_L_C, const Camera& camera) {
+    tsdf_integrator().integrateFrame(depth_frame, T_L_C, camera, nullptr, nullptr);
+  }
+  void updateEsdf(UpdateFullLayer full = UpdateFullLayer::kNo) {
+    b200_detail::check(nvb_mapper_update_esdf(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdf", nvb_last_error());
+  }
+  void clear() { b200_detail::check(nvb_mapper_clear(m_), "clear", nvb_last_error()); }
+  float voxel_size_m() const { return nvb_mapper_voxel_size(m_); }
+  TsdfLayer tsdf_layer() const { return TsdfLayer(m_, NVB_LAYER_TSDF); }
+  EsdfLayer esdf_layer() const { return EsdfLayer(m_, NVB_LAYER_ESDF); }
+  ProjectiveTsdfIntegrator tsdf_integrator() const { return ProjectiveTsdfIntegrator(m_); }
+  EsdfIntegrator esdf_integrator() const { return EsdfIntegrator(m_); }
+  NvbMapper* c_abi() const { return m_; }
+ private:
+  NvbMapper* m_ = nullptr;
+};
+}  // namespace nvblox

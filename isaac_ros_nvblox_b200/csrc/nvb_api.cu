@@ -544,10 +544,14 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
   ca.todo_slots = m->todo_slots;
   ca.todo_count = m->todo_count;
   launchCompactAllocate(ca, m->stream);
-  m->ticket_base += (unsigned int)compactNumTiles(grid);
+  if (compactUsesTickets(grid)) m->ticket_base += (unsigned int)compactNumTiles(grid);
   endStage(m);
   m->launches++;
 
+  if (!integrate) {
+    launchClearBits(m->bits, grid.num_words, m->stream);
+    m->launches++;
+  }
   if (integrate) {
     beginStage(m, 2);
     TsdfKernelParams p;
@@ -561,7 +565,7 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
     p.weighting_type = m->tp.weighting_type;
     const Rigid T_C_L = invertRigid(T_L_C);
     launchTsdfIntegrate(m->frame_blocks, m->frame_count, m->tsdf.blocks, depth_dev, mask_dev, mask_mode, rows, cols,
-                        T_C_L, *cam, p, m->num_sms, m->stream);
+                        T_C_L, *cam, p, m->num_sms, m->bits, grid.num_words, m->stream);
     endStage(m);
     m->launches++;
     // asynchronous read-back of the slab fill level for the host-side capacity bound

@@ -21,27 +21,11 @@
 //     (atomicExch), which replaces the sort + unique launch;
 //   * the whole wavefront (both computeEsdf calls) runs in ONE cooperative
 //     persistent launch with a grid barrier between phases.
-#include <cooperative_groups.h>
-
-#include "nvb_internal.cuh"
+#include "nvb_esdf_common.cuh"
 
 namespace nvb {
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kGroups = kThreads / 64;  // 64-thread groups, one ESDF block each
-constexpr int kBlockWords = kEsdfBlockBytes / 4;  // 2560
-
-__device__ __forceinline__ unsigned int* esdfBlockPtr(const DevLayer& L, int slot) {
-  return reinterpret_cast<unsigned int*>(L.blocks + (size_t)slot * kEsdfBlockBytes);
-}
-
-// EsdfVoxel words: [0] squared_distance_vox, [1..3] parent_direction, [4] flags
-// (byte0 is_inside, byte1 observed, byte2 is_site) -- map/voxels.h:55-74.
-__device__ __forceinline__ bool flagInside(unsigned int f) { return (f & 0xffu) != 0; }
-__device__ __forceinline__ bool flagObserved(unsigned int f) { return (f & 0xff00u) != 0; }
-__device__ __forceinline__ bool flagSite(unsigned int f) { return (f & 0xff0000u) != 0; }
 
 // ---------------------------------------------------------------------------
 // Allocation of the ESDF blocks + per-update counter reset
@@ -296,19 +280,6 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
 // (cta, num_ctas) so the persistent kernel and the per-phase kernels share them.
 // ---------------------------------------------------------------------------
 
-__device__ __forceinline__ void loadBlockGroup(unsigned int* sm, const unsigned int* g, int lane64) {
-  const uint4* src = reinterpret_cast<const uint4*>(g);
-  uint4* dst = reinterpret_cast<uint4*>(sm);
-#pragma unroll
-  for (int k = 0; k < kBlockWords / 4 / 64; k++) dst[lane64 + k * 64] = __ldcg(src + lane64 + k * 64);
-}
-__device__ __forceinline__ void storeBlockGroup(unsigned int* g, const unsigned int* sm, int lane64) {
-  uint4* dst = reinterpret_cast<uint4*>(g);
-  const uint4* src = reinterpret_cast<const uint4*>(sm);
-#pragma unroll
-  for (int k = 0; k < kBlockWords / 4 / 64; k++) __stcg(dst + lane64 + k * 64, src[lane64 + k * 64]);
-}
-
 // sweepSingleBand (:542-600): forward then backward along one line of 8 voxels.
 __device__ __forceinline__ bool sweepLine(unsigned int* s, int c0, int c1, int c2, int axis, float max_sq) {
   const int stride = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
@@ -382,37 +353,6 @@ __device__ void phaseSweep(const EsdfCtx& c, const int* src, int* list, int n, i
     if (slot >= 0 && s_changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
     __syncthreads();
   }
-}
-
-struct VoxelRegs {
-  float sq;
-  int p0, p1, p2;
-  unsigned int fl;
-};
-__device__ __forceinline__ VoxelRegs loadVoxel(const unsigned int* g) {
-  VoxelRegs v;
-  v.sq = __uint_as_float(__ldcg(g + 0));
-  v.p0 = (int)__ldcg(g + 1), v.p1 = (int)__ldcg(g + 2), v.p2 = (int)__ldcg(g + 3);
-  v.fl = __ldcg(g + 4);
-  return v;
-}
-// updateSingleNeighbor (:602-633): src -> dst across a face; `direction` is the
-// block direction from src to dst along `axis`.
-__device__ __forceinline__ bool updateSingleNeighbor(const VoxelRegs& e, VoxelRegs& nb, unsigned int* g_nb, int axis,
-                                                     int direction, float max_sq) {
-  if (!flagObserved(e.fl) || !flagObserved(nb.fl) || flagSite(nb.fl) || e.sq >= max_sq) return false;
-  int d0 = e.p0, d1 = e.p1, d2 = e.p2;
-  if (axis == 0) d0 -= direction;
-  else if (axis == 1) d1 -= direction;
-  else d2 -= direction;
-  const float pdist = (float)(d0 * d0 + (d1 * d1 + d2 * d2));
-  if (nb.sq > pdist) {
-    nb.p0 = d0, nb.p1 = d1, nb.p2 = d2, nb.sq = pdist;
-    __stcg(g_nb + 1, (unsigned)d0), __stcg(g_nb + 2, (unsigned)d1), __stcg(g_nb + 3, (unsigned)d2);
-    __stcg(g_nb + 0, __float_as_uint(pdist));
-    return true;
-  }
-  return false;
 }
 
 __device__ __forceinline__ void appendUnique(int slot, int* nxt, int* nxt_count, int* stamp_nxt, int ring_next) {
@@ -490,274 +430,6 @@ __device__ void phaseNeighbors(const EsdfCtx& c, int axis, const int* cur, int n
 
 // Grid-wide barrier for the cooperative launch: monotonically increasing arrival
 // counter in L2 (reset by esdfAllocateKernel before every update).
-__device__ __forceinline__ long long globalTimerNs() {
-  long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-__device__ __forceinline__ void gridBarrier(unsigned int* bar, unsigned int& generation, unsigned int nctas) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    generation++;
-    const unsigned int target = generation * nctas;
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (*(volatile unsigned int*)bar < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// ---------------------------------------------------------------------------
-// Persistent wavefront, ownership based.
-//
-// CTA c owns the ESDF slots {c, c + G, c + 2G, ...}. Ring membership is a per-slot
-// stamp (stamp[r & 1][slot] == r), so there are no global lists, no list atomics and
-// no sort/unique: a face update marks its destination block with one plain store,
-// and at the start of every sweep phase each CTA scans the stamps of the slots it owns
-// to find its members (they stay in shared memory for the three axis phases of the
-// next ring). Neighbour slots come from the nbr table built at allocation time.
-// Per ring: 3 axis phases + 1 sweep phase, one grid barrier each; the only global
-// atomic is one add per CTA per ring for the ring's block count.
-// ---------------------------------------------------------------------------
-constexpr int kMaxMembers = 1024;  // cached owned members per CTA (maps up to G*1024 blocks scan in one round)
-
-__device__ __forceinline__ int neighborSlot(const EsdfCtx& c, int slot, int dir) {
-  int v = __ldcg(c.nbr + 6 * slot + dir);
-  if (v < -1) {  // unknown (block created outside the ESDF update path): resolve through the hash once
-    const int* bi = c.esdf.block_index + 3 * slot;
-    int x = bi[0], y = bi[1], z = bi[2];
-    const int d = (dir & 1) ? -1 : 1;
-    if ((dir >> 1) == 0) x += d;
-    else if ((dir >> 1) == 1) y += d;
-    else z += d;
-    v = hashFind(c.esdf.hash, x, y, z);
-    c.nbr[6 * slot + dir] = v;
-  }
-  return v;
-}
-
-// Scan the owned slots for `tag[slot] == value`; compact the hits into s_members
-// (ascending slot order). Returns the number of members. If stamp_out is non-null
-// the members are also stamped (initial list of a computeEsdf call).
-__device__ int scanOwned(const int* tag, int value, int nslots, int cta, int nctas, int first_candidate,
-                         int num_candidates, int* s_members, int* s_scan, int* stamp_out, int stamp_value) {
-  const int tid = threadIdx.x;
-  __shared__ int s_count;
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  for (int base = 0; base < num_candidates; base += kThreads) {
-    const int k = first_candidate + base + tid;
-    const int slot = cta + k * nctas;
-    const bool hit = (base + tid < num_candidates) && slot < nslots && __ldcg(tag + slot) == value;
-    const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
-    if ((tid & 31) == 0) s_scan[tid >> 5] = __popc(ballot);
-    __syncthreads();
-    int offset = s_count;
-    for (int wq = 0; wq < (tid >> 5); wq++) offset += s_scan[wq];
-    if (hit) {
-      const int pos = offset + __popc(ballot & ((1u << (tid & 31)) - 1u));
-      if (pos < kMaxMembers) s_members[pos] = slot;
-      if (stamp_out) stamp_out[slot] = stamp_value;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int wq = 0; wq < kThreads / 32; wq++) tot += s_scan[wq];
-      s_count += tot;
-    }
-    __syncthreads();
-  }
-  return s_count;
-}
-
-// In-block sweeps of the cached members, kGroups blocks at a time (sweepBlockBandKernel, :1390-1431).
-__device__ void sweepMembers(const EsdfCtx& c, const int* s_members, int k, unsigned int* smem, int* s_changed) {
-  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
-  unsigned int* sm = smem + group * kBlockWords;
-  const int a = lane64 >> 3, b = lane64 & 7;
-  for (int base = 0; base < k; base += kGroups) {
-    const int item = base + group;
-    const int slot = item < k ? s_members[item] : -1;
-    if (lane64 == 0) s_changed[group] = 0;
-    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
-    __syncthreads();
-    bool ch = false;
-    if (slot >= 0) ch |= sweepLine(sm, 0, a, b, 0, c.max_sq);
-    __syncthreads();
-    if (slot >= 0) ch |= sweepLine(sm, a, 0, b, 1, c.max_sq);
-    __syncthreads();
-    if (slot >= 0) ch |= sweepLine(sm, a, b, 0, 2, c.max_sq);
-    if (ch) s_changed[group] = 1;
-    __syncthreads();
-    if (slot >= 0 && s_changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
-    __syncthreads();
-  }
-}
-
-// The two passes of one axis over the cached members (see phaseNeighbors for the
-// interface-ownership rule). Destination blocks are stamped for ring+1 with a plain store.
-__device__ void axisMembers(const EsdfCtx& c, int axis, const int* s_members, int k, const int* stamp_cur, int ring,
-                            int* stamp_nxt, int* s_slot, int* s_upd) {
-  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
-  const int entry_in_cta = group >> 1, side = group & 1;  // side 0 = hi (+dir), 1 = lo (-dir)
-  const int u = lane64 >> 3, w = lane64 & 7;
-  const int strideA = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
-  const int faceBase = (axis == 0) ? (u * 8 + w) : ((axis == 1) ? (u * 64 + w) : (u * 64 + w * 8));
-  const int vHi = faceBase + (kVps - 1) * strideA, vLo = faceBase;
-  for (int base = 0; base < k; base += kGroups / 2) {
-    const int item = base + entry_in_cta;
-    if (lane64 == 0) {
-      int mine = -1, other = -1;
-      if (item < k) {
-        mine = s_members[item];
-        other = neighborSlot(c, mine, axis * 2 + side);
-      }
-      s_slot[group * 2] = mine;
-      s_slot[group * 2 + 1] = other;
-      s_upd[group * 2] = 0;
-      s_upd[group * 2 + 1] = 0;
-    }
-    __syncthreads();
-    const int mine = s_slot[group * 2], other = s_slot[group * 2 + 1];
-    if (mine >= 0 && other >= 0) {
-      if (side == 0) {
-        unsigned int* gA = esdfBlockPtr(c.esdf, mine) + vHi * kEsdfVoxelWords;
-        unsigned int* gB = esdfBlockPtr(c.esdf, other) + vLo * kEsdfVoxelWords;
-        const int other_stamp = __ldcg(stamp_cur + other);
-        VoxelRegs A = loadVoxel(gA), B = loadVoxel(gB);
-        if (updateSingleNeighbor(A, B, gB, axis, +1, c.max_sq)) s_upd[group * 2 + 1] = 1;  // B updated
-        if (other_stamp == ring) {
-          if (updateSingleNeighbor(B, A, gA, axis, -1, c.max_sq)) s_upd[group * 2] = 1;  // A updated
-        }
-      } else {
-        const int other_stamp = __ldcg(stamp_cur + other);
-        if (other_stamp != ring) {
-          unsigned int* gA = esdfBlockPtr(c.esdf, other) + vHi * kEsdfVoxelWords;
-          unsigned int* gB = esdfBlockPtr(c.esdf, mine) + vLo * kEsdfVoxelWords;
-          VoxelRegs A = loadVoxel(gA), B = loadVoxel(gB);
-          if (updateSingleNeighbor(B, A, gA, axis, -1, c.max_sq)) s_upd[group * 2 + 1] = 1;  // A (= other) updated
-        }
-      }
-    }
-    __syncthreads();
-    if (lane64 == 0 && mine >= 0 && other >= 0) {
-      if (s_upd[group * 2]) __stcg(stamp_nxt + mine, ring + 1);
-      if (s_upd[group * 2 + 1]) __stcg(stamp_nxt + other, ring + 1);
-    }
-    __syncthreads();
-  }
-}
-
-// computeEsdf (:1465-1496) twice -- blocks with sites, then the persistent cleared
-// set (:254-257) -- in one cooperative launch.
-__global__ void __launch_bounds__(kThreads) esdfComputePersistentKernel(EsdfCtx c) {
-  extern __shared__ __align__(16) unsigned int smem[];
-  __shared__ int s_changed[kGroups];
-  __shared__ int s_slot[kGroups * 2];
-  __shared__ int s_upd[kGroups * 2];
-  __shared__ int s_scan[kThreads / 32];
-  __shared__ int s_members[kMaxMembers];
-  const int cta = blockIdx.x, nctas = gridDim.x;
-  // Empty block list: integrateBlocksTemplate returns before touching anything (:226-228).
-  if (*(volatile int*)c.work_count == 0) return;
-  unsigned int generation = 0;
-  int ring = *(volatile int*)c.ring_id;
-  const int nslots = min(*(volatile int*)c.esdf.count, c.esdf.capacity);
-  const int owned = (nslots > cta) ? (nslots - cta + nctas - 1) / nctas : 0;  // candidates of this CTA
-  const int max_owned = (nslots + nctas - 1) / nctas;                         // uniform bound
-  const int rounds = (max_owned + kMaxMembers - 1) / kMaxMembers;              // uniform
-  int* stamp[2] = {c.stamp_a, c.stamp_b};
-  long long swept = 0, faces = 0, rings = 0;
-  // CTA 0 keeps a coarse time split (ns): [8] barriers, [9] axis phases, [10] scan + sweep phases
-  long long t_bar = 0, t_axis = 0, t_sweep = 0, n_bar = 0, t0 = globalTimerNs(), t1;
-#define NVB_TICK(acc)        \
-  t1 = globalTimerNs();      \
-  acc += t1 - t0;            \
-  t0 = t1;
-  const int cleared_seq = *(volatile int*)c.cleared_seq;
-  for (int pass = 0; pass < 2; pass++) {
-    const int* seed = pass ? c.seed_clr : c.seed_upd;
-    const int seed_value = pass ? cleared_seq : c.update_seq;
-    if (pass == 1 && cleared_seq == 0) break;  // the clear pass never ran: the cleared set is empty
-    int ci = ring & 1;
-    // Initial sweep of the seed set; its members are stamped as ring `ring`.
-    int k_total = 0;
-    for (int r = 0; r < rounds; r++) {
-      const int first = r * kMaxMembers;
-      const int ncand = max(0, min(kMaxMembers, owned - first));
-      const int k = scanOwned(seed, seed_value, nslots, cta, nctas, first, ncand, s_members, s_scan, stamp[ci], ring);
-      sweepMembers(c, s_members, k, smem, s_changed);
-      k_total += k;
-    }
-    if (threadIdx.x == 0 && k_total > 0) atomicAdd(c.ring_count + ci, k_total);
-    if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
-    NVB_TICK(t_sweep)
-    gridBarrier(c.barrier, generation, nctas);
-    NVB_TICK(t_bar)
-    n_bar++;
-    int n = *(volatile int*)(c.ring_count + ci);
-    int k_cached = (rounds == 1) ? k_total : -1;  // s_members holds this CTA's members of ring `ring`
-    swept += n;
-    while (n > 0) {
-      const int ni = ci ^ 1;
-      for (int axis = 0; axis < 3; axis++) {
-        for (int r = 0; r < rounds; r++) {
-          int k = k_cached;
-          if (k < 0) {
-            const int first = r * kMaxMembers;
-            const int ncand = max(0, min(kMaxMembers, owned - first));
-            k = scanOwned(stamp[ci], ring, nslots, cta, nctas, first, ncand, s_members, s_scan, nullptr, 0);
-          }
-          axisMembers(c, axis, s_members, k, stamp[ci], ring, stamp[ni], s_slot, s_upd);
-        }
-        NVB_TICK(t_axis)
-        gridBarrier(c.barrier, generation, nctas);
-        NVB_TICK(t_bar)
-        n_bar++;
-      }
-      faces += 6ll * n;
-      // Members of ring+1 = owned slots stamped during the three axis phases.
-      int k_next = 0;
-      for (int r = 0; r < rounds; r++) {
-        const int first = r * kMaxMembers;
-        const int ncand = max(0, min(kMaxMembers, owned - first));
-        const int k = scanOwned(stamp[ni], ring + 1, nslots, cta, nctas, first, ncand, s_members, s_scan, nullptr, 0);
-        sweepMembers(c, s_members, k, smem, s_changed);
-        k_next += k;
-      }
-      if (threadIdx.x == 0 && k_next > 0) atomicAdd(c.ring_count + ni, k_next);
-      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the counter of ring+2
-      NVB_TICK(t_sweep)
-      gridBarrier(c.barrier, generation, nctas);
-      NVB_TICK(t_bar)
-      n_bar++;
-      const int n_next = *(volatile int*)(c.ring_count + ni);
-      k_cached = (rounds == 1) ? k_next : -1;
-      swept += n_next;
-      rings++;
-      ring++;
-      ci = ni;
-      n = n_next;
-    }
-    // both counters must be zero for the next pass; ring_count[ci] held n == 0 already
-    ring++;
-    if (cta == 0 && threadIdx.x == 0) c.ring_count[0] = c.ring_count[1] = 0;
-    gridBarrier(c.barrier, generation, nctas);
-    NVB_TICK(t_bar)
-    n_bar++;
-  }
-#undef NVB_TICK
-  if (cta == 0 && threadIdx.x == 0) {
-    *c.ring_id = ring + 1;
-    c.stats[4] = *(volatile int*)c.cleared_count;
-    c.stats[5] = swept, c.stats[6] = faces, c.stats[7] = rings;
-    c.stats[8] = t_bar, c.stats[9] = t_axis, c.stats[10] = t_sweep, c.stats[11] = n_bar;
-  }
-}
-
 // Per-phase kernels for the host-driven loop (reference-like orchestration).
 __global__ void __launch_bounds__(kThreads) esdfSweepKernel(EsdfCtx c, const int* src, int* list, const int* n_dev,
                                                             int* stamp, int ring) {
@@ -799,32 +471,6 @@ void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaSt
   if (esdf_count_upper < grid) grid = esdf_count_upper;
   if (grid < 1) grid = 1;
   esdfClearKernel<<<grid, kThreads, 0, stream>>>(c);
-}
-
-int esdfPersistentMaxCtas(int num_sms) {
-  static int per_sm = -1;
-  if (per_sm < 0) {
-    cudaFuncSetAttribute(esdfComputePersistentKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)kSweepSmemBytes);
-    int v = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, esdfComputePersistentKernel, kThreads,
-                                                      kSweepSmemBytes) != cudaSuccess)
-      v = 0;
-    per_sm = v;
-  }
-  return per_sm * num_sms;
-}
-
-cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches) {
-  const int max_ctas = esdfPersistentMaxCtas(num_sms);
-  if (max_ctas <= 0) return cudaErrorLaunchOutOfResources;
-  // One CTA per SM: the wavefront is latency-bound, more CTAs only make the barrier slower.
-  int grid = num_sms < max_ctas ? num_sms : max_ctas;
-  EsdfCtx cc = c;
-  void* args[] = {&cc};
-  (*launches)++;
-  return cudaLaunchCooperativeKernel((const void*)esdfComputePersistentKernel, dim3(grid), dim3(kThreads), args,
-                                     kSweepSmemBytes, stream);
 }
 
 // One launch per phase; the host reads the ring's block count after every ring,

@@ -1,0 +1,348 @@
+// nvb_esdf_wave.cu -- the ESDF wavefront (computeEsdf, nvblox/src/integrators/esdf_integrator.cu:1465-1496)
+// as ONE cooperative persistent launch.
+//
+// computeEsdf(list): sweep(list); while (list not empty) { list = updateNeighborBands(list); sweep(list); }
+// runs twice per update: for the blocks with sites and for the persistent "cleared" set (:254-257).
+//
+// Ownership instead of lists. CTA c owns the ESDF slots {c, c+G, c+2G, ...} (G = #SMs). Ring
+// membership is a per-slot stamp (stamp[r & 1][slot] == r); a face update marks its destination
+// block for ring r+1 with one plain store; at the start of every sweep phase each CTA scans the
+// stamps of the slots it owns, keeps its members in shared memory for the three axis phases of
+// the next ring, and prefetches their six neighbour slots from the nbr table. No global lists,
+// no list atomics, no sort/unique, no per-ring hash lookups. The only global atomic is one add
+// per CTA per ring for the ring's block count (loop termination).
+//
+// Latency shape (measured, profiles/): a grid barrier costs ~1.25 us on 148 SMs and a ring needs
+// four (3 axes in order + sweep), so a phase has to be ONE round trip to L2 deep, for every CTA.
+// Hence 1024-thread CTAs (16 groups of 64 threads): the ~2 +- 2 members a CTA owns per ring are
+// all processed concurrently -- both interfaces of 8 members per axis iteration, 16 blocks per
+// sweep iteration (16 x 10 KiB of shared memory) -- instead of looping over them; sweeps run on
+// registers (a line of 8 voxels is loaded once, walked forward and backward, changed voxels are
+// written back).
+#include "nvb_esdf_common.cuh"
+
+namespace nvb {
+
+namespace {
+
+constexpr int kWT = 1024;               // threads per CTA
+constexpr int kWG = kWT / 64;           // 16 groups of 64 threads
+constexpr int kWaveMaxMembers = 1024;   // owned candidates scanned per round
+constexpr int kNbrCache = 128;          // members whose neighbour slots are cached in smem
+constexpr size_t kWaveSmemBytes = (size_t)kWG * kEsdfBlockBytes;  // 160 KiB of sweep buffers
+
+__device__ __forceinline__ int resolveNeighbor(const EsdfCtx& c, int slot, int dir) {
+  int v = __ldcg(c.nbr + 6 * slot + dir);
+  if (v < -1) {  // unknown (block created outside the ESDF update path): resolve through the hash once
+    const int* bi = c.esdf.block_index + 3 * slot;
+    int x = bi[0], y = bi[1], z = bi[2];
+    const int d = (dir & 1) ? -1 : 1;
+    if ((dir >> 1) == 0) x += d;
+    else if ((dir >> 1) == 1) y += d;
+    else z += d;
+    v = hashFind(c.esdf.hash, x, y, z);
+    c.nbr[6 * slot + dir] = v;
+  }
+  return v;
+}
+
+struct WaveShared {
+  int members[kWaveMaxMembers];
+  int nbr[kNbrCache * 6];
+  int scan[kWT / 32];
+  int count;
+  int changed[kWG];
+  int slot[kWG * 2];
+  int upd[kWG * 2];
+};
+
+// Scan up to kWaveMaxMembers owned candidates (one per thread) for tag[slot] == value and compact
+// the hits into sh.members. Optionally stamps the hits (initial list). Returns the member count.
+__device__ int scanOwned(WaveShared& sh, const int* tag, int value, int nslots, int cta, int nctas, int first,
+                         int ncand, int* stamp_out, int stamp_value) {
+  const int tid = threadIdx.x;
+  const int slot = cta + (first + tid) * nctas;
+  const bool hit = tid < ncand && slot < nslots && __ldcg(tag + slot) == value;
+  const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+  if ((tid & 31) == 0) sh.scan[tid >> 5] = __popc(ballot);
+  __syncthreads();
+  int offset = 0;
+  for (int w = 0; w < (tid >> 5); w++) offset += sh.scan[w];
+  if (hit) {
+    sh.members[offset + __popc(ballot & ((1u << (tid & 31)) - 1u))] = slot;
+    if (stamp_out) stamp_out[slot] = stamp_value;
+  }
+  if (tid == kWT - 1) sh.count = offset + __popc(ballot);
+  __syncthreads();
+  return sh.count;
+}
+
+// Neighbour slots of the first kNbrCache members -> shared memory (one thread per (member, dir)).
+__device__ __forceinline__ void prefetchNeighbors(const EsdfCtx& c, WaveShared& sh, int k) {
+  const int tid = threadIdx.x;
+  const int kc = k < kNbrCache ? k : kNbrCache;
+  if (tid < kc * 6) sh.nbr[tid] = resolveNeighbor(c, sh.members[tid / 6], tid % 6);
+}
+
+// sweepSingleBand (:542-600) on registers. `s` points at the line's first voxel in shared memory,
+// `stride` is the voxel stride along the line; (c0,c1,c2) are the voxel coordinates at position 0.
+__device__ __forceinline__ bool sweepLineRegs(unsigned int* s, int stride, int c0, int c1, int c2, int axis,
+                                              float max_sq) {
+  float sq[kVps];
+  int p0[kVps], p1[kVps], p2[kVps];
+  unsigned int obs = 0, site = 0, dirty = 0;
+#pragma unroll
+  for (int i = 0; i < kVps; i++) {
+    const unsigned int* e = s + i * stride * kEsdfVoxelWords;
+    sq[i] = __uint_as_float(e[0]);
+    p0[i] = (int)e[1], p1[i] = (int)e[2], p2[i] = (int)e[3];
+    const unsigned int fl = e[4];
+    if (flagObserved(fl)) obs |= 1u << i;
+    if (flagSite(fl)) site |= 1u << i;
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    int l0 = 0, l1 = 0, l2 = 0;
+    bool found = false;
+#pragma unroll
+    for (int k = 0; k < kVps; k++) {
+      const int i = pass ? (kVps - 1 - k) : k;
+      if (!((obs >> i) & 1u)) continue;
+      const int v0 = c0 + (axis == 0 ? i : 0), v1 = c1 + (axis == 1 ? i : 0), v2 = c2 + (axis == 2 ? i : 0);
+      if ((site >> i) & 1u) {
+        l0 = v0, l1 = v1, l2 = v2;
+        found = true;
+      } else if (!found) {
+        if (sq[i] < max_sq) {
+          found = true;
+          l0 = p0[i] + v0, l1 = p1[i] + v1, l2 = p2[i] + v2;
+        }
+      } else {
+        const int d0 = l0 - v0, d1 = l1 - v1, d2 = l2 - v2;
+        const float pdist = (float)(d0 * d0 + (d1 * d1 + d2 * d2));
+        if (sq[i] > pdist) {
+          p0[i] = d0, p1[i] = d1, p2[i] = d2, sq[i] = pdist;
+          dirty |= 1u << i;
+        } else if (sq[i] < max_sq) {
+          l0 = p0[i] + v0, l1 = p1[i] + v1, l2 = p2[i] + v2;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kVps; i++) {
+    if ((dirty >> i) & 1u) {
+      unsigned int* e = s + i * stride * kEsdfVoxelWords;
+      e[0] = __float_as_uint(sq[i]);
+      e[1] = (unsigned)p0[i], e[2] = (unsigned)p1[i], e[3] = (unsigned)p2[i];
+    }
+  }
+  return dirty != 0;
+}
+
+// sweepBlockBandKernel (:1390-1431) for the cached members, kWG blocks at a time.
+__device__ void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned int* smem) {
+  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
+  unsigned int* sm = smem + group * kBlockWords;
+  const int a = lane64 >> 3, b = lane64 & 7;
+  for (int base = 0; base < k; base += kWG) {
+    const int item = base + group;
+    const int slot = item < k ? sh.members[item] : -1;
+    if (lane64 == 0) sh.changed[group] = 0;
+    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
+    __syncthreads();
+    bool ch = false;
+    if (slot >= 0) ch |= sweepLineRegs(sm + (a * 8 + b) * kEsdfVoxelWords, 64, 0, a, b, 0, c.max_sq);
+    __syncthreads();
+    if (slot >= 0) ch |= sweepLineRegs(sm + (a * 64 + b) * kEsdfVoxelWords, 8, a, 0, b, 1, c.max_sq);
+    __syncthreads();
+    if (slot >= 0) ch |= sweepLineRegs(sm + (a * 64 + b * 8) * kEsdfVoxelWords, 1, a, b, 0, 2, c.max_sq);
+    if (ch) sh.changed[group] = 1;
+    __syncthreads();
+    if (slot >= 0 && sh.changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
+    __syncthreads();
+  }
+}
+
+// The +dir and -dir passes of one axis of updateNeighborBands (:1323-1386), fused per block
+// interface (see nvb_esdf.cu phaseNeighbors for the ownership rule and why it is exact):
+//   group side 0 ("hi"): interface (b, b+d): P = b -> b+d, then Q = b+d -> b if b+d is a member;
+//   group side 1 ("lo"): interface (b-d, b) only when b-d is NOT a member: Q = b -> b-d.
+// Destination blocks are stamped for ring+1 with a plain store.
+__device__ void axisMembers(const EsdfCtx& c, WaveShared& sh, int axis, int k, const int* stamp_cur, int ring,
+                            int* stamp_nxt) {
+  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
+  const int entry_in_cta = group >> 1, side = group & 1;
+  const int u = lane64 >> 3, w = lane64 & 7;
+  const int strideA = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
+  const int faceBase = (axis == 0) ? (u * 8 + w) : ((axis == 1) ? (u * 64 + w) : (u * 64 + w * 8));
+  const int vHi = faceBase + (kVps - 1) * strideA, vLo = faceBase;
+  for (int base = 0; base < k; base += kWG / 2) {
+    const int item = base + entry_in_cta;
+    if (lane64 == 0) {
+      int mine = -1, other = -1;
+      if (item < k) {
+        mine = sh.members[item];
+        other = item < kNbrCache ? sh.nbr[item * 6 + axis * 2 + side] : resolveNeighbor(c, mine, axis * 2 + side);
+      }
+      sh.slot[group * 2] = mine;
+      sh.slot[group * 2 + 1] = other;
+      sh.upd[group * 2] = 0;
+      sh.upd[group * 2 + 1] = 0;
+    }
+    __syncthreads();
+    const int mine = sh.slot[group * 2], other = sh.slot[group * 2 + 1];
+    if (mine >= 0 && other >= 0) {
+      // membership of the neighbour and the two face voxels are fetched in the same round trip
+      const int other_stamp = __ldcg(stamp_cur + other);
+      unsigned int* gHi = esdfBlockPtr(c.esdf, side == 0 ? mine : other) + vHi * kEsdfVoxelWords;   // A.hi
+      unsigned int* gLo = esdfBlockPtr(c.esdf, side == 0 ? other : mine) + vLo * kEsdfVoxelWords;   // B.lo
+      VoxelRegs A = loadVoxel(gHi), B = loadVoxel(gLo);
+      if (side == 0) {
+        if (updateSingleNeighbor(A, B, gLo, axis, +1, c.max_sq)) sh.upd[group * 2 + 1] = 1;  // B (= other) updated
+        if (other_stamp == ring) {
+          if (updateSingleNeighbor(B, A, gHi, axis, -1, c.max_sq)) sh.upd[group * 2] = 1;  // A (= mine) updated
+        }
+      } else if (other_stamp != ring) {
+        if (updateSingleNeighbor(B, A, gHi, axis, -1, c.max_sq)) sh.upd[group * 2 + 1] = 1;  // A (= other) updated
+      }
+    }
+    __syncthreads();
+    if (lane64 == 0 && mine >= 0 && other >= 0) {
+      if (sh.upd[group * 2]) __stcg(stamp_nxt + mine, ring + 1);
+      if (sh.upd[group * 2 + 1]) __stcg(stamp_nxt + other, ring + 1);
+    }
+    // the next iteration's writes to sh.slot/sh.upd are ordered by the __syncthreads above
+  }
+}
+
+__global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
+  extern __shared__ __align__(16) unsigned int smem[];
+  __shared__ WaveShared sh;
+  const int cta = blockIdx.x, nctas = gridDim.x;
+  // Empty block list: integrateBlocksTemplate returns before touching anything (:226-228).
+  if (*(volatile int*)c.work_count == 0) return;
+  unsigned int generation = 0;
+  int ring = *(volatile int*)c.ring_id;
+  const int nslots = min(*(volatile int*)c.esdf.count, c.esdf.capacity);
+  const int owned = (nslots > cta) ? (nslots - cta + nctas - 1) / nctas : 0;  // candidates of this CTA
+  const int max_owned = (nslots + nctas - 1) / nctas;                         // uniform bound
+  const int rounds = (max_owned + kWaveMaxMembers - 1) / kWaveMaxMembers;      // uniform
+  int* stamp[2] = {c.stamp_a, c.stamp_b};
+  long long swept = 0, faces = 0, rings = 0;
+  // CTA 0 keeps a coarse time split (ns): barriers (incl. waiting for the slowest CTA), axis phases,
+  // scan + sweep phases
+  long long t_bar = 0, t_axis = 0, t_sweep = 0, n_bar = 0, t0 = globalTimerNs(), t1;
+#define NVB_TICK(acc)   \
+  t1 = globalTimerNs(); \
+  acc += t1 - t0;       \
+  t0 = t1;
+  const int cleared_seq = *(volatile int*)c.cleared_seq;
+  for (int pass = 0; pass < 2; pass++) {
+    const int* seed = pass ? c.seed_clr : c.seed_upd;
+    const int seed_value = pass ? cleared_seq : c.update_seq;
+    if (pass == 1 && cleared_seq == 0) break;  // the clear pass never ran: the cleared set is empty
+    int ci = ring & 1;
+    // Initial sweep of the seed set; its members are stamped as ring `ring`.
+    int k_total = 0;
+    for (int r = 0; r < rounds; r++) {
+      const int first = r * kWaveMaxMembers;
+      const int ncand = max(0, min(kWaveMaxMembers, owned - first));
+      const int k = scanOwned(sh, seed, seed_value, nslots, cta, nctas, first, ncand, stamp[ci], ring);
+      if (rounds == 1) prefetchNeighbors(c, sh, k);
+      sweepMembers(c, sh, k, smem);
+      k_total += k;
+    }
+    if (threadIdx.x == 0 && k_total > 0) atomicAdd(c.ring_count + ci, k_total);
+    if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
+    NVB_TICK(t_sweep)
+    gridBarrier(c.barrier, generation, nctas);
+    NVB_TICK(t_bar)
+    n_bar++;
+    int n = *(volatile int*)(c.ring_count + ci);
+    int k_cached = (rounds == 1) ? k_total : -1;  // sh.members / sh.nbr hold this CTA's members of ring `ring`
+    swept += n;
+    while (n > 0) {
+      const int ni = ci ^ 1;
+      for (int axis = 0; axis < 3; axis++) {
+        for (int r = 0; r < rounds; r++) {
+          int k = k_cached;
+          if (k < 0) {
+            const int first = r * kWaveMaxMembers;
+            const int ncand = max(0, min(kWaveMaxMembers, owned - first));
+            k = scanOwned(sh, stamp[ci], ring, nslots, cta, nctas, first, ncand, nullptr, 0);
+            prefetchNeighbors(c, sh, k);
+            __syncthreads();
+          }
+          axisMembers(c, sh, axis, k, stamp[ci], ring, stamp[ni]);
+        }
+        NVB_TICK(t_axis)
+        gridBarrier(c.barrier, generation, nctas);
+        NVB_TICK(t_bar)
+        n_bar++;
+      }
+      faces += 6ll * n;
+      // Members of ring+1 = owned slots stamped during the three axis phases.
+      int k_next = 0;
+      for (int r = 0; r < rounds; r++) {
+        const int first = r * kWaveMaxMembers;
+        const int ncand = max(0, min(kWaveMaxMembers, owned - first));
+        const int k = scanOwned(sh, stamp[ni], ring + 1, nslots, cta, nctas, first, ncand, nullptr, 0);
+        if (rounds == 1) prefetchNeighbors(c, sh, k);
+        sweepMembers(c, sh, k, smem);
+        k_next += k;
+      }
+      if (threadIdx.x == 0 && k_next > 0) atomicAdd(c.ring_count + ni, k_next);
+      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the counter of ring+2
+      NVB_TICK(t_sweep)
+      gridBarrier(c.barrier, generation, nctas);
+      NVB_TICK(t_bar)
+      n_bar++;
+      const int n_next = *(volatile int*)(c.ring_count + ni);
+      k_cached = (rounds == 1) ? k_next : -1;
+      swept += n_next;
+      rings++;
+      ring++;
+      ci = ni;
+      n = n_next;
+    }
+    ring++;
+    if (cta == 0 && threadIdx.x == 0) c.ring_count[0] = c.ring_count[1] = 0;
+    gridBarrier(c.barrier, generation, nctas);
+    NVB_TICK(t_bar)
+    n_bar++;
+  }
+#undef NVB_TICK
+  if (cta == 0 && threadIdx.x == 0) {
+    *c.ring_id = ring + 1;
+    c.stats[4] = *(volatile int*)c.cleared_count;
+    c.stats[5] = swept, c.stats[6] = faces, c.stats[7] = rings;
+    c.stats[8] = t_bar, c.stats[9] = t_axis, c.stats[10] = t_sweep, c.stats[11] = n_bar;
+  }
+}
+
+}  // namespace
+
+int esdfPersistentMaxCtas(int num_sms) {
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    cudaFuncSetAttribute(esdfWaveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmemBytes);
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, esdfWaveKernel, kWT, kWaveSmemBytes) != cudaSuccess) v = 0;
+    per_sm = v;
+  }
+  return per_sm * num_sms;
+}
+
+cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches) {
+  const int max_ctas = esdfPersistentMaxCtas(num_sms);
+  if (max_ctas <= 0) return cudaErrorLaunchOutOfResources;
+  // One CTA per SM: the wavefront is latency-bound, more CTAs only make the barrier slower.
+  int grid = num_sms < max_ctas ? num_sms : max_ctas;
+  EsdfCtx cc = c;
+  void* args[] = {&cc};
+  (*launches)++;
+  return cudaLaunchCooperativeKernel((const void*)esdfWaveKernel, dim3(grid), dim3(kWT), args, kWaveSmemBytes, stream);
+}
+
+}  // namespace nvb

@@ -210,13 +210,17 @@ struct CompactArgs {
   int* todo_count;
 };
 int compactNumTiles(const ViewGrid& grid);
+bool compactUsesTickets(const ViewGrid& grid);
+// The compaction leaves the bitset set; it is zeroed by the TSDF kernel's prologue or, on the
+// view-only path, by this launch.
+void launchClearBits(unsigned int* bits, int num_words, cudaStream_t stream);
 void launchCompactAllocate(const CompactArgs& args, cudaStream_t stream);
 
 // nvb_tsdf.cu
 void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* tsdf_blocks,
                          const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
                          const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p, int num_sms,
-                         cudaStream_t stream);
+                         unsigned int* bits_to_clear, int num_words, cudaStream_t stream);
 
 // nvb_esdf.cu
 struct EsdfCtx {

@@ -31,6 +31,8 @@ struct TsdfArgs {
   Rigid T_C_L;
   NvbCamera cam;
   TsdfKernelParams p;
+  unsigned int* bits_to_clear;  // view bitset of this frame: consumed by the compaction, zeroed here
+  int num_words;
 };
 
 // WeightingFunction (weighting_function_impl.h:29-117)
@@ -124,6 +126,7 @@ __device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, 
 __global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant__ TsdfArgs a) {
   const int n = *a.frame_count;
   const int tid = threadIdx.x;
+  for (int w = blockIdx.x * blockDim.x + tid; w < a.num_words; w += gridDim.x * blockDim.x) a.bits_to_clear[w] = 0;
   // voxel pair owned by this thread: linear voxel offset 2*tid = x*64 + y*8 + z
   const int vx = tid >> 5, vy = (tid >> 2) & 7, vz = (tid & 3) * 2;
   int i = blockIdx.x;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant
 void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* tsdf_blocks,
                          const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
                          const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p, int num_sms,
-                         cudaStream_t stream) {
+                         unsigned int* bits_to_clear, int num_words, cudaStream_t stream) {
   TsdfArgs a;
   a.frame_blocks = frame_blocks;
   a.frame_count = frame_count;
@@ -168,6 +171,8 @@ void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsig
   a.T_C_L = T_C_L;
   a.cam = cam;
   a.p = p;
+  a.bits_to_clear = bits_to_clear;
+  a.num_words = num_words;
   // 8 resident 256-thread CTAs per SM (2048 threads): one full wave.
   tsdfIntegrateKernel<<<num_sms * 8, 256, 0, stream>>>(a);
 }

@@ -130,89 +130,97 @@ __global__ void __launch_bounds__(kRayTileCols* kRayTileRows)
   }
 }
 
-constexpr int kCompactThreads = 256;  // one bitset word per thread -> 8192 cells per tile
+constexpr int kCompactThreads = 256;
+constexpr int kTileWords = 64;                       // 2048 cells per tile
+constexpr int kTileCells = kTileWords * 32;
+constexpr int kChainedThresholdWords = 1 << 16;      // above this the redundant prefix would be quadratic
 
-// Ordered compaction + allocation. Tiles take tickets in order and chain their
-// prefix through tile_state (epoch in the high word), so the emitted list is in
-// ascending linear-index order = the order convertAabbUpdatedToVector produces
-// (view_calculator.cu:185-195): x fastest, then y, then z. Inside a tile the set
-// bits are dealt round-robin to the threads (binary search over the popcount scan +
-// find-n-th-set-bit), so the dependent hash probes of one tile run in parallel
-// instead of up to 32 per thread in sequence.
+// Ordered compaction + allocation. The emitted list is in ascending linear-index order =
+// the order convertAabbUpdatedToVector produces (view_calculator.cu:185-195): x fastest,
+// then y, then z.
+//   * A tile is 64 bitset words. Its output offset is the popcount of ALL preceding words,
+//     which every tile recomputes for itself (the whole bitset is a few KB in L2), so tiles
+//     are independent: no chained scan, no tickets, and the hash work of all tiles overlaps.
+//     (Bitsets beyond 2^16 words fall back to a ticketed chained scan.)
+//   * Inside a tile the set bits are dealt round-robin to the 256 threads (binary search over
+//     the popcount scan + find-n-th-set-bit): the dependent hash probes run in parallel.
+//   * Entries are staged in shared memory and written out coalesced.
+// The bitset is NOT cleared here (other tiles still read it); the TSDF kernel that follows
+// zeroes it for the next frame.
 __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(CompactArgs a) {
+  __shared__ int s_incl[kTileWords];
+  __shared__ unsigned int s_word[kTileWords];
+  __shared__ int s_red[kCompactThreads / 32];
+  __shared__ int s_prefix;
   __shared__ unsigned int s_tile;
-  __shared__ int s_warp_sums[kCompactThreads / 32];
-  __shared__ int s_incl[kCompactThreads];
-  __shared__ unsigned int s_word[kCompactThreads];
-  __shared__ int s_prefix, s_total;
+  __shared__ int4 s_out[kTileCells];
   const int tid = threadIdx.x;
-  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
-  __syncthreads();
-  const unsigned int tile = s_tile;
-  const int num_tiles = (a.grid.num_words + kCompactThreads - 1) / kCompactThreads;
+  const bool chained = a.grid.num_words > kChainedThresholdWords;
+  unsigned int tile = blockIdx.x;
+  if (chained) {
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
+    __syncthreads();
+    tile = s_tile;
+  }
+  const int num_tiles = (a.grid.num_words + kTileWords - 1) / kTileWords;
+  const int w0 = (int)tile * kTileWords;
 
-  const int w = (int)tile * kCompactThreads + tid;
+  // popcount scan of this tile's words (2 warps)
   unsigned int word = 0;
-  if (w < a.grid.num_words) {
-    word = a.bits[w];
-    if (word) a.bits[w] = 0;  // self-cleaning: the next frame starts from a zero bitset
-  }
-  s_word[tid] = word;
-  const int cnt = __popc(word);
-  // block-wide inclusive scan of cnt
-  int incl = cnt;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int n = __shfl_up_sync(0xffffffffu, incl, off);
-    if ((tid & 31) >= off) incl += n;
-  }
-  if ((tid & 31) == 31) s_warp_sums[tid >> 5] = incl;
-  __syncthreads();
-  if (tid < 32) {
-    int v = (tid < kCompactThreads / 32) ? s_warp_sums[tid] : 0;
-    int vi = v;
+  if (tid < kTileWords && w0 + tid < a.grid.num_words) word = a.bits[w0 + tid];
+  if (tid < kTileWords) {
+    s_word[tid] = word;
+    int incl = __popc(word);
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int n = __shfl_up_sync(0xffffffffu, vi, off);
-      if (tid >= off) vi += n;
+      const int n = __shfl_up_sync(0xffffffffu, incl, off);
+      if ((tid & 31) >= off) incl += n;
     }
-    if (tid < kCompactThreads / 32) s_warp_sums[tid] = vi - v;  // exclusive warp offsets
-    if (tid == kCompactThreads / 32 - 1) {
-      const int tile_total = vi;
-      // chained scan: wait for the predecessor tile of this launch
-      int prefix = 0;
-      if (tile > 0) {
-        volatile unsigned long long* prev = a.tile_state + (tile - 1);
-        unsigned long long st;
-        do {
-          st = *prev;
-        } while ((unsigned int)(st >> 32) != a.epoch);
-        prefix = (int)(unsigned int)st;
-      }
-      __threadfence();
-      atomicExch(a.tile_state + tile, ((unsigned long long)a.epoch << 32) | (unsigned int)(prefix + tile_total));
-      if ((int)tile == num_tiles - 1) *a.frame_count = prefix + tile_total;
-      s_prefix = prefix;
-      s_total = tile_total;
-    }
+    s_incl[tid] = incl;
   }
+  // offset of the tile = popcount of every preceding word
+  int part = 0;
+  if (!chained)
+    for (int w = tid; w < w0; w += kCompactThreads) part += __popc(a.bits[w]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+  if ((tid & 31) == 0) s_red[tid >> 5] = part;
   __syncthreads();
-  s_incl[tid] = s_warp_sums[tid >> 5] + incl;
+  if (tid >= 32 && tid < kTileWords) s_incl[tid] += s_incl[31];  // second warp continues the first
   __syncthreads();
-  const int total = s_total, prefix = s_prefix;
+  const int total = s_incl[kTileWords - 1];
+  if (tid == 0) {
+    int prefix = 0;
+    if (!chained) {
+      for (int q = 0; q < kCompactThreads / 32; q++) prefix += s_red[q];
+    } else if (tile > 0) {
+      volatile unsigned long long* prev = a.tile_state + (tile - 1);
+      unsigned long long st;
+      do {
+        st = *prev;
+      } while ((unsigned int)(st >> 32) != a.epoch);
+      prefix = (int)(unsigned int)st;
+    }
+    if (chained) {
+      __threadfence();
+      atomicExch(a.tile_state + tile, ((unsigned long long)a.epoch << 32) | (unsigned int)(prefix + total));
+    }
+    if ((int)tile == num_tiles - 1) *a.frame_count = prefix + total;
+    s_prefix = prefix;
+  }
   const int sx = a.grid.size.x, sxy = a.grid.size.x * a.grid.size.y;
   for (int j = tid; j < total; j += kCompactThreads) {
     // first word whose inclusive count exceeds j
-    int lo = 0, hi = kCompactThreads - 1;
+    int lo = 0, hi = kTileWords - 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (s_incl[mid] > j) hi = mid;
       else lo = mid + 1;
     }
     const unsigned int wv = s_word[lo];
-    const int rank = j - (s_incl[lo] - __popc(wv));            // 0-based rank of the bit inside the word
-    const int bit = (int)__fns(wv, 0, rank + 1);               // position of the (rank+1)-th set bit
-    const int lin = ((int)tile * kCompactThreads + lo) * 32 + bit;
+    const int rank = j - (s_incl[lo] - __popc(wv));  // 0-based rank of the bit inside the word
+    const int bit = (int)__fns(wv, 0, rank + 1);     // position of the (rank+1)-th set bit
+    const int lin = (w0 + lo) * 32 + bit;
     // aabbLinearIndexToLayerIndex (view_calculator_impl.cuh:38-44)
     const int x = lin % sx + a.grid.min_index.x;
     const int y = (lin / sx) % a.grid.size.y + a.grid.min_index.y;
@@ -227,15 +235,28 @@ __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(Compact
         if (atomicExch(a.dirty + slot, 1) == 0) a.todo_slots[atomicAdd(a.todo_count, 1)] = slot;
       }
     }
-    a.frame_blocks[prefix + j] = make_int4(x, y, z, slot);
+    s_out[j] = make_int4(x, y, z, slot);
   }
+  __syncthreads();
+  const int prefix = s_prefix;
+  for (int j = tid; j < total; j += kCompactThreads) a.frame_blocks[prefix + j] = s_out[j];
+}
+
+__global__ void clearWordsKernel(unsigned int* bits, int n) {
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) bits[w] = 0;
 }
 
 }  // namespace
 
 int compactNumTiles(const ViewGrid& grid) {
-  const int t = (grid.num_words + kCompactThreads - 1) / kCompactThreads;
+  const int t = (grid.num_words + kTileWords - 1) / kTileWords;
   return t < 1 ? 1 : t;
+}
+
+bool compactUsesTickets(const ViewGrid& grid) { return grid.num_words > kChainedThresholdWords; }
+
+void launchClearBits(unsigned int* bits, int num_words, cudaStream_t stream) {
+  if (num_words > 0) clearWordsKernel<<<(num_words + 1023) / 1024 < 148 ? (num_words + 1023) / 1024 : 148, 1024, 0, stream>>>(bits, num_words);
 }
 
 void launchViewRaycast(const float* depth, int rows, int cols, const Rigid& T_L_C, const NvbCamera& cam,

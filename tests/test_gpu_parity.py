@@ -406,3 +406,13 @@ def test_full_sequence_properties(gpu):
         assert np.array_equal(blk["is_inside"].astype(bool) & obs, (t["distance"] <= 0) & obs)
         assert np.all(blk["squared_distance_vox"][obs] <= np.float32(max_sq))
     m.close()
+
+
+def test_cpp_dropin_program(gpu, tmp_path):
+    """tests/cpp/test_mapper_dropin.cpp: the reference-style C++ test through include/nvblox/mapper/mapper.h."""
+    import subprocess
+    from test_cabi_symbols import _compile_cpp_dropin
+    exe = _compile_cpp_dropin(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "drop-in C++ API ok" in out.stdout
