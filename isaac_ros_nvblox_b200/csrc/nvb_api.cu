@@ -110,6 +110,7 @@ struct NvbMapper {
   int update_seq = 0;
   long long* stats = nullptr;
   unsigned int* barrier = nullptr;
+  unsigned long long* phase_max = nullptr;
   int* xyz_upload = nullptr;
   int xyz_upload_cap = 0;
 
@@ -270,6 +271,7 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.cleared_seq = m->esdf_ints + kClearedSeq;
   c.update_seq = m->update_seq;
   c.barrier = m->barrier;
+  c.phase_max = m->phase_max;
   c.stats = m->stats;
   c.error = m->error_dev;
   // esdf_integrator.cu:693-696, 672-676
@@ -742,6 +744,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   m->error_dev = m->esdf_ints + kError;
   NVB_CUDA(cudaMalloc(&m->stats, 16 * sizeof(long long)));
   NVB_CUDA(cudaMemsetAsync(m->stats, 0, 16 * sizeof(long long), m->stream));
+  NVB_CUDA(cudaMalloc(&m->phase_max, 1000 * sizeof(unsigned long long)));
+  NVB_CUDA(cudaMemsetAsync(m->phase_max, 0, 1000 * sizeof(unsigned long long), m->stream));
   NVB_CUDA(cudaMalloc(&m->barrier, 64));
   NVB_CUDA(cudaMemsetAsync(m->barrier, 0, 64, m->stream));
   NVB_CUDA(cudaMalloc(&m->ticket, 64));
@@ -780,7 +784,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->work), cudaFree(m->esdf_ints), cudaFree(m->upd_list), cudaFree(m->clr_list), cudaFree(m->cleared_list);
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
   cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr);
-  cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->xyz_upload);
+  cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
   cudaStreamDestroy(m->stream), cudaStreamDestroy(m->copy_stream);
@@ -1108,9 +1112,13 @@ int32_t nvb_mapper_esdf_time_split(NvbMapper* m, int64_t out[4]) {
   if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
   NVB_CUDA(cudaSetDevice(m->device));
   NVB_CUDA(syncAll(m));
-  long long tmp[4];
+  long long tmp[5];
   NVB_CUDA(cudaMemcpy(tmp, m->stats + 8, sizeof(tmp), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; i++) out[i] = tmp[i];
+  out[0] = tmp[0];
+  // [1]+[2] are CTA 0's own work; tmp[4] is the sum over phases of the slowest CTA's work: report it in [1]
+  // of a second call convention: keep the API at 4 entries, fold it in as out[2] = slowest-CTA work total.
+  out[2] = tmp[4];
   return NVB_OK;
 }
 

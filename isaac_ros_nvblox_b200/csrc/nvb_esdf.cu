@@ -45,6 +45,9 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
     c.ring_count[2] = 0;  // mark-kernel "CTAs done" counter
     *c.barrier = 0;
     for (int k = 0; k < 16; k++) c.stats[k] = 0;
+  }
+  for (int q = i; q < 1000; q += gridDim.x * blockDim.x) c.phase_max[q] = 0ull;
+  if (i == 0) {
     c.stats[0] = n;
   }
   if (i >= n) return;

@@ -29,7 +29,57 @@ constexpr int kWT = 1024;               // threads per CTA
 constexpr int kWG = kWT / 64;           // 16 groups of 64 threads
 constexpr int kWaveMaxMembers = 1024;   // owned candidates scanned per round
 constexpr int kNbrCache = 128;          // members whose neighbour slots are cached in smem
-constexpr size_t kWaveSmemBytes = (size_t)kWG * kEsdfBlockBytes;  // 160 KiB of sweep buffers
+// Shared-memory image of an ESDF block for the sweeps: the 20-byte AoS voxels with ONE pad word after
+// every row of 8 voxels: word(v, f) = 5 v + f + (v >> 3). With this pitch the y- and z-line accesses of a
+// warp (32 lines) hit 32 distinct banks and x-lines are 2-way (the unpadded copy is 4-way / 8-way), which
+// matters because all 16 groups of the CTA share one shared-memory pipe.
+constexpr int kPadBlockWords = kBlockWords + kVpb / kVps;  // 2560 + 64
+constexpr size_t kWaveSmemBytes = (size_t)kWG * kPadBlockWords * sizeof(unsigned int);  // 164 KiB of sweep buffers
+
+// HBM -> padded smem image. Global side: 128-bit coalesced loads (640 chunks per block). Shared side:
+// the pad makes chunk destinations unaligned, so each chunk is stored as four 32-bit words; lane groups
+// of 8 rotate which word they store so that the 32 lanes of one store instruction hit 32 banks.
+__device__ __forceinline__ unsigned int pick(const uint4& q, int j) {
+  return j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w));
+}
+__device__ __forceinline__ void loadBlockPadded(unsigned int* sm, const unsigned int* g, int lane64) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  const int rot = (lane64 >> 3) & 3;
+  constexpr int kBatch = 5;  // 5 chunks (20 registers) in flight per thread, twice
+#pragma unroll 1
+  for (int k0 = 0; k0 < kBlockWords / 4 / 64; k0 += kBatch) {
+    uint4 q[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; k++) q[k] = __ldcg(src + lane64 + (k0 + k) * 64);
+#pragma unroll
+    for (int k = 0; k < kBatch; k++) {
+      const int c = lane64 + (k0 + k) * 64;
+      unsigned int* dst = sm + 4 * c + c / 10;  // row = (4c) / 40
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int j = (t + rot) & 3;
+        dst[j] = pick(q[k], j);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void storeBlockPadded(unsigned int* g, const unsigned int* sm, int lane64) {
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  const int rot = (lane64 >> 3) & 3;
+#pragma unroll
+  for (int k = 0; k < kBlockWords / 4 / 64; k++) {
+    const int c = lane64 + k * 64;
+    const unsigned int* src = sm + 4 * c + c / 10;
+    unsigned int w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int j = (t + rot) & 3;
+      const unsigned int val = src[j];
+      w0 = (j == 0) ? val : w0, w1 = (j == 1) ? val : w1, w2 = (j == 2) ? val : w2, w3 = (j == 3) ? val : w3;
+    }
+    __stcg(dst + c, make_uint4(w0, w1, w2, w3));
+  }
+}
 
 __device__ __forceinline__ int resolveNeighbor(const EsdfCtx& c, int slot, int dir) {
   int v = __ldcg(c.nbr + 6 * slot + dir);
@@ -84,16 +134,17 @@ __device__ __forceinline__ void prefetchNeighbors(const EsdfCtx& c, WaveShared& 
   if (tid < kc * 6) sh.nbr[tid] = resolveNeighbor(c, sh.members[tid / 6], tid % 6);
 }
 
-// sweepSingleBand (:542-600) on registers. `s` points at the line's first voxel in shared memory,
-// `stride` is the voxel stride along the line; (c0,c1,c2) are the voxel coordinates at position 0.
-__device__ __forceinline__ bool sweepLineRegs(unsigned int* s, int stride, int c0, int c1, int c2, int axis,
+// sweepSingleBand (:542-600) on registers. `sm` is the padded block image, v0 the line's first voxel,
+// `stride` the voxel stride along the line; (c0,c1,c2) are the voxel coordinates at position 0.
+__device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stride, int c0, int c1, int c2, int axis,
                                               float max_sq) {
   float sq[kVps];
   int p0[kVps], p1[kVps], p2[kVps];
   unsigned int obs = 0, site = 0, dirty = 0;
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
-    const unsigned int* e = s + i * stride * kEsdfVoxelWords;
+    const int v = v0 + i * stride;
+    const unsigned int* e = sm + v * kEsdfVoxelWords + (v >> 3);
     sq[i] = __uint_as_float(e[0]);
     p0[i] = (int)e[1], p1[i] = (int)e[2], p2[i] = (int)e[3];
     const unsigned int fl = e[4];
@@ -132,7 +183,8 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* s, int stride, int c
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
     if ((dirty >> i) & 1u) {
-      unsigned int* e = s + i * stride * kEsdfVoxelWords;
+      const int v = v0 + i * stride;
+      unsigned int* e = sm + v * kEsdfVoxelWords + (v >> 3);
       e[0] = __float_as_uint(sq[i]);
       e[1] = (unsigned)p0[i], e[2] = (unsigned)p1[i], e[3] = (unsigned)p2[i];
     }
@@ -143,23 +195,23 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* s, int stride, int c
 // sweepBlockBandKernel (:1390-1431) for the cached members, kWG blocks at a time.
 __device__ void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned int* smem) {
   const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
-  unsigned int* sm = smem + group * kBlockWords;
+  unsigned int* sm = smem + group * kPadBlockWords;
   const int a = lane64 >> 3, b = lane64 & 7;
   for (int base = 0; base < k; base += kWG) {
     const int item = base + group;
     const int slot = item < k ? sh.members[item] : -1;
     if (lane64 == 0) sh.changed[group] = 0;
-    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
+    if (slot >= 0) loadBlockPadded(sm, esdfBlockPtr(c.esdf, slot), lane64);
     __syncthreads();
     bool ch = false;
-    if (slot >= 0) ch |= sweepLineRegs(sm + (a * 8 + b) * kEsdfVoxelWords, 64, 0, a, b, 0, c.max_sq);
+    if (slot >= 0) ch |= sweepLineRegs(sm, a * 8 + b, 64, 0, a, b, 0, c.max_sq);
     __syncthreads();
-    if (slot >= 0) ch |= sweepLineRegs(sm + (a * 64 + b) * kEsdfVoxelWords, 8, a, 0, b, 1, c.max_sq);
+    if (slot >= 0) ch |= sweepLineRegs(sm, a * 64 + b, 8, a, 0, b, 1, c.max_sq);
     __syncthreads();
-    if (slot >= 0) ch |= sweepLineRegs(sm + (a * 64 + b * 8) * kEsdfVoxelWords, 1, a, b, 0, 2, c.max_sq);
+    if (slot >= 0) ch |= sweepLineRegs(sm, a * 64 + b * 8, 1, a, b, 0, 2, c.max_sq);
     if (ch) sh.changed[group] = 1;
     __syncthreads();
-    if (slot >= 0 && sh.changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
+    if (slot >= 0 && sh.changed[group]) storeBlockPadded(esdfBlockPtr(c.esdf, slot), sm, lane64);
     __syncthreads();
   }
 }
@@ -237,6 +289,13 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
   t1 = globalTimerNs(); \
   acc += t1 - t0;       \
   t0 = t1;
+  // every CTA: duration of its own work in the phase that ends at barrier #n_bar -> max over CTAs
+  long long tw0 = globalTimerNs();
+#define NVB_PHASE_MAX()                                                                                   \
+  if (threadIdx.x == 0 && n_bar < 1000) {                                                                 \
+    atomicMax((unsigned long long*)c.phase_max + n_bar, (unsigned long long)(globalTimerNs() - tw0));     \
+  }
+#define NVB_PHASE_BEGIN() tw0 = globalTimerNs();
   const int cleared_seq = *(volatile int*)c.cleared_seq;
   for (int pass = 0; pass < 2; pass++) {
     const int* seed = pass ? c.seed_clr : c.seed_upd;
@@ -256,9 +315,11 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
     if (threadIdx.x == 0 && k_total > 0) atomicAdd(c.ring_count + ci, k_total);
     if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
     NVB_TICK(t_sweep)
+    NVB_PHASE_MAX()
     gridBarrier(c.barrier, generation, nctas);
     NVB_TICK(t_bar)
     n_bar++;
+    NVB_PHASE_BEGIN()
     int n = *(volatile int*)(c.ring_count + ci);
     int k_cached = (rounds == 1) ? k_total : -1;  // sh.members / sh.nbr hold this CTA's members of ring `ring`
     swept += n;
@@ -277,9 +338,11 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
           axisMembers(c, sh, axis, k, stamp[ci], ring, stamp[ni]);
         }
         NVB_TICK(t_axis)
+        NVB_PHASE_MAX()
         gridBarrier(c.barrier, generation, nctas);
         NVB_TICK(t_bar)
         n_bar++;
+        NVB_PHASE_BEGIN()
       }
       faces += 6ll * n;
       // Members of ring+1 = owned slots stamped during the three axis phases.
@@ -295,9 +358,11 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
       if (threadIdx.x == 0 && k_next > 0) atomicAdd(c.ring_count + ni, k_next);
       if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the counter of ring+2
       NVB_TICK(t_sweep)
+      NVB_PHASE_MAX()
       gridBarrier(c.barrier, generation, nctas);
       NVB_TICK(t_bar)
       n_bar++;
+      NVB_PHASE_BEGIN()
       const int n_next = *(volatile int*)(c.ring_count + ni);
       k_cached = (rounds == 1) ? k_next : -1;
       swept += n_next;
@@ -308,9 +373,11 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
     }
     ring++;
     if (cta == 0 && threadIdx.x == 0) c.ring_count[0] = c.ring_count[1] = 0;
+    NVB_PHASE_MAX()
     gridBarrier(c.barrier, generation, nctas);
     NVB_TICK(t_bar)
     n_bar++;
+    NVB_PHASE_BEGIN()
   }
 #undef NVB_TICK
   if (cta == 0 && threadIdx.x == 0) {
@@ -318,6 +385,9 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
     c.stats[4] = *(volatile int*)c.cleared_count;
     c.stats[5] = swept, c.stats[6] = faces, c.stats[7] = rings;
     c.stats[8] = t_bar, c.stats[9] = t_axis, c.stats[10] = t_sweep, c.stats[11] = n_bar;
+    long long sum_max = 0;
+    for (int q = 0; q < n_bar && q < 1000; q++) sum_max += (long long)c.phase_max[q];
+    c.stats[12] = sum_max;  // sum over phases of the slowest CTA's work time
   }
 }
 

@@ -250,6 +250,7 @@ struct EsdfCtx {
   int* cleared_seq;   // device: update_seq of the last update whose clear pass ran
   int update_seq;     // host: sequence number of this update (monotone, starts at 1)
   unsigned int* barrier;  // grid barrier counter
+  unsigned long long* phase_max;  // debug: per-phase max-over-CTAs work time (1000 entries)
   long long* stats;    // 8 counters
   int* error;
   float max_sq;

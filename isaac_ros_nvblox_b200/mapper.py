@@ -211,7 +211,7 @@ class Mapper:
     def esdf_time_split(self):
         out = (C.c_int64 * 4)()
         check(self._L.nvb_mapper_esdf_time_split(self._h, out))
-        return {"barrier_ns": out[0], "axis_ns": out[1], "sweep_ns": out[2], "barriers": out[3]}
+        return {"barrier_wait_ns_cta0": out[0], "axis_ns_cta0": out[1], "slowest_cta_work_ns": out[2], "barriers": out[3]}
 
     def __init__(self, voxel_size_m, device=0, tsdf_capacity_blocks=0, esdf_capacity_blocks=0,
                  esdf_persistent=True):
