@@ -245,6 +245,9 @@ NVB_API int32_t nvb_mapper_last_esdf_stats(NvbMapper* m, int64_t out[8]);
  * [1] face-propagation phases, [2] scan + sweep phases, [3] number of grid barriers. Synchronising. */
 NVB_API int32_t nvb_mapper_esdf_time_split(NvbMapper* m, int64_t out[4]);
 
+/* Debug: work time (ns) of the slowest CTA in each barrier-delimited phase of the last wavefront. */
+NVB_API int32_t nvb_mapper_debug_phase_max(NvbMapper* m, int64_t* out, int32_t cap);
+
 /* Per-stage device time of the frames since the last reset, measured with CUDA
  * events on the mapper's stream when profiling is enabled (same names as the
  * reference's timers: "tsdf/integrate", "esdf/integrate", ...;

@@ -41,6 +41,7 @@ def build(force=False, verbose=False):
         "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
         "-shared", "-cudart", "static",
+    ] + os.environ.get("NVB_EXTRA_NVCC_FLAGS", "").split() + [
         "-o", OUT,
     ] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:

@@ -470,7 +470,8 @@ int checkDeviceError(NvbMapper* m) {
   int err = 0;
   NVB_CUDA(cudaMemcpy(&err, m->error_dev, sizeof(int), cudaMemcpyDeviceToHost));
   if (err) {
-    cudaMemset(m->error_dev, 0, sizeof(int));
+    cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream);
+    cudaStreamSynchronize(m->stream);
     if (err & 2) return fail(NVB_ERR_INDEX_RANGE, "a block index does not fit the 21-bit hash key");
     return fail(NVB_ERR_CAPACITY, "a layer slab overflowed on the device");
   }
@@ -937,8 +938,10 @@ int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, 
     NVB_CUDA(cudaMalloc(&m->xyz_upload, (size_t)n * 2 * 3 * sizeof(int)));
     m->xyz_upload_cap = n * 2;
   }
-  NVB_CUDA(syncAll(m));  // v is pageable: order the copy before it goes out of scope
-  NVB_CUDA(cudaMemcpy(m->xyz_upload, v.data(), (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  // Stream-ordered upload: a blocking cudaMemcpy from pageable memory may return before the DMA has landed,
+  // and the mapper's stream is non-blocking (not ordered against the legacy default stream).
+  NVB_CUDA(cudaMemcpyAsync(m->xyz_upload, v.data(), (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));  // v is pageable and about to go out of scope
   int rc = enqueueEsdf(m, m->xyz_upload, n, false);
   if (rc) return rc;
   return nvb_mapper_synchronize(m);
@@ -1021,12 +1024,12 @@ int32_t nvb_layer_get_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   NVB_CUDA(cudaMalloc(&xyz_dev, (size_t)n * 3 * sizeof(int)));
   NVB_CUDA(cudaMalloc(&out_dev, (size_t)n * L->block_bytes));
   NVB_CUDA(cudaMalloc(&found_dev, (size_t)n));
-  NVB_CUDA(cudaMemcpy(xyz_dev, xyz_host, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  NVB_CUDA(cudaMemcpyAsync(xyz_dev, xyz_host, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
   launchGatherBlocks(*L, xyz_dev, n, out_dev, found_dev, m->stream);
   m->launches++;
+  NVB_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)n * L->block_bytes, cudaMemcpyDeviceToHost, m->stream));
+  if (found_host) NVB_CUDA(cudaMemcpyAsync(found_host, found_dev, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
   NVB_CUDA(syncAll(m));
-  NVB_CUDA(cudaMemcpy(out_host, out_dev, (size_t)n * L->block_bytes, cudaMemcpyDeviceToHost));
-  if (found_host) NVB_CUDA(cudaMemcpy(found_host, found_dev, (size_t)n, cudaMemcpyDeviceToHost));
   cudaFree(xyz_dev), cudaFree(out_dev), cudaFree(found_dev);
   return NVB_OK;
 }
@@ -1055,8 +1058,8 @@ int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   unsigned char* in_dev = nullptr;
   NVB_CUDA(cudaMalloc(&xyz_dev, (size_t)n * 3 * sizeof(int)));
   NVB_CUDA(cudaMalloc(&in_dev, (size_t)n * L->block_bytes));
-  NVB_CUDA(cudaMemcpy(xyz_dev, xyz_host, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice));
-  NVB_CUDA(cudaMemcpy(in_dev, in_host, (size_t)n * L->block_bytes, cudaMemcpyHostToDevice));
+  NVB_CUDA(cudaMemcpyAsync(xyz_dev, xyz_host, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  NVB_CUDA(cudaMemcpyAsync(in_dev, in_host, (size_t)n * L->block_bytes, cudaMemcpyHostToDevice, m->stream));
   launchScatterBlocks(*L, xyz_dev, n, in_dev, m->error_dev, m->stream);
   m->launches++;
   NVB_CUDA(syncAll(m));
@@ -1067,7 +1070,8 @@ int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   } else {
     // blocks created outside the ESDF update path are not linked: forget the neighbour table,
     // it is re-resolved lazily through the hash
-    NVB_CUDA(cudaMemset(m->nbr, 0xFE, (size_t)m->esdf.capacity * 6 * sizeof(int)));
+    NVB_CUDA(cudaMemsetAsync(m->nbr, 0xFE, (size_t)m->esdf.capacity * 6 * sizeof(int), m->stream));
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
   }
   return checkDeviceError(m);
 }
@@ -1119,6 +1123,15 @@ int32_t nvb_mapper_esdf_time_split(NvbMapper* m, int64_t out[4]) {
   // [1]+[2] are CTA 0's own work; tmp[4] is the sum over phases of the slowest CTA's work: report it in [1]
   // of a second call convention: keep the API at 4 entries, fold it in as out[2] = slowest-CTA work total.
   out[2] = tmp[4];
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_debug_phase_max(NvbMapper* m, int64_t* out, int32_t cap) {
+  if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(syncAll(m));
+  if (cap > 1000) cap = 1000;
+  NVB_CUDA(cudaMemcpy(out, m->phase_max, (size_t)cap * sizeof(long long), cudaMemcpyDeviceToHost));
   return NVB_OK;
 }
 

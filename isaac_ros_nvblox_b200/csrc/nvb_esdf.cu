@@ -22,6 +22,9 @@
 //   * the whole wavefront (both computeEsdf calls) runs in ONE cooperative
 //     persistent launch with a grid barrier between phases.
 #include "nvb_esdf_common.cuh"
+#include "nvb_tma.cuh"
+
+#include <cstdlib>
 
 namespace nvb {
 
@@ -168,6 +171,167 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
   // list is about to be rewritten (clearAllInvalid resizes it, :1620); otherwise it
   // keeps the previous call's content (:242-257).
   if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      const int nclr = *(volatile int*)c.clr_count;
+      const int nupd = *(volatile int*)c.upd_count;
+      if (nclr > 0) {
+        *c.cleared_count = 0;
+        *c.cleared_seq = c.update_seq;
+      }
+      c.stats[1] = nupd, c.stats[2] = nclr;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// markAllSites with TMA staging. Same per-voxel state machine as esdfMarkKernel; what
+// changes is how blocks move: one elected thread issues cp.async.bulk copies (SASS UBLKCP)
+// of the 10 KiB ESDF block and the 4 KiB TSDF block into a 3-stage shared-memory ring,
+// completion is tracked by an mbarrier per stage (expect_tx = 14 336 B), the block is updated
+// in place in shared memory and goes back with one bulk store. Loads of the next two work
+// items are in flight while the current one is processed, so a persistent CTA keeps
+// ~28 KiB outstanding without spending registers or LSU slots on it.
+// ---------------------------------------------------------------------------
+constexpr int kMarkStages = 3;
+struct __align__(128) MarkStage {
+  unsigned int esdf[kBlockWords];     // 10 240 B
+  float2 tsdf[kVpb];                  //  4 096 B
+};
+constexpr unsigned int kMarkStageTxBytes = kEsdfBlockBytes + kTsdfBlockBytes;
+
+__global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MarkStage* st = reinterpret_cast<MarkStage*>(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar[kMarkStages];
+  __shared__ int4 s_work[kMarkStages];
+  __shared__ int s_flags[3];  // updated, cleared, changed
+  const int tid = threadIdx.x;
+  const int n = *c.work_count;
+  const int my_count = (n > (int)blockIdx.x) ? (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (tid == 0) {
+    for (int s = 0; s < kMarkStages; s++) tma::mbarInit(&s_bar[s], 1);
+    tma::fenceBarrierInit();
+  }
+  __syncthreads();
+  // producer (thread 0): stage the blocks of this CTA's j-th work item
+  auto issue = [&](int j) {
+    const int s = j % kMarkStages;
+    const int4 w = c.work[blockIdx.x + j * gridDim.x];
+    s_work[s] = w;
+    if (w.x >= 0 && w.y >= 0) {
+      tma::mbarArriveExpectTx(&s_bar[s], kMarkStageTxBytes);
+      tma::bulkLoad(st[s].esdf, c.esdf.blocks + (size_t)w.x * kEsdfBlockBytes, kEsdfBlockBytes, &s_bar[s]);
+      tma::bulkLoad(st[s].tsdf, c.tsdf.blocks + (size_t)w.y * kTsdfBlockBytes, kTsdfBlockBytes, &s_bar[s]);
+    } else {
+      tma::mbarArrive(&s_bar[s]);  // nothing to load: complete the phase
+    }
+  };
+  if (tid == 0) {
+    for (int j = 0; j < kMarkStages - 1 && j < my_count; j++) issue(j);
+  }
+  __syncthreads();
+  for (int j = 0; j < my_count; j++) {
+    const int s = j % kMarkStages;
+    if (tid == 0 && j + kMarkStages - 1 < my_count) {
+      // stage (j-1) % S is about to be refilled: its bulk store must have finished reading it
+      tma::bulkWaitRead<0>();
+      issue(j + kMarkStages - 1);
+    }
+    tma::mbarWait(&s_bar[s], (unsigned int)((j / kMarkStages) & 1));
+    const int4 w = s_work[s];
+    if (w.x >= 0 && w.z && tid < 6) {
+      // Newly allocated ESDF block: link it with its six face neighbours (both directions).
+      const int* bi = c.esdf.block_index + 3 * w.x;
+      int x = bi[0], y = bi[1], z = bi[2];
+      const int d = (tid & 1) ? -1 : 1;
+      if ((tid >> 1) == 0) x += d;
+      else if ((tid >> 1) == 1) y += d;
+      else z += d;
+      const int other = hashFind(c.esdf.hash, x, y, z);
+      c.nbr[6 * w.x + tid] = other;
+      if (other >= 0) c.nbr[6 * other + (tid ^ 1)] = w.x;
+    }
+    const bool valid = (w.x >= 0 && w.y >= 0);  // block_ptr == nullptr || esdf_block == nullptr (:513-517)
+    if (tid < 3) s_flags[tid] = 0;
+    __syncthreads();
+    if (valid) {
+      unsigned int* sblk = st[s].esdf;
+      bool updated = false, cleared = false, changed = false;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const float2 t = st[s].tsdf[tid + h * kThreads];
+        unsigned int* e = sblk + (tid + h * kThreads) * kEsdfVoxelWords;
+        float sq = __uint_as_float(e[0]);
+        int p0 = (int)e[1], p1 = (int)e[2], p2 = (int)e[3];
+        const unsigned int fl = e[4];
+        bool e_inside = flagInside(fl), e_observed = flagObserved(fl), e_site = flagSite(fl);
+        const bool is_observed = t.y >= c.min_weight;
+        if (is_observed) {
+          const bool is_inside = t.x <= 0.0f;
+          const bool is_site = is_inside && (fabsf(t.x) <= c.max_site_distance_m);
+          if (e_inside && !is_inside) {
+            p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+            cleared = true;
+          }
+          e_inside = is_inside;
+          if (is_site) {
+            if (!e_site) {
+              e_site = true, sq = 0.0f, p0 = p1 = p2 = 0;
+            }
+            updated = true;
+          } else {
+            if (e_site) {
+              p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+              cleared = true;
+            } else if (!e_observed) {
+              p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+            } else if ((double)sq <= 1e-4) {
+              p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+              cleared = true;
+            }
+          }
+          e_observed = true;
+        } else {
+          p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+          cleared = true;
+          e_observed = false;
+        }
+        const unsigned int nfl = (fl & 0xff000000u) | (e_inside ? 1u : 0u) | (e_observed ? 0x100u : 0u) |
+                                 (e_site ? 0x10000u : 0u);
+        const unsigned int nsq = __float_as_uint(sq);
+        if (nsq != e[0] || (unsigned)p0 != e[1] || (unsigned)p1 != e[2] || (unsigned)p2 != e[3] || nfl != fl) {
+          e[0] = nsq, e[1] = (unsigned)p0, e[2] = (unsigned)p1, e[3] = (unsigned)p2, e[4] = nfl;
+          changed = true;
+        }
+      }
+      if (updated) s_flags[0] = 1;
+      if (cleared) s_flags[1] = 1;
+      if (changed) s_flags[2] = 1;
+      tma::fenceProxyAsyncShared();  // this thread's smem writes -> visible to the bulk store
+    }
+    __syncthreads();
+    if (valid && tid == 0) {
+      if (s_flags[2]) {
+        tma::bulkStore(c.esdf.blocks + (size_t)w.x * kEsdfBlockBytes, st[s].esdf, kEsdfBlockBytes);
+        tma::bulkCommit();
+      }
+      if (s_flags[0]) {
+        c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
+        c.seed_upd[w.x] = c.update_seq;
+      }
+      if (s_flags[1]) {
+        c.clr_list[atomicAdd(c.clr_count, 1)] = w.x;
+        const int* bi = c.esdf.block_index + 3 * w.x;
+        atomicMin(c.clr_aabb + 0, bi[0]), atomicMin(c.clr_aabb + 1, bi[1]), atomicMin(c.clr_aabb + 2, bi[2]);
+        atomicMax(c.clr_aabb + 3, bi[0]), atomicMax(c.clr_aabb + 4, bi[1]), atomicMax(c.clr_aabb + 5, bi[2]);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    tma::bulkWait<0>();  // all write-backs performed before this CTA reports "done"
     __threadfence();
     if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
       __threadfence();
@@ -463,6 +627,21 @@ void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots
 }
 
 void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream) {
+  static int use_tma = -1;
+  if (use_tma < 0) {
+    const char* e = getenv("NVB_MARK_TMA");
+    use_tma = (e && e[0] == '0') ? 0 : 1;
+    if (use_tma)
+      cudaFuncSetAttribute(esdfMarkTmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(kMarkStages * sizeof(MarkStage)));
+  }
+  if (use_tma) {
+    int grid = num_sms * 4;  // 4 x 43 KiB of staging per SM; ~3000 items -> ~5 per CTA, 2 loads in flight each
+    if (count_upper < grid) grid = count_upper;
+    if (grid < 1) grid = 1;
+    esdfMarkTmaKernel<<<grid, kThreads, kMarkStages * sizeof(MarkStage), stream>>>(c);
+    return;
+  }
   int grid = num_sms * 8;  // 8 resident CTAs per SM (10 KiB smem, 256 threads each)
   if (count_upper < grid) grid = count_upper;
   if (grid < 1) grid = 1;

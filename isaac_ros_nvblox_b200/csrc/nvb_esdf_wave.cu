@@ -25,8 +25,19 @@ namespace nvb {
 
 namespace {
 
-constexpr int kWT = 1024;               // threads per CTA
-constexpr int kWG = kWT / 64;           // 16 groups of 64 threads
+#ifndef NVB_WAVE_INLINE
+#define NVB_WAVE_INLINE 0
+#endif
+#if NVB_WAVE_INLINE
+#define NVB_WAVE_FN __forceinline__
+#else
+#define NVB_WAVE_FN __noinline__
+#endif
+#ifndef NVB_WAVE_THREADS
+#define NVB_WAVE_THREADS 512
+#endif
+constexpr int kWT = NVB_WAVE_THREADS;   // threads per CTA (512 -> 128 registers per thread: the register sweeps do not spill)
+constexpr int kWG = kWT / 64;           // groups of 64 threads
 constexpr int kWaveMaxMembers = 1024;   // owned candidates scanned per round
 constexpr int kNbrCache = 128;          // members whose neighbour slots are cached in smem
 // Shared-memory image of an ESDF block for the sweeps: the 20-byte AoS voxels with ONE pad word after
@@ -108,36 +119,47 @@ struct WaveShared {
 
 // Scan up to kWaveMaxMembers owned candidates (one per thread) for tag[slot] == value and compact
 // the hits into sh.members. Optionally stamps the hits (initial list). Returns the member count.
-__device__ int scanOwned(WaveShared& sh, const int* tag, int value, int nslots, int cta, int nctas, int first,
+__device__ NVB_WAVE_FN int scanOwned(WaveShared& sh, const int* tag, int value, int nslots, int cta, int nctas, int first,
                          int ncand, int* stamp_out, int stamp_value) {
   const int tid = threadIdx.x;
-  const int slot = cta + (first + tid) * nctas;
-  const bool hit = tid < ncand && slot < nslots && __ldcg(tag + slot) == value;
-  const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
-  if ((tid & 31) == 0) sh.scan[tid >> 5] = __popc(ballot);
-  __syncthreads();
-  int offset = 0;
-  for (int w = 0; w < (tid >> 5); w++) offset += sh.scan[w];
-  if (hit) {
-    sh.members[offset + __popc(ballot & ((1u << (tid & 31)) - 1u))] = slot;
-    if (stamp_out) stamp_out[slot] = stamp_value;
+  int total = 0;
+  for (int base = 0; base < ncand; base += kWT) {
+    const int slot = cta + (first + base + tid) * nctas;
+    const bool hit = base + tid < ncand && slot < nslots && __ldcg(tag + slot) == value;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+    if ((tid & 31) == 0) sh.scan[tid >> 5] = __popc(ballot);
+    __syncthreads();
+    int offset = total;
+    for (int w = 0; w < (tid >> 5); w++) offset += sh.scan[w];
+    if (hit) {
+      sh.members[offset + __popc(ballot & ((1u << (tid & 31)) - 1u))] = slot;
+      if (stamp_out) stamp_out[slot] = stamp_value;
+    }
+    if (tid == kWT - 1) sh.count = offset + __popc(ballot);
+    __syncthreads();
+    total = sh.count;
+    __syncthreads();
   }
-  if (tid == kWT - 1) sh.count = offset + __popc(ballot);
-  __syncthreads();
-  return sh.count;
+  return total;
 }
 
 // Neighbour slots of the first kNbrCache members -> shared memory (one thread per (member, dir)).
 __device__ __forceinline__ void prefetchNeighbors(const EsdfCtx& c, WaveShared& sh, int k) {
   const int tid = threadIdx.x;
   const int kc = k < kNbrCache ? k : kNbrCache;
-  if (tid < kc * 6) sh.nbr[tid] = resolveNeighbor(c, sh.members[tid / 6], tid % 6);
+  for (int q = tid; q < kc * 6; q += kWT) sh.nbr[q] = resolveNeighbor(c, sh.members[q / 6], q % 6);
 }
 
-// sweepSingleBand (:542-600) on registers. `sm` is the padded block image, v0 the line's first voxel,
-// `stride` the voxel stride along the line; (c0,c1,c2) are the voxel coordinates at position 0.
+// sweepSingleBand (:542-600) on registers: the line's 8 voxels are loaded once, walked forward, the
+// register image is reversed, walked "forward" again (= the backward pass) and changed voxels are
+// written back. ONE copy of the 8-step body serves both passes and all three axes (axis and pass
+// are run-time values): the wavefront kernel alternates between the barrier, the axis code and the
+// sweep code, and a fully unrolled 3 axes x 2 passes x 8 steps body does not fit the instruction
+// cache next to them.
+// `sm` is the padded block image, v0 the line's first voxel, `stride` the voxel stride along the
+// line; (c0,c1,c2) are the voxel coordinates at position 0.
 __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stride, int c0, int c1, int c2, int axis,
-                                              float max_sq) {
+                                           float max_sq) {
   float sq[kVps];
   int p0[kVps], p1[kVps], p2[kVps];
   unsigned int obs = 0, site = 0, dirty = 0;
@@ -151,35 +173,48 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
     if (flagObserved(fl)) obs |= 1u << i;
     if (flagSite(fl)) site |= 1u << i;
   }
-#pragma unroll
+  const int a0 = (axis == 0), a1 = (axis == 1), a2 = (axis == 2);
+#pragma unroll 1
   for (int pass = 0; pass < 2; pass++) {
     int l0 = 0, l1 = 0, l2 = 0;
     bool found = false;
 #pragma unroll
     for (int k = 0; k < kVps; k++) {
-      const int i = pass ? (kVps - 1 - k) : k;
-      if (!((obs >> i) & 1u)) continue;
-      const int v0 = c0 + (axis == 0 ? i : 0), v1 = c1 + (axis == 1 ? i : 0), v2 = c2 + (axis == 2 ? i : 0);
-      if ((site >> i) & 1u) {
-        l0 = v0, l1 = v1, l2 = v2;
+      // register slot k holds line position pos = k (pass 0) or 7 - k (pass 1, image reversed)
+      if (!((obs >> k) & 1u)) continue;
+      const int pos = pass ? (kVps - 1 - k) : k;
+      const int v0c = c0 + a0 * pos, v1c = c1 + a1 * pos, v2c = c2 + a2 * pos;
+      if ((site >> k) & 1u) {
+        l0 = v0c, l1 = v1c, l2 = v2c;
         found = true;
       } else if (!found) {
-        if (sq[i] < max_sq) {
+        if (sq[k] < max_sq) {
           found = true;
-          l0 = p0[i] + v0, l1 = p1[i] + v1, l2 = p2[i] + v2;
+          l0 = p0[k] + v0c, l1 = p1[k] + v1c, l2 = p2[k] + v2c;
         }
       } else {
-        const int d0 = l0 - v0, d1 = l1 - v1, d2 = l2 - v2;
+        const int d0 = l0 - v0c, d1 = l1 - v1c, d2 = l2 - v2c;
         const float pdist = (float)(d0 * d0 + (d1 * d1 + d2 * d2));
-        if (sq[i] > pdist) {
-          p0[i] = d0, p1[i] = d1, p2[i] = d2, sq[i] = pdist;
-          dirty |= 1u << i;
-        } else if (sq[i] < max_sq) {
-          l0 = p0[i] + v0, l1 = p1[i] + v1, l2 = p2[i] + v2;
+        if (sq[k] > pdist) {
+          p0[k] = d0, p1[k] = d1, p2[k] = d2, sq[k] = pdist;
+          dirty |= 1u << k;
+        } else if (sq[k] < max_sq) {
+          l0 = p0[k] + v0c, l1 = p1[k] + v1c, l2 = p2[k] + v2c;
         }
       }
     }
+    // reverse the register image (and the bit masks) for the other direction / back to line order
+#pragma unroll
+    for (int k = 0; k < kVps / 2; k++) {
+      const int r = kVps - 1 - k;
+      float tf = sq[k]; sq[k] = sq[r]; sq[r] = tf;
+      int ti = p0[k]; p0[k] = p0[r]; p0[r] = ti;
+      ti = p1[k]; p1[k] = p1[r]; p1[r] = ti;
+      ti = p2[k]; p2[k] = p2[r]; p2[r] = ti;
+    }
+    obs = __brev(obs) >> 24, site = __brev(site) >> 24, dirty = __brev(dirty) >> 24;
   }
+  // after two reversals slot i is line position i again
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
     if ((dirty >> i) & 1u) {
@@ -193,7 +228,7 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
 }
 
 // sweepBlockBandKernel (:1390-1431) for the cached members, kWG blocks at a time.
-__device__ void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned int* smem) {
+__device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned int* smem) {
   const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
   unsigned int* sm = smem + group * kPadBlockWords;
   const int a = lane64 >> 3, b = lane64 & 7;
@@ -204,11 +239,17 @@ __device__ void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned i
     if (slot >= 0) loadBlockPadded(sm, esdfBlockPtr(c.esdf, slot), lane64);
     __syncthreads();
     bool ch = false;
-    if (slot >= 0) ch |= sweepLineRegs(sm, a * 8 + b, 64, 0, a, b, 0, c.max_sq);
-    __syncthreads();
-    if (slot >= 0) ch |= sweepLineRegs(sm, a * 64 + b, 8, a, 0, b, 1, c.max_sq);
-    __syncthreads();
-    if (slot >= 0) ch |= sweepLineRegs(sm, a * 64 + b * 8, 1, a, b, 0, 2, c.max_sq);
+#pragma unroll 1
+    for (int axis = 0; axis < 3; axis++) {
+      // x lines: (x, a, b); y lines: (a, y, b); z lines: (a, b, z)
+      const int v0 = (axis == 0) ? (a * 8 + b) : ((axis == 1) ? (a * 64 + b) : (a * 64 + b * 8));
+      const int stride = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
+      const int c0 = (axis == 0) ? 0 : a;
+      const int c1 = (axis == 0) ? a : ((axis == 1) ? 0 : b);
+      const int c2 = (axis == 2) ? 0 : b;
+      if (slot >= 0) ch |= sweepLineRegs(sm, v0, stride, c0, c1, c2, axis, c.max_sq);
+      __syncthreads();
+    }
     if (ch) sh.changed[group] = 1;
     __syncthreads();
     if (slot >= 0 && sh.changed[group]) storeBlockPadded(esdfBlockPtr(c.esdf, slot), sm, lane64);
@@ -221,7 +262,7 @@ __device__ void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned i
 //   group side 0 ("hi"): interface (b, b+d): P = b -> b+d, then Q = b+d -> b if b+d is a member;
 //   group side 1 ("lo"): interface (b-d, b) only when b-d is NOT a member: Q = b -> b-d.
 // Destination blocks are stamped for ring+1 with a plain store.
-__device__ void axisMembers(const EsdfCtx& c, WaveShared& sh, int axis, int k, const int* stamp_cur, int ring,
+__device__ NVB_WAVE_FN void axisMembers(const EsdfCtx& c, WaveShared& sh, int axis, int k, const int* stamp_cur, int ring,
                             int* stamp_nxt) {
   const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
   const int entry_in_cta = group >> 1, side = group & 1;
@@ -325,6 +366,7 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
     swept += n;
     while (n > 0) {
       const int ni = ci ^ 1;
+#pragma unroll 1
       for (int axis = 0; axis < 3; axis++) {
         for (int r = 0; r < rounds; r++) {
           int k = k_cached;

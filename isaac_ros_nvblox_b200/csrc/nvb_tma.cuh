@@ -24,6 +24,11 @@ __device__ __forceinline__ void mbarArriveExpectTx(uint64_t* bar, uint32_t bytes
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
 }
 
+// Plain arrival (completes a phase that expects no bytes).
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+
 __device__ __forceinline__ bool mbarTryWait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

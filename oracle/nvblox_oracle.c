@@ -13,6 +13,7 @@
 #include <float.h>
 #include <limits.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -851,14 +852,29 @@ static List esdf_update_neighbor_bands(OrMap* map, const List* l, float max_sq) 
   return out;
 }
 
+/* Debug aid (not part of the algorithm): when set, every ring's ESDF slot list is appended to this file. */
+static FILE* g_ring_dump = NULL;
+void or_debug_ring_dump(const char* path) {
+  if (g_ring_dump) fclose(g_ring_dump);
+  g_ring_dump = path ? fopen(path, "w") : NULL;
+}
+static void dump_ring(const OrMap* map, const List* l, const char* tag) {
+  if (!g_ring_dump) return;
+  fprintf(g_ring_dump, "%s %d", tag, l->n);
+  for (int32_t i = 0; i < l->n; i++) fprintf(g_ring_dump, " %d", hash_find(&map->esdf.hash, l->v[i]));
+  fprintf(g_ring_dump, "\n");
+}
+
 /* computeEsdf (:1465-1496). */
 static void esdf_compute(OrMap* map, const List* blocks_with_sites, float max_sq) {
   if (blocks_with_sites->n == 0) return;
   List cur = {0};
   for (int32_t i = 0; i < blocks_with_sites->n; i++) list_push(&cur, blocks_with_sites->v[i]);
+  dump_ring(map, &cur, "init");
   esdf_sweep_list(map, &cur, max_sq);
   while (cur.n > 0) {
     List upd = esdf_update_neighbor_bands(map, &cur, max_sq);
+    dump_ring(map, &upd, "ring");
     esdf_sweep_list(map, &upd, max_sq);
     list_free(&cur);
     cur = upd;

@@ -15,4 +15,11 @@ for i, (_, T) in enumerate(seq):
     m.integrate_depth_device(depth[i].data_ptr(), 480, 640, T, cam)
     m.update_esdf(sync=False)
     m.synchronize()
-    print(i, m.esdf_integrator().last_stats(), m.esdf_time_split())
+    sp = m.esdf_time_split()
+    print(i, m.esdf_integrator().last_stats(), sp)
+    if i >= 8:
+        import ctypes as C
+        n = int(sp["barriers"])
+        arr = (C.c_int64 * 1000)()
+        m._L.nvb_mapper_debug_phase_max(m._h, arr, 1000)
+        print("   per-phase slowest-CTA work (ns):", [int(arr[q]) for q in range(min(n, 80))])
