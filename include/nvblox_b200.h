@@ -209,6 +209,14 @@ NVB_API int32_t nvb_mapper_last_frame_block_count(NvbMapper* m, int32_t* out_cou
 /* `updated_blocks` of the most recent frame again (e.g. after a too-small buffer). */
 NVB_API int32_t nvb_mapper_last_frame_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_t cap,
                                              int32_t* out_count);
+/* Multi-GPU merge step (no reference counterpart: the reference is single-GPU): sorted unique
+ * union of block-index lists. xyz_dev holds n int32 triples in device memory (e.g. the NCCL all-gather of the
+ * ranks' padded lists; a triple whose x is INT32_MIN is padding), aabb_min/max bound the union. Writes up to cap
+ * triples to out_xyz_dev in the view calculator's order (x fastest, then y, then z) and the count to the host. */
+NVB_API int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n, const int32_t aabb_min[3],
+                                 const int32_t aabb_max[3], int32_t* out_xyz_dev, int32_t cap,
+                                 int32_t* out_count_host);
+
 /* Device-side join (no host synchronisation): work enqueued on nvb_mapper_stream() after this
  * call also waits for the ESDF wavefront, which runs on an internal side stream so that it
  * overlaps the next frame's TSDF chain. Needed before recording an event on the mapper's stream. */

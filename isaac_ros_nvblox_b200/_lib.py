@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "nvb_view_raycast", "nvb_mapper_integrate_depth", "nvb_mapper_integrate_depth_async",
     "nvb_mapper_update_esdf", "nvb_mapper_update_esdf_async", "nvb_esdf_integrate_blocks",
     "nvb_mapper_synchronize", "nvb_mapper_last_frame_block_count", "nvb_mapper_last_frame_blocks",
-    "nvb_mapper_stream", "nvb_mapper_join_streams",
+    "nvb_mapper_stream", "nvb_mapper_join_streams", "nvb_blocks_union",
     "nvb_layer_num_blocks", "nvb_layer_block_indices", "nvb_layer_get_blocks",
     "nvb_layer_set_blocks", "nvb_layer_block_device_ptr", "nvb_layer_block_bytes",
     "nvb_mapper_last_esdf_stats", "nvb_mapper_esdf_time_split", "nvb_mapper_debug_phase_max", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
@@ -112,6 +112,7 @@ def load():
     L.nvb_mapper_last_frame_block_count.argtypes = [vp, ip]
     L.nvb_mapper_last_frame_blocks.argtypes = [vp, ip, i32, ip]
     L.nvb_mapper_join_streams.argtypes = [vp]
+    L.nvb_blocks_union.argtypes = [vp, vp, i32, ip, ip, vp, i32, ip]
     L.nvb_mapper_stream.argtypes = [vp]
     L.nvb_mapper_stream.restype = vp
     L.nvb_layer_num_blocks.argtypes = [vp, i32, ip]

@@ -745,8 +745,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   m->error_dev = m->esdf_ints + kError;
   NVB_CUDA(cudaMalloc(&m->stats, 16 * sizeof(long long)));
   NVB_CUDA(cudaMemsetAsync(m->stats, 0, 16 * sizeof(long long), m->stream));
-  NVB_CUDA(cudaMalloc(&m->phase_max, 1000 * sizeof(unsigned long long)));
-  NVB_CUDA(cudaMemsetAsync(m->phase_max, 0, 1000 * sizeof(unsigned long long), m->stream));
+  NVB_CUDA(cudaMalloc(&m->phase_max, 4000 * sizeof(unsigned long long)));
+  NVB_CUDA(cudaMemsetAsync(m->phase_max, 0, 4000 * sizeof(unsigned long long), m->stream));
   NVB_CUDA(cudaMalloc(&m->barrier, 64));
   NVB_CUDA(cudaMemsetAsync(m->barrier, 0, 64, m->stream));
   NVB_CUDA(cudaMalloc(&m->ticket, 64));
@@ -968,6 +968,50 @@ int32_t nvb_mapper_last_frame_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_
   return readFrameList(m, out_xyz_host, cap, out_count);
 }
 
+int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n, const int32_t aabb_min[3],
+                         const int32_t aabb_max[3], int32_t* out_xyz_dev, int32_t cap, int32_t* out_count_host) {
+  if (!m || !aabb_min || !aabb_max || (n > 0 && !xyz_dev)) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  ViewGrid g{};
+  g.min_index = make_int3(aabb_min[0], aabb_min[1], aabb_min[2]);
+  const long long sx = (long long)aabb_max[0] - aabb_min[0] + 1, sy = (long long)aabb_max[1] - aabb_min[1] + 1,
+                  sz = (long long)aabb_max[2] - aabb_min[2] + 1;
+  if (n <= 0 || sx <= 0 || sy <= 0 || sz <= 0) {
+    if (out_count_host) *out_count_host = 0;
+    return NVB_OK;
+  }
+  if (sx * sy * sz > 0x7fffffffll) return fail(NVB_ERR_CAPACITY, "union AABB has more than 2^31 cells");
+  g.size = make_int3((int)sx, (int)sy, (int)sz);
+  g.linear_size = (int)(sx * sy * sz);
+  g.num_words = (g.linear_size + 31) / 32;
+  int rc;
+  if ((rc = ensureFrameScratch(m, g))) return rc;
+  launchMarkList(xyz_dev, n, g, m->bits, m->stream);
+  CompactArgs ca{};
+  ca.bits = m->bits;
+  ca.grid = g;
+  ca.frame_blocks = m->frame_blocks;
+  ca.frame_count = m->frame_count;
+  ca.tile_state = m->tile_state;
+  ca.ticket = m->ticket;
+  ca.ticket_base = m->ticket_base;
+  ca.epoch = ++m->epoch;
+  ca.allocate = 0;
+  ca.layer = m->tsdf;
+  ca.error = m->error_dev;
+  launchCompactAllocate(ca, m->stream);
+  if (compactUsesTickets(g)) m->ticket_base += (unsigned int)compactNumTiles(g);
+  launchClearBits(m->bits, g.num_words, m->stream);
+  if (out_xyz_dev && cap > 0) launchUnpackList(m->frame_blocks, m->frame_count, out_xyz_dev, cap, m->stream);
+  m->launches += 4;
+  if (out_count_host) {
+    NVB_CUDA(cudaMemcpyAsync(m->h_ints, m->frame_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    *out_count_host = m->h_ints[0];
+  }
+  return NVB_OK;
+}
+
 int32_t nvb_mapper_join_streams(NvbMapper* m) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
@@ -1130,7 +1174,7 @@ int32_t nvb_mapper_debug_phase_max(NvbMapper* m, int64_t* out, int32_t cap) {
   if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
   NVB_CUDA(cudaSetDevice(m->device));
   NVB_CUDA(syncAll(m));
-  if (cap > 1000) cap = 1000;
+  if (cap > 4000) cap = 4000;
   NVB_CUDA(cudaMemcpy(out, m->phase_max, (size_t)cap * sizeof(long long), cudaMemcpyDeviceToHost));
   return NVB_OK;
 }

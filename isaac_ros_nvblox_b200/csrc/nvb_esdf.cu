@@ -49,7 +49,7 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
     *c.barrier = 0;
     for (int k = 0; k < 16; k++) c.stats[k] = 0;
   }
-  for (int q = i; q < 1000; q += gridDim.x * blockDim.x) c.phase_max[q] = 0ull;
+  for (int q = i; q < 4000; q += gridDim.x * blockDim.x) c.phase_max[q] = 0ull;
   if (i == 0) {
     c.stats[0] = n;
   }

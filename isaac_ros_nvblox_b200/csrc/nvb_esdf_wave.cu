@@ -45,7 +45,7 @@ constexpr int kNbrCache = 128;          // members whose neighbour slots are cac
 // warp (32 lines) hit 32 distinct banks and x-lines are 2-way (the unpadded copy is 4-way / 8-way), which
 // matters because all 16 groups of the CTA share one shared-memory pipe.
 constexpr int kPadBlockWords = kBlockWords + kVpb / kVps;  // 2560 + 64
-constexpr size_t kWaveSmemBytes = (size_t)kWG * kPadBlockWords * sizeof(unsigned int);  // 164 KiB of sweep buffers
+constexpr size_t kWaveSmemBytes = (size_t)kWG * kBlockWords * sizeof(unsigned int);  // sweep buffers
 
 // HBM -> padded smem image. Global side: 128-bit coalesced loads (640 chunks per block). Shared side:
 // the pad makes chunk destinations unaligned, so each chunk is stored as four 32-bit words; lane groups
@@ -150,28 +150,36 @@ __device__ __forceinline__ void prefetchNeighbors(const EsdfCtx& c, WaveShared& 
   for (int q = tid; q < kc * 6; q += kWT) sh.nbr[q] = resolveNeighbor(c, sh.members[q / 6], q % 6);
 }
 
-// sweepSingleBand (:542-600) on registers: the line's 8 voxels are loaded once, walked forward, the
-// register image is reversed, walked "forward" again (= the backward pass) and changed voxels are
-// written back. ONE copy of the 8-step body serves both passes and all three axes (axis and pass
-// are run-time values): the wavefront kernel alternates between the barrier, the axis code and the
-// sweep code, and a fully unrolled 3 axes x 2 passes x 8 steps body does not fit the instruction
-// cache next to them.
-// `sm` is the padded block image, v0 the line's first voxel, `stride` the voxel stride along the
+// sweepSingleBand (:542-600) on registers, written for a SHORT DEPENDENT CHAIN: one block's sweep is
+// 3 axes x 16 sequential steps on two warps, so its latency is (instructions on the chain) x (ALU
+// latency), not throughput. Per step the only loop-carried state is the candidate site (l0,l1,l2) and
+// `found`; everything that does not depend on it is hoisted:
+//   * squared distances are exact integers (or max_sq), so "sq > |d|^2" is evaluated as the integer test
+//     ceil(sq) > |d|^2 -- no int->float conversion on the chain; "sq < max_sq" becomes a bit mask;
+//   * each voxel's own parent position (parent + voxel) is precomputed;
+//   * the four cases of the reference (unobserved / site / first valid voxel / candidate vs own) are
+//     folded into branch-free selects.
+// The line's 8 voxels are loaded once, walked forward, the register image is reversed and walked again
+// (= the backward pass); changed voxels are written back. `axis` and `pass` are run-time values so that
+// ONE copy of the 8-step body serves all six passes.
+// `sm` is the block image in shared memory, v0 the line's first voxel, `stride` the voxel stride along the
 // line; (c0,c1,c2) are the voxel coordinates at position 0.
 __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stride, int c0, int c1, int c2, int axis,
-                                           float max_sq) {
-  float sq[kVps];
+                                              float max_sq) {
+  int T[kVps];  // ceil(squared distance): sq > n  <=>  T > n for every integer n
   int p0[kVps], p1[kVps], p2[kVps];
-  unsigned int obs = 0, site = 0, dirty = 0;
+  unsigned int obs = 0, site = 0, valid = 0, dirty = 0;
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
     const int v = v0 + i * stride;
-    const unsigned int* e = sm + v * kEsdfVoxelWords + (v >> 3);
-    sq[i] = __uint_as_float(e[0]);
+    const unsigned int* e = sm + v * kEsdfVoxelWords;
+    const float sq = __uint_as_float(e[0]);
+    T[i] = __float2int_ru(sq);
     p0[i] = (int)e[1], p1[i] = (int)e[2], p2[i] = (int)e[3];
     const unsigned int fl = e[4];
     if (flagObserved(fl)) obs |= 1u << i;
     if (flagSite(fl)) site |= 1u << i;
+    if (sq < max_sq) valid |= 1u << i;
   }
   const int a0 = (axis == 0), a1 = (axis == 1), a2 = (axis == 2);
 #pragma unroll 1
@@ -181,46 +189,43 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
 #pragma unroll
     for (int k = 0; k < kVps; k++) {
       // register slot k holds line position pos = k (pass 0) or 7 - k (pass 1, image reversed)
-      if (!((obs >> k) & 1u)) continue;
       const int pos = pass ? (kVps - 1 - k) : k;
-      const int v0c = c0 + a0 * pos, v1c = c1 + a1 * pos, v2c = c2 + a2 * pos;
-      if ((site >> k) & 1u) {
-        l0 = v0c, l1 = v1c, l2 = v2c;
-        found = true;
-      } else if (!found) {
-        if (sq[k] < max_sq) {
-          found = true;
-          l0 = p0[k] + v0c, l1 = p1[k] + v1c, l2 = p2[k] + v2c;
-        }
-      } else {
-        const int d0 = l0 - v0c, d1 = l1 - v1c, d2 = l2 - v2c;
-        const float pdist = (float)(d0 * d0 + (d1 * d1 + d2 * d2));
-        if (sq[k] > pdist) {
-          p0[k] = d0, p1[k] = d1, p2[k] = d2, sq[k] = pdist;
-          dirty |= 1u << k;
-        } else if (sq[k] < max_sq) {
-          l0 = p0[k] + v0c, l1 = p1[k] + v1c, l2 = p2[k] + v2c;
-        }
+      const int x0 = c0 + a0 * pos, x1 = c1 + a1 * pos, x2 = c2 + a2 * pos;  // voxel coordinates
+      const bool o = (obs >> k) & 1u, st = (site >> k) & 1u, vl = (valid >> k) & 1u;
+      const int own0 = p0[k] + x0, own1 = p1[k] + x1, own2 = p2[k] + x2;    // off the chain
+      const int d0 = l0 - x0, d1 = l1 - x1, d2 = l2 - x2;
+      const int pd = d0 * d0 + (d1 * d1 + d2 * d2);
+      const bool better = found && o && !st && (T[k] > pd);  // candidate site is closer than the voxel's value
+      const bool take_site = o && st;
+      const bool take_own = o && !st && !better && vl;       // voxel's own parent becomes the running site
+      if (better) {
+        p0[k] = d0, p1[k] = d1, p2[k] = d2, T[k] = pd;
+        dirty |= 1u << k;
+        valid |= 1u << k;  // pd < old sq <= max_sq
       }
+      l0 = take_site ? x0 : (take_own ? own0 : l0);
+      l1 = take_site ? x1 : (take_own ? own1 : l1);
+      l2 = take_site ? x2 : (take_own ? own2 : l2);
+      found = found || take_site || take_own;
     }
     // reverse the register image (and the bit masks) for the other direction / back to line order
 #pragma unroll
     for (int k = 0; k < kVps / 2; k++) {
       const int r = kVps - 1 - k;
-      float tf = sq[k]; sq[k] = sq[r]; sq[r] = tf;
-      int ti = p0[k]; p0[k] = p0[r]; p0[r] = ti;
+      int ti = T[k]; T[k] = T[r]; T[r] = ti;
+      ti = p0[k]; p0[k] = p0[r]; p0[r] = ti;
       ti = p1[k]; p1[k] = p1[r]; p1[r] = ti;
       ti = p2[k]; p2[k] = p2[r]; p2[r] = ti;
     }
-    obs = __brev(obs) >> 24, site = __brev(site) >> 24, dirty = __brev(dirty) >> 24;
+    obs = __brev(obs) >> 24, site = __brev(site) >> 24, dirty = __brev(dirty) >> 24, valid = __brev(valid) >> 24;
   }
   // after two reversals slot i is line position i again
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
     if ((dirty >> i) & 1u) {
       const int v = v0 + i * stride;
-      unsigned int* e = sm + v * kEsdfVoxelWords + (v >> 3);
-      e[0] = __float_as_uint(sq[i]);
+      unsigned int* e = sm + v * kEsdfVoxelWords;
+      e[0] = __float_as_uint((float)T[i]);
       e[1] = (unsigned)p0[i], e[2] = (unsigned)p1[i], e[3] = (unsigned)p2[i];
     }
   }
@@ -230,13 +235,13 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
 // sweepBlockBandKernel (:1390-1431) for the cached members, kWG blocks at a time.
 __device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned int* smem) {
   const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
-  unsigned int* sm = smem + group * kPadBlockWords;
+  unsigned int* sm = smem + group * kBlockWords;
   const int a = lane64 >> 3, b = lane64 & 7;
   for (int base = 0; base < k; base += kWG) {
     const int item = base + group;
     const int slot = item < k ? sh.members[item] : -1;
     if (lane64 == 0) sh.changed[group] = 0;
-    if (slot >= 0) loadBlockPadded(sm, esdfBlockPtr(c.esdf, slot), lane64);
+    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
     __syncthreads();
     bool ch = false;
 #pragma unroll 1
@@ -252,7 +257,7 @@ __device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k
     }
     if (ch) sh.changed[group] = 1;
     __syncthreads();
-    if (slot >= 0 && sh.changed[group]) storeBlockPadded(esdfBlockPtr(c.esdf, slot), sm, lane64);
+    if (slot >= 0 && sh.changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
     __syncthreads();
   }
 }
@@ -392,9 +397,17 @@ __global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
       for (int r = 0; r < rounds; r++) {
         const int first = r * kWaveMaxMembers;
         const int ncand = max(0, min(kWaveMaxMembers, owned - first));
+        long long ts0 = globalTimerNs();
         const int k = scanOwned(sh, stamp[ni], ring + 1, nslots, cta, nctas, first, ncand, nullptr, 0);
+        long long ts1 = globalTimerNs();
         if (rounds == 1) prefetchNeighbors(c, sh, k);
         sweepMembers(c, sh, k, smem);
+        long long ts2 = globalTimerNs();
+        if (threadIdx.x == 0 && n_bar < 1000) {
+          atomicMax((unsigned long long*)c.phase_max + 1000 + n_bar, (unsigned long long)(ts1 - ts0));
+          atomicMax((unsigned long long*)c.phase_max + 2000 + n_bar, (unsigned long long)(ts2 - ts1));
+          atomicMax((unsigned long long*)c.phase_max + 3000 + n_bar, (unsigned long long)k);
+        }
         k_next += k;
       }
       if (threadIdx.x == 0 && k_next > 0) atomicAdd(c.ring_count + ni, k_next);

@@ -214,6 +214,8 @@ bool compactUsesTickets(const ViewGrid& grid);
 // The compaction leaves the bitset set; it is zeroed by the TSDF kernel's prologue or, on the
 // view-only path, by this launch.
 void launchClearBits(unsigned int* bits, int num_words, cudaStream_t stream);
+void launchMarkList(const int* xyz_dev, int n, const ViewGrid& grid, unsigned int* bits, cudaStream_t stream);
+void launchUnpackList(const int4* in, const int* count, int* out, int cap, cudaStream_t stream);
 void launchCompactAllocate(const CompactArgs& args, cudaStream_t stream);
 
 // nvb_tsdf.cu

@@ -242,6 +242,25 @@ __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(Compact
   for (int j = tid; j < total; j += kCompactThreads) a.frame_blocks[prefix + j] = s_out[j];
 }
 
+// Union of block-index lists (multi-GPU merge): every valid entry marks its cell of the union AABB.
+__global__ void markListKernel(const int* __restrict__ xyz, int n, ViewGrid g, unsigned int* bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  if (x == INT32_MIN) return;  // padding entry
+  const int sx = x - g.min_index.x, sy = y - g.min_index.y, sz = z - g.min_index.z;
+  if (sx < 0 || sy < 0 || sz < 0 || sx >= g.size.x || sy >= g.size.y || sz >= g.size.z) return;
+  const int lin = sx + sy * g.size.x + sz * g.size.x * g.size.y;
+  atomicOr(bits + (lin >> 5), 1u << (lin & 31));
+}
+__global__ void unpackListKernel(const int4* __restrict__ in, const int* __restrict__ count, int* out, int cap) {
+  const int n = *count < cap ? *count : cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int4 v = in[i];
+    out[3 * i] = v.x, out[3 * i + 1] = v.y, out[3 * i + 2] = v.z;
+  }
+}
+
 __global__ void clearWordsKernel(unsigned int* bits, int n) {
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) bits[w] = 0;
 }
@@ -251,6 +270,13 @@ __global__ void clearWordsKernel(unsigned int* bits, int n) {
 int compactNumTiles(const ViewGrid& grid) {
   const int t = (grid.num_words + kTileWords - 1) / kTileWords;
   return t < 1 ? 1 : t;
+}
+
+void launchMarkList(const int* xyz_dev, int n, const ViewGrid& grid, unsigned int* bits, cudaStream_t stream) {
+  if (n > 0) markListKernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz_dev, n, grid, bits);
+}
+void launchUnpackList(const int4* in, const int* count, int* out, int cap, cudaStream_t stream) {
+  unpackListKernel<<<148, 256, 0, stream>>>(in, count, out, cap);
 }
 
 bool compactUsesTickets(const ViewGrid& grid) { return grid.num_words > kChainedThresholdWords; }

@@ -20,6 +20,7 @@ for i, (_, T) in enumerate(seq):
     if i >= 8:
         import ctypes as C
         n = int(sp["barriers"])
-        arr = (C.c_int64 * 1000)()
-        m._L.nvb_mapper_debug_phase_max(m._h, arr, 1000)
+        arr = (C.c_int64 * 4000)()
+        m._L.nvb_mapper_debug_phase_max(m._h, arr, 4000)
         print("   per-phase slowest-CTA work (ns):", [int(arr[q]) for q in range(min(n, 80))])
+        print("   sweep phases (total, scan, load+sweep+store, max k):", [(int(arr[q]), int(arr[1000+q]), int(arr[2000+q]), int(arr[3000+q])) for q in range(min(n, 80)) if arr[3000+q] or arr[2000+q]])

@@ -416,3 +416,28 @@ def test_cpp_dropin_program(gpu, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "drop-in C++ API ok" in out.stdout
+
+
+def test_block_list_union_kernel(gpu):
+    """nvb_blocks_union == sort(unique(concat)) as a set, in x-fastest order, with padding and duplicates."""
+    import torch
+    nvb = _nvb()
+    from isaac_ros_nvblox_b200 import multi_gpu
+    m = nvb.Mapper(0.05)
+    rng = np.random.default_rng(4)
+    lists = [rng.integers(-30, 30, size=(n, 3)).astype(np.int32) for n in (700, 0, 1500)]
+    cap = 1500
+    padded = np.full((3, cap, 3), multi_gpu.PAD, np.int32)
+    for r, l in enumerate(lists):
+        padded[r, :len(l)] = l
+    got = multi_gpu.union_on_device(m, torch.from_numpy(padded.reshape(-1, 3)).cuda()).cpu().numpy()
+    want = np.unique(np.concatenate(lists), axis=0)
+    assert len(got) == len(want)
+    assert np.array_equal(sort_rows(got), want)
+    lin = got[:, 0].astype(np.int64) + 1000 * got[:, 1] + 1000000 * got[:, 2]
+    assert np.all(np.diff(lin) > 0)  # x fastest, then y, then z
+    assert len(multi_gpu.union_on_device(m, torch.from_numpy(padded[1]).cuda())) == 0
+    # world size 1 path used by bench.py
+    u = multi_gpu.merge_block_lists_device(m, torch.from_numpy(lists[0]).cuda()).cpu().numpy()
+    assert np.array_equal(sort_rows(u), np.unique(lists[0], axis=0))
+    m.close()
