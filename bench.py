@@ -182,6 +182,7 @@ def main():
     F = len(frames)
     depth_host = torch.from_numpy(np.stack([d for d, _ in frames])).pin_memory()
     depth_dev = depth_host.cuda(non_blocking=False)
+    depth_host_np = [depth_host[i].numpy() for i in range(F)]  # views of the pinned buffer
     poses = [T for _, T in frames]
 
     m = nvb.Mapper(VOXEL, device=local_rank, esdf_persistent=not args.esdf_host_loop)
@@ -200,7 +201,7 @@ def main():
         m.clear()
         d2h = 0
         for i in range(F):
-            b = m.integrate_depth(frames[i][0], poses[i], cam)  # host in, updated_blocks out, synchronous
+            b = m.integrate_depth(depth_host_np[i], poses[i], cam)  # pinned host in, updated_blocks out, synchronous
             m.update_esdf()
             d2h += b.nbytes
         return d2h

@@ -268,53 +268,60 @@ __device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k
 //   group side 1 ("lo"): interface (b-d, b) only when b-d is NOT a member: Q = b -> b-d.
 // Destination blocks are stamped for ring+1 with a plain store.
 __device__ NVB_WAVE_FN void axisMembers(const EsdfCtx& c, WaveShared& sh, int axis, int k, const int* stamp_cur, int ring,
-                            int* stamp_nxt) {
-  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
-  const int entry_in_cta = group >> 1, side = group & 1;
-  const int u = lane64 >> 3, w = lane64 & 7;
+                                        int* stamp_nxt) {
+  // One warp per (member, side) interface, two face voxels per lane: kWT/32 interfaces = kWT/64 members per
+  // iteration, so the handful of members a CTA owns are all in flight at once (one L2 round trip per phase).
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarps = kWT / 32;
+  const int entry_in_cta = warp >> 1, side = warp & 1;
   const int strideA = (axis == 0) ? 64 : ((axis == 1) ? 8 : 1);
-  const int faceBase = (axis == 0) ? (u * 8 + w) : ((axis == 1) ? (u * 64 + w) : (u * 64 + w * 8));
-  const int vHi = faceBase + (kVps - 1) * strideA, vLo = faceBase;
-  for (int base = 0; base < k; base += kWG / 2) {
+  for (int base = 0; base < k; base += kWarps / 2) {
     const int item = base + entry_in_cta;
-    if (lane64 == 0) {
-      int mine = -1, other = -1;
-      if (item < k) {
-        mine = sh.members[item];
-        other = item < kNbrCache ? sh.nbr[item * 6 + axis * 2 + side] : resolveNeighbor(c, mine, axis * 2 + side);
-      }
-      sh.slot[group * 2] = mine;
-      sh.slot[group * 2 + 1] = other;
-      sh.upd[group * 2] = 0;
-      sh.upd[group * 2 + 1] = 0;
+    int mine = -1, other = -1;
+    if (item < k) {
+      mine = sh.members[item];
+      other = item < kNbrCache ? sh.nbr[item * 6 + axis * 2 + side] : resolveNeighbor(c, mine, axis * 2 + side);
     }
-    __syncthreads();
-    const int mine = sh.slot[group * 2], other = sh.slot[group * 2 + 1];
+    bool updA = false, updB = false;  // A = low block's hi face, B = high block's lo face
     if (mine >= 0 && other >= 0) {
-      // membership of the neighbour and the two face voxels are fetched in the same round trip
+      // membership of the neighbour and the face voxels are fetched in the same round trip
       const int other_stamp = __ldcg(stamp_cur + other);
-      unsigned int* gHi = esdfBlockPtr(c.esdf, side == 0 ? mine : other) + vHi * kEsdfVoxelWords;   // A.hi
-      unsigned int* gLo = esdfBlockPtr(c.esdf, side == 0 ? other : mine) + vLo * kEsdfVoxelWords;   // B.lo
-      VoxelRegs A = loadVoxel(gHi), B = loadVoxel(gLo);
-      if (side == 0) {
-        if (updateSingleNeighbor(A, B, gLo, axis, +1, c.max_sq)) sh.upd[group * 2 + 1] = 1;  // B (= other) updated
-        if (other_stamp == ring) {
-          if (updateSingleNeighbor(B, A, gHi, axis, -1, c.max_sq)) sh.upd[group * 2] = 1;  // A (= mine) updated
+      unsigned int* blkA = esdfBlockPtr(c.esdf, side == 0 ? mine : other);
+      unsigned int* blkB = esdfBlockPtr(c.esdf, side == 0 ? other : mine);
+      VoxelRegs A[2], B[2];
+      unsigned int *gHi[2], *gLo[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int f = lane + 32 * h, u = f >> 3, w = f & 7;
+        const int faceBase = (axis == 0) ? (u * 8 + w) : ((axis == 1) ? (u * 64 + w) : (u * 64 + w * 8));
+        gHi[h] = blkA + (faceBase + (kVps - 1) * strideA) * kEsdfVoxelWords;
+        gLo[h] = blkB + faceBase * kEsdfVoxelWords;
+        A[h] = loadVoxel(gHi[h]);
+        B[h] = loadVoxel(gLo[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (side == 0) {
+          updB |= updateSingleNeighbor(A[h], B[h], gLo[h], axis, +1, c.max_sq);  // P: mine -> mine + d
+          if (other_stamp == ring) updA |= updateSingleNeighbor(B[h], A[h], gHi[h], axis, -1, c.max_sq);  // Q
+        } else if (other_stamp != ring) {
+          updA |= updateSingleNeighbor(B[h], A[h], gHi[h], axis, -1, c.max_sq);  // Q: mine -> mine - d
         }
-      } else if (other_stamp != ring) {
-        if (updateSingleNeighbor(B, A, gHi, axis, -1, c.max_sq)) sh.upd[group * 2 + 1] = 1;  // A (= other) updated
       }
     }
-    __syncthreads();
-    if (lane64 == 0 && mine >= 0 && other >= 0) {
-      if (sh.upd[group * 2]) __stcg(stamp_nxt + mine, ring + 1);
-      if (sh.upd[group * 2 + 1]) __stcg(stamp_nxt + other, ring + 1);
+    updA = __any_sync(0xffffffffu, updA);
+    updB = __any_sync(0xffffffffu, updB);
+    if (lane == 0 && mine >= 0 && other >= 0) {
+      const int slotA = side == 0 ? mine : other, slotB = side == 0 ? other : mine;
+      if (updA) __stcg(stamp_nxt + slotA, ring + 1);
+      if (updB) __stcg(stamp_nxt + slotB, ring + 1);
     }
-    // the next iteration's writes to sh.slot/sh.upd are ordered by the __syncthreads above
   }
 }
 
-__global__ void __launch_bounds__(kWT, 1) esdfWaveKernel(EsdfCtx c) {
+// 96 registers x 512 threads = 3/4 of the register file: the wavefront runs on a side stream and must
+// leave room for the next frame's raycast / compaction / TSDF CTAs on the same SM.
+__global__ void __maxnreg__(96) esdfWaveKernel(EsdfCtx c) {
   extern __shared__ __align__(16) unsigned int smem[];
   __shared__ WaveShared sh;
   const int cta = blockIdx.x, nctas = gridDim.x;

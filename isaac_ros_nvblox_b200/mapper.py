@@ -284,7 +284,7 @@ class Mapper:
         cap = 0
         out = None
         if return_blocks:
-            cap = 1 << 16
+            cap = 1 << 14
             out = np.empty((cap, 3), dtype=np.int32)
         n = C.c_int32(0)
         check(self._L.nvb_mapper_integrate_depth(
