@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
 __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
   __shared__ __align__(16) unsigned int s[kBlockWords];
   __shared__ int s_any;
+  __shared__ int s_nb[27];  // slots of the 3x3x3 block neighbourhood (most parents live there)
   const int nclr = *c.clr_count;
   if (nclr == 0) return;
   const int tid = threadIdx.x;
@@ -388,6 +389,12 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
       s_any = 0;
       atomicAdd((unsigned long long*)&c.stats[3], 1ull);
     }
+    // the block load and the 27 neighbourhood probes are issued together
+    if (tid >= 32 && tid < 32 + 27) {
+      const int q = tid - 32;
+      const int dx = q % 3 - 1, dy = (q / 3) % 3 - 1, dz = q / 9 - 1;
+      s_nb[q] = (q == 13) ? slot : hashFind(c.esdf.hash, bx + dx, by + dy, bz + dz);
+    }
     unsigned int* gw = esdfBlockPtr(c.esdf, slot);
     const uint4* gblk = reinterpret_cast<const uint4*>(gw);
     for (int k = tid; k < kBlockWords / 4; k += kThreads) reinterpret_cast<uint4*>(s)[k] = gblk[k];
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
         int nb[3], nv[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          nb[a] = bi[a] + p[a] / kVps;
+          nb[a] = p[a] / kVps;  // block offset (relative)
           nv[a] = vi[a] + p[a] % kVps;
           if (nv[a] >= kVps) {
             nv[a] -= kVps;
@@ -417,10 +424,14 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
         }
         const int pv = (nv[0] * kVps + nv[1]) * kVps + nv[2];
         bool parent_is_site = false;
-        if (nb[0] == bx && nb[1] == by && nb[2] == bz) {
+        if (nb[0] == 0 && nb[1] == 0 && nb[2] == 0) {
           parent_is_site = flagSite(s[pv * kEsdfVoxelWords + 4]);
         } else {
-          const int ps = hashFind(c.esdf.hash, nb[0], nb[1], nb[2]);
+          int ps;
+          if (nb[0] >= -1 && nb[0] <= 1 && nb[1] >= -1 && nb[1] <= 1 && nb[2] >= -1 && nb[2] <= 1)
+            ps = s_nb[(nb[0] + 1) + 3 * (nb[1] + 1) + 9 * (nb[2] + 1)];
+          else
+            ps = hashFind(c.esdf.hash, bx + nb[0], by + nb[1], bz + nb[2]);
           // is_site is never written by this kernel: reading it from a block another
           // CTA is processing is race-free.
           if (ps >= 0) parent_is_site = flagSite(esdfBlockPtr(c.esdf, ps)[pv * kEsdfVoxelWords + 4]);

@@ -26,7 +26,7 @@ namespace nvb {
 namespace {
 
 #ifndef NVB_WAVE_INLINE
-#define NVB_WAVE_INLINE 0
+#define NVB_WAVE_INLINE 1
 #endif
 #if NVB_WAVE_INLINE
 #define NVB_WAVE_FN __forceinline__
@@ -34,9 +34,11 @@ namespace {
 #define NVB_WAVE_FN __noinline__
 #endif
 #ifndef NVB_WAVE_THREADS
-#define NVB_WAVE_THREADS 512
+#define NVB_WAVE_THREADS 256
 #endif
-constexpr int kWT = NVB_WAVE_THREADS;   // threads per CTA (512 -> 128 registers per thread: the register sweeps do not spill)
+constexpr int kWT = NVB_WAVE_THREADS;   // threads per CTA. Measured (profiles/wave_variants.sh): 256 and 512 threads are equally fast
+                                        // (the phase time is one block's dependent chain), 1024 threads / 64 registers spills and is 50 % slower;
+                                        // 256 x 128 registers = half of an SM's register file, so the next frame's kernels co-reside.
 constexpr int kWG = kWT / 64;           // groups of 64 threads
 constexpr int kWaveMaxMembers = 1024;   // owned candidates scanned per round
 constexpr int kNbrCache = 128;          // members whose neighbour slots are cached in smem
@@ -321,7 +323,10 @@ __device__ NVB_WAVE_FN void axisMembers(const EsdfCtx& c, WaveShared& sh, int ax
 
 // 96 registers x 512 threads = 3/4 of the register file: the wavefront runs on a side stream and must
 // leave room for the next frame's raycast / compaction / TSDF CTAs on the same SM.
-__global__ void __maxnreg__(96) esdfWaveKernel(EsdfCtx c) {
+#ifndef NVB_WAVE_MAXREG
+#define NVB_WAVE_MAXREG 128
+#endif
+__global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
   extern __shared__ __align__(16) unsigned int smem[];
   __shared__ WaveShared sh;
   const int cta = blockIdx.x, nctas = gridDim.x;
