@@ -119,30 +119,23 @@ struct WaveShared {
   int upd[kWG * 2];
 };
 
-// Scan up to kWaveMaxMembers owned candidates (one per thread) for tag[slot] == value and compact
-// the hits into sh.members. Optionally stamps the hits (initial list). Returns the member count.
-__device__ NVB_WAVE_FN int scanOwned(WaveShared& sh, const int* tag, int value, int nslots, int cta, int nctas, int first,
-                         int ncand, int* stamp_out, int stamp_value) {
+// Members of a ring are dealt round-robin over the CTAs from the ring's global list: CTA c takes entries
+// c, c+G, c+2G, ... so every CTA gets ceil(n/G) or floor(n/G) blocks (the static slot-ownership scheme this
+// replaces had max/mean of 2.5, and the slowest CTA is what a phase costs). Entries [first, first+cap) of this
+// CTA's share are cached in shared memory. Optionally stamps them (initial list of a computeEsdf call).
+__device__ NVB_WAVE_FN int loadMembers(WaveShared& sh, const int* list, int n, int cta, int nctas, int first,
+                                       int* stamp_out, int stamp_value) {
   const int tid = threadIdx.x;
-  int total = 0;
-  for (int base = 0; base < ncand; base += kWT) {
-    const int slot = cta + (first + base + tid) * nctas;
-    const bool hit = base + tid < ncand && slot < nslots && __ldcg(tag + slot) == value;
-    const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
-    if ((tid & 31) == 0) sh.scan[tid >> 5] = __popc(ballot);
-    __syncthreads();
-    int offset = total;
-    for (int w = 0; w < (tid >> 5); w++) offset += sh.scan[w];
-    if (hit) {
-      sh.members[offset + __popc(ballot & ((1u << (tid & 31)) - 1u))] = slot;
-      if (stamp_out) stamp_out[slot] = stamp_value;
-    }
-    if (tid == kWT - 1) sh.count = offset + __popc(ballot);
-    __syncthreads();
-    total = sh.count;
-    __syncthreads();
+  const int mine = (n > cta) ? (n - cta + nctas - 1) / nctas : 0;  // entries of this CTA
+  int k = mine - first;
+  k = k < 0 ? 0 : (k > kWaveMaxMembers ? kWaveMaxMembers : k);
+  for (int j = tid; j < k; j += kWT) {
+    const int slot = __ldcg(list + cta + (first + j) * nctas);
+    sh.members[j] = slot;
+    if (stamp_out) stamp_out[slot] = stamp_value;
   }
-  return total;
+  __syncthreads();
+  return k;
 }
 
 // Neighbour slots of the first kNbrCache members -> shared memory (one thread per (member, dir)).
@@ -270,7 +263,7 @@ __device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k
 //   group side 1 ("lo"): interface (b-d, b) only when b-d is NOT a member: Q = b -> b-d.
 // Destination blocks are stamped for ring+1 with a plain store.
 __device__ NVB_WAVE_FN void axisMembers(const EsdfCtx& c, WaveShared& sh, int axis, int k, const int* stamp_cur, int ring,
-                                        int* stamp_nxt) {
+                                        int* stamp_nxt, int* list_nxt, int* count_nxt) {
   // One warp per (member, side) interface, two face voxels per lane: kWT/32 interfaces = kWT/64 members per
   // iteration, so the handful of members a CTA owns are all in flight at once (one L2 round trip per phase).
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -315,8 +308,9 @@ __device__ NVB_WAVE_FN void axisMembers(const EsdfCtx& c, WaveShared& sh, int ax
     updB = __any_sync(0xffffffffu, updB);
     if (lane == 0 && mine >= 0 && other >= 0) {
       const int slotA = side == 0 ? mine : other, slotB = side == 0 ? other : mine;
-      if (updA) __stcg(stamp_nxt + slotA, ring + 1);
-      if (updB) __stcg(stamp_nxt + slotB, ring + 1);
+      // unique append to ring+1 (the stamp doubles as the membership flag of ring+1)
+      if (updA && atomicExch(stamp_nxt + slotA, ring + 1) != ring + 1) list_nxt[atomicAdd(count_nxt, 1)] = slotA;
+      if (updB && atomicExch(stamp_nxt + slotB, ring + 1) != ring + 1) list_nxt[atomicAdd(count_nxt, 1)] = slotB;
     }
   }
 }
@@ -334,14 +328,11 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
   if (*(volatile int*)c.work_count == 0) return;
   unsigned int generation = 0;
   int ring = *(volatile int*)c.ring_id;
-  const int nslots = min(*(volatile int*)c.esdf.count, c.esdf.capacity);
-  const int owned = (nslots > cta) ? (nslots - cta + nctas - 1) / nctas : 0;  // candidates of this CTA
-  const int max_owned = (nslots + nctas - 1) / nctas;                         // uniform bound
-  const int rounds = (max_owned + kWaveMaxMembers - 1) / kWaveMaxMembers;      // uniform
   int* stamp[2] = {c.stamp_a, c.stamp_b};
+  int* list[2] = {c.ring_a, c.ring_b};
   long long swept = 0, faces = 0, rings = 0;
   // CTA 0 keeps a coarse time split (ns): barriers (incl. waiting for the slowest CTA), axis phases,
-  // scan + sweep phases
+  // sweep phases
   long long t_bar = 0, t_axis = 0, t_sweep = 0, n_bar = 0, t0 = globalTimerNs(), t1;
 #define NVB_TICK(acc)   \
   t1 = globalTimerNs(); \
@@ -354,23 +345,24 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
     atomicMax((unsigned long long*)c.phase_max + n_bar, (unsigned long long)(globalTimerNs() - tw0));     \
   }
 #define NVB_PHASE_BEGIN() tw0 = globalTimerNs();
-  const int cleared_seq = *(volatile int*)c.cleared_seq;
   for (int pass = 0; pass < 2; pass++) {
-    const int* seed = pass ? c.seed_clr : c.seed_upd;
-    const int seed_value = pass ? cleared_seq : c.update_seq;
-    if (pass == 1 && cleared_seq == 0) break;  // the clear pass never ran: the cleared set is empty
+    // pass 0: blocks with sites; pass 1: the persistent cleared list (:254-257)
+    const int* src = pass ? c.cleared_list : c.upd_list;
+    int n = pass ? *(volatile int*)c.cleared_count : *(volatile int*)c.upd_count;
+    if (n == 0) continue;
     int ci = ring & 1;
-    // Initial sweep of the seed set; its members are stamped as ring `ring`.
-    int k_total = 0;
-    for (int r = 0; r < rounds; r++) {
-      const int first = r * kWaveMaxMembers;
-      const int ncand = max(0, min(kWaveMaxMembers, owned - first));
-      const int k = scanOwned(sh, seed, seed_value, nslots, cta, nctas, first, ncand, stamp[ci], ring);
-      if (rounds == 1) prefetchNeighbors(c, sh, k);
-      sweepMembers(c, sh, k, smem);
-      k_total += k;
+    const int* cur = src;  // the first ring's members are read straight from the source list
+    auto share = [&](int count) { return (count > cta) ? (count - cta + nctas - 1) / nctas : 0; };
+    auto roundsOf = [&](int count) { return ((count + nctas - 1) / nctas + kWaveMaxMembers - 1) / kWaveMaxMembers; };
+    // Initial sweep of the source list; its members are stamped as ring `ring`.
+    {
+      const int rounds = roundsOf(n);
+      for (int r = 0; r < rounds; r++) {
+        const int k = loadMembers(sh, cur, n, cta, nctas, r * kWaveMaxMembers, stamp[ci], ring);
+        if (rounds == 1) prefetchNeighbors(c, sh, k);
+        sweepMembers(c, sh, k, smem);
+      }
     }
-    if (threadIdx.x == 0 && k_total > 0) atomicAdd(c.ring_count + ci, k_total);
     if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
     NVB_TICK(t_sweep)
     NVB_PHASE_MAX()
@@ -378,23 +370,20 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
     NVB_TICK(t_bar)
     n_bar++;
     NVB_PHASE_BEGIN()
-    int n = *(volatile int*)(c.ring_count + ci);
-    int k_cached = (rounds == 1) ? k_total : -1;  // sh.members / sh.nbr hold this CTA's members of ring `ring`
     swept += n;
     while (n > 0) {
       const int ni = ci ^ 1;
+      const int rounds = roundsOf(n);
 #pragma unroll 1
       for (int axis = 0; axis < 3; axis++) {
         for (int r = 0; r < rounds; r++) {
-          int k = k_cached;
-          if (k < 0) {
-            const int first = r * kWaveMaxMembers;
-            const int ncand = max(0, min(kWaveMaxMembers, owned - first));
-            k = scanOwned(sh, stamp[ci], ring, nslots, cta, nctas, first, ncand, nullptr, 0);
+          int k = share(n);
+          if (rounds > 1) {
+            k = loadMembers(sh, cur, n, cta, nctas, r * kWaveMaxMembers, nullptr, 0);
             prefetchNeighbors(c, sh, k);
             __syncthreads();
           }
-          axisMembers(c, sh, axis, k, stamp[ci], ring, stamp[ni]);
+          axisMembers(c, sh, axis, k, stamp[ci], ring, stamp[ni], list[ni], c.ring_count + ni);
         }
         NVB_TICK(t_axis)
         NVB_PHASE_MAX()
@@ -404,38 +393,28 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
         NVB_PHASE_BEGIN()
       }
       faces += 6ll * n;
-      // Members of ring+1 = owned slots stamped during the three axis phases.
-      int k_next = 0;
-      for (int r = 0; r < rounds; r++) {
-        const int first = r * kWaveMaxMembers;
-        const int ncand = max(0, min(kWaveMaxMembers, owned - first));
-        long long ts0 = globalTimerNs();
-        const int k = scanOwned(sh, stamp[ni], ring + 1, nslots, cta, nctas, first, ncand, nullptr, 0);
-        long long ts1 = globalTimerNs();
-        if (rounds == 1) prefetchNeighbors(c, sh, k);
-        sweepMembers(c, sh, k, smem);
-        long long ts2 = globalTimerNs();
-        if (threadIdx.x == 0 && n_bar < 1000) {
-          atomicMax((unsigned long long*)c.phase_max + 1000 + n_bar, (unsigned long long)(ts1 - ts0));
-          atomicMax((unsigned long long*)c.phase_max + 2000 + n_bar, (unsigned long long)(ts2 - ts1));
-          atomicMax((unsigned long long*)c.phase_max + 3000 + n_bar, (unsigned long long)k);
+      // ring+1 = the blocks appended during the three axis phases
+      const int n_next = *(volatile int*)(c.ring_count + ni);
+      {
+        const int rounds_next = roundsOf(n_next);
+        for (int r = 0; r < rounds_next; r++) {
+          const int k = loadMembers(sh, list[ni], n_next, cta, nctas, r * kWaveMaxMembers, nullptr, 0);
+          if (rounds_next == 1) prefetchNeighbors(c, sh, k);
+          sweepMembers(c, sh, k, smem);
         }
-        k_next += k;
       }
-      if (threadIdx.x == 0 && k_next > 0) atomicAdd(c.ring_count + ni, k_next);
-      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the counter of ring+2
+      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the append counter of ring+2
       NVB_TICK(t_sweep)
       NVB_PHASE_MAX()
       gridBarrier(c.barrier, generation, nctas);
       NVB_TICK(t_bar)
       n_bar++;
       NVB_PHASE_BEGIN()
-      const int n_next = *(volatile int*)(c.ring_count + ni);
-      k_cached = (rounds == 1) ? k_next : -1;
       swept += n_next;
       rings++;
       ring++;
       ci = ni;
+      cur = list[ni];
       n = n_next;
     }
     ring++;
