@@ -41,6 +41,7 @@ constexpr int kWT = NVB_WAVE_THREADS;   // threads per CTA. Measured (profiles/w
                                         // 256 x 128 registers = half of an SM's register file, so the next frame's kernels co-reside.
 constexpr int kWG = kWT / 64;           // groups of 64 threads
 constexpr int kWaveMaxMembers = 1024;   // owned candidates scanned per round
+constexpr int kPendMax = 1024;         // pending "updated block" records per CTA per ring before a forced flush
 constexpr int kNbrCache = 128;          // members whose neighbour slots are cached in smem
 // Shared-memory image of an ESDF block for the sweeps: the 20-byte AoS voxels with ONE pad word after
 // every row of 8 voxels: word(v, f) = 5 v + f + (v >> 3). With this pitch the y- and z-line accesses of a
@@ -117,6 +118,8 @@ struct WaveShared {
   int changed[kWG];
   int slot[kWG * 2];
   int upd[kWG * 2];
+  int npend;
+  int pend[kPendMax];  // blocks updated by this CTA's face operations in the current ring (with duplicates)
 };
 
 // Members of a ring are dealt round-robin over the CTAs from the ring's global list: CTA c takes entries
@@ -308,15 +311,51 @@ __device__ NVB_WAVE_FN void axisMembers(const EsdfCtx& c, WaveShared& sh, int ax
     updB = __any_sync(0xffffffffu, updB);
     if (lane == 0 && mine >= 0 && other >= 0) {
       const int slotA = side == 0 ? mine : other, slotB = side == 0 ? other : mine;
-      // unique append to ring+1 (the stamp doubles as the membership flag of ring+1)
-      if (updA && atomicExch(stamp_nxt + slotA, ring + 1) != ring + 1) list_nxt[atomicAdd(count_nxt, 1)] = slotA;
-      if (updB && atomicExch(stamp_nxt + slotB, ring + 1) != ring + 1) list_nxt[atomicAdd(count_nxt, 1)] = slotB;
+      // Record the updated blocks; they are appended to ring+1 once per ring (flushPending), so the two
+      // dependent L2 atomics of the unique append are paid once instead of in each of the three axis phases.
+      if (updA) {
+        const int q = atomicAdd(&sh.npend, 1);
+        if (q < kPendMax) sh.pend[q] = slotA;
+        else if (atomicExch(stamp_nxt + slotA, ring + 1) != ring + 1) list_nxt[atomicAdd(count_nxt, 1)] = slotA;
+      }
+      if (updB) {
+        const int q = atomicAdd(&sh.npend, 1);
+        if (q < kPendMax) sh.pend[q] = slotB;
+        else if (atomicExch(stamp_nxt + slotB, ring + 1) != ring + 1) list_nxt[atomicAdd(count_nxt, 1)] = slotB;
+      }
     }
   }
 }
 
 // 96 registers x 512 threads = 3/4 of the register file: the wavefront runs on a side stream and must
 // leave room for the next frame's raycast / compaction / TSDF CTAs on the same SM.
+// Unique append of the recorded blocks to ring+1: the stamp (atomicExch) dedupes across CTAs and doubles as the
+// membership flag of ring+1; each warp reserves its range of the list with one atomicAdd.
+__device__ NVB_WAVE_FN void flushPending(WaveShared& sh, int* stamp_nxt, int ring, int* list_nxt, int* count_nxt) {
+  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int np = sh.npend < kPendMax ? sh.npend : kPendMax;
+  for (int base = 0; base < np; base += kWT) {
+    const int q = base + tid;
+    int slot = -1;
+    bool fresh = false;
+    if (q < np) {
+      slot = sh.pend[q];
+      fresh = atomicExch(stamp_nxt + slot, ring + 1) != ring + 1;
+    }
+    const unsigned int ballot = __ballot_sync(0xffffffffu, fresh);
+    if (ballot) {
+      int basepos = 0;
+      if (lane == 0) basepos = atomicAdd(count_nxt, __popc(ballot));
+      basepos = __shfl_sync(0xffffffffu, basepos, 0);
+      if (fresh) list_nxt[basepos + __popc(ballot & ((1u << lane) - 1u))] = slot;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) sh.npend = 0;
+  __syncthreads();
+}
+
 #ifndef NVB_WAVE_MAXREG
 #define NVB_WAVE_MAXREG 128
 #endif
@@ -326,6 +365,8 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
   const int cta = blockIdx.x, nctas = gridDim.x;
   // Empty block list: integrateBlocksTemplate returns before touching anything (:226-228).
   if (*(volatile int*)c.work_count == 0) return;
+  if (threadIdx.x == 0) sh.npend = 0;
+  __syncthreads();
   unsigned int generation = 0;
   int ring = *(volatile int*)c.ring_id;
   int* stamp[2] = {c.stamp_a, c.stamp_b};
@@ -384,7 +425,9 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
             __syncthreads();
           }
           axisMembers(c, sh, axis, k, stamp[ci], ring, stamp[ni], list[ni], c.ring_count + ni);
+          if (rounds > 1) flushPending(sh, stamp[ni], ring, list[ni], c.ring_count + ni);
         }
+        if (axis == 2 && rounds == 1) flushPending(sh, stamp[ni], ring, list[ni], c.ring_count + ni);
         NVB_TICK(t_axis)
         NVB_PHASE_MAX()
         gridBarrier(c.barrier, generation, nctas);
