@@ -2,23 +2,29 @@
 // as ONE cooperative persistent launch.
 //
 // computeEsdf(list): sweep(list); while (list not empty) { list = updateNeighborBands(list); sweep(list); }
-// runs twice per update: for the blocks with sites and for the persistent "cleared" set (:254-257).
+// runs twice per update: for the blocks with sites and for the persistent "cleared" list (:254-257).
+// The result depends on the order of the passes (x,y,z in-block sweeps; +x,-x,+y,-y,+z,-z face propagation,
+// each seeing the previous ones), so that order is kept: per ring three axis phases and one sweep phase,
+// separated by grid barriers.
 //
-// Ownership instead of lists. CTA c owns the ESDF slots {c, c+G, c+2G, ...} (G = #SMs). Ring
-// membership is a per-slot stamp (stamp[r & 1][slot] == r); a face update marks its destination
-// block for ring r+1 with one plain store; at the start of every sweep phase each CTA scans the
-// stamps of the slots it owns, keeps its members in shared memory for the three axis phases of
-// the next ring, and prefetches their six neighbour slots from the nbr table. No global lists,
-// no list atomics, no sort/unique, no per-ring hash lookups. The only global atomic is one add
-// per CTA per ring for the ring's block count (loop termination).
-//
-// Latency shape (measured, profiles/): a grid barrier costs ~1.25 us on 148 SMs and a ring needs
-// four (3 axes in order + sweep), so a phase has to be ONE round trip to L2 deep, for every CTA.
-// Hence 1024-thread CTAs (16 groups of 64 threads): the ~2 +- 2 members a CTA owns per ring are
-// all processed concurrently -- both interfaces of 8 members per axis iteration, 16 blocks per
-// sweep iteration (16 x 10 KiB of shared memory) -- instead of looping over them; sweeps run on
-// registers (a line of 8 voxels is loaded once, walked forward and backward, changed voxels are
-// written back).
+// What a phase costs is the SLOWEST CTA's dependent chain plus a 1.25 us barrier (measured,
+// profiles/README.md), ~18 rings x 4 phases per frame. The design therefore minimises round trips and
+// imbalance per phase, not bytes:
+//   * Ring membership is a per-slot stamp (stamp[r & 1][slot] == r): the face operations test "is my
+//     neighbour a member of this ring" with one load that travels with the voxel loads.
+//   * Ring r+1's member list is built unique with atomicExch on that stamp. Updated blocks are first recorded
+//     in shared memory during the three axis phases and appended once per ring (two dependent L2 atomics per
+//     ring instead of per phase); a warp reserves its list range with one atomicAdd. No sort/unique launch.
+//   * Members are dealt round-robin from the list (CTA c takes entries c, c+G, ...): every CTA gets
+//     ceil(n/G) blocks. (Static slot ownership was tried: max/mean 2.5 and the slowest CTA sets the pace.)
+//     A CTA keeps its members and their six neighbour slots (nbr table, built at allocation) in shared
+//     memory for the three axis phases: an axis phase is ONE L2 round trip (face voxels + neighbour stamp).
+//   * The +dir/-dir passes of an axis are fused per block interface (exact, see axisMembers): 3 phases, not 6;
+//     one warp per interface, two face voxels per lane, no block-level synchronisation inside the phase.
+//   * A block's three-axis sweep is a ~2 000-instruction dependent chain on two warps; it runs on registers
+//     with an integer, branch-free formulation (sweepLineRegs) -- 10 us -> ~2.5 us per block.
+//   * 256-thread CTAs with up to 128 registers (half an SM's register file) so that the next frame's
+//     raycast / compaction / TSDF kernels co-reside while the wavefront runs on its side stream.
 #include "nvb_esdf_common.cuh"
 
 namespace nvb {
@@ -48,7 +54,11 @@ constexpr int kNbrCache = 128;          // members whose neighbour slots are cac
 // warp (32 lines) hit 32 distinct banks and x-lines are 2-way (the unpadded copy is 4-way / 8-way), which
 // matters because all 16 groups of the CTA share one shared-memory pipe.
 constexpr int kPadBlockWords = kBlockWords + kVpb / kVps;  // 2560 + 64
-constexpr size_t kWaveSmemBytes = (size_t)kWG * kBlockWords * sizeof(unsigned int);  // sweep buffers
+#ifndef NVB_WAVE_PAD
+#define NVB_WAVE_PAD 0  // measured: the padded image is 30 % slower (scalar smem stores); see profiles/README.md
+#endif
+constexpr int kSweepBlockWords = NVB_WAVE_PAD ? kPadBlockWords : kBlockWords;
+constexpr size_t kWaveSmemBytes = (size_t)kWG * kSweepBlockWords * sizeof(unsigned int);  // sweep buffers
 
 // HBM -> padded smem image. Global side: 128-bit coalesced loads (640 chunks per block). Shared side:
 // the pad makes chunk destinations unaligned, so each chunk is stored as four 32-bit words; lane groups
@@ -170,7 +180,7 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
     const int v = v0 + i * stride;
-    const unsigned int* e = sm + v * kEsdfVoxelWords;
+    const unsigned int* e = sm + v * kEsdfVoxelWords + (NVB_WAVE_PAD ? (v >> 3) : 0);
     const float sq = __uint_as_float(e[0]);
     T[i] = __float2int_ru(sq);
     p0[i] = (int)e[1], p1[i] = (int)e[2], p2[i] = (int)e[3];
@@ -222,7 +232,7 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
   for (int i = 0; i < kVps; i++) {
     if ((dirty >> i) & 1u) {
       const int v = v0 + i * stride;
-      unsigned int* e = sm + v * kEsdfVoxelWords;
+      unsigned int* e = sm + v * kEsdfVoxelWords + (NVB_WAVE_PAD ? (v >> 3) : 0);
       e[0] = __float_as_uint((float)T[i]);
       e[1] = (unsigned)p0[i], e[2] = (unsigned)p1[i], e[3] = (unsigned)p2[i];
     }
@@ -231,15 +241,21 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
 }
 
 // sweepBlockBandKernel (:1390-1431) for the cached members, kWG blocks at a time.
-__device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned int* smem) {
+__device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k, unsigned int* smem,
+                                         bool prefetch_nbr) {
   const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
-  unsigned int* sm = smem + group * kBlockWords;
+  unsigned int* sm = smem + group * kSweepBlockWords;
   const int a = lane64 >> 3, b = lane64 & 7;
   for (int base = 0; base < k; base += kWG) {
     const int item = base + group;
     const int slot = item < k ? sh.members[item] : -1;
     if (lane64 == 0) sh.changed[group] = 0;
-    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
+    if (slot >= 0) {
+      if (NVB_WAVE_PAD) loadBlockPadded(sm, esdfBlockPtr(c.esdf, slot), lane64);
+      else loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
+    }
+    // neighbour slots for the coming axis phases: issued behind the block loads, not in front of them
+    if (prefetch_nbr && base == 0) prefetchNeighbors(c, sh, k);
     __syncthreads();
     bool ch = false;
 #pragma unroll 1
@@ -255,7 +271,10 @@ __device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k
     }
     if (ch) sh.changed[group] = 1;
     __syncthreads();
-    if (slot >= 0 && sh.changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
+    if (slot >= 0 && sh.changed[group]) {
+      if (NVB_WAVE_PAD) storeBlockPadded(esdfBlockPtr(c.esdf, slot), sm, lane64);
+      else storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
+    }
     __syncthreads();
   }
 }
@@ -400,8 +419,7 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
       const int rounds = roundsOf(n);
       for (int r = 0; r < rounds; r++) {
         const int k = loadMembers(sh, cur, n, cta, nctas, r * kWaveMaxMembers, stamp[ci], ring);
-        if (rounds == 1) prefetchNeighbors(c, sh, k);
-        sweepMembers(c, sh, k, smem);
+        sweepMembers(c, sh, k, smem, rounds == 1);
       }
     }
     if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
@@ -442,8 +460,7 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
         const int rounds_next = roundsOf(n_next);
         for (int r = 0; r < rounds_next; r++) {
           const int k = loadMembers(sh, list[ni], n_next, cta, nctas, r * kWaveMaxMembers, nullptr, 0);
-          if (rounds_next == 1) prefetchNeighbors(c, sh, k);
-          sweepMembers(c, sh, k, smem);
+          sweepMembers(c, sh, k, smem, rounds_next == 1);
         }
       }
       if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the append counter of ring+2
