@@ -62,10 +62,15 @@ typedef enum { NVB_MEM_HOST = 0, NVB_MEM_DEVICE = 1 } NvbMemory;
 /* Layers of the map (C/include/nvblox/map/common_names.h TsdfLayer / EsdfLayer). */
 typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1 } NvbLayer;
 
-/* nvblox::Camera without distortion (C/include/nvblox/sensors/camera.h:193-203). */
+/* nvblox::Camera (C/include/nvblox/sensors/camera.h:193-203) with its
+ * std::optional<RadialTangentialDistortionParams> (C/include/nvblox/sensors/distortion.h:24-62):
+ * has_distortion = 0 is std::nullopt. */
 typedef struct {
   float fu, fv, cu, cv;
   int32_t width, height;
+  int32_t has_distortion;
+  float k1, k2, k3, k4, k5, k6; /* radial: numerator k1..k3, denominator k4..k6 */
+  float p1, p2;                 /* tangential */
 } NvbCamera;
 
 /* WeightingFunctionType (C/include/nvblox/integrators/weighting_function.h:11-18). */

@@ -35,7 +35,9 @@ EXPORTED_SYMBOLS = [
 
 class NvbCamera(C.Structure):
     _fields_ = [("fu", C.c_float), ("fv", C.c_float), ("cu", C.c_float), ("cv", C.c_float),
-                ("width", C.c_int32), ("height", C.c_int32)]
+                ("width", C.c_int32), ("height", C.c_int32), ("has_distortion", C.c_int32),
+                ("k1", C.c_float), ("k2", C.c_float), ("k3", C.c_float), ("k4", C.c_float),
+                ("k5", C.c_float), ("k6", C.c_float), ("p1", C.c_float), ("p2", C.c_float)]
 
 
 class NvbTsdfParams(C.Structure):

@@ -312,7 +312,12 @@ bool computeViewGrid(const NvbCamera& cam, const Rigid& T_L_C, float block_size,
   const float ux[4] = {0.0f, w, w, 0.0f};
   const float vy[4] = {0.0f, 0.0f, h, h};
   Vec3 ray[4];
-  for (int k = 0; k < 4; k++) ray[k] = Vec3{(ux[k] - cam.cu) / cam.fu, (vy[k] - cam.cv) / cam.fv, 1.0f};
+  for (int k = 0; k < 4; k++) {
+    // Camera::vectorFromImagePlaneCoordinates (sensors/internal/impl/camera_impl.h:89-104)
+    float nx = (ux[k] - cam.cu) / cam.fu, ny = (vy[k] - cam.cv) / cam.fv;
+    if (cam.has_distortion) removeDistortion(cam, nx, ny);
+    ray[k] = Vec3{nx, ny, 1.0f};
+  }
   const int order[4] = {2, 1, 0, 3};
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int k = 0; k < 8; k++) {

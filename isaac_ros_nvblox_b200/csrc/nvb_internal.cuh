@@ -66,6 +66,72 @@ __host__ __device__ __forceinline__ int3 blockIndexFromPosition(float block_size
 }
 
 // ---------------------------------------------------------------------------
+// Radial-tangential lens distortion (sensors/internal/impl/distortion_impl.h). The reference mixes
+// float and double through its `1.0` / `2.0` literals; the same promotions are spelled out here.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ float radialScaleF(float r2, const NvbCamera& c) {  // :24-32, T = float
+  const float r4 = r2 * r2;
+  const float r6 = r2 * r4;
+  const float numerator = (float)(1.0 + (double)(c.k1 * r2) + (double)(c.k2 * r4) + (double)(c.k3 * r6));
+  const float denominator = (float)(1.0 + (double)(c.k4 * r2) + (double)(c.k5 * r4) + (double)(c.k6 * r6));
+  return numerator / denominator;
+}
+__host__ __device__ __forceinline__ double radialScaleD(double r2, const NvbCamera& c) {  // T = double
+  const double r4 = r2 * r2;
+  const double r6 = r2 * r4;
+  const double numerator = 1.0 + (double)c.k1 * r2 + (double)c.k2 * r4 + (double)c.k3 * r6;
+  const double denominator = 1.0 + (double)c.k4 * r2 + (double)c.k5 * r4 + (double)c.k6 * r6;
+  return numerator / denominator;
+}
+// applyDistortion (:37-60)
+__host__ __device__ __forceinline__ void applyDistortion(const NvbCamera& c, float& ux, float& uy) {
+  const float x = ux, y = uy;
+  const float r2 = x * x + y * y;
+  const float scale = radialScaleF(r2, c);
+  const float xy = x * y;
+  const float tx = (float)(2.0 * (double)c.p1 * (double)xy + (double)c.p2 * ((double)r2 + 2.0 * (double)x * (double)x));
+  const float ty = (float)(2.0 * (double)c.p2 * (double)xy + (double)c.p1 * ((double)r2 + 2.0 * (double)y * (double)y));
+  ux = x * scale + tx;
+  uy = y * scale + ty;
+}
+// removeDistortion (:93-176): Newton-Raphson in double, at most 6 iterations; compute_dR_dr2 (:62-91).
+__host__ __device__ inline void removeDistortion(const NvbCamera& c, float& ux, float& uy) {
+  const double k1 = c.k1, k2 = c.k2, k3 = c.k3, k4 = c.k4, k5 = c.k5, k6 = c.k6, p1 = c.p1, p2 = c.p2;
+  const double u_in_x = ux, u_in_y = uy;
+  double x = u_in_x, y = u_in_y;
+  for (int i = 0; i < 6; i++) {
+    const double x2 = x * x, y2 = y * y, r2 = x2 + y2;
+    const double R = radialScaleD(r2, c);
+    const double xy = x * y;
+    const double tan_x = 2.0 * p1 * xy + p2 * (r2 + 2.0 * x * x);
+    const double tan_y = 2.0 * p2 * xy + p1 * (r2 + 2.0 * y * y);
+    const double x_est = x * R + tan_x, y_est = y * R + tan_y;
+    const double error_x = x_est - u_in_x, error_y = y_est - u_in_y;
+    const double q = r2, q2 = q * q, q3 = q2 * q;
+    const double ja = k1 + 2. * k2 * q + 3. * k3 * q2;
+    const double jc = k4 + 2. * k5 * q + 3. * k6 * q2;
+    const double jb = k4 * q + k5 * q2 + k6 * q3 + 1.;
+    const double jd = k1 * q + k2 * q2 + k3 * q3 + 1.;
+    const double dR_dr2 = (ja * jb - jc * jd) / (jb * jb);
+    const double dR_dx = 2.0 * x * dR_dr2, dR_dy = 2.0 * y * dR_dr2;
+    const double a = R + x * dR_dx + 2 * p1 * y + 6 * p2 * x;
+    const double b = x * dR_dy + 2 * p1 * x + 2 * p2 * y;
+    const double cc = y * dR_dx + 2 * p2 * y + 2 * p1 * x;
+    const double d = R + y * dR_dy + 2 * p2 * x + 6 * p1 * y;
+    const double det = a * d - b * cc;
+    const double delta_x = (d * error_x - b * error_y) / det;
+    const double delta_y = (-cc * error_x + a * error_y) / det;
+    if (isfinite(delta_x) && isfinite(delta_y)) {
+      x = x - delta_x;
+      y = y - delta_y;
+    }
+    if (delta_x * delta_x + delta_y * delta_y < 1e-20) break;
+  }
+  ux = (float)x;
+  uy = (float)y;
+}
+
+// ---------------------------------------------------------------------------
 // Device-resident block hash: packed Index3D -> slot in the layer's slab.
 // Open addressing, linear probing, 64-bit keys (3 x 21 bit, biased).
 // Replaces the host unordered_map + stdgpu mirror of the reference

@@ -71,6 +71,7 @@ __device__ __forceinline__ float weighting(int type, float measured, float voxel
 }
 
 // One voxel: project, look the depth up, fuse. Returns true if (dist, weight) changed.
+template <bool kDistort>
 __device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, int vx, int vy, int vz, float& dist,
                                             float& wgt) {
   // getCenterPositionFromBlockIndexAndVoxelIndex (core/internal/impl/indexing_impl.h:51-81)
@@ -82,8 +83,10 @@ __device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, 
   // Camera::project (sensors/internal/impl/camera_impl.h:37-76)
   if (!(isfinite(p_C.x) && isfinite(p_C.y) && isfinite(p_C.z))) return false;
   if (!(p_C.z >= 1e-6f)) return false;
-  const float u = (p_C.x / p_C.z) * a.cam.fu + a.cam.cu;
-  const float v = (p_C.y / p_C.z) * a.cam.fv + a.cam.cv;
+  float un = p_C.x / p_C.z, vn = p_C.y / p_C.z;
+  if (kDistort) applyDistortion(a.cam, un, vn);
+  const float u = un * a.cam.fu + a.cam.cu;
+  const float v = vn * a.cam.fv + a.cam.cv;
   if (u > (float)a.cam.width || v > (float)a.cam.height || u < 0.0f || v < 0.0f) return false;
   const float voxel_depth = p_C.z;
   // projectThreadVoxel max-depth test (projective_integrators_common_impl.cuh:42-45)
@@ -123,6 +126,7 @@ __device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, 
   return true;
 }
 
+template <bool kDistort>
 __global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant__ TsdfArgs a) {
   const int n = *a.frame_count;
   const int tid = threadIdx.x;
@@ -145,8 +149,8 @@ __global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant
         nword = __ldcs(reinterpret_cast<const float4*>(a.tsdf_blocks + (size_t)nblk.w * kTsdfBlockBytes) + tid);
     }
     if (blk.w >= 0) {
-      const bool c0 = updateVoxel(a, blk, vx, vy, vz, word.x, word.y);
-      const bool c1 = updateVoxel(a, blk, vx, vy, vz + 1, word.z, word.w);
+      const bool c0 = updateVoxel<kDistort>(a, blk, vx, vy, vz, word.x, word.y);
+      const bool c1 = updateVoxel<kDistort>(a, blk, vx, vy, vz + 1, word.z, word.w);
       if (c0 || c1) *(reinterpret_cast<float4*>(a.tsdf_blocks + (size_t)blk.w * kTsdfBlockBytes) + tid) = word;
     }
     if (inext >= n) break;
@@ -174,7 +178,9 @@ void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsig
   a.bits_to_clear = bits_to_clear;
   a.num_words = num_words;
   // 8 resident 256-thread CTAs per SM (2048 threads): one full wave.
-  tsdfIntegrateKernel<<<num_sms * 8, 256, 0, stream>>>(a);
+  // the lens-distortion variant is a separate instantiation so the pinhole path keeps its register budget
+  if (cam.has_distortion) tsdfIntegrateKernel<true><<<num_sms * 8, 256, 0, stream>>>(a);
+  else tsdfIntegrateKernel<false><<<num_sms * 8, 256, 0, stream>>>(a);
 }
 
 }  // namespace nvb

@@ -73,8 +73,9 @@ __global__ void __launch_bounds__(kRayTileCols* kRayTileRows)
   if (active) {
     if (max_dist > 0.0f && d > max_dist) d = max_dist;
     // Camera::vectorFromPixelIndices (sensors/internal/impl/camera_impl.h:89-112)
-    const float vx = (((float)pixel_col + 0.5f) - cam.cu) / cam.fu;
-    const float vy = (((float)pixel_row + 0.5f) - cam.cv) / cam.fv;
+    float vx = (((float)pixel_col + 0.5f) - cam.cu) / cam.fu;
+    float vy = (((float)pixel_row + 0.5f) - cam.cv) / cam.fv;
+    if (cam.has_distortion) removeDistortion(cam, vx, vy);
     const float s = d + trunc_m;
     Vec3 p_C = {s * vx, s * vy, s * 1.0f};
     const Vec3 p_L = transformPoint(T_L_C, p_C);

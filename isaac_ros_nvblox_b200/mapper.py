@@ -41,10 +41,15 @@ def colmajor(T):
 
 
 class Camera:
-    """nvblox::Camera(fu, fv, cu, cv, width, height) (sensors/camera.h:33-203), no distortion."""
+    """nvblox::Camera(fu, fv, cu, cv, width, height, distortion_params) (sensors/camera.h:33-203).
+    radial = (k1..k6), tangential = (p1, p2) = RadialTangentialDistortionParams; None = std::nullopt."""
 
-    def __init__(self, fu, fv, cu, cv, width, height):
-        self.c = NvbCamera(float(fu), float(fv), float(cu), float(cv), int(width), int(height))
+    def __init__(self, fu, fv, cu, cv, width, height, radial=None, tangential=None):
+        has = radial is not None or tangential is not None
+        k = [float(v) for v in (radial or (0, 0, 0, 0, 0, 0))]
+        p = [float(v) for v in (tangential or (0, 0))]
+        self.c = NvbCamera(float(fu), float(fv), float(cu), float(cv), int(width), int(height), 1 if has else 0,
+                           *k, *p)
 
     fu = property(lambda s: s.c.fu)
     fv = property(lambda s: s.c.fv)

@@ -90,11 +90,85 @@ static i3 block_index_from_position(float block_size, v3 p) {
 /* Camera (sensors/internal/impl/camera_impl.h)                              */
 /* ------------------------------------------------------------------------- */
 
-/* vectorFromImagePlaneCoordinates (camera_impl.h:89-104), no distortion. */
+/* radialDistortionScale<T> (sensors/internal/impl/distortion_impl.h:24-32). The literal 1.0 is a double, so
+ * for T = float the float products are promoted and summed in double, then narrowed to T. */
+static float radial_scale_f(float r2, const OrCamera* c) {
+  const float r4 = r2 * r2;
+  const float r6 = r2 * r4;
+  const float numerator = (float)(1.0 + (double)(c->k1 * r2) + (double)(c->k2 * r4) + (double)(c->k3 * r6));
+  const float denominator = (float)(1.0 + (double)(c->k4 * r2) + (double)(c->k5 * r4) + (double)(c->k6 * r6));
+  return numerator / denominator;
+}
+static double radial_scale_d(double r2, const OrCamera* c) {
+  const double r4 = r2 * r2;
+  const double r6 = r2 * r4;
+  const double numerator = 1.0 + (double)c->k1 * r2 + (double)c->k2 * r4 + (double)c->k3 * r6;
+  const double denominator = 1.0 + (double)c->k4 * r2 + (double)c->k5 * r4 + (double)c->k6 * r6;
+  return numerator / denominator;
+}
+
+/* applyDistortion (distortion_impl.h:37-60): float in/out, tangential terms evaluated in double
+ * (2.0 literals) and narrowed to float. */
+static void apply_distortion(const OrCamera* c, float* ux, float* uy) {
+  const float x = *ux, y = *uy;
+  const float r2 = x * x + y * y;
+  const float scale = radial_scale_f(r2, c);
+  const float xy = x * y;
+  const float tx = (float)(2.0 * (double)c->p1 * (double)xy + (double)c->p2 * ((double)r2 + 2.0 * (double)x * (double)x));
+  const float ty = (float)(2.0 * (double)c->p2 * (double)xy + (double)c->p1 * ((double)r2 + 2.0 * (double)y * (double)y));
+  *ux = x * scale + tx;
+  *uy = y * scale + ty;
+}
+
+/* compute_dR_dr2 (distortion_impl.h:62-91). */
+static double compute_dR_dr2(double r2, double k1, double k2, double k3, double k4, double k5, double k6) {
+  const double q = r2, q2 = q * q, q3 = q2 * q;
+  const double k4q = k4 * q, k5q2 = k5 * q2, k6q3 = k6 * q3;
+  const double a = k1 + 2. * k2 * q + 3. * k3 * q2;
+  const double cc = k4 + 2. * k5 * q + 3. * k6 * q2;
+  const double b = k4q + k5q2 + k6q3 + 1.;
+  const double d = k1 * q + k2 * q2 + k3 * q3 + 1.;
+  return (a * b - cc * d) / (b * b);
+}
+
+/* removeDistortion (distortion_impl.h:93-176): Newton-Raphson in double, at most 6 iterations. */
+static void remove_distortion(const OrCamera* c, float* ux, float* uy) {
+  const double k1 = c->k1, k2 = c->k2, k3 = c->k3, k4 = c->k4, k5 = c->k5, k6 = c->k6, p1 = c->p1, p2 = c->p2;
+  const double u_in_x = *ux, u_in_y = *uy;
+  double x = u_in_x, y = u_in_y;
+  for (int i = 0; i < 6; i++) {
+    const double x2 = x * x, y2 = y * y, r2 = x2 + y2;
+    const double R = radial_scale_d(r2, c);
+    const double xy = x * y;
+    const double tan_x = 2.0 * p1 * xy + p2 * (r2 + 2.0 * x * x);
+    const double tan_y = 2.0 * p2 * xy + p1 * (r2 + 2.0 * y * y);
+    const double x_est = x * R + tan_x, y_est = y * R + tan_y;
+    const double error_x = x_est - u_in_x, error_y = y_est - u_in_y;
+    const double dR_dr2 = compute_dR_dr2(r2, k1, k2, k3, k4, k5, k6);
+    const double dR_dx = 2.0 * x * dR_dr2, dR_dy = 2.0 * y * dR_dr2;
+    const double a = R + x * dR_dx + 2 * p1 * y + 6 * p2 * x;
+    const double b = x * dR_dy + 2 * p1 * x + 2 * p2 * y;
+    const double cc = y * dR_dx + 2 * p2 * y + 2 * p1 * x;
+    const double d = R + y * dR_dy + 2 * p2 * x + 6 * p1 * y;
+    const double det = a * d - b * cc;
+    const double delta_x = (d * error_x - b * error_y) / det;
+    const double delta_y = (-cc * error_x + a * error_y) / det;
+    if (isfinite(delta_x) && isfinite(delta_y)) {
+      x = x - delta_x;
+      y = y - delta_y;
+    }
+    if (delta_x * delta_x + delta_y * delta_y < 1e-20) break;
+  }
+  *ux = (float)x;
+  *uy = (float)y;
+}
+
+/* vectorFromImagePlaneCoordinates (camera_impl.h:89-104). */
 static v3 cam_vector_from_image_plane(const OrCamera* c, float u, float v) {
   v3 r;
   r.x = (u - c->cu) / c->fu;
   r.y = (v - c->cv) / c->fv;
+  if (c->has_distortion) remove_distortion(c, &r.x, &r.y);
   r.z = 1.0f;
   return r;
 }
@@ -105,13 +179,14 @@ static v3 cam_vector_from_pixel(const OrCamera* c, int col, int row) {
 }
 
 /* Camera::project (camera_impl.h:37-63, 65-76), min_depth = 1e-6, viewport
- * check on. Returns 0 if rejected. */
+ * check on, distortion applied to the normalised coordinates if present. Returns 0 if rejected. */
 static int cam_project(const OrCamera* c, v3 p, float* u, float* v) {
   if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) return 0;
   const float min_depth = 1e-6f;
   if (!(p.z >= min_depth)) return 0;
   float un = p.x / p.z;
   float vn = p.y / p.z;
+  if (c->has_distortion) apply_distortion(c, &un, &vn);
   *u = un * c->fu + c->cu;
   *v = vn * c->fv + c->cv;
   if (*u > (float)c->width || *v > (float)c->height || *u < 0.0f || *v < 0.0f)
@@ -1064,6 +1139,15 @@ void or_tsdf_set_block(OrMap* m, const int32_t xyz[3], const OrTsdfVoxel* in) {
   i3 k = {xyz[0], xyz[1], xyz[2]};
   int32_t s = layer_allocate(&m->tsdf, k);
   memcpy(layer_block(&m->tsdf, s), in, m->tsdf.block_bytes);
+}
+
+int32_t or_camera_project(const OrCamera* cam, const float p_C[3], float uv[2]) {
+  v3 p = {p_C[0], p_C[1], p_C[2]};
+  return cam_project(cam, p, &uv[0], &uv[1]);
+}
+void or_camera_vector_from_image_plane(const OrCamera* cam, float u, float v, float out[3]) {
+  v3 r = cam_vector_from_image_plane(cam, u, v);
+  out[0] = r.x, out[1] = r.y, out[2] = r.z;
 }
 
 int32_t or_num_threads(void) {

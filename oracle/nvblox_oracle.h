@@ -31,10 +31,14 @@
 extern "C" {
 #endif
 
-/* Pinhole camera. (include/nvblox/sensors/camera.h:193-203, no distortion) */
+/* Pinhole camera with optional radial-tangential distortion (include/nvblox/sensors/camera.h:193-203). */
 typedef struct {
   float fu, fv, cu, cv;
   int32_t width, height;
+  /* std::optional<RadialTangentialDistortionParams> (sensors/distortion.h:24-62, camera.h:202) */
+  int32_t has_distortion;
+  float k1, k2, k3, k4, k5, k6; /* radial numerator k1..k3, denominator k4..k6 */
+  float p1, p2;                 /* tangential */
 } OrCamera;
 
 /* Weighting modes (include/nvblox/integrators/weighting_function.h:11-18). */
@@ -140,6 +144,10 @@ int32_t or_tsdf_get_block(const OrMap* map, const int32_t xyz[3], OrTsdfVoxel* o
 int32_t or_esdf_get_block(const OrMap* map, const int32_t xyz[3], OrEsdfVoxel* out);
 /* Test helper: overwrite / create a TSDF block. */
 void or_tsdf_set_block(OrMap* map, const int32_t xyz[3], const OrTsdfVoxel* in);
+
+/* Camera::project / vectorFromImagePlaneCoordinates exposed for the distortion tests. */
+int32_t or_camera_project(const OrCamera* cam, const float p_C[3], float uv[2]);
+void or_camera_vector_from_image_plane(const OrCamera* cam, float u, float v, float out[3]);
 
 /* Number of OpenMP threads the oracle will use (1 if built without OpenMP). */
 int32_t or_num_threads(void);

@@ -35,7 +35,15 @@ WEIGHT_LINEAR_WITH_MAX = 5
 
 class Camera(C.Structure):
     _fields_ = [("fu", C.c_float), ("fv", C.c_float), ("cu", C.c_float), ("cv", C.c_float),
-                ("width", C.c_int32), ("height", C.c_int32)]
+                ("width", C.c_int32), ("height", C.c_int32), ("has_distortion", C.c_int32),
+                ("k1", C.c_float), ("k2", C.c_float), ("k3", C.c_float), ("k4", C.c_float),
+                ("k5", C.c_float), ("k6", C.c_float), ("p1", C.c_float), ("p2", C.c_float)]
+
+    def with_distortion(self, k=(0, 0, 0, 0, 0, 0), p=(0, 0)):
+        """RadialTangentialDistortionParams{radial k1..k6, tangential p1, p2}."""
+        c = Camera(self.fu, self.fv, self.cu, self.cv, self.width, self.height, 1, *[float(v) for v in k],
+                   *[float(v) for v in p])
+        return c
 
 
 class TsdfParams(C.Structure):
@@ -106,6 +114,9 @@ def lib():
     L.or_esdf_get_block.argtypes = [vp, ip, vp]
     L.or_esdf_get_block.restype = C.c_int32
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
+    L.or_camera_project.argtypes = [C.POINTER(Camera), fp, fp]
+    L.or_camera_project.restype = C.c_int32
+    L.or_camera_vector_from_image_plane.argtypes = [C.POINTER(Camera), C.c_float, C.c_float, fp]
     L.or_num_threads.restype = C.c_int32
     L.or_set_num_threads.argtypes = [C.c_int32]
     _lib = L
@@ -253,6 +264,19 @@ class OracleMap:
 
     def esdf_layer(self):
         return {tuple(int(c) for c in k): self.esdf_block(k) for k in self.esdf_block_indices()}
+
+
+def camera_project(cam, p_C):
+    p = np.asarray(p_C, dtype=np.float32)
+    uv = np.zeros(2, np.float32)
+    ok = lib().or_camera_project(C.byref(cam), _fp(p), _fp(uv))
+    return (uv if ok else None)
+
+
+def camera_vector_from_image_plane(cam, u, v):
+    out = np.zeros(3, np.float32)
+    lib().or_camera_vector_from_image_plane(C.byref(cam), float(u), float(v), _fp(out))
+    return out
 
 
 def num_threads():

@@ -4,14 +4,18 @@ import numpy as np
 from isaac_ros_nvblox_b200 import synthetic as syn
 
 
-def cameras(width=640, height=480, f=300.0):
+def cameras(width=640, height=480, f=300.0, radial=None, tangential=None):
     """(synthetic, product, oracle) camera objects with the reference's test intrinsics
-    (nvblox/tests/test_esdf_integrator.cpp:121), scaled to the image size."""
+    (nvblox/tests/test_esdf_integrator.cpp:121), scaled to the image size; optional lens distortion
+    for the product and oracle cameras (the synthetic renderer stays pinhole: it only makes inputs)."""
     import isaac_ros_nvblox_b200 as nvb
     from oracle import oracle as orc
     s = f * width / 640.0
     cs = syn.PinholeCamera(s, s, width / 2.0, height / 2.0, width, height)
-    return cs, nvb.Camera(cs.fu, cs.fv, cs.cu, cs.cv, width, height), orc.Camera(cs.fu, cs.fv, cs.cu, cs.cv, width, height)
+    ocam = orc.Camera(cs.fu, cs.fv, cs.cu, cs.cv, width, height)
+    if radial is not None or tangential is not None:
+        ocam = ocam.with_distortion(k=radial or (0,) * 6, p=tangential or (0, 0))
+    return cs, nvb.Camera(cs.fu, cs.fv, cs.cu, cs.cv, width, height, radial, tangential), ocam
 
 
 def sort_rows(a):

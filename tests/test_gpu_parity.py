@@ -441,3 +441,30 @@ def test_block_list_union_kernel(gpu):
     u = multi_gpu.merge_block_lists_device(m, torch.from_numpy(lists[0]).cuda()).cpu().numpy()
     assert np.array_equal(sort_rows(u), np.unique(lists[0], axis=0))
     m.close()
+
+
+FIXTURE_RADIAL = (0.1, 0.1, 0.01, 0.001, 0.001, 0.001)  # tests/include/nvblox/tests/sensor_fixture.h:97-104
+FIXTURE_TANGENTIAL = (0.01, 0.02)
+
+
+@pytest.mark.parametrize("dist", [(FIXTURE_RADIAL, FIXTURE_TANGENTIAL), ((-0.05, 0.01, 0, 0.02, 0, 0), (0.001, -0.0005)),
+                                  ((0,) * 6, (0, 0))])
+def test_distorted_camera_full_path(gpu, dist):
+    """Camera with RadialTangentialDistortionParams through raycast (removeDistortion), TSDF (applyDistortion)
+    and ESDF: block lists, TSDF bits and ESDF fields equal the oracle's."""
+    cs, cam, ocam = cameras(320, 240, radial=dist[0], tangential=dist[1])
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:3], noise_sigma_rel=0.005, seed=11)
+    m, _ = _run_pair(0.05, frames, cam, ocam, esdf=True)
+    m.close()
+
+
+def test_distorted_view_raycast_640x480(gpu):
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(radial=FIXTURE_RADIAL, tangential=FIXTURE_TANGENTIAL)
+    m = nvb.Mapper(0.05)
+    for T in syn.circle_trajectory(80)[::20]:
+        depth = syn.render_depth(syn.box_with_cube(), cs, T)
+        got = nvb.ViewCalculator(m).get_blocks_in_image_view_raycast(depth, T, cam, 0.4, 0.2, 7.0)
+        want = orc.view_raycast(depth, T, ocam, 0.4, 0.2)
+        assert np.array_equal(got, want)
+    m.close()

@@ -314,3 +314,70 @@ def test_ragged_and_tiny_images():
         blocks = orc.view_raycast(depth, np.eye(4, dtype=np.float32), cam, 0.4, 0.2, orc.default_tsdf_params())
         assert len(blocks) >= 1
         assert len({tuple(b) for b in blocks}) == len(blocks)
+
+
+# --- test_camera.cu:518-566 (DistortionUndistortion_P3dRoundtrip / P2dRoundtrip) ---------------
+ORBEC = dict(fu=504.563, fv=504.501, cu=522.327, cv=512.519, w=1024, h=1024,
+             k=(9.51684, 4.65586, 0.167834, 9.84895, 7.84502, 1.066), p=(0.000100116, 4.73081e-05))
+
+
+def _orbec(scale=None):
+    s = scale if scale is not None else np.ones(12)
+    c = orc.Camera(ORBEC["fu"] * s[0], ORBEC["fv"] * s[1], ORBEC["cu"] * s[2], ORBEC["cv"] * s[3], 1024, 1024)
+    return c.with_distortion(k=[ORBEC["k"][i] * s[4 + i] for i in range(6)], p=[ORBEC["p"][i] * s[10 + i] for i in range(2)])
+
+
+def test_distortion_p2d_roundtrip():
+    """unproject(u) -> project == u within 1e-4 relative (test_camera.cu:545-566), perturbed Orbbec calibrations."""
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        cam = _orbec(rng.uniform(0.9, 1.1, 12))
+        u, v = rng.uniform(0, 1024), rng.uniform(0, 1024)
+        ray = orc.camera_vector_from_image_plane(cam, u, v)
+        uv = orc.camera_project(cam, ray * 10.0)
+        if uv is None:  # outside the viewport by rounding at the border
+            assert min(u, v) < 1.0 or max(u, v) > 1023.0
+            continue
+        assert np.allclose(uv, [u, v], rtol=1e-4, atol=2e-2)
+
+
+def test_distortion_p3d_roundtrip():
+    """project(p) -> unproject at p.z == p (test_camera.cu:518-543)."""
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        cam = _orbec(rng.uniform(0.9, 1.1, 12))
+        u, v = rng.uniform(100, 900), rng.uniform(100, 900)
+        ray = orc.camera_vector_from_image_plane(cam, u, v)
+        p = ray * rng.uniform(1.0, 1000.0)
+        uv = orc.camera_project(cam, p)
+        assert uv is not None
+        back = orc.camera_vector_from_image_plane(cam, uv[0], uv[1]) * p[2]
+        assert np.allclose(back, p, rtol=1e-4, atol=1e-4 * p[2])
+
+
+def test_zero_distortion_equals_pinhole():
+    pin = orc.Camera(300, 300, 320, 240, 640, 480)
+    zero = pin.with_distortion()
+    for u, v in [(0.5, 0.5), (320.0, 240.0), (639.5, 479.5), (123.4, 456.7)]:
+        a = orc.camera_vector_from_image_plane(pin, u, v)
+        b = orc.camera_vector_from_image_plane(zero, u, v)
+        assert np.allclose(a, b, atol=1e-7)
+        pa, pb = orc.camera_project(pin, a * 3), orc.camera_project(zero, b * 3)
+        assert np.allclose(pa, pb, atol=1e-4)
+
+
+def test_distorted_camera_integrates_a_plane():
+    """The default test camera of the reference's fixtures carries distortion
+    (tests/include/nvblox/tests/sensor_fixture.h:91-104); a plane seen through it still reconstructs."""
+    cam = orc.Camera(300, 300, 320, 240, 640, 480).with_distortion(k=(0.1, 0.1, 0.01, 0.001, 0.001, 0.001), p=(0.01, 0.02))
+    m = orc.OracleMap(0.05)
+    blocks = m.integrate_depth(np.full((480, 640), 4.0, np.float32), np.eye(4, dtype=np.float32), cam)
+    assert len(blocks) > 500
+    n = 0
+    for k, blk in m.tsdf_layer().items():
+        sel = blk["weight"] > 0
+        z = k[2] * 0.4 + (np.arange(8) + 0.5) * 0.05
+        expect = np.clip(np.broadcast_to(4.0 - z, (8, 8, 8)), -0.2, 0.2)
+        assert np.allclose(blk["distance"][sel], expect[sel], atol=1e-5)
+        n += int(sel.sum())
+    assert n > 10000
