@@ -47,48 +47,74 @@ def make_frames(num_frames, rank, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every 5 ms
+    (the timed region is a fraction of a second, too short for `nvidia-smi -lms`); falls back to one
+    nvidia-smi query if NVML is not importable."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
             try:
-                sm.append(float(r[0])), mx.append(float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1)
+        if not self.sm:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "samples": 1, "reasons": [], "source": "nvidia-smi after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock source"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "samples": len(self.sm),
+                "reasons": sorted(self.reasons), "source": "NVML, 5 ms period, timed region only"}
+
+
+def ncu_traffic_bytes(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of the same launch sequence (profiles/ncu_full_raw_r1_final.csv); None if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "ncu_full_raw_r1_final.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if kernel_substr in r[ik]]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
 
 
 def measured_peak_gbs():
@@ -99,10 +125,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def cpu_threads():
+    """OpenMP threads for the CPU port: its parallel regions are short (one per ESDF phase), so beyond ~16
+    threads the fork/join cost outweighs the work on a many-core host."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def cpu_baseline(frames_np, cam_s, sample_frames):
     """The reference's algorithm on the host cores (oracle port, OpenMP where the reference's kernels
     are race-free): TSDF + ESDF on the first `sample_frames` frames of the same sequence."""
     from oracle import oracle as orc
+    orc.set_num_threads(cpu_threads())
     ocam = orc.Camera(cam_s.fu, cam_s.fv, cam_s.cu, cam_s.cv, cam_s.width, cam_s.height)
     o = orc.OracleMap(VOXEL)
     t0 = time.perf_counter()
@@ -119,6 +152,7 @@ def run_reference(args, rank, world):
         return
     cam_s, frames = make_frames(args.cpu_sample_frames, 0, 1)
     from oracle import oracle as orc
+    orc.set_num_threads(cpu_threads())
     ocam = orc.Camera(cam_s.fu, cam_s.fv, cam_s.cu, cam_s.cv, cam_s.width, cam_s.height)
 
     def step():
@@ -286,8 +320,15 @@ def main():
         peak, peak_src = measured_peak_gbs()
         dom_ms, dom_calls = st[dom]
         achieved = (bytes_by_stage[dom] / (dom_ms * 1e-3)) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        kernel_of_stage = {"esdf/integrate/compute": "esdfWaveKernel", "esdf/integrate/mark_sites": "esdfMarkTmaKernel",
+                           "esdf/integrate/clear": "esdfClearKernel", "tsdf/integrate/update_blocks": "tsdfIntegrateKernel",
+                           "tsdf/integrate/allocate_blocks": "compactAllocateKernel",
+                           "view_calculator/raycast": "viewRaycastKernel"}
+        roofline = {"bound": "hbm", "kernel": "%s (%s)" % (kernel_of_stage.get(dom, dom), dom), "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic_bytes(kernel_of_stage.get(dom, dom)), "peak_source": peak_src,
+                    "note": "latency/dependency-bound at 5 cm voxels (see DESIGN.md section 6); traffic = DRAM bytes per launch "
+                            "from the committed ncu capture (cold cache), below the algorithmic bytes because the map is L2-resident",
                     "bytes_per_launch": bytes_by_stage[dom] / max(dom_calls, 1),
                     "avg_launch_ms": dom_ms / max(dom_calls, 1)}
         map_stats = {"tsdf_blocks": m.tsdf_layer().num_blocks(), "esdf_blocks": m.esdf_layer().num_blocks(),
