@@ -623,14 +623,14 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
   if ((rc = ensureEsdfCapacity(m, (long long)std::min(m->tsdf_count_ub, m->tsdf.capacity) + m->esdf_extra_ub))) return rc;
   m->update_seq++;
   EsdfCtx c = makeEsdfCtx(m);
+  c.tracker_dirty = from_tracker ? m->dirty : nullptr;
+  c.tracker_todo_count = from_tracker ? m->todo_count : nullptr;
   // the previous wavefront still owns the ESDF scratch (counters, stamps, barrier)
   NVB_CUDA(joinEsdf(m));
   beginStage(m, 3);
   if (from_tracker) {
     launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, m->stream);
-    launchTodoConsume(m->todo_slots, m->todo_count, m->dirty, m->stream);
-    NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
-    m->launches += 2;
+    m->launches += 1;
   } else {
     launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, m->stream);
     m->launches += 1;

@@ -57,6 +57,7 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
   int x, y, z, tslot;
   if (in_slots) {
     tslot = in_slots[i];
+    if (c.tracker_dirty) c.tracker_dirty[tslot] = 0;  // this block's pending update is being consumed
     x = c.tsdf.block_index[3 * tslot], y = c.tsdf.block_index[3 * tslot + 1], z = c.tsdf.block_index[3 * tslot + 2];
   } else {
     x = in_xyz[3 * i], y = in_xyz[3 * i + 1], z = in_xyz[3 * i + 2];
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
   __shared__ int s_flags[3];  // updated, cleared, changed
   const int tid = threadIdx.x;
   const int n = *c.work_count;
+  if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;  // list consumed by the allocate kernel
   for (int item = blockIdx.x; item < n; item += gridDim.x) {
     const int4 w = c.work[item];
     if (w.x >= 0 && w.z && tid < 6) {
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
   __shared__ int s_flags[3];  // updated, cleared, changed
   const int tid = threadIdx.x;
   const int n = *c.work_count;
+  if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;  // list consumed by the allocate kernel
   const int my_count = (n > (int)blockIdx.x) ? (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (tid == 0) {
     for (int s = 0; s < kMarkStages; s++) tma::mbarInit(&s_bar[s], 1);

@@ -317,6 +317,9 @@ struct EsdfCtx {
   int* seed_clr;      // per slot: == *cleared_seq <=> member of the persistent cleared list (computeEsdf #2 seeds)
   int* cleared_seq;   // device: update_seq of the last update whose clear pass ran
   int update_seq;     // host: sequence number of this update (monotone, starts at 1)
+  // tracker (BlocksToUpdateTracker::markBlocksAsUpdated fused into the ESDF kernels); null on explicit lists
+  int* tracker_dirty;
+  int* tracker_todo_count;
   unsigned int* barrier;  // grid barrier counter
   unsigned long long* phase_max;  // debug: per-phase max-over-CTAs work time (1000 entries)
   long long* stats;    // 8 counters
