@@ -209,6 +209,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the depth-integration path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # rank 0 must print exactly one line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION) goes there too
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cam_s, frames = make_frames(args.frames, rank, world)
