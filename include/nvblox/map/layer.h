@@ -56,5 +56,6 @@ class VoxelBlockLayer {
   int id_;
 };
 using TsdfLayer = VoxelBlockLayer<TsdfVoxel>;
+using OccupancyLayer = VoxelBlockLayer<OccupancyVoxel>;
 using EsdfLayer = VoxelBlockLayer<EsdfVoxel>;
 }  // namespace nvblox

@@ -1,4 +1,4 @@
-// nvblox/map/voxels.h -- TsdfVoxel / EsdfVoxel with the reference's layout
+// nvblox/map/voxels.h -- TsdfVoxel / OccupancyVoxel / EsdfVoxel with the reference's layout
 // (nvblox/include/nvblox/map/voxels.h:28-74); these are the bytes stored in HBM.
 #pragma once
 #include "nvblox/core/types.h"
@@ -6,6 +6,9 @@ namespace nvblox {
 struct TsdfVoxel {
   float distance = 0.0f;
   float weight = 0.0f;
+};
+struct OccupancyVoxel {
+  float log_odds = 0.0f;
 };
 struct EsdfVoxel {
   float squared_distance_vox = 0.0f;
@@ -15,5 +18,6 @@ struct EsdfVoxel {
   bool is_site = false;
 };
 static_assert(sizeof(TsdfVoxel) == 8, "TsdfVoxel layout");
+static_assert(sizeof(OccupancyVoxel) == 4, "OccupancyVoxel layout");
 static_assert(sizeof(EsdfVoxel) == 20, "EsdfVoxel layout");
 }  // namespace nvblox

@@ -5,6 +5,8 @@
 //   updateEsdf(UpdateFullLayer)                            mapper.h:326
 //   tsdf_layer() / esdf_layer()                            mapper.h:372,393
 //   tsdf_integrator() / esdf_integrator()                  mapper.h:442,534
+//   Mapper(voxel_size_m, memory_type, ProjectiveLayerType::kOccupancy), occupancy_layer(), occupancy_integrator()
+//                                                          mapper.h:52-53,119-124,374,456
 #pragma once
 #include <vector>
 #include "nvblox/integrators/weighting_function.h"
@@ -16,6 +18,30 @@ namespace nvblox {
 
 enum class UpdateFullLayer { kNo, kYes };
 enum class ProjectiveLayerType { kTsdf, kOccupancy, kTsdfWithFreespace, kNone };
+
+namespace b200_detail {
+// integrateFrame(depth_frame, T_L_C, camera, layer, updated_blocks) of either projective integrator.
+inline void integrateFrame(NvbMapper* m, const MaskedDepthImageConstView& depth, const Transform& T_L_C,
+                           const Camera& camera, std::vector<Index3D>* updated_blocks) {
+  const MonoImageConstView& mk = depth.mask();
+  int32_t n = 0;
+  std::vector<int32_t> raw;
+  int32_t cap = 0;
+  if (updated_blocks) { cap = 1 << 16; raw.resize((size_t)cap * 3); }
+  check(nvb_mapper_integrate_depth(m, depth.dataConstPtr(), mk.dataConstPtr(), (int)depth.mode(),
+                                   depth.on_device() ? NVB_MEM_DEVICE : NVB_MEM_HOST, depth.rows(), depth.cols(),
+                                   T_L_C.data(), camera.c_abi(), cap ? raw.data() : nullptr, cap, &n),
+        "integrateFrame", nvb_last_error());
+  if (updated_blocks) {
+    if (n > cap) {
+      raw.resize((size_t)n * 3);
+      check(nvb_mapper_last_frame_blocks(m, raw.data(), n, &n), "integrateFrame", nvb_last_error());
+    }
+    updated_blocks->resize((size_t)n);
+    for (int i = 0; i < n; i++) (*updated_blocks)[i] = Index3D(raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]);
+  }
+}
+}  // namespace b200_detail
 
 // ProjectiveTsdfIntegrator's parameter surface + integrateFrame
 // (integrators/projective_tsdf_integrator.h:48-121, internal/projective_integrator.h:56-85).
@@ -36,27 +62,37 @@ class ProjectiveTsdfIntegrator {
   // integrateFrame(depth_frame, T_L_C, camera, layer, updated_blocks)
   void integrateFrame(const MaskedDepthImageConstView& depth, const Transform& T_L_C, const Camera& camera,
                       TsdfLayer* /*layer of this mapper*/, std::vector<Index3D>* updated_blocks = nullptr) {
-    const MonoImageConstView& mk = depth.mask();
-    int32_t n = 0;
-    std::vector<int32_t> raw;
-    int32_t cap = 0;
-    if (updated_blocks) { cap = 1 << 16; raw.resize((size_t)cap * 3); }
-    b200_detail::check(nvb_mapper_integrate_depth(m_, depth.dataConstPtr(), mk.dataConstPtr(), (int)depth.mode(),
-                                                  depth.on_device() ? NVB_MEM_DEVICE : NVB_MEM_HOST, depth.rows(),
-                                                  depth.cols(), T_L_C.data(), camera.c_abi(), cap ? raw.data() : nullptr,
-                                                  cap, &n), "integrateFrame", nvb_last_error());
-    if (updated_blocks) {
-      if (n > cap) {
-        raw.resize((size_t)n * 3);
-        b200_detail::check(nvb_mapper_last_frame_blocks(m_, raw.data(), n, &n), "integrateFrame", nvb_last_error());
-      }
-      updated_blocks->resize((size_t)n);
-      for (int i = 0; i < n; i++) (*updated_blocks)[i] = Index3D(raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]);
-    }
+    b200_detail::integrateFrame(m_, depth, T_L_C, camera, updated_blocks);
   }
  private:
   NvbTsdfParams get() const { NvbTsdfParams p; b200_detail::check(nvb_mapper_get_tsdf_params(m_, &p), "tsdf params", nvb_last_error()); return p; }
   void set(const NvbTsdfParams& p) { b200_detail::check(nvb_mapper_set_tsdf_params(m_, &p), "tsdf params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+
+// ProjectiveOccupancyIntegrator (integrators/projective_occupancy_integrator.h:36-131): sensor model + integrateFrame.
+class ProjectiveOccupancyIntegrator {
+ public:
+  explicit ProjectiveOccupancyIntegrator(NvbMapper* m) : m_(m) {}
+  float free_region_occupancy_probability() const { return get().free_region_occupancy_probability; }
+  void free_region_occupancy_probability(float v) { auto p = get(); p.free_region_occupancy_probability = v; set(p); }
+  float occupied_region_occupancy_probability() const { return get().occupied_region_occupancy_probability; }
+  void occupied_region_occupancy_probability(float v) { auto p = get(); p.occupied_region_occupancy_probability = v; set(p); }
+  float unobserved_region_occupancy_probability() const { return get().unobserved_region_occupancy_probability; }
+  void unobserved_region_occupancy_probability(float v) { auto p = get(); p.unobserved_region_occupancy_probability = v; set(p); }
+  float occupied_region_half_width_m() const { return get().occupied_region_half_width_m; }
+  void occupied_region_half_width_m(float v) { auto p = get(); p.occupied_region_half_width_m = v; set(p); }
+  float truncation_distance_vox() const { return ProjectiveTsdfIntegrator(m_).truncation_distance_vox(); }
+  void truncation_distance_vox(float v) { ProjectiveTsdfIntegrator(m_).truncation_distance_vox(v); }
+  float max_integration_distance_m() const { return ProjectiveTsdfIntegrator(m_).max_integration_distance_m(); }
+  void max_integration_distance_m(float v) { ProjectiveTsdfIntegrator(m_).max_integration_distance_m(v); }
+  void integrateFrame(const MaskedDepthImageConstView& depth, const Transform& T_L_C, const Camera& camera,
+                      OccupancyLayer* /*layer of this mapper*/, std::vector<Index3D>* updated_blocks = nullptr) {
+    b200_detail::integrateFrame(m_, depth, T_L_C, camera, updated_blocks);
+  }
+ private:
+  NvbOccupancyParams get() const { NvbOccupancyParams p; b200_detail::check(nvb_mapper_get_occupancy_params(m_, &p), "occupancy params", nvb_last_error()); return p; }
+  void set(const NvbOccupancyParams& p) { b200_detail::check(nvb_mapper_set_occupancy_params(m_, &p), "occupancy params", nvb_last_error()); }
   NvbMapper* m_;
 };
 
@@ -70,13 +106,21 @@ class EsdfIntegrator {
   void max_site_distance_vox(float v) { auto p = get(); p.max_site_distance_vox = v; set(p); }
   float min_weight() const { return get().min_weight; }
   void min_weight(float v) { auto p = get(); p.min_weight = v; set(p); }
+  float occupied_threshold() const { return get().occupied_threshold; }
+  void occupied_threshold(float v) { auto p = get(); p.occupied_threshold = v; set(p); }
   // integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
-  void integrateBlocks(const TsdfLayer&, const std::vector<Index3D>& block_indices, EsdfLayer*) {
+  void integrateBlocks(const OccupancyLayer&, const std::vector<Index3D>& block_indices, EsdfLayer* e) {
+    integrateBlocksImpl(block_indices, e);
+  }
+  void integrateBlocks(const TsdfLayer&, const std::vector<Index3D>& block_indices, EsdfLayer* e) {
+    integrateBlocksImpl(block_indices, e);
+  }
+ private:
+  void integrateBlocksImpl(const std::vector<Index3D>& block_indices, EsdfLayer*) {
     std::vector<int32_t> raw(block_indices.size() * 3 + 3);
     for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
     b200_detail::check(nvb_esdf_integrate_blocks(m_, raw.data(), (int32_t)block_indices.size()), "integrateBlocks", nvb_last_error());
   }
- private:
   NvbEsdfParams get() const { NvbEsdfParams p; b200_detail::check(nvb_mapper_get_esdf_params(m_, &p), "esdf params", nvb_last_error()); return p; }
   void set(const NvbEsdfParams& p) { b200_detail::check(nvb_mapper_set_esdf_params(m_, &p), "esdf params", nvb_last_error()); }
   NvbMapper* m_;
@@ -84,10 +128,16 @@ class EsdfIntegrator {
 
 class Mapper {
  public:
-  explicit Mapper(float voxel_size_m, MemoryType = MemoryType::kDevice, ProjectiveLayerType = ProjectiveLayerType::kTsdf) {
+  explicit Mapper(float voxel_size_m, MemoryType = MemoryType::kDevice,
+                  ProjectiveLayerType projective_layer_type = ProjectiveLayerType::kTsdf)
+      : projective_layer_type_(projective_layer_type) {
     NvbMapperOptions o;
     nvb_default_mapper_options(&o);
     o.voxel_size_m = voxel_size_m;
+    // kTsdfWithFreespace / kNone are outside this path: nvb_mapper_create rejects them.
+    o.projective_layer_type = projective_layer_type == ProjectiveLayerType::kTsdf        ? NVB_PROJECTIVE_TSDF
+                              : projective_layer_type == ProjectiveLayerType::kOccupancy ? NVB_PROJECTIVE_OCCUPANCY
+                                                                                         : -1;
     b200_detail::check(nvb_mapper_create(&o, &m_), "Mapper", nvb_last_error());
   }
   ~Mapper() { nvb_mapper_destroy(m_); }
@@ -98,7 +148,8 @@ class Mapper {
     integrateDepth(MaskedDepthImageConstView(depth_frame, kMaskActiveEverywhere), T_L_C, camera);
   }
   void integrateDepth(const MaskedDepthImageConstView& depth_frame, const Transform& T_L_C, const Camera& camera) {
-    tsdf_integrator().integrateFrame(depth_frame, T_L_C, camera, nullptr, nullptr);
+    // Mapper::integrateDepth dispatches on the projective layer type (mapper_impl.h:28-81)
+    b200_detail::integrateFrame(m_, depth_frame, T_L_C, camera, nullptr);
   }
   void updateEsdf(UpdateFullLayer full = UpdateFullLayer::kNo) {
     b200_detail::check(nvb_mapper_update_esdf(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdf", nvb_last_error());
@@ -106,11 +157,15 @@ class Mapper {
   void clear() { b200_detail::check(nvb_mapper_clear(m_), "clear", nvb_last_error()); }
   float voxel_size_m() const { return nvb_mapper_voxel_size(m_); }
   TsdfLayer tsdf_layer() const { return TsdfLayer(m_, NVB_LAYER_TSDF); }
+  OccupancyLayer occupancy_layer() const { return OccupancyLayer(m_, NVB_LAYER_OCCUPANCY); }
   EsdfLayer esdf_layer() const { return EsdfLayer(m_, NVB_LAYER_ESDF); }
+  ProjectiveLayerType projective_layer_type() const { return projective_layer_type_; }
+  ProjectiveOccupancyIntegrator occupancy_integrator() const { return ProjectiveOccupancyIntegrator(m_); }
   ProjectiveTsdfIntegrator tsdf_integrator() const { return ProjectiveTsdfIntegrator(m_); }
   EsdfIntegrator esdf_integrator() const { return EsdfIntegrator(m_); }
   NvbMapper* c_abi() const { return m_; }
  private:
   NvbMapper* m_ = nullptr;
+  ProjectiveLayerType projective_layer_type_;
 };
 }  // namespace nvblox

@@ -60,7 +60,10 @@ typedef enum {
 typedef enum { NVB_MEM_HOST = 0, NVB_MEM_DEVICE = 1 } NvbMemory;
 
 /* Layers of the map (C/include/nvblox/map/common_names.h TsdfLayer / EsdfLayer). */
-typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1 } NvbLayer;
+typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1, NVB_LAYER_OCCUPANCY = 2 } NvbLayer;
+
+/* ProjectiveLayerType of a Mapper (C/include/nvblox/mapper/mapper.h:40-48): which layer integrateDepth feeds. */
+typedef enum { NVB_PROJECTIVE_TSDF = 0, NVB_PROJECTIVE_OCCUPANCY = 1 } NvbProjectiveLayerType;
 
 /* nvblox::Camera (C/include/nvblox/sensors/camera.h:193-203) with its
  * std::optional<RadialTangentialDistortionParams> (C/include/nvblox/sensors/distortion.h:24-62):
@@ -109,7 +112,18 @@ typedef struct {
   float max_esdf_distance_m;   /* 2    */
   float max_site_distance_vox; /* 1    */
   float min_weight;            /* 1e-4 */
+  float occupied_threshold;    /* 0.5: probability above which an occupancy voxel is inside an obstacle
+                                  (EsdfIntegrator::occupied_threshold, esdf_integrator.h:198,219,375) */
 } NvbEsdfParams;
+
+/* ProjectiveOccupancyIntegrator's inverse sensor model
+ * (C/include/nvblox/integrators/occupancy_integrator_params.h:21-40). */
+typedef struct {
+  float free_region_occupancy_probability;       /* 0.3 */
+  float occupied_region_occupancy_probability;   /* 0.7 */
+  float unobserved_region_occupancy_probability; /* 0.5 */
+  float occupied_region_half_width_m;            /* 0.1 */
+} NvbOccupancyParams;
 
 /* TsdfVoxel / EsdfVoxel as stored in HBM (C/include/nvblox/map/voxels.h:28-34,55-74). */
 typedef struct {
@@ -134,6 +148,7 @@ typedef struct {
   int32_t esdf_capacity_blocks;
   int32_t esdf_persistent;       /* 1: whole ESDF wavefront in one cooperative launch (default);
                                     0: one launch per ring with a host-read counter, like the reference */
+  int32_t projective_layer_type; /* NvbProjectiveLayerType: TSDF (default) or occupancy */
 } NvbMapperOptions;
 
 /* = nvblox::Mapper restricted to {TsdfLayer, EsdfLayer, ProjectiveTsdfIntegrator,
@@ -161,6 +176,13 @@ NVB_API int32_t nvb_mapper_get_tsdf_params(const NvbMapper* m, NvbTsdfParams* p)
 /* Mapper::esdf_integrator().<setters> (esdf_integrator.h:178-283). */
 NVB_API int32_t nvb_mapper_set_esdf_params(NvbMapper* m, const NvbEsdfParams* p);
 NVB_API int32_t nvb_mapper_get_esdf_params(const NvbMapper* m, NvbEsdfParams* p);
+/* Mapper::occupancy_integrator().<setters> (C/include/nvblox/integrators/projective_occupancy_integrator.h:57-88).
+ * With an occupancy mapper, nvb_mapper_integrate_depth runs ProjectiveOccupancyIntegrator::integrateFrame
+ * (same raycast + block list, UpdateOccupancyVoxelFunctor, projective_occupancy_integrator_impl.cuh:27-73) and
+ * nvb_mapper_update_esdf runs EsdfIntegrator::integrateBlocks(OccupancyLayer, ...) (esdf_integrator.h:72-80). */
+NVB_API void nvb_default_occupancy_params(NvbOccupancyParams* p);
+NVB_API int32_t nvb_mapper_set_occupancy_params(NvbMapper* m, const NvbOccupancyParams* p);
+NVB_API int32_t nvb_mapper_get_occupancy_params(const NvbMapper* m, NvbOccupancyParams* p);
 NVB_API float nvb_mapper_voxel_size(const NvbMapper* m);
 NVB_API float nvb_mapper_block_size(const NvbMapper* m);
 
@@ -236,7 +258,7 @@ NVB_API int32_t nvb_layer_block_indices(NvbMapper* m, int32_t layer, int32_t* ou
                                         int32_t cap, int32_t* out_count);                    /* getAllBlockIndices */
 /* getBlockAtIndex(...)->voxels copied to host: out_host receives n blocks of
  * block_bytes (4096 TSDF / 10240 ESDF); found[i] = 0 for unallocated indices
- * (their output bytes are zero). */
+ * (their output bytes are zero). block_bytes: 4096 TSDF / 10240 ESDF / 2048 occupancy. */
 NVB_API int32_t nvb_layer_get_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_host,
                                      int32_t n, void* out_host, uint8_t* found_host);
 /* allocateBlockAtIndex + host->device copy of the voxels (tests, map loading). */

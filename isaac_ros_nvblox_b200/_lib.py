@@ -12,12 +12,14 @@ LIB_PATH = os.path.join(_HERE, "libnvblox_b200.so")
 
 NVB_OK = 0
 NVB_MEM_HOST, NVB_MEM_DEVICE = 0, 1
-NVB_LAYER_TSDF, NVB_LAYER_ESDF = 0, 1
+NVB_LAYER_TSDF, NVB_LAYER_ESDF, NVB_LAYER_OCCUPANCY = 0, 1, 2
+NVB_PROJECTIVE_TSDF, NVB_PROJECTIVE_OCCUPANCY = 0, 1
 
 # Every symbol include/nvblox_b200.h declares (checked by tests/test_cabi_symbols.py).
 EXPORTED_SYMBOLS = [
     "nvb_last_error", "nvb_version", "nvb_device_count",
     "nvb_default_mapper_options", "nvb_default_tsdf_params", "nvb_default_esdf_params",
+    "nvb_default_occupancy_params", "nvb_mapper_set_occupancy_params", "nvb_mapper_get_occupancy_params",
     "nvb_mapper_create", "nvb_mapper_destroy", "nvb_mapper_clear",
     "nvb_mapper_set_tsdf_params", "nvb_mapper_get_tsdf_params",
     "nvb_mapper_set_esdf_params", "nvb_mapper_get_esdf_params",
@@ -55,13 +57,21 @@ class NvbTsdfParams(C.Structure):
 class NvbEsdfParams(C.Structure):
     _fields_ = [("max_esdf_distance_m", C.c_float),
                 ("max_site_distance_vox", C.c_float),
-                ("min_weight", C.c_float)]
+                ("min_weight", C.c_float),
+                ("occupied_threshold", C.c_float)]
+
+
+class NvbOccupancyParams(C.Structure):
+    _fields_ = [("free_region_occupancy_probability", C.c_float),
+                ("occupied_region_occupancy_probability", C.c_float),
+                ("unobserved_region_occupancy_probability", C.c_float),
+                ("occupied_region_half_width_m", C.c_float)]
 
 
 class NvbMapperOptions(C.Structure):
     _fields_ = [("voxel_size_m", C.c_float), ("device", C.c_int32),
                 ("tsdf_capacity_blocks", C.c_int32), ("esdf_capacity_blocks", C.c_int32),
-                ("esdf_persistent", C.c_int32)]
+                ("esdf_persistent", C.c_int32), ("projective_layer_type", C.c_int32)]
 
 
 class NvbError(RuntimeError):
@@ -91,6 +101,10 @@ def load():
     L.nvb_default_mapper_options.argtypes = [C.POINTER(NvbMapperOptions)]
     L.nvb_default_tsdf_params.argtypes = [C.POINTER(NvbTsdfParams)]
     L.nvb_default_esdf_params.argtypes = [C.POINTER(NvbEsdfParams)]
+    L.nvb_default_occupancy_params.argtypes = [C.POINTER(NvbOccupancyParams)]
+    L.nvb_default_occupancy_params.restype = None
+    L.nvb_mapper_set_occupancy_params.argtypes = [vp, C.POINTER(NvbOccupancyParams)]
+    L.nvb_mapper_get_occupancy_params.argtypes = [vp, C.POINTER(NvbOccupancyParams)]
     L.nvb_mapper_create.argtypes = [C.POINTER(NvbMapperOptions), C.POINTER(vp)]
     L.nvb_mapper_create.restype = i32
     L.nvb_mapper_destroy.argtypes = [vp]

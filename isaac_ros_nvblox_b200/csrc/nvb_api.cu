@@ -60,6 +60,10 @@ struct NvbMapper {
   float voxel_size = 0.05f, block_size = 0.4f;
   NvbTsdfParams tp;
   NvbEsdfParams ep;
+  NvbOccupancyParams op;
+  // NVB_PROJECTIVE_TSDF or NVB_PROJECTIVE_OCCUPANCY: which voxel type the projective layer (`tsdf` below) holds
+  // (ProjectiveLayerType, mapper/mapper.h:52-53).
+  int projective_layer_type = 0;
   int esdf_persistent = 1;
 
   DevLayer tsdf{}, esdf{};
@@ -254,6 +258,8 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
        kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kNumInts = 32 };
 
+float logOddsFromProbability(float p);
+
 EsdfCtx makeEsdfCtx(NvbMapper* m) {
   EsdfCtx c{};
   c.tsdf = m->tsdf, c.esdf = m->esdf;
@@ -281,7 +287,17 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.max_site_distance_m = m->ep.max_site_distance_vox * m->voxel_size;
   c.min_weight = m->ep.min_weight;
   c.block_size = m->block_size;
+  // OccupancySiteFunctor (esdf_integrator.cu:71-75, 140-170)
+  c.from_occupancy = m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? 1 : 0;
+  c.occupied_threshold_log_odds = logOddsFromProbability(m->ep.occupied_threshold);
   return c;
+}
+
+// logOddsFromProbability (core/log_odds.h:23-30): clamp to [1e-3, 1 - 1e-3], then log(p / (1 - p)). The reference
+// evaluates it on the host too (integrator members and setters), so glibc's logf is the function to match.
+float logOddsFromProbability(float p) {
+  p = fmaxf(1e-3f, fminf(p, 1.0f - 1e-3f));
+  return logf(p / (1.0f - p));
 }
 
 Rigid rigidFromColMajor(const float* T) {
@@ -572,8 +588,21 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
     p.invalid_depth_decay_factor = m->tp.invalid_depth_decay_factor;
     p.weighting_type = m->tp.weighting_type;
     const Rigid T_C_L = invertRigid(T_L_C);
-    launchTsdfIntegrate(m->frame_blocks, m->frame_count, m->tsdf.blocks, depth_dev, mask_dev, mask_mode, rows, cols,
-                        T_C_L, *cam, p, m->num_sms, m->bits, grid.num_words, m->stream);
+    if (m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY) {
+      // ProjectiveOccupancyIntegrator::setFunctorParameters (src/integrators/projective_occupancy_integrator.cu:41-49)
+      OccKernelParams o;
+      o.free_log_odds = logOddsFromProbability(m->op.free_region_occupancy_probability);
+      o.occupied_log_odds = logOddsFromProbability(m->op.occupied_region_occupancy_probability);
+      o.unobserved_log_odds = logOddsFromProbability(m->op.unobserved_region_occupancy_probability);
+      o.occupied_half_width_m = m->op.occupied_region_half_width_m;
+      o.min_log_odds = logOddsFromProbability(0.01f);
+      o.max_log_odds = logOddsFromProbability(0.99f);
+      launchOccupancyIntegrate(m->frame_blocks, m->frame_count, m->tsdf.blocks, depth_dev, mask_dev, mask_mode, rows,
+                               cols, T_C_L, *cam, p, o, m->num_sms, m->bits, grid.num_words, m->stream);
+    } else {
+      launchTsdfIntegrate(m->frame_blocks, m->frame_count, m->tsdf.blocks, depth_dev, mask_dev, mask_mode, rows, cols,
+                          T_C_L, *cam, p, m->num_sms, m->bits, grid.num_words, m->stream);
+    }
     endStage(m);
     m->launches++;
     // asynchronous read-back of the slab fill level for the host-side capacity bound
@@ -690,6 +719,7 @@ void nvb_default_mapper_options(NvbMapperOptions* o) {
   o->tsdf_capacity_blocks = kDefaultCapacity;
   o->esdf_capacity_blocks = kDefaultCapacity;
   o->esdf_persistent = 1;
+  o->projective_layer_type = NVB_PROJECTIVE_TSDF;
 }
 void nvb_default_tsdf_params(NvbTsdfParams* p) {
   if (!p) return;
@@ -707,6 +737,15 @@ void nvb_default_esdf_params(NvbEsdfParams* p) {
   p->max_esdf_distance_m = 2.0f;
   p->max_site_distance_vox = 1.0f;
   p->min_weight = 1e-4f;
+  p->occupied_threshold = 0.5f;
+}
+void nvb_default_occupancy_params(NvbOccupancyParams* p) {
+  if (!p) return;
+  // integrators/occupancy_integrator_params.h:21-40
+  p->free_region_occupancy_probability = 0.3f;
+  p->occupied_region_occupancy_probability = 0.7f;
+  p->unobserved_region_occupancy_probability = 0.5f;
+  p->occupied_region_half_width_m = 0.1f;
 }
 
 int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
@@ -718,6 +757,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
     return fail(NVB_ERR_NO_DEVICE, "no CUDA device: the depth-integration path has no CPU fallback");
   }
   if (opts->device < 0 || opts->device >= ndev) return fail(NVB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+  if (opts->projective_layer_type != NVB_PROJECTIVE_TSDF && opts->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "unknown projective_layer_type");
   NVB_CUDA(cudaSetDevice(opts->device));
   NvbMapper* m = new NvbMapper();
   m->device = opts->device;
@@ -728,6 +769,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   m->block_size = opts->voxel_size_m * (float)kVps;  // voxelSizeToBlockSize (indexing_impl.h:22-24)
   nvb_default_tsdf_params(&m->tp);
   nvb_default_esdf_params(&m->ep);
+  nvb_default_occupancy_params(&m->op);
+  m->projective_layer_type = opts->projective_layer_type;
   m->esdf_persistent = opts->esdf_persistent;
   NVB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   NVB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
@@ -737,7 +780,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   const int tcap = opts->tsdf_capacity_blocks > 0 ? opts->tsdf_capacity_blocks : kDefaultCapacity;
   const int ecap = std::max(opts->esdf_capacity_blocks > 0 ? opts->esdf_capacity_blocks : kDefaultCapacity, tcap);
   int rc;
-  if ((rc = allocLayer(&m->tsdf, tcap, kTsdfBlockBytes, m->stream))) return rc;
+  if ((rc = allocLayer(&m->tsdf, tcap, m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? kOccBlockBytes : kTsdfBlockBytes,
+                       m->stream))) return rc;
   if ((rc = allocLayer(&m->esdf, ecap, kEsdfBlockBytes, m->stream))) return rc;
   if ((rc = allocTsdfSide(m, 0, tcap))) return rc;
   if ((rc = allocEsdfScratch(m, 0, ecap))) return rc;
@@ -850,12 +894,31 @@ int32_t nvb_mapper_set_esdf_params(NvbMapper* m, const NvbEsdfParams* p) {
   // CHECK_GT in the setters (src/integrators/esdf_integrator.cu:55-68)
   if (!(p->max_esdf_distance_m > 0.0f) || !(p->max_site_distance_vox > 0.0f) || !(p->min_weight > 0.0f))
     return fail(NVB_ERR_INVALID_ARGUMENT, "ESDF parameters must be > 0");
+  // occupied_threshold: CHECK_GE(0) / CHECK_LE(1) (esdf_integrator.cu:71-75)
+  if (!(p->occupied_threshold >= 0.0f && p->occupied_threshold <= 1.0f))
+    return fail(NVB_ERR_INVALID_ARGUMENT, "occupied_threshold must be a probability");
   m->ep = *p;
   return NVB_OK;
 }
 int32_t nvb_mapper_get_esdf_params(const NvbMapper* m, NvbEsdfParams* p) {
   if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
   *p = m->ep;
+  return NVB_OK;
+}
+int32_t nvb_mapper_set_occupancy_params(NvbMapper* m, const NvbOccupancyParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  // CHECK(value >= 0 && value <= 1) in the probability setters (src/integrators/projective_occupancy_integrator.cu:71-99);
+  // the half width has no check there
+  const float probs[3] = {p->free_region_occupancy_probability, p->occupied_region_occupancy_probability,
+                          p->unobserved_region_occupancy_probability};
+  for (float q : probs)
+    if (!(q >= 0.0f && q <= 1.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "occupancy probabilities must be in [0, 1]");
+  m->op = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_occupancy_params(const NvbMapper* m, NvbOccupancyParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->op;
   return NVB_OK;
 }
 float nvb_mapper_voxel_size(const NvbMapper* m) { return m ? m->voxel_size : 0.0f; }
@@ -883,6 +946,12 @@ int32_t nvb_mapper_integrate_depth_async(NvbMapper* m, const float* depth, const
   NVB_CUDA(cudaSetDevice(m->device));
   // max_integration_distance_behind_surface_m = truncation_distance_vox * voxel_size
   // (projective_integrator_impl.cuh:234-235)
+  if (m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY &&
+      m->tp.truncation_distance_vox * m->voxel_size < m->op.occupied_region_half_width_m) {
+    // "truncation distance must be >= occupied region half width": the integrator raises it through its own
+    // setter, so the new value persists (src/integrators/projective_occupancy_integrator.cu:51-64)
+    m->tp.truncation_distance_vox = m->op.occupied_region_half_width_m / m->voxel_size;
+  }
   const float trunc_m = m->tp.truncation_distance_vox * m->voxel_size;
   return enqueueFrame(m, depth, mask, mask_mode, memory, rows, cols, T_L_C, cam, m->block_size, trunc_m,
                       m->tp.max_integration_distance_m, true);
@@ -1026,14 +1095,20 @@ int32_t nvb_mapper_join_streams(NvbMapper* m) {
 
 void* nvb_mapper_stream(NvbMapper* m) { return m ? (void*)m->stream : nullptr; }
 
+// The projective layer is a TsdfLayer or an OccupancyLayer, never both (Mapper allocates the one its
+// ProjectiveLayerType names, src/mapper/mapper.cpp:32-52): asking for the other one is an unknown layer.
 static DevLayer* layerOf(NvbMapper* m, int layer) {
-  if (layer == NVB_LAYER_TSDF) return &m->tsdf;
+  if (layer == NVB_LAYER_TSDF) return m->projective_layer_type == NVB_PROJECTIVE_TSDF ? &m->tsdf : nullptr;
+  if (layer == NVB_LAYER_OCCUPANCY) return m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? &m->tsdf : nullptr;
   if (layer == NVB_LAYER_ESDF) return &m->esdf;
   return nullptr;
 }
 
 int32_t nvb_layer_block_bytes(int32_t layer) {
-  return layer == NVB_LAYER_TSDF ? kTsdfBlockBytes : (layer == NVB_LAYER_ESDF ? kEsdfBlockBytes : 0);
+  if (layer == NVB_LAYER_TSDF) return kTsdfBlockBytes;
+  if (layer == NVB_LAYER_ESDF) return kEsdfBlockBytes;
+  if (layer == NVB_LAYER_OCCUPANCY) return kOccBlockBytes;
+  return 0;
 }
 
 int32_t nvb_layer_num_blocks(NvbMapper* m, int32_t layer, int32_t* out_count) {

@@ -188,6 +188,121 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
 }
 
 // ---------------------------------------------------------------------------
+// markAllSitesKernel<OccupancyBlock, OccupancySiteFunctor> (:140-170, :467-540): the projective layer holds
+// log odds; observed <=> |log_odds| > 1e-4, inside <=> log_odds > threshold, every inside voxel is a site.
+// Same staging as esdfMarkKernel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) esdfMarkOccupancyKernel(EsdfCtx c) {
+  __shared__ __align__(16) unsigned int s[kBlockWords];
+  __shared__ int s_flags[3];  // updated, cleared, changed
+  const int tid = threadIdx.x;
+  const int n = *c.work_count;
+  if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    const int4 w = c.work[item];
+    if (w.x >= 0 && w.z && tid < 6) {
+      const int* bi = c.esdf.block_index + 3 * w.x;
+      int x = bi[0], y = bi[1], z = bi[2];
+      const int d = (tid & 1) ? -1 : 1;
+      if ((tid >> 1) == 0) x += d;
+      else if ((tid >> 1) == 1) y += d;
+      else z += d;
+      const int other = hashFind(c.esdf.hash, x, y, z);
+      c.nbr[6 * w.x + tid] = other;
+      if (other >= 0) c.nbr[6 * other + (tid ^ 1)] = w.x;
+    }
+    if (w.x < 0 || w.y < 0) continue;
+    if (tid < 3) s_flags[tid] = 0;
+    uint4* gblk = reinterpret_cast<uint4*>(esdfBlockPtr(c.esdf, w.x));
+    for (int k = tid; k < kBlockWords / 4; k += kThreads) reinterpret_cast<uint4*>(s)[k] = gblk[k];
+    const float* occ = reinterpret_cast<const float*>(c.tsdf.blocks + (size_t)w.y * kOccBlockBytes);
+    const float lo0 = occ[tid], lo1 = occ[tid + kThreads];
+    __syncthreads();
+    bool updated = false, cleared = false, changed = false;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float lo = h ? lo1 : lo0;
+      unsigned int* e = s + (tid + h * kThreads) * kEsdfVoxelWords;
+      float sq = __uint_as_float(e[0]);
+      int p0 = (int)e[1], p1 = (int)e[2], p2 = (int)e[3];
+      const unsigned int fl = e[4];
+      bool e_inside = flagInside(fl), e_observed = flagObserved(fl), e_site = flagSite(fl);
+      const bool is_observed = fabsf(lo - 0.0f) > 1e-4f;
+      if (is_observed) {
+        const bool is_inside = lo > c.occupied_threshold_log_odds;
+        const bool is_site = is_inside;  // isVoxelNearSurface == true
+        if (e_inside && !is_inside) {
+          p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+          cleared = true;
+        }
+        e_inside = is_inside;
+        if (is_site) {
+          if (!e_site) {
+            e_site = true, sq = 0.0f, p0 = p1 = p2 = 0;
+          }
+          updated = true;
+        } else {
+          if (e_site) {
+            p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+            cleared = true;
+          } else if (!e_observed) {
+            p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+          } else if ((double)sq <= 1e-4) {
+            p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+            cleared = true;
+          }
+        }
+        e_observed = true;
+      } else {
+        p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+        cleared = true;
+        e_observed = false;
+      }
+      const unsigned int nfl = (fl & 0xff000000u) | (e_inside ? 1u : 0u) | (e_observed ? 0x100u : 0u) |
+                               (e_site ? 0x10000u : 0u);
+      const unsigned int nsq = __float_as_uint(sq);
+      if (nsq != e[0] || (unsigned)p0 != e[1] || (unsigned)p1 != e[2] || (unsigned)p2 != e[3] || nfl != fl) {
+        e[0] = nsq, e[1] = (unsigned)p0, e[2] = (unsigned)p1, e[3] = (unsigned)p2, e[4] = nfl;
+        changed = true;
+      }
+    }
+    if (updated) s_flags[0] = 1;
+    if (cleared) s_flags[1] = 1;
+    if (changed) s_flags[2] = 1;
+    __syncthreads();
+    if (s_flags[2]) {
+      for (int k = tid; k < kBlockWords / 4; k += kThreads) gblk[k] = reinterpret_cast<uint4*>(s)[k];
+    }
+    if (tid == 0) {
+      if (s_flags[0]) {
+        c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
+        c.seed_upd[w.x] = c.update_seq;
+      }
+      if (s_flags[1]) {
+        c.clr_list[atomicAdd(c.clr_count, 1)] = w.x;
+        const int* bi = c.esdf.block_index + 3 * w.x;
+        atomicMin(c.clr_aabb + 0, bi[0]), atomicMin(c.clr_aabb + 1, bi[1]), atomicMin(c.clr_aabb + 2, bi[2]);
+        atomicMax(c.clr_aabb + 3, bi[0]), atomicMax(c.clr_aabb + 4, bi[1]), atomicMax(c.clr_aabb + 5, bi[2]);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      const int nclr = *(volatile int*)c.clr_count;
+      const int nupd = *(volatile int*)c.upd_count;
+      if (nclr > 0) {
+        *c.cleared_count = 0;
+        *c.cleared_seq = c.update_seq;
+      }
+      c.stats[1] = nupd, c.stats[2] = nclr;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // markAllSites with TMA staging. Same per-voxel state machine as esdfMarkKernel; what
 // changes is how blocks move: one elected thread issues cp.async.bulk copies (SASS UBLKCP)
 // of the 10 KiB ESDF block and the 4 KiB TSDF block into a 3-stage shared-memory ring,
@@ -648,6 +763,13 @@ void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t
     if (use_tma)
       cudaFuncSetAttribute(esdfMarkTmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(kMarkStages * sizeof(MarkStage)));
+  }
+  if (c.from_occupancy) {
+    int grid = num_sms * 8;
+    if (count_upper < grid) grid = count_upper;
+    if (grid < 1) grid = 1;
+    esdfMarkOccupancyKernel<<<grid, kThreads, 0, stream>>>(c);
+    return;
   }
   if (use_tma) {
     int grid = num_sms * 4;  // 4 x 43 KiB of staging per SM; ~3000 items -> ~5 per CTA, 2 loads in flight each

@@ -19,6 +19,7 @@ constexpr int kVpb = kVps * kVps * kVps;
 constexpr int kTsdfBlockBytes = kVpb * 8;   // 4096
 constexpr int kEsdfBlockBytes = kVpb * 20;  // 10240
 constexpr int kEsdfVoxelWords = 5;
+constexpr int kOccBlockBytes = kVpb * 4;    // OccupancyVoxel{float log_odds} (map/voxels.h:92-97)
 
 struct Vec3 {
   float x, y, z;
@@ -249,6 +250,14 @@ struct TsdfKernelParams {
   int weighting_type;
 };
 
+// UpdateOccupancyVoxelFunctor's parameters (projective_occupancy_integrator_impl.cuh:58-72), log odds computed
+// on the host like in the reference.
+struct OccKernelParams {
+  float free_log_odds, occupied_log_odds, unobserved_log_odds;
+  float occupied_half_width_m;
+  float min_log_odds, max_log_odds;
+};
+
 // ---------------------------------------------------------------------------
 // Kernel launchers (implemented in the .cu files; all enqueue on `stream`).
 // ---------------------------------------------------------------------------
@@ -290,6 +299,12 @@ void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsig
                          const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p, int num_sms,
                          unsigned int* bits_to_clear, int num_words, cudaStream_t stream);
 
+void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* occ_blocks,
+                              const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
+                              const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p,
+                              const OccKernelParams& op, int num_sms, unsigned int* bits_to_clear, int num_words,
+                              cudaStream_t stream);
+
 // nvb_esdf.cu
 struct EsdfCtx {
   DevLayer tsdf;
@@ -329,6 +344,8 @@ struct EsdfCtx {
   float max_site_distance_m;
   float min_weight;
   float block_size;
+  int from_occupancy;               // the projective layer (`tsdf` above) holds OccupancyVoxels
+  float occupied_threshold_log_odds;
 };
 void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
                         int in_count_upper, cudaStream_t stream);

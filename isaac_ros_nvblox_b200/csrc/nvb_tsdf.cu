@@ -70,10 +70,11 @@ __device__ __forceinline__ float weighting(int type, float measured, float voxel
   }
 }
 
-// One voxel: project, look the depth up, fuse. Returns true if (dist, weight) changed.
+// Shared front end of integrateBlocksKernel (projective_integrator_impl.cuh:59-114): project the voxel centre,
+// look the depth (and the mask) up. Returns false if the voxel is not updated at all.
 template <bool kDistort>
-__device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, int vx, int vy, int vz, float& dist,
-                                            float& wgt) {
+__device__ __forceinline__ bool sampleVoxel(const TsdfArgs& a, const int4& blk, int vx, int vy, int vz, float& d,
+                                            float& voxel_depth, bool& is_active) {
   // getCenterPositionFromBlockIndexAndVoxelIndex (core/internal/impl/indexing_impl.h:51-81)
   Vec3 p_L;
   p_L.x = (a.p.block_size * (float)blk.x + a.p.voxel_size * (float)vx) + a.p.half_voxel_size;
@@ -88,20 +89,30 @@ __device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, 
   const float u = un * a.cam.fu + a.cam.cu;
   const float v = vn * a.cam.fv + a.cam.cv;
   if (u > (float)a.cam.width || v > (float)a.cam.height || u < 0.0f || v < 0.0f) return false;
-  const float voxel_depth = p_C.z;
+  voxel_depth = p_C.z;
   // projectThreadVoxel max-depth test (projective_integrators_common_impl.cuh:42-45)
   if (a.p.max_integration_distance_m > 0.0f && voxel_depth > a.p.max_integration_distance_m) return false;
   // interpolate2DClosest (interpolation/internal/impl/interpolation_2d_impl.h:125-150)
   const int ux = floatToIntRz(floorf(u)), uy = floatToIntRz(floorf(v));
   if (ux < 0 || uy < 0 || ux >= a.cols || uy >= a.rows) return false;
   const size_t pix = (size_t)uy * a.cols + ux;
-  float d = __ldg(a.depth + pix);
+  d = __ldg(a.depth + pix);
   if (!(isfinite(d) && d > 1e-6f)) d = 0.0f;  // PixelIsValidDepth (interpolation_2d_impl.h:99-104)
-  bool is_active = true;  // MaskedImageView::isMasked (sensors/internal/impl/image_impl.h:250-259)
+  is_active = true;  // MaskedImageView::isMasked (sensors/internal/impl/image_impl.h:250-259)
   if (a.mask != nullptr) {
     const unsigned char mv = __ldg(a.mask + pix);
     is_active = (a.mask_mode == NVB_MASK_NON_INVERTED) ? (mv != 0) : (mv == 0);
   }
+  return true;
+}
+
+// One TSDF voxel: sample, fuse. Returns true if (dist, weight) changed.
+template <bool kDistort>
+__device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, int vx, int vy, int vz, float& dist,
+                                            float& wgt) {
+  float d, voxel_depth;
+  bool is_active;
+  if (!sampleVoxel<kDistort>(a, blk, vx, vy, vz, d, voxel_depth, is_active)) return false;
   // UpdateTsdfVoxelFunctor (projective_tsdf_integrator_impl.cuh:30-90)
   const float trunc = a.p.truncation_distance_m;
   if (d <= 0.0f) {
@@ -124,6 +135,51 @@ __device__ __forceinline__ bool updateVoxel(const TsdfArgs& a, const int4& blk, 
   dist = fused;
   wgt = fminf(w + wgt, a.p.max_weight);
   return true;
+}
+
+// One occupancy voxel: UpdateOccupancyVoxelFunctor (projective_occupancy_integrator_impl.cuh:27-73).
+template <bool kDistort>
+__device__ __forceinline__ bool updateOccupancyVoxel(const TsdfArgs& a, const OccKernelParams& o, const int4& blk, int vx,
+                                                     int vy, int vz, float& log_odds) {
+  float d, voxel_depth;
+  bool is_active;
+  if (!sampleVoxel<kDistort>(a, blk, vx, vy, vz, d, voxel_depth, is_active)) return false;
+  if (d <= 0.0f) return false;
+  float upd;
+  if (!is_active || voxel_depth > d + o.occupied_half_width_m) {
+    upd = o.unobserved_log_odds;
+  } else if (voxel_depth > d - o.occupied_half_width_m) {
+    upd = o.occupied_log_odds;
+  } else {
+    upd = o.free_log_odds;
+  }
+  const float updated = log_odds + upd;
+  log_odds = fmaxf(o.min_log_odds, fminf(updated, o.max_log_odds));
+  return true;
+}
+
+// Occupancy twin of tsdfIntegrateKernel: a block is 2 KiB (512 floats); 128 threads, four z-adjacent voxels
+// (one 128-bit word) per thread, two blocks per 256-thread CTA iteration.
+template <bool kDistort>
+__global__ void __launch_bounds__(256) occupancyIntegrateKernel(const __grid_constant__ TsdfArgs a,
+                                                                const __grid_constant__ OccKernelParams o) {
+  const int n = *a.frame_count;
+  const int tid = threadIdx.x;
+  for (int w = blockIdx.x * blockDim.x + tid; w < a.num_words; w += gridDim.x * blockDim.x) a.bits_to_clear[w] = 0;
+  const int half = tid >> 7, t = tid & 127;
+  // voxels 4t .. 4t+3 : linear offset = x*64 + y*8 + z
+  const int vx = t >> 4, vy = (t >> 1) & 7, vz = (t & 1) * 4;
+  for (int i = blockIdx.x * 2 + half; i < n; i += gridDim.x * 2) {
+    const int4 blk = a.frame_blocks[i];
+    if (blk.w < 0) continue;
+    float4* gp = reinterpret_cast<float4*>(a.tsdf_blocks + (size_t)blk.w * kOccBlockBytes) + t;
+    float4 word = *gp;
+    bool c = updateOccupancyVoxel<kDistort>(a, o, blk, vx, vy, vz, word.x);
+    c |= updateOccupancyVoxel<kDistort>(a, o, blk, vx, vy, vz + 1, word.y);
+    c |= updateOccupancyVoxel<kDistort>(a, o, blk, vx, vy, vz + 2, word.z);
+    c |= updateOccupancyVoxel<kDistort>(a, o, blk, vx, vy, vz + 3, word.w);
+    if (c) *gp = word;
+  }
 }
 
 template <bool kDistort>
@@ -181,6 +237,28 @@ void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsig
   // the lens-distortion variant is a separate instantiation so the pinhole path keeps its register budget
   if (cam.has_distortion) tsdfIntegrateKernel<true><<<num_sms * 8, 256, 0, stream>>>(a);
   else tsdfIntegrateKernel<false><<<num_sms * 8, 256, 0, stream>>>(a);
+}
+
+void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* occ_blocks,
+                              const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
+                              const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p,
+                              const OccKernelParams& op, int num_sms, unsigned int* bits_to_clear, int num_words,
+                              cudaStream_t stream) {
+  TsdfArgs a;
+  a.frame_blocks = frame_blocks;
+  a.frame_count = frame_count;
+  a.tsdf_blocks = occ_blocks;
+  a.depth = depth;
+  a.mask = mask;
+  a.mask_mode = mask_mode;
+  a.rows = rows, a.cols = cols;
+  a.T_C_L = T_C_L;
+  a.cam = cam;
+  a.p = p;
+  a.bits_to_clear = bits_to_clear;
+  a.num_words = num_words;
+  if (cam.has_distortion) occupancyIntegrateKernel<true><<<num_sms * 8, 256, 0, stream>>>(a, op);
+  else occupancyIntegrateKernel<false><<<num_sms * 8, 256, 0, stream>>>(a, op);
 }
 
 }  // namespace nvb

@@ -7,6 +7,8 @@ path (nvblox/include/nvblox/mapper/mapper.h:107-836):
     Mapper.update_esdf()                       mapper.h:326      (updateEsdf)
     Mapper.tsdf_layer() / esdf_layer()         mapper.h:372,393
     Mapper.tsdf_integrator() / esdf_integrator()  parameter setters
+    Mapper(voxel_size_m, projective_layer_type=ProjectiveLayerType.kOccupancy)  mapper.h:52-53,119-124
+    Mapper.occupancy_layer() / occupancy_integrator()  mapper.h:374,456
     ViewCalculator.get_blocks_in_image_view_raycast  view_calculator.h:75-80
 Everything forwards to the C-ABI in libnvblox_b200.so through ctypes; numpy arrays
 are host buffers, integers are raw device pointers.
@@ -16,12 +18,21 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import NvbCamera, NvbEsdfParams, NvbMapperOptions, NvbTsdfParams, check
+from ._lib import NvbCamera, NvbEsdfParams, NvbMapperOptions, NvbOccupancyParams, NvbTsdfParams, check
 
 TSDF_VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4")])
 ESDF_VOXEL_DTYPE = np.dtype(
     [("squared_distance_vox", "<f4"), ("parent_direction", "<i4", (3,)),
      ("is_inside", "u1"), ("observed", "u1"), ("is_site", "u1"), ("pad", "u1")])
+
+OCCUPANCY_VOXEL_DTYPE = np.dtype([("log_odds", "<f4")])  # map/voxels.h:51-53
+
+
+class ProjectiveLayerType:
+    """mapper/mapper.h:52-53."""
+    kTsdf = _lib.NVB_PROJECTIVE_TSDF
+    kOccupancy = _lib.NVB_PROJECTIVE_OCCUPANCY
+
 
 STAGE_NAMES = ("view_calculator/raycast", "tsdf/integrate/allocate_blocks", "tsdf/integrate/update_blocks",
                "esdf/integrate/mark_sites", "esdf/integrate/clear", "esdf/integrate/compute")
@@ -170,6 +181,40 @@ class _TsdfIntegrator:
         return self._get().raycast_subsampling
 
 
+class _OccupancyIntegrator(_TsdfIntegrator):
+    """ProjectiveOccupancyIntegrator parameter surface (projective_occupancy_integrator.h:57-109) on top of
+    the shared ProjectiveIntegrator / ViewCalculator one."""
+
+    def _get_occ(self):
+        p = NvbOccupancyParams()
+        check(self._m._L.nvb_mapper_get_occupancy_params(self._m._h, C.byref(p)))
+        return p
+
+    def occupancy_params(self, **kw):
+        p = self._get_occ()
+        for k, v in kw.items():
+            setattr(p, k, float(v))
+        if kw:
+            check(self._m._L.nvb_mapper_set_occupancy_params(self._m._h, C.byref(p)))
+        return p
+
+    def free_region_occupancy_probability(self, v=None):
+        return self.occupancy_params(**({} if v is None else {"free_region_occupancy_probability": v})) \
+            .free_region_occupancy_probability
+
+    def occupied_region_occupancy_probability(self, v=None):
+        return self.occupancy_params(**({} if v is None else {"occupied_region_occupancy_probability": v})) \
+            .occupied_region_occupancy_probability
+
+    def unobserved_region_occupancy_probability(self, v=None):
+        return self.occupancy_params(**({} if v is None else {"unobserved_region_occupancy_probability": v})) \
+            .unobserved_region_occupancy_probability
+
+    def occupied_region_half_width_m(self, v=None):
+        return self.occupancy_params(**({} if v is None else {"occupied_region_half_width_m": v})) \
+            .occupied_region_half_width_m
+
+
 class _EsdfIntegrator:
     """EsdfIntegrator parameter surface (esdf_integrator.h:178-283) + integrateBlocks."""
 
@@ -198,8 +243,11 @@ class _EsdfIntegrator:
     def min_weight(self, v=None):
         return self.params(**({} if v is None else {"min_weight": float(v)})).min_weight
 
+    def occupied_threshold(self, v=None):
+        return self.params(**({} if v is None else {"occupied_threshold": float(v)})).occupied_threshold
+
     def integrate_blocks(self, block_indices):
-        """EsdfIntegrator::integrateBlocks(tsdf_layer, block_indices, esdf_layer)."""
+        """EsdfIntegrator::integrateBlocks(tsdf_layer | occupancy_layer, block_indices, esdf_layer)."""
         idx = np.ascontiguousarray(block_indices, dtype=np.int32).reshape(-1, 3)
         check(self._m._L.nvb_esdf_integrate_blocks(self._m._h, _ip(idx), idx.shape[0]))
 
@@ -211,7 +259,7 @@ class _EsdfIntegrator:
 
 
 class Mapper:
-    """nvblox::Mapper(voxel_size_m, ...) with a TSDF and an ESDF layer."""
+    """nvblox::Mapper(voxel_size_m, projective_layer_type) with a projective (TSDF or occupancy) and an ESDF layer."""
 
     def esdf_time_split(self):
         out = (C.c_int64 * 4)()
@@ -219,7 +267,7 @@ class Mapper:
         return {"barrier_wait_ns_cta0": out[0], "axis_ns_cta0": out[1], "slowest_cta_work_ns": out[2], "barriers": out[3]}
 
     def __init__(self, voxel_size_m, device=0, tsdf_capacity_blocks=0, esdf_capacity_blocks=0,
-                 esdf_persistent=True):
+                 esdf_persistent=True, projective_layer_type=ProjectiveLayerType.kTsdf):
         self._L = _lib.load()
         o = NvbMapperOptions()
         self._L.nvb_default_mapper_options(C.byref(o))
@@ -230,10 +278,13 @@ class Mapper:
         if esdf_capacity_blocks:
             o.esdf_capacity_blocks = int(esdf_capacity_blocks)
         o.esdf_persistent = 1 if esdf_persistent else 0
+        o.projective_layer_type = int(projective_layer_type)
+        self._projective_layer_type = int(projective_layer_type)
         h = C.c_void_p(0)
         check(self._L.nvb_mapper_create(C.byref(o), C.byref(h)))
         self._h = h
         self._tsdf = _Layer(self, _lib.NVB_LAYER_TSDF, TSDF_VOXEL_DTYPE)
+        self._occupancy = _Layer(self, _lib.NVB_LAYER_OCCUPANCY, OCCUPANCY_VOXEL_DTYPE)
         self._esdf = _Layer(self, _lib.NVB_LAYER_ESDF, ESDF_VOXEL_DTYPE)
         self._keep = []  # host buffers of in-flight async frames
 
@@ -258,11 +309,20 @@ class Mapper:
     def tsdf_layer(self):
         return self._tsdf
 
+    def occupancy_layer(self):
+        return self._occupancy
+
     def esdf_layer(self):
         return self._esdf
 
+    def projective_layer_type(self):
+        return self._projective_layer_type
+
     def tsdf_integrator(self):
         return _TsdfIntegrator(self)
+
+    def occupancy_integrator(self):
+        return _OccupancyIntegrator(self)
 
     def esdf_integrator(self):
         return _EsdfIntegrator(self)

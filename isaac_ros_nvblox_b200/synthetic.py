@@ -67,6 +67,23 @@ class Scene:
                 best = np.minimum(best, t)
         return np.where(best <= max_dist, best, np.inf)
 
+    def distance(self, points):
+        """Distance of points (...,3) to the nearest primitive: unsigned for planes, signed (negative inside)
+        for spheres and boxes (Scene::getSignedDistanceToPoint, primitives/scene.h, restricted to the room's
+        interior where the reference's inward-facing plane normals give the same value)."""
+        p = np.asarray(points, dtype=np.float64)
+        best = np.full(p.shape[:-1], np.inf)
+        for axis, off in self.planes:
+            best = np.minimum(best, np.abs(p[..., axis] - off))
+        for c, r in self.spheres:
+            best = np.minimum(best, np.linalg.norm(p - c, axis=-1) - r)
+        for bmin, bmax in self.boxes:
+            q = np.maximum(bmin - p, p - bmax)
+            outside = np.linalg.norm(np.maximum(q, 0.0), axis=-1)
+            inside = np.minimum(np.max(q, axis=-1), 0.0)
+            best = np.minimum(best, outside + inside)
+        return best
+
 
 def sphere_in_box():
     """getSphereInBox: ground z=0, ceiling z=5, walls at +-5, sphere r=2 at (0,0,2)."""

@@ -447,7 +447,7 @@ static void list_sort_unique(List* l) {
 
 struct OrMap {
   float voxel_size, block_size;
-  Layer tsdf, esdf;
+  Layer tsdf, esdf, occ;
   /* EsdfIntegrator::cleared_block_indices_device_ (integrators/esdf_integrator.h:389)
    * is a member that is only overwritten when a call has blocks to clear
    * (esdf_integrator.cu:242-257), so its content carries over between calls. */
@@ -471,6 +471,14 @@ void or_default_esdf_params(OrEsdfParams* p) {
   p->max_esdf_distance_m = 2.0f;
   p->max_site_distance_vox = 1.0f;
   p->min_weight = 1e-4f;
+  p->occupied_threshold = 0.5f; /* esdf_integrator.h:375 */
+}
+void or_default_occupancy_params(OrOccupancyParams* p) {
+  /* integrators/occupancy_integrator_params.h:21-40 */
+  p->free_region_occupancy_probability = 0.3f;
+  p->occupied_region_occupancy_probability = 0.7f;
+  p->unobserved_region_occupancy_probability = 0.5f;
+  p->occupied_region_half_width_m = 0.1f;
 }
 
 OrMap* or_map_create(float voxel_size_m) {
@@ -479,16 +487,17 @@ OrMap* or_map_create(float voxel_size_m) {
   m->block_size = voxel_size_m * (float)VPS; /* voxelSizeToBlockSize, indexing_impl.h:22 */
   layer_init(&m->tsdf, sizeof(OrTsdfVoxel) * VPB);
   layer_init(&m->esdf, sizeof(OrEsdfVoxel) * VPB);
+  layer_init(&m->occ, sizeof(float) * VPB); /* OccupancyVoxel{float log_odds} (map/voxels.h:92-97) */
   return m;
 }
 void or_map_destroy(OrMap* m) {
   if (!m) return;
-  layer_free(&m->tsdf), layer_free(&m->esdf);
+  layer_free(&m->tsdf), layer_free(&m->esdf), layer_free(&m->occ);
   list_free(&m->esdf_cleared_persistent);
   free(m);
 }
 void or_map_clear(OrMap* m) {
-  layer_clear(&m->tsdf), layer_clear(&m->esdf);
+  layer_clear(&m->tsdf), layer_clear(&m->esdf), layer_clear(&m->occ);
   m->esdf_cleared_persistent.n = 0;
 }
 
@@ -663,10 +672,38 @@ static void tsdf_update_voxel(float surface_depth, float voxel_depth, int is_act
  * projective_integrator_impl.cuh:59-114, projective_integrators_common_impl.cuh:21-55,
  * interpolation/internal/impl/interpolation_2d_impl.h:99-150,
  * sensors/internal/impl/image_impl.h:250-259). */
-static void tsdf_integrate_block(OrTsdfVoxel* blk, i3 bi, const float* depth,
+typedef struct {
+  float free_lo, occ_lo, unobs_lo, half_width, min_lo, max_lo;
+} OccFunctor;
+
+/* logOddsFromProbability (core/log_odds.h:23-30); evaluated on the host in the reference as well. */
+static float log_odds_from_probability(float p) {
+  p = fmaxf(1e-3f, fminf(p, 1.0f - 1e-3f));
+  return logf(p / (1.0f - p));
+}
+
+/* UpdateOccupancyVoxelFunctor::operator() (integrators/internal/cuda/impl/projective_occupancy_integrator_impl.cuh:27-73). */
+static void occupancy_update_voxel(float surface_depth, float voxel_depth, int is_active, const OccFunctor* f,
+                                   float* log_odds) {
+  if (surface_depth <= 0.0f) return;
+  float upd;
+  if (!is_active || voxel_depth > surface_depth + f->half_width) {
+    upd = f->unobs_lo;
+  } else if (voxel_depth > surface_depth - f->half_width) {
+    upd = f->occ_lo;
+  } else {
+    upd = f->free_lo;
+  }
+  const float updated = *log_odds + upd;
+  *log_odds = fmaxf(f->min_lo, fminf(updated, f->max_lo));
+}
+
+/* `blk` is OrTsdfVoxel[512] when occ == NULL, float[512] otherwise. */
+static void projective_integrate_block(void* blk_any, const OccFunctor* occ, i3 bi, const float* depth,
                                  const uint8_t* mask, int mask_mode, int rows, int cols,
                                  const float* T_C_L, const OrCamera* cam, float block_size,
                                  float trunc, const OrTsdfParams* P) {
+  OrTsdfVoxel* blk = (OrTsdfVoxel*)blk_any;
   const float voxel_size = block_size * (1.0f / VPS);      /* indexing_impl.h:26-29 */
   const float half_voxel = block_size * (0.5f / VPS);      /* indexing_impl.h:75-77 */
   const float max_depth = P->max_integration_distance_m;
@@ -695,28 +732,38 @@ static void tsdf_integrate_block(OrTsdfVoxel* blk, i3 bi, const float* depth,
           const uint8_t mv = mask[(size_t)uy * cols + ux];
           is_active = (mask_mode == OR_MASK_NON_INVERTED) ? (mv != 0) : (mv == 0);
         }
-        tsdf_update_voxel(d, voxel_depth, is_active, trunc, P->max_weight,
-                          P->invalid_depth_decay_factor, P->weighting_type,
-                          &blk[(vx * VPS + vy) * VPS + vz]);
+        if (occ == NULL) {
+          tsdf_update_voxel(d, voxel_depth, is_active, trunc, P->max_weight,
+                            P->invalid_depth_decay_factor, P->weighting_type,
+                            &blk[(vx * VPS + vy) * VPS + vz]);
+        } else {
+          occupancy_update_voxel(d, voxel_depth, is_active, occ, &((float*)blk_any)[(vx * VPS + vy) * VPS + vz]);
+        }
       }
 }
 
-static void tsdf_integrate_list(OrMap* map, const List* blocks, const float* depth,
+static void projective_integrate_list(OrMap* map, Layer* layer, const OccFunctor* occ, const List* blocks,
+                                const float* depth,
                                 const uint8_t* mask, int mask_mode, int rows, int cols,
                                 const float* T_L_C, const OrCamera* cam,
                                 const OrTsdfParams* P) {
   const float trunc = P->truncation_distance_vox * map->voxel_size;
   /* allocateBlocksWhereRequired (integrators/internal/impl/integrators_common_impl.h:52-58) */
   int32_t* slots = (int32_t*)malloc(sizeof(int32_t) * (size_t)(blocks->n + 1));
-  for (int32_t i = 0; i < blocks->n; i++) slots[i] = layer_allocate(&map->tsdf, blocks->v[i]);
+  for (int32_t i = 0; i < blocks->n; i++) slots[i] = layer_allocate(layer, blocks->v[i]);
   float T_C_L[16];
   invert_isometry(T_L_C, T_C_L); /* projective_integrator_impl.cuh:268 */
 #pragma omp parallel for schedule(static)
   for (int32_t i = 0; i < blocks->n; i++) {
-    tsdf_integrate_block((OrTsdfVoxel*)layer_block(&map->tsdf, slots[i]), blocks->v[i], depth,
+    projective_integrate_block(layer_block(layer, slots[i]), occ, blocks->v[i], depth,
                          mask, mask_mode, rows, cols, T_C_L, cam, map->block_size, trunc, P);
   }
   free(slots);
+}
+static void tsdf_integrate_list(OrMap* map, const List* blocks, const float* depth, const uint8_t* mask,
+                                int mask_mode, int rows, int cols, const float* T_L_C, const OrCamera* cam,
+                                const OrTsdfParams* P) {
+  projective_integrate_list(map, &map->tsdf, NULL, blocks, depth, mask, mask_mode, rows, cols, T_L_C, cam, P);
 }
 
 /* ProjectiveIntegrator::integrateFrameTemplate (projective_integrator_impl.cuh:211-275). */
@@ -731,6 +778,32 @@ int32_t or_tsdf_integrate(OrMap* map, const float* depth, const uint8_t* mask,
     return 0;
   }
   tsdf_integrate_list(map, &blocks, depth, mask, mask_mode, rows, cols, T_L_C, cam, P);
+  int32_t n = copy_out(&blocks, out_xyz, cap);
+  list_free(&blocks);
+  return n;
+}
+
+/* ProjectiveOccupancyIntegrator::integrateFrame (projective_occupancy_integrator_impl.cuh:75-86) +
+ * setFunctorParameters (src/integrators/projective_occupancy_integrator.cu:42-65). */
+int32_t or_occupancy_integrate(OrMap* map, const float* depth, const uint8_t* mask, int32_t mask_mode,
+                               int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam,
+                               OrTsdfParams* P, const OrOccupancyParams* O, int32_t* out_xyz, int32_t cap) {
+  OccFunctor f;
+  f.free_lo = log_odds_from_probability(O->free_region_occupancy_probability);
+  f.occ_lo = log_odds_from_probability(O->occupied_region_occupancy_probability);
+  f.unobs_lo = log_odds_from_probability(O->unobserved_region_occupancy_probability);
+  f.half_width = O->occupied_region_half_width_m;
+  f.max_lo = log_odds_from_probability(0.99f);
+  f.min_lo = log_odds_from_probability(0.01f);
+  if (P->truncation_distance_vox * map->voxel_size < f.half_width)
+    P->truncation_distance_vox = f.half_width / map->voxel_size; /* persists, like the setter call */
+  const float trunc = P->truncation_distance_vox * map->voxel_size;
+  List blocks = view_raycast(depth, rows, cols, T_L_C, cam, map->block_size, trunc, P);
+  if (blocks.n == 0) {
+    list_free(&blocks);
+    return 0;
+  }
+  projective_integrate_list(map, &map->occ, &f, &blocks, depth, mask, mask_mode, rows, cols, T_L_C, cam, P);
   int32_t n = copy_out(&blocks, out_xyz, cap);
   list_free(&blocks);
   return n;
@@ -763,13 +836,30 @@ static void esdf_clear_voxel(OrEsdfVoxel* v, float max_sq) { /* :152-157 */
 }
 
 /* updateEsdfVoxelToChanges with TsdfSiteFunctor (:113-138, :401-458). */
+static void esdf_apply_observation(int is_observed, int is_inside, int near_surface, float max_sq,
+                                   OrEsdfVoxel* e, int* cleared, int* updated);
+
 static void esdf_update_voxel_to_changes(const OrTsdfVoxel* t, float min_weight,
                                          float max_site_distance_m, float max_sq,
                                          OrEsdfVoxel* e, int* cleared, int* updated) {
-  const int is_observed = t->weight >= min_weight;
+  /* TsdfSiteFunctor (:113-138) */
+  esdf_apply_observation(t->weight >= min_weight, t->distance <= 0.0f, fabsf(t->distance) <= max_site_distance_m,
+                         max_sq, e, cleared, updated);
+}
+
+/* OccupancySiteFunctor (:140-170): observed <=> |log_odds - 0| > 1e-4; inside <=> log_odds > threshold;
+ * every inside voxel is near the surface. */
+static void esdf_update_voxel_to_changes_occ(float log_odds, float threshold_log_odds, float max_sq, OrEsdfVoxel* e,
+                                             int* cleared, int* updated) {
+  esdf_apply_observation(fabsf(log_odds - 0.0f) > 1e-4f, log_odds > threshold_log_odds, 1, max_sq, e, cleared, updated);
+}
+
+/* updateEsdfVoxelToChanges (:401-458), no freespace layer. */
+static void esdf_apply_observation(int is_observed, int is_inside_in, int near_surface, float max_sq,
+                                   OrEsdfVoxel* e, int* cleared, int* updated) {
   if (is_observed) {
-    const int is_inside = t->distance <= 0.0f; /* no freespace layer */
-    const int is_site = is_inside && (fabsf(t->distance) <= max_site_distance_m);
+    const int is_inside = is_inside_in;
+    const int is_site = is_inside && near_surface;
     if (e->is_inside && !is_inside) {
       esdf_clear_voxel(e, max_sq);
       *cleared = 1;
@@ -1053,8 +1143,16 @@ static void esdf_clear_all_invalid(OrMap* map, const List* to_clear, float max_e
 
 /* EsdfIntegrator::integrateBlocksTemplate<TsdfLayer> (:220-260) with
  * markAllSites (:678-747) / markAllSitesKernel (:467-540). */
-void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,
-                       const OrEsdfParams* P) {
+static void esdf_integrate_from(OrMap* map, int from_occupancy, const int32_t* blocks_xyz, int32_t num_blocks,
+                                const OrEsdfParams* P);
+void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, const OrEsdfParams* P) {
+  esdf_integrate_from(map, 0, blocks_xyz, num_blocks, P);
+}
+void or_esdf_integrate_occupancy(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, const OrEsdfParams* P) {
+  esdf_integrate_from(map, 1, blocks_xyz, num_blocks, P);
+}
+static void esdf_integrate_from(OrMap* map, int from_occupancy, const int32_t* blocks_xyz, int32_t num_blocks,
+                                const OrEsdfParams* P) {
   memset(map->stats, 0, sizeof(map->stats));
   if (num_blocks == 0) return;
   /* allocateBlocksOnCPU (:391-397) */
@@ -1072,20 +1170,28 @@ void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks
   const float max_esdf_distance_vox = P->max_esdf_distance_m / map->voxel_size;
   const float max_sq = max_esdf_distance_vox * max_esdf_distance_vox;
   const float max_site_distance_m = P->max_site_distance_vox * map->voxel_size; /* :672-676 */
+  const float occupied_threshold_log_odds = log_odds_from_probability(P->occupied_threshold); /* :71-75 */
 
   uint8_t* upd = (uint8_t*)calloc((size_t)num_blocks, 1);
   uint8_t* clr = (uint8_t*)calloc((size_t)num_blocks, 1);
 #pragma omp parallel for schedule(static)
   for (int32_t i = 0; i < num_blocks; i++) {
-    const int32_t ts = hash_find(&map->tsdf.hash, blocks.v[i]);
+    const Layer* src = from_occupancy ? &map->occ : &map->tsdf;
+    const int32_t ts = hash_find(&src->hash, blocks.v[i]);
     const int32_t es = hash_find(&map->esdf.hash, blocks.v[i]);
     if (ts < 0 || es < 0) continue;
-    const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(&map->tsdf, ts);
     OrEsdfVoxel* e = (OrEsdfVoxel*)layer_block(&map->esdf, es);
     int cleared = 0, updated = 0;
-    for (int v = 0; v < VPB; v++)
-      esdf_update_voxel_to_changes(&t[v], P->min_weight, max_site_distance_m, max_sq, &e[v],
-                                   &cleared, &updated);
+    if (from_occupancy) {
+      const float* lo = (const float*)layer_block(src, ts);
+      for (int v = 0; v < VPB; v++)
+        esdf_update_voxel_to_changes_occ(lo[v], occupied_threshold_log_odds, max_sq, &e[v], &cleared, &updated);
+    } else {
+      const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(src, ts);
+      for (int v = 0; v < VPB; v++)
+        esdf_update_voxel_to_changes(&t[v], P->min_weight, max_site_distance_m, max_sq, &e[v],
+                                     &cleared, &updated);
+    }
     upd[i] = (uint8_t)updated, clr[i] = (uint8_t)cleared;
   }
   List updated = {0}, to_clear = {0};
@@ -1121,6 +1227,15 @@ static int32_t layer_indices(const Layer* l, int32_t* out, int32_t cap) {
 }
 int32_t or_tsdf_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->tsdf, out, cap); }
 int32_t or_esdf_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->esdf, out, cap); }
+int32_t or_occupancy_num_blocks(const OrMap* m) { return m->occ.n; }
+int32_t or_occupancy_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->occ, out, cap); }
+int32_t or_occupancy_get_block(const OrMap* m, const int32_t xyz[3], float* out) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = hash_find(&m->occ.hash, k);
+  if (s < 0) return 0;
+  memcpy(out, layer_block(&m->occ, s), m->occ.block_bytes);
+  return 1;
+}
 int32_t or_tsdf_get_block(const OrMap* m, const int32_t xyz[3], OrTsdfVoxel* out) {
   i3 k = {xyz[0], xyz[1], xyz[2]};
   int32_t s = hash_find(&m->tsdf.hash, k);
@@ -1139,6 +1254,12 @@ void or_tsdf_set_block(OrMap* m, const int32_t xyz[3], const OrTsdfVoxel* in) {
   i3 k = {xyz[0], xyz[1], xyz[2]};
   int32_t s = layer_allocate(&m->tsdf, k);
   memcpy(layer_block(&m->tsdf, s), in, m->tsdf.block_bytes);
+}
+
+void or_occupancy_set_block(OrMap* m, const int32_t xyz[3], const float* in) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = layer_allocate(&m->occ, k);
+  memcpy(layer_block(&m->occ, s), in, m->occ.block_bytes);
 }
 
 int32_t or_camera_project(const OrCamera* cam, const float p_C[3], float uv[2]) {

@@ -73,7 +73,16 @@ typedef struct {
   float max_esdf_distance_m;   /* default 2    */
   float max_site_distance_vox; /* default 1    */
   float min_weight;            /* default 1e-4 */
+  float occupied_threshold;    /* default 0.5 (probability; OccupancyLayer input only) */
 } OrEsdfParams;
+
+/* ProjectiveOccupancyIntegrator's sensor model (integrators/occupancy_integrator_params.h:21-40). */
+typedef struct {
+  float free_region_occupancy_probability;       /* 0.3 */
+  float occupied_region_occupancy_probability;   /* 0.7 */
+  float unobserved_region_occupancy_probability; /* 0.5 */
+  float occupied_region_half_width_m;            /* 0.1 */
+} OrOccupancyParams;
 
 /* Voxel layouts = the reference's (include/nvblox/map/voxels.h:28-74). */
 typedef struct {
@@ -123,6 +132,24 @@ void or_tsdf_integrate_blocks(OrMap* map, const float* depth, const uint8_t* mas
                               const float* T_L_C, const OrCamera* cam,
                               const OrTsdfParams* params, const int32_t* blocks_xyz,
                               int32_t num_blocks);
+
+/* ProjectiveOccupancyIntegrator::integrateFrame (integrators/projective_occupancy_integrator.h:51-55). `params`
+ * carries the shared ProjectiveIntegrator settings (truncation, max distance, raycast, workspace); its
+ * truncation_distance_vox is raised in place when smaller than the occupied half width
+ * (src/integrators/projective_occupancy_integrator.cu:42-65). */
+void or_default_occupancy_params(OrOccupancyParams* p);
+int32_t or_occupancy_integrate(OrMap* map, const float* depth, const uint8_t* mask, int32_t mask_mode,
+                               int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam,
+                               OrTsdfParams* params, const OrOccupancyParams* occ, int32_t* out_xyz, int32_t cap);
+/* EsdfIntegrator::integrateBlocks(OccupancyLayer, blocks, EsdfLayer*) (integrators/esdf_integrator.h:72-80). */
+void or_esdf_integrate_occupancy(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,
+                                 const OrEsdfParams* params);
+int32_t or_occupancy_num_blocks(const OrMap* map);
+int32_t or_occupancy_block_indices(const OrMap* map, int32_t* out_xyz, int32_t cap);
+int32_t or_occupancy_get_block(const OrMap* map, const int32_t xyz[3], float* out_log_odds);
+
+/* Test helper: overwrite / create an occupancy block (512 log-odds, [x][y][z] order). */
+void or_occupancy_set_block(OrMap* map, const int32_t xyz[3], const float* in_log_odds);
 
 /* EsdfIntegrator::integrateBlocks(TsdfLayer, blocks, EsdfLayer*). */
 void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,

@@ -61,7 +61,15 @@ class TsdfParams(C.Structure):
 class EsdfParams(C.Structure):
     _fields_ = [("max_esdf_distance_m", C.c_float),
                 ("max_site_distance_vox", C.c_float),
-                ("min_weight", C.c_float)]
+                ("min_weight", C.c_float),
+                ("occupied_threshold", C.c_float)]
+
+
+class OccupancyParams(C.Structure):
+    _fields_ = [("free_region_occupancy_probability", C.c_float),
+                ("occupied_region_occupancy_probability", C.c_float),
+                ("unobserved_region_occupancy_probability", C.c_float),
+                ("occupied_region_half_width_m", C.c_float)]
 
 
 def build(force=False):
@@ -103,6 +111,17 @@ def lib():
                                            C.POINTER(Camera), C.POINTER(TsdfParams), ip, C.c_int32]
     L.or_esdf_integrate.argtypes = [vp, ip, C.c_int32, C.POINTER(EsdfParams)]
     L.or_esdf_last_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.or_default_occupancy_params.argtypes = [C.POINTER(OccupancyParams)]
+    L.or_occupancy_integrate.argtypes = [vp, fp, u8p, C.c_int32, C.c_int32, C.c_int32, fp, C.POINTER(Camera),
+                                         C.POINTER(TsdfParams), C.POINTER(OccupancyParams), ip, C.c_int32]
+    L.or_occupancy_integrate.restype = C.c_int32
+    L.or_esdf_integrate_occupancy.argtypes = [vp, ip, C.c_int32, C.POINTER(EsdfParams)]
+    L.or_occupancy_num_blocks.argtypes = [vp]
+    L.or_occupancy_num_blocks.restype = C.c_int32
+    L.or_occupancy_block_indices.argtypes = [vp, ip, C.c_int32]
+    L.or_occupancy_block_indices.restype = C.c_int32
+    L.or_occupancy_get_block.argtypes = [vp, ip, vp]
+    L.or_occupancy_get_block.restype = C.c_int32
     for name in ("or_tsdf_num_blocks", "or_esdf_num_blocks"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = C.c_int32
@@ -114,6 +133,8 @@ def lib():
     L.or_esdf_get_block.argtypes = [vp, ip, vp]
     L.or_esdf_get_block.restype = C.c_int32
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
+    L.or_occupancy_set_block.argtypes = [vp, ip, vp]
+    L.or_occupancy_set_block.restype = None
     L.or_camera_project.argtypes = [C.POINTER(Camera), fp, fp]
     L.or_camera_project.restype = C.c_int32
     L.or_camera_vector_from_image_plane.argtypes = [C.POINTER(Camera), C.c_float, C.c_float, fp]
@@ -150,6 +171,14 @@ def default_tsdf_params(**kw):
 def default_esdf_params(**kw):
     p = EsdfParams()
     lib().or_default_esdf_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_occupancy_params(**kw):
+    p = OccupancyParams()
+    lib().or_default_occupancy_params(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -216,6 +245,48 @@ class OracleMap:
         lib().or_tsdf_integrate_blocks(self._h, _fp(depth), mp, mask_mode, depth.shape[0],
                                        depth.shape[1], _fp(T), C.byref(cam), C.byref(params),
                                        _ip(blocks), blocks.shape[0])
+
+    def integrate_occupancy(self, depth, T_L_C, cam, params=None, occ_params=None, mask=None, mask_mode=0, cap=1 << 20):
+        """ProjectiveOccupancyIntegrator::integrateFrame; `params` (TsdfParams) is updated in place when the
+        truncation distance is raised to the occupied half width."""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        params = params or default_tsdf_params()
+        occ_params = occ_params or default_occupancy_params()
+        T = colmajor(T_L_C)
+        out = np.zeros((cap, 3), dtype=np.int32)
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            mp = mask.ctypes.data_as(C.POINTER(C.c_uint8))
+        n = lib().or_occupancy_integrate(self._h, _fp(depth), mp, mask_mode, depth.shape[0], depth.shape[1], _fp(T),
+                                         C.byref(cam), C.byref(params), C.byref(occ_params), _ip(out), cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def integrate_esdf_occupancy(self, blocks, params=None):
+        params = params or default_esdf_params()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        lib().or_esdf_integrate_occupancy(self._h, _ip(blocks), blocks.shape[0], C.byref(params))
+
+    def occupancy_block_indices(self):
+        n = lib().or_occupancy_num_blocks(self._h)
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        lib().or_occupancy_block_indices(self._h, _ip(out), n)
+        return out[:n].copy()
+
+    def occupancy_layer(self):
+        """{(x,y,z): (8,8,8) float32 log-odds} for every allocated occupancy block."""
+        out = {}
+        for k in self.occupancy_block_indices():
+            blk = np.zeros((8, 8, 8), dtype=np.float32)
+            lib().or_occupancy_get_block(self._h, _ip(np.ascontiguousarray(k, dtype=np.int32)), blk.ctypes.data)
+            out[tuple(int(c) for c in k)] = blk
+        return out
+
+    def set_occupancy_block(self, idx, log_odds):
+        k = np.asarray(idx, dtype=np.int32)
+        v = np.ascontiguousarray(log_odds, dtype=np.float32).reshape(8, 8, 8)
+        lib().or_occupancy_set_block(self._h, _ip(k), v.ctypes.data)
 
     def integrate_esdf(self, blocks, params=None):
         params = params or default_esdf_params()

@@ -381,3 +381,195 @@ def test_distorted_camera_integrates_a_plane():
         assert np.allclose(blk["distance"][sel], expect[sel], atol=1e-5)
         n += int(sel.sum())
     assert n > 10000
+
+
+# --- occupancy: test_occupancy_integrator.cpp, test_esdf_integrator.cpp:554-582 ----------
+def _prob(log_odds):
+    e = np.exp(np.asarray(log_odds, dtype=np.float64))
+    return e / (1.0 + e)  # probabilityFromLogOdds, core/log_odds.h:32-34
+
+
+def _log_odds(p):
+    """logOddsFromProbability in binary32 with a correctly rounded log (numpy's float32 log is 1 ulp off)."""
+    import math
+    p = min(max(np.float32(p), np.float32(1e-3)), np.float32(1.0) - np.float32(1e-3))
+    return np.float32(math.log(float(np.float32(p / (np.float32(1.0) - p)))))
+
+
+def test_log_odds_constants():
+    """core/log_odds.h:23-30 and the sensor-model defaults (occupancy_integrator_params.h:21-40)."""
+    m = orc.OracleMap(0.1)
+    cam = _cam()
+    depth = np.full((480, 640), 2.0, np.float32)
+    m.integrate_occupancy(depth, np.eye(4, dtype=np.float32), cam)
+    vals = np.unique(np.concatenate([b.ravel() for b in m.occupancy_layer().values()]))
+    lo_free, lo_occ = _log_odds(0.3), _log_odds(0.7)
+    assert set(vals.tolist()) <= {0.0, float(lo_free), float(lo_occ)}
+    assert float(lo_free) in vals.tolist() and float(lo_occ) in vals.tolist()
+    # saturation at logOdds(0.01) / logOdds(0.99) after many frames
+    for _ in range(8):
+        m.integrate_occupancy(depth, np.eye(4, dtype=np.float32), cam)
+    vals = np.concatenate([b.ravel() for b in m.occupancy_layer().values()])
+    assert abs(float(vals.max()) - np.log(0.99 / 0.01)) < 1e-5
+    assert abs(float(vals.min()) - np.log(0.01 / 0.99)) < 1e-5
+
+
+def test_occupancy_reconstruct_plane():
+    """ReconstructPlane (test_occupancy_integrator.cpp:51-128): surface points end up with p > 0.5."""
+    voxel = 0.1
+    cs = syn.PinholeCamera()
+    depth, = [d for d, _ in syn.make_sequence(syn.plane_scene(5.0), cs, [np.eye(4)])]
+    cam = _cam()
+    m = orc.OracleMap(voxel)
+    p = orc.default_tsdf_params(max_integration_distance_m=10.0, truncation_distance_vox=10.0)
+    m.integrate_occupancy(depth, np.eye(4, dtype=np.float32), cam, p)
+    layer = m.occupancy_layer()
+    rng = np.random.default_rng(0)
+    n = 0
+    for _ in range(1000):
+        u, v = rng.uniform(1, 639), rng.uniform(1, 479)
+        z = float(depth[int(v), int(u)])
+        pt = np.array([(u - 320.0) / 300.0 * z, (v - 240.0) / 300.0 * z, z])
+        g = np.floor(pt / voxel).astype(int)
+        blk = layer.get(tuple(int(c) for c in g // 8))
+        assert blk is not None
+        assert _prob(blk[tuple(g % 8)]) > 0.5
+        n += 1
+    assert n == 1000
+
+
+def test_occupancy_sphere_scene():
+    """SphereSceneTest (test_occupancy_integrator.cpp:130-219): after the 80-pose orbit fewer than 2.5 % of the
+    voxels contradict the ground truth occupancy."""
+    voxel = 0.1
+    cs = syn.PinholeCamera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    cam = orc.Camera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    scene = syn.sphere_in_box()
+    m = orc.OracleMap(voxel)
+    p = orc.default_tsdf_params(truncation_distance_vox=2.0)
+    for depth, T in syn.make_sequence(scene, cs, syn.circle_trajectory(80)):
+        m.integrate_occupancy(depth, T, cam, p)
+    assert p.truncation_distance_vox == 2.0  # 0.2 m >= half width 0.1 m: not raised
+    tot = bad = 0
+    ii = (np.indices((8, 8, 8)).reshape(3, -1).T + 0.5)
+    for k, blk in m.occupancy_layer().items():
+        pos = (np.asarray(k) * 8 + ii) * voxel
+        inside = np.all((pos > [-5.5, -5.5, -0.5]) & (pos < [5.5, 5.5, 5.5]), axis=1)
+        gt_occ = scene.distance(pos) <= np.sqrt(3.0) * voxel / 2.0  # scene_impl.h:84-100
+        pr = _prob(blk.reshape(-1))
+        bad += int(((gt_occ & (pr < 0.5)) | (~gt_occ & (pr > 0.5)))[inside].sum())
+        tot += int(inside.sum())
+    assert tot > 100000
+    assert 100.0 * bad / tot < 2.5
+
+
+def test_occupancy_masked_pixels_are_unobserved():
+    """MaskedDepthPixels (test_occupancy_integrator.cpp:248-304): voxels that project onto inactive pixels are
+    integrated as unobserved, i.e. keep log_odds == 0."""
+    voxel = 0.1
+    cs = syn.PinholeCamera()
+    cam = _cam()
+    scene = syn.Scene().add_sphere((0.0, 0.0, 5.0), 2.0)
+    depth = syn.render_depth(scene, cs, np.eye(4), max_dist=5.0, invalid_depth=5.0)
+    mask = np.where(depth < 5.0 - 0.8 * 2.0, 255, 0).astype(np.uint8)
+    m = orc.OracleMap(voxel)
+    m.integrate_occupancy(depth, np.eye(4, dtype=np.float32), cam, mask=mask, mask_mode=0)
+    checked = changed = 0
+    ii = (np.indices((8, 8, 8)).reshape(3, -1).T + 0.5)
+    for k, blk in m.occupancy_layer().items():
+        pos = ((np.asarray(k) * 8 + ii) * voxel).astype(np.float32)
+        z = pos[:, 2]
+        ok = z > 1e-6
+        u = pos[:, 0] / np.where(ok, z, 1) * 300.0 + 320.0
+        v = pos[:, 1] / np.where(ok, z, 1) * 300.0 + 240.0
+        ok &= (u >= 0) & (v >= 0) & (u < 640) & (v < 480)
+        fu, fv = np.floor(u), np.floor(v)
+        ok &= ((u - fu) < 1 - 1e-4) & ((v - fv) < 1 - 1e-4)  # pixel-boundary guard of the reference test
+        px = np.clip(fu.astype(int), 0, 639)
+        py = np.clip(fv.astype(int), 0, 479)
+        inactive = ok & (mask[py, px] == 0)
+        lo = blk.reshape(-1)
+        assert np.all(lo[inactive] == 0.0)
+        checked += int(inactive.sum())
+        changed += int((lo != 0).sum())
+    assert checked > 0 and changed > 0
+
+
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf, -1.0, 0.0, -10.0])
+def test_occupancy_invalid_depth_integrates_nothing(bad):
+    """InvalidDepthHandling (test_occupancy_integrator.cpp:306-393)."""
+    cam = _cam()
+    T = np.eye(4, dtype=np.float32)
+    m = orc.OracleMap(0.1)
+    m.integrate_occupancy(np.full((480, 640), bad, np.float32), T, cam)
+    assert all(not (np.abs(b) > 1e-6).any() for b in m.occupancy_layer().values())
+    m.integrate_occupancy(np.full((480, 640), 2.0, np.float32), T, cam)
+    before = {k: b.copy() for k, b in m.occupancy_layer().items()}
+    assert sum(int((np.abs(b) > 1e-6).sum()) for b in before.values()) > 0
+    m.integrate_occupancy(np.full((480, 640), bad, np.float32), T, cam)
+    after = m.occupancy_layer()
+    for k, b in before.items():
+        assert np.array_equal(after[k], b)  # no decay for invalid depth
+
+
+def test_occupancy_truncation_raised_to_half_width():
+    """setFunctorParameters (projective_occupancy_integrator.cu:41-65): the truncation distance is raised to the
+    occupied half width, and the new value sticks."""
+    m = orc.OracleMap(0.05)
+    p = orc.default_tsdf_params(truncation_distance_vox=1.0)
+    m.integrate_occupancy(np.full((120, 160), 2.0, np.float32), np.eye(4, dtype=np.float32),
+                          orc.Camera(75.0, 75.0, 80.0, 60.0, 160, 120), p)
+    assert p.truncation_distance_vox == np.float32(np.float32(0.1) / np.float32(0.05))
+
+
+def _gt_occupancy_map(scene, voxel):
+    """Scene::generateLayerFromScene<OccupancyVoxel> over the test's AABB (scene_impl.h:105-145)."""
+    m = orc.OracleMap(voxel)
+    lo_hi, lo_lo = _log_odds(1.0), _log_odds(0.0)
+    ii = (np.indices((8, 8, 8)).reshape(3, -1).T + 0.5)
+    bs = 8 * voxel
+    lo_b, hi_b = np.floor(np.array([-5.5, -5.5, -0.5]) / bs).astype(int), np.floor(np.array([5.5, 5.5, 5.5]) / bs).astype(int)
+    keys = []
+    for x in range(lo_b[0], hi_b[0] + 1):
+        for y in range(lo_b[1], hi_b[1] + 1):
+            for z in range(lo_b[2], hi_b[2] + 1):
+                pos = (np.array([x, y, z]) * 8 + ii) * voxel
+                inside = np.all((pos >= [-5.5, -5.5, -0.5]) & (pos <= [5.5, 5.5, 5.5]), axis=1)
+                occ = scene.distance(pos) <= np.sqrt(3.0) * voxel / 2.0
+                blk = np.where(inside, np.where(occ, lo_hi, lo_lo), np.float32(0)).astype(np.float32)
+                m.set_occupancy_block((x, y, z), blk.reshape(8, 8, 8))
+                keys.append((x, y, z))
+    return m, np.asarray(keys, dtype=np.int32)
+
+
+@pytest.mark.parametrize("make_scene", [syn.sphere_in_box, syn.box_with_cube])
+def test_esdf_from_occupancy_close_to_ground_truth(make_scene):
+    """OccupancySingleEsdfTestGPU (test_esdf_integrator.cpp:554-582): ESDF of a ground-truth occupancy layer vs the
+    analytic distance, outside obstacles only; plus the validateEsdf invariants."""
+    voxel = 0.2
+    scene = make_scene()
+    m, keys = _gt_occupancy_map(scene, voxel)
+    ep = orc.default_esdf_params(max_esdf_distance_m=4.0)
+    m.integrate_esdf_occupancy(keys, ep)
+    world = _esdf_world(m)
+    n = bad = sites = 0
+    for c, v in world.items():
+        p = v["parent_direction"]
+        if v["is_site"]:
+            sites += 1
+            assert v["is_inside"] and v["squared_distance_vox"] == 0.0
+            continue
+        if p.any():
+            parent = world.get((c[0] + int(p[0]), c[1] + int(p[1]), c[2] + int(p[2])))
+            assert parent is not None and parent["is_site"]
+            assert float(v["squared_distance_vox"]) == float(int(p[0]) ** 2 + int(p[1]) ** 2 + int(p[2]) ** 2)
+        pos = (np.asarray(c) + 0.5) * voxel
+        gt = float(scene.distance(pos))
+        if gt <= 0 or gt >= 4.0 - voxel or not p.any():
+            continue
+        d = voxel * float(np.sqrt(v["squared_distance_vox"]))
+        n += 1
+        if abs(d - gt) > 2.0 * voxel:  # sites are whole occupied voxels: up to ~one diagonal of slack
+            bad += 1
+    assert sites > 1000 and n > 10000
+    assert bad / n < 0.002  # very_small_cutoff_, test_esdf_integrator.cpp:78-80
