@@ -109,6 +109,13 @@ struct NvbMapper {
   int* stamp_a = nullptr;
   int* stamp_b = nullptr;
   int* nbr = nullptr;
+  int* nbr27 = nullptr;
+  unsigned char* shadow = nullptr;
+  int shadow_cap = 0;
+  int* cand_stamp = nullptr;
+  int* cand_a = nullptr;
+  int* cand_b = nullptr;
+  int ges_switch = 160;
   int* seed_upd = nullptr;
   int* seed_clr = nullptr;
   int update_seq = 0;
@@ -244,6 +251,26 @@ int allocEsdfScratch(NvbMapper* m, int old_cap, int cap) {
     if (m->nbr) cudaFree(m->nbr);
     m->nbr = q;
   }
+  {
+    int* q = nullptr;
+    NVB_CUDA(cudaMalloc(&q, (size_t)cap * 27 * sizeof(int)));
+    NVB_CUDA(cudaMemsetAsync(q, 0xFE, (size_t)cap * 27 * sizeof(int), m->stream));
+    if (m->nbr27 && old_cap)
+      NVB_CUDA(cudaMemcpyAsync(q, m->nbr27, (size_t)old_cap * 27 * sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
+    NVB_CUDA(syncAll(m));
+    if (m->nbr27) cudaFree(m->nbr27);
+    m->nbr27 = q;
+  }
+  if ((rc = reallocCopy(&m->cand_stamp, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->cand_a, 0, (size_t)cap, false, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->cand_b, 0, (size_t)cap, false, m->stream))) return rc;
+  if (m->esdf_persistent == 2) {
+    // gather-emulate-sweep wavefront: second ESDF slab (contents only live inside one launch)
+    if (m->shadow) cudaFree(m->shadow);
+    m->shadow = nullptr;
+    NVB_CUDA(cudaMalloc(&m->shadow, (size_t)cap * kEsdfBlockBytes));
+    m->shadow_cap = cap;
+  }
   return NVB_OK;
 }
 
@@ -256,7 +283,7 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kNumInts = 32 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kGesCounts = 24, kNumInts = 32 };
 
 float logOddsFromProbability(float p);
 
@@ -271,9 +298,13 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.cleared_list = m->cleared_list, c.cleared_count = m->esdf_ints + kClearedCount;
   c.ring_a = m->ring_a, c.ring_b = m->ring_b;
   c.ring_count = m->esdf_ints + kRingCount;
+  c.tail_state = m->esdf_ints + kTailState;
   c.stamp_a = m->stamp_a, c.stamp_b = m->stamp_b;
   c.ring_id = m->esdf_ints + kRingId;
   c.nbr = m->nbr, c.seed_upd = m->seed_upd, c.seed_clr = m->seed_clr;
+  c.nbr27 = m->nbr27, c.shadow = m->shadow, c.cand_stamp = m->cand_stamp;
+  c.ges_counts = m->esdf_ints + kGesCounts;
+  c.cand_a = m->cand_a, c.cand_b = m->cand_b, c.ges_switch = m->ges_switch;
   c.cleared_seq = m->esdf_ints + kClearedSeq;
   c.update_seq = m->update_seq;
   c.barrier = m->barrier;
@@ -677,7 +708,8 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
     NVB_CUDA(cudaEventRecord(m->esdf_ready, m->stream));
     NVB_CUDA(cudaStreamWaitEvent(m->esdf_stream, m->esdf_ready, 0));
     beginStageOn(m, 5, m->esdf_stream);
-    e = launchEsdfComputePersistent(c, m->num_sms, m->esdf_stream, &launches);
+    e = m->esdf_persistent == 2 ? launchEsdfComputeGes(c, m->num_sms, m->esdf_stream, &launches)
+                                : launchEsdfComputePersistent(c, m->num_sms, m->esdf_stream, &launches);
     endStageOn(m, m->esdf_stream);
     if (e == cudaSuccess) {
       NVB_CUDA(cudaEventRecord(m->esdf_done, m->esdf_stream));
@@ -772,6 +804,9 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   nvb_default_occupancy_params(&m->op);
   m->projective_layer_type = opts->projective_layer_type;
   m->esdf_persistent = opts->esdf_persistent;
+  // A/B switch for measurements: 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
+  if (const char* e = getenv("NVB_ESDF_MODE")) m->esdf_persistent = atoi(e);
+  if (const char* e = getenv("NVB_GES_SWITCH")) m->ges_switch = atoi(e);
   NVB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   NVB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   NVB_CUDA(cudaStreamCreateWithFlags(&m->esdf_stream, cudaStreamNonBlocking));
@@ -834,6 +869,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->work), cudaFree(m->esdf_ints), cudaFree(m->upd_list), cudaFree(m->clr_list), cudaFree(m->cleared_list);
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
   cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr);
+  cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
@@ -862,6 +898,7 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(cudaMemsetAsync(m->seed_upd, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->seed_clr, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->nbr, 0xFE, (size_t)m->esdf.capacity * 6 * sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->nbr27, 0xFE, (size_t)m->esdf.capacity * 27 * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
   m->tracker_initialized = false;
   m->tsdf_count_ub = 0, m->tsdf_count_confirmed = 0, m->esdf_extra_ub = 0;

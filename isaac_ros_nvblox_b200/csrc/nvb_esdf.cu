@@ -46,6 +46,7 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
     c.clr_aabb[3] = c.clr_aabb[4] = c.clr_aabb[5] = INT32_MIN;
     c.ring_count[0] = c.ring_count[1] = 0;
     c.ring_count[2] = 0;  // mark-kernel "CTAs done" counter
+    c.ges_counts[0] = c.ges_counts[1] = c.ges_counts[2] = c.ges_counts[3] = 0;
     *c.barrier = 0;
     for (int k = 0; k < 16; k++) c.stats[k] = 0;
   }
@@ -80,19 +81,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
   if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;  // list consumed by the allocate kernel
   for (int item = blockIdx.x; item < n; item += gridDim.x) {
     const int4 w = c.work[item];
-    if (w.x >= 0 && w.z && tid < 6) {
-      // Newly allocated ESDF block: link it with its six face neighbours (both directions).
-      // Replaces the per-ring getBlockPtr hash lookups (:1100-1131).
-      const int* bi = c.esdf.block_index + 3 * w.x;
-      int x = bi[0], y = bi[1], z = bi[2];
-      const int d = (tid & 1) ? -1 : 1;
-      if ((tid >> 1) == 0) x += d;
-      else if ((tid >> 1) == 1) y += d;
-      else z += d;
-      const int other = hashFind(c.esdf.hash, x, y, z);
-      c.nbr[6 * w.x + tid] = other;
-      if (other >= 0) c.nbr[6 * other + (tid ^ 1)] = w.x;
-    }
+    if (w.x >= 0 && w.z) linkNewBlock(c, w.x, tid);  // newly allocated ESDF block
     if (w.x < 0 || w.y < 0) continue;  // block_ptr == nullptr || esdf_block == nullptr (:513-517)
     if (tid < 3) s_flags[tid] = 0;
     uint4* gblk = reinterpret_cast<uint4*>(esdfBlockPtr(c.esdf, w.x));
@@ -200,17 +189,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkOccupancyKernel(EsdfCtx c) {
   if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;
   for (int item = blockIdx.x; item < n; item += gridDim.x) {
     const int4 w = c.work[item];
-    if (w.x >= 0 && w.z && tid < 6) {
-      const int* bi = c.esdf.block_index + 3 * w.x;
-      int x = bi[0], y = bi[1], z = bi[2];
-      const int d = (tid & 1) ? -1 : 1;
-      if ((tid >> 1) == 0) x += d;
-      else if ((tid >> 1) == 1) y += d;
-      else z += d;
-      const int other = hashFind(c.esdf.hash, x, y, z);
-      c.nbr[6 * w.x + tid] = other;
-      if (other >= 0) c.nbr[6 * other + (tid ^ 1)] = w.x;
-    }
+    if (w.x >= 0 && w.z) linkNewBlock(c, w.x, tid);  // newly allocated ESDF block
     if (w.x < 0 || w.y < 0) continue;
     if (tid < 3) s_flags[tid] = 0;
     uint4* gblk = reinterpret_cast<uint4*>(esdfBlockPtr(c.esdf, w.x));
@@ -359,18 +338,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
     }
     tma::mbarWait(&s_bar[s], (unsigned int)((j / kMarkStages) & 1));
     const int4 w = s_work[s];
-    if (w.x >= 0 && w.z && tid < 6) {
-      // Newly allocated ESDF block: link it with its six face neighbours (both directions).
-      const int* bi = c.esdf.block_index + 3 * w.x;
-      int x = bi[0], y = bi[1], z = bi[2];
-      const int d = (tid & 1) ? -1 : 1;
-      if ((tid >> 1) == 0) x += d;
-      else if ((tid >> 1) == 1) y += d;
-      else z += d;
-      const int other = hashFind(c.esdf.hash, x, y, z);
-      c.nbr[6 * w.x + tid] = other;
-      if (other >= 0) c.nbr[6 * other + (tid ^ 1)] = w.x;
-    }
+    if (w.x >= 0 && w.z) linkNewBlock(c, w.x, tid);  // newly allocated ESDF block
     const bool valid = (w.x >= 0 && w.y >= 0);  // block_ptr == nullptr || esdf_block == nullptr (:513-517)
     if (tid < 3) s_flags[tid] = 0;
     __syncthreads();

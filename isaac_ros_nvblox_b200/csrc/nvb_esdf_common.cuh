@@ -63,6 +63,26 @@ __device__ __forceinline__ bool updateSingleNeighbor(const VoxelRegs& e, VoxelRe
   return false;
 }
 
+// A newly allocated ESDF block is linked with its neighbours in both directions: the six face neighbours
+// (c.nbr) and the whole 3x3x3 neighbourhood (c.nbr27). Replaces the per-ring getBlockPtr hash lookups
+// (esdf_integrator.cu:1100-1131). Threads 0..26 of the calling CTA take one offset each.
+__device__ __forceinline__ void linkNewBlock(const EsdfCtx& c, int slot, int tid) {
+  if (tid >= 27) return;
+  const int dx = tid / 9 - 1, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
+  const int* bi = c.esdf.block_index + 3 * slot;
+  const int other = (tid == 13) ? slot : hashFind(c.esdf.hash, bi[0] + dx, bi[1] + dy, bi[2] + dz);
+  c.nbr27[27 * slot + tid] = other;
+  if (other >= 0) c.nbr27[27 * other + (26 - tid)] = slot;
+  // face neighbours: c.nbr order is +x,-x,+y,-y,+z,-z
+  const int nz = (dx != 0) + (dy != 0) + (dz != 0);
+  if (nz == 1) {
+    const int axis = dx ? 0 : (dy ? 1 : 2);
+    const int neg = (dx + dy + dz) < 0 ? 1 : 0;
+    c.nbr[6 * slot + axis * 2 + neg] = other;
+    if (other >= 0) c.nbr[6 * other + axis * 2 + (neg ^ 1)] = slot;
+  }
+}
+
 __device__ __forceinline__ long long globalTimerNs() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

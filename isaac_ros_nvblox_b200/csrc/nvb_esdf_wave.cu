@@ -26,6 +26,7 @@
 //   * 256-thread CTAs with up to 128 registers (half an SM's register file) so that the next frame's
 //     raycast / compaction / TSDF kernels co-reside while the wavefront runs on its side stream.
 #include "nvb_esdf_common.cuh"
+#include "nvb_tma.cuh"
 
 namespace nvb {
 
@@ -49,61 +50,8 @@ constexpr int kWG = kWT / 64;           // groups of 64 threads
 constexpr int kWaveMaxMembers = 1024;   // owned candidates scanned per round
 constexpr int kPendMax = 1024;         // pending "updated block" records per CTA per ring before a forced flush
 constexpr int kNbrCache = 128;          // members whose neighbour slots are cached in smem
-// Shared-memory image of an ESDF block for the sweeps: the 20-byte AoS voxels with ONE pad word after
-// every row of 8 voxels: word(v, f) = 5 v + f + (v >> 3). With this pitch the y- and z-line accesses of a
-// warp (32 lines) hit 32 distinct banks and x-lines are 2-way (the unpadded copy is 4-way / 8-way), which
-// matters because all 16 groups of the CTA share one shared-memory pipe.
-constexpr int kPadBlockWords = kBlockWords + kVpb / kVps;  // 2560 + 64
-#ifndef NVB_WAVE_PAD
-#define NVB_WAVE_PAD 0  // measured: the padded image is 30 % slower (scalar smem stores); see profiles/README.md
-#endif
-constexpr int kSweepBlockWords = NVB_WAVE_PAD ? kPadBlockWords : kBlockWords;
+constexpr int kSweepBlockWords = kBlockWords;  // (a bank-conflict-free padded image was measured 30 % slower: scalar smem stores)
 constexpr size_t kWaveSmemBytes = (size_t)kWG * kSweepBlockWords * sizeof(unsigned int);  // sweep buffers
-
-// HBM -> padded smem image. Global side: 128-bit coalesced loads (640 chunks per block). Shared side:
-// the pad makes chunk destinations unaligned, so each chunk is stored as four 32-bit words; lane groups
-// of 8 rotate which word they store so that the 32 lanes of one store instruction hit 32 banks.
-__device__ __forceinline__ unsigned int pick(const uint4& q, int j) {
-  return j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w));
-}
-__device__ __forceinline__ void loadBlockPadded(unsigned int* sm, const unsigned int* g, int lane64) {
-  const uint4* src = reinterpret_cast<const uint4*>(g);
-  const int rot = (lane64 >> 3) & 3;
-  constexpr int kBatch = 5;  // 5 chunks (20 registers) in flight per thread, twice
-#pragma unroll 1
-  for (int k0 = 0; k0 < kBlockWords / 4 / 64; k0 += kBatch) {
-    uint4 q[kBatch];
-#pragma unroll
-    for (int k = 0; k < kBatch; k++) q[k] = __ldcg(src + lane64 + (k0 + k) * 64);
-#pragma unroll
-    for (int k = 0; k < kBatch; k++) {
-      const int c = lane64 + (k0 + k) * 64;
-      unsigned int* dst = sm + 4 * c + c / 10;  // row = (4c) / 40
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const int j = (t + rot) & 3;
-        dst[j] = pick(q[k], j);
-      }
-    }
-  }
-}
-__device__ __forceinline__ void storeBlockPadded(unsigned int* g, const unsigned int* sm, int lane64) {
-  uint4* dst = reinterpret_cast<uint4*>(g);
-  const int rot = (lane64 >> 3) & 3;
-#pragma unroll
-  for (int k = 0; k < kBlockWords / 4 / 64; k++) {
-    const int c = lane64 + k * 64;
-    const unsigned int* src = sm + 4 * c + c / 10;
-    unsigned int w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const int j = (t + rot) & 3;
-      const unsigned int val = src[j];
-      w0 = (j == 0) ? val : w0, w1 = (j == 1) ? val : w1, w2 = (j == 2) ? val : w2, w3 = (j == 3) ? val : w3;
-    }
-    __stcg(dst + c, make_uint4(w0, w1, w2, w3));
-  }
-}
 
 __device__ __forceinline__ int resolveNeighbor(const EsdfCtx& c, int slot, int dir) {
   int v = __ldcg(c.nbr + 6 * slot + dir);
@@ -136,14 +84,15 @@ struct WaveShared {
 // c, c+G, c+2G, ... so every CTA gets ceil(n/G) or floor(n/G) blocks (the static slot-ownership scheme this
 // replaces had max/mean of 2.5, and the slowest CTA is what a phase costs). Entries [first, first+cap) of this
 // CTA's share are cached in shared memory. Optionally stamps them (initial list of a computeEsdf call).
+// `have` leading entries are already in sh.members (fetched speculatively with the ring's count).
 __device__ NVB_WAVE_FN int loadMembers(WaveShared& sh, const int* list, int n, int cta, int nctas, int first,
-                                       int* stamp_out, int stamp_value) {
+                                       int* stamp_out, int stamp_value, int have = 0) {
   const int tid = threadIdx.x;
   const int mine = (n > cta) ? (n - cta + nctas - 1) / nctas : 0;  // entries of this CTA
   int k = mine - first;
   k = k < 0 ? 0 : (k > kWaveMaxMembers ? kWaveMaxMembers : k);
   for (int j = tid; j < k; j += kWT) {
-    const int slot = __ldcg(list + cta + (first + j) * nctas);
+    const int slot = j < have ? sh.members[j] : __ldcg(list + cta + (first + j) * nctas);
     sh.members[j] = slot;
     if (stamp_out) stamp_out[slot] = stamp_value;
   }
@@ -170,17 +119,16 @@ __device__ __forceinline__ void prefetchNeighbors(const EsdfCtx& c, WaveShared& 
 // The line's 8 voxels are loaded once, walked forward, the register image is reversed and walked again
 // (= the backward pass); changed voxels are written back. `axis` and `pass` are run-time values so that
 // ONE copy of the 8-step body serves all six passes.
-// `sm` is the block image in shared memory, v0 the line's first voxel, `stride` the voxel stride along the
-// line; (c0,c1,c2) are the voxel coordinates at position 0.
-__device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stride, int c0, int c1, int c2, int axis,
-                                              float max_sq) {
+// `sm` is the block image in shared memory, base_w the word offset of the line's first voxel, stride_w the word
+// stride along the line; (c0,c1,c2) are the voxel coordinates at position 0.
+__device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int base_w, int stride_w, int c0, int c1, int c2,
+                                              int axis, float max_sq) {
   int T[kVps];  // ceil(squared distance): sq > n  <=>  T > n for every integer n
   int p0[kVps], p1[kVps], p2[kVps];
   unsigned int obs = 0, site = 0, valid = 0, dirty = 0;
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
-    const int v = v0 + i * stride;
-    const unsigned int* e = sm + v * kEsdfVoxelWords + (NVB_WAVE_PAD ? (v >> 3) : 0);
+    const unsigned int* e = sm + base_w + i * stride_w;
     const float sq = __uint_as_float(e[0]);
     T[i] = __float2int_ru(sq);
     p0[i] = (int)e[1], p1[i] = (int)e[2], p2[i] = (int)e[3];
@@ -231,8 +179,7 @@ __device__ __forceinline__ bool sweepLineRegs(unsigned int* sm, int v0, int stri
 #pragma unroll
   for (int i = 0; i < kVps; i++) {
     if ((dirty >> i) & 1u) {
-      const int v = v0 + i * stride;
-      unsigned int* e = sm + v * kEsdfVoxelWords + (NVB_WAVE_PAD ? (v >> 3) : 0);
+      unsigned int* e = sm + base_w + i * stride_w;
       e[0] = __float_as_uint((float)T[i]);
       e[1] = (unsigned)p0[i], e[2] = (unsigned)p1[i], e[3] = (unsigned)p2[i];
     }
@@ -250,10 +197,7 @@ __device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k
     const int item = base + group;
     const int slot = item < k ? sh.members[item] : -1;
     if (lane64 == 0) sh.changed[group] = 0;
-    if (slot >= 0) {
-      if (NVB_WAVE_PAD) loadBlockPadded(sm, esdfBlockPtr(c.esdf, slot), lane64);
-      else loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
-    }
+    if (slot >= 0) loadBlockGroup(sm, esdfBlockPtr(c.esdf, slot), lane64);
     // neighbour slots for the coming axis phases: issued behind the block loads, not in front of them
     if (prefetch_nbr && base == 0) prefetchNeighbors(c, sh, k);
     __syncthreads();
@@ -266,15 +210,13 @@ __device__ NVB_WAVE_FN void sweepMembers(const EsdfCtx& c, WaveShared& sh, int k
       const int c0 = (axis == 0) ? 0 : a;
       const int c1 = (axis == 0) ? a : ((axis == 1) ? 0 : b);
       const int c2 = (axis == 2) ? 0 : b;
-      if (slot >= 0) ch |= sweepLineRegs(sm, v0, stride, c0, c1, c2, axis, c.max_sq);
+      if (slot >= 0)
+        ch |= sweepLineRegs(sm, v0 * kEsdfVoxelWords, stride * kEsdfVoxelWords, c0, c1, c2, axis, c.max_sq);
       __syncthreads();
     }
     if (ch) sh.changed[group] = 1;
     __syncthreads();
-    if (slot >= 0 && sh.changed[group]) {
-      if (NVB_WAVE_PAD) storeBlockPadded(esdfBlockPtr(c.esdf, slot), sm, lane64);
-      else storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
-    }
+    if (slot >= 0 && sh.changed[group]) storeBlockGroup(esdfBlockPtr(c.esdf, slot), sm, lane64);
     __syncthreads();
   }
 }
@@ -378,6 +320,39 @@ __device__ NVB_WAVE_FN void flushPending(WaveShared& sh, int* stamp_nxt, int rin
 #ifndef NVB_WAVE_MAXREG
 #define NVB_WAVE_MAXREG 128
 #endif
+#ifndef NVB_WAVE_TAIL
+#define NVB_WAVE_TAIL 4  // rings with at most this many members (= one sweep round of a CTA) are run by CTA 0 alone; 0 disables. Measured: 0 -> 0.320, 4 -> 0.287, 8 -> 0.300, 16 -> 0.330 ms per frame
+#endif
+constexpr int kTail = NVB_WAVE_TAIL;
+constexpr int kSpec = 8;  // list entries per CTA fetched speculatively together with the ring's member count
+
+// Unique hand-over of the recorded blocks to the next ring when ONE CTA runs the ring (tail mode): duplicates are
+// found by comparing the (<= 12 per member) records in shared memory; no atomics, no L2 round trip.
+// Next ring's members end up in sh.members[0..n), their stamps and the global list are written with plain stores
+// (the list is only read if the ring outgrows the tail mode).
+__device__ NVB_WAVE_FN int flushLocal(WaveShared& sh, int* stamp_nxt, int ring, int* list_nxt) {
+  const int tid = threadIdx.x;
+  if (tid == 0) sh.count = 0;
+  __syncthreads();
+  const int np = sh.npend;
+  for (int q = tid; q < np; q += kWT) {
+    const int slot = sh.pend[q];
+    bool fresh = true;
+    for (int j = 0; j < q; j++) fresh = fresh && (sh.pend[j] != slot);
+    if (fresh) {
+      const int pos = atomicAdd(&sh.count, 1);
+      sh.members[pos] = slot;
+      stamp_nxt[slot] = ring + 1;
+      list_nxt[pos] = slot;
+    }
+  }
+  __syncthreads();
+  const int n = sh.count;
+  if (tid == 0) sh.npend = 0;
+  __syncthreads();
+  return n;
+}
+
 __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
   extern __shared__ __align__(16) unsigned int smem[];
   __shared__ WaveShared sh;
@@ -405,40 +380,81 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
     atomicMax((unsigned long long*)c.phase_max + n_bar, (unsigned long long)(globalTimerNs() - tw0));     \
   }
 #define NVB_PHASE_BEGIN() tw0 = globalTimerNs();
+#define NVB_BARRIER(acc)                      \
+  NVB_TICK(acc)                               \
+  NVB_PHASE_MAX()                             \
+  gridBarrier(c.barrier, generation, nctas);  \
+  NVB_TICK(t_bar)                             \
+  n_bar++;                                    \
+  NVB_PHASE_BEGIN()
+  auto share = [&](int count) { return (count > cta) ? (count - cta + nctas - 1) / nctas : 0; };
+  auto roundsOf = [&](int count) { return ((count + nctas - 1) / nctas + kWaveMaxMembers - 1) / kWaveMaxMembers; };
   for (int pass = 0; pass < 2; pass++) {
     // pass 0: blocks with sites; pass 1: the persistent cleared list (:254-257)
-    const int* src = pass ? c.cleared_list : c.upd_list;
     int n = pass ? *(volatile int*)c.cleared_count : *(volatile int*)c.upd_count;
     if (n == 0) continue;
     int ci = ring & 1;
-    const int* cur = src;  // the first ring's members are read straight from the source list
-    auto share = [&](int count) { return (count > cta) ? (count - cta + nctas - 1) / nctas : 0; };
-    auto roundsOf = [&](int count) { return ((count + nctas - 1) / nctas + kWaveMaxMembers - 1) / kWaveMaxMembers; };
-    // Initial sweep of the source list; its members are stamped as ring `ring`.
-    {
-      const int rounds = roundsOf(n);
-      for (int r = 0; r < rounds; r++) {
-        const int k = loadMembers(sh, cur, n, cta, nctas, r * kWaveMaxMembers, stamp[ci], ring);
-        sweepMembers(c, sh, k, smem, rounds == 1);
-      }
-    }
-    if (cta == 0 && threadIdx.x == 0) c.ring_count[ci ^ 1] = 0;
-    NVB_TICK(t_sweep)
-    NVB_PHASE_MAX()
-    gridBarrier(c.barrier, generation, nctas);
-    NVB_TICK(t_bar)
-    n_bar++;
-    NVB_PHASE_BEGIN()
-    swept += n;
+    const int* cur = pass ? c.cleared_list : c.upd_list;  // the first ring's members are read straight from the source list
+    bool initial = true;  // members of `cur` still have to be stamped as ring `ring`
+    int spec = 0;         // leading entries of this CTA's share already in sh.members (speculative fetch)
+    // Loop invariant: the n members of `cur` (ring `ring`) have received their face updates and wait for their sweep.
     while (n > 0) {
       const int ni = ci ^ 1;
+      if (kTail > 0 && n <= kTail) {
+        // ---- tail mode: the ring fits one CTA. CTA 0 runs whole rings (sweep, three axis phases, hand-over) with
+        // block-level synchronisation only, until the wavefront dies out or outgrows the tail; everybody else
+        // waits at ONE grid barrier. A ring costs its dependent chain (~6 us) instead of chain + 4 barriers + the
+        // list hand-over through L2 (~14 us).
+        if (cta == 0) {
+          int t = 0, tn = n, tci = ci, tring = ring;
+          int k = loadMembers(sh, cur, tn, 0, 1, 0, initial ? stamp[tci] : nullptr, tring);
+          while (true) {
+            const int tni = tci ^ 1;
+            sweepMembers(c, sh, k, smem, true);
+            swept += k;
+#pragma unroll 1
+            for (int axis = 0; axis < 3; axis++) {
+              axisMembers(c, sh, axis, k, stamp[tci], tring, stamp[tni], list[tni], c.ring_count + tni);
+              __syncthreads();
+            }
+            faces += 6ll * k;
+            rings++, t++;
+            k = flushLocal(sh, stamp[tni], tring, list[tni]);
+            tring++, tci = tni, tn = k;
+            if (tn == 0 || tn > kTail) break;
+          }
+          if (threadIdx.x == 0) c.tail_state[0] = t, c.tail_state[1] = tn;
+        }
+        NVB_BARRIER(t_sweep)
+        if (threadIdx.x == 0) sh.scan[0] = __ldcg(c.tail_state + 0), sh.scan[1] = __ldcg(c.tail_state + 1);
+        __syncthreads();
+        const int t = sh.scan[0];
+        n = sh.scan[1];
+        __syncthreads();
+        ring += t;
+        ci ^= (t & 1);
+        cur = list[ci];
+        initial = false, spec = 0;
+        continue;
+      }
+      // ---- grid mode
       const int rounds = roundsOf(n);
+      // sweep phase
+      for (int r = 0; r < rounds; r++) {
+        const int k = loadMembers(sh, cur, n, cta, nctas, r * kWaveMaxMembers, initial ? stamp[ci] : nullptr, ring,
+                                  r == 0 ? spec : 0);
+        sweepMembers(c, sh, k, smem, rounds == 1);
+      }
+      if (cta == 0 && threadIdx.x == 0) c.ring_count[ni] = 0;  // append counter of ring+1
+      NVB_BARRIER(t_sweep)
+      swept += n;
+      // axis phases
 #pragma unroll 1
       for (int axis = 0; axis < 3; axis++) {
         for (int r = 0; r < rounds; r++) {
           int k = share(n);
           if (rounds > 1) {
-            k = loadMembers(sh, cur, n, cta, nctas, r * kWaveMaxMembers, nullptr, 0);
+            k = loadMembers(sh, cur, n, cta, nctas, r * kWaveMaxMembers, nullptr, 0, 0);
             prefetchNeighbors(c, sh, k);
             __syncthreads();
           }
@@ -446,44 +462,31 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
           if (rounds > 1) flushPending(sh, stamp[ni], ring, list[ni], c.ring_count + ni);
         }
         if (axis == 2 && rounds == 1) flushPending(sh, stamp[ni], ring, list[ni], c.ring_count + ni);
-        NVB_TICK(t_axis)
-        NVB_PHASE_MAX()
-        gridBarrier(c.barrier, generation, nctas);
-        NVB_TICK(t_bar)
-        n_bar++;
-        NVB_PHASE_BEGIN()
+        NVB_BARRIER(t_axis)
       }
       faces += 6ll * n;
-      // ring+1 = the blocks appended during the three axis phases
-      const int n_next = *(volatile int*)(c.ring_count + ni);
-      {
-        const int rounds_next = roundsOf(n_next);
-        for (int r = 0; r < rounds_next; r++) {
-          const int k = loadMembers(sh, list[ni], n_next, cta, nctas, r * kWaveMaxMembers, nullptr, 0);
-          sweepMembers(c, sh, k, smem, rounds_next == 1);
-        }
-      }
-      if (cta == 0 && threadIdx.x == 0) c.ring_count[ci] = 0;  // becomes the append counter of ring+2
-      NVB_TICK(t_sweep)
-      NVB_PHASE_MAX()
-      gridBarrier(c.barrier, generation, nctas);
-      NVB_TICK(t_bar)
-      n_bar++;
-      NVB_PHASE_BEGIN()
-      swept += n_next;
       rings++;
+      // ring+1 = the blocks appended during the three axis phases. Its member count and the first entries of this
+      // CTA's share are fetched in the same round trip (entries past the count are ignored).
+      {
+        const int j = threadIdx.x;
+        const long long idx = (long long)cta + (long long)j * nctas;
+        int e = 0;
+        if (j < kSpec && idx < c.esdf.capacity) e = __ldcg(list[ni] + idx);
+        const int n_next = *(volatile int*)(c.ring_count + ni);
+        if (j < kSpec) sh.members[j] = e;
+        spec = kSpec;
+        __syncthreads();
+        n = n_next;
+      }
       ring++;
       ci = ni;
       cur = list[ni];
-      n = n_next;
+      initial = false;
     }
     ring++;
     if (cta == 0 && threadIdx.x == 0) c.ring_count[0] = c.ring_count[1] = 0;
-    NVB_PHASE_MAX()
-    gridBarrier(c.barrier, generation, nctas);
-    NVB_TICK(t_bar)
-    n_bar++;
-    NVB_PHASE_BEGIN()
+    NVB_BARRIER(t_sweep)
   }
 #undef NVB_TICK
   if (cta == 0 && threadIdx.x == 0) {
@@ -494,6 +497,489 @@ __global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveKernel(EsdfCtx c) {
     long long sum_max = 0;
     for (int q = 0; q < n_bar && q < 1000; q++) sum_max += (long long)c.phase_max[q];
     c.stats[12] = sum_max;  // sum over phases of the slowest CTA's work time
+  }
+}
+
+// =====================================================================================================
+// Gather-emulate-sweep wavefront ("GES"): the same computeEsdf, two grid barriers per ring instead of four.
+//
+// A ring's six face passes only move information across block boundaries by ONE voxel, so what they do to a
+// block B is a function of B and its one-voxel halo (10x10x10 voxels, taken from the 3x3x3 block neighbourhood)
+// as they were at the start of the ring, plus which of those 27 blocks are members (sources) of the ring: every
+// voxel pair of every pass that touches the region has both voxels inside it. So the CTA that owns a CANDIDATE
+// block (= neighbour of a member) gathers the region into shared memory, replays the six passes there in the
+// reference's order (halo results are thrown away: their owners compute the same values), and if B changed --
+// i.e. B is a member of the next ring -- sweeps it straight away in shared memory. No communication between
+// the passes, no unique-append of "updated" blocks (a candidate has exactly one owner). Results are parked in a
+// shadow slab until every CTA has finished reading the old state (barrier), then copied over the layer while
+// the next ring's candidates and their neighbour rows are fetched (barrier).
+// =====================================================================================================
+// Region layout (words): "core" = the 10 x 10 z-rows (rx, ry) of the 8 voxels rz = 1..8, 40 words each, in
+// the same order as in a block -- so runs of rows that are contiguous in their source block are contiguous here
+// and move with ONE TMA bulk copy (30 copies per region); then the two z-halo planes rz = 0 and rz = 9, one
+// 8-word cell per voxel, padded so that four of the five voxel words are a 16-byte aligned chunk on both sides.
+constexpr int kCoreWords = 100 * 40;
+constexpr int kZCell = 8;
+constexpr int kZLoBase = kCoreWords;                 // cell: [pad x3][w0][w1 w2 w3 w4]
+constexpr int kZHiBase = kCoreWords + 100 * kZCell;  // cell: [w0 w1 w2 w3][w4][pad x3]
+constexpr int kRegionWords = kCoreWords + 200 * kZCell;  // 5600
+constexpr int kGesMaxCand = 32;                 // candidates of one CTA per chunk
+constexpr int kGesDoneMax = 64;                 // changed blocks remembered per 64-thread group and ring
+constexpr size_t kGesSmemBytes = (size_t)kWG * kRegionWords * sizeof(unsigned int);
+
+struct GesShared {
+  // per-lane constants of the gather and of the pass replay (the same for every candidate): packed descriptors
+  unsigned int tz[4][64];  // z-halo voxel copies:  d27 | hi << 5 | zr << 6 | src_off << 13 | valid << 27
+  unsigned int tc[4][64];  // core row copies:      d27 | zr << 6 | src_off << 13 | valid << 27
+  unsigned int te[6][4][64];  // boundary pairs per pass: src word | dst word << 13 | d27 << 26 | inner << 31; 0 = none
+  int cand[kGesMaxCand];
+  int rows[kGesMaxCand * 27];
+  int done_slots[kWG][kGesDoneMax];
+  int done_n[kWG];
+  int overflow;
+  unsigned int mask[kWG];
+  int changed[kWG];
+};
+
+__device__ __forceinline__ void groupSync(int group) { asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ void cpAsync16(unsigned int* smem_dst, const void* gsrc, bool valid) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;  // src-size 0: nothing is read, the 16 bytes are zero-filled (block not allocated)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ int regionWord(int rx, int ry, int rz) {
+  const int zr = rx * 10 + ry;
+  return rz == 0 ? (kZLoBase + zr * kZCell + 3) : (rz == 9 ? (kZHiBase + zr * kZCell) : (zr * 40 + (rz - 1) * kEsdfVoxelWords));
+}
+// region coordinate (0..9) -> block offset (-1, 0, +1) and voxel coordinate inside that block
+__device__ __forceinline__ int regOff(int r) { return r == 0 ? -1 : (r == 9 ? 1 : 0); }
+__device__ __forceinline__ int regLoc(int r) { return r == 0 ? 7 : (r == 9 ? 0 : r - 1); }
+
+// Region of a candidate block <- the 27 blocks of `row` (slots; < 0 = not allocated -> zeros = unobserved voxels).
+// All bulk traffic is 16-byte cp.async.cg (L2 -> shared, no L1, no registers). Core: a z-row is 160 contiguous,
+// 16-byte aligned bytes on both sides; two neighbouring lanes take alternate chunks of one row, so every request
+// of a warp covers whole 32-byte sectors, and the row is decoded once per five copies. z-halo planes: per voxel one
+// aligned chunk plus one word. (A TMA bulk-copy version -- 30 copies per region issued by 30 lanes -- was measured
+// slower: the per-lane issue of the uniform-datapath copies costs more than the address arithmetic it saves.)
+__device__ __forceinline__ void gesInitTables(GesShared& gs, int tid) {
+  if (tid < 64) {
+    for (int j = 0; j < 4; j++) {
+      {
+        const int t = tid + 64 * j;
+        unsigned int v = 0;
+        if (t < 200) {
+          const int zr = t >> 1, hi = t & 1;  // hi: rz = 9 <- block +z, voxel z = 0; lo: rz = 0 <- block -z, voxel z = 7
+          const int rx = zr / 10, ry = zr % 10;
+          const int d = (regOff(rx) + 1) * 9 + (regOff(ry) + 1) * 3 + (hi ? 2 : 0);
+          const int off = ((regLoc(rx) * 8 + regLoc(ry)) * 8 + (hi ? 0 : 7)) * 20;
+          v = (unsigned)d | ((unsigned)hi << 5) | ((unsigned)zr << 6) | ((unsigned)off << 13) | (1u << 27);
+        }
+        gs.tz[j][tid] = v;
+      }
+      {
+        const int zr = j * 32 + (tid >> 1);
+        unsigned int v = 0;
+        if (zr < 100) {
+          const int rx = zr / 10, ry = zr % 10;
+          const int d = (regOff(rx) + 1) * 9 + (regOff(ry) + 1) * 3 + 1;
+          const int off = (regLoc(rx) * 8 + regLoc(ry)) * 160 + (tid & 1) * 16;
+          v = (unsigned)d | ((unsigned)zr << 6) | ((unsigned)off << 13) | (1u << 27);
+        }
+        gs.tc[j][tid] = v;
+      }
+      for (int pass = 0; pass < 6; pass++) {
+        const int t = tid + 64 * j;
+        unsigned int v = 0;
+        if (t < 200) {
+          const int axis = pass >> 1, dir = (pass & 1) ? -1 : 1;
+          const int A = axis == 0 ? 9 : (axis == 1 ? 3 : 1), U = axis == 0 ? 3 : 9, W = axis == 2 ? 3 : 1;
+          const int p = t / 100, u = (t % 100) / 10, w = t % 10;
+          const int sa = dir > 0 ? (p ? 8 : 0) : (p ? 9 : 1);  // source coordinate along the axis
+          const int so = dir > 0 ? (p ? 0 : -1) : (p ? 1 : 0);   // block offset of the source along the axis
+          const int da = sa + dir;
+          const int d = 13 + so * A + regOff(u) * U + regOff(w) * W;
+          const int inner = da >= 1 && da <= 8 && u >= 1 && u <= 8 && w >= 1 && w <= 8;
+          const int sw = axis == 0 ? regionWord(sa, u, w) : (axis == 1 ? regionWord(u, sa, w) : regionWord(u, w, sa));
+          const int dw = axis == 0 ? regionWord(da, u, w) : (axis == 1 ? regionWord(u, da, w) : regionWord(u, w, da));
+          v = (unsigned)sw | ((unsigned)dw << 13) | ((unsigned)d << 26) | ((unsigned)inner << 31);
+        }
+        gs.te[pass][j][tid] = v;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void gesGather(const EsdfCtx& c, const GesShared& gs, unsigned int* R, const int* row,
+                                          int lane64) {
+  unsigned int zw[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned int t = gs.tz[j][lane64];
+    zw[j] = 0;
+    if (t >> 27) {
+      const int slot = row[t & 31u], hi = (t >> 5) & 1u, zr = (t >> 6) & 127u;
+      const unsigned char* vox = c.esdf.blocks + (size_t)(slot < 0 ? 0 : slot) * kEsdfBlockBytes + ((t >> 13) & 16383u);
+      if (hi) {
+        cpAsync16(R + kZHiBase + zr * kZCell, vox, slot >= 0);  // words 0..3
+        if (slot >= 0) zw[j] = __ldcg(reinterpret_cast<const unsigned int*>(vox + 16));
+      } else {
+        cpAsync16(R + kZLoBase + zr * kZCell + 4, vox + 4, slot >= 0);  // words 1..4
+        if (slot >= 0) zw[j] = __ldcg(reinterpret_cast<const unsigned int*>(vox));
+      }
+    }
+  }
+  const int half = lane64 & 1;
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const unsigned int t = gs.tc[it][lane64];
+    if (t >> 27) {
+      const int slot = row[t & 31u], zr = (t >> 6) & 127u;
+      const unsigned char* src = c.esdf.blocks + (size_t)(slot < 0 ? 0 : slot) * kEsdfBlockBytes + ((t >> 13) & 16383u);
+      unsigned int* dst = R + zr * 40 + half * 4;
+#pragma unroll
+      for (int j = 0; j < 5; j++) cpAsync16(dst + j * 8, src + j * 32, slot >= 0);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned int t = gs.tz[j][lane64];
+    if (t >> 27) {
+      const int hi = (t >> 5) & 1u, zr = (t >> 6) & 127u;
+      R[hi ? (kZHiBase + zr * kZCell + 4) : (kZLoBase + zr * kZCell + 3)] = zw[j];
+    }
+  }
+  cpAsyncWaitAll();
+}
+
+// updateSingleNeighbor (:602-633) on two voxels in shared memory, split into an operand fetch and the update so
+// that the fetches of a thread's (up to three) pairs of a plane are in flight together.
+struct PairOps {
+  unsigned int e0, e1, e2, e3, e4, n0, n4;
+  unsigned int* nb;
+  bool act;
+};
+__device__ __forceinline__ PairOps pairLoad(unsigned int* R, unsigned int desc, bool act) {
+  PairOps q;
+  q.act = act;
+  q.nb = R + ((desc >> 13) & 8191u);
+  // unconditional fetch (the addresses of an inactive descriptor are valid words of the region): no branch, so the
+  // operands of the lane's four pairs are in flight together
+  const unsigned int* e = R + (desc & 8191u);
+  q.e0 = e[0], q.e1 = e[1], q.e2 = e[2], q.e3 = e[3], q.e4 = e[4];
+  q.n0 = q.nb[0], q.n4 = q.nb[4];
+  return q;
+}
+__device__ __forceinline__ bool pairApply(const PairOps& q, int axis, int direction, float max_sq) {
+  const bool ok = q.act && flagObserved(q.e4) && flagObserved(q.n4) && !flagSite(q.n4) && !(__uint_as_float(q.e0) >= max_sq);
+  const int d0 = (int)q.e1 - (axis == 0 ? direction : 0), d1 = (int)q.e2 - (axis == 1 ? direction : 0),
+            d2 = (int)q.e3 - (axis == 2 ? direction : 0);
+  const float pdist = (float)(d0 * d0 + (d1 * d1 + d2 * d2));
+  if (ok && __uint_as_float(q.n0) > pdist) {
+    q.nb[1] = (unsigned)d0, q.nb[2] = (unsigned)d1, q.nb[3] = (unsigned)d2;
+    q.nb[0] = __float_as_uint(pdist);
+    return true;
+  }
+  return false;
+}
+
+// The six passes of updateLocalNeighborBands (:1323-1386) restricted to the region: +x, -x, +y, -y, +z, -z, each
+// seeing the previous ones. A pass along `axis` has two boundary planes (block -1|0 and block 0|+1) of 10 x 10
+// voxel pairs; a pair is processed iff its SOURCE block is a member of the ring (bit in `mask`). Inside one pass
+// sources and destinations are disjoint planes, so its 200 pairs are independent: each lane owns (up to) four of
+// them -- the same for every candidate, so their shared-memory addresses and source-block indices come from a
+// table built once per launch (the replay is instruction-bound, not latency-bound) -- fetches the operands of the
+// active ones together and then applies them.
+__device__ __forceinline__ bool gesEmulate(const GesShared& gs, unsigned int* R, unsigned int mask, int lane64, int group,
+                                           float max_sq) {
+  bool changed = false;
+#pragma unroll 1
+  for (int pass = 0; pass < 6; pass++) {
+    const int axis = pass >> 1, dir = (pass & 1) ? -1 : 1;
+    const int A = axis == 0 ? 9 : (axis == 1 ? 3 : 1);
+    // source blocks of this pass: offset along the axis in {-1, 0} (dir +) or {0, +1} (dir -)
+    const unsigned int lo = axis == 0 ? 0x000001ffu : (axis == 1 ? 0x001c0e07u : 0x01249249u);  // offset -1 along the axis
+    const unsigned int src_blocks = dir > 0 ? (lo | (lo << A)) : ((lo << A) | (lo << (2 * A)));
+    if (!(mask & src_blocks)) continue;  // group-uniform
+    unsigned int desc[4];
+    PairOps q[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      desc[j] = gs.te[pass][j][lane64];
+      q[j] = pairLoad(R, desc[j], desc[j] != 0u && ((mask >> ((desc[j] >> 26) & 31u)) & 1u));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (pairApply(q[j], axis, dir, max_sq)) changed = changed || (desc[j] >> 31);
+    groupSync(group);
+  }
+  return changed;
+}
+
+__device__ __forceinline__ void copyShadowToLayer(const EsdfCtx& c, int slot, int lane64) {
+  const uint4* src = reinterpret_cast<const uint4*>(c.shadow + (size_t)slot * kEsdfBlockBytes);
+  uint4* dst = reinterpret_cast<uint4*>(c.esdf.blocks + (size_t)slot * kEsdfBlockBytes);
+  uint4 q[kBlockWords / 4 / 64];
+#pragma unroll
+  for (int k = 0; k < kBlockWords / 4 / 64; k++) q[k] = __ldcg(src + lane64 + k * 64);
+#pragma unroll
+  for (int k = 0; k < kBlockWords / 4 / 64; k++) __stcg(dst + lane64 + k * 64, q[k]);
+}
+
+__global__ void __maxnreg__(NVB_WAVE_MAXREG) esdfWaveGesKernel(EsdfCtx c) {
+  extern __shared__ __align__(16) unsigned int smem[];
+  __shared__ WaveShared sh;
+  __shared__ GesShared gs;
+  const int cta = blockIdx.x, nctas = gridDim.x;
+  const int tid = threadIdx.x, group = tid >> 6, lane64 = tid & 63;
+  if (*(volatile int*)c.work_count == 0) return;
+  if (tid == 0) sh.npend = 0;
+  if (tid < kWG) gs.done_n[tid] = 0;
+  if (tid == 0) gs.overflow = 0;
+  gesInitTables(gs, tid);
+  __syncthreads();
+  unsigned int generation = 0;
+  int ring = *(volatile int*)c.ring_id;
+  int* stamp[2] = {c.stamp_a, c.stamp_b};
+  int* list[2] = {c.ring_a, c.ring_b};
+  int* clist[2] = {c.cand_a, c.cand_b};
+  int* ccount = c.ges_counts;      // [parity] candidates of the ring with that parity
+  int* mcount = c.ges_counts + 2;  // [parity] members of the ring with that parity
+  long long swept = 0, faces = 0, rings = 0, n_bar = 0, t_bar = 0, t_work = 0, t0 = globalTimerNs(), t1;
+  unsigned int* R = smem + group * kRegionWords;
+  long long tg = 0, te = 0, ts = 0, ncand = 0, nchg = 0, tq;  // CTA 0 / group 0: gather, emulate, sweep+store time (SM clock cycles: %globaltimer costs ~a round trip per read)
+#define GES_BARRIER()                                                                                           \
+  t1 = globalTimerNs(), t_work += t1 - t0;                                                                      \
+  if (tid == 0 && n_bar < 1000) atomicMax((unsigned long long*)c.phase_max + n_bar, (unsigned long long)(t1 - t0)); \
+  t0 = t1;                                                                                                      \
+  gridBarrier(c.barrier, generation, nctas);                                                                    \
+  t1 = globalTimerNs(), t_bar += t1 - t0, t0 = t1;                                                              \
+  n_bar++;
+  auto roundsOf = [&](int count) { return ((count + nctas - 1) / nctas + kWaveMaxMembers - 1) / kWaveMaxMembers; };
+  for (int pass = 0; pass < 2; pass++) {
+    const int* src = pass ? c.cleared_list : c.upd_list;
+    int n0 = pass ? *(volatile int*)c.cleared_count : *(volatile int*)c.upd_count;
+    if (n0 == 0) continue;
+    int ci = ring & 1;
+    bool initial = true;
+    // ---- large rings: four-phase rings (sweep | x | y | z, member lists with unique append), exactly as in
+    // esdfWaveKernel. A large ring has several candidates per 64-thread group, which the gather-replay below would
+    // process one after the other; here the per-member work is smaller and the four barriers amortise.
+    {
+      auto share = [&](int count) { return (count > cta) ? (count - cta + nctas - 1) / nctas : 0; };
+      int spec = 0;
+      while (n0 > c.ges_switch) {
+        const int ni = ci ^ 1;
+        const int rounds = roundsOf(n0);
+        for (int r = 0; r < rounds; r++) {
+          const int k = loadMembers(sh, src, n0, cta, nctas, r * kWaveMaxMembers, initial ? stamp[ci] : nullptr, ring,
+                                    r == 0 ? spec : 0);
+          sweepMembers(c, sh, k, smem, rounds == 1);
+        }
+        if (cta == 0 && tid == 0) c.ring_count[ni] = 0;  // append counter of ring+1
+        GES_BARRIER()
+        swept += n0;
+#pragma unroll 1
+        for (int axis = 0; axis < 3; axis++) {
+          for (int r = 0; r < rounds; r++) {
+            int k = share(n0);
+            if (rounds > 1) {
+              k = loadMembers(sh, src, n0, cta, nctas, r * kWaveMaxMembers, nullptr, 0, 0);
+              prefetchNeighbors(c, sh, k);
+              __syncthreads();
+            }
+            axisMembers(c, sh, axis, k, stamp[ci], ring, stamp[ni], list[ni], c.ring_count + ni);
+            if (rounds > 1) flushPending(sh, stamp[ni], ring, list[ni], c.ring_count + ni);
+          }
+          if (axis == 2 && rounds == 1) flushPending(sh, stamp[ni], ring, list[ni], c.ring_count + ni);
+          GES_BARRIER()
+        }
+        faces += 6ll * n0;
+        rings++;
+        {
+          const long long idx = (long long)cta + (long long)tid * nctas;
+          int e = 0;
+          if (tid < kSpec && idx < c.esdf.capacity) e = __ldcg(list[ni] + idx);
+          const int n_next = *(volatile int*)(c.ring_count + ni);
+          if (tid < kSpec) sh.members[tid] = e;
+          spec = kSpec;
+          __syncthreads();
+          n0 = n_next;
+        }
+        ring++;
+        ci = ni;
+        src = list[ni];
+        initial = false;
+      }
+      if (n0 == 0) {  // the wavefront died out in the large-ring regime
+        ring++;
+        if (cta == 0 && tid == 0) c.ring_count[0] = c.ring_count[1] = 0;
+        GES_BARRIER()
+        continue;
+      }
+    }
+    // ---- hand-over / initial phase: sweep the current member list in place, stamp it as ring `ring`, register its
+    // neighbours as the candidates of that ring
+    {
+      const int rounds = roundsOf(n0);
+      for (int r = 0; r < rounds; r++) {
+        const int k = loadMembers(sh, src, n0, cta, nctas, r * kWaveMaxMembers, stamp[ci], ring);
+        sweepMembers(c, sh, k, smem, true);
+        for (int q = tid; q < k * 6; q += kWT) {
+          const int item = q / 6;
+          const int nb = item < kNbrCache ? sh.nbr[q] : resolveNeighbor(c, sh.members[item], q % 6);
+          if (nb >= 0 && atomicExch(c.cand_stamp + nb, ring) != ring) clist[ci][atomicAdd(ccount + ci, 1)] = nb;
+        }
+        __syncthreads();
+      }
+    }
+    GES_BARRIER()
+    swept += n0;
+    int M = n0;
+    int K_prev = 0;  // candidates of the previous ring (clist[ni])
+    while (true) {
+      const int ni = ci ^ 1;
+      // ---- phase P: results of the previous ring go from the shadow slab into the layer (nobody reads the layer
+      // now); this ring's candidates and their 27-neighbourhood rows come into shared memory
+      const int K = *(volatile int*)(ccount + ci);
+      const int share = (K > cta) ? (K - cta + nctas - 1) / nctas : 0;
+      {
+        const int kc = share < kGesMaxCand ? share : kGesMaxCand;
+        int myslot = -1;
+        if (tid < kc) myslot = __ldcg(clist[ci] + cta + tid * nctas);  // issued before the copies
+        if (gs.overflow) {
+          // more changed blocks than a group remembers: find them again through the previous ring's candidate
+          // list (a candidate that became a member of ring `ring` is a changed block)
+          for (int j = group; cta + (long long)j * nctas < K_prev; j += kWG) {
+            const int s = __ldcg(clist[ni] + cta + j * nctas);
+            if (__ldcg(stamp[ci] + s) == ring) copyShadowToLayer(c, s, lane64);
+          }
+        } else {
+          for (int j = 0; j < gs.done_n[group]; j++) copyShadowToLayer(c, gs.done_slots[group][j], lane64);
+        }
+        __syncthreads();
+        if (tid < kWG) gs.done_n[tid] = 0;
+        if (tid == 0) gs.overflow = 0;
+        if (tid < kc) gs.cand[tid] = myslot;
+        __syncthreads();
+        for (int q = tid; q < kc * 27; q += kWT) {
+          const int s = gs.cand[q / 27], d = q % 27;
+          int v = __ldcg(c.nbr27 + 27 * s + d);
+          if (v < -1) {  // never linked (block created outside the ESDF update path): resolve through the hash once
+            const int* bi = c.esdf.block_index + 3 * s;
+            v = hashFind(c.esdf.hash, bi[0] + d / 9 - 1, bi[1] + (d / 3) % 3 - 1, bi[2] + d % 3 - 1);
+            c.nbr27[27 * s + d] = v;
+          }
+          gs.rows[q] = v;
+        }
+        if (cta == 0 && tid == 0) ccount[ni] = 0, mcount[ni] = 0;  // filled during the coming phase A
+      }
+      GES_BARRIER()
+      // ---- phase A: every candidate of the ring: gather, replay the six passes, sweep if it changed
+      for (int base = 0; base < share; base += kGesMaxCand) {
+        const int kc = (share - base) < kGesMaxCand ? (share - base) : kGesMaxCand;
+        if (base > 0) {  // further chunks (very large rings only): fetch in place
+          __syncthreads();
+          if (tid < kc) gs.cand[tid] = __ldcg(clist[ci] + cta + (base + tid) * nctas);
+          __syncthreads();
+          for (int q = tid; q < kc * 27; q += kWT) {
+            const int s = gs.cand[q / 27], d = q % 27;
+            int v = __ldcg(c.nbr27 + 27 * s + d);
+            if (v < -1) {
+              const int* bi = c.esdf.block_index + 3 * s;
+              v = hashFind(c.esdf.hash, bi[0] + d / 9 - 1, bi[1] + (d / 3) % 3 - 1, bi[2] + d % 3 - 1);
+              c.nbr27[27 * s + d] = v;
+            }
+            gs.rows[q] = v;
+          }
+          __syncthreads();
+        }
+        for (int i = group; i < kc; i += kWG) {
+          const int slot = gs.cand[i];
+          const int* row = gs.rows + i * 27;
+          // membership of the 27 blocks in this ring (sources of the passes); the loads travel with the gather
+          int st = ring - 1;
+          tq = clock64();
+          if (lane64 < 27 && row[lane64] >= 0) st = __ldcg(stamp[ci] + row[lane64]);
+          gesGather(c, gs, R, row, lane64);
+          const unsigned int m = __ballot_sync(0xffffffffu, lane64 < 27 && st == ring);
+          if (lane64 == 0) gs.mask[group] = m, gs.changed[group] = 0;
+          groupSync(group);
+          tg += clock64() - tq, tq = clock64(), ncand++;
+          const bool ch = gesEmulate(gs, R, gs.mask[group], lane64, group, c.max_sq);
+          if (ch) gs.changed[group] = 1;
+          groupSync(group);
+          te += clock64() - tq, tq = clock64();
+          if (gs.changed[group]) {
+            nchg++;
+            // B is a member of ring+1: tell its face neighbours (candidates of ring+1). The exchange is issued
+            // now and consumed after the sweep.
+            int nb = -1, old = ring + 1;
+            if (lane64 < 6) {
+              const int face = lane64 == 0 ? 22 : (lane64 == 1 ? 4 : (lane64 == 2 ? 16 : (lane64 == 3 ? 10 : (lane64 == 4 ? 14 : 12))));
+              nb = row[face];
+              if (nb >= 0) old = atomicExch(c.cand_stamp + nb, ring + 1);
+            }
+            if (lane64 == 0) {
+              stamp[ni][slot] = ring + 1;
+              atomicAdd(mcount + ni, 1);
+              const int dn = gs.done_n[group];
+              if (dn < kGesDoneMax) gs.done_slots[group][dn] = slot, gs.done_n[group] = dn + 1;
+              else gs.overflow = 1;
+            }
+            int pos = -1;
+            {
+              const int a = lane64 >> 3, b = lane64 & 7;
+              sweepLineRegs(R, regionWord(1, a + 1, b + 1), 400, 0, a, b, 0, c.max_sq);
+              groupSync(group);
+              // the exchange is back by now; the position fetch overlaps the other two axes
+              if (nb >= 0 && old != ring + 1) pos = atomicAdd(ccount + ni, 1);
+              sweepLineRegs(R, regionWord(a + 1, 1, b + 1), 40, a, 0, b, 1, c.max_sq);
+              groupSync(group);
+              sweepLineRegs(R, regionWord(a + 1, b + 1, 1), kEsdfVoxelWords, a, b, 0, 2, c.max_sq);
+              groupSync(group);
+            }
+            if (pos >= 0) clist[ni][pos] = nb;
+            // inner 8x8x8 -> shadow slab
+            uint4* dst = reinterpret_cast<uint4*>(c.shadow + (size_t)slot * kEsdfBlockBytes);
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+              const int r = it * 32 + (lane64 >> 1);  // block row (lx, ly); two lanes share a row
+              const unsigned int* srow = R + (((r >> 3) + 1) * 10 + (r & 7) + 1) * 40 + (lane64 & 1) * 4;
+#pragma unroll
+              for (int j = 0; j < 5; j++) __stcg(dst + r * 10 + (lane64 & 1) + 2 * j, *reinterpret_cast<const uint4*>(srow + j * 8));
+            }
+          }
+          groupSync(group);
+          ts += clock64() - tq;
+        }
+      }
+      GES_BARRIER()
+      const int M_next = *(volatile int*)(mcount + ni);
+      faces += 6ll * M;
+      rings++;
+      swept += M_next;
+      ring++;
+      ci = ni;
+      M = M_next;
+      K_prev = K;
+      if (M == 0) break;
+    }
+    ring++;
+    if (cta == 0 && tid == 0) ccount[0] = ccount[1] = mcount[0] = mcount[1] = 0;
+    GES_BARRIER()
+  }
+#undef GES_BARRIER
+  if (cta == 0 && tid == 0) {
+    *c.ring_id = ring + 1;
+    c.stats[4] = *(volatile int*)c.cleared_count;
+    c.stats[5] = swept, c.stats[6] = faces, c.stats[7] = rings;
+    c.stats[8] = t_bar, c.stats[9] = t_work, c.stats[10] = 0, c.stats[11] = n_bar;
+    long long sum_max = 0;
+    for (int q = 0; q < n_bar && q < 1000; q++) sum_max += (long long)c.phase_max[q];
+    c.stats[12] = sum_max;
+    c.phase_max[3990] = tg, c.phase_max[3991] = te, c.phase_max[3992] = ts, c.phase_max[3993] = ncand, c.phase_max[3994] = nchg;
   }
 }
 
@@ -508,6 +994,21 @@ int esdfPersistentMaxCtas(int num_sms) {
     per_sm = v;
   }
   return per_sm * num_sms;
+}
+
+cudaError_t launchEsdfComputeGes(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches) {
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    cudaFuncSetAttribute(esdfWaveGesKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGesSmemBytes);
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, esdfWaveGesKernel, kWT, kGesSmemBytes) != cudaSuccess) v = 0;
+    per_sm = v;
+  }
+  if (per_sm <= 0) return cudaErrorLaunchOutOfResources;
+  EsdfCtx cc = c;
+  void* args[] = {&cc};
+  (*launches)++;
+  return cudaLaunchCooperativeKernel((const void*)esdfWaveGesKernel, dim3(num_sms), dim3(kWT), args, kGesSmemBytes, stream);
 }
 
 cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches) {

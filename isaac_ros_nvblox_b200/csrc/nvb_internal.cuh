@@ -323,11 +323,20 @@ struct EsdfCtx {
   int* ring_a;
   int* ring_b;
   int* ring_count;     // 2 ints
+  int* tail_state;     // 2 ints: rings advanced / final member count of a single-CTA tail episode
   int* stamp_a;        // per ESDF slot
   int* stamp_b;
   int* ring_id;        // device: monotonically increasing ring id
   // Ownership-based wavefront (persistent kernel): no lists, every CTA scans the slots it owns.
   int* nbr;           // 6 ints per ESDF slot: slot of the +x,-x,+y,-y,+z,-z neighbour, -1 none, < -1 unknown
+  int* nbr27;         // 27 ints per ESDF slot: slot of the block at offset (dx,dy,dz), entry (dx+1)*9+(dy+1)*3+(dz+1);
+                      // -1 none, < -1 unknown (never linked)
+  unsigned char* shadow;  // second ESDF slab (same slot indexing): results of a ring wait here until all reads are done
+  int* cand_a;        // candidate lists of the gather-emulate-sweep rings (ping-pong by ring parity)
+  int* cand_b;
+  int ges_switch;     // rings with more members than this run as four-phase rings
+  int* cand_stamp;    // per slot: == ring  <=> registered as a candidate (neighbour of a member) of that ring
+  int* ges_counts;    // 4 ints: candidate count [2], member count [2] (ping-pong by ring parity)
   int* seed_upd;      // per slot: == update_seq  <=> block has sites in this update (computeEsdf #1 seeds)
   int* seed_clr;      // per slot: == *cleared_seq <=> member of the persistent cleared list (computeEsdf #2 seeds)
   int* cleared_seq;   // device: update_seq of the last update whose clear pass ran
@@ -352,6 +361,7 @@ void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots
 void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream);
 void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream);
 // Whole wavefront (both computeEsdf calls) in one cooperative launch. Returns cudaError.
+cudaError_t launchEsdfComputeGes(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
 cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
 // Reference-like driver: one launch per phase, host reads the ring counter.
 cudaError_t runEsdfComputeHostLoop(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);

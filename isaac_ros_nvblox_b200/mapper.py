@@ -277,7 +277,7 @@ class Mapper:
             o.tsdf_capacity_blocks = int(tsdf_capacity_blocks)
         if esdf_capacity_blocks:
             o.esdf_capacity_blocks = int(esdf_capacity_blocks)
-        o.esdf_persistent = 1 if esdf_persistent else 0
+        o.esdf_persistent = int(esdf_persistent)  # 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
         o.projective_layer_type = int(projective_layer_type)
         self._projective_layer_type = int(projective_layer_type)
         h = C.c_void_p(0)

@@ -23,4 +23,5 @@ for i, (_, T) in enumerate(seq):
         arr = (C.c_int64 * 4000)()
         m._L.nvb_mapper_debug_phase_max(m._h, arr, 4000)
         print("   per-phase slowest-CTA work (ns):", [int(arr[q]) for q in range(min(n, 80))])
+        print("   GES cta0/group0 (gather cycles, emulate cycles, sweep+store cycles, candidates, changed):", [int(arr[q]) for q in range(3990, 3995)])
         print("   sweep phases (total, scan, load+sweep+store, max k):", [(int(arr[q]), int(arr[1000+q]), int(arr[2000+q]), int(arr[3000+q])) for q in range(min(n, 80)) if arr[3000+q] or arr[2000+q]])

@@ -41,6 +41,34 @@ __device__ __forceinline__ void barR(unsigned* bar, unsigned& gen, unsigned n) {
   }
   __syncthreads();
 }
+// fence + red + PIPELINED polling: kPoll loads in flight, issued ~RT/kPoll apart, so the release is seen
+// ~one-way latency after it lands instead of on average half a round trip later
+template <int kPoll>
+__device__ __forceinline__ void barP(unsigned* bar, unsigned& gen, unsigned n, unsigned gap_ns) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    gen++;
+    const unsigned target = gen * n;
+    __threadfence();
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned v[kPoll];
+#pragma unroll
+    for (int i = 0; i < kPoll; i++) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[i]) : "l"(bar) : "memory");
+      if (i + 1 < kPoll) __nanosleep(gap_ns);
+    }
+    bool done = false;
+    while (!done) {
+#pragma unroll
+      for (int i = 0; i < kPoll; i++) {
+        if (v[i] >= target) { done = true; break; }
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[i]) : "l"(bar) : "memory");
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
 template <int V>
 __global__ void kbar(unsigned* bar, int iters, int work, float* sink) {
   unsigned gen = 0;
@@ -52,6 +80,9 @@ __global__ void kbar(unsigned* bar, int iters, int work, float* sink) {
     if (V == 1) barB(bar, gen, gridDim.x);
     if (V == 2) g.sync();
     if (V == 3) barR(bar, gen, gridDim.x);
+    if (V == 4) barP<4>(bar, gen, gridDim.x, 120);
+    if (V == 5) barP<2>(bar, gen, gridDim.x, 250);
+    if (V == 6) barP<8>(bar, gen, gridDim.x, 60);
   }
   if (acc == 12345.f) *sink = acc;
 }
@@ -89,11 +120,11 @@ float run(int grid, int threads, int iters) {
 int main() {
   const int iters = 2000;
   int grids[] = {148, 74, 32, 16, 8, 296};
-  printf("grid threads  A(fence+atom+volatile)  B(red.release+ld.acquire)  C(cg grid.sync)  R(relaxed, lower bound)   [us per barrier]\n");
+  printf("grid threads  A(fence+atom+volatile)  B(red.release+ld.acquire)  C(cg grid.sync)  R(relaxed, lower bound)  P4 P2 P8 (pipelined polls)   [us per barrier]\n");
   for (int g : grids)
     for (int t : {256, 64}) {
-      printf("%4d %4d   %8.3f   %8.3f   %8.3f   %8.3f\n", g, t, run<0>(g, t, iters), run<1>(g, t, iters), run<2>(g, t, iters),
-             run<3>(g, t, iters));
+      printf("%4d %4d   %8.3f   %8.3f   %8.3f   %8.3f   %8.3f %8.3f %8.3f\n", g, t, run<0>(g, t, iters), run<1>(g, t, iters),
+             run<2>(g, t, iters), run<3>(g, t, iters), run<4>(g, t, iters), run<5>(g, t, iters), run<6>(g, t, iters));
     }
   float* sink;
   cudaMalloc(&sink, 4);

@@ -290,6 +290,28 @@ def test_esdf_incremental_sequence(gpu, persistent):
     m.close()
 
 
+@pytest.mark.parametrize("switch", [0, 40, 160, 100000])
+def test_esdf_gather_replay_wavefront(gpu, monkeypatch, switch):
+    """esdf_persistent=2: rings with more than `switch` members run as four-phase rings, the others as gather-replay
+    rings (every candidate block replays the six face passes on its one-voxel halo). Same results, bit for bit."""
+    monkeypatch.setenv("NVB_GES_SWITCH", str(switch))
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:6], noise_sigma_rel=0.005, seed=11)
+    m, o = _run_pair(0.05, frames, cam, ocam, esdf=True, mapper_kw=dict(esdf_persistent=2))
+    s_gpu, s_cpu = m.esdf_integrator().last_stats(), o.esdf_stats()
+    for k in ("marked", "with_sites", "to_clear", "cleared", "swept", "face_passes", "rings"):
+        assert s_gpu[k] == s_cpu[k], (k, s_gpu, s_cpu)
+    m.close()
+
+
+def test_esdf_gather_replay_640x480_with_growth(gpu):
+    cs, cam, ocam = cameras()
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(80)[:5])
+    m, _ = _run_pair(0.05, frames, cam, ocam, esdf=True, check_every_frame=False,
+                     mapper_kw=dict(esdf_persistent=2, tsdf_capacity_blocks=1024, esdf_capacity_blocks=1024))
+    m.close()
+
+
 def test_esdf_640x480_5cm_sequence(gpu):
     cs, cam, ocam = cameras()
     frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(80)[:4])
