@@ -54,7 +54,8 @@ struct NvbMapper {
   // The ESDF wavefront only touches the ESDF layer: it runs on its own stream so that the next
   // frame's raycast / compaction / TSDF update overlaps it.
   cudaStream_t esdf_stream = nullptr;
-  cudaEvent_t esdf_ready = nullptr;  // mark + clear done on `stream`
+  cudaEvent_t esdf_ready = nullptr;  // TSDF chain of the update done on `stream`
+  cudaEvent_t mark_done = nullptr;   // allocate + mark done on `esdf_stream`
   cudaEvent_t esdf_done = nullptr;   // wavefront done on `esdf_stream`
   bool esdf_in_flight = false;
   float voxel_size = 0.05f, block_size = 0.4f;
@@ -685,37 +686,49 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
   EsdfCtx c = makeEsdfCtx(m);
   c.tracker_dirty = from_tracker ? m->dirty : nullptr;
   c.tracker_todo_count = from_tracker ? m->todo_count : nullptr;
-  // the previous wavefront still owns the ESDF scratch (counters, stamps, barrier)
-  NVB_CUDA(joinEsdf(m));
-  beginStage(m, 3);
-  if (from_tracker) {
-    launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, m->stream);
-    m->launches += 1;
-  } else {
-    launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, m->stream);
-    m->launches += 1;
-  }
-  launchEsdfMark(c, upper, m->num_sms, m->stream);
-  m->launches++;
-  endStage(m);
-  beginStage(m, 4);
-  launchEsdfClear(c, m->esdf.capacity, m->num_sms, m->stream);
-  m->launches++;
-  endStage(m);
   int launches = 0;
   cudaError_t e;
   if (m->esdf_persistent) {
-    NVB_CUDA(cudaEventRecord(m->esdf_ready, m->stream));
-    NVB_CUDA(cudaStreamWaitEvent(m->esdf_stream, m->esdf_ready, 0));
-    beginStageOn(m, 5, m->esdf_stream);
-    e = m->esdf_persistent == 2 ? launchEsdfComputeGes(c, m->num_sms, m->esdf_stream, &launches)
-                                : launchEsdfComputePersistent(c, m->num_sms, m->esdf_stream, &launches);
-    endStageOn(m, m->esdf_stream);
+    // The whole ESDF chain (allocate, mark, clear, wavefront) runs back to back on the side stream; the frame's
+    // critical path has no cross-stream hand-over. `stream` only waits for the mark kernel: after it nothing on
+    // the side stream reads the projective layer or the tracker, so the next frame's raycast / compaction /
+    // TSDF update overlaps the clear pass and the wavefront. (The previous wavefront is ordered before this
+    // chain by the side stream itself.)
+    cudaStream_t es = m->esdf_stream;
+    NVB_CUDA(cudaEventRecord(m->esdf_ready, m->stream));  // projective layer + tracker of this update are final
+    NVB_CUDA(cudaStreamWaitEvent(es, m->esdf_ready, 0));
+    beginStageOn(m, 3, es);
+    if (from_tracker) launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, es);
+    else launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, es);
+    launchEsdfMark(c, upper, m->num_sms, es);
+    m->launches += 2;
+    endStageOn(m, es);
+    NVB_CUDA(cudaEventRecord(m->mark_done, es));
+    NVB_CUDA(cudaStreamWaitEvent(m->stream, m->mark_done, 0));
+    beginStageOn(m, 4, es);
+    launchEsdfClear(c, m->esdf.capacity, m->num_sms, es);
+    m->launches++;
+    endStageOn(m, es);
+    beginStageOn(m, 5, es);
+    e = m->esdf_persistent == 2 ? launchEsdfComputeGes(c, m->num_sms, es, &launches)
+                                : launchEsdfComputePersistent(c, m->num_sms, es, &launches);
+    endStageOn(m, es);
     if (e == cudaSuccess) {
-      NVB_CUDA(cudaEventRecord(m->esdf_done, m->esdf_stream));
+      NVB_CUDA(cudaEventRecord(m->esdf_done, es));
       m->esdf_in_flight = true;
     }
   } else {
+    NVB_CUDA(joinEsdf(m));
+    beginStage(m, 3);
+    if (from_tracker) launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, m->stream);
+    else launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, m->stream);
+    launchEsdfMark(c, upper, m->num_sms, m->stream);
+    m->launches += 2;
+    endStage(m);
+    beginStage(m, 4);
+    launchEsdfClear(c, m->esdf.capacity, m->num_sms, m->stream);
+    m->launches++;
+    endStage(m);
     beginStage(m, 5);
     e = runEsdfComputeHostLoop(c, m->num_sms, m->stream, &launches);
     endStage(m);
@@ -812,6 +825,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   NVB_CUDA(cudaStreamCreateWithFlags(&m->esdf_stream, cudaStreamNonBlocking));
   NVB_CUDA(cudaEventCreateWithFlags(&m->esdf_ready, cudaEventDisableTiming));
   NVB_CUDA(cudaEventCreateWithFlags(&m->esdf_done, cudaEventDisableTiming));
+  NVB_CUDA(cudaEventCreateWithFlags(&m->mark_done, cudaEventDisableTiming));
   const int tcap = opts->tsdf_capacity_blocks > 0 ? opts->tsdf_capacity_blocks : kDefaultCapacity;
   const int ecap = std::max(opts->esdf_capacity_blocks > 0 ? opts->esdf_capacity_blocks : kDefaultCapacity, tcap);
   int rc;
@@ -857,7 +871,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   syncAll(m);
   cudaStreamSynchronize(m->copy_stream);
   collectStages(m);
-  cudaEventDestroy(m->esdf_ready), cudaEventDestroy(m->esdf_done);
+  cudaEventDestroy(m->esdf_ready), cudaEventDestroy(m->esdf_done), cudaEventDestroy(m->mark_done);
   cudaStreamDestroy(m->esdf_stream);
   freeLayer(&m->tsdf), freeLayer(&m->esdf);
   cudaFree(m->bits), cudaFree(m->frame_blocks), cudaFree(m->tile_state), cudaFree(m->ticket);

@@ -69,6 +69,52 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
   c.work[i] = make_int4(eslot, tslot, was_new ? 1 : 0, 0);
 }
 
+// Per-CTA bookkeeping of the mark kernels: which of this CTA's blocks have sites / lost sites, and the AABB of the
+// latter. Kept in shared memory and published once per CTA (two atomicAdds + six atomicMin/Max per CTA instead of
+// per block: the returning atomics were 1.4 us of dependent L2 round trips per block on thread 0's critical path).
+constexpr int kMarkLocalMax = 64;
+struct MarkLocal {
+  int upd[kMarkLocalMax];
+  int clr[kMarkLocalMax];
+  int nu, nc;
+  int aabb[6];
+};
+__device__ __forceinline__ void markLocalInit(MarkLocal& ml) {
+  ml.nu = ml.nc = 0;
+  ml.aabb[0] = ml.aabb[1] = ml.aabb[2] = INT32_MAX;
+  ml.aabb[3] = ml.aabb[4] = ml.aabb[5] = INT32_MIN;
+}
+// thread 0 only
+__device__ __forceinline__ void markLocalFlush(const EsdfCtx& c, MarkLocal& ml) {
+  if (ml.nu) {
+    const int base = atomicAdd(c.upd_count, ml.nu);
+    for (int i = 0; i < ml.nu; i++) c.upd_list[base + i] = ml.upd[i];
+  }
+  if (ml.nc) {
+    const int base = atomicAdd(c.clr_count, ml.nc);
+    for (int i = 0; i < ml.nc; i++) c.clr_list[base + i] = ml.clr[i];
+    atomicMin(c.clr_aabb + 0, ml.aabb[0]), atomicMin(c.clr_aabb + 1, ml.aabb[1]), atomicMin(c.clr_aabb + 2, ml.aabb[2]);
+    atomicMax(c.clr_aabb + 3, ml.aabb[3]), atomicMax(c.clr_aabb + 4, ml.aabb[4]), atomicMax(c.clr_aabb + 5, ml.aabb[5]);
+  }
+  markLocalInit(ml);
+}
+// thread 0 only
+__device__ __forceinline__ void markLocalRecord(const EsdfCtx& c, MarkLocal& ml, int slot, bool updated, bool cleared) {
+  if (updated) {
+    if (ml.nu == kMarkLocalMax) markLocalFlush(c, ml);
+    ml.upd[ml.nu++] = slot;
+    c.seed_upd[slot] = c.update_seq;
+  }
+  if (cleared) {
+    if (ml.nc == kMarkLocalMax) markLocalFlush(c, ml);
+    ml.clr[ml.nc++] = slot;
+    const int* bi = c.esdf.block_index + 3 * slot;
+    const int x = bi[0], y = bi[1], z = bi[2];
+    ml.aabb[0] = min(ml.aabb[0], x), ml.aabb[1] = min(ml.aabb[1], y), ml.aabb[2] = min(ml.aabb[2], z);
+    ml.aabb[3] = max(ml.aabb[3], x), ml.aabb[4] = max(ml.aabb[4], y), ml.aabb[5] = max(ml.aabb[5], z);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // markAllSitesKernel + updateEsdfVoxelToChanges with TsdfSiteFunctor
 // (esdf_integrator.cu:113-138, 401-540).
@@ -76,7 +122,9 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
 __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
   __shared__ __align__(16) unsigned int s[kBlockWords];
   __shared__ int s_flags[3];  // updated, cleared, changed
+  __shared__ MarkLocal ml;
   const int tid = threadIdx.x;
+  if (tid == 0) markLocalInit(ml);
   const int n = *c.work_count;
   if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;  // list consumed by the allocate kernel
   for (int item = blockIdx.x; item < n; item += gridDim.x) {
@@ -144,24 +192,14 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
     if (s_flags[2]) {
       for (int k = tid; k < kBlockWords / 4; k += kThreads) gblk[k] = reinterpret_cast<uint4*>(s)[k];
     }
-    if (tid == 0) {
-      if (s_flags[0]) {
-        c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
-        c.seed_upd[w.x] = c.update_seq;
-      }
-      if (s_flags[1]) {
-        c.clr_list[atomicAdd(c.clr_count, 1)] = w.x;
-        const int* bi = c.esdf.block_index + 3 * w.x;
-        atomicMin(c.clr_aabb + 0, bi[0]), atomicMin(c.clr_aabb + 1, bi[1]), atomicMin(c.clr_aabb + 2, bi[2]);
-        atomicMax(c.clr_aabb + 3, bi[0]), atomicMax(c.clr_aabb + 4, bi[1]), atomicMax(c.clr_aabb + 5, bi[2]);
-      }
-    }
+    if (tid == 0) markLocalRecord(c, ml, w.x, s_flags[0] != 0, s_flags[1] != 0);
     __syncthreads();
   }
   // Last CTA out: if this update has blocks to clear, the persistent "cleared"
   // list is about to be rewritten (clearAllInvalid resizes it, :1620); otherwise it
   // keeps the previous call's content (:242-257).
   if (tid == 0) {
+    markLocalFlush(c, ml);
     __threadfence();
     if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
       __threadfence();
@@ -184,7 +222,9 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
 __global__ void __launch_bounds__(kThreads) esdfMarkOccupancyKernel(EsdfCtx c) {
   __shared__ __align__(16) unsigned int s[kBlockWords];
   __shared__ int s_flags[3];  // updated, cleared, changed
+  __shared__ MarkLocal ml;
   const int tid = threadIdx.x;
+  if (tid == 0) markLocalInit(ml);
   const int n = *c.work_count;
   if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;
   for (int item = blockIdx.x; item < n; item += gridDim.x) {
@@ -252,21 +292,11 @@ __global__ void __launch_bounds__(kThreads) esdfMarkOccupancyKernel(EsdfCtx c) {
     if (s_flags[2]) {
       for (int k = tid; k < kBlockWords / 4; k += kThreads) gblk[k] = reinterpret_cast<uint4*>(s)[k];
     }
-    if (tid == 0) {
-      if (s_flags[0]) {
-        c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
-        c.seed_upd[w.x] = c.update_seq;
-      }
-      if (s_flags[1]) {
-        c.clr_list[atomicAdd(c.clr_count, 1)] = w.x;
-        const int* bi = c.esdf.block_index + 3 * w.x;
-        atomicMin(c.clr_aabb + 0, bi[0]), atomicMin(c.clr_aabb + 1, bi[1]), atomicMin(c.clr_aabb + 2, bi[2]);
-        atomicMax(c.clr_aabb + 3, bi[0]), atomicMax(c.clr_aabb + 4, bi[1]), atomicMax(c.clr_aabb + 5, bi[2]);
-      }
-    }
+    if (tid == 0) markLocalRecord(c, ml, w.x, s_flags[0] != 0, s_flags[1] != 0);
     __syncthreads();
   }
   if (tid == 0) {
+    markLocalFlush(c, ml);
     __threadfence();
     if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
       __threadfence();
@@ -303,7 +333,9 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
   __shared__ __align__(8) uint64_t s_bar[kMarkStages];
   __shared__ int4 s_work[kMarkStages];
   __shared__ int s_flags[3];  // updated, cleared, changed
+  __shared__ MarkLocal ml;
   const int tid = threadIdx.x;
+  if (tid == 0) markLocalInit(ml);
   const int n = *c.work_count;
   if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;  // list consumed by the allocate kernel
   const int my_count = (n > (int)blockIdx.x) ? (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -403,21 +435,13 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
         tma::bulkStore(c.esdf.blocks + (size_t)w.x * kEsdfBlockBytes, st[s].esdf, kEsdfBlockBytes);
         tma::bulkCommit();
       }
-      if (s_flags[0]) {
-        c.upd_list[atomicAdd(c.upd_count, 1)] = w.x;
-        c.seed_upd[w.x] = c.update_seq;
-      }
-      if (s_flags[1]) {
-        c.clr_list[atomicAdd(c.clr_count, 1)] = w.x;
-        const int* bi = c.esdf.block_index + 3 * w.x;
-        atomicMin(c.clr_aabb + 0, bi[0]), atomicMin(c.clr_aabb + 1, bi[1]), atomicMin(c.clr_aabb + 2, bi[2]);
-        atomicMax(c.clr_aabb + 3, bi[0]), atomicMax(c.clr_aabb + 4, bi[1]), atomicMax(c.clr_aabb + 5, bi[2]);
-      }
+      markLocalRecord(c, ml, w.x, s_flags[0] != 0, s_flags[1] != 0);
     }
     __syncthreads();
   }
   if (tid == 0) {
     tma::bulkWait<0>();  // all write-backs performed before this CTA reports "done"
+    markLocalFlush(c, ml);
     __threadfence();
     if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
       __threadfence();
@@ -438,13 +462,29 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
 // (geometry/bounding_spheres.cpp:76-91, bounding_boxes.cpp:20-27);
 // clearAllInvalidKernel (:1522-1585) per candidate.
 // ---------------------------------------------------------------------------
+constexpr int kClearMaxCand = 256;  // candidates of one CTA per selection round
+__device__ __forceinline__ void clearPrefetch(const EsdfCtx& c, unsigned int* sblk, int* snb, int slot, int tid) {
+  const unsigned char* g = c.esdf.blocks + (size_t)slot * kEsdfBlockBytes;
+  for (int k = tid; k < kBlockWords / 4; k += kThreads) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(sblk + 4 * k);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g + 16 * k) : "memory");
+  }
+  if (tid < 27) {  // the 3x3x3 block neighbourhood (most parents live there): one row of the neighbour table
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(snb + tid);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(c.nbr27 + 27 * slot + tid) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
-  __shared__ __align__(16) unsigned int s[kBlockWords];
-  __shared__ int s_any;
-  __shared__ int s_nb[27];  // slots of the 3x3x3 block neighbourhood (most parents live there)
+  __shared__ __align__(16) unsigned int s_blk[2][kBlockWords];
+  __shared__ int s_nb[2][32];
+  __shared__ int s_cand[kClearMaxCand];
+  __shared__ int s_done[kClearMaxCand];
+  __shared__ int s_ncand, s_ndone, s_any;
   const int nclr = *c.clr_count;
   if (nclr == 0) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nblocks = *c.esdf.count < c.esdf.capacity ? *c.esdf.count : c.esdf.capacity;
   const float bs = c.block_size;
   float amin[3], amax[3];
@@ -453,90 +493,119 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
     amin[a] = (float)c.clr_aabb[a] * bs;
     amax[a] = ((float)c.clr_aabb[3 + a] + 1.0f) * bs;
   }
-  for (int slot = blockIdx.x; slot < nblocks; slot += gridDim.x) {
-    const int bx = c.esdf.block_index[3 * slot], by = c.esdf.block_index[3 * slot + 1],
-              bz = c.esdf.block_index[3 * slot + 2];
-    const int bi[3] = {bx, by, bz};
-    // AlignedBox::exteriorDistance(box) > radius -> skip
-    float d2 = 0.0f;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      const float lo = (float)bi[a] * bs, hi = ((float)bi[a] + 1.0f) * bs;
-      if (amin[a] > hi) {
-        const float aux = amin[a] - hi;
-        d2 += aux * aux;
-      } else if (lo > amax[a]) {
-        const float aux = lo - amax[a];
-        d2 += aux * aux;
-      }
-    }
-    if (sqrtf(d2) > c.max_esdf_distance_m) continue;
-    if (tid == 0) {
-      s_any = 0;
-      atomicAdd((unsigned long long*)&c.stats[3], 1ull);
-    }
-    // the block load and the 27 neighbourhood probes are issued together
-    if (tid >= 32 && tid < 32 + 27) {
-      const int q = tid - 32;
-      const int dx = q % 3 - 1, dy = (q / 3) % 3 - 1, dz = q / 9 - 1;
-      s_nb[q] = (q == 13) ? slot : hashFind(c.esdf.hash, bx + dx, by + dy, bz + dz);
-    }
-    unsigned int* gw = esdfBlockPtr(c.esdf, slot);
-    const uint4* gblk = reinterpret_cast<const uint4*>(gw);
-    for (int k = tid; k < kBlockWords / 4; k += kThreads) reinterpret_cast<uint4*>(s)[k] = gblk[k];
+  long long ncand_total = 0;
+  // Slots are dealt round-robin over the CTAs (recently allocated = high slots are the likely candidates);
+  // one selection round tests 256 of this CTA's slots at once, one thread per slot.
+  for (long long first = blockIdx.x; first < nblocks; first += (long long)gridDim.x * kThreads) {
+    if (tid == 0) s_ncand = 0, s_ndone = 0;
     __syncthreads();
-    bool any = false;
+    const long long slot_ll = first + (long long)tid * gridDim.x;
+    bool is_cand = false;
+    if (slot_ll < nblocks) {
+      const int* bi = c.esdf.block_index + 3 * slot_ll;
+      const int b3[3] = {bi[0], bi[1], bi[2]};
+      // AlignedBox::exteriorDistance(box) > radius -> skip
+      float d2 = 0.0f;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int v = tid + h * kThreads;
-      const unsigned int* e = s + v * kEsdfVoxelWords;
-      const unsigned int fl = e[4];
-      const int p[3] = {(int)e[1], (int)e[2], (int)e[3]};
-      if (flagObserved(fl) && !flagSite(fl) && (p[0] != 0 || p[1] != 0 || p[2] != 0)) {
-        // getBlockAndVoxelIndexFromOffset (:1498-1520): C++ '/' and '%' truncate toward zero.
-        const int vi[3] = {v >> 6, (v >> 3) & 7, v & 7};
-        int nb[3], nv[3];
+      for (int a = 0; a < 3; a++) {
+        const float lo = (float)b3[a] * bs, hi = ((float)b3[a] + 1.0f) * bs;
+        if (amin[a] > hi) {
+          const float aux = amin[a] - hi;
+          d2 += aux * aux;
+        } else if (lo > amax[a]) {
+          const float aux = lo - amax[a];
+          d2 += aux * aux;
+        }
+      }
+      is_cand = !(sqrtf(d2) > c.max_esdf_distance_m);
+    }
+    const unsigned int ballot = __ballot_sync(0xffffffffu, is_cand);
+    int wbase = 0;
+    if (lane == 0 && ballot) wbase = atomicAdd(&s_ncand, __popc(ballot));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (is_cand) s_cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = (int)slot_ll;
+    __syncthreads();
+    const int ncand = s_ncand;
+    ncand_total += ncand;
+    // Candidates one after the other; the next one's block and neighbour row are already on their way.
+    if (ncand > 0) clearPrefetch(c, s_blk[0], s_nb[0], s_cand[0], tid);
+    for (int i = 0; i < ncand; i++) {
+      const int buf = i & 1;
+      const int slot = s_cand[i];
+      if (i + 1 < ncand) {
+        clearPrefetch(c, s_blk[buf ^ 1], s_nb[buf ^ 1], s_cand[i + 1], tid);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      if (tid == 0) s_any = 0;
+      __syncthreads();
+      const unsigned int* s = s_blk[buf];
+      const int* nbrow = s_nb[buf];
+      unsigned int* gw = esdfBlockPtr(c.esdf, slot);
+      const int bx = c.esdf.block_index[3 * slot], by = c.esdf.block_index[3 * slot + 1], bz = c.esdf.block_index[3 * slot + 2];
+      bool any = false;
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-          nb[a] = p[a] / kVps;  // block offset (relative)
-          nv[a] = vi[a] + p[a] % kVps;
-          if (nv[a] >= kVps) {
-            nv[a] -= kVps;
-            nb[a]++;
-          } else if (nv[a] < 0) {
-            nv[a] += kVps;
-            nb[a]--;
+      for (int h = 0; h < 2; h++) {
+        const int v = tid + h * kThreads;
+        const unsigned int* e = s + v * kEsdfVoxelWords;
+        const unsigned int fl = e[4];
+        const int p[3] = {(int)e[1], (int)e[2], (int)e[3]};
+        if (flagObserved(fl) && !flagSite(fl) && (p[0] != 0 || p[1] != 0 || p[2] != 0)) {
+          // getBlockAndVoxelIndexFromOffset (:1498-1520): C++ '/' and '%' truncate toward zero.
+          const int vi[3] = {v >> 6, (v >> 3) & 7, v & 7};
+          int nb[3], nv[3];
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            nb[a] = p[a] / kVps;  // block offset (relative)
+            nv[a] = vi[a] + p[a] % kVps;
+            if (nv[a] >= kVps) {
+              nv[a] -= kVps;
+              nb[a]++;
+            } else if (nv[a] < 0) {
+              nv[a] += kVps;
+              nb[a]--;
+            }
+          }
+          const int pv = (nv[0] * kVps + nv[1]) * kVps + nv[2];
+          bool parent_is_site = false;
+          if (nb[0] == 0 && nb[1] == 0 && nb[2] == 0) {
+            parent_is_site = flagSite(s[pv * kEsdfVoxelWords + 4]);
+          } else {
+            int ps = -2;
+            if (nb[0] >= -1 && nb[0] <= 1 && nb[1] >= -1 && nb[1] <= 1 && nb[2] >= -1 && nb[2] <= 1)
+              ps = nbrow[(nb[0] + 1) * 9 + (nb[1] + 1) * 3 + (nb[2] + 1)];
+            if (ps < -1) ps = hashFind(c.esdf.hash, bx + nb[0], by + nb[1], bz + nb[2]);  // far parent / row never linked
+            // is_site is never written by this kernel: reading it from a block another
+            // CTA is processing is race-free.
+            if (ps >= 0) parent_is_site = flagSite(__ldcg(esdfBlockPtr(c.esdf, ps) + pv * kEsdfVoxelWords + 4));
+          }
+          if (!parent_is_site) {
+            unsigned int* g = gw + v * kEsdfVoxelWords;
+            g[0] = __float_as_uint(c.max_sq), g[1] = 0u, g[2] = 0u, g[3] = 0u;
+            any = true;
           }
         }
-        const int pv = (nv[0] * kVps + nv[1]) * kVps + nv[2];
-        bool parent_is_site = false;
-        if (nb[0] == 0 && nb[1] == 0 && nb[2] == 0) {
-          parent_is_site = flagSite(s[pv * kEsdfVoxelWords + 4]);
-        } else {
-          int ps;
-          if (nb[0] >= -1 && nb[0] <= 1 && nb[1] >= -1 && nb[1] <= 1 && nb[2] >= -1 && nb[2] <= 1)
-            ps = s_nb[(nb[0] + 1) + 3 * (nb[1] + 1) + 9 * (nb[2] + 1)];
-          else
-            ps = hashFind(c.esdf.hash, bx + nb[0], by + nb[1], bz + nb[2]);
-          // is_site is never written by this kernel: reading it from a block another
-          // CTA is processing is race-free.
-          if (ps >= 0) parent_is_site = flagSite(esdfBlockPtr(c.esdf, ps)[pv * kEsdfVoxelWords + 4]);
-        }
-        if (!parent_is_site) {
-          unsigned int* g = gw + v * kEsdfVoxelWords;
-          g[0] = __float_as_uint(c.max_sq), g[1] = 0u, g[2] = 0u, g[3] = 0u;
-          any = true;
-        }
       }
+      if (any) s_any = 1;
+      __syncthreads();
+      if (tid == 0 && s_any) {
+        s_done[s_ndone++] = slot;
+        c.seed_clr[slot] = c.update_seq;
+      }
+      // (the next iteration's __syncthreads orders s_any / the buffers)
     }
-    if (any) s_any = 1;
     __syncthreads();
-    if (tid == 0 && s_any) {
-      c.cleared_list[atomicAdd(c.cleared_count, 1)] = slot;
-      c.seed_clr[slot] = c.update_seq;
+    // publish this round's cleared blocks: one atomicAdd per CTA
+    if (s_ndone > 0) {
+      __shared__ int s_base;
+      if (tid == 0) s_base = atomicAdd(c.cleared_count, s_ndone);
+      __syncthreads();
+      for (int i = tid; i < s_ndone; i += kThreads) c.cleared_list[s_base + i] = s_done[i];
     }
     __syncthreads();
   }
+  if (tid == 0 && ncand_total) atomicAdd((unsigned long long*)&c.stats[3], (unsigned long long)ncand_total);
 }
 
 // ---------------------------------------------------------------------------

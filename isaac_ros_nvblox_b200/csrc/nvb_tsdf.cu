@@ -16,6 +16,8 @@
 // re-uploads every frame). Unchanged words are not written back.
 #include "nvb_internal.cuh"
 
+#include <cstdlib>
+
 namespace nvb {
 
 namespace {
@@ -216,6 +218,19 @@ __global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant
 
 }  // namespace
 
+// Resident CTAs per SM of the projective update kernels. 8 x 256 threads fill an SM's thread slots, which keeps the
+// cooperative ESDF wavefront of the previous frame (side stream, one 256-thread CTA per SM) from starting until
+// this kernel drains; NVB_TSDF_CTAS_PER_SM is the A/B switch for that trade-off.
+static int projectiveCtasPerSm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVB_TSDF_CTAS_PER_SM");
+    v = e ? atoi(e) : 8;
+    if (v < 1 || v > 8) v = 8;
+  }
+  return v;
+}
+
 void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* tsdf_blocks,
                          const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
                          const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p, int num_sms,
@@ -235,8 +250,9 @@ void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsig
   a.num_words = num_words;
   // 8 resident 256-thread CTAs per SM (2048 threads): one full wave.
   // the lens-distortion variant is a separate instantiation so the pinhole path keeps its register budget
-  if (cam.has_distortion) tsdfIntegrateKernel<true><<<num_sms * 8, 256, 0, stream>>>(a);
-  else tsdfIntegrateKernel<false><<<num_sms * 8, 256, 0, stream>>>(a);
+  const int grid = num_sms * projectiveCtasPerSm();
+  if (cam.has_distortion) tsdfIntegrateKernel<true><<<grid, 256, 0, stream>>>(a);
+  else tsdfIntegrateKernel<false><<<grid, 256, 0, stream>>>(a);
 }
 
 void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* occ_blocks,
@@ -257,8 +273,9 @@ void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, 
   a.p = p;
   a.bits_to_clear = bits_to_clear;
   a.num_words = num_words;
-  if (cam.has_distortion) occupancyIntegrateKernel<true><<<num_sms * 8, 256, 0, stream>>>(a, op);
-  else occupancyIntegrateKernel<false><<<num_sms * 8, 256, 0, stream>>>(a, op);
+  const int grid = num_sms * projectiveCtasPerSm();
+  if (cam.has_distortion) occupancyIntegrateKernel<true><<<grid, 256, 0, stream>>>(a, op);
+  else occupancyIntegrateKernel<false><<<grid, 256, 0, stream>>>(a, op);
 }
 
 }  // namespace nvb
