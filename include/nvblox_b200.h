@@ -183,6 +183,37 @@ NVB_API int32_t nvb_mapper_get_esdf_params(const NvbMapper* m, NvbEsdfParams* p)
 NVB_API void nvb_default_occupancy_params(NvbOccupancyParams* p);
 NVB_API int32_t nvb_mapper_set_occupancy_params(NvbMapper* m, const NvbOccupancyParams* p);
 NVB_API int32_t nvb_mapper_get_occupancy_params(const NvbMapper* m, NvbOccupancyParams* p);
+
+/* TsdfDecayIntegrator / OccupancyDecayIntegrator parameters (C/include/nvblox/integrators/tsdf_decay_integrator_params.h:21-48,
+ * occupancy_decay_integrator_params.h:21-43, internal/decay_integrator_base_params.h:22-29; setters
+ * tsdf_decay_integrator.h:73-101, occupancy_decay_integrator.h:72-101). */
+typedef struct NvbTsdfDecayParams {
+  float decay_factor;                   /* 0.95: weight *= decay_factor                                  */
+  float decayed_weight_threshold;       /* 1e-3: weights never decay below it; below = "fully decayed" */
+  int32_t set_free_distance_on_decayed; /* 0                                                            */
+  float free_distance_vox;              /* 4                                                            */
+  int32_t deallocate_decayed_blocks;    /* 1: blocks whose voxels are all fully decayed leave the map   */
+} NvbTsdfDecayParams;
+typedef struct NvbOccupancyDecayParams {
+  float free_region_decay_probability;     /* 0.55, in [0.5, 1]  */
+  float occupied_region_decay_probability; /* 0.4, in [0, 0.5)   */
+  float decay_to_probability;              /* 0.5 (decay_to_free(true): 0.49, occupancy_decay_integrator.h:35-36) */
+  int32_t deallocate_decayed_blocks;       /* 1                  */
+} NvbOccupancyDecayParams;
+/* DecayBlockExclusionOptions (C/include/nvblox/integrators/internal/decayer.h:31-44): blocks that are spared. */
+typedef struct NvbDecayExclusion {
+  const int32_t* excluded_blocks_xyz_host; /* may be NULL */
+  int32_t num_excluded_blocks;
+  int32_t has_exclusion_sphere;            /* blocks whose origin is within the sphere are spared */
+  float exclusion_center[3];
+  float exclusion_radius_m;
+} NvbDecayExclusion;
+NVB_API void nvb_default_tsdf_decay_params(NvbTsdfDecayParams* p);
+NVB_API int32_t nvb_mapper_set_tsdf_decay_params(NvbMapper* m, const NvbTsdfDecayParams* p);
+NVB_API int32_t nvb_mapper_get_tsdf_decay_params(const NvbMapper* m, NvbTsdfDecayParams* p);
+NVB_API void nvb_default_occupancy_decay_params(NvbOccupancyDecayParams* p);
+NVB_API int32_t nvb_mapper_set_occupancy_decay_params(NvbMapper* m, const NvbOccupancyDecayParams* p);
+NVB_API int32_t nvb_mapper_get_occupancy_decay_params(const NvbMapper* m, NvbOccupancyDecayParams* p);
 NVB_API float nvb_mapper_voxel_size(const NvbMapper* m);
 NVB_API float nvb_mapper_block_size(const NvbMapper* m);
 
@@ -223,6 +254,20 @@ NVB_API int32_t nvb_mapper_integrate_depth_async(NvbMapper* m, const float* dept
  * (all TSDF blocks on the first call or when update_full_layer != 0). */
 NVB_API int32_t nvb_mapper_update_esdf(NvbMapper* m, int32_t update_full_layer);
 NVB_API int32_t nvb_mapper_update_esdf_async(NvbMapper* m, int32_t update_full_layer);
+
+/* Mapper::decayTsdf / decayOccupancy (mapper.h:268-292; mapper_impl.h:190-265; VoxelDecayer::decay,
+ * C/include/nvblox/integrators/internal/cuda/impl/decayer_impl.cuh:150-262) on the mapper's projective layer.
+ * depth == NULL: decay*AllVoxels. depth != NULL: decay*ExcludeLastView -- voxels that have a depth measurement in
+ * the given view (doesVoxelHaveDepthMeasurement, projective_integrators_common_impl.cuh:58-101, with the
+ * integrator's max integration distance and truncation distance) are spared; the caller passes the view it wants
+ * excluded (the reference's Mapper keeps a copy of the last frame for this). `exclusion` (may be NULL) spares whole
+ * blocks. Fully decayed blocks are deallocated when the parameters say so, from the projective AND the ESDF
+ * layer (Mapper::clearBlocksInLayers, src/mapper/mapper.cpp:546-575), their indices are written to
+ * removed_xyz_host (up to cap; may be NULL) and counted in *out_count; the next nvb_mapper_update_esdf covers all
+ * blocks (BlocksToUpdateTracker::addAllBlocksToUpdate). Synchronous. */
+NVB_API int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const float* depth,
+                                 int32_t depth_memory, int32_t rows, int32_t cols, const float* T_L_C,
+                                 const NvbCamera* cam, int32_t* removed_xyz_host, int32_t cap, int32_t* out_count);
 
 /* EsdfIntegrator::integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
  * (esdf_integrator.h:56-58, src/integrators/esdf_integrator.cu:220-266) on an

@@ -20,6 +20,9 @@ EXPORTED_SYMBOLS = [
     "nvb_last_error", "nvb_version", "nvb_device_count",
     "nvb_default_mapper_options", "nvb_default_tsdf_params", "nvb_default_esdf_params",
     "nvb_default_occupancy_params", "nvb_mapper_set_occupancy_params", "nvb_mapper_get_occupancy_params",
+    "nvb_default_tsdf_decay_params", "nvb_mapper_set_tsdf_decay_params", "nvb_mapper_get_tsdf_decay_params",
+    "nvb_default_occupancy_decay_params", "nvb_mapper_set_occupancy_decay_params",
+    "nvb_mapper_get_occupancy_decay_params", "nvb_mapper_decay",
     "nvb_mapper_create", "nvb_mapper_destroy", "nvb_mapper_clear",
     "nvb_mapper_set_tsdf_params", "nvb_mapper_get_tsdf_params",
     "nvb_mapper_set_esdf_params", "nvb_mapper_get_esdf_params",
@@ -68,6 +71,23 @@ class NvbOccupancyParams(C.Structure):
                 ("occupied_region_half_width_m", C.c_float)]
 
 
+class NvbTsdfDecayParams(C.Structure):
+    _fields_ = [("decay_factor", C.c_float), ("decayed_weight_threshold", C.c_float),
+                ("set_free_distance_on_decayed", C.c_int32), ("free_distance_vox", C.c_float),
+                ("deallocate_decayed_blocks", C.c_int32)]
+
+
+class NvbOccupancyDecayParams(C.Structure):
+    _fields_ = [("free_region_decay_probability", C.c_float), ("occupied_region_decay_probability", C.c_float),
+                ("decay_to_probability", C.c_float), ("deallocate_decayed_blocks", C.c_int32)]
+
+
+class NvbDecayExclusion(C.Structure):
+    _fields_ = [("excluded_blocks_xyz_host", C.POINTER(C.c_int32)), ("num_excluded_blocks", C.c_int32),
+                ("has_exclusion_sphere", C.c_int32), ("exclusion_center", C.c_float * 3),
+                ("exclusion_radius_m", C.c_float)]
+
+
 class NvbMapperOptions(C.Structure):
     _fields_ = [("voxel_size_m", C.c_float), ("device", C.c_int32),
                 ("tsdf_capacity_blocks", C.c_int32), ("esdf_capacity_blocks", C.c_int32),
@@ -105,6 +125,15 @@ def load():
     L.nvb_default_occupancy_params.restype = None
     L.nvb_mapper_set_occupancy_params.argtypes = [vp, C.POINTER(NvbOccupancyParams)]
     L.nvb_mapper_get_occupancy_params.argtypes = [vp, C.POINTER(NvbOccupancyParams)]
+    L.nvb_default_tsdf_decay_params.argtypes = [C.POINTER(NvbTsdfDecayParams)]
+    L.nvb_default_tsdf_decay_params.restype = None
+    L.nvb_mapper_set_tsdf_decay_params.argtypes = [vp, C.POINTER(NvbTsdfDecayParams)]
+    L.nvb_mapper_get_tsdf_decay_params.argtypes = [vp, C.POINTER(NvbTsdfDecayParams)]
+    L.nvb_default_occupancy_decay_params.argtypes = [C.POINTER(NvbOccupancyDecayParams)]
+    L.nvb_default_occupancy_decay_params.restype = None
+    L.nvb_mapper_set_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
+    L.nvb_mapper_get_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
+    L.nvb_mapper_decay.argtypes = [vp, C.POINTER(NvbDecayExclusion), vp, i32, i32, i32, fp, C.POINTER(NvbCamera), ip, i32, ip]
     L.nvb_mapper_create.argtypes = [C.POINTER(NvbMapperOptions), C.POINTER(vp)]
     L.nvb_mapper_create.restype = i32
     L.nvb_mapper_destroy.argtypes = [vp]

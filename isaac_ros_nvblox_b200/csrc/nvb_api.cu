@@ -114,6 +114,16 @@ struct NvbMapper {
   unsigned char* shadow = nullptr;
   int shadow_cap = 0;
   int* cand_stamp = nullptr;
+  // decay integrators
+  NvbTsdfDecayParams tdp;
+  NvbOccupancyDecayParams odp;
+  int4* dead = nullptr;          // deallocated projective blocks of the last decay call
+  int dead_cap = 0;
+  int* skip_stamp = nullptr;     // per projective slot: == skip_seq -> block excluded from this decay call
+  int skip_cap = 0;
+  int skip_seq = 0;
+  int* dead_cleared_xyz = nullptr;
+  int dead_cleared_cap = 0;
   int* cand_a = nullptr;
   int* cand_b = nullptr;
   int ges_switch = 160;
@@ -175,6 +185,9 @@ int allocLayer(DevLayer* L, int capacity, int block_bytes, cudaStream_t stream) 
   NVB_CUDA(cudaMalloc(&L->block_index, (size_t)capacity * 3 * sizeof(int)));
   NVB_CUDA(cudaMalloc(&L->count, sizeof(int)));
   NVB_CUDA(cudaMemsetAsync(L->count, 0, sizeof(int), stream));
+  NVB_CUDA(cudaMalloc(&L->free_slots, (size_t)capacity * sizeof(int)));
+  NVB_CUDA(cudaMalloc(&L->free_count, sizeof(int)));
+  NVB_CUDA(cudaMemsetAsync(L->free_count, 0, sizeof(int), stream));
   const int hcap = nextPow2(2ll * capacity);
   L->hash.mask = (unsigned int)hcap - 1;
   NVB_CUDA(cudaMalloc(&L->hash.keys, (size_t)hcap * sizeof(unsigned long long)));
@@ -185,6 +198,7 @@ int allocLayer(DevLayer* L, int capacity, int block_bytes, cudaStream_t stream) 
 
 void freeLayer(DevLayer* L) {
   cudaFree(L->blocks), cudaFree(L->block_index), cudaFree(L->count), cudaFree(L->hash.keys), cudaFree(L->hash.vals);
+  cudaFree(L->free_slots), cudaFree(L->free_count);
   *L = DevLayer{};
 }
 
@@ -209,6 +223,10 @@ int growLayer(NvbMapper* m, DevLayer* L, int new_capacity) {
   count = std::min(count, L->capacity);
   DevLayer N{};
   N.count = L->count;
+  N.free_count = L->free_count;
+  NVB_CUDA(cudaMalloc(&N.free_slots, (size_t)new_capacity * sizeof(int)));
+  NVB_CUDA(cudaMemcpyAsync(N.free_slots, L->free_slots, (size_t)L->capacity * sizeof(int), cudaMemcpyDeviceToDevice,
+                           m->stream));
   N.capacity = new_capacity;
   N.block_bytes = L->block_bytes;
   NVB_CUDA(cudaMalloc(&N.blocks, (size_t)new_capacity * L->block_bytes));
@@ -224,7 +242,7 @@ int growLayer(NvbMapper* m, DevLayer* L, int new_capacity) {
   launchFillU64(N.hash.keys, kEmptyKey, (size_t)hcap, m->stream);
   launchRehash(N, count, m->stream);
   NVB_CUDA(syncAll(m));
-  cudaFree(L->blocks), cudaFree(L->block_index), cudaFree(L->hash.keys), cudaFree(L->hash.vals);
+  cudaFree(L->blocks), cudaFree(L->block_index), cudaFree(L->hash.keys), cudaFree(L->hash.vals), cudaFree(L->free_slots);
   *L = N;
   return NVB_OK;
 }
@@ -284,7 +302,7 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kGesCounts = 24, kNumInts = 32 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kNumInts = 32 };
 
 float logOddsFromProbability(float p);
 
@@ -306,6 +324,8 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.nbr27 = m->nbr27, c.shadow = m->shadow, c.cand_stamp = m->cand_stamp;
   c.ges_counts = m->esdf_ints + kGesCounts;
   c.cand_a = m->cand_a, c.cand_b = m->cand_b, c.ges_switch = m->ges_switch;
+  c.dead_cleared_xyz = m->dead_cleared_xyz;
+  c.dead_cleared_count = m->dead_cleared_xyz ? m->esdf_ints + kDeadClearedCount : nullptr;
   c.cleared_seq = m->esdf_ints + kClearedSeq;
   c.update_seq = m->update_seq;
   c.barrier = m->barrier;
@@ -815,6 +835,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   nvb_default_tsdf_params(&m->tp);
   nvb_default_esdf_params(&m->ep);
   nvb_default_occupancy_params(&m->op);
+  nvb_default_tsdf_decay_params(&m->tdp);
+  nvb_default_occupancy_decay_params(&m->odp);
   m->projective_layer_type = opts->projective_layer_type;
   m->esdf_persistent = opts->esdf_persistent;
   // A/B switch for measurements: 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
@@ -884,6 +906,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
   cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr);
   cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
+  cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
@@ -903,12 +926,14 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
     // re-zero only the slots that were handed out: the slab invariant is "free slots are zero"
     NVB_CUDA(cudaMemsetAsync(L->blocks, 0, (size_t)count * L->block_bytes, m->stream));
     NVB_CUDA(cudaMemsetAsync(L->count, 0, sizeof(int), m->stream));
+    NVB_CUDA(cudaMemsetAsync(L->free_count, 0, sizeof(int), m->stream));
     launchFillU64(L->hash.keys, kEmptyKey, (size_t)L->hash.mask + 1, m->stream);
   }
   NVB_CUDA(cudaMemsetAsync(m->dirty, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kClearedCount, 0, sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kClearedSeq, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kDeadClearedCount, 0, sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->seed_upd, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->seed_clr, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->nbr, 0xFE, (size_t)m->esdf.capacity * 6 * sizeof(int), m->stream));
@@ -972,6 +997,183 @@ int32_t nvb_mapper_get_occupancy_params(const NvbMapper* m, NvbOccupancyParams* 
   *p = m->op;
   return NVB_OK;
 }
+void nvb_default_tsdf_decay_params(NvbTsdfDecayParams* p) {
+  if (!p) return;
+  // integrators/tsdf_decay_integrator_params.h:21-48, internal/decay_integrator_base_params.h:22-29
+  p->decay_factor = 0.95f;
+  p->decayed_weight_threshold = 1e-3f;
+  p->set_free_distance_on_decayed = 0;
+  p->free_distance_vox = 4.0f;
+  p->deallocate_decayed_blocks = 1;
+}
+void nvb_default_occupancy_decay_params(NvbOccupancyDecayParams* p) {
+  if (!p) return;
+  // integrators/occupancy_decay_integrator_params.h:21-43
+  p->free_region_decay_probability = 0.55f;
+  p->occupied_region_decay_probability = 0.4f;
+  p->decay_to_probability = 0.5f;
+  p->deallocate_decayed_blocks = 1;
+}
+int32_t nvb_mapper_set_tsdf_decay_params(NvbMapper* m, const NvbTsdfDecayParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  // CHECK_GT(decay_factor, 0) / CHECK_LT(decay_factor, 1) (src/integrators/tsdf_decay_integrator.cu:30-37)
+  if (!(p->decay_factor > 0.0f && p->decay_factor < 1.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "decay_factor must be in (0, 1)");
+  m->tdp = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_tsdf_decay_params(const NvbMapper* m, NvbTsdfDecayParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->tdp;
+  return NVB_OK;
+}
+int32_t nvb_mapper_set_occupancy_decay_params(NvbMapper* m, const NvbOccupancyDecayParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  // CHECKs of the setters (src/integrators/occupancy_decay_integrator.cu:24-57)
+  if (!(p->free_region_decay_probability >= 0.5f && p->free_region_decay_probability <= 1.0f))
+    return fail(NVB_ERR_INVALID_ARGUMENT, "free_region_decay_probability must be in [0.5, 1]");
+  if (!(p->occupied_region_decay_probability >= 0.0f && p->occupied_region_decay_probability < 0.5f))
+    return fail(NVB_ERR_INVALID_ARGUMENT, "occupied_region_decay_probability must be in [0, 0.5)");
+  if (!(p->decay_to_probability >= 0.0f && p->decay_to_probability <= 1.0f))
+    return fail(NVB_ERR_INVALID_ARGUMENT, "decay_to_probability must be a probability");
+  m->odp = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_occupancy_decay_params(const NvbMapper* m, NvbOccupancyDecayParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->odp;
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const float* depth, int32_t depth_memory,
+                         int32_t rows, int32_t cols, const float* T_L_C, const NvbCamera* cam, int32_t* removed_xyz_host,
+                         int32_t cap, int32_t* out_count) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (out_count) *out_count = 0;
+  if (depth) {
+    int rc = validateFrameArgs(m, depth, rows, cols, T_L_C, cam);
+    if (rc) return rc;
+  }
+  if (exclusion && exclusion->num_excluded_blocks > 0 && !exclusion->excluded_blocks_xyz_host)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "exclusion list is null");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(syncAll(m));  // the decay touches both layers: nothing of the ESDF chain may be in flight
+  const bool occupancy = m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY;
+  DevLayer& P = m->tsdf;
+  // scratch sized to the layer
+  if (m->dead_cap < P.capacity) {
+    if (m->dead) cudaFree(m->dead);
+    NVB_CUDA(cudaMalloc(&m->dead, (size_t)P.capacity * sizeof(int4)));
+    m->dead_cap = P.capacity;
+  }
+  if (m->skip_cap < P.capacity) {
+    if (m->skip_stamp) cudaFree(m->skip_stamp);
+    NVB_CUDA(cudaMalloc(&m->skip_stamp, (size_t)P.capacity * sizeof(int)));
+    NVB_CUDA(cudaMemsetAsync(m->skip_stamp, 0, (size_t)P.capacity * sizeof(int), m->stream));
+    m->skip_cap = P.capacity;
+  }
+  if (m->dead_cleared_cap < m->esdf.capacity) {
+    int* q = nullptr;
+    NVB_CUDA(cudaMalloc(&q, (size_t)m->esdf.capacity * 3 * sizeof(int)));
+    if (m->dead_cleared_xyz) {
+      NVB_CUDA(cudaMemcpy(q, m->dead_cleared_xyz, (size_t)m->dead_cleared_cap * 3 * sizeof(int), cudaMemcpyDeviceToDevice));
+      cudaFree(m->dead_cleared_xyz);
+    }
+    m->dead_cleared_xyz = q;
+    m->dead_cleared_cap = m->esdf.capacity;
+  }
+  DecayArgs a{};
+  a.layer = P;
+  a.occupancy = occupancy ? 1 : 0;
+  a.p.block_size = m->block_size;
+  a.p.voxel_size = m->block_size * (1.0f / kVps);
+  a.p.half_voxel_size = m->block_size * (0.5f / kVps);
+  // DepthObservationSpace of Mapper::decay*ExcludeLastView (mapper_impl.h:190-203,227-243)
+  a.p.max_integration_distance_m = m->tp.max_integration_distance_m;
+  a.p.truncation_distance_m = m->tp.truncation_distance_vox * m->voxel_size;
+  if (occupancy) {
+    a.free_log_odds = logOddsFromProbability(m->odp.free_region_decay_probability);
+    a.occupied_log_odds = logOddsFromProbability(m->odp.occupied_region_decay_probability);
+    a.to_log_odds = logOddsFromProbability(m->odp.decay_to_probability);
+    a.deallocate = m->odp.deallocate_decayed_blocks ? 1 : 0;
+  } else {
+    a.decay_factor = m->tdp.decay_factor;
+    a.weight_threshold = m->tdp.decayed_weight_threshold;
+    a.set_free_distance = m->tdp.set_free_distance_on_decayed ? 1 : 0;
+    a.free_distance_m = m->tdp.free_distance_vox * m->voxel_size;  // tsdf_decay_integrator_impl.cuh:85
+    a.deallocate = m->tdp.deallocate_decayed_blocks ? 1 : 0;
+  }
+  // block exclusion
+  std::vector<int> excl;
+  int* excl_dev = nullptr;
+  if (exclusion && exclusion->num_excluded_blocks > 0) {
+    const int ne = exclusion->num_excluded_blocks;
+    NVB_CUDA(cudaMalloc(&excl_dev, (size_t)ne * 3 * sizeof(int)));
+    NVB_CUDA(cudaMemcpyAsync(excl_dev, exclusion->excluded_blocks_xyz_host, (size_t)ne * 3 * sizeof(int), cudaMemcpyHostToDevice,
+                             m->stream));
+    m->skip_seq++;
+    launchMarkSkipped(P, excl_dev, ne, m->skip_stamp, m->skip_seq, m->stream);
+    a.skip_stamp = m->skip_stamp;
+    a.skip_seq = m->skip_seq;
+  }
+  if (exclusion && exclusion->has_exclusion_sphere && exclusion->exclusion_radius_m * exclusion->exclusion_radius_m > 0.0f) {
+    a.has_sphere = 1;
+    a.cx = exclusion->exclusion_center[0], a.cy = exclusion->exclusion_center[1], a.cz = exclusion->exclusion_center[2];
+    a.r2 = exclusion->exclusion_radius_m * exclusion->exclusion_radius_m;
+  }
+  // view exclusion
+  float* depth_tmp = nullptr;
+  if (depth) {
+    const float* depth_dev = depth;
+    if (depth_memory == NVB_MEM_HOST) {
+      NVB_CUDA(cudaMalloc(&depth_tmp, (size_t)rows * cols * sizeof(float)));
+      NVB_CUDA(cudaMemcpyAsync(depth_tmp, depth, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+      depth_dev = depth_tmp;
+    }
+    a.depth = depth_dev, a.rows = rows, a.cols = cols;
+    a.T_C_L = invertRigid(rigidFromColMajor(T_L_C));
+    a.cam = *cam;
+  }
+  a.dead = m->dead;
+  a.dead_count = m->esdf_ints + kDeadCount;
+  a.tracker_dirty = m->dirty;
+  NVB_CUDA(cudaMemsetAsync(a.dead_count, 0, sizeof(int), m->stream));
+  launchDecay(a, m->num_sms, m->stream);
+  m->launches++;
+  int n_dead = 0;
+  NVB_CUDA(cudaMemcpyAsync(&n_dead, a.dead_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  if (depth_tmp) cudaFree(depth_tmp);
+  if (excl_dev) cudaFree(excl_dev);
+  if (n_dead > 0) {
+    // Mapper::clearBlocksInLayers: the same blocks leave the ESDF layer; then both hashes are rebuilt without them
+    EsdfCtx c = makeEsdfCtx(m);
+    launchEsdfRemoveBlocks(c, m->dead, a.dead_count, n_dead, m->stream);
+    for (DevLayer* L : {&m->tsdf, &m->esdf}) {
+      int hw = 0;
+      NVB_CUDA(cudaMemcpyAsync(&hw, L->count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+      NVB_CUDA(cudaStreamSynchronize(m->stream));
+      hw = std::min(hw, L->capacity);
+      launchFillU64(L->hash.keys, kEmptyKey, (size_t)L->hash.mask + 1, m->stream);
+      launchRehash(*L, hw, m->stream);
+    }
+    m->launches += 6;
+    if (out_count) *out_count = n_dead;
+    if (removed_xyz_host && cap > 0) {
+      const int k = std::min(n_dead, (int)cap);
+      std::vector<int4> tmp((size_t)k);
+      NVB_CUDA(cudaMemcpyAsync(tmp.data(), m->dead, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
+      NVB_CUDA(cudaStreamSynchronize(m->stream));
+      for (int i = 0; i < k; i++)
+        removed_xyz_host[3 * i] = tmp[i].y, removed_xyz_host[3 * i + 1] = tmp[i].z, removed_xyz_host[3 * i + 2] = tmp[i].w;
+    }
+  }
+  // BlocksToUpdateTracker::addAllBlocksToUpdate (mapper_impl.h:208-211): the next ESDF update covers every block
+  m->tracker_initialized = false;
+  NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
+  NVB_CUDA(syncAll(m));
+  return checkDeviceError(m);
+}
+
 float nvb_mapper_voxel_size(const NvbMapper* m) { return m ? m->voxel_size : 0.0f; }
 float nvb_mapper_block_size(const NvbMapper* m) { return m ? m->block_size : 0.0f; }
 
@@ -1168,9 +1370,10 @@ int32_t nvb_layer_num_blocks(NvbMapper* m, int32_t layer, int32_t* out_count) {
   if (!L) return fail(NVB_ERR_INVALID_ARGUMENT, "unknown layer");
   NVB_CUDA(cudaSetDevice(m->device));
   NVB_CUDA(syncAll(m));
-  int count = 0;
+  int count = 0, nfree = 0;
   NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
-  *out_count = std::min(count, L->capacity);
+  NVB_CUDA(cudaMemcpy(&nfree, L->free_count, sizeof(int), cudaMemcpyDeviceToHost));
+  *out_count = std::min(count, L->capacity) - nfree;  // slots handed out minus deallocated ones
   return NVB_OK;
 }
 
@@ -1180,9 +1383,23 @@ int32_t nvb_layer_block_indices(NvbMapper* m, int32_t layer, int32_t* out_xyz_ho
   if (rc) return rc;
   if (out_count) *out_count = n;
   DevLayer* L = layerOf(m, layer);
-  const int k = std::min(n, cap);
-  if (out_xyz_host && k > 0)
-    NVB_CUDA(cudaMemcpy(out_xyz_host, L->block_index, (size_t)k * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  if (out_xyz_host && cap > 0 && n > 0) {
+    int hw = 0;
+    NVB_CUDA(cudaMemcpy(&hw, L->count, sizeof(int), cudaMemcpyDeviceToHost));
+    hw = std::min(hw, L->capacity);
+    if (hw == n) {  // no deallocated slots below the high-water mark
+      NVB_CUDA(cudaMemcpy(out_xyz_host, L->block_index, (size_t)std::min(n, cap) * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<int> all((size_t)hw * 3);
+      NVB_CUDA(cudaMemcpy(all.data(), L->block_index, all.size() * sizeof(int), cudaMemcpyDeviceToHost));
+      int k = 0;
+      for (int sl = 0; sl < hw && k < cap; sl++) {
+        if (all[3 * sl] == kDeadSlotX) continue;
+        out_xyz_host[3 * k] = all[3 * sl], out_xyz_host[3 * k + 1] = all[3 * sl + 1], out_xyz_host[3 * k + 2] = all[3 * sl + 2];
+        k++;
+      }
+    }
+  }
   return NVB_OK;
 }
 

@@ -115,6 +115,34 @@ __device__ __forceinline__ void markLocalRecord(const EsdfCtx& c, MarkLocal& ml,
   }
 }
 
+// The persistent cleared list at the end of the mark pass (last CTA, one thread). If this update has blocks to
+// clear the list is about to be rewritten (clearAllInvalid resizes it, :1620); otherwise it keeps the previous
+// call's content (:242-257). The reference keeps block INDICES, so an entry whose block was deallocated (decay
+// integrators) and allocated again counts again: such indices wait in dead_cleared_xyz and rejoin here.
+__device__ __forceinline__ void updatePersistentClearedList(const EsdfCtx& c, int nclr) {
+  if (nclr > 0) {
+    *c.cleared_count = 0;
+    *c.cleared_seq = c.update_seq;
+    if (c.dead_cleared_count) *c.dead_cleared_count = 0;
+    return;
+  }
+  if (!c.dead_cleared_count) return;
+  int nd = *c.dead_cleared_count;
+  for (int i = 0; i < nd;) {
+    const int slot = hashFind(c.esdf.hash, c.dead_cleared_xyz[3 * i], c.dead_cleared_xyz[3 * i + 1], c.dead_cleared_xyz[3 * i + 2]);
+    if (slot >= 0) {
+      c.cleared_list[(*c.cleared_count)++] = slot;
+      c.seed_clr[slot] = *c.cleared_seq;
+      nd--;
+      c.dead_cleared_xyz[3 * i] = c.dead_cleared_xyz[3 * nd], c.dead_cleared_xyz[3 * i + 1] = c.dead_cleared_xyz[3 * nd + 1],
+                          c.dead_cleared_xyz[3 * i + 2] = c.dead_cleared_xyz[3 * nd + 2];
+    } else {
+      i++;
+    }
+  }
+  *c.dead_cleared_count = nd;
+}
+
 // ---------------------------------------------------------------------------
 // markAllSitesKernel + updateEsdfVoxelToChanges with TsdfSiteFunctor
 // (esdf_integrator.cu:113-138, 401-540).
@@ -205,10 +233,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
       __threadfence();
       const int nclr = *(volatile int*)c.clr_count;
       const int nupd = *(volatile int*)c.upd_count;
-      if (nclr > 0) {
-        *c.cleared_count = 0;
-        *c.cleared_seq = c.update_seq;
-      }
+      updatePersistentClearedList(c, nclr);
       c.stats[1] = nupd, c.stats[2] = nclr;
     }
   }
@@ -302,10 +327,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkOccupancyKernel(EsdfCtx c) {
       __threadfence();
       const int nclr = *(volatile int*)c.clr_count;
       const int nupd = *(volatile int*)c.upd_count;
-      if (nclr > 0) {
-        *c.cleared_count = 0;
-        *c.cleared_seq = c.update_seq;
-      }
+      updatePersistentClearedList(c, nclr);
       c.stats[1] = nupd, c.stats[2] = nclr;
     }
   }
@@ -447,10 +469,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
       __threadfence();
       const int nclr = *(volatile int*)c.clr_count;
       const int nupd = *(volatile int*)c.upd_count;
-      if (nclr > 0) {
-        *c.cleared_count = 0;
-        *c.cleared_seq = c.update_seq;
-      }
+      updatePersistentClearedList(c, nclr);
       c.stats[1] = nupd, c.stats[2] = nclr;
     }
   }
@@ -501,7 +520,7 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
     __syncthreads();
     const long long slot_ll = first + (long long)tid * gridDim.x;
     bool is_cand = false;
-    if (slot_ll < nblocks) {
+    if (slot_ll < nblocks && c.esdf.block_index[3 * slot_ll] != kDeadSlotX) {
       const int* bi = c.esdf.block_index + 3 * slot_ll;
       const int b3[3] = {bi[0], bi[1], bi[2]};
       // AlignedBox::exteriorDistance(box) > radius -> skip
@@ -792,6 +811,107 @@ void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots
                                                                        in_count_upper);
 }
 
+// ---------------------------------------------------------------------------
+// Mapper::clearBlocksInLayers (src/mapper/mapper.cpp:546-575) for the ESDF layer: the blocks the decay integrator
+// deallocated leave the ESDF layer too. One CTA per block: unlink it from its neighbours' tables, zero its bytes
+// (slab invariant), give the slot back. The host rebuilds the hash afterwards.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) esdfRemoveBlocksKernel(EsdfCtx c, const int4* dead, const int* dead_count) {
+  const int tid = threadIdx.x;
+  const int n = *dead_count;
+  __shared__ int s_slot;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int4 d = dead[i];
+    if (tid == 0) s_slot = hashFind(c.esdf.hash, d.y, d.z, d.w);
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot >= 0) {
+      if (tid < 27 && tid != 13) {
+        int nb = c.nbr27[27 * slot + tid];
+        const int dx = tid / 9 - 1, dy = (tid / 3) % 3 - 1, dz = tid % 3 - 1;
+        if (nb < -1) nb = hashFind(c.esdf.hash, d.y + dx, d.z + dy, d.w + dz);  // row never linked
+        if (nb >= 0) {
+          c.nbr27[27 * nb + (26 - tid)] = -1;
+          if ((dx != 0) + (dy != 0) + (dz != 0) == 1) {
+            const int axis = dx ? 0 : (dy ? 1 : 2);
+            const int neg = (dx + dy + dz) < 0 ? 1 : 0;
+            c.nbr[6 * nb + axis * 2 + (neg ^ 1)] = -1;
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < 27) c.nbr27[27 * slot + tid] = (int)0xFEFEFEFE;
+      if (tid < 6) c.nbr[6 * slot + tid] = (int)0xFEFEFEFE;
+      uint4* g = reinterpret_cast<uint4*>(esdfBlockPtr(c.esdf, slot));
+      for (int k = tid; k < kBlockWords / 4; k += kThreads) g[k] = make_uint4(0, 0, 0, 0);
+      if (tid == 0) {
+        if (*c.cleared_count > 0 && c.seed_clr[slot] == *c.cleared_seq) {
+          const int q = atomicAdd(c.dead_cleared_count, 1);
+          c.dead_cleared_xyz[3 * q] = d.y, c.dead_cleared_xyz[3 * q + 1] = d.z, c.dead_cleared_xyz[3 * q + 2] = d.w;
+        }
+        c.seed_clr[slot] = 0, c.seed_upd[slot] = 0;
+        c.esdf.block_index[3 * slot] = kDeadSlotX;
+        c.esdf.free_slots[atomicAdd(c.esdf.free_count, 1)] = slot;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Drops the deallocated slots from the persistent cleared list (stable, one CTA).
+__global__ void __launch_bounds__(kThreads) esdfFilterClearedKernel(EsdfCtx c) {
+  __shared__ int s_base, s_warp[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = *c.cleared_count;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int first = 0; first < n; first += kThreads) {
+    const int i = first + tid;
+    int slot = -1;
+    bool keep = false;
+    if (i < n) {
+      slot = c.cleared_list[i];
+      keep = c.esdf.block_index[3 * slot] != kDeadSlotX;
+    }
+    const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();  // also: every thread has read its entry before anyone overwrites the list
+    int off = s_base;
+    for (int w = 0; w < warp; w++) off += s_warp[w];
+    if (keep) c.cleared_list[off + __popc(ballot & ((1u << lane) - 1u))] = slot;
+    __syncthreads();
+    if (tid == 0) {
+      int total = 0;
+      for (int w = 0; w < kThreads / 32; w++) total += s_warp[w];
+      s_base += total;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *c.cleared_count = s_base;
+}
+
+void launchEsdfRemoveBlocks(const EsdfCtx& c, const int4* dead, const int* dead_count, int upper, cudaStream_t stream) {
+  int grid = upper < 1184 ? (upper < 1 ? 1 : upper) : 1184;
+  esdfRemoveBlocksKernel<<<grid, kThreads, 0, stream>>>(c, dead, dead_count);
+  esdfFilterClearedKernel<<<1, kThreads, 0, stream>>>(c);
+}
+
+// Test hook: NVB_ESDF_GRID_CAP=<n> caps the grids of the mark and clear kernels so that small maps exercise their
+// multi-round paths (per-CTA list flushes, several selection rounds).
+static int esdfGridCap() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVB_ESDF_GRID_CAP");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+static int cappedGrid(int grid) {
+  const int cap = esdfGridCap();
+  return (cap > 0 && grid > cap) ? cap : grid;
+}
+
 void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream) {
   static int use_tma = -1;
   if (use_tma < 0) {
@@ -805,27 +925,27 @@ void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t
     int grid = num_sms * 8;
     if (count_upper < grid) grid = count_upper;
     if (grid < 1) grid = 1;
-    esdfMarkOccupancyKernel<<<grid, kThreads, 0, stream>>>(c);
+    esdfMarkOccupancyKernel<<<cappedGrid(grid), kThreads, 0, stream>>>(c);
     return;
   }
   if (use_tma) {
     int grid = num_sms * 4;  // 4 x 43 KiB of staging per SM; ~3000 items -> ~5 per CTA, 2 loads in flight each
     if (count_upper < grid) grid = count_upper;
     if (grid < 1) grid = 1;
-    esdfMarkTmaKernel<<<grid, kThreads, kMarkStages * sizeof(MarkStage), stream>>>(c);
+    esdfMarkTmaKernel<<<cappedGrid(grid), kThreads, kMarkStages * sizeof(MarkStage), stream>>>(c);
     return;
   }
   int grid = num_sms * 8;  // 8 resident CTAs per SM (10 KiB smem, 256 threads each)
   if (count_upper < grid) grid = count_upper;
   if (grid < 1) grid = 1;
-  esdfMarkKernel<<<grid, kThreads, 0, stream>>>(c);
+  esdfMarkKernel<<<cappedGrid(grid), kThreads, 0, stream>>>(c);
 }
 
 void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream) {
   int grid = num_sms * 8;
   if (esdf_count_upper < grid) grid = esdf_count_upper;
   if (grid < 1) grid = 1;
-  esdfClearKernel<<<grid, kThreads, 0, stream>>>(c);
+  esdfClearKernel<<<cappedGrid(grid), kThreads, 0, stream>>>(c);
 }
 
 // One launch per phase; the host reads the ring's block count after every ring,

@@ -6,6 +6,7 @@
 // choices (the reference's nvcc build contracts at the compiler's discretion,
 // nvblox_core/cmake/nvblox_targets.cmake:120-171 -- see DESIGN.md "Numerics").
 #pragma once
+#include <cstdint>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -170,12 +171,15 @@ struct DevHash {
 // One layer = one contiguous slab of fixed-size blocks + the hash + the reverse map.
 struct DevLayer {
   unsigned char* blocks;  // capacity * block_bytes, zero-initialised
-  int* block_index;       // 3 ints per slot (Index3D of the block living in that slot)
-  int* count;             // device counter: slots handed out so far
+  int* block_index;       // 3 ints per slot (Index3D of the block living in that slot); x == kDeadSlotX: slot is free
+  int* count;             // device counter: slots handed out so far (high-water mark; freed slots are below it)
+  int* free_slots;        // stack of deallocated slots (their blocks are zero again), reused before the slab grows
+  int* free_count;
   int capacity;
   int block_bytes;
   DevHash hash;
 };
+constexpr int kDeadSlotX = INT32_MIN;  // block_index[3 * slot] of a deallocated slot
 
 #ifdef __CUDACC__
 __device__ __forceinline__ int hashFind(const DevHash& h, int x, int y, int z) {
@@ -208,7 +212,14 @@ __device__ __forceinline__ int hashFindOrInsert(const DevLayer& L, int x, int y,
     if (k == kEmptyKey) {
       const unsigned long long old = atomicCAS(&L.hash.keys[p], kEmptyKey, key);
       if (old == kEmptyKey) {
-        const int slot = atomicAdd(L.count, 1);
+        // a deallocated slot first (decay integrators), else the next fresh one
+        int slot = -1;
+        if (*(volatile int*)L.free_count > 0) {
+          const int f = atomicSub(L.free_count, 1) - 1;
+          if (f >= 0) slot = L.free_slots[f];
+          else atomicAdd(L.free_count, 1);
+        }
+        if (slot < 0) slot = atomicAdd(L.count, 1);
         if (slot >= L.capacity) {
           atomicOr(error, 1);
           L.hash.vals[p] = -1;
@@ -332,6 +343,8 @@ struct EsdfCtx {
   int* nbr27;         // 27 ints per ESDF slot: slot of the block at offset (dx,dy,dz), entry (dx+1)*9+(dy+1)*3+(dz+1);
                       // -1 none, < -1 unknown (never linked)
   unsigned char* shadow;  // second ESDF slab (same slot indexing): results of a ring wait here until all reads are done
+  int* dead_cleared_xyz;    // indices of deallocated blocks that were on the persistent cleared list (3 ints each) ...
+  int* dead_cleared_count;  // ... they rejoin it if a block with that index is allocated again while the list persists
   int* cand_a;        // candidate lists of the gather-emulate-sweep rings (ping-pong by ring parity)
   int* cand_b;
   int ges_switch;     // rings with more members than this run as four-phase rings
@@ -366,6 +379,36 @@ cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStrea
 // Reference-like driver: one launch per phase, host reads the ring counter.
 cudaError_t runEsdfComputeHostLoop(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
 int esdfPersistentMaxCtas(int num_sms);
+
+// nvb_tsdf.cu: decay (VoxelDecayer::decay, integrators/internal/cuda/impl/decayer_impl.cuh)
+struct DecayArgs {
+  DevLayer layer;  // the projective layer (TsdfVoxel or OccupancyVoxel blocks)
+  int occupancy;
+  // TsdfDecayFunctor / OccupancyDecayFunctor
+  float decay_factor, weight_threshold, free_distance_m;
+  int set_free_distance;
+  float free_log_odds, occupied_log_odds, to_log_odds;
+  int deallocate;
+  // DecayBlockExclusionOptions
+  const int* skip_stamp;  // per slot: == skip_seq -> spared
+  int skip_seq;
+  int has_sphere;
+  float cx, cy, cz, r2;
+  // DepthObservationSpace (null depth: every voxel decays)
+  const float* depth;
+  int rows, cols;
+  Rigid T_C_L;
+  NvbCamera cam;
+  TsdfKernelParams p;  // block/voxel sizes, max view distance (max_integration_distance_m), truncation
+  // outputs
+  int4* dead;  // {slot, x, y, z} of deallocated blocks
+  int* dead_count;
+  int* tracker_dirty;
+};
+void launchDecay(const DecayArgs& a, int num_sms, cudaStream_t stream);
+void launchMarkSkipped(const DevLayer& layer, const int* xyz_dev, int n, int* skip_stamp, int skip_seq, cudaStream_t stream);
+// nvb_esdf.cu: ESDF side of a deallocation (Mapper::clearBlocksInLayers)
+void launchEsdfRemoveBlocks(const EsdfCtx& c, const int4* dead, const int* dead_count, int upper, cudaStream_t stream);
 
 // nvb_util.cu
 void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsigned char* out, unsigned char* found,

@@ -218,6 +218,104 @@ __global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// VoxelDecayer::decay (decayer_impl.cuh:84-262) with TsdfDecayFunctor (tsdf_decay_integrator_impl.cuh:25-75) or
+// OccupancyDecayFunctor (occupancy_decay_integrator_impl.cuh:26-70). Persistent CTAs over the slab's slots, one
+// block per iteration, two voxels per thread. A block whose voxels are all fully decayed is deallocated on the
+// spot: its bytes go back to zero (the slab invariant), its slot onto the layer's free stack, its index into
+// the `dead` list (the host rebuilds the hash afterwards and removes the ESDF twin).
+// ---------------------------------------------------------------------------
+template <bool kDistort>
+__device__ __forceinline__ bool voxelHasDepthMeasurement(const TsdfArgs& v, const int4& blk, int vx, int vy, int vz) {
+  // doesVoxelHaveDepthMeasurement (projective_integrators_common_impl.cuh:58-101)
+  float d, voxel_depth;
+  bool is_active;
+  if (!sampleVoxel<kDistort>(v, blk, vx, vy, vz, d, voxel_depth, is_active)) return false;
+  if (!(d > 0.0f)) return false;  // invalid depth (sampleVoxel maps it to 0): not in view
+  return !(d - voxel_depth < -v.p.truncation_distance_m);
+}
+
+template <bool kDistort>
+__global__ void __launch_bounds__(256) decayKernel(const __grid_constant__ DecayArgs a) {
+  const int tid = threadIdx.x;
+  const int n = *a.layer.count < a.layer.capacity ? *a.layer.count : a.layer.capacity;
+  TsdfArgs v;  // view description for sampleVoxel
+  v.depth = a.depth, v.mask = nullptr, v.mask_mode = 0, v.rows = a.rows, v.cols = a.cols;
+  v.T_C_L = a.T_C_L, v.cam = a.cam, v.p = a.p;
+  // voxels 2 tid, 2 tid + 1 (z-adjacent): linear offset = x*64 + y*8 + z
+  const int vx = tid >> 5, vy = (tid >> 2) & 7, vz = (tid & 3) * 2;
+  for (int slot = blockIdx.x; slot < n; slot += gridDim.x) {
+    const int bx = a.layer.block_index[3 * slot];
+    if (bx == kDeadSlotX) continue;
+    const int by = a.layer.block_index[3 * slot + 1], bz = a.layer.block_index[3 * slot + 2];
+    // getBlockIndicesToDecay (decayer_impl.cuh:38-80)
+    if (a.skip_stamp && a.skip_stamp[slot] == a.skip_seq) continue;
+    if (a.has_sphere) {
+      // getPositionFromBlockIndex = block origin; squaredNorm in Eigen's a0 + (a1 + a2) order
+      const float dx = a.p.block_size * (float)bx - a.cx, dy = a.p.block_size * (float)by - a.cy,
+                  dz = a.p.block_size * (float)bz - a.cz;
+      const float d2 = sum3(dx * dx, dy * dy, dz * dz);
+      if (!(d2 > a.r2)) continue;
+    }
+    const int4 blk = make_int4(bx, by, bz, slot);
+    bool decay0 = true, decay1 = true;
+    if (a.depth) {
+      decay0 = !voxelHasDepthMeasurement<kDistort>(v, blk, vx, vy, vz);
+      decay1 = !voxelHasDepthMeasurement<kDistort>(v, blk, vx, vy, vz + 1);
+    }
+    bool fully;
+    if (a.occupancy) {
+      float2* gp = reinterpret_cast<float2*>(a.layer.blocks + (size_t)slot * kOccBlockBytes) + tid;
+      float2 w = *gp;
+      const float2 old = w;
+      auto is_fully = [&](float lo) {
+        return lo >= a.to_log_odds ? (lo + a.occupied_log_odds < a.to_log_odds) : (lo + a.free_log_odds >= a.to_log_odds);
+      };
+      auto step = [&](float lo) {
+        if (is_fully(lo)) return a.to_log_odds;
+        return lo >= 0.0f ? lo + a.occupied_log_odds : lo + a.free_log_odds;
+      };
+      if (decay0) w.x = step(w.x);
+      if (decay1) w.y = step(w.y);
+      fully = is_fully(w.x) && is_fully(w.y);
+      const bool all = __syncthreads_and(fully);
+      if (all && a.deallocate) *gp = make_float2(0.0f, 0.0f);
+      else if (w.x != old.x || w.y != old.y) *gp = w;
+      fully = all;
+    } else {
+      float4* gp = reinterpret_cast<float4*>(a.layer.blocks + (size_t)slot * kTsdfBlockBytes) + tid;
+      float4 w = *gp;  // {distance0, weight0, distance1, weight1}
+      const float4 old = w;
+      auto step = [&](float& dist, float& weight) {
+        if (weight < (a.weight_threshold - 1e-6f)) return;
+        weight = fmaxf(weight * a.decay_factor, a.weight_threshold);
+        if (a.set_free_distance && weight < (a.weight_threshold + 1e-6f)) dist = a.free_distance_m;
+      };
+      if (decay0) step(w.x, w.y);
+      if (decay1) step(w.z, w.w);
+      fully = (w.y < (a.weight_threshold + 1e-6f)) && (w.w < (a.weight_threshold + 1e-6f));
+      const bool all = __syncthreads_and(fully);
+      if (all && a.deallocate) *gp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      else if (w.x != old.x || w.y != old.y || w.z != old.z || w.w != old.w) *gp = w;
+      fully = all;
+    }
+    if (fully && a.deallocate && tid == 0) {
+      a.layer.block_index[3 * slot] = kDeadSlotX;
+      a.dead[atomicAdd(a.dead_count, 1)] = make_int4(slot, bx, by, bz);
+      a.layer.free_slots[atomicAdd(a.layer.free_count, 1)] = slot;
+      if (a.tracker_dirty) a.tracker_dirty[slot] = 0;
+    }
+  }
+}
+
+// DecayBlockExclusionOptions::block_indices_to_exclude: stamp the slots of the listed blocks.
+__global__ void markSkippedKernel(DevLayer L, const int* xyz, int n, int* skip_stamp, int skip_seq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int slot = hashFind(L.hash, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  if (slot >= 0) skip_stamp[slot] = skip_seq;
+}
+
 // Resident CTAs per SM of the projective update kernels. 8 x 256 threads fill an SM's thread slots, which keeps the
 // cooperative ESDF wavefront of the previous frame (side stream, one 256-thread CTA per SM) from starting until
 // this kernel drains; NVB_TSDF_CTAS_PER_SM is the A/B switch for that trade-off.
@@ -276,6 +374,15 @@ void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, 
   const int grid = num_sms * projectiveCtasPerSm();
   if (cam.has_distortion) occupancyIntegrateKernel<true><<<grid, 256, 0, stream>>>(a, op);
   else occupancyIntegrateKernel<false><<<grid, 256, 0, stream>>>(a, op);
+}
+
+void launchDecay(const DecayArgs& a, int num_sms, cudaStream_t stream) {
+  const int grid = num_sms * 8;
+  if (a.depth && a.cam.has_distortion) decayKernel<true><<<grid, 256, 0, stream>>>(a);
+  else decayKernel<false><<<grid, 256, 0, stream>>>(a);
+}
+void launchMarkSkipped(const DevLayer& layer, const int* xyz_dev, int n, int* skip_stamp, int skip_seq, cudaStream_t stream) {
+  if (n > 0) markSkippedKernel<<<(n + 255) / 256, 256, 0, stream>>>(layer, xyz_dev, n, skip_stamp, skip_seq);
 }
 
 }  // namespace nvb

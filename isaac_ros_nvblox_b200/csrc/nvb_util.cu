@@ -57,6 +57,7 @@ __global__ void fillU64Kernel(unsigned long long* p, unsigned long long v, size_
 __global__ void rehashKernel(DevLayer L, int count) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= count) return;
+  if (L.block_index[3 * slot] == kDeadSlotX) return;  // deallocated slot
   const unsigned long long key = packIndex(L.block_index[3 * slot], L.block_index[3 * slot + 1],
                                            L.block_index[3 * slot + 2]);
   unsigned int p = hashKey(key) & L.hash.mask;
@@ -72,13 +73,21 @@ __global__ void rehashKernel(DevLayer L, int count) {
 
 // BlocksToUpdateState::setUpdateAllBlocks (map/blocks_to_update_tracker.h): the todo
 // list becomes every allocated TSDF slot.
+// (*todo_count is zeroed by a memset in front of this kernel; deallocated slots are skipped.)
 __global__ void todoAllKernel(DevLayer tsdf, int* dirty, int* todo_slots, int* todo_count) {
   const int n = *tsdf.count < tsdf.capacity ? *tsdf.count : tsdf.capacity;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *todo_count = n;
-  for (; i < n; i += gridDim.x * blockDim.x) {
-    todo_slots[i] = i;
-    dirty[i] = 1;
+  const int lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    const bool live = i < n && tsdf.block_index[3 * i] != kDeadSlotX;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, live);
+    int pos = 0;
+    if (lane == 0 && ballot) pos = atomicAdd(todo_count, __popc(ballot));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (live) {
+      todo_slots[pos + __popc(ballot & ((1u << lane) - 1u))] = i;
+      dirty[i] = 1;
+    }
   }
 }
 
@@ -106,6 +115,7 @@ void launchRehash(const DevLayer& layer, int count, cudaStream_t stream) {
   if (count > 0) rehashKernel<<<(count + 255) / 256, 256, 0, stream>>>(layer, count);
 }
 void launchTodoAll(const DevLayer& tsdf, int* dirty, int* todo_slots, int* todo_count, cudaStream_t stream) {
+  cudaMemsetAsync(todo_count, 0, sizeof(int), stream);
   todoAllKernel<<<296, 256, 0, stream>>>(tsdf, dirty, todo_slots, todo_count);
 }
 void launchTodoConsume(const int* todo_slots, const int* todo_count, int* dirty, cudaStream_t stream) {

@@ -18,7 +18,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import NvbCamera, NvbEsdfParams, NvbMapperOptions, NvbOccupancyParams, NvbTsdfParams, check
+from ._lib import (NvbCamera, NvbDecayExclusion, NvbEsdfParams, NvbMapperOptions, NvbOccupancyDecayParams,
+                   NvbOccupancyParams, NvbTsdfDecayParams, NvbTsdfParams, check)
 
 TSDF_VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4")])
 ESDF_VOXEL_DTYPE = np.dtype(
@@ -215,6 +216,36 @@ class _OccupancyIntegrator(_TsdfIntegrator):
             .occupied_region_half_width_m
 
 
+class _DecayIntegrator:
+    """TsdfDecayIntegrator / OccupancyDecayIntegrator parameter surface (tsdf_decay_integrator.h:73-101,
+    occupancy_decay_integrator.h:72-101, internal/decay_integrator_base.h:50-58)."""
+
+    def __init__(self, mapper, occupancy):
+        self._m, self._occ = mapper, occupancy
+
+    def params(self, **kw):
+        L, h = self._m._L, self._m._h
+        p = NvbOccupancyDecayParams() if self._occ else NvbTsdfDecayParams()
+        get = L.nvb_mapper_get_occupancy_decay_params if self._occ else L.nvb_mapper_get_tsdf_decay_params
+        put = L.nvb_mapper_set_occupancy_decay_params if self._occ else L.nvb_mapper_set_tsdf_decay_params
+        check(get(h, C.byref(p)))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        if kw:
+            check(put(h, C.byref(p)))
+        return p
+
+    def deallocate_decayed_blocks(self, v=None):
+        return bool(self.params(**({} if v is None else {"deallocate_decayed_blocks": 1 if v else 0})).deallocate_decayed_blocks)
+
+    def decay_factor(self, v=None):
+        return self.params(**({} if v is None else {"decay_factor": float(v)})).decay_factor
+
+    def decay_to_free(self, v):
+        """OccupancyDecayIntegrator::decay_to_free (src/integrators/occupancy_decay_integrator.cu:59-72)."""
+        return self.params(decay_to_probability=0.49 if v else 0.5).decay_to_probability
+
+
 class _EsdfIntegrator:
     """EsdfIntegrator parameter surface (esdf_integrator.h:178-283) + integrateBlocks."""
 
@@ -326,6 +357,47 @@ class Mapper:
 
     def esdf_integrator(self):
         return _EsdfIntegrator(self)
+
+    def tsdf_decay_integrator(self):
+        return _DecayIntegrator(self, False)
+
+    def occupancy_decay_integrator(self):
+        return _DecayIntegrator(self, True)
+
+    def decay(self, depth=None, T_L_C=None, camera=None, excluded_blocks=None, exclusion_center=None,
+              exclusion_radius_m=None):
+        """Mapper::decayTsdf / decayOccupancy on the mapper's projective layer (mapper.h:268-292). depth=None: every
+        voxel decays (decay*AllVoxels); with a view, voxels that have a depth measurement in it are spared
+        (decay*ExcludeLastView -- pass the last integrated frame). Returns the (n,3) indices of the deallocated
+        blocks (gone from the projective and the ESDF layer)."""
+        x = NvbDecayExclusion()
+        keep = None
+        if excluded_blocks is not None and len(excluded_blocks):
+            keep = np.ascontiguousarray(excluded_blocks, dtype=np.int32).reshape(-1, 3)
+            x.excluded_blocks_xyz_host, x.num_excluded_blocks = _ip(keep), keep.shape[0]
+        if exclusion_center is not None and exclusion_radius_m is not None:
+            x.has_exclusion_sphere = 1
+            x.exclusion_center = (C.c_float * 3)(*[float(v) for v in exclusion_center])
+            x.exclusion_radius_m = float(exclusion_radius_m)
+        n = C.c_int32(0)
+        cap = max(self._tsdf.num_blocks() if self._projective_layer_type == 0 else self._occupancy.num_blocks(), 1)
+        out = np.zeros((cap, 3), dtype=np.int32)
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, dtype=np.float32)
+            T = colmajor(T_L_C)
+            check(self._L.nvb_mapper_decay(self._h, C.byref(x), depth.ctypes.data, _lib.NVB_MEM_HOST, depth.shape[0],
+                                           depth.shape[1], _fp(T), C.byref(camera.c), _ip(out), cap, C.byref(n)))
+        else:
+            check(self._L.nvb_mapper_decay(self._h, C.byref(x), None, 0, 0, 0, None, None, _ip(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def decay_tsdf(self, **kw):
+        assert self._projective_layer_type == ProjectiveLayerType.kTsdf
+        return self.decay(**kw)
+
+    def decay_occupancy(self, **kw):
+        assert self._projective_layer_type == ProjectiveLayerType.kOccupancy
+        return self.decay(**kw)
 
     def cuda_stream(self):
         return self._L.nvb_mapper_stream(self._h)

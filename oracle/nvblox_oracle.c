@@ -410,6 +410,34 @@ static int32_t layer_allocate(Layer* l, i3 k) {
 static void* layer_block(const Layer* l, int32_t slot) {
   return l->data + l->block_bytes * (size_t)slot;
 }
+/* BlockLayer::clearBlockAsync (map/internal/impl/layer_impl.h): the listed blocks (those that exist) leave the
+ * layer. Slots are an internal detail of this file: the survivors are compacted and the hash is rebuilt. */
+static void layer_remove_blocks(Layer* l, const i3* keys, int32_t n) {
+  if (n == 0 || l->n == 0) return;
+  uint8_t* dead = (uint8_t*)calloc((size_t)l->n, 1);
+  int any = 0;
+  for (int32_t i = 0; i < n; i++) {
+    const int32_t s = hash_find(&l->hash, keys[i]);
+    if (s >= 0) dead[s] = 1, any = 1;
+  }
+  if (any) {
+    int32_t w = 0;
+    for (int32_t s = 0; s < l->n; s++) {
+      if (dead[s]) continue;
+      if (w != s) {
+        l->index[w] = l->index[s];
+        memmove(l->data + l->block_bytes * (size_t)w, l->data + l->block_bytes * (size_t)s, l->block_bytes);
+      }
+      w++;
+    }
+    l->n = w;
+    const int32_t cap = l->hash.cap;
+    hash_free(&l->hash);
+    hash_init(&l->hash, cap);
+    for (int32_t s = 0; s < l->n; s++) hash_put(&l->hash, l->index[s], s);
+  }
+  free(dead);
+}
 
 /* Growable list of block indices. */
 typedef struct {
@@ -1250,6 +1278,176 @@ int32_t or_esdf_get_block(const OrMap* m, const int32_t xyz[3], OrEsdfVoxel* out
   memcpy(out, layer_block(&m->esdf, s), m->esdf.block_bytes);
   return 1;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Decay (integrators/internal/cuda/impl/decayer_impl.cuh)                   */
+/* ------------------------------------------------------------------------- */
+
+/* doesVoxelHaveDepthMeasurement (integrators/internal/cuda/impl/projective_integrators_common_impl.cuh:58-101). */
+static int voxel_has_depth_measurement(i3 bi, int vx, int vy, int vz, const float* depth, int rows, int cols,
+                                       const float* T_C_L, const OrCamera* cam, float block_size, float max_distance,
+                                       float truncation_distance) {
+  const float voxel_size = block_size * (1.0f / VPS);
+  const float half_voxel = block_size * (0.5f / VPS);
+  v3 p_L;
+  p_L.x = (block_size * (float)bi.x + voxel_size * (float)vx) + half_voxel;
+  p_L.y = (block_size * (float)bi.y + voxel_size * (float)vy) + half_voxel;
+  p_L.z = (block_size * (float)bi.z + voxel_size * (float)vz) + half_voxel;
+  const v3 p_C = transform_point(T_C_L, p_L);
+  float u, v;
+  if (!cam_project(cam, p_C, &u, &v)) return 0;
+  const float voxel_depth = p_C.z;
+  if (max_distance > 0.0f && voxel_depth > max_distance) return 0;
+  const int ux = f2i(floorf(u)), uy = f2i(floorf(v));
+  if (ux < 0 || uy < 0 || ux >= cols || uy >= rows) return 0;
+  const float d = depth[(size_t)uy * cols + ux];
+  if (!(isfinite(d) && d > 1e-6f)) return 0; /* invalid depth: not in view */
+  if (d - voxel_depth < -truncation_distance) return 0; /* occluded */
+  return 1;
+}
+
+/* getBlockIndicesToDecay (decayer_impl.cuh:38-80): 1 = decay this block. */
+static int decay_block_selected(const OrMap* map, i3 k, const Hash* excluded, const OrDecayExclusion* X) {
+  if (excluded && hash_find(excluded, k) >= 0) return 0;
+  if (X && X->has_exclusion_sphere && X->exclusion_radius_m * X->exclusion_radius_m > 0.0f) {
+    /* getPositionFromBlockIndex (indexing_impl.h): block origin = block_size * index */
+    const float px = map->block_size * (float)k.x, py = map->block_size * (float)k.y, pz = map->block_size * (float)k.z;
+    const float dx = px - X->exclusion_center[0], dy = py - X->exclusion_center[1], dz = pz - X->exclusion_center[2];
+    const float d2 = sum3(dx * dx, dy * dy, dz * dz);
+    return d2 > X->exclusion_radius_m * X->exclusion_radius_m;
+  }
+  return 1;
+}
+
+/* TsdfDecayFunctor (integrators/internal/cuda/impl/tsdf_decay_integrator_impl.cuh:25-75). */
+static int tsdf_is_fully_decayed(const OrTsdfVoxel* v, float thr) { return v->weight < (thr + 1e-6f); }
+static void tsdf_decay_voxel(OrTsdfVoxel* v, const OrTsdfDecayParams* P, float free_distance_m) {
+  float weight = v->weight;
+  if (weight < (P->decayed_weight_threshold - 1e-6f)) return;
+  weight *= P->decay_factor;
+  weight = fmaxf(weight, P->decayed_weight_threshold);
+  v->weight = weight;
+  if (P->set_free_distance_on_decayed && tsdf_is_fully_decayed(v, P->decayed_weight_threshold)) v->distance = free_distance_m;
+}
+
+/* OccupancyDecayFunctor (integrators/internal/cuda/impl/occupancy_decay_integrator_impl.cuh:26-70). */
+typedef struct {
+  float free_lo, occ_lo, to_lo;
+} OccDecay;
+static int occ_is_fully_decayed(float lo, const OccDecay* f) {
+  if (lo >= f->to_lo) return lo + f->occ_lo < f->to_lo;
+  return lo + f->free_lo >= f->to_lo;
+}
+static void occ_decay_voxel(float* lo, const OccDecay* f) {
+  if (occ_is_fully_decayed(*lo, f)) {
+    *lo = f->to_lo;
+    return;
+  }
+  if (*lo >= 0) *lo += f->occ_lo;
+  else *lo += f->free_lo;
+}
+
+/* VoxelDecayer::decay (decayer_impl.cuh:150-262) followed by Mapper::clearBlocksInLayers for the removed blocks
+ * (src/mapper/mapper.cpp:546-575) when `clear_esdf` is set. */
+static int32_t decay_layer(OrMap* map, int occupancy, const void* params, const OrDecayExclusion* X, const float* depth,
+                           int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam, float max_view_distance_m,
+                           float truncation_distance_m, int32_t deallocate, int32_t clear_esdf, int32_t* out_xyz,
+                           int32_t cap) {
+  Layer* L = occupancy ? &map->occ : &map->tsdf;
+  if (L->n == 0) return 0;
+  Hash excl;
+  Hash* exclp = NULL;
+  if (X && X->num_excluded_blocks > 0) {
+    int32_t hc = 16;
+    while (hc < 4 * X->num_excluded_blocks) hc *= 2;
+    hash_init(&excl, hc);
+    for (int32_t i = 0; i < X->num_excluded_blocks; i++) {
+      i3 k = {X->excluded_blocks_xyz[3 * i], X->excluded_blocks_xyz[3 * i + 1], X->excluded_blocks_xyz[3 * i + 2]};
+      if (hash_find(&excl, k) < 0) hash_put(&excl, k, i);
+    }
+    exclp = &excl;
+  }
+  float T_C_L[16];
+  if (depth) invert_isometry(T_L_C, T_C_L);
+  const OrTsdfDecayParams* TP = (const OrTsdfDecayParams*)params;
+  const OrOccupancyDecayParams* OP = (const OrOccupancyDecayParams*)params;
+  OccDecay of = {0, 0, 0};
+  float free_distance_m = 0.0f;
+  if (occupancy) {
+    of.free_lo = log_odds_from_probability(OP->free_region_decay_probability);
+    of.occ_lo = log_odds_from_probability(OP->occupied_region_decay_probability);
+    of.to_lo = log_odds_from_probability(OP->decay_to_probability);
+  } else {
+    free_distance_m = TP->free_distance_vox * map->voxel_size;
+  }
+  uint8_t* fully = (uint8_t*)calloc((size_t)L->n, 1);
+  uint8_t* selected = (uint8_t*)calloc((size_t)L->n, 1);
+#pragma omp parallel for schedule(static)
+  for (int32_t s = 0; s < L->n; s++) {
+    const i3 k = L->index[s];
+    if (!decay_block_selected(map, k, exclp, X)) continue;
+    selected[s] = 1;
+    int all = 1;
+    for (int vx = 0; vx < VPS; vx++)
+      for (int vy = 0; vy < VPS; vy++)
+        for (int vz = 0; vz < VPS; vz++) {
+          const int v = (vx * VPS + vy) * VPS + vz;
+          const int do_decay = depth ? !voxel_has_depth_measurement(k, vx, vy, vz, depth, rows, cols, T_C_L, cam, map->block_size,
+                                                                    max_view_distance_m, truncation_distance_m)
+                                     : 1;
+          if (occupancy) {
+            float* lo = (float*)layer_block(L, s) + v;
+            if (do_decay) occ_decay_voxel(lo, &of);
+            if (!occ_is_fully_decayed(*lo, &of)) all = 0;
+          } else {
+            OrTsdfVoxel* tv = (OrTsdfVoxel*)layer_block(L, s) + v;
+            if (do_decay) tsdf_decay_voxel(tv, TP, free_distance_m);
+            if (!tsdf_is_fully_decayed(tv, TP->decayed_weight_threshold)) all = 0;
+          }
+        }
+    fully[s] = (uint8_t)all;
+  }
+  int32_t n_removed = 0;
+  if (deallocate) {
+    List rm = {0};
+    for (int32_t s = 0; s < L->n; s++)
+      if (selected[s] && fully[s]) list_push(&rm, L->index[s]);
+    n_removed = copy_out(&rm, out_xyz, cap);
+    layer_remove_blocks(L, rm.v, rm.n);
+    if (clear_esdf) layer_remove_blocks(&map->esdf, rm.v, rm.n);
+    list_free(&rm);
+  }
+  free(fully), free(selected);
+  if (exclp) hash_free(exclp);
+  return n_removed;
+}
+
+void or_default_tsdf_decay_params(OrTsdfDecayParams* p) {
+  p->decay_factor = 0.95f;
+  p->decayed_weight_threshold = 1e-3f;
+  p->set_free_distance_on_decayed = 0;
+  p->free_distance_vox = 4.0f;
+  p->deallocate_decayed_blocks = 1;
+}
+void or_default_occupancy_decay_params(OrOccupancyDecayParams* p) {
+  p->free_region_decay_probability = 0.55f;
+  p->occupied_region_decay_probability = 0.4f;
+  p->decay_to_probability = 0.5f;
+  p->deallocate_decayed_blocks = 1;
+}
+int32_t or_tsdf_decay(OrMap* map, const OrTsdfDecayParams* P, const OrDecayExclusion* X, const float* depth, int32_t rows,
+                      int32_t cols, const float* T_L_C, const OrCamera* cam, float max_view_distance_m,
+                      float truncation_distance_m, int32_t clear_esdf, int32_t* out_xyz, int32_t cap) {
+  return decay_layer(map, 0, P, X, depth, rows, cols, T_L_C, cam, max_view_distance_m, truncation_distance_m,
+                     P->deallocate_decayed_blocks, clear_esdf, out_xyz, cap);
+}
+int32_t or_occupancy_decay(OrMap* map, const OrOccupancyDecayParams* P, const OrDecayExclusion* X, const float* depth,
+                           int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam, float max_view_distance_m,
+                           float truncation_distance_m, int32_t clear_esdf, int32_t* out_xyz, int32_t cap) {
+  return decay_layer(map, 1, P, X, depth, rows, cols, T_L_C, cam, max_view_distance_m, truncation_distance_m,
+                     P->deallocate_decayed_blocks, clear_esdf, out_xyz, cap);
+}
+
 void or_tsdf_set_block(OrMap* m, const int32_t xyz[3], const OrTsdfVoxel* in) {
   i3 k = {xyz[0], xyz[1], xyz[2]};
   int32_t s = layer_allocate(&m->tsdf, k);

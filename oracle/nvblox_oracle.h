@@ -151,6 +151,43 @@ int32_t or_occupancy_get_block(const OrMap* map, const int32_t xyz[3], float* ou
 /* Test helper: overwrite / create an occupancy block (512 log-odds, [x][y][z] order). */
 void or_occupancy_set_block(OrMap* map, const int32_t xyz[3], const float* in_log_odds);
 
+/* TsdfDecayIntegrator / OccupancyDecayIntegrator (integrators/tsdf_decay_integrator_params.h:21-48,
+ * occupancy_decay_integrator_params.h:21-43, internal/decay_integrator_base_params.h:22-29). */
+typedef struct {
+  float decay_factor;                   /* 0.95 */
+  float decayed_weight_threshold;       /* 1e-3 */
+  int32_t set_free_distance_on_decayed; /* 0    */
+  float free_distance_vox;              /* 4    */
+  int32_t deallocate_decayed_blocks;    /* 1    */
+} OrTsdfDecayParams;
+typedef struct {
+  float free_region_decay_probability;     /* 0.55 */
+  float occupied_region_decay_probability; /* 0.4  */
+  float decay_to_probability;              /* 0.5 (Mapper's occupancy_decay_to_free: 0.49, occupancy_decay_integrator.h:35-36) */
+  int32_t deallocate_decayed_blocks;       /* 1    */
+} OrOccupancyDecayParams;
+/* DecayBlockExclusionOptions (integrators/internal/decayer.h:31-44). */
+typedef struct {
+  const int32_t* excluded_blocks_xyz;
+  int32_t num_excluded_blocks;
+  int32_t has_exclusion_sphere;
+  float exclusion_center[3];
+  float exclusion_radius_m;
+} OrDecayExclusion;
+void or_default_tsdf_decay_params(OrTsdfDecayParams* p);
+void or_default_occupancy_decay_params(OrOccupancyDecayParams* p);
+/* VoxelDecayer::decay (integrators/internal/cuda/impl/decayer_impl.cuh:150-262). depth == NULL: every voxel decays;
+ * otherwise voxels with a depth measurement in that view are spared (DepthObservationSpace). clear_esdf: also remove
+ * the deallocated blocks from the ESDF layer, like Mapper::decayTsdfInternal does. Returns the number of deallocated
+ * blocks, writes up to cap triples. `exclusion` may be NULL. */
+int32_t or_tsdf_decay(OrMap* map, const OrTsdfDecayParams* params, const OrDecayExclusion* exclusion, const float* depth,
+                      int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam, float max_view_distance_m,
+                      float truncation_distance_m, int32_t clear_esdf, int32_t* out_xyz, int32_t cap);
+int32_t or_occupancy_decay(OrMap* map, const OrOccupancyDecayParams* params, const OrDecayExclusion* exclusion,
+                           const float* depth, int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam,
+                           float max_view_distance_m, float truncation_distance_m, int32_t clear_esdf, int32_t* out_xyz,
+                           int32_t cap);
+
 /* EsdfIntegrator::integrateBlocks(TsdfLayer, blocks, EsdfLayer*). */
 void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,
                        const OrEsdfParams* params);

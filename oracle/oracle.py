@@ -72,6 +72,23 @@ class OccupancyParams(C.Structure):
                 ("occupied_region_half_width_m", C.c_float)]
 
 
+class TsdfDecayParams(C.Structure):
+    _fields_ = [("decay_factor", C.c_float), ("decayed_weight_threshold", C.c_float),
+                ("set_free_distance_on_decayed", C.c_int32), ("free_distance_vox", C.c_float),
+                ("deallocate_decayed_blocks", C.c_int32)]
+
+
+class OccupancyDecayParams(C.Structure):
+    _fields_ = [("free_region_decay_probability", C.c_float), ("occupied_region_decay_probability", C.c_float),
+                ("decay_to_probability", C.c_float), ("deallocate_decayed_blocks", C.c_int32)]
+
+
+class DecayExclusion(C.Structure):
+    _fields_ = [("excluded_blocks_xyz", C.POINTER(C.c_int32)), ("num_excluded_blocks", C.c_int32),
+                ("has_exclusion_sphere", C.c_int32), ("exclusion_center", C.c_float * 3),
+                ("exclusion_radius_m", C.c_float)]
+
+
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
     if force or not os.path.exists(_LIB_PATH) or (
@@ -135,6 +152,15 @@ def lib():
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.restype = None
+    L.or_default_tsdf_decay_params.argtypes = [C.POINTER(TsdfDecayParams)]
+    L.or_default_tsdf_decay_params.restype = None
+    L.or_default_occupancy_decay_params.argtypes = [C.POINTER(OccupancyDecayParams)]
+    L.or_default_occupancy_decay_params.restype = None
+    for name, ptype in (("or_tsdf_decay", TsdfDecayParams), ("or_occupancy_decay", OccupancyDecayParams)):
+        f = getattr(L, name)
+        f.argtypes = [vp, C.POINTER(ptype), C.POINTER(DecayExclusion), fp, C.c_int32, C.c_int32, fp, C.POINTER(Camera),
+                      C.c_float, C.c_float, C.c_int32, ip, C.c_int32]
+        f.restype = C.c_int32
     L.or_camera_project.argtypes = [C.POINTER(Camera), fp, fp]
     L.or_camera_project.restype = C.c_int32
     L.or_camera_vector_from_image_plane.argtypes = [C.POINTER(Camera), C.c_float, C.c_float, fp]
@@ -171,6 +197,22 @@ def default_tsdf_params(**kw):
 def default_esdf_params(**kw):
     p = EsdfParams()
     lib().or_default_esdf_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_tsdf_decay_params(**kw):
+    p = TsdfDecayParams()
+    lib().or_default_tsdf_decay_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_occupancy_decay_params(**kw):
+    p = OccupancyDecayParams()
+    lib().or_default_occupancy_decay_params(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -282,6 +324,49 @@ class OracleMap:
             lib().or_occupancy_get_block(self._h, _ip(np.ascontiguousarray(k, dtype=np.int32)), blk.ctypes.data)
             out[tuple(int(c) for c in k)] = blk
         return out
+
+    def _decay(self, fn, params, depth, T_L_C, cam, max_view_distance_m, truncation_distance_m, excluded_blocks,
+               exclusion_center, exclusion_radius_m, clear_esdf, cap):
+        x = DecayExclusion()
+        keep = None
+        if excluded_blocks is not None and len(excluded_blocks):
+            keep = np.ascontiguousarray(excluded_blocks, dtype=np.int32).reshape(-1, 3)
+            x.excluded_blocks_xyz, x.num_excluded_blocks = _ip(keep), keep.shape[0]
+        if exclusion_center is not None and exclusion_radius_m is not None:
+            x.has_exclusion_sphere = 1
+            x.exclusion_center = (C.c_float * 3)(*[float(v) for v in exclusion_center])
+            x.exclusion_radius_m = float(exclusion_radius_m)
+        out = np.zeros((cap, 3), dtype=np.int32)
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, dtype=np.float32)
+            T = colmajor(T_L_C)
+            n = fn(self._h, C.byref(params), C.byref(x), _fp(depth), depth.shape[0], depth.shape[1], _fp(T), C.byref(cam),
+                   float(max_view_distance_m), float(truncation_distance_m), 1 if clear_esdf else 0, _ip(out), cap)
+        else:
+            n = fn(self._h, C.byref(params), C.byref(x), None, 0, 0, None, None, 0.0, 0.0, 1 if clear_esdf else 0,
+                   _ip(out), cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def decay_tsdf(self, params=None, depth=None, T_L_C=None, cam=None, max_view_distance_m=7.0,
+                   truncation_distance_m=None, excluded_blocks=None, exclusion_center=None, exclusion_radius_m=None,
+                   clear_esdf=True, cap=1 << 20):
+        """TsdfDecayIntegrator::decay (+ Mapper::clearBlocksInLayers for the ESDF layer). depth=None decays every voxel;
+        with a view (depth, T_L_C, cam) voxels that have a depth measurement are spared. Returns deallocated indices."""
+        if truncation_distance_m is None:
+            truncation_distance_m = 4.0 * self.voxel_size
+        return self._decay(lib().or_tsdf_decay, params or default_tsdf_decay_params(), depth, T_L_C, cam,
+                           max_view_distance_m, truncation_distance_m, excluded_blocks, exclusion_center,
+                           exclusion_radius_m, clear_esdf, cap)
+
+    def decay_occupancy(self, params=None, depth=None, T_L_C=None, cam=None, max_view_distance_m=7.0,
+                        truncation_distance_m=None, excluded_blocks=None, exclusion_center=None, exclusion_radius_m=None,
+                        clear_esdf=True, cap=1 << 20):
+        if truncation_distance_m is None:
+            truncation_distance_m = 4.0 * self.voxel_size
+        return self._decay(lib().or_occupancy_decay, params or default_occupancy_decay_params(), depth, T_L_C, cam,
+                           max_view_distance_m, truncation_distance_m, excluded_blocks, exclusion_center,
+                           exclusion_radius_m, clear_esdf, cap)
 
     def set_occupancy_block(self, idx, log_odds):
         k = np.asarray(idx, dtype=np.int32)

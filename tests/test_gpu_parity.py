@@ -312,6 +312,52 @@ def test_esdf_gather_replay_640x480_with_growth(gpu):
     m.close()
 
 
+@pytest.mark.parametrize("mark_tma", ["1", "0"])
+def test_esdf_small_grids_exercise_multi_round_paths(gpu, mark_tma):
+    """Runs in a subprocess with NVB_ESDF_GRID_CAP=3 (the cap is read once per process): three CTAs mark ~1000 blocks
+    each (per-CTA lists flush when full) and the clear kernel needs several selection rounds of 256 slots per CTA."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        from helpers import assert_esdf_equal, assert_tsdf_equal, cameras
+        from isaac_ros_nvblox_b200 import synthetic as syn
+        import isaac_ros_nvblox_b200 as nvb
+        from oracle import oracle as orc
+        cs, cam, ocam = cameras(320, 240)
+        frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:4])
+        m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+        for i, (d, T) in enumerate(frames):
+            b = m.integrate_depth(d, T, cam)
+            o.integrate_depth(d, T, ocam)
+            m.update_esdf()
+            o.integrate_esdf(b if i > 0 else o.tsdf_block_indices())
+        assert m.esdf_layer().num_blocks() > 3 * 256 * 2
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+        m.close()
+        print("ok")
+    """) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, NVB_ESDF_GRID_CAP="3", NVB_MARK_TMA=mark_tma)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_esdf_gather_replay_2cm_many_candidates(gpu):
+    """2 cm voxels: rings with thousands of candidates (several chunks of 32 per CTA in the gather-replay kernel)."""
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(80)[:2])
+    import os as _os
+    _os.environ["NVB_GES_SWITCH"] = "100000"
+    try:
+        m, o = _run_pair(0.02, frames, cam, ocam, esdf=True, tsdf_kw=dict(max_integration_distance_m=4.0),
+                         mapper_kw=dict(esdf_persistent=2), check_every_frame=False)
+    finally:
+        _os.environ.pop("NVB_GES_SWITCH", None)
+    assert m.esdf_layer().num_blocks() > 10000
+    m.close()
+
+
 def test_esdf_640x480_5cm_sequence(gpu):
     cs, cam, ocam = cameras()
     frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(80)[:4])

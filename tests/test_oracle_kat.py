@@ -573,3 +573,206 @@ def test_esdf_from_occupancy_close_to_ground_truth(make_scene):
             bad += 1
     assert sites > 1000 and n > 10000
     assert bad / n < 0.002  # very_small_cutoff_, test_esdf_integrator.cpp:78-80
+
+
+# --- decay: test_tsdf_decay.cpp, test_occupancy_decay.cpp ---------------------------------
+def _gt_tsdf_map(voxel=0.2, trunc_vox=2.0):
+    """TsdfDecayIntegratorTestFixture::SetUp (test_tsdf_decay.cpp:39-45): Scene::generateLayerFromScene<TsdfVoxel> of
+    getSphereInBox -- distance truncated to +-max_dist, weight 1 inside the scene AABB."""
+    scene = syn.sphere_in_box()
+    m = orc.OracleMap(voxel)
+    ii = (np.indices((8, 8, 8)).reshape(3, -1).T + 0.5)
+    bs = 8 * voxel
+    lo_b = np.floor(np.array([-5.5, -5.5, -0.5]) / bs).astype(int)
+    hi_b = np.floor(np.array([5.5, 5.5, 5.5]) / bs).astype(int)
+    max_dist = trunc_vox * voxel
+    for x in range(lo_b[0], hi_b[0] + 1):
+        for y in range(lo_b[1], hi_b[1] + 1):
+            for z in range(lo_b[2], hi_b[2] + 1):
+                pos = (np.array([x, y, z]) * 8 + ii) * voxel
+                inside = np.all((pos >= [-5.5, -5.5, -0.5]) & (pos <= [5.5, 5.5, 5.5]), axis=1)
+                blk = np.zeros(512, dtype=orc.TSDF_VOXEL_DTYPE)
+                blk["distance"] = np.where(inside, np.clip(scene.distance(pos), -max_dist, max_dist), 0).astype(np.float32)
+                blk["weight"] = inside.astype(np.float32)
+                m.set_tsdf_block((x, y, z), blk.reshape(8, 8, 8))
+    return m
+
+
+def test_decay_empty_layer():
+    """EmptyLayer (test_tsdf_decay.cpp:55-66), EmptyLayerTest (test_occupancy_decay.cpp:78-90)."""
+    m = orc.OracleMap(0.2)
+    assert len(m.decay_tsdf()) == 0 and len(m.decay_occupancy()) == 0
+    assert len(m.tsdf_block_indices()) == 0
+
+
+def test_tsdf_single_decay():
+    """SingleDecay (test_tsdf_decay.cpp:69-97): every weight is multiplied by the decay factor."""
+    m = _gt_tsdf_map()
+    before = m.tsdf_layer()
+    removed = m.decay_tsdf(orc.default_tsdf_decay_params(decay_factor=0.75, deallocate_decayed_blocks=0))
+    assert len(removed) == 0
+    after = m.tsdf_layer()
+    assert set(before) == set(after)
+    for k, b in before.items():
+        assert np.allclose(b["weight"] * np.float32(0.75), after[k]["weight"], atol=1e-6)
+        assert np.array_equal(b["distance"], after[k]["distance"])
+
+
+def test_tsdf_single_decay_with_exclusion_list_and_sphere():
+    """SingleDecayWithExclusionList / SingleDecayWithRadialExclusion (test_tsdf_decay.cpp:100-186)."""
+    m = _gt_tsdf_map()
+    before = m.tsdf_layer()
+    excluded = np.array([k for k in before if k[0] % 2 == 0 or k[1] % 2 == 0 or k[2] % 2 == 0], np.int32)
+    assert len(excluded) > 0
+    m.decay_tsdf(orc.default_tsdf_decay_params(decay_factor=0.75, deallocate_decayed_blocks=0), excluded_blocks=excluded)
+    after = m.tsdf_layer()
+    ex = set(map(tuple, excluded.tolist()))
+    for k, b in before.items():
+        if k in ex:
+            assert np.array_equal(b["weight"], after[k]["weight"])
+        else:
+            assert np.allclose(b["weight"] * np.float32(0.75), after[k]["weight"], atol=1e-6)
+    m2 = _gt_tsdf_map()
+    r = float(np.sqrt(0.025))
+    m2.decay_tsdf(orc.default_tsdf_decay_params(decay_factor=0.75, deallocate_decayed_blocks=0),
+                  exclusion_center=(1.0, 1.0, 1.0), exclusion_radius_m=r)
+    after2 = m2.tsdf_layer()
+    n_in = 0
+    for k, b in before.items():
+        origin = np.asarray(k, np.float32) * np.float32(1.6)
+        if float(((origin - 1.0) ** 2).sum()) < 0.025:
+            assert np.array_equal(b["weight"], after2[k]["weight"])
+            n_in += 1
+        else:
+            assert np.allclose(b["weight"] * np.float32(0.75), after2[k]["weight"], atol=1e-6)
+
+
+def test_tsdf_decay_until_removed():
+    """DecayUntilRemoved (test_tsdf_decay.cpp:189-205): with the defaults every block is eventually deallocated."""
+    m = _gt_tsdf_map()
+    n0 = len(m.tsdf_block_indices())
+    removed = it = 0
+    while len(m.tsdf_block_indices()) > 0 and it < 1000:
+        removed += len(m.decay_tsdf())
+        it += 1
+    assert 0 < it < 1000 and len(m.tsdf_block_indices()) == 0 and removed == n0
+
+
+def test_tsdf_decay_to_free():
+    """TsdfDecayToFree (test_tsdf_decay.cpp:235-291)."""
+    m = _gt_tsdf_map()
+    p = orc.default_tsdf_decay_params(set_free_distance_on_decayed=1, deallocate_decayed_blocks=0)
+    obs_before = sum(int((b["weight"] > 1e-6).sum()) for b in m.tsdf_layer().values())
+    it = 0
+    while any((b["weight"] > p.decayed_weight_threshold + 1e-6).any() for b in m.tsdf_layer().values()) and it < 1000:
+        assert len(m.decay_tsdf(p)) == 0
+        it += 1
+    layer = m.tsdf_layer()
+    assert len(layer) > 0
+    for b in layer.values():
+        o = b["weight"] > 0
+        assert np.allclose(b["weight"][o], p.decayed_weight_threshold, atol=1e-6)
+        assert np.allclose(b["distance"][o], p.free_distance_vox * 0.2, atol=1e-6)
+    assert obs_before == sum(int((b["weight"] > 1e-6).sum()) for b in layer.values())
+
+
+def test_tsdf_decay_exclude_view():
+    """TsdfDecayExcludeView (test_tsdf_decay.cpp:321-404): only voxels without a depth measurement decay."""
+    voxel, trunc_m = 0.2, 0.4
+    m = _gt_tsdf_map(voxel)
+    cs = syn.PinholeCamera()
+    cam = _cam()
+    q = np.array([0.5123, 0.5456, 0.5789, 0.5])
+    q = q / np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = [-4.0, 0.0, 2.0]
+    depth = syn.render_depth(syn.sphere_in_box(), cs, T, max_dist=10.0, invalid_depth=-1.0)
+    before = m.tsdf_layer()
+    removed = m.decay_tsdf(depth=depth, T_L_C=T.astype(np.float32), cam=cam, max_view_distance_m=10.0,
+                           truncation_distance_m=trunc_m)
+    assert len(removed) == 0
+    after = m.tsdf_layer()
+    Tinv = np.linalg.inv(T)
+    ii = (np.indices((8, 8, 8)).reshape(3, -1).T + 0.5)
+    n_dec = n_not = 0
+    for k, b in before.items():
+        pos = (np.asarray(k) * 8 + ii) * voxel
+        pc = pos @ Tinv[:3, :3].T + Tinv[:3, 3]
+        zc = pc[:, 2]
+        ok = (zc >= 1e-6) & (zc <= 10.0)
+        u = pc[:, 0] / np.where(ok, zc, 1) * 300.0 + 320.0
+        v = pc[:, 1] / np.where(ok, zc, 1) * 300.0 + 240.0
+        ok &= (u >= 0) & (v >= 0) & (u < 640) & (v < 480)
+        d = depth[np.clip(np.floor(v).astype(int), 0, 479), np.clip(np.floor(u).astype(int), 0, 639)]
+        margin = np.abs((d - zc) + trunc_m)  # voxels within float noise of the occlusion boundary are not checked
+        in_view = ok & (d > 1e-6) & (d - zc >= -trunc_m)
+        w0 = b["weight"].reshape(-1)
+        w1 = after[k]["weight"].reshape(-1)
+        valid = (w0 > 1e-3) & (margin > 1e-3)
+        frac_u, frac_v = u - np.floor(u), v - np.floor(v)
+        valid &= (frac_u > 1e-3) & (frac_u < 1 - 1e-3) & (frac_v > 1e-3) & (frac_v < 1 - 1e-3)
+        not_decayed = (w0 - w1) < 1e-3
+        assert np.all(not_decayed[valid] == in_view[valid])
+        n_dec += int((~not_decayed & valid).sum())
+        n_not += int((not_decayed & valid).sum())
+    assert n_dec > 0 and n_not > 0
+
+
+def _encode_log_odds(block, voxel, max_lo=1000.0):
+    """A deterministic, sign-alternating pattern (stands in for encodeIndexToLogOdds, test_occupancy_decay.cpp:27-41)."""
+    v = (abs(block[0]) * 7 + abs(block[1]) * 13 + abs(block[2]) * 31 + voxel[0] * 64 + voxel[1] * 8 + voxel[2]) * 0.37
+    sign = -1.0 if (voxel[0] + voxel[1] + voxel[2] + block[0]) % 2 else 1.0
+    return np.float32(sign * min(v, max_lo))
+
+
+def _occ_test_map(n_blocks=40, max_lo=1000.0):
+    rng = np.random.default_rng(0)
+    m = orc.OracleMap(0.05)
+    keys = set()
+    while len(keys) < n_blocks:
+        keys.add(tuple(int(c) for c in np.floor(rng.uniform(-100, 100, 3) / 0.4)))
+    init = {}
+    for k in keys:
+        blk = np.array([[[_encode_log_odds(k, (x, y, z), max_lo) for z in range(8)] for y in range(8)] for x in range(8)],
+                       np.float32)
+        m.set_occupancy_block(k, blk)
+        init[k] = blk
+    return m, init
+
+
+def test_occupancy_single_decay():
+    """SingleDecayTest (test_occupancy_decay.cpp:92-148)."""
+    m, init = _occ_test_map()
+    p = orc.default_occupancy_decay_params(deallocate_decayed_blocks=0)
+    assert len(m.decay_occupancy(p)) == 0
+    lo_occ, lo_free = _log_odds(0.4), _log_odds(0.55)
+    after = m.occupancy_layer()
+    assert set(after) == set(init)
+    for k, b in init.items():
+        a = after[k]
+        pos = b >= 0
+        exp = np.where(pos, np.where(b + lo_occ < 0, np.float32(0), b + lo_occ), np.where(b + lo_free >= 0, np.float32(0), b + lo_free))
+        assert np.allclose(a, exp.astype(np.float32), atol=1e-6)
+
+
+@pytest.mark.parametrize("to_p", [0.5, 0.4])
+def test_occupancy_decay_all(to_p):
+    """decayAllTo05 / decayAllTo04 (test_occupancy_decay.cpp:150-214)."""
+    m, init = _occ_test_map(n_blocks=20, max_lo=200.0)
+    step = 1.5
+    p = orc.default_occupancy_decay_params(free_region_decay_probability=float(np.exp(step) / (1 + np.exp(step))),
+                                           occupied_region_decay_probability=float(np.exp(-step) / (1 + np.exp(-step))),
+                                           decay_to_probability=to_p, deallocate_decayed_blocks=0)
+    for _ in range(int(200.0 / step) + 1):
+        assert len(m.decay_occupancy(p)) == 0
+    target = _log_odds(to_p)
+    for b in m.occupancy_layer().values():
+        assert np.all(b == target)
+    p.deallocate_decayed_blocks = 1
+    removed = m.decay_occupancy(p)
+    assert len(removed) == len(init) and len(m.occupancy_block_indices()) == 0
