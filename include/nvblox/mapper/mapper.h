@@ -7,6 +7,8 @@
 //   tsdf_integrator() / esdf_integrator()                  mapper.h:442,534
 //   Mapper(voxel_size_m, memory_type, ProjectiveLayerType::kOccupancy), occupancy_layer(), occupancy_integrator()
 //                                                          mapper.h:52-53,119-124,374,456
+//   decayTsdfAllVoxels / decayTsdfExcludeLastView / decayOccupancy...   mapper.h:218-233
+//   tsdf_decay_integrator() / occupancy_decay_integrator()  mapper.h:496-504
 #pragma once
 #include <vector>
 #include "nvblox/integrators/weighting_function.h"
@@ -96,6 +98,46 @@ class ProjectiveOccupancyIntegrator {
   NvbMapper* m_;
 };
 
+// TsdfDecayIntegrator / OccupancyDecayIntegrator parameter surfaces (integrators/tsdf_decay_integrator.h:73-101,
+// occupancy_decay_integrator.h:72-101, internal/decay_integrator_base.h:50-58).
+class TsdfDecayIntegrator {
+ public:
+  explicit TsdfDecayIntegrator(NvbMapper* m) : m_(m) {}
+  bool deallocate_decayed_blocks() const { return get().deallocate_decayed_blocks != 0; }
+  void deallocate_decayed_blocks(bool v) { auto p = get(); p.deallocate_decayed_blocks = v ? 1 : 0; set(p); }
+  float decay_factor() const { return get().decay_factor; }
+  void decay_factor(float v) { auto p = get(); p.decay_factor = v; set(p); }
+  float decayed_weight_threshold() const { return get().decayed_weight_threshold; }
+  void decayed_weight_threshold(float v) { auto p = get(); p.decayed_weight_threshold = v; set(p); }
+  bool set_free_distance_on_decayed() const { return get().set_free_distance_on_decayed != 0; }
+  void set_free_distance_on_decayed(bool v) { auto p = get(); p.set_free_distance_on_decayed = v ? 1 : 0; set(p); }
+  float free_distance_vox() const { return get().free_distance_vox; }
+  void free_distance_vox(float v) { auto p = get(); p.free_distance_vox = v; set(p); }
+ private:
+  NvbTsdfDecayParams get() const { NvbTsdfDecayParams p; b200_detail::check(nvb_mapper_get_tsdf_decay_params(m_, &p), "tsdf decay params", nvb_last_error()); return p; }
+  void set(const NvbTsdfDecayParams& p) { b200_detail::check(nvb_mapper_set_tsdf_decay_params(m_, &p), "tsdf decay params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+class OccupancyDecayIntegrator {
+ public:
+  static constexpr float kDefaultProbabilityUnknown = 0.5f;
+  static constexpr float kDefaultProbabilityFree = 0.49f;
+  explicit OccupancyDecayIntegrator(NvbMapper* m) : m_(m) {}
+  bool deallocate_decayed_blocks() const { return get().deallocate_decayed_blocks != 0; }
+  void deallocate_decayed_blocks(bool v) { auto p = get(); p.deallocate_decayed_blocks = v ? 1 : 0; set(p); }
+  float free_region_decay_probability() const { return get().free_region_decay_probability; }
+  void free_region_decay_probability(float v) { auto p = get(); p.free_region_decay_probability = v; set(p); }
+  float occupied_region_decay_probability() const { return get().occupied_region_decay_probability; }
+  void occupied_region_decay_probability(float v) { auto p = get(); p.occupied_region_decay_probability = v; set(p); }
+  float decay_to_probability() const { return get().decay_to_probability; }
+  void decay_to_probability(float v) { auto p = get(); p.decay_to_probability = v; set(p); }
+  void decay_to_free(bool v) { decay_to_probability(v ? kDefaultProbabilityFree : kDefaultProbabilityUnknown); }
+ private:
+  NvbOccupancyDecayParams get() const { NvbOccupancyDecayParams p; b200_detail::check(nvb_mapper_get_occupancy_decay_params(m_, &p), "occupancy decay params", nvb_last_error()); return p; }
+  void set(const NvbOccupancyDecayParams& p) { b200_detail::check(nvb_mapper_set_occupancy_decay_params(m_, &p), "occupancy decay params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+
 // EsdfIntegrator (integrators/esdf_integrator.h:45-401): parameters + integrateBlocks.
 class EsdfIntegrator {
  public:
@@ -135,6 +177,7 @@ class Mapper {
     nvb_default_mapper_options(&o);
     o.voxel_size_m = voxel_size_m;
     // kTsdfWithFreespace / kNone are outside this path: nvb_mapper_create rejects them.
+    o.keep_last_view = 1;  // Mapper::integrateDepth keeps the last posed depth image for the decay (mapper_impl.h:70-78)
     o.projective_layer_type = projective_layer_type == ProjectiveLayerType::kTsdf        ? NVB_PROJECTIVE_TSDF
                               : projective_layer_type == ProjectiveLayerType::kOccupancy ? NVB_PROJECTIVE_OCCUPANCY
                                                                                          : -1;
@@ -155,6 +198,13 @@ class Mapper {
     b200_detail::check(nvb_mapper_update_esdf(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdf", nvb_last_error());
   }
   void clear() { b200_detail::check(nvb_mapper_clear(m_), "clear", nvb_last_error()); }
+  // Decay of the projective layer; deallocated blocks also leave the ESDF layer (mapper.h:218-233).
+  void decayTsdfAllVoxels() { decayAll(ProjectiveLayerType::kTsdf); }
+  void decayOccupancyAllVoxels() { decayAll(ProjectiveLayerType::kOccupancy); }
+  void decayTsdfExcludeLastView() { decayLastView(ProjectiveLayerType::kTsdf); }
+  void decayOccupancyExcludeLastView() { decayLastView(ProjectiveLayerType::kOccupancy); }
+  TsdfDecayIntegrator tsdf_decay_integrator() const { return TsdfDecayIntegrator(m_); }
+  OccupancyDecayIntegrator occupancy_decay_integrator() const { return OccupancyDecayIntegrator(m_); }
   float voxel_size_m() const { return nvb_mapper_voxel_size(m_); }
   TsdfLayer tsdf_layer() const { return TsdfLayer(m_, NVB_LAYER_TSDF); }
   OccupancyLayer occupancy_layer() const { return OccupancyLayer(m_, NVB_LAYER_OCCUPANCY); }
@@ -165,6 +215,19 @@ class Mapper {
   EsdfIntegrator esdf_integrator() const { return EsdfIntegrator(m_); }
   NvbMapper* c_abi() const { return m_; }
  private:
+  void requireLayer(ProjectiveLayerType t) const {
+    if (projective_layer_type_ != t) b200_detail::check(NVB_ERR_INVALID_ARGUMENT, "decay", "the mapper does not hold that projective layer");
+  }
+  void decayAll(ProjectiveLayerType t) {
+    requireLayer(t);
+    int32_t n = 0;
+    b200_detail::check(nvb_mapper_decay(m_, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, 0, &n), "decay", nvb_last_error());
+  }
+  void decayLastView(ProjectiveLayerType t) {
+    requireLayer(t);
+    int32_t n = 0;
+    b200_detail::check(nvb_mapper_decay_exclude_last_view(m_, nullptr, nullptr, 0, &n), "decay", nvb_last_error());
+  }
   NvbMapper* m_ = nullptr;
   ProjectiveLayerType projective_layer_type_;
 };

@@ -147,8 +147,12 @@ typedef struct {
   int32_t tsdf_capacity_blocks;
   int32_t esdf_capacity_blocks;
   int32_t esdf_persistent;       /* 1: whole ESDF wavefront in one cooperative launch (default);
-                                    0: one launch per ring with a host-read counter, like the reference */
+                                    0: one launch per ring with a host-read counter, like the reference;
+                                    2: gather-replay wavefront (experimental) */
   int32_t projective_layer_type; /* NvbProjectiveLayerType: TSDF (default) or occupancy */
+  int32_t keep_last_view;        /* 1: every integrated frame leaves a device copy of its depth image, pose and camera
+                                    behind for nvb_mapper_decay_exclude_last_view, like Mapper::integrateDepth does
+                                    (mapper_impl.h:70-78); 0 (default): no copy, pass the view to nvb_mapper_decay */
 } NvbMapperOptions;
 
 /* = nvblox::Mapper restricted to {TsdfLayer, EsdfLayer, ProjectiveTsdfIntegrator,
@@ -268,6 +272,11 @@ NVB_API int32_t nvb_mapper_update_esdf_async(NvbMapper* m, int32_t update_full_l
 NVB_API int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const float* depth,
                                  int32_t depth_memory, int32_t rows, int32_t cols, const float* T_L_C,
                                  const NvbCamera* cam, int32_t* removed_xyz_host, int32_t cap, int32_t* out_count);
+
+/* Mapper::decayTsdfExcludeLastView / decayOccupancyExcludeLastView (mapper.h:218-230) with the view the mapper kept
+ * (NvbMapperOptions.keep_last_view); decays every voxel if no frame was integrated yet, like the reference. */
+NVB_API int32_t nvb_mapper_decay_exclude_last_view(NvbMapper* m, const NvbDecayExclusion* exclusion,
+                                                   int32_t* removed_xyz_host, int32_t cap, int32_t* out_count);
 
 /* EsdfIntegrator::integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
  * (esdf_integrator.h:56-58, src/integrators/esdf_integrator.cu:220-266) on an

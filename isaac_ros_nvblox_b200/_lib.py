@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "nvb_default_occupancy_params", "nvb_mapper_set_occupancy_params", "nvb_mapper_get_occupancy_params",
     "nvb_default_tsdf_decay_params", "nvb_mapper_set_tsdf_decay_params", "nvb_mapper_get_tsdf_decay_params",
     "nvb_default_occupancy_decay_params", "nvb_mapper_set_occupancy_decay_params",
-    "nvb_mapper_get_occupancy_decay_params", "nvb_mapper_decay",
+    "nvb_mapper_get_occupancy_decay_params", "nvb_mapper_decay", "nvb_mapper_decay_exclude_last_view",
     "nvb_mapper_create", "nvb_mapper_destroy", "nvb_mapper_clear",
     "nvb_mapper_set_tsdf_params", "nvb_mapper_get_tsdf_params",
     "nvb_mapper_set_esdf_params", "nvb_mapper_get_esdf_params",
@@ -91,7 +91,8 @@ class NvbDecayExclusion(C.Structure):
 class NvbMapperOptions(C.Structure):
     _fields_ = [("voxel_size_m", C.c_float), ("device", C.c_int32),
                 ("tsdf_capacity_blocks", C.c_int32), ("esdf_capacity_blocks", C.c_int32),
-                ("esdf_persistent", C.c_int32), ("projective_layer_type", C.c_int32)]
+                ("esdf_persistent", C.c_int32), ("projective_layer_type", C.c_int32),
+                ("keep_last_view", C.c_int32)]
 
 
 class NvbError(RuntimeError):
@@ -134,6 +135,7 @@ def load():
     L.nvb_mapper_set_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
     L.nvb_mapper_get_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
     L.nvb_mapper_decay.argtypes = [vp, C.POINTER(NvbDecayExclusion), vp, i32, i32, i32, fp, C.POINTER(NvbCamera), ip, i32, ip]
+    L.nvb_mapper_decay_exclude_last_view.argtypes = [vp, C.POINTER(NvbDecayExclusion), ip, i32, ip]
     L.nvb_mapper_create.argtypes = [C.POINTER(NvbMapperOptions), C.POINTER(vp)]
     L.nvb_mapper_create.restype = i32
     L.nvb_mapper_destroy.argtypes = [vp]

@@ -124,6 +124,14 @@ struct NvbMapper {
   int skip_seq = 0;
   int* dead_cleared_xyz = nullptr;
   int dead_cleared_cap = 0;
+  // last integrated view (Mapper::last_posed_depth_image_, mapper.h:830-833), kept when keep_last_view is set
+  int keep_last_view = 0;
+  float* last_depth = nullptr;
+  size_t last_depth_cap = 0;
+  int last_rows = 0, last_cols = 0;
+  float last_T_L_C[16];
+  NvbCamera last_cam;
+  bool has_last_view = false;
   int* cand_a = nullptr;
   int* cand_b = nullptr;
   int ges_switch = 160;
@@ -596,6 +604,18 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
     mask_dev = mask ? m->mask_stage[stage_slot] : nullptr;
   }
   m->frame_seq++;
+  if (integrate && m->keep_last_view) {
+    const size_t pixels = (size_t)rows * cols;
+    if (m->last_depth_cap < pixels) {
+      NVB_CUDA(syncAll(m));
+      if (m->last_depth) cudaFree(m->last_depth);
+      NVB_CUDA(cudaMalloc(&m->last_depth, pixels * sizeof(float)));
+      m->last_depth_cap = pixels;
+    }
+    NVB_CUDA(cudaMemcpyAsync(m->last_depth, depth_dev, pixels * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+    m->last_rows = rows, m->last_cols = cols, m->last_cam = *cam, m->has_last_view = true;
+    memcpy(m->last_T_L_C, T_L_C_cm, sizeof(m->last_T_L_C));
+  }
 
   beginStage(m, 0);
   launchViewRaycast(depth_dev, rows, cols, T_L_C, *cam, block_size, trunc_m, max_dist, m->tp.raycast_subsampling,
@@ -785,6 +805,7 @@ void nvb_default_mapper_options(NvbMapperOptions* o) {
   o->esdf_capacity_blocks = kDefaultCapacity;
   o->esdf_persistent = 1;
   o->projective_layer_type = NVB_PROJECTIVE_TSDF;
+  o->keep_last_view = 0;
 }
 void nvb_default_tsdf_params(NvbTsdfParams* p) {
   if (!p) return;
@@ -838,6 +859,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   nvb_default_tsdf_decay_params(&m->tdp);
   nvb_default_occupancy_decay_params(&m->odp);
   m->projective_layer_type = opts->projective_layer_type;
+  m->keep_last_view = opts->keep_last_view ? 1 : 0;
   m->esdf_persistent = opts->esdf_persistent;
   // A/B switch for measurements: 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
   if (const char* e = getenv("NVB_ESDF_MODE")) m->esdf_persistent = atoi(e);
@@ -906,7 +928,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
   cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr);
   cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
-  cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz);
+  cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
@@ -940,6 +962,7 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(cudaMemsetAsync(m->nbr27, 0xFE, (size_t)m->esdf.capacity * 27 * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
   m->tracker_initialized = false;
+  m->has_last_view = false;
   m->tsdf_count_ub = 0, m->tsdf_count_confirmed = 0, m->esdf_extra_ub = 0;
   m->cells_cum = 0, m->confirmed_cum = 0;
   for (int k = 0; k < kCountRing; k++) m->count_pending[k] = false;
@@ -1172,6 +1195,16 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
   NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
   NVB_CUDA(syncAll(m));
   return checkDeviceError(m);
+}
+
+int32_t nvb_mapper_decay_exclude_last_view(NvbMapper* m, const NvbDecayExclusion* exclusion, int32_t* removed_xyz_host,
+                                           int32_t cap, int32_t* out_count) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (!m->keep_last_view) return fail(NVB_ERR_INVALID_ARGUMENT, "the mapper was created without keep_last_view");
+  if (!m->has_last_view)  // "Last view not set for sensor type. Decaying all voxels" (mapper_impl.h:200-203)
+    return nvb_mapper_decay(m, exclusion, nullptr, 0, 0, 0, nullptr, nullptr, removed_xyz_host, cap, out_count);
+  return nvb_mapper_decay(m, exclusion, m->last_depth, NVB_MEM_DEVICE, m->last_rows, m->last_cols, m->last_T_L_C,
+                          &m->last_cam, removed_xyz_host, cap, out_count);
 }
 
 float nvb_mapper_voxel_size(const NvbMapper* m) { return m ? m->voxel_size : 0.0f; }

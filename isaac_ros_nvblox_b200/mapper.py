@@ -298,7 +298,7 @@ class Mapper:
         return {"barrier_wait_ns_cta0": out[0], "axis_ns_cta0": out[1], "slowest_cta_work_ns": out[2], "barriers": out[3]}
 
     def __init__(self, voxel_size_m, device=0, tsdf_capacity_blocks=0, esdf_capacity_blocks=0,
-                 esdf_persistent=True, projective_layer_type=ProjectiveLayerType.kTsdf):
+                 esdf_persistent=True, projective_layer_type=ProjectiveLayerType.kTsdf, keep_last_view=False):
         self._L = _lib.load()
         o = NvbMapperOptions()
         self._L.nvb_default_mapper_options(C.byref(o))
@@ -310,6 +310,7 @@ class Mapper:
             o.esdf_capacity_blocks = int(esdf_capacity_blocks)
         o.esdf_persistent = int(esdf_persistent)  # 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
         o.projective_layer_type = int(projective_layer_type)
+        o.keep_last_view = 1 if keep_last_view else 0
         self._projective_layer_type = int(projective_layer_type)
         h = C.c_void_p(0)
         check(self._L.nvb_mapper_create(C.byref(o), C.byref(h)))
@@ -389,6 +390,15 @@ class Mapper:
                                            depth.shape[1], _fp(T), C.byref(camera.c), _ip(out), cap, C.byref(n)))
         else:
             check(self._L.nvb_mapper_decay(self._h, C.byref(x), None, 0, 0, 0, None, None, _ip(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def decay_exclude_last_view(self):
+        """Mapper::decayTsdfExcludeLastView / decayOccupancyExcludeLastView with the view kept by the mapper
+        (Mapper(..., keep_last_view=True))."""
+        n = C.c_int32(0)
+        cap = max(self._tsdf.num_blocks() if self._projective_layer_type == 0 else self._occupancy.num_blocks(), 1)
+        out = np.zeros((cap, 3), dtype=np.int32)
+        check(self._L.nvb_mapper_decay_exclude_last_view(self._h, None, _ip(out), cap, C.byref(n)))
         return out[:n.value].copy()
 
     def decay_tsdf(self, **kw):

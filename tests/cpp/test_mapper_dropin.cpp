@@ -56,6 +56,15 @@ int main() {
     }
   }
   EXPECT(sites > 1000);
+  // decay (test_tsdf_decay.cpp): the last view is spared, everything decays away without it
+  const int blocks_before = tsdf.numBlocks();
+  mapper.tsdf_decay_integrator().decay_factor(0.1f);
+  EXPECT(std::fabs(mapper.tsdf_decay_integrator().decay_factor() - 0.1f) < 1e-7f);
+  for (int i = 0; i < 6; i++) mapper.decayTsdfExcludeLastView();
+  EXPECT(tsdf.numBlocks() > 0 && tsdf.numBlocks() <= blocks_before);
+  for (int i = 0; i < 6 && tsdf.numBlocks() > 0; i++) mapper.decayTsdfAllVoxels();
+  EXPECT(tsdf.numBlocks() == 0);
+  EXPECT(esdf.numBlocks() == 0);
   std::printf("drop-in C++ API ok: %zu blocks, %ld observed voxels, %ld sites\n", updated.size(), observed, sites);
   return 0;
 }

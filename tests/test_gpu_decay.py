@@ -200,3 +200,25 @@ def test_persistent_cleared_list_survives_deallocation_and_reallocation(gpu):
         assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
     assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
     m.close()
+
+
+def test_keep_last_view_equals_explicit_view(gpu):
+    nvb = _nvb()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:3])
+    a, b = nvb.Mapper(0.05, keep_last_view=True), nvb.Mapper(0.05)
+    with pytest.raises(Exception):
+        b.decay_exclude_last_view()  # created without keep_last_view
+    assert len(a.decay_exclude_last_view()) == 0  # nothing integrated yet: decays all (of nothing)
+    for d, T in frames:
+        a.integrate_depth(d, T, cam)
+        b.integrate_depth(d, T, cam)
+    for m in (a, b):
+        m.tsdf_decay_integrator().params(decay_factor=0.4)
+    d, T = frames[-1]
+    for _ in range(6):
+        ra = a.decay_exclude_last_view()
+        rb = b.decay(depth=d, T_L_C=T, camera=cam)
+        assert _as_set(ra) == _as_set(rb)
+    assert_tsdf_equal(a.tsdf_layer().as_dict(), b.tsdf_layer().as_dict())
+    a.close(), b.close()
