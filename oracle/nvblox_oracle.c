@@ -475,7 +475,8 @@ static void list_sort_unique(List* l) {
 
 struct OrMap {
   float voxel_size, block_size;
-  Layer tsdf, esdf, occ;
+  Layer tsdf, esdf, occ, freespace;
+  int64_t freespace_last_update_time_ms; /* FreespaceIntegrator::last_update_time_ms_ (freespace_integrator.h:171) */
   /* EsdfIntegrator::cleared_block_indices_device_ (integrators/esdf_integrator.h:389)
    * is a member that is only overwritten when a call has blocks to clear
    * (esdf_integrator.cu:242-257), so its content carries over between calls. */
@@ -516,16 +517,17 @@ OrMap* or_map_create(float voxel_size_m) {
   layer_init(&m->tsdf, sizeof(OrTsdfVoxel) * VPB);
   layer_init(&m->esdf, sizeof(OrEsdfVoxel) * VPB);
   layer_init(&m->occ, sizeof(float) * VPB); /* OccupancyVoxel{float log_odds} (map/voxels.h:92-97) */
+  layer_init(&m->freespace, sizeof(OrFreespaceVoxel) * VPB);
   return m;
 }
 void or_map_destroy(OrMap* m) {
   if (!m) return;
-  layer_free(&m->tsdf), layer_free(&m->esdf), layer_free(&m->occ);
+  layer_free(&m->tsdf), layer_free(&m->esdf), layer_free(&m->occ), layer_free(&m->freespace);
   list_free(&m->esdf_cleared_persistent);
   free(m);
 }
 void or_map_clear(OrMap* m) {
-  layer_clear(&m->tsdf), layer_clear(&m->esdf), layer_clear(&m->occ);
+  layer_clear(&m->tsdf), layer_clear(&m->esdf), layer_clear(&m->occ), layer_clear(&m->freespace);
   m->esdf_cleared_persistent.n = 0;
 }
 
@@ -867,12 +869,12 @@ static void esdf_clear_voxel(OrEsdfVoxel* v, float max_sq) { /* :152-157 */
 static void esdf_apply_observation(int is_observed, int is_inside, int near_surface, float max_sq,
                                    OrEsdfVoxel* e, int* cleared, int* updated);
 
-static void esdf_update_voxel_to_changes(const OrTsdfVoxel* t, float min_weight,
+static void esdf_update_voxel_to_changes(const OrTsdfVoxel* t, int is_freespace, float min_weight,
                                          float max_site_distance_m, float max_sq,
                                          OrEsdfVoxel* e, int* cleared, int* updated) {
-  /* TsdfSiteFunctor (:113-138) */
-  esdf_apply_observation(t->weight >= min_weight, t->distance <= 0.0f, fabsf(t->distance) <= max_site_distance_m,
-                         max_sq, e, cleared, updated);
+  /* TsdfSiteFunctor (:113-138); "voxels being freespace can not be inside an object" (:413-415) */
+  esdf_apply_observation(t->weight >= min_weight, (t->distance <= 0.0f) & !is_freespace,
+                         fabsf(t->distance) <= max_site_distance_m, max_sq, e, cleared, updated);
 }
 
 /* OccupancySiteFunctor (:140-170): observed <=> |log_odds - 0| > 1e-4; inside <=> log_odds > threshold;
@@ -1171,16 +1173,20 @@ static void esdf_clear_all_invalid(OrMap* map, const List* to_clear, float max_e
 
 /* EsdfIntegrator::integrateBlocksTemplate<TsdfLayer> (:220-260) with
  * markAllSites (:678-747) / markAllSitesKernel (:467-540). */
-static void esdf_integrate_from(OrMap* map, int from_occupancy, const int32_t* blocks_xyz, int32_t num_blocks,
-                                const OrEsdfParams* P);
+static void esdf_integrate_from(OrMap* map, int from_occupancy, int use_freespace, const int32_t* blocks_xyz,
+                                int32_t num_blocks, const OrEsdfParams* P);
 void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, const OrEsdfParams* P) {
-  esdf_integrate_from(map, 0, blocks_xyz, num_blocks, P);
+  esdf_integrate_from(map, 0, 0, blocks_xyz, num_blocks, P);
 }
 void or_esdf_integrate_occupancy(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, const OrEsdfParams* P) {
-  esdf_integrate_from(map, 1, blocks_xyz, num_blocks, P);
+  esdf_integrate_from(map, 1, 0, blocks_xyz, num_blocks, P);
 }
-static void esdf_integrate_from(OrMap* map, int from_occupancy, const int32_t* blocks_xyz, int32_t num_blocks,
-                                const OrEsdfParams* P) {
+/* EsdfIntegrator::integrateBlocks(tsdf_layer, freespace_layer, blocks, esdf_layer) (esdf_integrator.h:64-70, .cu:266-275). */
+void or_esdf_integrate_with_freespace(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, const OrEsdfParams* P) {
+  esdf_integrate_from(map, 0, 1, blocks_xyz, num_blocks, P);
+}
+static void esdf_integrate_from(OrMap* map, int from_occupancy, int use_freespace, const int32_t* blocks_xyz,
+                                int32_t num_blocks, const OrEsdfParams* P) {
   memset(map->stats, 0, sizeof(map->stats));
   if (num_blocks == 0) return;
   /* allocateBlocksOnCPU (:391-397) */
@@ -1216,9 +1222,12 @@ static void esdf_integrate_from(OrMap* map, int from_occupancy, const int32_t* b
         esdf_update_voxel_to_changes_occ(lo[v], occupied_threshold_log_odds, max_sq, &e[v], &cleared, &updated);
     } else {
       const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(src, ts);
+      /* isVoxelFreespace (:101-111): no freespace block -> not freespace */
+      const int32_t fs = use_freespace ? hash_find(&map->freespace.hash, blocks.v[i]) : -1;
+      const OrFreespaceVoxel* f = fs >= 0 ? (const OrFreespaceVoxel*)layer_block(&map->freespace, fs) : NULL;
       for (int v = 0; v < VPB; v++)
-        esdf_update_voxel_to_changes(&t[v], P->min_weight, max_site_distance_m, max_sq, &e[v],
-                                     &cleared, &updated);
+        esdf_update_voxel_to_changes(&t[v], f ? f[v].is_high_confidence_freespace != 0 : 0, P->min_weight,
+                                     max_site_distance_m, max_sq, &e[v], &cleared, &updated);
     }
     upd[i] = (uint8_t)updated, clr[i] = (uint8_t)cleared;
   }
@@ -1257,6 +1266,7 @@ int32_t or_tsdf_block_indices(const OrMap* m, int32_t* out, int32_t cap) { retur
 int32_t or_esdf_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->esdf, out, cap); }
 int32_t or_occupancy_num_blocks(const OrMap* m) { return m->occ.n; }
 int32_t or_occupancy_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->occ, out, cap); }
+int32_t or_freespace_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->freespace, out, cap); }
 int32_t or_occupancy_get_block(const OrMap* m, const int32_t xyz[3], float* out) {
   i3 k = {xyz[0], xyz[1], xyz[2]};
   int32_t s = hash_find(&m->occ.hash, k);
@@ -1414,12 +1424,113 @@ static int32_t decay_layer(OrMap* map, int occupancy, const void* params, const 
       if (selected[s] && fully[s]) list_push(&rm, L->index[s]);
     n_removed = copy_out(&rm, out_xyz, cap);
     layer_remove_blocks(L, rm.v, rm.n);
-    if (clear_esdf) layer_remove_blocks(&map->esdf, rm.v, rm.n);
+    if (clear_esdf) layer_remove_blocks(&map->esdf, rm.v, rm.n), layer_remove_blocks(&map->freespace, rm.v, rm.n);
     list_free(&rm);
   }
   free(fully), free(selected);
   if (exclp) hash_free(exclp);
   return n_removed;
+}
+
+
+/* ------------------------------------------------------------------------- */
+/* Freespace (integrators/internal/cuda/impl/freespace_integrator_impl.cuh)  */
+/* ------------------------------------------------------------------------- */
+void or_default_freespace_params(OrFreespaceParams* p) {
+  /* integrators/freespace_integrator_params.h:22-58 */
+  p->max_tsdf_distance_for_occupancy_m = 0.15f;
+  p->max_unobserved_to_keep_consecutive_occupancy_ms = 200;
+  p->min_duration_since_occupied_for_freespace_ms = 1000;
+  p->min_consecutive_occupancy_duration_for_reset_ms = 2000;
+  p->check_neighborhood = 1;
+  p->initialize_to_high_confidence_freespace = 0;
+}
+
+/* FreespaceIntegrator::updateFreespaceLayer (:324-383) + updateFreespaceLayerKernel (:99-246). */
+void or_freespace_update(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, int64_t update_time_ms,
+                         const OrFreespaceParams* P, const float* depth, int32_t rows, int32_t cols, const float* T_L_C,
+                         const OrCamera* cam, float max_view_distance_m, float truncation_distance_m) {
+  if (num_blocks == 0) return;
+  float T_C_L[16];
+  if (depth) invert_isometry(T_L_C, T_C_L);
+  const int64_t last_update = map->freespace_last_update_time_ms;
+  for (int32_t i = 0; i < num_blocks; i++) { /* allocateBlocksAtIndices */
+    i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], blocks_xyz[3 * i + 2]};
+    layer_allocate(&map->freespace, k);
+  }
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < num_blocks; i++) {
+    const i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], blocks_xyz[3 * i + 2]};
+    const int32_t fsl = hash_find(&map->freespace.hash, k);
+    const int32_t ts = hash_find(&map->tsdf.hash, k);
+    if (fsl < 0 || ts < 0) continue; /* the reference hands the kernel a TSDF pointer for every block to update */
+    OrFreespaceVoxel* fv = (OrFreespaceVoxel*)layer_block(&map->freespace, fsl);
+    const OrTsdfVoxel* tv = (const OrTsdfVoxel*)layer_block(&map->tsdf, ts);
+    uint8_t is_free_blk[VPB];
+    uint8_t update_voxel[VPB], init_voxel[VPB];
+    memset(is_free_blk, 0, sizeof(is_free_blk));
+    for (int vx = 0; vx < VPS; vx++)
+      for (int vy = 0; vy < VPS; vy++)
+        for (int vz = 0; vz < VPS; vz++) {
+          const int v = (vx * VPS + vy) * VPS + vz;
+          OrFreespaceVoxel f = fv[v];
+          int upd = 1;
+          if (depth && !voxel_has_depth_measurement(k, vx, vy, vz, depth, rows, cols, T_C_L, cam, map->block_size,
+                                                    max_view_distance_m, truncation_distance_m))
+            upd = 0;
+          const int init = f.last_occupied_timestamp_ms == 0;
+          if (init) {
+            f.last_occupied_timestamp_ms = update_time_ms;
+            f.consecutive_occupancy_duration_ms = 0;
+            f.is_high_confidence_freespace = (uint8_t)(P->initialize_to_high_confidence_freespace != 0);
+          }
+          if (upd && !init) {
+            if (update_time_ms - f.last_occupied_timestamp_ms <= P->max_unobserved_to_keep_consecutive_occupancy_ms)
+              f.consecutive_occupancy_duration_ms += update_time_ms - last_update;
+            else
+              f.consecutive_occupancy_duration_ms = 0;
+            if (tv[v].distance <= P->max_tsdf_distance_for_occupancy_m) f.last_occupied_timestamp_ms = update_time_ms;
+            /* isVoxelFree (:36-44): `weight > 1e-6` compares the float with a double literal */
+            is_free_blk[v] = (uint8_t)((double)tv[v].weight > 1e-6 && f.last_occupied_timestamp_ms != 0 &&
+                                       f.last_occupied_timestamp_ms <= update_time_ms - P->min_duration_since_occupied_for_freespace_ms);
+          }
+          update_voxel[v] = (uint8_t)upd, init_voxel[v] = (uint8_t)init;
+          if (upd || init) fv[v] = f; /* written back below as well; intermediate state is per voxel */
+        }
+    for (int vx = 0; vx < VPS; vx++)
+      for (int vy = 0; vy < VPS; vy++)
+        for (int vz = 0; vz < VPS; vz++) {
+          const int v = (vx * VPS + vy) * VPS + vz;
+          if (!(update_voxel[v] && !init_voxel[v])) continue;
+          OrFreespaceVoxel f = fv[v];
+          int is_free = is_free_blk[v];
+          if (P->check_neighborhood && is_free) { /* isVoxelNeighborhoodFree (:46-83), inside the block only */
+            for (int u = -1; u <= 1; u++)
+              for (int w = -1; w <= 1; w++)
+                for (int q = -1; q <= 1; q++) {
+                  const int x = vx + u, y = vy + w, z = vz + q;
+                  if (u == 0 && w == 0 && q == 0) continue;
+                  if (x < 0 || x >= VPS || y < 0 || y >= VPS || z < 0 || z >= VPS) continue;
+                  is_free &= is_free_blk[(x * VPS + y) * VPS + z];
+                }
+          }
+          if (f.consecutive_occupancy_duration_ms >= P->min_consecutive_occupancy_duration_for_reset_ms)
+            f.is_high_confidence_freespace = 0;
+          else
+            f.is_high_confidence_freespace = (uint8_t)(f.is_high_confidence_freespace || is_free);
+          fv[v] = f;
+        }
+  }
+  map->freespace_last_update_time_ms = update_time_ms;
+}
+int32_t or_freespace_num_blocks(const OrMap* m) { return m->freespace.n; }
+int32_t or_freespace_block_indices(const OrMap* m, int32_t* out, int32_t cap);
+int32_t or_freespace_get_block(const OrMap* m, const int32_t xyz[3], OrFreespaceVoxel* out) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = hash_find(&m->freespace.hash, k);
+  if (s < 0) return 0;
+  memcpy(out, layer_block(&m->freespace, s), m->freespace.block_bytes);
+  return 1;
 }
 
 void or_default_tsdf_decay_params(OrTsdfDecayParams* p) {

@@ -96,6 +96,23 @@ typedef struct {
   uint8_t is_inside, observed, is_site, pad_;
 } OrEsdfVoxel; /* 20 B */
 
+/* FreespaceVoxel (map/voxels.h:38-52): two Time (int64 ms) fields and a bool. */
+typedef struct {
+  int64_t last_occupied_timestamp_ms;
+  int64_t consecutive_occupancy_duration_ms;
+  uint8_t is_high_confidence_freespace, pad_[7];
+} OrFreespaceVoxel; /* 24 B */
+
+/* FreespaceIntegrator parameters (integrators/freespace_integrator_params.h:22-58). */
+typedef struct {
+  float max_tsdf_distance_for_occupancy_m;                   /* 0.15 */
+  int64_t max_unobserved_to_keep_consecutive_occupancy_ms;   /* 200  */
+  int64_t min_duration_since_occupied_for_freespace_ms;      /* 1000 */
+  int64_t min_consecutive_occupancy_duration_for_reset_ms;   /* 2000 */
+  int32_t check_neighborhood;                                /* 1    */
+  int32_t initialize_to_high_confidence_freespace;           /* 0    */
+} OrFreespaceParams;
+
 typedef struct OrMap OrMap;
 
 void or_default_tsdf_params(OrTsdfParams* p);
@@ -187,6 +204,20 @@ int32_t or_occupancy_decay(OrMap* map, const OrOccupancyDecayParams* params, con
                            const float* depth, int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam,
                            float max_view_distance_m, float truncation_distance_m, int32_t clear_esdf, int32_t* out_xyz,
                            int32_t cap);
+
+/* FreespaceIntegrator::updateFreespaceLayer (integrators/freespace_integrator.h:60-66): dynablox freespace update of
+ * the listed blocks at `update_time_ms`. depth == NULL: no viewpoint exclusion; otherwise only voxels with a depth
+ * measurement in that view are updated. The time of the last call is kept in the map. */
+void or_default_freespace_params(OrFreespaceParams* p);
+void or_freespace_update(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, int64_t update_time_ms,
+                         const OrFreespaceParams* params, const float* depth, int32_t rows, int32_t cols,
+                         const float* T_L_C, const OrCamera* cam, float max_view_distance_m, float truncation_distance_m);
+int32_t or_freespace_num_blocks(const OrMap* map);
+int32_t or_freespace_block_indices(const OrMap* map, int32_t* out_xyz, int32_t cap);
+int32_t or_freespace_get_block(const OrMap* map, const int32_t xyz[3], OrFreespaceVoxel* out);
+/* EsdfIntegrator::integrateBlocks(TsdfLayer, FreespaceLayer, blocks, EsdfLayer*) (esdf_integrator.h:64-70). */
+void or_esdf_integrate_with_freespace(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,
+                                      const OrEsdfParams* params);
 
 /* EsdfIntegrator::integrateBlocks(TsdfLayer, blocks, EsdfLayer*). */
 void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,

@@ -72,6 +72,19 @@ class OccupancyParams(C.Structure):
                 ("occupied_region_half_width_m", C.c_float)]
 
 
+FREESPACE_VOXEL_DTYPE = np.dtype([("last_occupied_timestamp_ms", "<i8"), ("consecutive_occupancy_duration_ms", "<i8"),
+                                  ("is_high_confidence_freespace", "u1"), ("pad", "u1", (7,))])
+assert FREESPACE_VOXEL_DTYPE.itemsize == 24
+
+
+class FreespaceParams(C.Structure):
+    _fields_ = [("max_tsdf_distance_for_occupancy_m", C.c_float),
+                ("max_unobserved_to_keep_consecutive_occupancy_ms", C.c_int64),
+                ("min_duration_since_occupied_for_freespace_ms", C.c_int64),
+                ("min_consecutive_occupancy_duration_for_reset_ms", C.c_int64),
+                ("check_neighborhood", C.c_int32), ("initialize_to_high_confidence_freespace", C.c_int32)]
+
+
 class TsdfDecayParams(C.Structure):
     _fields_ = [("decay_factor", C.c_float), ("decayed_weight_threshold", C.c_float),
                 ("set_free_distance_on_decayed", C.c_int32), ("free_distance_vox", C.c_float),
@@ -152,6 +165,19 @@ def lib():
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.restype = None
+    L.or_default_freespace_params.argtypes = [C.POINTER(FreespaceParams)]
+    L.or_default_freespace_params.restype = None
+    L.or_freespace_update.argtypes = [vp, ip, C.c_int32, C.c_int64, C.POINTER(FreespaceParams), fp, C.c_int32, C.c_int32, fp,
+                                      C.POINTER(Camera), C.c_float, C.c_float]
+    L.or_freespace_update.restype = None
+    L.or_freespace_num_blocks.argtypes = [vp]
+    L.or_freespace_num_blocks.restype = C.c_int32
+    L.or_freespace_block_indices.argtypes = [vp, ip, C.c_int32]
+    L.or_freespace_block_indices.restype = C.c_int32
+    L.or_freespace_get_block.argtypes = [vp, ip, vp]
+    L.or_freespace_get_block.restype = C.c_int32
+    L.or_esdf_integrate_with_freespace.argtypes = [vp, ip, C.c_int32, C.POINTER(EsdfParams)]
+    L.or_esdf_integrate_with_freespace.restype = None
     L.or_default_tsdf_decay_params.argtypes = [C.POINTER(TsdfDecayParams)]
     L.or_default_tsdf_decay_params.restype = None
     L.or_default_occupancy_decay_params.argtypes = [C.POINTER(OccupancyDecayParams)]
@@ -197,6 +223,14 @@ def default_tsdf_params(**kw):
 def default_esdf_params(**kw):
     p = EsdfParams()
     lib().or_default_esdf_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_freespace_params(**kw):
+    p = FreespaceParams()
+    lib().or_default_freespace_params(C.byref(p))
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -367,6 +401,40 @@ class OracleMap:
         return self._decay(lib().or_occupancy_decay, params or default_occupancy_decay_params(), depth, T_L_C, cam,
                            max_view_distance_m, truncation_distance_m, excluded_blocks, exclusion_center,
                            exclusion_radius_m, clear_esdf, cap)
+
+    def update_freespace(self, blocks, update_time_ms, params=None, depth=None, T_L_C=None, cam=None,
+                         max_view_distance_m=3.4028234663852886e38, truncation_distance_m=3.4028234663852886e38):
+        """FreespaceIntegrator::updateFreespaceLayer; with a view only voxels that have a depth measurement are updated."""
+        params = params or default_freespace_params()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, dtype=np.float32)
+            T = colmajor(T_L_C)
+            lib().or_freespace_update(self._h, _ip(blocks), blocks.shape[0], int(update_time_ms), C.byref(params), _fp(depth),
+                                      depth.shape[0], depth.shape[1], _fp(T), C.byref(cam), float(max_view_distance_m),
+                                      float(truncation_distance_m))
+        else:
+            lib().or_freespace_update(self._h, _ip(blocks), blocks.shape[0], int(update_time_ms), C.byref(params), None, 0, 0,
+                                      None, None, 0.0, 0.0)
+
+    def freespace_block_indices(self):
+        n = lib().or_freespace_num_blocks(self._h)
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        lib().or_freespace_block_indices(self._h, _ip(out), n)
+        return out[:n].copy()
+
+    def freespace_layer(self):
+        out = {}
+        for k in self.freespace_block_indices():
+            blk = np.zeros((8, 8, 8), dtype=FREESPACE_VOXEL_DTYPE)
+            lib().or_freespace_get_block(self._h, _ip(np.ascontiguousarray(k, dtype=np.int32)), blk.ctypes.data)
+            out[tuple(int(c) for c in k)] = blk
+        return out
+
+    def integrate_esdf_with_freespace(self, blocks, params=None):
+        params = params or default_esdf_params()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        lib().or_esdf_integrate_with_freespace(self._h, _ip(blocks), blocks.shape[0], C.byref(params))
 
     def set_occupancy_block(self, idx, log_odds):
         k = np.asarray(idx, dtype=np.int32)

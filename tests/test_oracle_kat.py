@@ -776,3 +776,148 @@ def test_occupancy_decay_all(to_p):
     p.deallocate_decayed_blocks = 1
     removed = m.decay_occupancy(p)
     assert len(removed) == len(init) and len(m.occupancy_block_indices()) == 0
+
+
+# --- freespace: test_freespace_integrator.cpp -----------------------------------------------
+def _check_fs(m, expect, max_tsdf_distance=np.inf):
+    """checkVoxels (test_freespace_integrator.cpp:41-103): every freespace voxel whose TSDF voxel is observed (and closer
+    than max_tsdf_distance) equals `expect` = (last_occupied, consecutive_duration, high_confidence)."""
+    fs, ts = m.freespace_layer(), m.tsdf_layer()
+    n = 0
+    for k, t in ts.items():
+        assert k in fs
+        sel = (t["weight"] > 1e-4) & (t["distance"] < max_tsdf_distance)
+        f = fs[k]
+        assert np.all(f["last_occupied_timestamp_ms"][sel] == expect[0])
+        assert np.all(f["consecutive_occupancy_duration_ms"][sel] == expect[1])
+        assert np.all(f["is_high_confidence_freespace"][sel] == (1 if expect[2] else 0))
+        n += int(sel.sum())
+    assert n > 0
+
+
+def test_freespace_plane_state_machine():
+    """FreespacePlane (test_freespace_integrator.cpp:107-290), camera looking along +z instead of +x."""
+    voxel, step = 0.1, 100
+    cs = syn.PinholeCamera()
+    cam = _cam()
+    T = np.eye(4, dtype=np.float32)
+    trunc = 4 * voxel
+    max_int = 4.0 - 2 * trunc
+    depth = syn.render_depth(syn.plane_scene(4.0), cs, np.eye(4), max_dist=8.0)
+    m = orc.OracleMap(voxel)
+    tp = orc.default_tsdf_params(truncation_distance_vox=4.0, max_integration_distance_m=max_int)
+    fp_ = orc.default_freespace_params(max_tsdf_distance_for_occupancy_m=0.75 * trunc,
+                                       max_unobserved_to_keep_consecutive_occupancy_ms=2 * step,
+                                       min_duration_since_occupied_for_freespace_ms=5 * step,
+                                       min_consecutive_occupancy_duration_for_reset_ms=10 * step, check_neighborhood=0)
+    t0 = 42
+    blocks = m.integrate_depth(depth, T, cam, tp)
+    m.update_freespace(blocks, t0, fp_)
+    _check_fs(m, (t0, 0, False))
+    m.update_freespace(blocks, t0 + step, fp_)
+    _check_fs(m, (t0, step, False))
+    m.update_freespace(blocks, t0 + 3 * step, fp_)
+    _check_fs(m, (t0, 0, False))
+    m.update_freespace(blocks, t0 + 5 * step, fp_)
+    _check_fs(m, (t0, 0, True))
+    # a plane appears at the maximum integration distance
+    depth2 = syn.render_depth(syn.plane_scene(max_int), cs, np.eye(4), max_dist=8.0)
+    t1 = t0 + 10 * step
+    blocks = m.integrate_depth(depth2, T, cam, tp)
+    m.update_freespace(blocks, t1, fp_)
+    dmax = fp_.max_tsdf_distance_for_occupancy_m
+    _check_fs(m, (t1, 0, True), dmax)
+    for j in (2, 4, 6, 8):
+        m.update_freespace(blocks, t1 + j * step, fp_)
+    _check_fs(m, (t1 + 8 * step, 8 * step, True), dmax)
+    m.update_freespace(blocks, t1 + 10 * step, fp_)
+    _check_fs(m, (t1 + 10 * step, 10 * step, False), dmax)
+
+
+def _tsdf_cube(m, n, distance, weight):
+    for x in range(n):
+        for y in range(n):
+            for z in range(n):
+                blk = np.zeros((8, 8, 8), dtype=orc.TSDF_VOXEL_DTYPE)
+                blk["distance"], blk["weight"] = distance, weight
+                m.set_tsdf_block((x, y, z), blk)
+
+
+def test_freespace_view_exclusion():
+    """ViewExclusion (test_freespace_integrator.cpp:312-385)."""
+    voxel = 0.1
+    m = orc.OracleMap(voxel)
+    _tsdf_cube(m, 2, 10.0 * voxel, 1.0)
+    cam = _cam()
+    depth = np.full((480, 640), 5.0, np.float32)
+    T = np.eye(4, dtype=np.float32)
+    blocks = m.tsdf_block_indices()
+    fp_ = orc.default_freespace_params()
+    m.update_freespace(blocks, 0, fp_)
+    tmin = fp_.min_duration_since_occupied_for_freespace_ms
+    m.update_freespace(blocks, tmin, fp_, depth=depth, T_L_C=T, cam=cam)
+    m.update_freespace(blocks, 2 * tmin, fp_, depth=depth, T_L_C=T, cam=cam)
+    n_free = n_not = 0
+    ii = (np.indices((8, 8, 8)).reshape(3, -1).T + 0.5)
+    for k, f in m.freespace_layer().items():
+        pos = ((np.asarray(k) * 8 + ii) * voxel).astype(np.float32)
+        hc = f["is_high_confidence_freespace"].reshape(-1) != 0
+        z = pos[:, 2]
+        u = pos[:, 0] / z * 300.0 + 320.0
+        v = pos[:, 1] / z * 300.0 + 240.0
+        in_view = (z >= 1e-6) & (u >= 0) & (v >= 0) & (u <= 640) & (v <= 480)
+        assert np.all(in_view[hc])
+        n_free += int(hc.sum())
+        n_not += int((~hc).sum())
+    assert n_free > 0 and n_not > 0
+
+
+def test_freespace_check_neighborhood():
+    """CheckNeighbohood (test_freespace_integrator.cpp:387-441)."""
+    fp_ = orc.default_freespace_params(check_neighborhood=1)
+    for occupied_neighbor in (False, True):
+        m = orc.OracleMap(0.1)
+        blk = np.zeros((8, 8, 8), dtype=orc.TSDF_VOXEL_DTYPE)
+        blk["distance"], blk["weight"] = fp_.max_tsdf_distance_for_occupancy_m + 1e-3, 1e6
+        if occupied_neighbor:
+            blk["distance"][2, 2, 2] = 0.0
+        m.set_tsdf_block((0, 0, 0), blk)
+        blocks = m.tsdf_block_indices()
+        m.update_freespace(blocks, 1, fp_)
+        m.update_freespace(blocks, 1000000, fp_)
+        hc = m.freespace_layer()[(0, 0, 0)]["is_high_confidence_freespace"]
+        assert bool(hc[3, 3, 3]) == (not occupied_neighbor)
+        if occupied_neighbor:
+            assert not hc[2, 2, 2] and hc[5, 5, 5]
+
+
+def test_freespace_initialize_to_high_confidence():
+    """InitializeToHighConfidenceFreespace (test_freespace_integrator.cpp:443-495)."""
+    voxel = 0.1
+    cs = syn.PinholeCamera()
+    depth = syn.render_depth(syn.plane_scene(4.0), cs, np.eye(4), max_dist=8.0)
+    m = orc.OracleMap(voxel)
+    tp = orc.default_tsdf_params(truncation_distance_vox=4.0, max_integration_distance_m=4.0 - 8 * voxel)
+    blocks = m.integrate_depth(depth, np.eye(4, dtype=np.float32), _cam(), tp)
+    m.update_freespace(blocks, 100, orc.default_freespace_params(initialize_to_high_confidence_freespace=1))
+    _check_fs(m, (100, 0, True))
+
+
+def test_esdf_with_freespace_removes_sites():
+    """EsdfIntegrator with a freespace layer (esdf_integrator.cu:401-415): a high-confidence-free voxel is never inside an
+    object, hence never a site."""
+    voxel = 0.1
+    cs = syn.PinholeCamera(75.0, 75.0, 80.0, 60.0, 160, 120)
+    cam = orc.Camera(75.0, 75.0, 80.0, 60.0, 160, 120)
+    depth, T = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(8)[:1])[0]
+    a, b = orc.OracleMap(voxel), orc.OracleMap(voxel)
+    for m in (a, b):
+        blocks = m.integrate_depth(depth, T, cam)
+    a.integrate_esdf(blocks)
+    # everything high-confidence free in b
+    b.update_freespace(blocks, 100, orc.default_freespace_params(initialize_to_high_confidence_freespace=1))
+    b.integrate_esdf_with_freespace(blocks)
+    sa = sum(int(v["is_site"].sum()) for v in a.esdf_layer().values())
+    sb = sum(int(v["is_site"].sum()) for v in b.esdf_layer().values())
+    ib = sum(int(v["is_inside"].sum()) for v in b.esdf_layer().values())
+    assert sa > 100 and sb == 0 and ib == 0
