@@ -60,10 +60,14 @@ typedef enum {
 typedef enum { NVB_MEM_HOST = 0, NVB_MEM_DEVICE = 1 } NvbMemory;
 
 /* Layers of the map (C/include/nvblox/map/common_names.h TsdfLayer / EsdfLayer). */
-typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1, NVB_LAYER_OCCUPANCY = 2 } NvbLayer;
+typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1, NVB_LAYER_OCCUPANCY = 2, NVB_LAYER_FREESPACE = 3 } NvbLayer;
 
 /* ProjectiveLayerType of a Mapper (C/include/nvblox/mapper/mapper.h:40-48): which layer integrateDepth feeds. */
-typedef enum { NVB_PROJECTIVE_TSDF = 0, NVB_PROJECTIVE_OCCUPANCY = 1 } NvbProjectiveLayerType;
+typedef enum {
+  NVB_PROJECTIVE_TSDF = 0,
+  NVB_PROJECTIVE_OCCUPANCY = 1,
+  NVB_PROJECTIVE_TSDF_WITH_FREESPACE = 2 /* TSDF + FreespaceLayer (dynablox), used by the ESDF to ignore free voxels */
+} NvbProjectiveLayerType;
 
 /* nvblox::Camera (C/include/nvblox/sensors/camera.h:193-203) with its
  * std::optional<RadialTangentialDistortionParams> (C/include/nvblox/sensors/distortion.h:24-62):
@@ -136,6 +140,13 @@ typedef struct {
   int32_t parent_direction[3];
   uint8_t is_inside, observed, is_site, pad_;
 } NvbEsdfVoxel;
+
+/* FreespaceVoxel (C/include/nvblox/map/voxels.h:38-52): two nvblox::Time (int64 milliseconds) and a bool. */
+typedef struct {
+  int64_t last_occupied_timestamp_ms;
+  int64_t consecutive_occupancy_duration_ms;
+  uint8_t is_high_confidence_freespace, pad_[7];
+} NvbFreespaceVoxel;
 
 /* Construction options. capacity = number of 8x8x8 blocks each layer's slab is
  * sized for up front (it grows by doubling, which is a synchronising event;
@@ -218,6 +229,19 @@ NVB_API int32_t nvb_mapper_get_tsdf_decay_params(const NvbMapper* m, NvbTsdfDeca
 NVB_API void nvb_default_occupancy_decay_params(NvbOccupancyDecayParams* p);
 NVB_API int32_t nvb_mapper_set_occupancy_decay_params(NvbMapper* m, const NvbOccupancyDecayParams* p);
 NVB_API int32_t nvb_mapper_get_occupancy_decay_params(const NvbMapper* m, NvbOccupancyDecayParams* p);
+/* FreespaceIntegrator parameters (C/include/nvblox/integrators/freespace_integrator_params.h:22-58; setters
+ * freespace_integrator.h:75-128). */
+typedef struct NvbFreespaceParams {
+  float max_tsdf_distance_for_occupancy_m;                 /* 0.15 */
+  int64_t max_unobserved_to_keep_consecutive_occupancy_ms; /* 200  */
+  int64_t min_duration_since_occupied_for_freespace_ms;    /* 1000 */
+  int64_t min_consecutive_occupancy_duration_for_reset_ms; /* 2000 */
+  int32_t check_neighborhood;                              /* 1    */
+  int32_t initialize_to_high_confidence_freespace;         /* 0    */
+} NvbFreespaceParams;
+NVB_API void nvb_default_freespace_params(NvbFreespaceParams* p);
+NVB_API int32_t nvb_mapper_set_freespace_params(NvbMapper* m, const NvbFreespaceParams* p);
+NVB_API int32_t nvb_mapper_get_freespace_params(const NvbMapper* m, NvbFreespaceParams* p);
 NVB_API float nvb_mapper_voxel_size(const NvbMapper* m);
 NVB_API float nvb_mapper_block_size(const NvbMapper* m);
 
@@ -272,6 +296,23 @@ NVB_API int32_t nvb_mapper_update_esdf_async(NvbMapper* m, int32_t update_full_l
 NVB_API int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const float* depth,
                                  int32_t depth_memory, int32_t rows, int32_t cols, const float* T_L_C,
                                  const NvbCamera* cam, int32_t* removed_xyz_host, int32_t cap, int32_t* out_count);
+
+/* Mapper::updateFreespace(update_time_ms, T_L_C, sensor, depth_frame, update_full_layer) (mapper.h:196-214,
+ * mapper_impl.h:152-188) on a NVB_PROJECTIVE_TSDF_WITH_FREESPACE mapper: FreespaceIntegrator::updateFreespaceLayer
+ * (C/include/nvblox/integrators/internal/cuda/impl/freespace_integrator_impl.cuh:99-383) over the TSDF blocks touched
+ * since the last call (all on the first call / update_full_layer). depth != NULL: only voxels with a depth measurement
+ * in that view are updated (max view distance = the integrator's max integration distance, truncation = 2 x the
+ * truncation distance, mapper_impl.h:157-172); depth == NULL: no viewpoint exclusion. Synchronous. The following
+ * nvb_mapper_update_esdf treats high-confidence-free voxels as outside (esdf_integrator.cu:401-415). */
+NVB_API int32_t nvb_mapper_update_freespace(NvbMapper* m, int64_t update_time_ms, const float* depth, int32_t depth_memory,
+                                            int32_t rows, int32_t cols, const float* T_L_C, const NvbCamera* cam,
+                                            int32_t update_full_layer);
+/* FreespaceIntegrator::updateFreespaceLayer on an explicit block list (freespace_integrator.h:60-66); max_view_distance_m
+ * / truncation_distance_m <= 0 mean "unset" (no limit). Does not consult or reset the tracker. */
+NVB_API int32_t nvb_freespace_update_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks,
+                                            int64_t update_time_ms, const float* depth, int32_t depth_memory, int32_t rows,
+                                            int32_t cols, const float* T_L_C, const NvbCamera* cam,
+                                            float max_view_distance_m, float truncation_distance_m);
 
 /* Mapper::decayTsdfExcludeLastView / decayOccupancyExcludeLastView (mapper.h:218-230) with the view the mapper kept
  * (NvbMapperOptions.keep_last_view); decays every voxel if no frame was integrated yet, like the reference. */

@@ -12,8 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libnvblox_b200.so")
 
 NVB_OK = 0
 NVB_MEM_HOST, NVB_MEM_DEVICE = 0, 1
-NVB_LAYER_TSDF, NVB_LAYER_ESDF, NVB_LAYER_OCCUPANCY = 0, 1, 2
-NVB_PROJECTIVE_TSDF, NVB_PROJECTIVE_OCCUPANCY = 0, 1
+NVB_LAYER_TSDF, NVB_LAYER_ESDF, NVB_LAYER_OCCUPANCY, NVB_LAYER_FREESPACE = 0, 1, 2, 3
+NVB_PROJECTIVE_TSDF, NVB_PROJECTIVE_OCCUPANCY, NVB_PROJECTIVE_TSDF_WITH_FREESPACE = 0, 1, 2
 
 # Every symbol include/nvblox_b200.h declares (checked by tests/test_cabi_symbols.py).
 EXPORTED_SYMBOLS = [
@@ -23,6 +23,8 @@ EXPORTED_SYMBOLS = [
     "nvb_default_tsdf_decay_params", "nvb_mapper_set_tsdf_decay_params", "nvb_mapper_get_tsdf_decay_params",
     "nvb_default_occupancy_decay_params", "nvb_mapper_set_occupancy_decay_params",
     "nvb_mapper_get_occupancy_decay_params", "nvb_mapper_decay", "nvb_mapper_decay_exclude_last_view",
+    "nvb_default_freespace_params", "nvb_mapper_set_freespace_params", "nvb_mapper_get_freespace_params",
+    "nvb_mapper_update_freespace", "nvb_freespace_update_blocks",
     "nvb_mapper_create", "nvb_mapper_destroy", "nvb_mapper_clear",
     "nvb_mapper_set_tsdf_params", "nvb_mapper_get_tsdf_params",
     "nvb_mapper_set_esdf_params", "nvb_mapper_get_esdf_params",
@@ -69,6 +71,14 @@ class NvbOccupancyParams(C.Structure):
                 ("occupied_region_occupancy_probability", C.c_float),
                 ("unobserved_region_occupancy_probability", C.c_float),
                 ("occupied_region_half_width_m", C.c_float)]
+
+
+class NvbFreespaceParams(C.Structure):
+    _fields_ = [("max_tsdf_distance_for_occupancy_m", C.c_float),
+                ("max_unobserved_to_keep_consecutive_occupancy_ms", C.c_int64),
+                ("min_duration_since_occupied_for_freespace_ms", C.c_int64),
+                ("min_consecutive_occupancy_duration_for_reset_ms", C.c_int64),
+                ("check_neighborhood", C.c_int32), ("initialize_to_high_confidence_freespace", C.c_int32)]
 
 
 class NvbTsdfDecayParams(C.Structure):
@@ -135,6 +145,12 @@ def load():
     L.nvb_mapper_set_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
     L.nvb_mapper_get_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
     L.nvb_mapper_decay.argtypes = [vp, C.POINTER(NvbDecayExclusion), vp, i32, i32, i32, fp, C.POINTER(NvbCamera), ip, i32, ip]
+    L.nvb_default_freespace_params.argtypes = [C.POINTER(NvbFreespaceParams)]
+    L.nvb_default_freespace_params.restype = None
+    L.nvb_mapper_set_freespace_params.argtypes = [vp, C.POINTER(NvbFreespaceParams)]
+    L.nvb_mapper_get_freespace_params.argtypes = [vp, C.POINTER(NvbFreespaceParams)]
+    L.nvb_mapper_update_freespace.argtypes = [vp, C.c_int64, vp, i32, i32, i32, fp, C.POINTER(NvbCamera), i32]
+    L.nvb_freespace_update_blocks.argtypes = [vp, ip, i32, C.c_int64, vp, i32, i32, i32, fp, C.POINTER(NvbCamera), f32, f32]
     L.nvb_mapper_decay_exclude_last_view.argtypes = [vp, C.POINTER(NvbDecayExclusion), ip, i32, ip]
     L.nvb_mapper_create.argtypes = [C.POINTER(NvbMapperOptions), C.POINTER(vp)]
     L.nvb_mapper_create.restype = i32

@@ -68,6 +68,14 @@ struct NvbMapper {
   int esdf_persistent = 1;
 
   DevLayer tsdf{}, esdf{};
+  DevLayer freespace{};    // FreespaceLayer of a NVB_PROJECTIVE_TSDF_WITH_FREESPACE mapper
+  NvbFreespaceParams fp;
+  long long fs_last_update_ms = 0;  // FreespaceIntegrator::last_update_time_ms_ (freespace_integrator.h:171)
+  int* dirty_fs = nullptr;          // the tracker's second consumer (BlocksToUpdateType::kFreespace)
+  int* todo_fs_slots = nullptr;
+  bool fs_tracker_initialized = false;
+  int4* fs_work = nullptr;
+  int fs_work_cap = 0;
   int tsdf_count_ub = 0;   // host-side upper bound of *tsdf.count
   int esdf_extra_ub = 0;   // blocks submitted to the ESDF through explicit lists
 
@@ -305,18 +313,24 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
   int rc;
   if ((rc = reallocCopy(&m->dirty, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
   if ((rc = reallocCopy(&m->todo_slots, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if (m->projective_layer_type == NVB_PROJECTIVE_TSDF_WITH_FREESPACE) {
+    if ((rc = reallocCopy(&m->dirty_fs, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+    if ((rc = reallocCopy(&m->todo_fs_slots, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  }
   return NVB_OK;
 }
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kNumInts = 32 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kNumInts = 32 };
 
 float logOddsFromProbability(float p);
 
 EsdfCtx makeEsdfCtx(NvbMapper* m) {
   EsdfCtx c{};
   c.tsdf = m->tsdf, c.esdf = m->esdf;
+  c.freespace = m->freespace;
+  c.use_freespace = m->projective_layer_type == NVB_PROJECTIVE_TSDF_WITH_FREESPACE ? 1 : 0;
   c.work = m->work;
   c.work_count = m->esdf_ints + kWorkCount;
   c.upd_list = m->upd_list, c.upd_count = m->esdf_ints + kUpdCount;
@@ -639,6 +653,9 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
   ca.dirty = (integrate && m->tracker_initialized) ? m->dirty : nullptr;
   ca.todo_slots = m->todo_slots;
   ca.todo_count = m->todo_count;
+  ca.dirty2 = (integrate && m->dirty_fs && m->fs_tracker_initialized) ? m->dirty_fs : nullptr;
+  ca.todo2_slots = m->todo_fs_slots;
+  ca.todo2_count = m->esdf_ints + kTodoFsCount;
   launchCompactAllocate(ca, m->stream);
   if (compactUsesTickets(grid)) m->ticket_base += (unsigned int)compactNumTiles(grid);
   endStage(m);
@@ -843,7 +860,8 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
     return fail(NVB_ERR_NO_DEVICE, "no CUDA device: the depth-integration path has no CPU fallback");
   }
   if (opts->device < 0 || opts->device >= ndev) return fail(NVB_ERR_INVALID_ARGUMENT, "bad device ordinal");
-  if (opts->projective_layer_type != NVB_PROJECTIVE_TSDF && opts->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY)
+  if (opts->projective_layer_type != NVB_PROJECTIVE_TSDF && opts->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY &&
+      opts->projective_layer_type != NVB_PROJECTIVE_TSDF_WITH_FREESPACE)
     return fail(NVB_ERR_INVALID_ARGUMENT, "unknown projective_layer_type");
   NVB_CUDA(cudaSetDevice(opts->device));
   NvbMapper* m = new NvbMapper();
@@ -858,6 +876,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   nvb_default_occupancy_params(&m->op);
   nvb_default_tsdf_decay_params(&m->tdp);
   nvb_default_occupancy_decay_params(&m->odp);
+  nvb_default_freespace_params(&m->fp);
   m->projective_layer_type = opts->projective_layer_type;
   m->keep_last_view = opts->keep_last_view ? 1 : 0;
   m->esdf_persistent = opts->esdf_persistent;
@@ -876,6 +895,9 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   if ((rc = allocLayer(&m->tsdf, tcap, m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? kOccBlockBytes : kTsdfBlockBytes,
                        m->stream))) return rc;
   if ((rc = allocLayer(&m->esdf, ecap, kEsdfBlockBytes, m->stream))) return rc;
+  if (m->projective_layer_type == NVB_PROJECTIVE_TSDF_WITH_FREESPACE &&
+      (rc = allocLayer(&m->freespace, tcap, kFreespaceBlockBytes, m->stream)))
+    return rc;
   if ((rc = allocTsdfSide(m, 0, tcap))) return rc;
   if ((rc = allocEsdfScratch(m, 0, ecap))) return rc;
   NVB_CUDA(cudaMalloc(&m->esdf_ints, kNumInts * sizeof(int)));
@@ -918,6 +940,8 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaEventDestroy(m->esdf_ready), cudaEventDestroy(m->esdf_done), cudaEventDestroy(m->mark_done);
   cudaStreamDestroy(m->esdf_stream);
   freeLayer(&m->tsdf), freeLayer(&m->esdf);
+  if (m->freespace.blocks) freeLayer(&m->freespace);
+  cudaFree(m->dirty_fs), cudaFree(m->todo_fs_slots), cudaFree(m->fs_work);
   cudaFree(m->bits), cudaFree(m->frame_blocks), cudaFree(m->tile_state), cudaFree(m->ticket);
   for (int k = 0; k < kStagingBuffers; k++) {
     cudaFree(m->depth_stage[k]), cudaFree(m->mask_stage[k]);
@@ -940,7 +964,8 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
   NVB_CUDA(syncAll(m));
-  DevLayer* layers[2] = {&m->tsdf, &m->esdf};
+  std::vector<DevLayer*> layers = {&m->tsdf, &m->esdf};
+  if (m->freespace.blocks) layers.push_back(&m->freespace);
   for (DevLayer* L : layers) {
     int count = 0;
     NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
@@ -962,6 +987,10 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(cudaMemsetAsync(m->nbr27, 0xFE, (size_t)m->esdf.capacity * 27 * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
   m->tracker_initialized = false;
+  m->fs_tracker_initialized = false;
+  m->fs_last_update_ms = 0;
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoFsCount, 0, sizeof(int), m->stream));
+  if (m->dirty_fs) NVB_CUDA(cudaMemsetAsync(m->dirty_fs, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
   m->has_last_view = false;
   m->tsdf_count_ub = 0, m->tsdf_count_confirmed = 0, m->esdf_extra_ub = 0;
   m->cells_cum = 0, m->confirmed_cum = 0;
@@ -1171,7 +1200,12 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
     // Mapper::clearBlocksInLayers: the same blocks leave the ESDF layer; then both hashes are rebuilt without them
     EsdfCtx c = makeEsdfCtx(m);
     launchEsdfRemoveBlocks(c, m->dead, a.dead_count, n_dead, m->stream);
-    for (DevLayer* L : {&m->tsdf, &m->esdf}) {
+    std::vector<DevLayer*> touched = {&m->tsdf, &m->esdf};
+    if (m->freespace.blocks) {
+      launchRemoveBlocks(m->freespace, m->dead, a.dead_count, n_dead, m->stream);
+      touched.push_back(&m->freespace);
+    }
+    for (DevLayer* L : touched) {
       int hw = 0;
       NVB_CUDA(cudaMemcpyAsync(&hw, L->count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
       NVB_CUDA(cudaStreamSynchronize(m->stream));
@@ -1180,6 +1214,7 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
       launchRehash(*L, hw, m->stream);
     }
     m->launches += 6;
+    if (m->dirty_fs) NVB_CUDA(cudaMemsetAsync(m->dirty_fs, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
     if (out_count) *out_count = n_dead;
     if (removed_xyz_host && cap > 0) {
       const int k = std::min(n_dead, (int)cap);
@@ -1192,9 +1227,148 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
   }
   // BlocksToUpdateTracker::addAllBlocksToUpdate (mapper_impl.h:208-211): the next ESDF update covers every block
   m->tracker_initialized = false;
+  m->fs_tracker_initialized = false;
   NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoFsCount, 0, sizeof(int), m->stream));
   NVB_CUDA(syncAll(m));
   return checkDeviceError(m);
+}
+
+void nvb_default_freespace_params(NvbFreespaceParams* p) {
+  if (!p) return;
+  // integrators/freespace_integrator_params.h:22-58
+  p->max_tsdf_distance_for_occupancy_m = 0.15f;
+  p->max_unobserved_to_keep_consecutive_occupancy_ms = 200;
+  p->min_duration_since_occupied_for_freespace_ms = 1000;
+  p->min_consecutive_occupancy_duration_for_reset_ms = 2000;
+  p->check_neighborhood = 1;
+  p->initialize_to_high_confidence_freespace = 0;
+}
+int32_t nvb_mapper_set_freespace_params(NvbMapper* m, const NvbFreespaceParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  m->fp = *p;  // the reference's setters do not check (src/integrators/freespace_integrator.cu:35-83)
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_freespace_params(const NvbMapper* m, NvbFreespaceParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->fp;
+  return NVB_OK;
+}
+
+namespace {
+// FreespaceIntegrator::updateFreespaceLayer on the tracker's list (in_xyz_dev == nullptr) or on an explicit one.
+int freespaceUpdateImpl(NvbMapper* m, const int* in_xyz_dev, int n_explicit, long long now_ms, const float* depth, int memory,
+                        int rows, int cols, const float* T_L_C, const NvbCamera* cam, float max_view_distance_m,
+                        float truncation_distance_m) {
+  // the freespace slab follows the TSDF slab's capacity
+  if (m->freespace.capacity < m->tsdf.capacity) {
+    int rc = growLayer(m, &m->freespace, m->tsdf.capacity);
+    if (rc) return rc;
+  }
+  int upper = in_xyz_dev ? n_explicit : std::min(m->tsdf_count_ub, m->tsdf.capacity);
+  if (!in_xyz_dev) pollCounts(m), upper = std::min(m->tsdf_count_ub, m->tsdf.capacity);
+  if (upper < 1) upper = 1;
+  if (m->fs_work_cap < upper) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->fs_work) cudaFree(m->fs_work);
+    NVB_CUDA(cudaMalloc(&m->fs_work, (size_t)upper * 2 * sizeof(int4)));
+    m->fs_work_cap = upper * 2;
+  }
+  FreespaceArgs a{};
+  a.tsdf = m->tsdf, a.fs = m->freespace;
+  if (in_xyz_dev) {
+    a.in_xyz = in_xyz_dev, a.n_explicit = n_explicit;
+  } else {
+    a.todo_slots = m->todo_fs_slots, a.todo_count = m->esdf_ints + kTodoFsCount, a.tracker_dirty = m->dirty_fs;
+  }
+  a.work = m->fs_work, a.work_count = m->esdf_ints + kFsWorkCount, a.error = m->error_dev;
+  a.max_tsdf_distance_for_occupancy_m = m->fp.max_tsdf_distance_for_occupancy_m;
+  a.max_unobserved_ms = m->fp.max_unobserved_to_keep_consecutive_occupancy_ms;
+  a.min_free_ms = m->fp.min_duration_since_occupied_for_freespace_ms;
+  a.min_reset_ms = m->fp.min_consecutive_occupancy_duration_for_reset_ms;
+  a.check_neighborhood = m->fp.check_neighborhood ? 1 : 0;
+  a.init_high_confidence = m->fp.initialize_to_high_confidence_freespace ? 1 : 0;
+  a.last_update_ms = m->fs_last_update_ms, a.now_ms = now_ms;
+  a.p.block_size = m->block_size;
+  a.p.voxel_size = m->block_size * (1.0f / kVps);
+  a.p.half_voxel_size = m->block_size * (0.5f / kVps);
+  a.p.max_integration_distance_m = max_view_distance_m > 0.0f ? max_view_distance_m : FLT_MAX;
+  a.p.truncation_distance_m = truncation_distance_m > 0.0f ? truncation_distance_m : FLT_MAX;
+  float* depth_tmp = nullptr;
+  if (depth) {
+    const float* depth_dev = depth;
+    if (memory == NVB_MEM_HOST) {
+      NVB_CUDA(cudaMalloc(&depth_tmp, (size_t)rows * cols * sizeof(float)));
+      NVB_CUDA(cudaMemcpyAsync(depth_tmp, depth, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+      depth_dev = depth_tmp;
+    }
+    a.depth = depth_dev, a.rows = rows, a.cols = cols;
+    a.T_C_L = invertRigid(rigidFromColMajor(T_L_C));
+    a.cam = *cam;
+  }
+  launchFreespaceUpdate(a, upper, m->num_sms, m->stream);
+  m->launches += 2;
+  m->fs_last_update_ms = now_ms;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  if (depth_tmp) cudaFree(depth_tmp);
+  return checkDeviceError(m);
+}
+}  // namespace
+
+int32_t nvb_mapper_update_freespace(NvbMapper* m, int64_t update_time_ms, const float* depth, int32_t depth_memory,
+                                    int32_t rows, int32_t cols, const float* T_L_C, const NvbCamera* cam,
+                                    int32_t update_full_layer) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (m->projective_layer_type != NVB_PROJECTIVE_TSDF_WITH_FREESPACE)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "the mapper has no freespace layer");  // CHECK(hasFreespaceLayer(...)), mapper_impl.h:180-181
+  if (depth) {
+    int rc = validateFrameArgs(m, depth, rows, cols, T_L_C, cam);
+    if (rc) return rc;
+  }
+  NVB_CUDA(cudaSetDevice(m->device));
+  if (!m->fs_tracker_initialized || update_full_layer) {
+    launchTodoAll(m->tsdf, m->dirty_fs, m->todo_fs_slots, m->esdf_ints + kTodoFsCount, m->stream);
+    m->launches++;
+    m->fs_tracker_initialized = true;
+  }
+  // kTruncationDistanceMultiplier = 2 (mapper_impl.h:157-172)
+  return freespaceUpdateImpl(m, nullptr, 0, update_time_ms, depth, depth_memory, rows, cols, T_L_C, cam,
+                             m->tp.max_integration_distance_m, 2.0f * (m->tp.truncation_distance_vox * m->voxel_size));
+}
+
+int32_t nvb_freespace_update_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks, int64_t update_time_ms,
+                                    const float* depth, int32_t depth_memory, int32_t rows, int32_t cols, const float* T_L_C,
+                                    const NvbCamera* cam, float max_view_distance_m, float truncation_distance_m) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (m->projective_layer_type != NVB_PROJECTIVE_TSDF_WITH_FREESPACE)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "the mapper has no freespace layer");
+  if (num_blocks < 0 || (num_blocks > 0 && !blocks_xyz_host)) return fail(NVB_ERR_INVALID_ARGUMENT, "bad block list");
+  if (num_blocks == 0) return NVB_OK;  // early return (:337-339)
+  if (depth) {
+    int rc = validateFrameArgs(m, depth, rows, cols, T_L_C, cam);
+    if (rc) return rc;
+  }
+  NVB_CUDA(cudaSetDevice(m->device));
+  for (int i = 0; i < num_blocks; i++)
+    if (!indexInRange(blocks_xyz_host[3 * i], blocks_xyz_host[3 * i + 1], blocks_xyz_host[3 * i + 2]))
+      return fail(NVB_ERR_INDEX_RANGE, "block index outside +-2^20");
+  // a set, like every caller's list in the reference (find-or-insert needs unique keys per launch)
+  struct K3 {
+    int x, y, z;
+  };
+  std::vector<K3> v((size_t)num_blocks);
+  memcpy(v.data(), blocks_xyz_host, (size_t)num_blocks * sizeof(K3));
+  std::sort(v.begin(), v.end(), [](const K3& a, const K3& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); });
+  v.erase(std::unique(v.begin(), v.end(), [](const K3& a, const K3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }), v.end());
+  num_blocks = (int)v.size();
+  int* xyz_dev = nullptr;
+  NVB_CUDA(cudaMalloc(&xyz_dev, (size_t)num_blocks * 3 * sizeof(int)));
+  NVB_CUDA(cudaMemcpyAsync(xyz_dev, v.data(), (size_t)num_blocks * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  const int rc = freespaceUpdateImpl(m, xyz_dev, num_blocks, update_time_ms, depth, depth_memory, rows, cols, T_L_C, cam,
+                                     max_view_distance_m, truncation_distance_m);
+  cudaFree(xyz_dev);
+  return rc;
 }
 
 int32_t nvb_mapper_decay_exclude_last_view(NvbMapper* m, const NvbDecayExclusion* exclusion, int32_t* removed_xyz_host,
@@ -1384,7 +1558,8 @@ void* nvb_mapper_stream(NvbMapper* m) { return m ? (void*)m->stream : nullptr; }
 // The projective layer is a TsdfLayer or an OccupancyLayer, never both (Mapper allocates the one its
 // ProjectiveLayerType names, src/mapper/mapper.cpp:32-52): asking for the other one is an unknown layer.
 static DevLayer* layerOf(NvbMapper* m, int layer) {
-  if (layer == NVB_LAYER_TSDF) return m->projective_layer_type == NVB_PROJECTIVE_TSDF ? &m->tsdf : nullptr;
+  if (layer == NVB_LAYER_TSDF) return m->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY ? &m->tsdf : nullptr;
+  if (layer == NVB_LAYER_FREESPACE) return m->freespace.blocks ? &m->freespace : nullptr;
   if (layer == NVB_LAYER_OCCUPANCY) return m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? &m->tsdf : nullptr;
   if (layer == NVB_LAYER_ESDF) return &m->esdf;
   return nullptr;
@@ -1394,6 +1569,7 @@ int32_t nvb_layer_block_bytes(int32_t layer) {
   if (layer == NVB_LAYER_TSDF) return kTsdfBlockBytes;
   if (layer == NVB_LAYER_ESDF) return kEsdfBlockBytes;
   if (layer == NVB_LAYER_OCCUPANCY) return kOccBlockBytes;
+  if (layer == NVB_LAYER_FREESPACE) return kFreespaceBlockBytes;
   return 0;
 }
 

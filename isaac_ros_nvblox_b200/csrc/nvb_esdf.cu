@@ -66,7 +66,9 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
   }
   bool was_new;
   const int eslot = hashFindOrInsert(c.esdf, x, y, z, c.error, &was_new);
-  c.work[i] = make_int4(eslot, tslot, was_new ? 1 : 0, 0);
+  // isVoxelFreespace (:101-111): the freespace twin, if the mapper has a freespace layer and the block exists there
+  const int fslot = c.use_freespace ? hashFind(c.freespace.hash, x, y, z) : -1;
+  c.work[i] = make_int4(eslot, tslot, was_new ? 1 : 0, fslot);
 }
 
 // Per-CTA bookkeeping of the mark kernels: which of this CTA's blocks have sites / lost sites, and the AABB of the
@@ -164,11 +166,19 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
     for (int k = tid; k < kBlockWords / 4; k += kThreads) reinterpret_cast<uint4*>(s)[k] = gblk[k];
     const float2* tsdf = reinterpret_cast<const float2*>(c.tsdf.blocks + (size_t)w.y * kTsdfBlockBytes);
     const float2 t0 = tsdf[tid], t1 = tsdf[tid + kThreads];
+    // FreespaceVoxel::is_high_confidence_freespace of the two voxels (byte 16 of the 24-byte voxel)
+    bool fs0 = false, fs1 = false;
+    if (c.use_freespace && w.w >= 0) {
+      const unsigned char* fb = c.freespace.blocks + (size_t)w.w * kFreespaceBlockBytes;
+      fs0 = fb[(size_t)tid * kFreespaceVoxelBytes + 16] != 0;
+      fs1 = fb[(size_t)(tid + kThreads) * kFreespaceVoxelBytes + 16] != 0;
+    }
     __syncthreads();
     bool updated = false, cleared = false, changed = false;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const float2 t = h ? t1 : t0;
+      const bool is_freespace = h ? fs1 : fs0;
       unsigned int* e = s + (tid + h * kThreads) * kEsdfVoxelWords;
       float sq = __uint_as_float(e[0]);
       int p0 = (int)e[1], p1 = (int)e[2], p2 = (int)e[3];
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkKernel(EsdfCtx c) {
       bool e_inside = flagInside(fl), e_observed = flagObserved(fl), e_site = flagSite(fl);
       const bool is_observed = t.y >= c.min_weight;
       if (is_observed) {
-        const bool is_inside = t.x <= 0.0f;
+        const bool is_inside = (t.x <= 0.0f) & !is_freespace;  // "voxels being freespace can not be inside an object" (:413-415)
         const bool is_site = is_inside && (fabsf(t.x) <= c.max_site_distance_m);
         if (e_inside && !is_inside) {
           p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
@@ -928,7 +938,7 @@ void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t
     esdfMarkOccupancyKernel<<<cappedGrid(grid), kThreads, 0, stream>>>(c);
     return;
   }
-  if (use_tma) {
+  if (use_tma && !c.use_freespace) {  // the TMA ring stages the ESDF + TSDF blocks only
     int grid = num_sms * 4;  // 4 x 43 KiB of staging per SM; ~3000 items -> ~5 per CTA, 2 loads in flight each
     if (count_upper < grid) grid = count_upper;
     if (grid < 1) grid = 1;

@@ -294,6 +294,9 @@ struct CompactArgs {
   int* dirty;                      // per-slot dirty flag for the ESDF tracker (may be null)
   int* todo_slots;
   int* todo_count;
+  int* dirty2;                     // second consumer of the tracker (freespace; may be null)
+  int* todo2_slots;
+  int* todo2_count;
 };
 int compactNumTiles(const ViewGrid& grid);
 bool compactUsesTickets(const ViewGrid& grid);
@@ -320,6 +323,8 @@ void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, 
 struct EsdfCtx {
   DevLayer tsdf;
   DevLayer esdf;
+  DevLayer freespace;  // FreespaceLayer of a TSDF-with-freespace mapper (use_freespace)
+  int use_freespace;
   // work list of this update: {esdf_slot, tsdf_slot, is_new, 0}
   int4* work;
   int* work_count;
@@ -380,6 +385,34 @@ cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStrea
 cudaError_t runEsdfComputeHostLoop(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
 int esdfPersistentMaxCtas(int num_sms);
 
+constexpr int kFreespaceVoxelBytes = 24;
+constexpr int kFreespaceBlockBytes = 512 * kFreespaceVoxelBytes;  // 12 288
+// nvb_tsdf.cu: freespace (FreespaceIntegrator, integrators/internal/cuda/impl/freespace_integrator_impl.cuh)
+struct FreespaceArgs {
+  DevLayer tsdf, fs;
+  // blocks to update: TSDF slots from the tracker, or explicit indices
+  const int* todo_slots;
+  const int* todo_count;
+  const int* in_xyz;
+  int n_explicit;
+  int* tracker_dirty;  // cleared for the consumed slots (tracker mode)
+  int4* work;          // {tsdf slot, freespace slot, -, -}
+  int* work_count;
+  int* error;
+  // parameters
+  float max_tsdf_distance_for_occupancy_m;
+  long long max_unobserved_ms, min_free_ms, min_reset_ms;
+  int check_neighborhood, init_high_confidence;
+  long long last_update_ms, now_ms;
+  // DepthObservationSpace (null depth: every voxel is updated)
+  const float* depth;
+  int rows, cols;
+  Rigid T_C_L;
+  NvbCamera cam;
+  TsdfKernelParams p;
+};
+void launchFreespaceUpdate(const FreespaceArgs& a, int upper, int num_sms, cudaStream_t stream);
+
 // nvb_tsdf.cu: decay (VoxelDecayer::decay, integrators/internal/cuda/impl/decayer_impl.cuh)
 struct DecayArgs {
   DevLayer layer;  // the projective layer (TsdfVoxel or OccupancyVoxel blocks)
@@ -417,6 +450,7 @@ void launchScatterBlocks(const DevLayer& layer, const int* xyz_dev, int n, const
                          cudaStream_t stream);
 void launchFillU64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t stream);
 void launchRehash(const DevLayer& layer, int count, cudaStream_t stream);
+void launchRemoveBlocks(const DevLayer& layer, const int4* dead, const int* dead_count, int upper, cudaStream_t stream);
 void launchTodoAll(const DevLayer& tsdf, int* dirty, int* todo_slots, int* todo_count, cudaStream_t stream);
 void launchTodoConsume(const int* todo_slots, const int* todo_count, int* dirty, cudaStream_t stream);
 

@@ -316,6 +316,97 @@ __global__ void markSkippedKernel(DevLayer L, const int* xyz, int n, int* skip_s
   if (slot >= 0) skip_stamp[slot] = skip_seq;
 }
 
+// ---------------------------------------------------------------------------
+// FreespaceIntegrator::updateFreespaceLayer (freespace_integrator_impl.cuh:324-383): allocate the freespace twins of
+// the blocks to update, then updateFreespaceLayerKernel (:99-246) -- the dynablox freespace state machine, one CTA
+// (512 threads, one voxel each) per block.
+// ---------------------------------------------------------------------------
+__global__ void freespaceAllocateKernel(FreespaceArgs a) {
+  const int n = a.todo_count ? *a.todo_count : a.n_explicit;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *a.work_count = n;
+  if (i >= n) return;
+  int x, y, z, tslot;
+  if (a.todo_slots) {
+    tslot = a.todo_slots[i];
+    if (a.tracker_dirty) a.tracker_dirty[tslot] = 0;
+    x = a.tsdf.block_index[3 * tslot], y = a.tsdf.block_index[3 * tslot + 1], z = a.tsdf.block_index[3 * tslot + 2];
+  } else {
+    x = a.in_xyz[3 * i], y = a.in_xyz[3 * i + 1], z = a.in_xyz[3 * i + 2];
+    tslot = hashFind(a.tsdf.hash, x, y, z);
+  }
+  bool was_new;
+  const int fslot = hashFindOrInsert(a.fs, x, y, z, a.error, &was_new);  // allocateBlocksAtIndices (:343-345)
+  a.work[i] = make_int4(tslot, fslot, 0, 0);
+}
+
+struct FsVoxel {
+  long long last_occupied, consecutive;
+  unsigned long long flag;  // byte 0: is_high_confidence_freespace
+};
+
+template <bool kDistort>
+__global__ void __launch_bounds__(512) freespaceUpdateKernel(const __grid_constant__ FreespaceArgs a) {
+  __shared__ unsigned char s_free[512];
+  const int tid = threadIdx.x;
+  const int n = *a.work_count;
+  if (blockIdx.x == 0 && tid == 0 && a.todo_count) *const_cast<int*>(a.todo_count) = 0;  // tracker list consumed
+  TsdfArgs v;
+  v.depth = a.depth, v.mask = nullptr, v.mask_mode = 0, v.rows = a.rows, v.cols = a.cols;
+  v.T_C_L = a.T_C_L, v.cam = a.cam, v.p = a.p;
+  const int vx = tid >> 6, vy = (tid >> 3) & 7, vz = tid & 7;
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    const int4 w = a.work[item];
+    if (w.x < 0 || w.y < 0) continue;  // no TSDF block / slab exhausted
+    s_free[tid] = 0;
+    __syncthreads();
+    FsVoxel* gp = reinterpret_cast<FsVoxel*>(a.fs.blocks + (size_t)w.y * kFreespaceBlockBytes) + tid;
+    FsVoxel f = *gp;
+    const float2 t = reinterpret_cast<const float2*>(a.tsdf.blocks + (size_t)w.x * kTsdfBlockBytes)[tid];  // {distance, weight}
+    bool update_voxel = true;
+    if (a.depth) {
+      const int4 blk = make_int4(a.tsdf.block_index[3 * w.x], a.tsdf.block_index[3 * w.x + 1], a.tsdf.block_index[3 * w.x + 2], w.x);
+      update_voxel = voxelHasDepthMeasurement<kDistort>(v, blk, vx, vy, vz);
+    }
+    const bool init = f.last_occupied == 0;
+    if (init) {  // all voxels are initialised to being occupied
+      f.last_occupied = a.now_ms;
+      f.consecutive = 0;
+      f.flag = (f.flag & ~0xffull) | (a.init_high_confidence ? 1ull : 0ull);
+    }
+    bool is_free = false;
+    if (update_voxel && !init) {
+      // dynablox Eq. (9): consecutive occupancy duration
+      if (a.now_ms - f.last_occupied <= a.max_unobserved_ms) f.consecutive += a.now_ms - a.last_update_ms;
+      else f.consecutive = 0;
+      // Eq. (8): last occupied timestamp
+      if (t.x <= a.max_tsdf_distance_for_occupancy_m) f.last_occupied = a.now_ms;
+      // isVoxelFree (:36-44); `weight > 1e-6` is a float compared with a double literal
+      is_free = ((double)t.y > 1e-6) && (f.last_occupied != 0) && (f.last_occupied <= a.now_ms - a.min_free_ms);
+      s_free[tid] = is_free ? 1 : 0;
+    }
+    __syncthreads();
+    if (update_voxel && !init) {
+      if (a.check_neighborhood && is_free) {  // isVoxelNeighborhoodFree (:46-83): 3x3x3, inside this block only
+        for (int dx = -1; dx <= 1; dx++)
+          for (int dy = -1; dy <= 1; dy++)
+            for (int dz = -1; dz <= 1; dz++) {
+              const int x = vx + dx, y = vy + dy, z = vz + dz;
+              if ((dx | dy | dz) == 0) continue;
+              if (x < 0 || x > 7 || y < 0 || y > 7 || z < 0 || z > 7) continue;
+              is_free = is_free && s_free[(x * 8 + y) * 8 + z];
+            }
+      }
+      // Eq. (12) / (11): high confidence freespace
+      const bool hc = (f.flag & 0xffull) != 0;
+      const bool nhc = (f.consecutive >= a.min_reset_ms) ? false : (hc || is_free);
+      f.flag = (f.flag & ~0xffull) | (nhc ? 1ull : 0ull);
+    }
+    if (update_voxel || init) *gp = f;
+    __syncthreads();
+  }
+}
+
 // Resident CTAs per SM of the projective update kernels. 8 x 256 threads fill an SM's thread slots, which keeps the
 // cooperative ESDF wavefront of the previous frame (side stream, one 256-thread CTA per SM) from starting until
 // this kernel drains; NVB_TSDF_CTAS_PER_SM is the A/B switch for that trade-off.
@@ -374,6 +465,15 @@ void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, 
   const int grid = num_sms * projectiveCtasPerSm();
   if (cam.has_distortion) occupancyIntegrateKernel<true><<<grid, 256, 0, stream>>>(a, op);
   else occupancyIntegrateKernel<false><<<grid, 256, 0, stream>>>(a, op);
+}
+
+void launchFreespaceUpdate(const FreespaceArgs& a, int upper, int num_sms, cudaStream_t stream) {
+  if (upper < 1) upper = 1;
+  freespaceAllocateKernel<<<(upper + 255) / 256, 256, 0, stream>>>(a);
+  int grid = num_sms * 4;
+  if (upper < grid) grid = upper;
+  if (a.depth && a.cam.has_distortion) freespaceUpdateKernel<true><<<grid, 512, 0, stream>>>(a);
+  else freespaceUpdateKernel<false><<<grid, 512, 0, stream>>>(a);
 }
 
 void launchDecay(const DecayArgs& a, int num_sms, cudaStream_t stream) {

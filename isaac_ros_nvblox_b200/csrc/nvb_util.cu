@@ -98,7 +98,34 @@ __global__ void todoConsumeKernel(const int* todo_slots, const int* todo_count, 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dirty[todo_slots[i]] = 0;
 }
 
+// Generic twin of a deallocation (Mapper::clearBlocksInLayers for a layer without side tables): zero the block,
+// mark the slot dead, give it back. One CTA per dead block. The host rebuilds the hash afterwards.
+__global__ void removeBlocksKernel(DevLayer L, const int4* dead, const int* dead_count) {
+  __shared__ int s_slot;
+  const int n = *dead_count;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int4 d = dead[i];
+    if (threadIdx.x == 0) s_slot = hashFind(L.hash, d.y, d.z, d.w);
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot >= 0) {
+      uint4* g = reinterpret_cast<uint4*>(L.blocks + (size_t)slot * L.block_bytes);
+      for (int k = threadIdx.x; k < L.block_bytes / 16; k += blockDim.x) g[k] = make_uint4(0, 0, 0, 0);
+      if (threadIdx.x == 0) {
+        L.block_index[3 * slot] = kDeadSlotX;
+        L.free_slots[atomicAdd(L.free_count, 1)] = slot;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
+
+void launchRemoveBlocks(const DevLayer& layer, const int4* dead, const int* dead_count, int upper, cudaStream_t stream) {
+  int grid = upper < 1184 ? (upper < 1 ? 1 : upper) : 1184;
+  removeBlocksKernel<<<grid, 256, 0, stream>>>(layer, dead, dead_count);
+}
 
 void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsigned char* out, unsigned char* found,
                         cudaStream_t stream) {

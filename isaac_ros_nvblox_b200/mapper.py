@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (NvbCamera, NvbDecayExclusion, NvbEsdfParams, NvbMapperOptions, NvbOccupancyDecayParams,
+from ._lib import (NvbCamera, NvbDecayExclusion, NvbEsdfParams, NvbFreespaceParams, NvbMapperOptions, NvbOccupancyDecayParams,
                    NvbOccupancyParams, NvbTsdfDecayParams, NvbTsdfParams, check)
 
 TSDF_VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4")])
@@ -27,12 +27,15 @@ ESDF_VOXEL_DTYPE = np.dtype(
      ("is_inside", "u1"), ("observed", "u1"), ("is_site", "u1"), ("pad", "u1")])
 
 OCCUPANCY_VOXEL_DTYPE = np.dtype([("log_odds", "<f4")])  # map/voxels.h:51-53
+FREESPACE_VOXEL_DTYPE = np.dtype([("last_occupied_timestamp_ms", "<i8"), ("consecutive_occupancy_duration_ms", "<i8"),
+                                  ("is_high_confidence_freespace", "u1"), ("pad", "u1", (7,))])  # map/voxels.h:38-52
 
 
 class ProjectiveLayerType:
     """mapper/mapper.h:52-53."""
     kTsdf = _lib.NVB_PROJECTIVE_TSDF
     kOccupancy = _lib.NVB_PROJECTIVE_OCCUPANCY
+    kTsdfWithFreespace = _lib.NVB_PROJECTIVE_TSDF_WITH_FREESPACE
 
 
 STAGE_NAMES = ("view_calculator/raycast", "tsdf/integrate/allocate_blocks", "tsdf/integrate/update_blocks",
@@ -216,6 +219,36 @@ class _OccupancyIntegrator(_TsdfIntegrator):
             .occupied_region_half_width_m
 
 
+class _FreespaceIntegrator:
+    """FreespaceIntegrator parameter surface (freespace_integrator.h:75-128) + updateFreespaceLayer on a block list."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def params(self, **kw):
+        p = NvbFreespaceParams()
+        check(self._m._L.nvb_mapper_get_freespace_params(self._m._h, C.byref(p)))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        if kw:
+            check(self._m._L.nvb_mapper_set_freespace_params(self._m._h, C.byref(p)))
+        return p
+
+    def update_freespace_layer(self, block_indices, update_time_ms, depth=None, T_L_C=None, camera=None,
+                               max_view_distance_m=0.0, truncation_distance_m=0.0):
+        idx = np.ascontiguousarray(block_indices, dtype=np.int32).reshape(-1, 3)
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, dtype=np.float32)
+            T = colmajor(T_L_C)
+            check(self._m._L.nvb_freespace_update_blocks(self._m._h, _ip(idx), idx.shape[0], int(update_time_ms),
+                                                         depth.ctypes.data, _lib.NVB_MEM_HOST, depth.shape[0], depth.shape[1],
+                                                         _fp(T), C.byref(camera.c), float(max_view_distance_m),
+                                                         float(truncation_distance_m)))
+        else:
+            check(self._m._L.nvb_freespace_update_blocks(self._m._h, _ip(idx), idx.shape[0], int(update_time_ms), None, 0, 0, 0,
+                                                         None, None, 0.0, 0.0))
+
+
 class _DecayIntegrator:
     """TsdfDecayIntegrator / OccupancyDecayIntegrator parameter surface (tsdf_decay_integrator.h:73-101,
     occupancy_decay_integrator.h:72-101, internal/decay_integrator_base.h:50-58)."""
@@ -317,6 +350,7 @@ class Mapper:
         self._h = h
         self._tsdf = _Layer(self, _lib.NVB_LAYER_TSDF, TSDF_VOXEL_DTYPE)
         self._occupancy = _Layer(self, _lib.NVB_LAYER_OCCUPANCY, OCCUPANCY_VOXEL_DTYPE)
+        self._freespace = _Layer(self, _lib.NVB_LAYER_FREESPACE, FREESPACE_VOXEL_DTYPE)
         self._esdf = _Layer(self, _lib.NVB_LAYER_ESDF, ESDF_VOXEL_DTYPE)
         self._keep = []  # host buffers of in-flight async frames
 
@@ -343,6 +377,24 @@ class Mapper:
 
     def occupancy_layer(self):
         return self._occupancy
+
+    def freespace_layer(self):
+        return self._freespace
+
+    def freespace_integrator(self):
+        return _FreespaceIntegrator(self)
+
+    def update_freespace(self, update_time_ms, depth=None, T_L_C=None, camera=None, update_full_layer=False):
+        """Mapper::updateFreespace(update_time_ms, T_L_C, sensor, depth_frame, update_full_layer) (mapper.h:196-214)."""
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, dtype=np.float32)
+            T = colmajor(T_L_C)
+            check(self._L.nvb_mapper_update_freespace(self._h, int(update_time_ms), depth.ctypes.data, _lib.NVB_MEM_HOST,
+                                                      depth.shape[0], depth.shape[1], _fp(T), C.byref(camera.c),
+                                                      1 if update_full_layer else 0))
+        else:
+            check(self._L.nvb_mapper_update_freespace(self._h, int(update_time_ms), None, 0, 0, 0, None, None,
+                                                      1 if update_full_layer else 0))
 
     def esdf_layer(self):
         return self._esdf
@@ -381,7 +433,7 @@ class Mapper:
             x.exclusion_center = (C.c_float * 3)(*[float(v) for v in exclusion_center])
             x.exclusion_radius_m = float(exclusion_radius_m)
         n = C.c_int32(0)
-        cap = max(self._tsdf.num_blocks() if self._projective_layer_type == 0 else self._occupancy.num_blocks(), 1)
+        cap = max(self._occupancy.num_blocks() if self._projective_layer_type == 1 else self._tsdf.num_blocks(), 1)
         out = np.zeros((cap, 3), dtype=np.int32)
         if depth is not None:
             depth = np.ascontiguousarray(depth, dtype=np.float32)
@@ -396,13 +448,13 @@ class Mapper:
         """Mapper::decayTsdfExcludeLastView / decayOccupancyExcludeLastView with the view kept by the mapper
         (Mapper(..., keep_last_view=True))."""
         n = C.c_int32(0)
-        cap = max(self._tsdf.num_blocks() if self._projective_layer_type == 0 else self._occupancy.num_blocks(), 1)
+        cap = max(self._occupancy.num_blocks() if self._projective_layer_type == 1 else self._tsdf.num_blocks(), 1)
         out = np.zeros((cap, 3), dtype=np.int32)
         check(self._L.nvb_mapper_decay_exclude_last_view(self._h, None, _ip(out), cap, C.byref(n)))
         return out[:n.value].copy()
 
     def decay_tsdf(self, **kw):
-        assert self._projective_layer_type == ProjectiveLayerType.kTsdf
+        assert self._projective_layer_type != ProjectiveLayerType.kOccupancy
         return self.decay(**kw)
 
     def decay_occupancy(self, **kw):
