@@ -57,5 +57,6 @@ class VoxelBlockLayer {
 };
 using TsdfLayer = VoxelBlockLayer<TsdfVoxel>;
 using OccupancyLayer = VoxelBlockLayer<OccupancyVoxel>;
+using FreespaceLayer = VoxelBlockLayer<FreespaceVoxel>;
 using EsdfLayer = VoxelBlockLayer<EsdfVoxel>;
 }  // namespace nvblox

@@ -1,6 +1,7 @@
-// nvblox/map/voxels.h -- TsdfVoxel / OccupancyVoxel / EsdfVoxel with the reference's layout
+// nvblox/map/voxels.h -- TsdfVoxel / OccupancyVoxel / FreespaceVoxel / EsdfVoxel with the reference's layout
 // (nvblox/include/nvblox/map/voxels.h:28-74); these are the bytes stored in HBM.
 #pragma once
+#include <cstdint>
 #include "nvblox/core/types.h"
 namespace nvblox {
 struct TsdfVoxel {
@@ -9,6 +10,13 @@ struct TsdfVoxel {
 };
 struct OccupancyVoxel {
   float log_odds = 0.0f;
+};
+// nvblox::Time is a strongly typed int64 of milliseconds (core/time.h:25-70); plain int64_t here.
+using Time = int64_t;
+struct FreespaceVoxel {
+  Time last_occupied_timestamp_ms = 0;
+  Time consecutive_occupancy_duration_ms = 0;
+  bool is_high_confidence_freespace = false;
 };
 struct EsdfVoxel {
   float squared_distance_vox = 0.0f;
@@ -19,5 +27,6 @@ struct EsdfVoxel {
 };
 static_assert(sizeof(TsdfVoxel) == 8, "TsdfVoxel layout");
 static_assert(sizeof(OccupancyVoxel) == 4, "OccupancyVoxel layout");
+static_assert(sizeof(FreespaceVoxel) == 24, "FreespaceVoxel layout");
 static_assert(sizeof(EsdfVoxel) == 20, "EsdfVoxel layout");
 }  // namespace nvblox

@@ -98,6 +98,35 @@ class ProjectiveOccupancyIntegrator {
   NvbMapper* m_;
 };
 
+// FreespaceIntegrator (integrators/freespace_integrator.h:36-175): parameters + updateFreespaceLayer on a block list.
+class FreespaceIntegrator {
+ public:
+  explicit FreespaceIntegrator(NvbMapper* m) : m_(m) {}
+  float max_tsdf_distance_for_occupancy_m() const { return get().max_tsdf_distance_for_occupancy_m; }
+  void max_tsdf_distance_for_occupancy_m(float v) { auto p = get(); p.max_tsdf_distance_for_occupancy_m = v; set(p); }
+  Time max_unobserved_to_keep_consecutive_occupancy_ms() const { return get().max_unobserved_to_keep_consecutive_occupancy_ms; }
+  void max_unobserved_to_keep_consecutive_occupancy_ms(Time v) { auto p = get(); p.max_unobserved_to_keep_consecutive_occupancy_ms = v; set(p); }
+  Time min_duration_since_occupied_for_freespace_ms() const { return get().min_duration_since_occupied_for_freespace_ms; }
+  void min_duration_since_occupied_for_freespace_ms(Time v) { auto p = get(); p.min_duration_since_occupied_for_freespace_ms = v; set(p); }
+  Time min_consecutive_occupancy_duration_for_reset_ms() const { return get().min_consecutive_occupancy_duration_for_reset_ms; }
+  void min_consecutive_occupancy_duration_for_reset_ms(Time v) { auto p = get(); p.min_consecutive_occupancy_duration_for_reset_ms = v; set(p); }
+  bool check_neighborhood() const { return get().check_neighborhood != 0; }
+  void check_neighborhood(bool v) { auto p = get(); p.check_neighborhood = v ? 1 : 0; set(p); }
+  bool initialize_to_high_confidence_freespace() const { return get().initialize_to_high_confidence_freespace != 0; }
+  void initialize_to_high_confidence_freespace(bool v) { auto p = get(); p.initialize_to_high_confidence_freespace = v ? 1 : 0; set(p); }
+  // updateFreespaceLayer(block_indices, update_time_ms, tsdf_layer, {} /* no view */, freespace_layer)
+  void updateFreespaceLayer(const std::vector<Index3D>& block_indices, Time update_time_ms, const TsdfLayer&, FreespaceLayer*) {
+    std::vector<int32_t> raw(block_indices.size() * 3 + 3);
+    for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
+    b200_detail::check(nvb_freespace_update_blocks(m_, raw.data(), (int32_t)block_indices.size(), update_time_ms, nullptr, 0, 0, 0,
+                                                   nullptr, nullptr, 0.0f, 0.0f), "updateFreespaceLayer", nvb_last_error());
+  }
+ private:
+  NvbFreespaceParams get() const { NvbFreespaceParams p; b200_detail::check(nvb_mapper_get_freespace_params(m_, &p), "freespace params", nvb_last_error()); return p; }
+  void set(const NvbFreespaceParams& p) { b200_detail::check(nvb_mapper_set_freespace_params(m_, &p), "freespace params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+
 // TsdfDecayIntegrator / OccupancyDecayIntegrator parameter surfaces (integrators/tsdf_decay_integrator.h:73-101,
 // occupancy_decay_integrator.h:72-101, internal/decay_integrator_base.h:50-58).
 class TsdfDecayIntegrator {
@@ -198,6 +227,20 @@ class Mapper {
     b200_detail::check(nvb_mapper_update_esdf(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdf", nvb_last_error());
   }
   void clear() { b200_detail::check(nvb_mapper_clear(m_), "clear", nvb_last_error()); }
+  // Mapper::updateFreespace(update_time_ms, T_L_C, camera, depth_frame, update_full_layer) (mapper.h:196-214)
+  void updateFreespace(Time update_time_ms, const Transform& T_L_C, const Camera& camera,
+                       const DepthImageConstView& depth_frame, UpdateFullLayer full = UpdateFullLayer::kNo) {
+    b200_detail::check(nvb_mapper_update_freespace(m_, update_time_ms, depth_frame.dataConstPtr(),
+                                                   depth_frame.on_device() ? NVB_MEM_DEVICE : NVB_MEM_HOST, depth_frame.rows(),
+                                                   depth_frame.cols(), T_L_C.data(), camera.c_abi(),
+                                                   full == UpdateFullLayer::kYes ? 1 : 0), "updateFreespace", nvb_last_error());
+  }
+  void updateFreespace(Time update_time_ms, UpdateFullLayer full = UpdateFullLayer::kNo) {
+    b200_detail::check(nvb_mapper_update_freespace(m_, update_time_ms, nullptr, 0, 0, 0, nullptr, nullptr,
+                                                   full == UpdateFullLayer::kYes ? 1 : 0), "updateFreespace", nvb_last_error());
+  }
+  FreespaceLayer freespace_layer() const { return FreespaceLayer(m_, NVB_LAYER_FREESPACE); }
+  FreespaceIntegrator freespace_integrator() const { return FreespaceIntegrator(m_); }
   // Decay of the projective layer; deallocated blocks also leave the ESDF layer (mapper.h:218-233).
   void decayTsdfAllVoxels() { decayAll(ProjectiveLayerType::kTsdf); }
   void decayOccupancyAllVoxels() { decayAll(ProjectiveLayerType::kOccupancy); }
@@ -216,7 +259,8 @@ class Mapper {
   NvbMapper* c_abi() const { return m_; }
  private:
   void requireLayer(ProjectiveLayerType t) const {
-    if (projective_layer_type_ != t) b200_detail::check(NVB_ERR_INVALID_ARGUMENT, "decay", "the mapper does not hold that projective layer");
+    const bool tsdf_like = projective_layer_type_ == ProjectiveLayerType::kTsdf || projective_layer_type_ == ProjectiveLayerType::kTsdfWithFreespace;
+    if (!(projective_layer_type_ == t || (t == ProjectiveLayerType::kTsdf && tsdf_like))) b200_detail::check(NVB_ERR_INVALID_ARGUMENT, "decay", "the mapper does not hold that projective layer");
   }
   void decayAll(ProjectiveLayerType t) {
     requireLayer(t);
