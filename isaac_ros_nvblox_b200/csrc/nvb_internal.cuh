@@ -452,6 +452,5 @@ void launchFillU64(unsigned long long* p, unsigned long long v, size_t n, cudaSt
 void launchRehash(const DevLayer& layer, int count, cudaStream_t stream);
 void launchRemoveBlocks(const DevLayer& layer, const int4* dead, const int* dead_count, int upper, cudaStream_t stream);
 void launchTodoAll(const DevLayer& tsdf, int* dirty, int* todo_slots, int* todo_count, cudaStream_t stream);
-void launchTodoConsume(const int* todo_slots, const int* todo_count, int* dirty, cudaStream_t stream);
 
 }  // namespace nvb

@@ -91,13 +91,6 @@ __global__ void todoAllKernel(DevLayer tsdf, int* dirty, int* todo_slots, int* t
   }
 }
 
-// BlocksToUpdateState::markBlocksAsUpdated: clear the dirty flags of the consumed list
-// (the count itself is zeroed by a memset that follows in the stream).
-__global__ void todoConsumeKernel(const int* todo_slots, const int* todo_count, int* dirty) {
-  const int n = *todo_count;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dirty[todo_slots[i]] = 0;
-}
-
 // Generic twin of a deallocation (Mapper::clearBlocksInLayers for a layer without side tables): zero the block,
 // mark the slot dead, give it back. One CTA per dead block. The host rebuilds the hash afterwards.
 __global__ void removeBlocksKernel(DevLayer L, const int4* dead, const int* dead_count) {
@@ -144,9 +137,6 @@ void launchRehash(const DevLayer& layer, int count, cudaStream_t stream) {
 void launchTodoAll(const DevLayer& tsdf, int* dirty, int* todo_slots, int* todo_count, cudaStream_t stream) {
   cudaMemsetAsync(todo_count, 0, sizeof(int), stream);
   todoAllKernel<<<296, 256, 0, stream>>>(tsdf, dirty, todo_slots, todo_count);
-}
-void launchTodoConsume(const int* todo_slots, const int* todo_count, int* dirty, cudaStream_t stream) {
-  todoConsumeKernel<<<148, 256, 0, stream>>>(todo_slots, todo_count, dirty);
 }
 
 }  // namespace nvb
