@@ -1249,6 +1249,108 @@ static void esdf_integrate_from(OrMap* map, int from_occupancy, int use_freespac
   list_free(&blocks), list_free(&updated), list_free(&to_clear);
 }
 
+/* getBlockAndVoxelIndexFrom1DPositionInLayer (core/internal/impl/indexing_impl.h:105-115). */
+static void block_and_voxel_from_1d(float block_size, float p, int* block_idx, int* voxel_idx) {
+  const float voxel_size_inv = (float)(1.0 / (double)(block_size * (1.0f / VPS)));
+  const int b = f2i(floorf(p / block_size));
+  int v = f2i((p - block_size * (float)b) * voxel_size_inv);
+  if (v > VPS - 1) v = VPS - 1;
+  *block_idx = b, *voxel_idx = v;
+}
+
+/* EsdfIntegrator::integrateSlice with a ConstantZSliceDescription (src/integrators/esdf_integrator.cu:283-347,
+ * markSitesInSlice + markSitesInSliceKernel :754-1055): the band z_min..z_max of the projective layer is squashed
+ * onto the x/y voxels of ONE layer of ESDF blocks (min TSDF distance / max log odds of the observed, non-freespace
+ * voxels of each column), those voxels go through updateEsdfVoxelToChanges, and the usual clear + computeEsdf
+ * follow on the slice's blocks. */
+void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
+                             int32_t num_blocks, const OrEsdfParams* P, float z_min_m, float z_max_m, float z_output_m) {
+  memset(map->stats, 0, sizeof(map->stats));
+  if (num_blocks == 0) return;
+  const float max_esdf_distance_vox = P->max_esdf_distance_m / map->voxel_size;
+  const float max_sq = max_esdf_distance_vox * max_esdf_distance_vox;
+  const float max_site_distance_m = P->max_site_distance_vox * map->voxel_size;
+  const float occupied_threshold_log_odds = log_odds_from_probability(P->occupied_threshold);
+  int out_bz, out_vz, min_bz, min_vz, max_bz, max_vz;
+  block_and_voxel_from_1d(map->block_size, z_output_m, &out_bz, &out_vz);
+  block_and_voxel_from_1d(map->block_size, z_min_m, &min_bz, &min_vz); /* ConstantZColumnBoundsGetter (:76-88 of the impl) */
+  block_and_voxel_from_1d(map->block_size, z_max_m, &max_bz, &max_vz);
+  /* one output block per vertical column (Index3DSet, :968-973) */
+  List blocks = {0};
+  {
+    Hash seen;
+    int32_t hc = 16;
+    while (hc < 4 * num_blocks) hc *= 2;
+    hash_init(&seen, hc);
+    for (int32_t i = 0; i < num_blocks; i++) {
+      i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], out_bz};
+      if (hash_find(&seen, k) >= 0) continue;
+      hash_put(&seen, k, i);
+      list_push(&blocks, k);
+      layer_allocate(&map->esdf, k);
+    }
+    hash_free(&seen);
+  }
+  const Layer* src = from_occupancy ? &map->occ : &map->tsdf;
+  uint8_t* upd = (uint8_t*)calloc((size_t)blocks.n, 1);
+  uint8_t* clr = (uint8_t*)calloc((size_t)blocks.n, 1);
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < blocks.n; i++) {
+    const i3 ob = blocks.v[i];
+    OrEsdfVoxel* e = (OrEsdfVoxel*)layer_block(&map->esdf, hash_find(&map->esdf.hash, ob));
+    int cleared = 0, updated = 0;
+    for (int vx = 0; vx < VPS; vx++)
+      for (int vy = 0; vy < VPS; vy++) {
+        int observed = 0;
+        float squashed = from_occupancy ? 0.0f : 2.0f * max_sq; /* :792-799 */
+        for (int bz = min_bz; bz <= max_bz; bz++) {
+          const i3 k = {ob.x, ob.y, bz};
+          const int32_t ss = hash_find(&src->hash, k);
+          if (ss < 0) continue;
+          const int32_t fs = use_freespace ? hash_find(&map->freespace.hash, k) : -1;
+          const OrFreespaceVoxel* f = fs >= 0 ? (const OrFreespaceVoxel*)layer_block(&map->freespace, fs) : NULL;
+          const int z0 = bz == min_bz ? min_vz : 0, z1 = bz == max_bz ? max_vz : VPS - 1; /* getMinAndMaxVoxelZIndex */
+          for (int vz = z0; vz <= z1; vz++) {
+            const int v = (vx * VPS + vy) * VPS + vz;
+            const int is_fs = f ? f[v].is_high_confidence_freespace != 0 : 0;
+            if (from_occupancy) {
+              const float lo = ((const float*)layer_block(src, ss))[v];
+              if (fabsf(lo - 0.0f) > 1e-4f) {
+                observed = 1;
+                if (!is_fs) squashed = fmaxf(squashed, lo); /* atomicMaxFloat */
+              }
+            } else {
+              const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(src, ss) + v;
+              if (t->weight >= P->min_weight) {
+                observed = 1;
+                if (!is_fs) squashed = fminf(squashed, t->distance); /* atomicMinFloat */
+              }
+            }
+          }
+        }
+        OrEsdfVoxel* ev = &e[(vx * VPS + vy) * VPS + out_vz];
+        if (from_occupancy)
+          esdf_apply_observation(observed, squashed > occupied_threshold_log_odds, 1, max_sq, ev, &cleared, &updated);
+        else
+          esdf_apply_observation(observed, squashed <= 0.0f, fabsf(squashed) <= max_site_distance_m, max_sq, ev, &cleared,
+                                 &updated);
+      }
+    upd[i] = (uint8_t)updated, clr[i] = (uint8_t)cleared;
+  }
+  List updated = {0}, to_clear = {0};
+  for (int32_t i = 0; i < blocks.n; i++) {
+    if (upd[i]) list_push(&updated, blocks.v[i]);
+    if (clr[i]) list_push(&to_clear, blocks.v[i]);
+  }
+  free(upd), free(clr);
+  map->stats[0] = blocks.n, map->stats[1] = updated.n, map->stats[2] = to_clear.n;
+  if (to_clear.n > 0) esdf_clear_all_invalid(map, &to_clear, P->max_esdf_distance_m, max_sq, &map->esdf_cleared_persistent);
+  map->stats[4] = map->esdf_cleared_persistent.n;
+  esdf_compute(map, &updated, max_sq);
+  if (map->esdf_cleared_persistent.n > 0) esdf_compute(map, &map->esdf_cleared_persistent, max_sq);
+  list_free(&blocks), list_free(&updated), list_free(&to_clear);
+}
+
 void or_esdf_last_stats(const OrMap* map, int64_t out[8]) { memcpy(out, map->stats, sizeof(map->stats)); }
 
 /* ------------------------------------------------------------------------- */

@@ -223,6 +223,13 @@ void or_esdf_integrate_with_freespace(OrMap* map, const int32_t* blocks_xyz, int
 void or_esdf_integrate(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks,
                        const OrEsdfParams* params);
 
+/* EsdfIntegrator::integrateSlice(layer [, freespace], blocks, esdf) with a constant-z slice
+ * (integrators/esdf_integrator.h:96-150; esdf_slice_min_height / max_height / slice_height,
+ * esdf_integrator_params.h:33-43): 2-D ESDF on one layer of blocks at z_output_m. */
+void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
+                             int32_t num_blocks, const OrEsdfParams* params, float z_min_m, float z_max_m,
+                             float z_output_m);
+
 /* Statistics of the last or_esdf_integrate call: [0] blocks marked, [1] blocks
  * with sites, [2] blocks to clear, [3] candidate blocks scanned by the clear
  * pass, [4] blocks cleared, [5] total swept blocks, [6] total (block,direction)

@@ -165,6 +165,9 @@ def lib():
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.restype = None
+    L.or_esdf_integrate_slice.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), C.c_float, C.c_float,
+                                          C.c_float]
+    L.or_esdf_integrate_slice.restype = None
     L.or_default_freespace_params.argtypes = [C.POINTER(FreespaceParams)]
     L.or_default_freespace_params.restype = None
     L.or_freespace_update.argtypes = [vp, ip, C.c_int32, C.c_int64, C.POINTER(FreespaceParams), fp, C.c_int32, C.c_int32, fp,
@@ -430,6 +433,14 @@ class OracleMap:
             lib().or_freespace_get_block(self._h, _ip(np.ascontiguousarray(k, dtype=np.int32)), blk.ctypes.data)
             out[tuple(int(c) for c in k)] = blk
         return out
+
+    def integrate_esdf_slice(self, blocks, params=None, z_min_m=0.0, z_max_m=1.0, z_output_m=1.0, from_occupancy=False,
+                             use_freespace=False):
+        """EsdfIntegrator::integrateSlice with a constant-z slice (defaults = esdf_integrator_params.h:33-43)."""
+        params = params or default_esdf_params()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        lib().or_esdf_integrate_slice(self._h, 1 if from_occupancy else 0, 1 if use_freespace else 0, _ip(blocks),
+                                      blocks.shape[0], C.byref(params), float(z_min_m), float(z_max_m), float(z_output_m))
 
     def integrate_esdf_with_freespace(self, blocks, params=None):
         params = params or default_esdf_params()

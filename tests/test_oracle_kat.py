@@ -921,3 +921,106 @@ def test_esdf_with_freespace_removes_sites():
     sb = sum(int(v["is_site"].sum()) for v in b.esdf_layer().values())
     ib = sum(int(v["is_inside"].sum()) for v in b.esdf_layer().values())
     assert sa > 100 and sb == 0 and ib == 0
+
+
+# --- 2-D ESDF slice: test_esdf_integrator.cpp:967-1060 ---------------------------------------
+def _slice_world(m, out_bz, out_vz):
+    out = {}
+    for k, blk in m.esdf_layer().items():
+        assert k[2] == out_bz, "slice ESDF blocks live on one z layer"
+        obs = blk["observed"]
+        assert not obs[:, :, [z for z in range(8) if z != out_vz]].any()
+        for x in range(8):
+            for y in range(8):
+                v = blk[x, y, out_vz]
+                if v["observed"]:
+                    out[(k[0] * 8 + x, k[1] * 8 + y)] = v
+    return out
+
+
+@pytest.mark.parametrize("from_occupancy", [False, True])
+def test_esdf_slice_invariants_and_ground_truth(from_occupancy):
+    """Slice of a thin ground-truth band at z = 1 m (the shape of the reference's slice test, :967-1047): parents are
+    sites of the same slice, squared distance = |parent|^2, and the 2-D distance matches the analytic one."""
+    voxel, h = 0.1, 1.0
+    scene = syn.sphere_in_box()
+    m = orc.OracleMap(voxel)
+    ii = (np.indices((8, 8, 8)).reshape(3, -1).T + 0.5)
+    bs = 8 * voxel
+    keys = []
+    for x in range(-7, 7):
+        for y in range(-7, 7):
+            pos = (np.array([x, y, 1]) * 8 + ii) * voxel
+            band = np.abs(pos[:, 2] - h) <= voxel / 2 + 1e-6
+            inside = np.all((pos[:, :2] >= -5.5) & (pos[:, :2] <= 5.5), axis=1) & band
+            d = np.clip(scene.distance(pos), -0.4, 0.4)
+            if from_occupancy:
+                occ = scene.distance(pos) <= np.sqrt(3.0) * voxel / 2.0
+                blk = np.where(inside, np.where(occ, _log_odds(1.0), _log_odds(0.0)), np.float32(0)).astype(np.float32)
+                m.set_occupancy_block((x, y, 1), blk.reshape(8, 8, 8))
+            else:
+                blk = np.zeros(512, dtype=orc.TSDF_VOXEL_DTYPE)
+                blk["distance"] = np.where(inside, d, 0).astype(np.float32)
+                blk["weight"] = inside.astype(np.float32)
+                m.set_tsdf_block((x, y, 1), blk.reshape(8, 8, 8))
+            keys.append((x, y, 1))
+    keys = np.asarray(keys, np.int32)
+    ep = orc.default_esdf_params(max_esdf_distance_m=4.0, min_weight=0.5)
+    m.integrate_esdf_slice(keys, ep, z_min_m=h - 0.02, z_max_m=h + 0.02, z_output_m=h, from_occupancy=from_occupancy)
+    out_bz, out_vz = 1, int((h - bs) / voxel)
+    world = _slice_world(m, out_bz, out_vz)
+    assert len(world) > 5000
+    n = bad = sites = 0
+    for c, v in world.items():
+        p = v["parent_direction"]
+        if v["is_site"]:
+            sites += 1
+            assert v["squared_distance_vox"] == 0.0
+            continue
+        if not p.any():
+            continue
+        assert p[2] == 0
+        parent = world.get((c[0] + int(p[0]), c[1] + int(p[1])))
+        assert parent is not None and parent["is_site"]
+        assert float(v["squared_distance_vox"]) == float(int(p[0]) ** 2 + int(p[1]) ** 2)
+        if v["is_inside"]:
+            continue
+        # in-plane ground truth: the sphere's cross-section circle at z = h (and the walls, which only the occupancy
+        # layer marks: the TSDF band has no negative distances behind them)
+        px, py = (c[0] + 0.5) * voxel, (c[1] + 0.5) * voxel
+        gt = float(np.hypot(px, py) - np.sqrt(4.0 - (2.0 - h) ** 2))
+        if from_occupancy:
+            gt = min(gt, 5.0 - abs(px), 5.0 - abs(py))
+        if gt <= 0 or gt > 4.0 - voxel:
+            continue
+        d = voxel * float(np.sqrt(v["squared_distance_vox"]))
+        n += 1
+        if abs(d - gt) > 2.0 * voxel:
+            bad += 1
+    assert sites > 80 and n > 3000
+    assert bad / n < 0.01
+
+
+def test_esdf_slice_squashes_a_band_and_updates_incrementally():
+    """A band z in [0.3, 1.7] m of an integrated TSDF map is squashed to the slice at z = 1 m: an obstacle anywhere in the
+    band makes a site; a second call after more frames keeps the invariants (incremental slice update)."""
+    voxel = 0.1
+    cs = syn.PinholeCamera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    cam = orc.Camera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(16)[:6])
+    m = orc.OracleMap(voxel)
+    for i, (d, T) in enumerate(frames):
+        b = m.integrate_depth(d, T, cam)
+        m.integrate_esdf_slice(b if i else m.tsdf_block_indices(), z_min_m=0.3, z_max_m=1.7, z_output_m=1.0)
+    # getBlockAndVoxelIndexFrom1DPositionInLayer in binary32: (1.0 - 0.8f) * 10 = 1.9999999 -> voxel 1 of block 1
+    world = _slice_world(m, 1, 1)
+    sites = [c for c, v in world.items() if v["is_site"]]
+    assert len(sites) > 100
+    # the sphere (r = 2 at z = 2) has radius sqrt(4 - 0.3^2) ~ 1.98 at the top of the band: sites near that circle exist
+    r = np.array([np.hypot((c[0] + 0.5) * voxel, (c[1] + 0.5) * voxel) for c in sites])
+    assert ((r > 1.6) & (r < 2.2)).sum() > 20
+    for c, v in world.items():
+        p = v["parent_direction"]
+        if p.any():
+            parent = world.get((c[0] + int(p[0]), c[1] + int(p[1])))
+            assert parent is not None and parent["is_site"]
