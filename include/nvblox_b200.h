@@ -229,6 +229,17 @@ NVB_API int32_t nvb_mapper_get_tsdf_decay_params(const NvbMapper* m, NvbTsdfDeca
 NVB_API void nvb_default_occupancy_decay_params(NvbOccupancyDecayParams* p);
 NVB_API int32_t nvb_mapper_set_occupancy_decay_params(NvbMapper* m, const NvbOccupancyDecayParams* p);
 NVB_API int32_t nvb_mapper_get_occupancy_decay_params(const NvbMapper* m, NvbOccupancyDecayParams* p);
+/* The constant-z slice of the 2-D ESDF (esdf_slice_min_height / esdf_slice_max_height / esdf_slice_height,
+ * C/include/nvblox/integrators/esdf_integrator_params.h:33-43; setters esdf_integrator.h:216-256). */
+typedef struct NvbEsdfSliceParams {
+  float slice_min_height_m; /* 0 */
+  float slice_max_height_m; /* 1 */
+  float slice_height_m;     /* 1: z of the output slice */
+} NvbEsdfSliceParams;
+NVB_API void nvb_default_esdf_slice_params(NvbEsdfSliceParams* p);
+NVB_API int32_t nvb_mapper_set_esdf_slice_params(NvbMapper* m, const NvbEsdfSliceParams* p);
+NVB_API int32_t nvb_mapper_get_esdf_slice_params(const NvbMapper* m, NvbEsdfSliceParams* p);
+
 /* FreespaceIntegrator parameters (C/include/nvblox/integrators/freespace_integrator_params.h:22-58; setters
  * freespace_integrator.h:75-128). */
 typedef struct NvbFreespaceParams {
@@ -318,6 +329,16 @@ NVB_API int32_t nvb_freespace_update_blocks(NvbMapper* m, const int32_t* blocks_
  * (NvbMapperOptions.keep_last_view); decays every voxel if no frame was integrated yet, like the reference. */
 NVB_API int32_t nvb_mapper_decay_exclude_last_view(NvbMapper* m, const NvbDecayExclusion* exclusion,
                                                    int32_t* removed_xyz_host, int32_t cap, int32_t* out_count);
+
+/* Mapper::updateEsdfSlice (mapper.h:331-343; EsdfMode::k2D) = EsdfIntegrator::integrateSlice with the constant-z
+ * slice description (C/src/integrators/esdf_integrator.cu:283-347, markSitesInSlice :754-1055): the band
+ * [slice_min_height, slice_max_height] of the projective layer (honouring the freespace layer if the mapper has one) is
+ * squashed onto ONE layer of ESDF blocks at slice_height; clear + computeEsdf then run on that layer. A mapper's ESDF
+ * layer is either 3-D or 2-D: mixing nvb_mapper_update_esdf and nvb_mapper_update_esdf_slice is an error, like the
+ * reference's EsdfMode check. Synchronous. */
+NVB_API int32_t nvb_mapper_update_esdf_slice(NvbMapper* m, int32_t update_full_layer);
+/* EsdfIntegrator::integrateSlice(layer, block_indices, esdf_layer) on an explicit block list (esdf_integrator.h:96-118). */
+NVB_API int32_t nvb_esdf_integrate_slice_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks);
 
 /* EsdfIntegrator::integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
  * (esdf_integrator.h:56-58, src/integrators/esdf_integrator.cu:220-266) on an

@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = [
     "nvb_mapper_get_occupancy_decay_params", "nvb_mapper_decay", "nvb_mapper_decay_exclude_last_view",
     "nvb_default_freespace_params", "nvb_mapper_set_freespace_params", "nvb_mapper_get_freespace_params",
     "nvb_mapper_update_freespace", "nvb_freespace_update_blocks",
+    "nvb_default_esdf_slice_params", "nvb_mapper_set_esdf_slice_params", "nvb_mapper_get_esdf_slice_params",
+    "nvb_mapper_update_esdf_slice", "nvb_esdf_integrate_slice_blocks",
     "nvb_mapper_create", "nvb_mapper_destroy", "nvb_mapper_clear",
     "nvb_mapper_set_tsdf_params", "nvb_mapper_get_tsdf_params",
     "nvb_mapper_set_esdf_params", "nvb_mapper_get_esdf_params",
@@ -71,6 +73,10 @@ class NvbOccupancyParams(C.Structure):
                 ("occupied_region_occupancy_probability", C.c_float),
                 ("unobserved_region_occupancy_probability", C.c_float),
                 ("occupied_region_half_width_m", C.c_float)]
+
+
+class NvbEsdfSliceParams(C.Structure):
+    _fields_ = [("slice_min_height_m", C.c_float), ("slice_max_height_m", C.c_float), ("slice_height_m", C.c_float)]
 
 
 class NvbFreespaceParams(C.Structure):
@@ -145,6 +151,12 @@ def load():
     L.nvb_mapper_set_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
     L.nvb_mapper_get_occupancy_decay_params.argtypes = [vp, C.POINTER(NvbOccupancyDecayParams)]
     L.nvb_mapper_decay.argtypes = [vp, C.POINTER(NvbDecayExclusion), vp, i32, i32, i32, fp, C.POINTER(NvbCamera), ip, i32, ip]
+    L.nvb_default_esdf_slice_params.argtypes = [C.POINTER(NvbEsdfSliceParams)]
+    L.nvb_default_esdf_slice_params.restype = None
+    L.nvb_mapper_set_esdf_slice_params.argtypes = [vp, C.POINTER(NvbEsdfSliceParams)]
+    L.nvb_mapper_get_esdf_slice_params.argtypes = [vp, C.POINTER(NvbEsdfSliceParams)]
+    L.nvb_mapper_update_esdf_slice.argtypes = [vp, i32]
+    L.nvb_esdf_integrate_slice_blocks.argtypes = [vp, ip, i32]
     L.nvb_default_freespace_params.argtypes = [C.POINTER(NvbFreespaceParams)]
     L.nvb_default_freespace_params.restype = None
     L.nvb_mapper_set_freespace_params.argtypes = [vp, C.POINTER(NvbFreespaceParams)]

@@ -70,6 +70,12 @@ struct NvbMapper {
   DevLayer tsdf{}, esdf{};
   DevLayer freespace{};    // FreespaceLayer of a NVB_PROJECTIVE_TSDF_WITH_FREESPACE mapper
   NvbFreespaceParams fp;
+  NvbEsdfSliceParams sp;
+  int esdf_mode = 0;                // EsdfMode: 0 unset, 1 3-D, 2 2-D slice (mapper.h:61, src/mapper/mapper.cpp:408-470)
+  unsigned long long* colset = nullptr;
+  size_t colset_n = 0;
+  int* cols = nullptr;
+  int cols_cap = 0;
   long long fs_last_update_ms = 0;  // FreespaceIntegrator::last_update_time_ms_ (freespace_integrator.h:171)
   int* dirty_fs = nullptr;          // the tracker's second consumer (BlocksToUpdateType::kFreespace)
   int* todo_fs_slots = nullptr;
@@ -322,7 +328,7 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kNumInts = 32 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kNumInts = 32 };
 
 float logOddsFromProbability(float p);
 
@@ -346,6 +352,8 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.nbr27 = m->nbr27, c.shadow = m->shadow, c.cand_stamp = m->cand_stamp;
   c.ges_counts = m->esdf_ints + kGesCounts;
   c.cand_a = m->cand_a, c.cand_b = m->cand_b, c.ges_switch = m->ges_switch;
+  c.colset_keys = m->colset, c.colset_mask = m->colset_n ? (unsigned int)(m->colset_n - 1) : 0u;
+  c.cols = m->cols, c.cols_count = m->esdf_ints + kColsCount;
   c.dead_cleared_xyz = m->dead_cleared_xyz;
   c.dead_cleared_count = m->dead_cleared_xyz ? m->esdf_ints + kDeadClearedCount : nullptr;
   c.cleared_seq = m->esdf_ints + kClearedSeq;
@@ -727,9 +735,14 @@ int readFrameList(NvbMapper* m, int32_t* out_xyz, int32_t cap, int32_t* out_coun
   return NVB_OK;
 }
 
-int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_tracker) {
+int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_tracker, bool slice = false) {
   int rc;
   int upper;
+  // EsdfMode: a mapper's ESDF layer is 3-D or a 2-D slice, never both (src/mapper/mapper.cpp:410-415,436-441)
+  const int want_mode = slice ? 2 : 1;
+  if (m->esdf_mode != 0 && m->esdf_mode != want_mode)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "the ESDF layer of this mapper is already in the other mode (3-D vs 2-D slice)");
+  m->esdf_mode = want_mode;
   if (from_tracker) {
     pollCounts(m);
     upper = std::min(m->tsdf_count_ub, m->tsdf.capacity);
@@ -739,12 +752,50 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
   }
   if (upper <= 0) upper = 1;
   if ((rc = ensureEsdfCapacity(m, (long long)std::min(m->tsdf_count_ub, m->tsdf.capacity) + m->esdf_extra_ub))) return rc;
+  if (slice) {
+    // column set + column list sized to the projective layer
+    const size_t want = (size_t)nextPow2(2ll * std::max(m->tsdf.capacity, upper));
+    if (m->colset_n < want || m->cols_cap < std::max(m->tsdf.capacity, upper)) {
+      NVB_CUDA(syncAll(m));
+      if (m->colset) cudaFree(m->colset);
+      if (m->cols) cudaFree(m->cols);
+      NVB_CUDA(cudaMalloc(&m->colset, want * sizeof(unsigned long long)));
+      m->colset_n = want;
+      m->cols_cap = std::max(m->tsdf.capacity, upper);
+      NVB_CUDA(cudaMalloc(&m->cols, (size_t)m->cols_cap * 2 * sizeof(int)));
+    }
+  }
   m->update_seq++;
   EsdfCtx c = makeEsdfCtx(m);
   c.tracker_dirty = from_tracker ? m->dirty : nullptr;
   c.tracker_todo_count = from_tracker ? m->todo_count : nullptr;
+  if (slice) {
+    // getBlockAndVoxelIndexFrom1DPositionInLayer (core/internal/impl/indexing_impl.h:105-115), on the host like the
+    // reference (ConstantZColumnBoundsGetter's constructor and markSitesInSlice, esdf_integrator.cu:959-962)
+    auto split = [&](float p, int* b, int* v) {
+      const float inv = (float)(1.0 / (double)(m->block_size * (1.0f / kVps)));
+      *b = (int)std::floor(p / m->block_size);
+      *v = std::min((int)((p - m->block_size * (float)*b) * inv), kVps - 1);
+    };
+    split(m->sp.slice_min_height_m, &c.slice_min_bz, &c.slice_min_vz);
+    split(m->sp.slice_max_height_m, &c.slice_max_bz, &c.slice_max_vz);
+    split(m->sp.slice_height_m, &c.slice_out_bz, &c.slice_out_vz);
+    if (c.slice_max_bz < c.slice_min_bz) return fail(NVB_ERR_INVALID_ARGUMENT, "slice_max_height below slice_min_height");
+  }
   int launches = 0;
   cudaError_t e;
+  auto allocAndMark = [&](cudaStream_t st) {
+    if (slice) {
+      launchEsdfSliceAllocateAndMark(c, from_tracker ? nullptr : in_xyz_dev, from_tracker ? m->todo_slots : nullptr,
+                                     from_tracker ? m->todo_count : nullptr, from_tracker ? upper : n_explicit, m->num_sms, st);
+      m->launches += 3;
+    } else {
+      if (from_tracker) launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, st);
+      else launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, st);
+      launchEsdfMark(c, upper, m->num_sms, st);
+      m->launches += 2;
+    }
+  };
   if (m->esdf_persistent) {
     // The whole ESDF chain (allocate, mark, clear, wavefront) runs back to back on the side stream; the frame's
     // critical path has no cross-stream hand-over. `stream` only waits for the mark kernel: after it nothing on
@@ -755,10 +806,7 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
     NVB_CUDA(cudaEventRecord(m->esdf_ready, m->stream));  // projective layer + tracker of this update are final
     NVB_CUDA(cudaStreamWaitEvent(es, m->esdf_ready, 0));
     beginStageOn(m, 3, es);
-    if (from_tracker) launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, es);
-    else launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, es);
-    launchEsdfMark(c, upper, m->num_sms, es);
-    m->launches += 2;
+    allocAndMark(es);
     endStageOn(m, es);
     NVB_CUDA(cudaEventRecord(m->mark_done, es));
     NVB_CUDA(cudaStreamWaitEvent(m->stream, m->mark_done, 0));
@@ -777,10 +825,7 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
   } else {
     NVB_CUDA(joinEsdf(m));
     beginStage(m, 3);
-    if (from_tracker) launchEsdfAllocate(c, nullptr, m->todo_slots, m->todo_count, upper, m->stream);
-    else launchEsdfAllocate(c, in_xyz_dev, nullptr, nullptr, n_explicit, m->stream);
-    launchEsdfMark(c, upper, m->num_sms, m->stream);
-    m->launches += 2;
+    allocAndMark(m->stream);
     endStage(m);
     beginStage(m, 4);
     launchEsdfClear(c, m->esdf.capacity, m->num_sms, m->stream);
@@ -877,6 +922,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   nvb_default_tsdf_decay_params(&m->tdp);
   nvb_default_occupancy_decay_params(&m->odp);
   nvb_default_freespace_params(&m->fp);
+  nvb_default_esdf_slice_params(&m->sp);
   m->projective_layer_type = opts->projective_layer_type;
   m->keep_last_view = opts->keep_last_view ? 1 : 0;
   m->esdf_persistent = opts->esdf_persistent;
@@ -941,7 +987,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaStreamDestroy(m->esdf_stream);
   freeLayer(&m->tsdf), freeLayer(&m->esdf);
   if (m->freespace.blocks) freeLayer(&m->freespace);
-  cudaFree(m->dirty_fs), cudaFree(m->todo_fs_slots), cudaFree(m->fs_work);
+  cudaFree(m->dirty_fs), cudaFree(m->todo_fs_slots), cudaFree(m->fs_work), cudaFree(m->colset), cudaFree(m->cols);
   cudaFree(m->bits), cudaFree(m->frame_blocks), cudaFree(m->tile_state), cudaFree(m->ticket);
   for (int k = 0; k < kStagingBuffers; k++) {
     cudaFree(m->depth_stage[k]), cudaFree(m->mask_stage[k]);
@@ -988,6 +1034,7 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
   m->tracker_initialized = false;
   m->fs_tracker_initialized = false;
+  m->esdf_mode = 0;
   m->fs_last_update_ms = 0;
   NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoFsCount, 0, sizeof(int), m->stream));
   if (m->dirty_fs) NVB_CUDA(cudaMemsetAsync(m->dirty_fs, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
@@ -1199,6 +1246,13 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
   if (n_dead > 0) {
     // Mapper::clearBlocksInLayers: the same blocks leave the ESDF layer; then both hashes are rebuilt without them
     EsdfCtx c = makeEsdfCtx(m);
+    if (m->esdf_mode == 2) {
+      c.slice_mode = 1;
+      // getBlockIndexFromPositionInLayer of the slice heights (src/mapper/mapper.cpp:574-590)
+      c.slice_min_bz = (int)std::floor(m->sp.slice_min_height_m / m->block_size);
+      c.slice_max_bz = (int)std::floor(m->sp.slice_max_height_m / m->block_size);
+      c.slice_out_bz = (int)std::floor(m->sp.slice_height_m / m->block_size);
+    }
     launchEsdfRemoveBlocks(c, m->dead, a.dead_count, n_dead, m->stream);
     std::vector<DevLayer*> touched = {&m->tsdf, &m->esdf};
     if (m->freespace.blocks) {
@@ -1477,6 +1531,59 @@ int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, 
   NVB_CUDA(cudaMemcpyAsync(m->xyz_upload, v.data(), (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
   NVB_CUDA(cudaStreamSynchronize(m->stream));  // v is pageable and about to go out of scope
   int rc = enqueueEsdf(m, m->xyz_upload, n, false);
+  if (rc) return rc;
+  return nvb_mapper_synchronize(m);
+}
+
+void nvb_default_esdf_slice_params(NvbEsdfSliceParams* p) {
+  if (!p) return;
+  // integrators/esdf_integrator_params.h:33-43
+  p->slice_min_height_m = 0.0f;
+  p->slice_max_height_m = 1.0f;
+  p->slice_height_m = 1.0f;
+}
+int32_t nvb_mapper_set_esdf_slice_params(NvbMapper* m, const NvbEsdfSliceParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (!(p->slice_max_height_m >= p->slice_min_height_m)) return fail(NVB_ERR_INVALID_ARGUMENT, "slice_max_height below slice_min_height");
+  m->sp = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_esdf_slice_params(const NvbMapper* m, NvbEsdfSliceParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->sp;
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_update_esdf_slice(NvbMapper* m, int32_t update_full_layer) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  NVB_CUDA(cudaSetDevice(m->device));
+  if (!m->tracker_initialized || update_full_layer) {
+    launchTodoAll(m->tsdf, m->dirty, m->todo_slots, m->todo_count, m->stream);
+    m->launches++;
+    m->tracker_initialized = true;
+  }
+  int rc = enqueueEsdf(m, nullptr, 0, true, true);
+  if (rc) return rc;
+  return nvb_mapper_synchronize(m);
+}
+
+int32_t nvb_esdf_integrate_slice_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (num_blocks < 0 || (num_blocks > 0 && !blocks_xyz_host)) return fail(NVB_ERR_INVALID_ARGUMENT, "bad block list");
+  if (num_blocks == 0) return NVB_OK;  // early return (:289-291)
+  NVB_CUDA(cudaSetDevice(m->device));
+  for (int i = 0; i < num_blocks; i++)
+    if (!indexInRange(blocks_xyz_host[3 * i], blocks_xyz_host[3 * i + 1], blocks_xyz_host[3 * i + 2]))
+      return fail(NVB_ERR_INDEX_RANGE, "block index outside +-2^20");
+  if (num_blocks > m->xyz_upload_cap) {
+    NVB_CUDA(syncAll(m));
+    if (m->xyz_upload) cudaFree(m->xyz_upload);
+    NVB_CUDA(cudaMalloc(&m->xyz_upload, (size_t)num_blocks * 2 * 3 * sizeof(int)));
+    m->xyz_upload_cap = num_blocks * 2;
+  }
+  NVB_CUDA(cudaMemcpyAsync(m->xyz_upload, blocks_xyz_host, (size_t)num_blocks * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int rc = enqueueEsdf(m, m->xyz_upload, num_blocks, false, true);
   if (rc) return rc;
   return nvb_mapper_synchronize(m);
 }

@@ -831,8 +831,26 @@ __global__ void __launch_bounds__(kThreads) esdfRemoveBlocksKernel(EsdfCtx c, co
   const int n = *dead_count;
   __shared__ int s_slot;
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const int4 d = dead[i];
-    if (tid == 0) s_slot = hashFind(c.esdf.hash, d.y, d.z, d.w);
+    int4 d = dead[i];
+    if (c.slice_mode) {
+      // 2-D ESDF (src/mapper/mapper.cpp:569-626): the column's slice block goes only when no projective block is left
+      // in the vertical column within the slice bounds; several dead blocks of one column elect one remover.
+      d.w = c.slice_out_bz;
+      if (tid == 0) {
+        int es = hashFind(c.esdf.hash, d.y, d.z, d.w);
+        if (es >= 0) {
+          bool has_block = false;
+          for (int bz = c.slice_min_bz; bz <= c.slice_max_bz && !has_block; bz++) {
+            const int ps = hashFind(c.tsdf.hash, d.y, d.z, bz);  // the hash still lists the dead blocks: check the slot
+            has_block = ps >= 0 && c.tsdf.block_index[3 * ps] != kDeadSlotX;
+          }
+          if (has_block || atomicExch(&c.esdf.block_index[3 * es], kDeadSlotX) == kDeadSlotX) es = -1;
+        }
+        s_slot = es;
+      }
+    } else if (tid == 0) {
+      s_slot = hashFind(c.esdf.hash, d.y, d.z, d.w);
+    }
     __syncthreads();
     const int slot = s_slot;
     if (slot >= 0) {
@@ -904,6 +922,191 @@ void launchEsdfRemoveBlocks(const EsdfCtx& c, const int4* dead, const int* dead_
   int grid = upper < 1184 ? (upper < 1 ? 1 : upper) : 1184;
   esdfRemoveBlocksKernel<<<grid, kThreads, 0, stream>>>(c, dead, dead_count);
   esdfFilterClearedKernel<<<1, kThreads, 0, stream>>>(c);
+}
+
+// ---------------------------------------------------------------------------
+// 2-D ESDF: EsdfIntegrator::markSitesInSlice with a ConstantZSliceDescription (esdf_integrator.cu:754-1055).
+// (1) the blocks to update are reduced to their (x, y) columns (the reference builds an Index3DSet on the host),
+// (2) the ESDF blocks of the output layer are allocated, (3) one CTA per column block squashes the band of the
+// projective layer onto the slice voxels (min TSDF distance / max log odds over the observed, non-freespace voxels:
+// order-independent, so no atomics are needed when one thread walks its own voxel column) and runs
+// updateEsdfVoxelToChanges on them.
+// ---------------------------------------------------------------------------
+__global__ void esdfSliceColumnsKernel(EsdfCtx c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
+                                       int in_count_host) {
+  const int n = in_count_dev ? *in_count_dev : in_count_host;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y;
+  if (in_slots) {
+    const int tslot = in_slots[i];
+    if (c.tracker_dirty) c.tracker_dirty[tslot] = 0;
+    x = c.tsdf.block_index[3 * tslot], y = c.tsdf.block_index[3 * tslot + 1];
+  } else {
+    x = in_xyz[3 * i], y = in_xyz[3 * i + 1];
+  }
+  if (!indexInRange(x, y, c.slice_out_bz)) {
+    atomicOr(c.error, 2);
+    return;
+  }
+  const unsigned long long key = packIndex(x, y, c.slice_out_bz);
+  unsigned int p = hashKey(key) & c.colset_mask;
+  while (true) {
+    const unsigned long long old = atomicCAS(&c.colset_keys[p], kEmptyKey, key);
+    if (old == kEmptyKey) {
+      const int q = atomicAdd(c.cols_count, 1);
+      c.cols[2 * q] = x, c.cols[2 * q + 1] = y;
+      return;
+    }
+    if (old == key) return;
+    p = (p + 1) & c.colset_mask;
+  }
+}
+
+__global__ void esdfSliceAllocateKernel(EsdfCtx c) {
+  const int n = *c.cols_count;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    *c.work_count = n;
+    *c.upd_count = 0;
+    *c.clr_count = 0;
+    c.clr_aabb[0] = c.clr_aabb[1] = c.clr_aabb[2] = INT32_MAX;
+    c.clr_aabb[3] = c.clr_aabb[4] = c.clr_aabb[5] = INT32_MIN;
+    c.ring_count[0] = c.ring_count[1] = 0;
+    c.ring_count[2] = 0;
+    c.ges_counts[0] = c.ges_counts[1] = c.ges_counts[2] = c.ges_counts[3] = 0;
+    *c.barrier = 0;
+    for (int k = 0; k < 16; k++) c.stats[k] = 0;
+    c.stats[0] = n;
+  }
+  for (int q = i; q < 4000; q += gridDim.x * blockDim.x) c.phase_max[q] = 0ull;
+  const int stride = gridDim.x * blockDim.x;
+  for (int k = i; k < n; k += stride) {
+    const int x = c.cols[2 * k], y = c.cols[2 * k + 1];
+    bool was_new;
+    const int eslot = hashFindOrInsert(c.esdf, x, y, c.slice_out_bz, c.error, &was_new);
+    c.work[k] = make_int4(eslot, x, y, was_new ? 1 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(64) esdfMarkSliceKernel(EsdfCtx c) {
+  __shared__ int s_src[16], s_fs[16];
+  __shared__ int s_flags[3];
+  __shared__ MarkLocal ml;
+  const int tid = threadIdx.x;
+  if (tid == 0) markLocalInit(ml);
+  const int n = *c.work_count;
+  if (blockIdx.x == 0 && tid == 0 && c.tracker_todo_count) *c.tracker_todo_count = 0;
+  const int vx = tid >> 3, vy = tid & 7;
+  const int nb_col = c.slice_max_bz - c.slice_min_bz + 1;
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    const int4 w = c.work[item];
+    if (w.x >= 0 && w.w) linkNewBlock(c, w.x, tid);
+    if (tid < 3) s_flags[tid] = 0;
+    __syncthreads();
+    if (w.x < 0) continue;
+    bool observed = false;
+    float squashed = c.from_occupancy ? 0.0f : 2.0f * c.max_sq;  // :792-799
+    for (int b0 = 0; b0 < nb_col; b0 += 16) {
+      if (tid < 16 && b0 + tid < nb_col) {
+        s_src[tid] = hashFind(c.tsdf.hash, w.y, w.z, c.slice_min_bz + b0 + tid);
+        s_fs[tid] = c.use_freespace ? hashFind(c.freespace.hash, w.y, w.z, c.slice_min_bz + b0 + tid) : -1;
+      }
+      __syncthreads();
+      for (int q = 0; q < 16 && b0 + q < nb_col; q++) {
+        const int ss = s_src[q];
+        if (ss < 0) continue;
+        const int bz = c.slice_min_bz + b0 + q;
+        const int z0 = bz == c.slice_min_bz ? c.slice_min_vz : 0, z1 = bz == c.slice_max_bz ? c.slice_max_vz : kVps - 1;
+        const unsigned char* fb = s_fs[q] >= 0 ? c.freespace.blocks + (size_t)s_fs[q] * kFreespaceBlockBytes : nullptr;
+        for (int vz = z0; vz <= z1; vz++) {
+          const int v = (vx * kVps + vy) * kVps + vz;
+          const bool is_fs = fb ? fb[(size_t)v * kFreespaceVoxelBytes + 16] != 0 : false;
+          if (c.from_occupancy) {
+            const float lo = reinterpret_cast<const float*>(c.tsdf.blocks + (size_t)ss * kOccBlockBytes)[v];
+            if (fabsf(lo - 0.0f) > 1e-4f) {
+              observed = true;
+              if (!is_fs) squashed = fmaxf(squashed, lo);
+            }
+          } else {
+            const float2 t = reinterpret_cast<const float2*>(c.tsdf.blocks + (size_t)ss * kTsdfBlockBytes)[v];
+            if (t.y >= c.min_weight) {
+              observed = true;
+              if (!is_fs) squashed = fminf(squashed, t.x);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // updateEsdfVoxelToChanges (:401-458) on the slice voxel
+    unsigned int* e = esdfBlockPtr(c.esdf, w.x) + ((vx * kVps + vy) * kVps + c.slice_out_vz) * kEsdfVoxelWords;
+    float sq = __uint_as_float(e[0]);
+    int p0 = (int)e[1], p1 = (int)e[2], p2 = (int)e[3];
+    const unsigned int fl = e[4];
+    bool e_inside = flagInside(fl), e_observed = flagObserved(fl), e_site = flagSite(fl);
+    bool updated = false, cleared = false;
+    if (observed) {
+      const bool is_inside = c.from_occupancy ? (squashed > c.occupied_threshold_log_odds) : (squashed <= 0.0f);
+      const bool is_site = is_inside && (c.from_occupancy ? true : (fabsf(squashed) <= c.max_site_distance_m));
+      if (e_inside && !is_inside) {
+        p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+        cleared = true;
+      }
+      e_inside = is_inside;
+      if (is_site) {
+        if (!e_site) e_site = true, sq = 0.0f, p0 = p1 = p2 = 0;
+        updated = true;
+      } else {
+        if (e_site) {
+          p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+          cleared = true;
+        } else if (!e_observed) {
+          p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+        } else if ((double)sq <= 1e-4) {
+          p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+          cleared = true;
+        }
+      }
+      e_observed = true;
+    } else {
+      p0 = p1 = p2 = 0, sq = c.max_sq, e_site = false;
+      cleared = true;
+      e_observed = false;
+    }
+    const unsigned int nfl = (fl & 0xff000000u) | (e_inside ? 1u : 0u) | (e_observed ? 0x100u : 0u) | (e_site ? 0x10000u : 0u);
+    const unsigned int nsq = __float_as_uint(sq);
+    if (nsq != e[0] || (unsigned)p0 != e[1] || (unsigned)p1 != e[2] || (unsigned)p2 != e[3] || nfl != fl)
+      e[0] = nsq, e[1] = (unsigned)p0, e[2] = (unsigned)p1, e[3] = (unsigned)p2, e[4] = nfl;
+    if (updated) s_flags[0] = 1;
+    if (cleared) s_flags[1] = 1;
+    __syncthreads();
+    if (tid == 0) markLocalRecord(c, ml, w.x, s_flags[0] != 0, s_flags[1] != 0);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    markLocalFlush(c, ml);
+    __threadfence();
+    if (atomicAdd(c.ring_count + 2, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      const int nclr = *(volatile int*)c.clr_count;
+      const int nupd = *(volatile int*)c.upd_count;
+      updatePersistentClearedList(c, nclr);
+      c.stats[1] = nupd, c.stats[2] = nclr;
+    }
+  }
+}
+
+void launchEsdfSliceAllocateAndMark(const EsdfCtx& c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
+                                    int in_count_upper, int num_sms, cudaStream_t stream) {
+  if (in_count_upper < 1) in_count_upper = 1;
+  cudaMemsetAsync(c.colset_keys, 0xFF, ((size_t)c.colset_mask + 1) * sizeof(unsigned long long), stream);
+  cudaMemsetAsync(c.cols_count, 0, sizeof(int), stream);
+  esdfSliceColumnsKernel<<<(in_count_upper + 255) / 256, 256, 0, stream>>>(c, in_xyz, in_slots, in_count_dev, in_count_upper);
+  esdfSliceAllocateKernel<<<(in_count_upper + 255) / 256, 256, 0, stream>>>(c);
+  int grid = num_sms * 16;
+  if (in_count_upper < grid) grid = in_count_upper;
+  esdfMarkSliceKernel<<<grid, 64, 0, stream>>>(c);
 }
 
 // Test hook: NVB_ESDF_GRID_CAP=<n> caps the grids of the mark and clear kernels so that small maps exercise their

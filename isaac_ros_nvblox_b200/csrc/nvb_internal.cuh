@@ -348,6 +348,13 @@ struct EsdfCtx {
   int* nbr27;         // 27 ints per ESDF slot: slot of the block at offset (dx,dy,dz), entry (dx+1)*9+(dy+1)*3+(dz+1);
                       // -1 none, < -1 unknown (never linked)
   unsigned char* shadow;  // second ESDF slab (same slot indexing): results of a ring wait here until all reads are done
+  int slice_mode;  // the ESDF layer is a 2-D slice (EsdfMode::k2D)
+  // constant-z slice (2-D ESDF): block / voxel z of the band's bottom and top and of the output layer
+  int slice_min_bz, slice_min_vz, slice_max_bz, slice_max_vz, slice_out_bz, slice_out_vz;
+  unsigned long long* colset_keys;  // set of (x, y) columns of this slice update (open addressing, keys only)
+  unsigned int colset_mask;
+  int* cols;                // unique columns: x, y pairs
+  int* cols_count;
   int* dead_cleared_xyz;    // indices of deallocated blocks that were on the persistent cleared list (3 ints each) ...
   int* dead_cleared_count;  // ... they rejoin it if a block with that index is allocated again while the list persists
   int* cand_a;        // candidate lists of the gather-emulate-sweep rings (ping-pong by ring parity)
@@ -374,6 +381,8 @@ struct EsdfCtx {
   int from_occupancy;               // the projective layer (`tsdf` above) holds OccupancyVoxels
   float occupied_threshold_log_odds;
 };
+void launchEsdfSliceAllocateAndMark(const EsdfCtx& c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
+                                    int in_count_upper, int num_sms, cudaStream_t stream);
 void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
                         int in_count_upper, cudaStream_t stream);
 void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream);

@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (NvbCamera, NvbDecayExclusion, NvbEsdfParams, NvbFreespaceParams, NvbMapperOptions, NvbOccupancyDecayParams,
+from ._lib import (NvbCamera, NvbDecayExclusion, NvbEsdfParams, NvbEsdfSliceParams, NvbFreespaceParams, NvbMapperOptions, NvbOccupancyDecayParams,
                    NvbOccupancyParams, NvbTsdfDecayParams, NvbTsdfParams, check)
 
 TSDF_VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4")])
@@ -310,6 +310,21 @@ class _EsdfIntegrator:
     def occupied_threshold(self, v=None):
         return self.params(**({} if v is None else {"occupied_threshold": float(v)})).occupied_threshold
 
+    def slice_params(self, **kw):
+        """esdf_slice_min_height / esdf_slice_max_height / esdf_slice_height (esdf_integrator.h:216-256)."""
+        p = NvbEsdfSliceParams()
+        check(self._m._L.nvb_mapper_get_esdf_slice_params(self._m._h, C.byref(p)))
+        for k, v in kw.items():
+            setattr(p, k, float(v))
+        if kw:
+            check(self._m._L.nvb_mapper_set_esdf_slice_params(self._m._h, C.byref(p)))
+        return p
+
+    def integrate_slice(self, block_indices):
+        """EsdfIntegrator::integrateSlice(layer, block_indices, esdf_layer) with the constant-z slice."""
+        idx = np.ascontiguousarray(block_indices, dtype=np.int32).reshape(-1, 3)
+        check(self._m._L.nvb_esdf_integrate_slice_blocks(self._m._h, _ip(idx), idx.shape[0]))
+
     def integrate_blocks(self, block_indices):
         """EsdfIntegrator::integrateBlocks(tsdf_layer | occupancy_layer, block_indices, esdf_layer)."""
         idx = np.ascontiguousarray(block_indices, dtype=np.int32).reshape(-1, 3)
@@ -527,6 +542,10 @@ class Mapper:
             self._keep.clear()
         else:
             check(self._L.nvb_mapper_update_esdf_async(self._h, 1 if update_full_layer else 0))
+
+    def update_esdf_slice(self, update_full_layer=False):
+        """Mapper::updateEsdfSlice (mapper.h:331-343): the 2-D ESDF on the slice layer."""
+        check(self._L.nvb_mapper_update_esdf_slice(self._h, 1 if update_full_layer else 0))
 
     def synchronize(self):
         check(self._L.nvb_mapper_synchronize(self._h))

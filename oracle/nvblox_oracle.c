@@ -477,6 +477,7 @@ struct OrMap {
   float voxel_size, block_size;
   Layer tsdf, esdf, occ, freespace;
   int64_t freespace_last_update_time_ms; /* FreespaceIntegrator::last_update_time_ms_ (freespace_integrator.h:171) */
+  float slice_min_z, slice_max_z, slice_out_z; /* heights of the last or_esdf_integrate_slice call (for the 2-D clear) */
   /* EsdfIntegrator::cleared_block_indices_device_ (integrators/esdf_integrator.h:389)
    * is a member that is only overwritten when a call has blocks to clear
    * (esdf_integrator.cu:242-257), so its content carries over between calls. */
@@ -1266,6 +1267,7 @@ static void block_and_voxel_from_1d(float block_size, float p, int* block_idx, i
 void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
                              int32_t num_blocks, const OrEsdfParams* P, float z_min_m, float z_max_m, float z_output_m) {
   memset(map->stats, 0, sizeof(map->stats));
+  map->slice_min_z = z_min_m, map->slice_max_z = z_max_m, map->slice_out_z = z_output_m;
   if (num_blocks == 0) return;
   const float max_esdf_distance_vox = P->max_esdf_distance_m / map->voxel_size;
   const float max_sq = max_esdf_distance_vox * max_esdf_distance_vox;
@@ -1526,7 +1528,27 @@ static int32_t decay_layer(OrMap* map, int occupancy, const void* params, const 
       if (selected[s] && fully[s]) list_push(&rm, L->index[s]);
     n_removed = copy_out(&rm, out_xyz, cap);
     layer_remove_blocks(L, rm.v, rm.n);
-    if (clear_esdf) layer_remove_blocks(&map->esdf, rm.v, rm.n), layer_remove_blocks(&map->freespace, rm.v, rm.n);
+    if (clear_esdf == 1) layer_remove_blocks(&map->esdf, rm.v, rm.n);
+    if (clear_esdf) layer_remove_blocks(&map->freespace, rm.v, rm.n);
+    if (clear_esdf == 2) {
+      /* 2-D ESDF (src/mapper/mapper.cpp:569-626): a column's slice block goes when no projective block is left in the
+       * vertical column within the slice bounds (the projective blocks were removed above) */
+      List er = {0};
+      const int min_bz = f2i(floorf(map->slice_min_z / map->block_size)), max_bz = f2i(floorf(map->slice_max_z / map->block_size)),
+                out_bz = f2i(floorf(map->slice_out_z / map->block_size));
+      for (int32_t i = 0; i < rm.n; i++) {
+        const i3 ek = {rm.v[i].x, rm.v[i].y, out_bz};
+        if (hash_find(&map->esdf.hash, ek) < 0) continue;
+        int has = 0;
+        for (int bz = min_bz; bz <= max_bz && !has; bz++) {
+          const i3 pk = {rm.v[i].x, rm.v[i].y, bz};
+          has = hash_find(&L->hash, pk) >= 0;
+        }
+        if (!has) list_push(&er, ek);
+      }
+      layer_remove_blocks(&map->esdf, er.v, er.n);
+      list_free(&er);
+    }
     list_free(&rm);
   }
   free(fully), free(selected);

@@ -194,8 +194,9 @@ typedef struct {
 void or_default_tsdf_decay_params(OrTsdfDecayParams* p);
 void or_default_occupancy_decay_params(OrOccupancyDecayParams* p);
 /* VoxelDecayer::decay (integrators/internal/cuda/impl/decayer_impl.cuh:150-262). depth == NULL: every voxel decays;
- * otherwise voxels with a depth measurement in that view are spared (DepthObservationSpace). clear_esdf: also remove
- * the deallocated blocks from the ESDF layer, like Mapper::decayTsdfInternal does. Returns the number of deallocated
+ * otherwise voxels with a depth measurement in that view are spared (DepthObservationSpace). clear_esdf: 1 = also remove
+ * the deallocated blocks from the (3-D) ESDF and the freespace layer, like Mapper::decayTsdfInternal does; 2 = the ESDF is
+ * a 2-D slice (heights of the last or_esdf_integrate_slice call): a slice block goes when its column is empty. Returns the number of deallocated
  * blocks, writes up to cap triples. `exclusion` may be NULL. */
 int32_t or_tsdf_decay(OrMap* map, const OrTsdfDecayParams* params, const OrDecayExclusion* exclusion, const float* depth,
                       int32_t rows, int32_t cols, const float* T_L_C, const OrCamera* cam, float max_view_distance_m,

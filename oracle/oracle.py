@@ -378,10 +378,9 @@ class OracleMap:
             depth = np.ascontiguousarray(depth, dtype=np.float32)
             T = colmajor(T_L_C)
             n = fn(self._h, C.byref(params), C.byref(x), _fp(depth), depth.shape[0], depth.shape[1], _fp(T), C.byref(cam),
-                   float(max_view_distance_m), float(truncation_distance_m), 1 if clear_esdf else 0, _ip(out), cap)
+                   float(max_view_distance_m), float(truncation_distance_m), int(clear_esdf), _ip(out), cap)
         else:
-            n = fn(self._h, C.byref(params), C.byref(x), None, 0, 0, None, None, 0.0, 0.0, 1 if clear_esdf else 0,
-                   _ip(out), cap)
+            n = fn(self._h, C.byref(params), C.byref(x), None, 0, 0, None, None, 0.0, 0.0, int(clear_esdf), _ip(out), cap)
         assert n <= cap
         return out[:n].copy()
 

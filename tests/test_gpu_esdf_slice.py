@@ -1,0 +1,91 @@
+"""Parity of the 2-D ESDF (EsdfIntegrator::integrateSlice with the constant-z slice, Mapper::updateEsdfSlice) with the
+CPU oracle, through the C-ABI. All five EsdfVoxel fields exact, block sets equal."""
+import numpy as np
+import pytest
+
+from helpers import assert_esdf_equal, cameras
+from isaac_ros_nvblox_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _nvb():
+    import isaac_ros_nvblox_b200 as nvb
+    return nvb
+
+
+def _orc():
+    from oracle import oracle as orc
+    return orc
+
+
+@pytest.mark.parametrize("mode", ["tsdf", "occupancy", "tsdf_freespace"])
+def test_esdf_slice_incremental_sequence(gpu, mode):
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    frames = [(d, T) for d, T, _ in syn.moving_sphere_sequence(cs, syn.circle_trajectory(40)[:7], step_m=0.25)]
+    ltype = {"tsdf": nvb.ProjectiveLayerType.kTsdf, "occupancy": nvb.ProjectiveLayerType.kOccupancy,
+             "tsdf_freespace": nvb.ProjectiveLayerType.kTsdfWithFreespace}[mode]
+    m, o = nvb.Mapper(0.05, projective_layer_type=ltype), orc.OracleMap(0.05)
+    z = dict(slice_min_height_m=0.25, slice_max_height_m=1.45, slice_height_m=0.9)
+    m.esdf_integrator().slice_params(**z)
+    tp = orc.default_tsdf_params()
+    fkw = dict(min_duration_since_occupied_for_freespace_ms=200)
+    if mode == "tsdf_freespace":
+        m.freespace_integrator().params(**fkw)
+    for i, (d, T) in enumerate(frames):
+        b = m.integrate_depth(d, T, cam)
+        if mode == "occupancy":
+            o.integrate_occupancy(d, T, ocam, tp)
+        else:
+            o.integrate_depth(d, T, ocam)
+        if mode == "tsdf_freespace":
+            m.update_freespace(1000 + 100 * i)
+            o.update_freespace(o.tsdf_block_indices() if i == 0 else b, 1000 + 100 * i, orc.default_freespace_params(**fkw))
+        m.update_esdf_slice()
+        blocks = b if i > 0 else (o.occupancy_block_indices() if mode == "occupancy" else o.tsdf_block_indices())
+        o.integrate_esdf_slice(blocks, z_min_m=0.25, z_max_m=1.45, z_output_m=0.9, from_occupancy=(mode == "occupancy"),
+                               use_freespace=(mode == "tsdf_freespace"))
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    s_gpu, s_cpu = m.esdf_integrator().last_stats(), o.esdf_stats()
+    for k in ("marked", "with_sites", "to_clear", "cleared"):
+        assert s_gpu[k] == s_cpu[k], (k, s_gpu, s_cpu)
+    layer = m.esdf_layer().as_dict()
+    assert len(layer) > 100 and len({k[2] for k in layer}) == 1  # one z layer of blocks
+    assert sum(int(v["is_site"].sum()) for v in layer.values()) > 100
+    m.close()
+
+
+def test_esdf_slice_explicit_lists_mode_check_and_decay(gpu):
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:4])
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    for d, T in frames[:3]:
+        b = m.integrate_depth(d, T, cam)
+        o.integrate_depth(d, T, ocam)
+        lst = np.vstack([b, b[:5]])
+        m.esdf_integrator().integrate_slice(lst)  # defaults: band 0..1 m, output at 1 m
+        o.integrate_esdf_slice(lst)
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    with pytest.raises(Exception):
+        m.update_esdf()  # the ESDF layer is 2-D now (EsdfMode)
+    # decay: a slice block disappears only when its whole column is gone
+    dp = orc.default_tsdf_decay_params(decay_factor=0.05)
+    m.tsdf_decay_integrator().params(decay_factor=0.05)
+    d, T = frames[2]
+    for _ in range(4):
+        r_gpu = m.decay(depth=d, T_L_C=T, camera=cam)
+        r_cpu = o.decay_tsdf(dp, depth=d, T_L_C=T, cam=ocam, max_view_distance_m=7.0, truncation_distance_m=0.2, clear_esdf=2)
+        assert set(map(tuple, r_gpu.tolist())) == set(map(tuple, r_cpu.tolist()))
+        assert set(m.esdf_layer().as_dict()) == set(o.esdf_layer())
+    d, T = frames[3]
+    m.integrate_depth(d, T, cam)
+    o.integrate_depth(d, T, ocam)
+    m.update_esdf_slice()  # tracker reset by the decay: all blocks
+    o.integrate_esdf_slice(o.tsdf_block_indices())
+    assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    m.clear()
+    m.integrate_depth(d, T, cam)
+    m.update_esdf()  # after clear() the mode is unset again
+    m.close()
