@@ -20,6 +20,7 @@ namespace nvblox {
 
 enum class UpdateFullLayer { kNo, kYes };
 enum class ProjectiveLayerType { kTsdf, kOccupancy, kTsdfWithFreespace, kNone };
+enum class EsdfMode { k3D, k2D, kUnset };
 
 namespace b200_detail {
 // integrateFrame(depth_frame, T_L_C, camera, layer, updated_blocks) of either projective integrator.
@@ -177,6 +178,20 @@ class EsdfIntegrator {
   void max_site_distance_vox(float v) { auto p = get(); p.max_site_distance_vox = v; set(p); }
   float min_weight() const { return get().min_weight; }
   void min_weight(float v) { auto p = get(); p.min_weight = v; set(p); }
+  // the constant-z slice of the 2-D ESDF (esdf_integrator.h:216-256)
+  float esdf_slice_min_height() const { return getSlice().slice_min_height_m; }
+  void esdf_slice_min_height(float v) { auto p = getSlice(); p.slice_min_height_m = v; setSlice(p); }
+  float esdf_slice_max_height() const { return getSlice().slice_max_height_m; }
+  void esdf_slice_max_height(float v) { auto p = getSlice(); p.slice_max_height_m = v; setSlice(p); }
+  float esdf_slice_height() const { return getSlice().slice_height_m; }
+  void esdf_slice_height(float v) { auto p = getSlice(); p.slice_height_m = v; setSlice(p); }
+  // integrateSlice(layer, block_indices, esdf_layer) (esdf_integrator.h:96-118)
+  template <typename LayerT>
+  void integrateSlice(const LayerT&, const std::vector<Index3D>& block_indices, EsdfLayer*) {
+    std::vector<int32_t> raw(block_indices.size() * 3 + 3);
+    for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
+    b200_detail::check(nvb_esdf_integrate_slice_blocks(m_, raw.data(), (int32_t)block_indices.size()), "integrateSlice", nvb_last_error());
+  }
   float occupied_threshold() const { return get().occupied_threshold; }
   void occupied_threshold(float v) { auto p = get(); p.occupied_threshold = v; set(p); }
   // integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
@@ -192,6 +207,8 @@ class EsdfIntegrator {
     for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
     b200_detail::check(nvb_esdf_integrate_blocks(m_, raw.data(), (int32_t)block_indices.size()), "integrateBlocks", nvb_last_error());
   }
+  NvbEsdfSliceParams getSlice() const { NvbEsdfSliceParams p; b200_detail::check(nvb_mapper_get_esdf_slice_params(m_, &p), "esdf slice params", nvb_last_error()); return p; }
+  void setSlice(const NvbEsdfSliceParams& p) { b200_detail::check(nvb_mapper_set_esdf_slice_params(m_, &p), "esdf slice params", nvb_last_error()); }
   NvbEsdfParams get() const { NvbEsdfParams p; b200_detail::check(nvb_mapper_get_esdf_params(m_, &p), "esdf params", nvb_last_error()); return p; }
   void set(const NvbEsdfParams& p) { b200_detail::check(nvb_mapper_set_esdf_params(m_, &p), "esdf params", nvb_last_error()); }
   NvbMapper* m_;
@@ -225,6 +242,10 @@ class Mapper {
   }
   void updateEsdf(UpdateFullLayer full = UpdateFullLayer::kNo) {
     b200_detail::check(nvb_mapper_update_esdf(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdf", nvb_last_error());
+  }
+  // Mapper::updateEsdfSlice (mapper.h:343): the 2-D ESDF on the slice layer
+  void updateEsdfSlice(UpdateFullLayer full = UpdateFullLayer::kNo) {
+    b200_detail::check(nvb_mapper_update_esdf_slice(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdfSlice", nvb_last_error());
   }
   void clear() { b200_detail::check(nvb_mapper_clear(m_), "clear", nvb_last_error()); }
   // Mapper::updateFreespace(update_time_ms, T_L_C, camera, depth_frame, update_full_layer) (mapper.h:196-214)
