@@ -340,6 +340,17 @@ NVB_API int32_t nvb_mapper_update_esdf_slice(NvbMapper* m, int32_t update_full_l
 /* EsdfIntegrator::integrateSlice(layer, block_indices, esdf_layer) on an explicit block list (esdf_integrator.h:96-118). */
 NVB_API int32_t nvb_esdf_integrate_slice_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks);
 
+/* EsdfSlicer::sliceLayerToDistanceImage (C/include/nvblox/integrators/esdf_slicer.h:52-78, C/src/integrators/esdf_slicer.cu:
+ * 25-67,112-215) and, if grid_host != NULL, EsdfSlicer::occupancyGridFromSliceImage (:78-110,254-300) of the ESDF layer
+ * (3-D or 2-D) at slice_height_m: one pixel per voxel over the AABB of the ESDF blocks at that height, rows along y,
+ * columns along x; value = distance in metres (negative inside), `unobserved_value` where nothing is known; grid = 100
+ * occupied (distance < 0.01), 0 free, -1 unknown. Writes the AABB (min xyz, max xyz), the image size, and up to
+ * cap_pixels pixels into the host buffers (either may be NULL to query the size). rows = cols = 0 if the layer has no
+ * block at that height. */
+NVB_API int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float unobserved_value,
+                                              float aabb_out[6], float* image_host, int8_t* grid_host, int32_t cap_pixels,
+                                              int32_t* rows_out, int32_t* cols_out);
+
 /* EsdfIntegrator::integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
  * (esdf_integrator.h:56-58, src/integrators/esdf_integrator.cu:220-266) on an
  * explicit block list; does not consult or reset the tracker. */

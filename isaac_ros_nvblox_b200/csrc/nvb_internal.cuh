@@ -459,6 +459,11 @@ void launchScatterBlocks(const DevLayer& layer, const int* xyz_dev, int n, const
                          cudaStream_t stream);
 void launchFillU64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t stream);
 void launchRehash(const DevLayer& layer, int count, cudaStream_t stream);
+// EsdfSlicer (integrators/esdf_slicer.h): AABB of the ESDF blocks at block height zb (min x, min y, max x, max y; int[4]
+// preset to INT_MAX / INT_MIN), and the distance image / occupancy grid over an AABB.
+void launchSliceAabb(const DevLayer& esdf, int zb, int* out4, cudaStream_t stream);
+void launchSliceImage(const DevLayer& esdf, float block_size, float min_x, float min_y, float slice_height, float unobserved_value,
+                      int rows, int cols, float* image, signed char* grid, cudaStream_t stream);
 void launchRemoveBlocks(const DevLayer& layer, const int4* dead, const int* dead_count, int upper, cudaStream_t stream);
 void launchTodoAll(const DevLayer& tsdf, int* dirty, int* todo_slots, int* todo_count, cudaStream_t stream);
 

@@ -113,7 +113,65 @@ __global__ void removeBlocksKernel(DevLayer L, const int4* dead, const int* dead
   }
 }
 
+// EsdfSlicer::getAabbOfLayerAtHeight (src/integrators/esdf_slicer.cu:112-135): extreme x / y block indices at height zb.
+__global__ void sliceAabbKernel(DevLayer L, int zb, int* out4) {
+  const int n = *L.count < L.capacity ? *L.count : L.capacity;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const int x = L.block_index[3 * s];
+    if (x == kDeadSlotX || L.block_index[3 * s + 2] != zb) continue;
+    const int y = L.block_index[3 * s + 1];
+    atomicMin(out4 + 0, x), atomicMin(out4 + 1, y), atomicMax(out4 + 2, x), atomicMax(out4 + 3, y);
+  }
+}
+
+// populateSliceFromLayerKernel (:25-67) + occupancyGridFromSliceImageKernel (:78-110), one thread per pixel.
+__global__ void sliceImageKernel(DevLayer L, float block_size, float min_x, float min_y, float slice_height,
+                                 float unobserved_value, int rows, int cols, float* image, signed char* grid) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y * blockDim.y + threadIdx.y;
+  if (col >= cols || row >= rows) return;
+  const float voxel_size = block_size / (float)kVps;
+  const float p[3] = {min_x + voxel_size / 2.0f + voxel_size * (float)col, min_y + voxel_size / 2.0f + voxel_size * (float)row,
+                      slice_height};
+  // getBlockAndVoxelIndexFromPositionInLayer (core/internal/impl/indexing_impl.h:37-49)
+  const float inv = (float)(1.0 / (double)(block_size * (1.0f / kVps)));
+  int b[3], v[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    b[a] = floatToIntRz(floorf(p[a] / block_size));
+    v[a] = floatToIntRz((p[a] - block_size * (float)b[a]) * inv);
+    if (v[a] > kVps - 1) v[a] = kVps - 1;
+  }
+  float d = unobserved_value;
+  const int slot = hashFind(L.hash, b[0], b[1], b[2]);
+  if (slot >= 0) {
+    const unsigned int* e = reinterpret_cast<const unsigned int*>(L.blocks + (size_t)slot * kEsdfBlockBytes) +
+                            ((v[0] * kVps + v[1]) * kVps + v[2]) * kEsdfVoxelWords;
+    if ((e[4] & 0xff00u) != 0) {  // observed
+      d = voxel_size * sqrtf(__uint_as_float(e[0]));
+      if ((e[4] & 0xffu) != 0) d = -d;  // is_inside
+    }
+  }
+  const size_t pix = (size_t)row * cols + col;
+  if (image) image[pix] = d;
+  if (grid) {
+    signed char g = (signed char)((d < 1e-2f) * 100);
+    if (fabsf(d - unobserved_value) < 1e-2f) g = -1;
+    grid[pix] = g;
+  }
+}
+
 }  // namespace
+
+void launchSliceAabb(const DevLayer& esdf, int zb, int* out4, cudaStream_t stream) {
+  sliceAabbKernel<<<296, 256, 0, stream>>>(esdf, zb, out4);
+}
+void launchSliceImage(const DevLayer& esdf, float block_size, float min_x, float min_y, float slice_height, float unobserved_value,
+                      int rows, int cols, float* image, signed char* grid, cudaStream_t stream) {
+  const dim3 threads(16, 16);
+  const dim3 blocks((cols + 15) / 16, (rows + 15) / 16);
+  sliceImageKernel<<<blocks, threads, 0, stream>>>(esdf, block_size, min_x, min_y, slice_height, unobserved_value, rows, cols,
+                                                   image, grid);
+}
 
 void launchRemoveBlocks(const DevLayer& layer, const int4* dead, const int* dead_count, int upper, cudaStream_t stream) {
   int grid = upper < 1184 ? (upper < 1 ? 1 : upper) : 1184;

@@ -337,6 +337,29 @@ class _EsdfIntegrator:
         return dict(zip(keys, list(out)))
 
 
+class EsdfSlicer:
+    """EsdfSlicer (integrators/esdf_slicer.h:36-138): distance-map image and occupancy grid of an ESDF slice."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def slice_layer_to_distance_image(self, slice_height, unobserved_value=1000.0, with_occupancy_grid=False):
+        """-> (aabb [min xyz, max xyz], (rows, cols) float32 image[, int8 grid]); rows follow y, columns x."""
+        L, h = self._m._L, self._m._h
+        aabb = np.zeros(6, np.float32)
+        r, c = C.c_int32(0), C.c_int32(0)
+        check(L.nvb_esdf_slice_distance_image(h, float(slice_height), float(unobserved_value), _fp(aabb), None, None, 0,
+                                              C.byref(r), C.byref(c)))
+        img = np.zeros((max(r.value, 1), max(c.value, 1)), np.float32)
+        grid = np.zeros((max(r.value, 1), max(c.value, 1)), np.int8)
+        if r.value * c.value > 0:
+            check(L.nvb_esdf_slice_distance_image(h, float(slice_height), float(unobserved_value), _fp(aabb), _fp(img),
+                                                  grid.ctypes.data_as(C.POINTER(C.c_int8)) if with_occupancy_grid else None,
+                                                  r.value * c.value, C.byref(r), C.byref(c)))
+        img = img[:r.value, :c.value]
+        return (aabb, img, grid[:r.value, :c.value]) if with_occupancy_grid else (aabb, img)
+
+
 class Mapper:
     """nvblox::Mapper(voxel_size_m, projective_layer_type) with a projective (TSDF or occupancy) and an ESDF layer."""
 

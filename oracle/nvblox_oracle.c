@@ -1353,6 +1353,68 @@ void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_fre
   list_free(&blocks), list_free(&updated), list_free(&to_clear);
 }
 
+/* EsdfSlicer::sliceLayerToDistanceImage (src/integrators/esdf_slicer.cu:128-215) + populateSliceFromLayerKernel (:25-67) +
+ * occupancyGridFromSliceImageKernel (:78-110). Returns rows * cols (0 if the layer has no block at that height); writes the
+ * AABB (min xyz, max xyz), and up to cap pixels of the image / grid (either may be NULL). */
+int32_t or_esdf_slice_image(const OrMap* map, float slice_height, float unobserved_value, float aabb_out[6],
+                            float* image_out, int8_t* grid_out, int32_t cap, int32_t* rows_out, int32_t* cols_out) {
+  const float bs = map->block_size;
+  const int zb = f2i(floorf(slice_height / bs));
+  int have = 0;
+  int32_t mnx = 0, mny = 0, mxx = 0, mxy = 0;
+  for (int32_t s = 0; s < map->esdf.n; s++) { /* getAabbOfLayerAtHeight (:112-135) */
+    const i3 k = map->esdf.index[s];
+    if (k.z != zb) continue;
+    if (!have) mnx = mxx = k.x, mny = mxy = k.y, have = 1;
+    if (k.x < mnx) mnx = k.x;
+    if (k.x > mxx) mxx = k.x;
+    if (k.y < mny) mny = k.y;
+    if (k.y > mxy) mxy = k.y;
+  }
+  *rows_out = *cols_out = 0;
+  if (!have) return 0;
+  /* getAABBOfBlock: [index * block_size, (index + 1) * block_size] */
+  const float amin[3] = {(float)mnx * bs, (float)mny * bs, (float)zb * bs};
+  const float amax[3] = {((float)mxx + 1.0f) * bs, ((float)mxy + 1.0f) * bs, ((float)zb + 1.0f) * bs};
+  for (int a = 0; a < 3; a++) aabb_out[a] = amin[a], aabb_out[3 + a] = amax[a];
+  const float voxel_size = bs / (float)VPS;
+  const int cols = f2i(ceilf((amax[0] - amin[0]) / voxel_size)), rows = f2i(ceilf((amax[1] - amin[1]) / voxel_size));
+  *rows_out = rows, *cols_out = cols;
+  const float inv = (float)(1.0 / (double)(bs * (1.0f / VPS)));
+  for (int r = 0; r < rows; r++)
+    for (int cidx = 0; cidx < cols; cidx++) {
+      const size_t pix = (size_t)r * cols + cidx;
+      if ((int64_t)pix >= cap) continue;
+      const float p[3] = {amin[0] + voxel_size / 2.0f + voxel_size * (float)cidx, amin[1] + voxel_size / 2.0f + voxel_size * (float)r,
+                          slice_height};
+      i3 b;
+      int v[3];
+      int bb[3];
+      for (int a = 0; a < 3; a++) { /* getBlockAndVoxelIndexFromPositionInLayer (indexing_impl.h:37-49) */
+        bb[a] = f2i(floorf(p[a] / bs));
+        v[a] = f2i((p[a] - bs * (float)bb[a]) * inv);
+        if (v[a] > VPS - 1) v[a] = VPS - 1;
+      }
+      b.x = bb[0], b.y = bb[1], b.z = bb[2];
+      float d = unobserved_value;
+      const int32_t sl = hash_find(&map->esdf.hash, b);
+      if (sl >= 0) {
+        const OrEsdfVoxel* e = (const OrEsdfVoxel*)layer_block(&map->esdf, sl) + (v[0] * VPS + v[1]) * VPS + v[2];
+        if (e->observed) {
+          d = voxel_size * sqrtf(e->squared_distance_vox);
+          if (e->is_inside) d = -d;
+        }
+      }
+      if (image_out) image_out[pix] = d;
+      if (grid_out) {
+        int8_t g = (int8_t)((d < 1e-2f) * 100);
+        if (fabsf(d - unobserved_value) < 1e-2f) g = -1;
+        grid_out[pix] = g;
+      }
+    }
+  return rows * cols;
+}
+
 void or_esdf_last_stats(const OrMap* map, int64_t out[8]) { memcpy(out, map->stats, sizeof(map->stats)); }
 
 /* ------------------------------------------------------------------------- */

@@ -231,6 +231,12 @@ void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_fre
                              int32_t num_blocks, const OrEsdfParams* params, float z_min_m, float z_max_m,
                              float z_output_m);
 
+/* EsdfSlicer::sliceLayerToDistanceImage + occupancyGridFromSliceImage (integrators/esdf_slicer.h:52-118): the distance map
+ * (m, negative inside, `unobserved_value` where nothing is known) of the ESDF layer at `slice_height`, one pixel per voxel
+ * over the AABB of the blocks at that height (aabb_out = min xyz, max xyz); rows follow y, columns x. */
+int32_t or_esdf_slice_image(const OrMap* map, float slice_height, float unobserved_value, float aabb_out[6],
+                            float* image_out, int8_t* grid_out, int32_t cap, int32_t* rows_out, int32_t* cols_out);
+
 /* Statistics of the last or_esdf_integrate call: [0] blocks marked, [1] blocks
  * with sites, [2] blocks to clear, [3] candidate blocks scanned by the clear
  * pass, [4] blocks cleared, [5] total swept blocks, [6] total (block,direction)

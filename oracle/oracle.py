@@ -165,6 +165,8 @@ def lib():
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.restype = None
+    L.or_esdf_slice_image.argtypes = [vp, C.c_float, C.c_float, fp, fp, C.POINTER(C.c_int8), C.c_int32, ip, ip]
+    L.or_esdf_slice_image.restype = C.c_int32
     L.or_esdf_integrate_slice.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), C.c_float, C.c_float,
                                           C.c_float]
     L.or_esdf_integrate_slice.restype = None
@@ -440,6 +442,19 @@ class OracleMap:
         blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
         lib().or_esdf_integrate_slice(self._h, 1 if from_occupancy else 0, 1 if use_freespace else 0, _ip(blocks),
                                       blocks.shape[0], C.byref(params), float(z_min_m), float(z_max_m), float(z_output_m))
+
+    def esdf_slice_image(self, slice_height, unobserved_value=1000.0):
+        """EsdfSlicer::sliceLayerToDistanceImage + occupancyGridFromSliceImage -> (aabb(6), image (rows, cols), grid int8)."""
+        aabb = np.zeros(6, np.float32)
+        r, c = C.c_int32(0), C.c_int32(0)
+        n = lib().or_esdf_slice_image(self._h, float(slice_height), float(unobserved_value), _fp(aabb), None, None, 0,
+                                      C.byref(r), C.byref(c))
+        img = np.zeros((max(r.value, 1), max(c.value, 1)), np.float32)
+        grid = np.zeros((max(r.value, 1), max(c.value, 1)), np.int8)
+        if n > 0:
+            lib().or_esdf_slice_image(self._h, float(slice_height), float(unobserved_value), _fp(aabb), _fp(img),
+                                      grid.ctypes.data_as(C.POINTER(C.c_int8)), n, C.byref(r), C.byref(c))
+        return aabb, img[:r.value, :c.value], grid[:r.value, :c.value]
 
     def integrate_esdf_with_freespace(self, blocks, params=None):
         params = params or default_esdf_params()

@@ -89,3 +89,33 @@ def test_esdf_slice_explicit_lists_mode_check_and_decay(gpu):
     m.integrate_depth(d, T, cam)
     m.update_esdf()  # after clear() the mode is unset again
     m.close()
+
+
+@pytest.mark.parametrize("two_d", [False, True])
+def test_esdf_slicer_distance_image_and_occupancy_grid(gpu, two_d):
+    """EsdfSlicer::sliceLayerToDistanceImage / occupancyGridFromSliceImage of a 3-D ESDF and of a 2-D slice ESDF: AABB, image
+    size, every pixel and every grid cell equal to the oracle's."""
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:4])
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    for i, (d, T) in enumerate(frames):
+        b = m.integrate_depth(d, T, cam)
+        o.integrate_depth(d, T, ocam)
+        if two_d:
+            m.update_esdf_slice()
+            o.integrate_esdf_slice(b if i else o.tsdf_block_indices())
+        else:
+            m.update_esdf()
+            o.integrate_esdf(b if i else o.tsdf_block_indices())
+    for h in (1.0, 0.93, 2.2, 40.0):
+        aabb_g, img_g, grid_g = nvb.EsdfSlicer(m).slice_layer_to_distance_image(h, 1000.0, with_occupancy_grid=True)
+        aabb_c, img_c, grid_c = o.esdf_slice_image(h, 1000.0)
+        assert img_g.shape == img_c.shape
+        if img_c.size:
+            assert np.array_equal(aabb_g, aabb_c)
+            assert np.array_equal(img_g.view(np.uint32), img_c.view(np.uint32))
+            assert np.array_equal(grid_g, grid_c)
+    aabb, img = nvb.EsdfSlicer(m).slice_layer_to_distance_image(1.0)
+    assert img.size > 10000 and (img == 1000.0).any() and (np.abs(img) < 0.01).any() and (img[img != 1000.0] > 0.5).any()
+    m.close()

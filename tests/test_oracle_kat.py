@@ -1024,3 +1024,33 @@ def test_esdf_slice_squashes_a_band_and_updates_incrementally():
         if p.any():
             parent = world.get((c[0] + int(p[0]), c[1] + int(p[1])))
             assert parent is not None and parent["is_site"]
+
+
+def test_esdf_slicer_image_of_the_slice():
+    """EsdfSlicer (esdf_slicer.cu:25-215): one pixel per voxel over the AABB of the slice's blocks; 0 at sites, the ESDF
+    distance elsewhere, the unobserved value where nothing is known; the occupancy grid maps them to 100 / 0 / -1."""
+    voxel = 0.1
+    cs = syn.PinholeCamera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    cam = orc.Camera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(16)[:4])
+    m = orc.OracleMap(voxel)
+    for i, (d, T) in enumerate(frames):
+        b = m.integrate_depth(d, T, cam)
+        m.integrate_esdf_slice(b if i else m.tsdf_block_indices(), z_min_m=0.3, z_max_m=1.7, z_output_m=1.0)
+    aabb, img, grid = m.esdf_slice_image(1.0, 1000.0)
+    keys = np.array(list(m.esdf_layer()))
+    assert np.allclose(aabb[:2], keys[:, :2].min(0) * 0.8) and np.allclose(aabb[3:5], (keys[:, :2].max(0) + 1) * 0.8)
+    assert img.shape == (round((aabb[4] - aabb[1]) / voxel), round((aabb[3] - aabb[0]) / voxel))
+    world = _slice_world(m, 1, 1)
+    x0, y0 = round(aabb[0] / voxel), round(aabb[1] / voxel)
+    n = 0
+    for (gx, gy), v in world.items():
+        px = img[gy - y0, gx - x0]
+        exp = voxel * np.sqrt(np.float32(v["squared_distance_vox"]))
+        assert abs(abs(px) - exp) < 1e-6 and (px <= 0) == bool(v["is_inside"] or exp == 0)
+        assert grid[gy - y0, gx - x0] == (100 if px < 1e-2 else 0)
+        n += 1
+    assert n > 1000
+    unknown = img == 1000.0
+    assert unknown.any() and np.all(grid[unknown] == -1)
+    assert m.esdf_slice_image(40.0)[1].size == 0
