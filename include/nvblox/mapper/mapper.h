@@ -192,6 +192,10 @@ class EsdfIntegrator {
     for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
     b200_detail::check(nvb_esdf_integrate_slice_blocks(m_, raw.data(), (int32_t)block_indices.size()), "integrateSlice", nvb_last_error());
   }
+  float slice_height_above_plane_m() const { return getSlice().slice_height_above_plane_m; }
+  void slice_height_above_plane_m(float v) { auto p = getSlice(); p.slice_height_above_plane_m = v; setSlice(p); }
+  float slice_height_thickness_m() const { return getSlice().slice_height_thickness_m; }
+  void slice_height_thickness_m(float v) { auto p = getSlice(); p.slice_height_thickness_m = v; setSlice(p); }
   float occupied_threshold() const { return get().occupied_threshold; }
   void occupied_threshold(float v) { auto p = get(); p.occupied_threshold = v; set(p); }
   // integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)

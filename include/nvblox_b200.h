@@ -235,6 +235,9 @@ typedef struct NvbEsdfSliceParams {
   float slice_min_height_m; /* 0 */
   float slice_max_height_m; /* 1 */
   float slice_height_m;     /* 1: z of the output slice */
+  /* planar slices (slice_height_above_plane_m / slice_height_thickness_m, esdf_integrator_params.h:45-52) */
+  float slice_height_above_plane_m; /* 0   */
+  float slice_height_thickness_m;   /* 0.1 */
 } NvbEsdfSliceParams;
 NVB_API void nvb_default_esdf_slice_params(NvbEsdfSliceParams* p);
 NVB_API int32_t nvb_mapper_set_esdf_slice_params(NvbMapper* m, const NvbEsdfSliceParams* p);
@@ -337,6 +340,14 @@ NVB_API int32_t nvb_mapper_decay_exclude_last_view(NvbMapper* m, const NvbDecayE
  * layer is either 3-D or 2-D: mixing nvb_mapper_update_esdf and nvb_mapper_update_esdf_slice is an error, like the
  * reference's EsdfMode check. Synchronous. */
 NVB_API int32_t nvb_mapper_update_esdf_slice(NvbMapper* m, int32_t update_full_layer);
+/* The same with a PlanarSliceDescription (Mapper::updateEsdfSlice(..., ground_plane), mapper.h:343;
+ * EsdfIntegrator::integrateSlice(layer, blocks, ground_plane, esdf), esdf_integrator.h:120-150): the band starts
+ * slice_height_above_plane_m above the plane n . p + d = 0 and is slice_height_thickness_m thick, per voxel column
+ * (PlanarSliceColumnBoundsGetter). plane = {nx, ny, nz, d} = Plane::normal() (unit length) and Plane::offset(); a
+ * near-vertical plane (|nz| < 1e-4) falls back to z = 0 like checkForVerticalPlane. */
+NVB_API int32_t nvb_mapper_update_esdf_slice_planar(NvbMapper* m, const float plane[4], int32_t update_full_layer);
+NVB_API int32_t nvb_esdf_integrate_slice_planar_blocks(NvbMapper* m, const float plane[4], const int32_t* blocks_xyz_host,
+                                                       int32_t num_blocks);
 /* EsdfIntegrator::integrateSlice(layer, block_indices, esdf_layer) on an explicit block list (esdf_integrator.h:96-118). */
 NVB_API int32_t nvb_esdf_integrate_slice_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks);
 

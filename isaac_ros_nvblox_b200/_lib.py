@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "nvb_mapper_update_freespace", "nvb_freespace_update_blocks",
     "nvb_default_esdf_slice_params", "nvb_mapper_set_esdf_slice_params", "nvb_mapper_get_esdf_slice_params",
     "nvb_mapper_update_esdf_slice", "nvb_esdf_integrate_slice_blocks", "nvb_esdf_slice_distance_image",
+    "nvb_mapper_update_esdf_slice_planar", "nvb_esdf_integrate_slice_planar_blocks",
     "nvb_mapper_create", "nvb_mapper_destroy", "nvb_mapper_clear",
     "nvb_mapper_set_tsdf_params", "nvb_mapper_get_tsdf_params",
     "nvb_mapper_set_esdf_params", "nvb_mapper_get_esdf_params",
@@ -76,7 +77,8 @@ class NvbOccupancyParams(C.Structure):
 
 
 class NvbEsdfSliceParams(C.Structure):
-    _fields_ = [("slice_min_height_m", C.c_float), ("slice_max_height_m", C.c_float), ("slice_height_m", C.c_float)]
+    _fields_ = [("slice_min_height_m", C.c_float), ("slice_max_height_m", C.c_float), ("slice_height_m", C.c_float),
+                ("slice_height_above_plane_m", C.c_float), ("slice_height_thickness_m", C.c_float)]
 
 
 class NvbFreespaceParams(C.Structure):
@@ -157,6 +159,8 @@ def load():
     L.nvb_mapper_get_esdf_slice_params.argtypes = [vp, C.POINTER(NvbEsdfSliceParams)]
     L.nvb_mapper_update_esdf_slice.argtypes = [vp, i32]
     L.nvb_esdf_integrate_slice_blocks.argtypes = [vp, ip, i32]
+    L.nvb_mapper_update_esdf_slice_planar.argtypes = [vp, fp, i32]
+    L.nvb_esdf_integrate_slice_planar_blocks.argtypes = [vp, fp, ip, i32]
     L.nvb_esdf_slice_distance_image.argtypes = [vp, f32, f32, fp, fp, C.POINTER(C.c_int8), i32, ip, ip]
     L.nvb_default_freespace_params.argtypes = [C.POINTER(NvbFreespaceParams)]
     L.nvb_default_freespace_params.restype = None

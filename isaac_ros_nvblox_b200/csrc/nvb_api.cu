@@ -735,7 +735,8 @@ int readFrameList(NvbMapper* m, int32_t* out_xyz, int32_t cap, int32_t* out_coun
   return NVB_OK;
 }
 
-int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_tracker, bool slice = false) {
+int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_tracker, bool slice = false,
+                const float* plane = nullptr) {
   int rc;
   int upper;
   // EsdfMode: a mapper's ESDF layer is 3-D or a 2-D slice, never both (src/mapper/mapper.cpp:410-415,436-441)
@@ -781,6 +782,13 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
     split(m->sp.slice_max_height_m, &c.slice_max_bz, &c.slice_max_vz);
     split(m->sp.slice_height_m, &c.slice_out_bz, &c.slice_out_vz);
     if (c.slice_max_bz < c.slice_min_bz) return fail(NVB_ERR_INVALID_ARGUMENT, "slice_max_height below slice_min_height");
+    if (plane) {
+      c.slice_planar = 1;
+      c.plane_nx = plane[0], c.plane_ny = plane[1], c.plane_nz = plane[2], c.plane_d = plane[3];
+      if (std::fabs(c.plane_nz) < 1e-4f) c.plane_nx = 0.0f, c.plane_ny = 0.0f, c.plane_nz = 1.0f, c.plane_d = 0.0f;  // checkForVerticalPlane
+      c.slice_above_plane_m = m->sp.slice_height_above_plane_m;
+      c.slice_thickness_m = m->sp.slice_height_thickness_m;
+    }
   }
   int launches = 0;
   cudaError_t e;
@@ -1541,10 +1549,15 @@ void nvb_default_esdf_slice_params(NvbEsdfSliceParams* p) {
   p->slice_min_height_m = 0.0f;
   p->slice_max_height_m = 1.0f;
   p->slice_height_m = 1.0f;
+  p->slice_height_above_plane_m = 0.0f;
+  p->slice_height_thickness_m = 0.1f;
 }
 int32_t nvb_mapper_set_esdf_slice_params(NvbMapper* m, const NvbEsdfSliceParams* p) {
   if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
   if (!(p->slice_max_height_m >= p->slice_min_height_m)) return fail(NVB_ERR_INVALID_ARGUMENT, "slice_max_height below slice_min_height");
+  // CHECK_GE(slice_height_above_plane_m, 0) / CHECK_GT(slice_height_thickness_m, 0) (esdf_integrator.cu:928-929)
+  if (!(p->slice_height_above_plane_m >= 0.0f) || !(p->slice_height_thickness_m > 0.0f))
+    return fail(NVB_ERR_INVALID_ARGUMENT, "planar slice: height above plane must be >= 0 and thickness > 0");
   m->sp = *p;
   return NVB_OK;
 }
@@ -1554,7 +1567,13 @@ int32_t nvb_mapper_get_esdf_slice_params(const NvbMapper* m, NvbEsdfSliceParams*
   return NVB_OK;
 }
 
-int32_t nvb_mapper_update_esdf_slice(NvbMapper* m, int32_t update_full_layer) {
+static int32_t updateEsdfSliceImpl(NvbMapper* m, const float* plane, int32_t update_full_layer);
+int32_t nvb_mapper_update_esdf_slice(NvbMapper* m, int32_t update_full_layer) { return updateEsdfSliceImpl(m, nullptr, update_full_layer); }
+int32_t nvb_mapper_update_esdf_slice_planar(NvbMapper* m, const float plane[4], int32_t update_full_layer) {
+  if (!plane) return fail(NVB_ERR_INVALID_ARGUMENT, "null plane");
+  return updateEsdfSliceImpl(m, plane, update_full_layer);
+}
+static int32_t updateEsdfSliceImpl(NvbMapper* m, const float* plane, int32_t update_full_layer) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
   if (!m->tracker_initialized || update_full_layer) {
@@ -1562,12 +1581,21 @@ int32_t nvb_mapper_update_esdf_slice(NvbMapper* m, int32_t update_full_layer) {
     m->launches++;
     m->tracker_initialized = true;
   }
-  int rc = enqueueEsdf(m, nullptr, 0, true, true);
+  int rc = enqueueEsdf(m, nullptr, 0, true, true, plane);
   if (rc) return rc;
   return nvb_mapper_synchronize(m);
 }
 
+static int32_t integrateSliceBlocksImpl(NvbMapper* m, const float* plane, const int32_t* blocks_xyz_host, int32_t num_blocks);
 int32_t nvb_esdf_integrate_slice_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks) {
+  return integrateSliceBlocksImpl(m, nullptr, blocks_xyz_host, num_blocks);
+}
+int32_t nvb_esdf_integrate_slice_planar_blocks(NvbMapper* m, const float plane[4], const int32_t* blocks_xyz_host,
+                                               int32_t num_blocks) {
+  if (!plane) return fail(NVB_ERR_INVALID_ARGUMENT, "null plane");
+  return integrateSliceBlocksImpl(m, plane, blocks_xyz_host, num_blocks);
+}
+static int32_t integrateSliceBlocksImpl(NvbMapper* m, const float* plane, const int32_t* blocks_xyz_host, int32_t num_blocks) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   if (num_blocks < 0 || (num_blocks > 0 && !blocks_xyz_host)) return fail(NVB_ERR_INVALID_ARGUMENT, "bad block list");
   if (num_blocks == 0) return NVB_OK;  // early return (:289-291)
@@ -1583,7 +1611,7 @@ int32_t nvb_esdf_integrate_slice_blocks(NvbMapper* m, const int32_t* blocks_xyz_
   }
   NVB_CUDA(cudaMemcpyAsync(m->xyz_upload, blocks_xyz_host, (size_t)num_blocks * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
   NVB_CUDA(cudaStreamSynchronize(m->stream));
-  int rc = enqueueEsdf(m, m->xyz_upload, num_blocks, false, true);
+  int rc = enqueueEsdf(m, m->xyz_upload, num_blocks, false, true, plane);
   if (rc) return rc;
   return nvb_mapper_synchronize(m);
 }

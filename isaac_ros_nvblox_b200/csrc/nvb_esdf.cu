@@ -989,9 +989,18 @@ __global__ void esdfSliceAllocateKernel(EsdfCtx c) {
   }
 }
 
+// getBlockAndVoxelIndexFrom1DPositionInLayer (core/internal/impl/indexing_impl.h:105-115)
+__device__ __forceinline__ void blockAndVoxelFrom1D(float block_size, float p, int& b, int& v) {
+  const float inv = (float)(1.0 / (double)(block_size * (1.0f / kVps)));
+  b = floatToIntRz(floorf(p / block_size));
+  v = floatToIntRz((p - block_size * (float)b) * inv);
+  if (v > kVps - 1) v = kVps - 1;
+}
+
 __global__ void __launch_bounds__(64) esdfMarkSliceKernel(EsdfCtx c) {
   __shared__ int s_src[16], s_fs[16];
   __shared__ int s_flags[3];
+  __shared__ int s_range[2];  // block range of the CTA's columns (planar slices: the union over the 64 voxel columns)
   __shared__ MarkLocal ml;
   const int tid = threadIdx.x;
   if (tid == 0) markLocalInit(ml);
@@ -1007,17 +1016,38 @@ __global__ void __launch_bounds__(64) esdfMarkSliceKernel(EsdfCtx c) {
     if (w.x < 0) continue;
     bool observed = false;
     float squashed = c.from_occupancy ? 0.0f : 2.0f * c.max_sq;  // :792-799
-    for (int b0 = 0; b0 < nb_col; b0 += 16) {
-      if (tid < 16 && b0 + tid < nb_col) {
-        s_src[tid] = hashFind(c.tsdf.hash, w.y, w.z, c.slice_min_bz + b0 + tid);
-        s_fs[tid] = c.use_freespace ? hashFind(c.freespace.hash, w.y, w.z, c.slice_min_bz + b0 + tid) : -1;
+    // ColumnBounds of this thread's voxel column: the constant-z slice's, or from the ground plane
+    // (PlanarSliceColumnBoundsGetter::getColumnBounds, esdf_integrator_slicing_impl.cuh:100-130)
+    int min_bz = c.slice_min_bz, min_vz = c.slice_min_vz, max_bz = c.slice_max_bz, max_vz = c.slice_max_vz;
+    int first_bz = c.slice_min_bz, ncol = nb_col;
+    if (c.slice_planar) {
+      const float vs = c.block_size * (1.0f / kVps), half = c.block_size * (0.5f / kVps);
+      const float px = (c.block_size * (float)w.y + vs * (float)vx) + half;
+      const float py = (c.block_size * (float)w.z + vs * (float)vy) + half;
+      const float plane_h = -1.0f * (c.plane_nx * px + c.plane_ny * py + c.plane_d) / c.plane_nz;
+      const float lo_h = plane_h + c.slice_above_plane_m, hi_h = lo_h + c.slice_thickness_m;
+      blockAndVoxelFrom1D(c.block_size, lo_h, min_bz, min_vz);
+      blockAndVoxelFrom1D(c.block_size, hi_h, max_bz, max_vz);
+      if (tid == 0) s_range[0] = INT32_MAX, s_range[1] = INT32_MIN;
+      __syncthreads();
+      atomicMin(&s_range[0], min_bz), atomicMax(&s_range[1], max_bz);
+      __syncthreads();
+      first_bz = s_range[0];
+      ncol = s_range[1] - s_range[0] + 1;
+      __syncthreads();
+    }
+    for (int b0 = 0; b0 < ncol; b0 += 16) {
+      if (tid < 16 && b0 + tid < ncol) {
+        s_src[tid] = hashFind(c.tsdf.hash, w.y, w.z, first_bz + b0 + tid);
+        s_fs[tid] = c.use_freespace ? hashFind(c.freespace.hash, w.y, w.z, first_bz + b0 + tid) : -1;
       }
       __syncthreads();
-      for (int q = 0; q < 16 && b0 + q < nb_col; q++) {
+      for (int q = 0; q < 16 && b0 + q < ncol; q++) {
         const int ss = s_src[q];
         if (ss < 0) continue;
-        const int bz = c.slice_min_bz + b0 + q;
-        const int z0 = bz == c.slice_min_bz ? c.slice_min_vz : 0, z1 = bz == c.slice_max_bz ? c.slice_max_vz : kVps - 1;
+        const int bz = first_bz + b0 + q;
+        if (bz < min_bz || bz > max_bz) continue;  // isBlockIdxInRange
+        const int z0 = bz == min_bz ? min_vz : 0, z1 = bz == max_bz ? max_vz : kVps - 1;
         const unsigned char* fb = s_fs[q] >= 0 ? c.freespace.blocks + (size_t)s_fs[q] * kFreespaceBlockBytes : nullptr;
         for (int vz = z0; vz <= z1; vz++) {
           const int v = (vx * kVps + vy) * kVps + vz;

@@ -351,6 +351,9 @@ struct EsdfCtx {
   int slice_mode;  // the ESDF layer is a 2-D slice (EsdfMode::k2D)
   // constant-z slice (2-D ESDF): block / voxel z of the band's bottom and top and of the output layer
   int slice_min_bz, slice_min_vz, slice_max_bz, slice_max_vz, slice_out_bz, slice_out_vz;
+  // planar slice (PlanarSliceDescription): per-column bounds from the ground plane n . p + d = 0
+  int slice_planar;
+  float plane_nx, plane_ny, plane_nz, plane_d, slice_above_plane_m, slice_thickness_m;
   unsigned long long* colset_keys;  // set of (x, y) columns of this slice update (open addressing, keys only)
   unsigned int colset_mask;
   int* cols;                // unique columns: x, y pairs

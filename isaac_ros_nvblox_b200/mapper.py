@@ -320,10 +320,15 @@ class _EsdfIntegrator:
             check(self._m._L.nvb_mapper_set_esdf_slice_params(self._m._h, C.byref(p)))
         return p
 
-    def integrate_slice(self, block_indices):
-        """EsdfIntegrator::integrateSlice(layer, block_indices, esdf_layer) with the constant-z slice."""
+    def integrate_slice(self, block_indices, ground_plane=None):
+        """EsdfIntegrator::integrateSlice(layer, block_indices[, ground_plane], esdf_layer): constant-z slice, or the planar
+        one when ground_plane = (nx, ny, nz, d) (unit normal, n . p + d = 0) is given."""
         idx = np.ascontiguousarray(block_indices, dtype=np.int32).reshape(-1, 3)
-        check(self._m._L.nvb_esdf_integrate_slice_blocks(self._m._h, _ip(idx), idx.shape[0]))
+        if ground_plane is None:
+            check(self._m._L.nvb_esdf_integrate_slice_blocks(self._m._h, _ip(idx), idx.shape[0]))
+        else:
+            pl = np.ascontiguousarray(ground_plane, dtype=np.float32).reshape(4)
+            check(self._m._L.nvb_esdf_integrate_slice_planar_blocks(self._m._h, _fp(pl), _ip(idx), idx.shape[0]))
 
     def integrate_blocks(self, block_indices):
         """EsdfIntegrator::integrateBlocks(tsdf_layer | occupancy_layer, block_indices, esdf_layer)."""
@@ -566,9 +571,13 @@ class Mapper:
         else:
             check(self._L.nvb_mapper_update_esdf_async(self._h, 1 if update_full_layer else 0))
 
-    def update_esdf_slice(self, update_full_layer=False):
-        """Mapper::updateEsdfSlice (mapper.h:331-343): the 2-D ESDF on the slice layer."""
-        check(self._L.nvb_mapper_update_esdf_slice(self._h, 1 if update_full_layer else 0))
+    def update_esdf_slice(self, update_full_layer=False, ground_plane=None):
+        """Mapper::updateEsdfSlice(update_full_layer, ground_plane) (mapper.h:331-343): the 2-D ESDF on the slice layer."""
+        if ground_plane is None:
+            check(self._L.nvb_mapper_update_esdf_slice(self._h, 1 if update_full_layer else 0))
+        else:
+            pl = np.ascontiguousarray(ground_plane, dtype=np.float32).reshape(4)
+            check(self._L.nvb_mapper_update_esdf_slice_planar(self._h, _fp(pl), 1 if update_full_layer else 0))
 
     def synchronize(self):
         check(self._L.nvb_mapper_synchronize(self._h))

@@ -1264,19 +1264,39 @@ static void block_and_voxel_from_1d(float block_size, float p, int* block_idx, i
  * onto the x/y voxels of ONE layer of ESDF blocks (min TSDF distance / max log odds of the observed, non-freespace
  * voxels of each column), those voxels go through updateEsdfVoxelToChanges, and the usual clear + computeEsdf
  * follow on the slice's blocks. */
+static void esdf_integrate_slice_impl(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
+                                      int32_t num_blocks, const OrEsdfParams* P, float z_min_m, float z_max_m, float z_output_m,
+                                      const float* plane, float above_plane_m, float thickness_m);
 void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
                              int32_t num_blocks, const OrEsdfParams* P, float z_min_m, float z_max_m, float z_output_m) {
-  memset(map->stats, 0, sizeof(map->stats));
   map->slice_min_z = z_min_m, map->slice_max_z = z_max_m, map->slice_out_z = z_output_m;
+  esdf_integrate_slice_impl(map, from_occupancy, use_freespace, blocks_xyz, num_blocks, P, z_min_m, z_max_m, z_output_m, NULL, 0.0f,
+                            0.0f);
+}
+/* integrateSlice with a PlanarSliceDescription (esdf_integrator.cu:349-390; PlanarSliceColumnBoundsGetter,
+ * esdf_integrator_slicing_impl.cuh:90-130): the band starts `above_plane_m` above the ground plane
+ * n . p + d = 0 (plane = nx, ny, nz, d with a unit normal) and is `thickness_m` thick, per voxel column. */
+void or_esdf_integrate_slice_planar(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
+                                    int32_t num_blocks, const OrEsdfParams* P, const float plane[4], float above_plane_m,
+                                    float thickness_m, float z_output_m) {
+  float pl[4] = {plane[0], plane[1], plane[2], plane[3]};
+  if (fabsf(pl[2]) < 1e-4f) pl[0] = 0.0f, pl[1] = 0.0f, pl[2] = 1.0f, pl[3] = 0.0f; /* checkForVerticalPlane (:208-216) */
+  esdf_integrate_slice_impl(map, from_occupancy, use_freespace, blocks_xyz, num_blocks, P, 0.0f, 0.0f, z_output_m, pl, above_plane_m,
+                            thickness_m);
+}
+static void esdf_integrate_slice_impl(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
+                                      int32_t num_blocks, const OrEsdfParams* P, float z_min_m, float z_max_m, float z_output_m,
+                                      const float* plane, float above_plane_m, float thickness_m) {
+  memset(map->stats, 0, sizeof(map->stats));
   if (num_blocks == 0) return;
   const float max_esdf_distance_vox = P->max_esdf_distance_m / map->voxel_size;
   const float max_sq = max_esdf_distance_vox * max_esdf_distance_vox;
   const float max_site_distance_m = P->max_site_distance_vox * map->voxel_size;
   const float occupied_threshold_log_odds = log_odds_from_probability(P->occupied_threshold);
-  int out_bz, out_vz, min_bz, min_vz, max_bz, max_vz;
+  int out_bz, out_vz, cmin_bz, cmin_vz, cmax_bz, cmax_vz;
   block_and_voxel_from_1d(map->block_size, z_output_m, &out_bz, &out_vz);
-  block_and_voxel_from_1d(map->block_size, z_min_m, &min_bz, &min_vz); /* ConstantZColumnBoundsGetter (:76-88 of the impl) */
-  block_and_voxel_from_1d(map->block_size, z_max_m, &max_bz, &max_vz);
+  block_and_voxel_from_1d(map->block_size, z_min_m, &cmin_bz, &cmin_vz); /* ConstantZColumnBoundsGetter (:76-88 of the impl) */
+  block_and_voxel_from_1d(map->block_size, z_max_m, &cmax_bz, &cmax_vz);
   /* one output block per vertical column (Index3DSet, :968-973) */
   List blocks = {0};
   {
@@ -1305,6 +1325,16 @@ void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_fre
       for (int vy = 0; vy < VPS; vy++) {
         int observed = 0;
         float squashed = from_occupancy ? 0.0f : 2.0f * max_sq; /* :792-799 */
+        int min_bz = cmin_bz, min_vz = cmin_vz, max_bz = cmax_bz, max_vz = cmax_vz;
+        if (plane) { /* PlanarSliceColumnBoundsGetter::getColumnBounds */
+          const float vs = map->block_size * (1.0f / VPS), half = map->block_size * (0.5f / VPS);
+          const float px = (map->block_size * (float)ob.x + vs * (float)vx) + half;
+          const float py = (map->block_size * (float)ob.y + vs * (float)vy) + half;
+          const float plane_h = -1.0f * (plane[0] * px + plane[1] * py + plane[3]) / plane[2];
+          const float lo_h = plane_h + above_plane_m, hi_h = lo_h + thickness_m;
+          block_and_voxel_from_1d(map->block_size, lo_h, &min_bz, &min_vz);
+          block_and_voxel_from_1d(map->block_size, hi_h, &max_bz, &max_vz);
+        }
         for (int bz = min_bz; bz <= max_bz; bz++) {
           const i3 k = {ob.x, ob.y, bz};
           const int32_t ss = hash_find(&src->hash, k);

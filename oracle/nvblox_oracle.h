@@ -231,6 +231,12 @@ void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_fre
                              int32_t num_blocks, const OrEsdfParams* params, float z_min_m, float z_max_m,
                              float z_output_m);
 
+/* integrateSlice with a PlanarSliceDescription: plane = (nx, ny, nz, d), unit normal, n . p + d = 0
+ * (slice_height_above_plane_m 0, slice_height_thickness_m 0.1 by default, esdf_integrator_params.h:45-52). */
+void or_esdf_integrate_slice_planar(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
+                                    int32_t num_blocks, const OrEsdfParams* params, const float plane[4], float above_plane_m,
+                                    float thickness_m, float z_output_m);
+
 /* EsdfSlicer::sliceLayerToDistanceImage + occupancyGridFromSliceImage (integrators/esdf_slicer.h:52-118): the distance map
  * (m, negative inside, `unobserved_value` where nothing is known) of the ESDF layer at `slice_height`, one pixel per voxel
  * over the AABB of the blocks at that height (aabb_out = min xyz, max xyz); rows follow y, columns x. */

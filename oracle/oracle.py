@@ -165,6 +165,9 @@ def lib():
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.restype = None
+    L.or_esdf_integrate_slice_planar.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), fp, C.c_float,
+                                                 C.c_float, C.c_float]
+    L.or_esdf_integrate_slice_planar.restype = None
     L.or_esdf_slice_image.argtypes = [vp, C.c_float, C.c_float, fp, fp, C.POINTER(C.c_int8), C.c_int32, ip, ip]
     L.or_esdf_slice_image.restype = C.c_int32
     L.or_esdf_integrate_slice.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), C.c_float, C.c_float,
@@ -442,6 +445,16 @@ class OracleMap:
         blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
         lib().or_esdf_integrate_slice(self._h, 1 if from_occupancy else 0, 1 if use_freespace else 0, _ip(blocks),
                                       blocks.shape[0], C.byref(params), float(z_min_m), float(z_max_m), float(z_output_m))
+
+    def integrate_esdf_slice_planar(self, blocks, plane, params=None, above_plane_m=0.0, thickness_m=0.1, z_output_m=1.0,
+                                    from_occupancy=False, use_freespace=False):
+        """EsdfIntegrator::integrateSlice(layer, blocks, ground_plane, esdf); plane = (nx, ny, nz, d), unit normal."""
+        params = params or default_esdf_params()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        pl = np.ascontiguousarray(plane, dtype=np.float32).reshape(4)
+        lib().or_esdf_integrate_slice_planar(self._h, 1 if from_occupancy else 0, 1 if use_freespace else 0, _ip(blocks),
+                                             blocks.shape[0], C.byref(params), _fp(pl), float(above_plane_m), float(thickness_m),
+                                             float(z_output_m))
 
     def esdf_slice_image(self, slice_height, unobserved_value=1000.0):
         """EsdfSlicer::sliceLayerToDistanceImage + occupancyGridFromSliceImage -> (aabb(6), image (rows, cols), grid int8)."""

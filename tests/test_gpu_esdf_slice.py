@@ -119,3 +119,28 @@ def test_esdf_slicer_distance_image_and_occupancy_grid(gpu, two_d):
     aabb, img = nvb.EsdfSlicer(m).slice_layer_to_distance_image(1.0)
     assert img.size > 10000 and (img == 1000.0).any() and (np.abs(img) < 0.01).any() and (img[img != 1000.0] > 0.5).any()
     m.close()
+
+
+@pytest.mark.parametrize("plane", [(0.0, 0.0, 1.0, -0.5), (0.0599, -0.0399, 0.9974, -0.3), (1.0, 0.0, 0.0, 0.0)])
+def test_esdf_planar_slice(gpu, plane):
+    """integrateSlice with a PlanarSliceDescription: per-column bounds from the ground plane (a level one, a tilted one, and a
+    vertical one that falls back to z = 0)."""
+    nvb, orc = _nvb(), _orc()
+    n = np.asarray(plane[:3], np.float64)
+    n = n / np.linalg.norm(n)
+    pl = np.array([n[0], n[1], n[2], plane[3]], np.float32)
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(40)[:4])
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    m.esdf_integrator().slice_params(slice_height_above_plane_m=0.3, slice_height_thickness_m=0.85, slice_height_m=1.0)
+    for i, (d, T) in enumerate(frames):
+        b = m.integrate_depth(d, T, cam)
+        o.integrate_depth(d, T, ocam)
+        m.update_esdf_slice(ground_plane=pl)
+        o.integrate_esdf_slice_planar(b if i else o.tsdf_block_indices(), pl, above_plane_m=0.3, thickness_m=0.85, z_output_m=1.0)
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    m.esdf_integrator().integrate_slice(b[::2], ground_plane=pl)  # explicit list
+    o.integrate_esdf_slice_planar(b[::2], pl, above_plane_m=0.3, thickness_m=0.85, z_output_m=1.0)
+    assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    assert sum(int(v["is_site"].sum()) for v in m.esdf_layer().as_dict().values()) > 50
+    m.close()
