@@ -515,6 +515,16 @@ int ensureTsdfCapacity(NvbMapper* m, long long new_cells) {
   return allocTsdfSide(m, old, (int)cap);
 }
 
+// The explicit-list entry points are synchronous: afterwards the real fill level of the ESDF slab is known and replaces
+// the running sum of list lengths (which would otherwise grow the slab without need in a long session).
+int tightenEsdfBound(NvbMapper* m) {
+  int count = 0;
+  NVB_CUDA(cudaMemcpy(&count, m->esdf.count, sizeof(int), cudaMemcpyDeviceToHost));
+  const int from_tsdf = std::min(m->tsdf_count_ub, m->tsdf.capacity);
+  m->esdf_extra_ub = std::max(0, std::min(count, m->esdf.capacity) - from_tsdf);
+  return NVB_OK;
+}
+
 int ensureEsdfCapacity(NvbMapper* m, long long needed_total) {
   if (needed_total <= m->esdf.capacity) return NVB_OK;
   long long cap = m->esdf.capacity;
@@ -1540,7 +1550,8 @@ int32_t nvb_esdf_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, 
   NVB_CUDA(cudaStreamSynchronize(m->stream));  // v is pageable and about to go out of scope
   int rc = enqueueEsdf(m, m->xyz_upload, n, false);
   if (rc) return rc;
-  return nvb_mapper_synchronize(m);
+  if ((rc = nvb_mapper_synchronize(m))) return rc;
+  return tightenEsdfBound(m);
 }
 
 void nvb_default_esdf_slice_params(NvbEsdfSliceParams* p) {
@@ -1613,7 +1624,8 @@ static int32_t integrateSliceBlocksImpl(NvbMapper* m, const float* plane, const 
   NVB_CUDA(cudaStreamSynchronize(m->stream));
   int rc = enqueueEsdf(m, m->xyz_upload, num_blocks, false, true, plane);
   if (rc) return rc;
-  return nvb_mapper_synchronize(m);
+  if ((rc = nvb_mapper_synchronize(m))) return rc;
+  return tightenEsdfBound(m);
 }
 
 int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float unobserved_value, float aabb_out[6],
