@@ -100,8 +100,9 @@ __device__ __forceinline__ void markLocalFlush(const EsdfCtx& c, MarkLocal& ml) 
   }
   markLocalInit(ml);
 }
-// thread 0 only
-__device__ __forceinline__ void markLocalRecord(const EsdfCtx& c, MarkLocal& ml, int slot, bool updated, bool cleared) {
+// thread 0 only; bi = the block's index if the caller already has it, else nullptr
+__device__ __forceinline__ void markLocalRecord(const EsdfCtx& c, MarkLocal& ml, int slot, bool updated, bool cleared,
+                                                const int* bi_known = nullptr) {
   if (updated) {
     if (ml.nu == kMarkLocalMax) markLocalFlush(c, ml);
     ml.upd[ml.nu++] = slot;
@@ -110,7 +111,7 @@ __device__ __forceinline__ void markLocalRecord(const EsdfCtx& c, MarkLocal& ml,
   if (cleared) {
     if (ml.nc == kMarkLocalMax) markLocalFlush(c, ml);
     ml.clr[ml.nc++] = slot;
-    const int* bi = c.esdf.block_index + 3 * slot;
+    const int* bi = bi_known ? bi_known : c.esdf.block_index + 3 * slot;
     const int x = bi[0], y = bi[1], z = bi[2];
     ml.aabb[0] = min(ml.aabb[0], x), ml.aabb[1] = min(ml.aabb[1], y), ml.aabb[2] = min(ml.aabb[2], z);
     ml.aabb[3] = max(ml.aabb[3], x), ml.aabb[4] = max(ml.aabb[4], y), ml.aabb[5] = max(ml.aabb[5], z);
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
   __shared__ __align__(8) uint64_t s_bar[kMarkStages];
   __shared__ int4 s_work[kMarkStages];
   __shared__ int s_flags[3];  // updated, cleared, changed
+  __shared__ int s_bi[3];
   __shared__ MarkLocal ml;
   const int tid = threadIdx.x;
   if (tid == 0) markLocalInit(ml);
@@ -402,6 +404,8 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
     }
     tma::mbarWait(&s_bar[s], (unsigned int)((j / kMarkStages) & 1));
     const int4 w = s_work[s];
+    // the block's index, for the to-clear AABB: fetched now so that thread 0 does not wait for it at the end of the item
+    if (tid >= 32 && tid < 35 && w.x >= 0) s_bi[tid - 32] = c.esdf.block_index[3 * w.x + (tid - 32)];
     if (w.x >= 0 && w.z) linkNewBlock(c, w.x, tid);  // newly allocated ESDF block
     const bool valid = (w.x >= 0 && w.y >= 0);  // block_ptr == nullptr || esdf_block == nullptr (:513-517)
     if (tid < 3) s_flags[tid] = 0;
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(kThreads) esdfMarkTmaKernel(EsdfCtx c) {
         tma::bulkStore(c.esdf.blocks + (size_t)w.x * kEsdfBlockBytes, st[s].esdf, kEsdfBlockBytes);
         tma::bulkCommit();
       }
-      markLocalRecord(c, ml, w.x, s_flags[0] != 0, s_flags[1] != 0);
+      markLocalRecord(c, ml, w.x, s_flags[0] != 0, s_flags[1] != 0, s_bi);
     }
     __syncthreads();
   }

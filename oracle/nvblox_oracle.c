@@ -1284,6 +1284,28 @@ void or_esdf_integrate_slice_planar(OrMap* map, int32_t from_occupancy, int32_t 
   esdf_integrate_slice_impl(map, from_occupancy, use_freespace, blocks_xyz, num_blocks, P, 0.0f, 0.0f, z_output_m, pl, above_plane_m,
                             thickness_m);
 }
+/* PlanarSliceColumnBoundsGetter::getColumnBounds (esdf_integrator_slicing_impl.cuh:103-130): out = min block z, min voxel z,
+ * max block z, max voxel z of the band over the voxel column (block x/y, voxel x/y). */
+void or_planar_column_bounds(float block_size, const float plane[4], float above_plane_m, float thickness_m, int32_t bx, int32_t by,
+                             int32_t vx, int32_t vy, int32_t out[4]) {
+  const float vs = block_size * (1.0f / VPS), half = block_size * (0.5f / VPS);
+  const float px = (block_size * (float)bx + vs * (float)vx) + half;
+  const float py = (block_size * (float)by + vs * (float)vy) + half;
+  const float plane_h = -1.0f * (plane[0] * px + plane[1] * py + plane[3]) / plane[2]; /* Plane::getHeightAtXY */
+  const float lo_h = plane_h + above_plane_m, hi_h = lo_h + thickness_m;
+  int b0, v0, b1, v1;
+  block_and_voxel_from_1d(block_size, lo_h, &b0, &v0);
+  block_and_voxel_from_1d(block_size, hi_h, &b1, &v1);
+  out[0] = b0, out[1] = v0, out[2] = b1, out[3] = v1;
+}
+/* PlanarSliceColumnBoundsGetter::num_blocks_in_vertical_column (:84-101) */
+int32_t or_planar_num_blocks_in_column(float block_size, float thickness_m) { return f2i(ceilf(thickness_m / block_size)) + 1; }
+/* getBlockAndVoxelIndexFrom1DPositionInLayer, exposed for the known-answer tests */
+void or_block_and_voxel_from_1d(float block_size, float p, int32_t out[2]) {
+  int b, v;
+  block_and_voxel_from_1d(block_size, p, &b, &v);
+  out[0] = b, out[1] = v;
+}
 static void esdf_integrate_slice_impl(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
                                       int32_t num_blocks, const OrEsdfParams* P, float z_min_m, float z_max_m, float z_output_m,
                                       const float* plane, float above_plane_m, float thickness_m) {
@@ -1326,14 +1348,10 @@ static void esdf_integrate_slice_impl(OrMap* map, int32_t from_occupancy, int32_
         int observed = 0;
         float squashed = from_occupancy ? 0.0f : 2.0f * max_sq; /* :792-799 */
         int min_bz = cmin_bz, min_vz = cmin_vz, max_bz = cmax_bz, max_vz = cmax_vz;
-        if (plane) { /* PlanarSliceColumnBoundsGetter::getColumnBounds */
-          const float vs = map->block_size * (1.0f / VPS), half = map->block_size * (0.5f / VPS);
-          const float px = (map->block_size * (float)ob.x + vs * (float)vx) + half;
-          const float py = (map->block_size * (float)ob.y + vs * (float)vy) + half;
-          const float plane_h = -1.0f * (plane[0] * px + plane[1] * py + plane[3]) / plane[2];
-          const float lo_h = plane_h + above_plane_m, hi_h = lo_h + thickness_m;
-          block_and_voxel_from_1d(map->block_size, lo_h, &min_bz, &min_vz);
-          block_and_voxel_from_1d(map->block_size, hi_h, &max_bz, &max_vz);
+        if (plane) {
+          int cb[4];
+          or_planar_column_bounds(map->block_size, plane, above_plane_m, thickness_m, ob.x, ob.y, vx, vy, cb);
+          min_bz = cb[0], min_vz = cb[1], max_bz = cb[2], max_vz = cb[3];
         }
         for (int bz = min_bz; bz <= max_bz; bz++) {
           const i3 k = {ob.x, ob.y, bz};

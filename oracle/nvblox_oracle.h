@@ -233,6 +233,10 @@ void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_fre
 
 /* integrateSlice with a PlanarSliceDescription: plane = (nx, ny, nz, d), unit normal, n . p + d = 0
  * (slice_height_above_plane_m 0, slice_height_thickness_m 0.1 by default, esdf_integrator_params.h:45-52). */
+void or_planar_column_bounds(float block_size, const float plane[4], float above_plane_m, float thickness_m, int32_t bx, int32_t by,
+                             int32_t vx, int32_t vy, int32_t out[4]);
+int32_t or_planar_num_blocks_in_column(float block_size, float thickness_m);
+void or_block_and_voxel_from_1d(float block_size, float p, int32_t out[2]);
 void or_esdf_integrate_slice_planar(OrMap* map, int32_t from_occupancy, int32_t use_freespace, const int32_t* blocks_xyz,
                                     int32_t num_blocks, const OrEsdfParams* params, const float plane[4], float above_plane_m,
                                     float thickness_m, float z_output_m);

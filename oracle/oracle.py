@@ -168,6 +168,12 @@ def lib():
     L.or_esdf_integrate_slice_planar.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), fp, C.c_float,
                                                  C.c_float, C.c_float]
     L.or_esdf_integrate_slice_planar.restype = None
+    L.or_planar_column_bounds.argtypes = [C.c_float, fp, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, ip]
+    L.or_planar_column_bounds.restype = None
+    L.or_planar_num_blocks_in_column.argtypes = [C.c_float, C.c_float]
+    L.or_planar_num_blocks_in_column.restype = C.c_int32
+    L.or_block_and_voxel_from_1d.argtypes = [C.c_float, C.c_float, ip]
+    L.or_block_and_voxel_from_1d.restype = None
     L.or_esdf_slice_image.argtypes = [vp, C.c_float, C.c_float, fp, fp, C.POINTER(C.c_int8), C.c_int32, ip, ip]
     L.or_esdf_slice_image.restype = C.c_int32
     L.or_esdf_integrate_slice.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), C.c_float, C.c_float,
@@ -526,6 +532,25 @@ class OracleMap:
 
     def esdf_layer(self):
         return {tuple(int(c) for c in k): self.esdf_block(k) for k in self.esdf_block_indices()}
+
+
+def planar_column_bounds(block_size, plane, above_plane_m, thickness_m, block_xy, voxel_xy):
+    """PlanarSliceColumnBoundsGetter::getColumnBounds -> (min block z, min voxel z, max block z, max voxel z)."""
+    out = np.zeros(4, np.int32)
+    pl = np.ascontiguousarray(plane, dtype=np.float32).reshape(4)
+    lib().or_planar_column_bounds(float(block_size), _fp(pl), float(above_plane_m), float(thickness_m), int(block_xy[0]),
+                                  int(block_xy[1]), int(voxel_xy[0]), int(voxel_xy[1]), _ip(out))
+    return tuple(int(v) for v in out)
+
+
+def planar_num_blocks_in_column(block_size, thickness_m):
+    return int(lib().or_planar_num_blocks_in_column(float(block_size), float(thickness_m)))
+
+
+def block_and_voxel_from_1d(block_size, p):
+    out = np.zeros(2, np.int32)
+    lib().or_block_and_voxel_from_1d(float(block_size), float(p), _ip(out))
+    return int(out[0]), int(out[1])
 
 
 def camera_project(cam, p_C):

@@ -144,3 +144,58 @@ def test_esdf_planar_slice(gpu, plane):
     assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
     assert sum(int(v["is_site"].sum()) for v in m.esdf_layer().as_dict().values()) > 50
     m.close()
+
+
+def _slice_both(m, o, lst, planar, kw):
+    if planar:
+        m.esdf_integrator().slice_params(slice_height_above_plane_m=kw["above_plane_m"],
+                                         slice_height_thickness_m=kw["thickness_m"], slice_height_m=kw["z_output_m"])
+        m.esdf_integrator().integrate_slice(lst, ground_plane=kw["plane"])
+        o.integrate_esdf_slice_planar(lst, kw["plane"], above_plane_m=kw["above_plane_m"], thickness_m=kw["thickness_m"],
+                                      z_output_m=kw["z_output_m"])
+    else:
+        m.esdf_integrator().slice_params(slice_min_height_m=kw["z_min_m"], slice_max_height_m=kw["z_max_m"],
+                                         slice_height_m=kw["z_output_m"])
+        m.esdf_integrator().integrate_slice(lst)
+        o.integrate_esdf_slice(lst, **kw)
+
+
+@pytest.mark.parametrize("planar", [False, True])
+@pytest.mark.parametrize("name", ["single_block", "across_block", "45_degree"])
+def test_slicing_reference_cases(gpu, name, planar):
+    """The reference's own slicing cases (tests/test_esdf_integrator_slicing.cu SingleBlock, AcrossBlock, 45DegreeSlice) on
+    hand-set TSDF blocks: the expected site columns, and all fields equal to the oracle's."""
+    from helpers import check_slicing_sites, slicing_case
+    nvb, orc = _nvb(), _orc()
+    blocks, kw, exp = slicing_case(name, planar)
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    lst = np.asarray(list(blocks), np.int32)
+    m.tsdf_layer().set_blocks(lst, np.stack([blocks[tuple(k)] for k in lst]))
+    for idx, vox in blocks.items():
+        o.set_tsdf_block(idx, vox)
+    _slice_both(m, o, lst, planar, kw)
+    layer = m.esdf_layer().as_dict()
+    check_slicing_sites(layer, exp)
+    assert_esdf_equal(layer, o.esdf_layer())
+    m.close()
+
+
+@pytest.mark.parametrize("planar", [False, True])
+def test_slicing_sphere_scene(gpu, planar):
+    """TestScene (:485-555): one-voxel band through the ground-truth TSDF of the sphere-in-a-box scene (8 788 blocks)."""
+    from helpers import check_sphere_scene_slice, sphere_scene_tsdf_layer, unit_plane
+    nvb, orc = _nvb(), _orc()
+    idx, vox = sphere_scene_tsdf_layer()
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    m.tsdf_layer().set_blocks(idx, vox)
+    for k, v in zip(idx, vox):
+        o.set_tsdf_block(k, v)
+    zmax = float(np.float32(2.0) + np.float32(0.05))
+    kw = (dict(plane=unit_plane((-1, 0, 1), (0, 0, 2)), above_plane_m=0.0, thickness_m=float(np.float32(zmax) - np.float32(2.0)),
+               z_output_m=0.0) if planar else dict(z_min_m=2.0, z_max_m=zmax, z_output_m=0.0))
+    _slice_both(m, o, idx, planar, kw)
+    layer = m.esdf_layer().as_dict()
+    assert len(layer) == 26 * 26
+    assert check_sphere_scene_slice(layer, planar) > 3000
+    assert_esdf_equal(layer, o.esdf_layer())
+    m.close()

@@ -1054,3 +1054,82 @@ def test_esdf_slicer_image_of_the_slice():
     unknown = img == 1000.0
     assert unknown.any() and np.all(grid[unknown] == -1)
     assert m.esdf_slice_image(40.0)[1].size == 0
+
+
+# ---------------------------------------------------------------------------
+# tests/test_esdf_integrator_slicing.cu and tests/test_indexing.cpp: the reference's own slicing / indexing answers
+# ---------------------------------------------------------------------------
+def _run_slicing_case(name, planar):
+    from helpers import check_slicing_sites, slicing_case
+    blocks, kw, exp = slicing_case(name, planar)
+    m = orc.OracleMap(0.05)
+    for idx, vox in blocks.items():
+        m.set_tsdf_block(idx, vox)
+    lst = np.asarray(list(blocks), np.int32)
+    if planar:
+        m.integrate_esdf_slice_planar(lst, kw["plane"], above_plane_m=kw["above_plane_m"], thickness_m=kw["thickness_m"],
+                                      z_output_m=kw["z_output_m"])
+    else:
+        m.integrate_esdf_slice(lst, **kw)
+    check_slicing_sites(m.esdf_layer(), exp)
+
+
+@pytest.mark.parametrize("planar", [False, True])
+@pytest.mark.parametrize("name", ["single_block", "across_block", "45_degree"])
+def test_slicing_reference_cases(name, planar):
+    """SingleBlock (:109-208), AcrossBlock (:210-287), 45DegreeSlice (:353-483) of test_esdf_integrator_slicing.cu, for the
+    height-based and the planar slice description."""
+    _run_slicing_case(name, planar)
+
+
+def test_planar_slice_column_bounds_constructor_case():
+    """PlanarSliceConstructor (test_esdf_integrator_slicing.cu:289-350)."""
+    from helpers import unit_plane
+    # the reference's constants are binary32 products: kBlockSizeM = 8 * 0.05f, thickness = 9 * 0.05f (= 0.45000002)
+    bs, above, thick = float(np.float32(8) * np.float32(0.05)), 0.0, float(np.float32(9) * np.float32(0.05))
+    assert orc.planar_num_blocks_in_column(bs, thick) == 3
+    flat = np.array([0, 0, 1, 0], np.float32)
+    assert orc.planar_column_bounds(bs, flat, above, thick, (0, 0), (0, 0)) == (0, 0, 1, 1)
+    assert orc.planar_column_bounds(bs, flat, above, thick, (1, 1), (0, 0)) == (0, 0, 1, 1)
+    tilted = unit_plane((-1, 0, 1), (0, 0, 1))
+    assert orc.planar_column_bounds(bs, tilted, above, thick, (0, 0), (0, 0)) == (2, 4, 3, 5)
+    assert orc.planar_column_bounds(bs, tilted, above, thick, (1, 1), (2, 2)) == (3, 6, 4, 7)
+
+
+@pytest.mark.parametrize("planar", [False, True])
+def test_slicing_sphere_scene(planar):
+    """TestScene (test_esdf_integrator_slicing.cu:485-555): a one-voxel band at 2 m (or along the 45-degree plane through
+    (0, 0, 2)) through the ground-truth TSDF of the sphere-in-a-box scene; inside voxels lie within the sphere's outline."""
+    from helpers import check_sphere_scene_slice, sphere_scene_tsdf_layer, unit_plane
+    idx, vox = sphere_scene_tsdf_layer()
+    m = orc.OracleMap(0.05)
+    for k, v in zip(idx, vox):
+        m.set_tsdf_block(k, v)
+    zmin = 2.0
+    zmax = float(np.float32(zmin) + np.float32(1.0 * np.float32(0.05)))
+    if planar:
+        m.integrate_esdf_slice_planar(idx, unit_plane((-1, 0, 1), (0, 0, 2)), above_plane_m=0.0,
+                                      thickness_m=float(np.float32(zmax) - np.float32(zmin)), z_output_m=0.0)
+    else:
+        m.integrate_esdf_slice(idx, z_min_m=zmin, z_max_m=zmax, z_output_m=0.0)
+    layer = m.esdf_layer()
+    assert len(layer) == 26 * 26 and {k[2] for k in layer} == {0}
+    n_inside = check_sphere_scene_slice(layer, planar)
+    # the disc of radius 2 (squashed by cos 45 degrees along x for the tilted plane): pi r^2 / voxel^2 voxels, roughly
+    expect = np.pi * 4.0 / 0.0025 * (np.sqrt(0.5) if planar else 1.0)
+    assert 0.8 * expect < n_inside < 1.1 * expect, (n_inside, expect)
+
+
+def test_indexing_1d_never_leaves_the_block():
+    """getBlockAndVoxelIndexFromPositionInLayerRoundingErrors (test_indexing.cpp:105-124) and
+    getBlockAndVoxelIndexFromPositionInLayer (:74-103), on the 1-D form the slice bounds use."""
+    rng = np.random.default_rng(0)
+    for p in rng.uniform(-1.0, 1.0, 20000).astype(np.float32):
+        b, v = orc.block_and_voxel_from_1d(0.1, p)
+        assert 0 <= v < 8
+        assert abs((b * 0.1 + (v + 0.5) * 0.0125) - float(p)) < 0.0125
+    voxel, bs = 0.1, np.float32(0.8)
+    for _ in range(2000):
+        b, v = int(rng.integers(-1000, 1001)), int(rng.integers(0, 8))
+        p = np.float32(b) * bs + np.float32(v) * np.float32(voxel) + np.float32(rng.uniform(0.0, voxel))
+        assert orc.block_and_voxel_from_1d(bs, p)[0] in (b, b + (1 if v == 7 else 0))
