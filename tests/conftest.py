@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# The oracle is OpenMP code with many short parallel regions: on a box whose visible core count exceeds what the
+# container may use, a full-width team spins at every barrier. A small passive team is faster everywhere.
+os.environ.setdefault("OMP_NUM_THREADS", str(max(1, min(8, len(os.sched_getaffinity(0))))))
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
