@@ -475,7 +475,7 @@ static void list_sort_unique(List* l) {
 
 struct OrMap {
   float voxel_size, block_size;
-  Layer tsdf, esdf, occ, freespace;
+  Layer tsdf, esdf, occ, freespace, color;
   int64_t freespace_last_update_time_ms; /* FreespaceIntegrator::last_update_time_ms_ (freespace_integrator.h:171) */
   float slice_min_z, slice_max_z, slice_out_z; /* heights of the last or_esdf_integrate_slice call (for the 2-D clear) */
   /* EsdfIntegrator::cleared_block_indices_device_ (integrators/esdf_integrator.h:389)
@@ -519,16 +519,17 @@ OrMap* or_map_create(float voxel_size_m) {
   layer_init(&m->esdf, sizeof(OrEsdfVoxel) * VPB);
   layer_init(&m->occ, sizeof(float) * VPB); /* OccupancyVoxel{float log_odds} (map/voxels.h:92-97) */
   layer_init(&m->freespace, sizeof(OrFreespaceVoxel) * VPB);
+  layer_init(&m->color, sizeof(OrColorVoxel) * VPB);
   return m;
 }
 void or_map_destroy(OrMap* m) {
   if (!m) return;
-  layer_free(&m->tsdf), layer_free(&m->esdf), layer_free(&m->occ), layer_free(&m->freespace);
+  layer_free(&m->tsdf), layer_free(&m->esdf), layer_free(&m->occ), layer_free(&m->freespace), layer_free(&m->color);
   list_free(&m->esdf_cleared_persistent);
   free(m);
 }
 void or_map_clear(OrMap* m) {
-  layer_clear(&m->tsdf), layer_clear(&m->esdf), layer_clear(&m->occ), layer_clear(&m->freespace);
+  layer_clear(&m->tsdf), layer_clear(&m->esdf), layer_clear(&m->occ), layer_clear(&m->freespace), layer_clear(&m->color);
   m->esdf_cleared_persistent.n = 0;
 }
 
@@ -1504,6 +1505,299 @@ int32_t or_esdf_get_block(const OrMap* m, const int32_t xyz[3], OrEsdfVoxel* out
 }
 
 /* ------------------------------------------------------------------------- */
+/* Colour integration (src/integrators/projective_appearance_integrator.cu,  */
+/* src/rays/sphere_tracer.cu)                                                */
+/* ------------------------------------------------------------------------- */
+void or_default_color_params(OrColorParams* p) {
+  memset(p, 0, sizeof(*p));
+  /* integrators/projective_integrator_params.h:24-75, projective_appearance_integrator.h:164, rays/sphere_tracer.h:216-218 */
+  p->max_integration_distance_m = 7.0f;
+  p->truncation_distance_vox = 4.0f;
+  p->max_weight = 5.0f;
+  p->measurement_weight = 0.8f;
+  p->sphere_tracing_ray_subsampling_factor = 4;
+  p->sphere_tracer_maximum_steps = 100;
+  p->sphere_tracer_maximum_ray_length_m = 7.0f; /* set from max_integration_distance_m_ in the constructor only (:61) */
+  p->sphere_tracer_surface_distance_epsilon_vox = 0.1f;
+  p->workspace_bounds_type = OR_WS_UNBOUNDED;
+}
+
+/* binary32 -> binary16 -> binary32 (__float2half then the implicit __half -> float), round to nearest even. */
+static float round_through_half(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = x & 0x80000000u;
+  const uint32_t ax = x & 0x7fffffffu;
+  uint32_t out;
+  if (ax >= 0x7f800000u) {
+    out = ax; /* inf / nan: unchanged (weights never get here) */
+  } else if (ax >= 0x477ff000u) {
+    out = 0x7f800000u; /* >= 65520 rounds to inf */
+  } else if (ax < 0x38800000u) { /* below the smallest normal half 2^-14: the result is a multiple of 2^-24 */
+    const float a = fabsf(f);
+    const float q = nearbyintf(a * 16777216.0f); /* exact scaling; default rounding mode = nearest even */
+    float r = q * (1.0f / 16777216.0f);
+    memcpy(&out, &r, 4);
+  } else {
+    const uint32_t lsb = (ax >> 13) & 1u;
+    out = (ax + 0x0fffu + lsb) & 0xffffe000u;
+  }
+  out |= sign;
+  float r;
+  memcpy(&r, &out, 4);
+  return r;
+}
+float or_round_through_half(float f) { return round_through_half(f); }
+
+/* getBlockAndVoxelIndexFromPositionInLayer (core/internal/impl/indexing_impl.h:37-49) */
+static void block_and_voxel_from_position(float block_size, v3 p, i3* b, int v[3]) {
+  const float inv = (float)(1.0 / (double)(block_size * (1.0f / VPS)));
+  const float pp[3] = {p.x, p.y, p.z};
+  int bb[3];
+  for (int a = 0; a < 3; a++) {
+    bb[a] = f2i(floorf(pp[a] / block_size));
+    v[a] = f2i((pp[a] - block_size * (float)bb[a]) * inv);
+    if (v[a] > VPS - 1) v[a] = VPS - 1;
+  }
+  b->x = bb[0], b->y = bb[1], b->z = bb[2];
+}
+
+/* cast (src/rays/sphere_tracer.cu:31-100): march along the ray by the TSDF distance of the voxel under the point. */
+static int sphere_trace_cast(const OrMap* map, v3 origin, v3 dir, float truncation_distance_m, int maximum_steps,
+                             float maximum_ray_length_m, float surface_distance_epsilon_m, float* t_out) {
+  int first = 0; /* 0 not yet known, 1 positive, 2 negative */
+  float t = 0.0f;
+  for (int i = 0; (i < maximum_steps) && (t < maximum_ray_length_m); i++) {
+    const v3 p_L = {origin.x + t * dir.x, origin.y + t * dir.y, origin.z + t * dir.z};
+    float step;
+    i3 b;
+    int v[3];
+    block_and_voxel_from_position(map->block_size, p_L, &b, v);
+    const int32_t slot = hash_find(&map->tsdf.hash, b);
+    const OrTsdfVoxel* vox = slot >= 0 ? (const OrTsdfVoxel*)layer_block(&map->tsdf, slot) + (v[0] * VPS + v[1]) * VPS + v[2] : NULL;
+    if (!vox || !(vox->weight > 1e-4f)) { /* isTsdfVoxelValid (:26-29) */
+      if (first == 0) {
+        step = truncation_distance_m;
+      } else {
+        *t_out = t;
+        return 0;
+      }
+    } else {
+      if (first == 0) first = (vox->distance >= 0.0f) ? 1 : 2;
+      if (first == 1) {
+        if (vox->distance < surface_distance_epsilon_m) {
+          *t_out = t + vox->distance;
+          return 1;
+        }
+        step = vox->distance;
+      } else {
+        if (vox->distance > -surface_distance_epsilon_m) {
+          *t_out = t - vox->distance;
+          return 1;
+        }
+        step = -vox->distance;
+      }
+    }
+    t += step;
+  }
+  *t_out = t;
+  return 0;
+}
+
+/* SphereTracer::castOnGPU(ray, ...) (src/rays/sphere_tracer.cu:341-387): one ray, direction already normalised. */
+int32_t or_sphere_trace_ray(const OrMap* map, const float origin[3], const float direction[3], float truncation_distance_m,
+                            int32_t maximum_steps, float maximum_ray_length_m, float surface_distance_epsilon_m, float* t_out) {
+  const v3 o = {origin[0], origin[1], origin[2]}, d = {direction[0], direction[1], direction[2]};
+  return sphere_trace_cast(map, o, d, truncation_distance_m, maximum_steps, maximum_ray_length_m, surface_distance_epsilon_m,
+                           t_out);
+}
+
+/* SphereTracer::renderImageOnGPU + sphereTracingKernel (src/rays/sphere_tracer.cu:134-173, 422-485):
+ * out is (rows / f) x (cols / f), -1 where the ray found no surface. */
+void or_sphere_trace_image(const OrMap* map, const float* T_L_C, const OrCamera* cam, float truncation_distance_m,
+                           int32_t maximum_steps, float maximum_ray_length_m, float surface_distance_epsilon_m,
+                           int32_t ray_subsampling_factor, float* out) {
+  const int f = ray_subsampling_factor;
+  const int ray_rows = cam->height / f, ray_cols = cam->width / f;
+  const v3 origin = {Tt(T_L_C, 0), Tt(T_L_C, 1), Tt(T_L_C, 2)};
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int r = 0; r < ray_rows; r++)
+    for (int c = 0; c < ray_cols; c++) {
+      const float half = 0.5f * (float)f;
+      const float px = (float)(c * f) + half * 1.0f, py = (float)(r * f) + half * 1.0f;
+      v3 d = cam_vector_from_image_plane(cam, px, py);
+      const float n = sqrtf(sum3(d.x * d.x, d.y * d.y, d.z * d.z)); /* Eigen normalized() */
+      d.x = d.x / n, d.y = d.y / n, d.z = d.z / n;
+      v3 dir;
+      dir.x = sum3(Rm(T_L_C, 0, 0) * d.x, Rm(T_L_C, 0, 1) * d.y, Rm(T_L_C, 0, 2) * d.z);
+      dir.y = sum3(Rm(T_L_C, 1, 0) * d.x, Rm(T_L_C, 1, 1) * d.y, Rm(T_L_C, 1, 2) * d.z);
+      dir.z = sum3(Rm(T_L_C, 2, 0) * d.x, Rm(T_L_C, 2, 1) * d.y, Rm(T_L_C, 2, 2) * d.z);
+      float t;
+      const int ok = sphere_trace_cast(map, origin, dir, truncation_distance_m, maximum_steps, maximum_ray_length_m,
+                                       surface_distance_epsilon_m, &t);
+      out[(size_t)r * ray_cols + c] = ok ? t * d.z : -1.0f;
+    }
+}
+
+/* ViewCalculator::getBlocksInImageViewProjection (view_calculator_impl.h:29-78) + getVisibleBlocksByProjection<Camera>
+ * (src/integrators/view_calculator.cu:380-417), then reduceBlocksToThoseInTruncationBand
+ * (projective_appearance_integrator.cu:378-481). */
+static List color_blocks_in_view_and_band(const OrMap* map, const float* T_L_C, const OrCamera* cam, const OrColorParams* P,
+                                          float truncation_distance_m) {
+  List out = {0};
+  const float max_distance = P->max_integration_distance_m + truncation_distance_m;
+  v3 mn, mx;
+  cam_view_aabb(cam, T_L_C, 1e-6f, max_distance, &mn, &mx);
+  OrTsdfParams ws;
+  memset(&ws, 0, sizeof(ws));
+  ws.workspace_bounds_type = P->workspace_bounds_type;
+  for (int a = 0; a < 3; a++) ws.workspace_min[a] = P->workspace_min[a], ws.workspace_max[a] = P->workspace_max[a];
+  if (!apply_workspace_bounds(&ws, &mn, &mx)) return out;
+  const i3 lo = block_index_from_position(map->block_size, mn), hi = block_index_from_position(map->block_size, mx);
+  float T_C_L[16];
+  invert_isometry(T_L_C, T_C_L);
+  /* Camera::getNormalizedViewport(getViewportMargin(height)) (src/sensors/camera.cpp:85-96, view_calculator_impl.h:81-83) */
+  const float margin = (float)cam->height / 20.0f;
+  const v3 vmin = cam_vector_from_image_plane(cam, -margin, -margin);
+  const v3 vmax = cam_vector_from_image_plane(cam, (float)cam->width + margin, (float)cam->height + margin);
+  for (int x = lo.x; x <= hi.x; x++)
+    for (int y = lo.y; y <= hi.y; y++)
+      for (int z = lo.z; z <= hi.z; z++) { /* getBlockIndicesTouchedByBoundingBox order (bounding_boxes_impl.h:28-53) */
+        const i3 k = {x, y, z};
+        const v3 c_L = {map->block_size * ((float)x + 0.5f), map->block_size * ((float)y + 0.5f),
+                        map->block_size * ((float)z + 0.5f)}; /* getCenterPositionFromBlockIndex */
+        const v3 p = transform_point(T_C_L, c_L);
+        if (!(p.z > 1e-6f)) continue;
+        if (!(p.z >= 1e-6f)) continue; /* projectToNormalizedCoordinates (camera_impl.h:65-75) */
+        const float un = p.x / p.z, vn = p.y / p.z;
+        /* Eigen::AlignedBox::contains: (min <= p).all() && (p <= max).all() */
+        if (!(vmin.x <= un && vmin.y <= vn && un <= vmax.x && vn <= vmax.y)) continue;
+        const int32_t slot = hash_find(&map->tsdf.hash, k);
+        if (slot < 0) continue;
+        const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(&map->tsdf, slot);
+        int in_band = 0;
+        for (int v = 0; v < VPB && !in_band; v++)
+          if (t[v].weight > 0.0f && fabsf(t[v].distance) < truncation_distance_m) in_band = 1; /* checkBlocksInTruncationBand */
+        if (in_band) list_push(&out, k);
+      }
+  return out;
+}
+
+/* interpolatePixels<float> (interpolation_2d_impl.h:26-36) */
+static float interpolate_pixels_f(float x, float y, float f00, float f01, float f10, float f11) {
+  const float dx = f10 - f00;
+  return f00 + x * dx + y * (f01 - f00) + x * y * (f11 - f01 - dx);
+}
+
+static int32_t color_layer_allocate(Layer* l, i3 k) {
+  const int32_t before = l->n;
+  const int32_t slot = layer_allocate(l, k);
+  if (l->n != before) { /* ColorVoxel() : color(Color::Gray()), weight(0) (map/voxels.h:77-83) */
+    OrColorVoxel* v = (OrColorVoxel*)layer_block(l, slot);
+    for (int i = 0; i < VPB; i++) v[i].r = v[i].g = v[i].b = 127, v[i].pad = 0, v[i].weight = 0.0f;
+  }
+  return slot;
+}
+
+/* ProjectiveAppearanceIntegrator<ColorLayer>::integrateFrame (projective_appearance_integrator.cu:68-165): blocks in view and in
+ * the truncation band, a sphere-traced synthetic depth image for the occlusion test, then integrateBlocksKernel for
+ * appearance voxels (projective_integrator_impl.cuh:117-185) with UpdateAppearanceVoxelFunctor (:312-348).
+ * color = rows x cols x 3 bytes (RGB). Returns the number of updated blocks (copied to out_xyz up to cap). */
+int32_t or_color_integrate(OrMap* map, const uint8_t* color, const uint8_t* mask, int32_t mask_mode, int32_t rows, int32_t cols,
+                           const float* T_L_C, const OrCamera* cam, const OrColorParams* P, int32_t* out_xyz, int32_t cap) {
+  const float trunc = P->truncation_distance_vox * map->voxel_size;
+  List blocks = color_blocks_in_view_and_band(map, T_L_C, cam, P, trunc);
+  if (blocks.n == 0) {
+    list_free(&blocks);
+    return 0;
+  }
+  int32_t* slots = (int32_t*)malloc(sizeof(int32_t) * (size_t)blocks.n);
+  for (int32_t i = 0; i < blocks.n; i++) slots[i] = color_layer_allocate(&map->color, blocks.v[i]);
+  const int f = P->sphere_tracing_ray_subsampling_factor;
+  const int drows = cam->height / f, dcols = cam->width / f;
+  float* synth = (float*)malloc(sizeof(float) * (size_t)drows * dcols);
+  or_sphere_trace_image(map, T_L_C, cam, trunc, P->sphere_tracer_maximum_steps, P->sphere_tracer_maximum_ray_length_m,
+                        P->sphere_tracer_surface_distance_epsilon_vox * map->voxel_size, f, synth);
+  float T_C_L[16];
+  invert_isometry(T_L_C, T_C_L);
+  const int depth_subsample = rows / drows; /* projective_integrator_impl.cuh:320 */
+  const float voxel_size = map->block_size * (1.0f / VPS), half_voxel = map->block_size * (0.5f / VPS);
+  const float max_depth = P->max_integration_distance_m;
+  /* blendTwoArrays' weights (:287-306) are the same for every voxel */
+  float w_old = 1.0f - P->measurement_weight, w_new = P->measurement_weight;
+  const float total = w_old + w_new;
+  w_old /= total, w_new /= total;
+  const float w_old_h = round_through_half(w_old), w_new_h = round_through_half(w_new);
+#pragma omp parallel for schedule(static)
+  for (int32_t i = 0; i < blocks.n; i++) {
+    OrColorVoxel* blk = (OrColorVoxel*)layer_block(&map->color, slots[i]);
+    const i3 bi = blocks.v[i];
+    for (int vx = 0; vx < VPS; vx++)
+      for (int vy = 0; vy < VPS; vy++)
+        for (int vz = 0; vz < VPS; vz++) {
+          v3 p_L;
+          p_L.x = (map->block_size * (float)bi.x + voxel_size * (float)vx) + half_voxel;
+          p_L.y = (map->block_size * (float)bi.y + voxel_size * (float)vy) + half_voxel;
+          p_L.z = (map->block_size * (float)bi.z + voxel_size * (float)vz) + half_voxel;
+          const v3 p_C = transform_point(T_C_L, p_L);
+          float u, v;
+          if (!cam_project(cam, p_C, &u, &v)) continue;
+          const float voxel_depth = p_C.z;
+          if (max_depth > 0.0f && voxel_depth > max_depth) continue;
+          /* occlusion test against the synthetic depth (interpolate2DClosest on the subsampled image) */
+          const float ud = u / (float)depth_subsample, vd = v / (float)depth_subsample;
+          const int dx = f2i(floorf(ud)), dy = f2i(floorf(vd));
+          if (dx < 0 || dy < 0 || dx >= dcols || dy >= drows) continue;
+          const float surface_depth = synth[(size_t)dy * dcols + dx];
+          if (!(isfinite(surface_depth) && surface_depth > 1e-6f)) continue; /* PixelIsValidDepth */
+          if (fabsf(surface_depth - voxel_depth) > trunc) continue;
+          /* interpolate2DLinear<Color> (interpolation_2d_impl.h:152-199) */
+          const float ucx = u - 0.5f, ucy = v - 0.5f;
+          const int lx = f2i(floorf(ucx)), ly = f2i(floorf(ucy));
+          if (lx < 0 || ly < 0 || (lx + 1) > (cols - 1) || (ly + 1) > (rows - 1)) continue;
+          const float ox = ucx - (float)lx, oy = ucy - (float)ly;
+          const uint8_t* c00 = color + ((size_t)ly * cols + lx) * 3;
+          const uint8_t* c01 = color + ((size_t)(ly + 1) * cols + lx) * 3;
+          const uint8_t* c10 = color + ((size_t)ly * cols + lx + 1) * 3;
+          const uint8_t* c11 = color + ((size_t)(ly + 1) * cols + lx + 1) * 3;
+          uint8_t meas[3];
+          for (int ch = 0; ch < 3; ch++)
+            meas[ch] = (uint8_t)roundf(interpolate_pixels_f(ox, oy, (float)c00[ch], (float)c01[ch], (float)c10[ch], (float)c11[ch]));
+          /* isMasked(u_px.y(), u_px.x()): the float coordinates convert to int by truncation */
+          int is_active = 1;
+          if (mask != NULL) {
+            const uint8_t mv = mask[(size_t)(int)v * cols + (int)u];
+            is_active = (mask_mode == OR_MASK_NON_INVERTED) ? (mv != 0) : (mv == 0);
+          }
+          if (!is_active) continue;
+          OrColorVoxel* cv = &blk[(vx * VPS + vy) * VPS + vz];
+          const float weight_current = cv->weight;
+          if (round_through_half(cv->weight) == 0.0f) {
+            cv->r = meas[0], cv->g = meas[1], cv->b = meas[2];
+          } else {
+            uint8_t* cur[3] = {&cv->r, &cv->g, &cv->b};
+            for (int ch = 0; ch < 3; ch++) /* weightedSum(uint8_t, float, uint8_t, float) (:277-285) */
+              *cur[ch] = (uint8_t)roundf((float)*cur[ch] * w_old_h + (float)meas[ch] * w_new_h);
+          }
+          cv->weight = fminf(P->measurement_weight + weight_current, P->max_weight);
+        }
+  }
+  free(synth), free(slots);
+  const int32_t n = copy_out(&blocks, out_xyz, cap);
+  list_free(&blocks);
+  return n;
+}
+int32_t or_color_num_blocks(const OrMap* m) { return m->color.n; }
+int32_t or_color_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->color, out, cap); }
+int32_t or_color_get_block(const OrMap* m, const int32_t xyz[3], OrColorVoxel* out) {
+  const i3 k = {xyz[0], xyz[1], xyz[2]};
+  const int32_t s = hash_find(&m->color.hash, k);
+  if (s < 0) return 0;
+  memcpy(out, layer_block(&m->color, s), sizeof(OrColorVoxel) * VPB);
+  return 1;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Decay (integrators/internal/cuda/impl/decayer_impl.cuh)                   */
 /* ------------------------------------------------------------------------- */
 
@@ -1639,7 +1933,7 @@ static int32_t decay_layer(OrMap* map, int occupancy, const void* params, const 
     n_removed = copy_out(&rm, out_xyz, cap);
     layer_remove_blocks(L, rm.v, rm.n);
     if (clear_esdf == 1) layer_remove_blocks(&map->esdf, rm.v, rm.n);
-    if (clear_esdf) layer_remove_blocks(&map->freespace, rm.v, rm.n);
+    if (clear_esdf) layer_remove_blocks(&map->freespace, rm.v, rm.n), layer_remove_blocks(&map->color, rm.v, rm.n);
     if (clear_esdf == 2) {
       /* 2-D ESDF (src/mapper/mapper.cpp:569-626): a column's slice block goes when no projective block is left in the
        * vertical column within the slice bounds (the projective blocks were removed above) */

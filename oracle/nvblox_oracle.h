@@ -233,6 +233,36 @@ void or_esdf_integrate_slice(OrMap* map, int32_t from_occupancy, int32_t use_fre
 
 /* integrateSlice with a PlanarSliceDescription: plane = (nx, ny, nz, d), unit normal, n . p + d = 0
  * (slice_height_above_plane_m 0, slice_height_thickness_m 0.1 by default, esdf_integrator_params.h:45-52). */
+/* ColorVoxel (map/voxels.h:77-83): Color (3 bytes) + 1 byte padding + float weight. */
+typedef struct {
+  uint8_t r, g, b, pad;
+  float weight;
+} OrColorVoxel;
+/* ProjectiveColorIntegrator + its SphereTracer + its ViewCalculator (projective_appearance_integrator.h:150-175) */
+typedef struct {
+  float max_integration_distance_m;
+  float truncation_distance_vox;
+  float max_weight;
+  float measurement_weight;
+  int32_t sphere_tracing_ray_subsampling_factor;
+  int32_t sphere_tracer_maximum_steps;
+  float sphere_tracer_maximum_ray_length_m;
+  float sphere_tracer_surface_distance_epsilon_vox;
+  int32_t workspace_bounds_type;
+  float workspace_min[3], workspace_max[3];
+} OrColorParams;
+void or_default_color_params(OrColorParams* p);
+float or_round_through_half(float f);
+int32_t or_sphere_trace_ray(const OrMap* map, const float origin[3], const float direction[3], float truncation_distance_m,
+                            int32_t maximum_steps, float maximum_ray_length_m, float surface_distance_epsilon_m, float* t_out);
+void or_sphere_trace_image(const OrMap* map, const float* T_L_C, const OrCamera* cam, float truncation_distance_m,
+                           int32_t maximum_steps, float maximum_ray_length_m, float surface_distance_epsilon_m,
+                           int32_t ray_subsampling_factor, float* out);
+int32_t or_color_integrate(OrMap* map, const uint8_t* color, const uint8_t* mask, int32_t mask_mode, int32_t rows, int32_t cols,
+                           const float* T_L_C, const OrCamera* cam, const OrColorParams* P, int32_t* out_xyz, int32_t cap);
+int32_t or_color_num_blocks(const OrMap* m);
+int32_t or_color_block_indices(const OrMap* m, int32_t* out, int32_t cap);
+int32_t or_color_get_block(const OrMap* m, const int32_t xyz[3], OrColorVoxel* out);
 void or_planar_column_bounds(float block_size, const float plane[4], float above_plane_m, float thickness_m, int32_t bx, int32_t by,
                              int32_t vx, int32_t vy, int32_t out[4]);
 int32_t or_planar_num_blocks_in_column(float block_size, float thickness_m);

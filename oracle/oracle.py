@@ -85,6 +85,18 @@ class FreespaceParams(C.Structure):
                 ("check_neighborhood", C.c_int32), ("initialize_to_high_confidence_freespace", C.c_int32)]
 
 
+COLOR_VOXEL_DTYPE = np.dtype([("color", "u1", (3,)), ("pad", "u1"), ("weight", "<f4")])
+assert COLOR_VOXEL_DTYPE.itemsize == 8
+
+
+class ColorParams(C.Structure):
+    _fields_ = [("max_integration_distance_m", C.c_float), ("truncation_distance_vox", C.c_float),
+                ("max_weight", C.c_float), ("measurement_weight", C.c_float),
+                ("sphere_tracing_ray_subsampling_factor", C.c_int32), ("sphere_tracer_maximum_steps", C.c_int32),
+                ("sphere_tracer_maximum_ray_length_m", C.c_float), ("sphere_tracer_surface_distance_epsilon_vox", C.c_float),
+                ("workspace_bounds_type", C.c_int32), ("workspace_min", C.c_float * 3), ("workspace_max", C.c_float * 3)]
+
+
 class TsdfDecayParams(C.Structure):
     _fields_ = [("decay_factor", C.c_float), ("decayed_weight_threshold", C.c_float),
                 ("set_free_distance_on_decayed", C.c_int32), ("free_distance_vox", C.c_float),
@@ -168,6 +180,22 @@ def lib():
     L.or_esdf_integrate_slice_planar.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), fp, C.c_float,
                                                  C.c_float, C.c_float]
     L.or_esdf_integrate_slice_planar.restype = None
+    u8p = C.POINTER(C.c_uint8)
+    L.or_round_through_half.argtypes = [C.c_float]
+    L.or_round_through_half.restype = C.c_float
+    L.or_sphere_trace_ray.argtypes = [vp, fp, fp, C.c_float, C.c_int32, C.c_float, C.c_float, fp]
+    L.or_sphere_trace_ray.restype = C.c_int32
+    L.or_sphere_trace_image.argtypes = [vp, fp, C.POINTER(Camera), C.c_float, C.c_int32, C.c_float, C.c_float, C.c_int32, fp]
+    L.or_sphere_trace_image.restype = None
+    L.or_color_integrate.argtypes = [vp, u8p, u8p, C.c_int32, C.c_int32, C.c_int32, fp, C.POINTER(Camera),
+                                     C.POINTER(ColorParams), ip, C.c_int32]
+    L.or_color_integrate.restype = C.c_int32
+    L.or_color_num_blocks.argtypes = [vp]
+    L.or_color_num_blocks.restype = C.c_int32
+    L.or_color_block_indices.argtypes = [vp, ip, C.c_int32]
+    L.or_color_block_indices.restype = C.c_int32
+    L.or_color_get_block.argtypes = [vp, ip, vp]
+    L.or_color_get_block.restype = C.c_int32
     L.or_planar_column_bounds.argtypes = [C.c_float, fp, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, ip]
     L.or_planar_column_bounds.restype = None
     L.or_planar_num_blocks_in_column.argtypes = [C.c_float, C.c_float]
@@ -248,6 +276,18 @@ def default_freespace_params(**kw):
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def default_color_params(**kw):
+    p = ColorParams()
+    lib().or_default_color_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def round_through_half(f):
+    return float(lib().or_round_through_half(float(f)))
 
 
 def default_tsdf_decay_params(**kw):
@@ -443,6 +483,63 @@ class OracleMap:
             lib().or_freespace_get_block(self._h, _ip(np.ascontiguousarray(k, dtype=np.int32)), blk.ctypes.data)
             out[tuple(int(c) for c in k)] = blk
         return out
+
+    def integrate_color(self, color, T_L_C, cam, params=None, mask=None, mask_mode=0, cap=1 << 20):
+        """ProjectiveColorIntegrator::integrateFrame(color image (rows, cols, 3) uint8 RGB, T_L_C, camera, tsdf_layer,
+        color_layer, &updated_blocks) -> updated blocks."""
+        color = np.ascontiguousarray(color, dtype=np.uint8)
+        assert color.ndim == 3 and color.shape[2] == 3
+        params = params or default_color_params()
+        T = colmajor(T_L_C)
+        out = np.zeros((cap, 3), dtype=np.int32)
+        u8p = C.POINTER(C.c_uint8)
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            mp = mask.ctypes.data_as(u8p)
+        n = lib().or_color_integrate(self._h, color.ctypes.data_as(u8p), mp, mask_mode, color.shape[0], color.shape[1], _fp(T),
+                                     C.byref(cam), C.byref(params), _ip(out), cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def sphere_trace_image(self, T_L_C, cam, truncation_distance_m, maximum_steps=100, maximum_ray_length_m=15.0,
+                           surface_distance_epsilon_m=None, ray_subsampling_factor=1):
+        """SphereTracer::renderImageOnGPU -> (rows / f, cols / f) depth image, -1 where no surface was found."""
+        f = int(ray_subsampling_factor)
+        out = np.zeros((cam.height // f, cam.width // f), np.float32)
+        if surface_distance_epsilon_m is None:
+            surface_distance_epsilon_m = np.float32(0.1) * np.float32(self.voxel_size)  # sphere_tracer.h:218
+        T = colmajor(T_L_C)
+        lib().or_sphere_trace_image(self._h, _fp(T), C.byref(cam), float(truncation_distance_m), int(maximum_steps),
+                                    float(maximum_ray_length_m), float(surface_distance_epsilon_m), f, _fp(out))
+        return out
+
+    def sphere_trace_ray(self, origin, direction, truncation_distance_m, maximum_steps=100, maximum_ray_length_m=15.0,
+                         surface_distance_epsilon_m=None):
+        """SphereTracer::castOnGPU(ray, layer, truncation_distance_m, &t) -> (converged, t)."""
+        if surface_distance_epsilon_m is None:
+            surface_distance_epsilon_m = np.float32(0.1) * np.float32(self.voxel_size)
+        o = np.ascontiguousarray(origin, dtype=np.float32)
+        d = np.ascontiguousarray(direction, dtype=np.float32)
+        t = np.zeros(1, np.float32)
+        ok = lib().or_sphere_trace_ray(self._h, _fp(o), _fp(d), float(truncation_distance_m), int(maximum_steps),
+                                       float(maximum_ray_length_m), float(surface_distance_epsilon_m), _fp(t))
+        return bool(ok), float(t[0])
+
+    def color_block_indices(self):
+        n = lib().or_color_num_blocks(self._h)
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        lib().or_color_block_indices(self._h, _ip(out), n)
+        return out[:n].copy()
+
+    def color_block(self, idx):
+        k = np.asarray(idx, dtype=np.int32)
+        out = np.zeros((8, 8, 8), dtype=COLOR_VOXEL_DTYPE)
+        ok = lib().or_color_get_block(self._h, _ip(k), out.ctypes.data)
+        return out if ok else None
+
+    def color_layer(self):
+        return {tuple(int(c) for c in k): self.color_block(k) for k in self.color_block_indices()}
 
     def integrate_esdf_slice(self, blocks, params=None, z_min_m=0.0, z_max_m=1.0, z_output_m=1.0, from_occupancy=False,
                              use_freespace=False):

@@ -134,28 +134,75 @@ def check_slicing_sites(esdf_layer, exp):
         assert np.array_equal(got, want), (idx, np.argwhere(got != want))
 
 
-def sphere_scene_tsdf_layer(voxel_size=0.05, truncation_m=0.2):
-    """Scene::generateLayerFromScene (primitives/internal/impl/scene_impl.h:100-140) for the sphere-in-a-box scene of the
-    TestScene case (:485-500): every voxel of the AABB gets the truncated ground-truth distance and weight 1."""
-    scene = syn.sphere_in_box()
-    bs = 8 * voxel_size
-    lo = [int(np.floor(-5.0 / bs)), int(np.floor(-5.0 / bs)), 0]  # getBlockIndicesTouchedByBoundingBox
-    hi = [int(np.floor(5.0 / bs)), int(np.floor(5.0 / bs)), int(np.floor(5.0 / bs))]
-    ax = [(np.arange(8 * (h - l + 1)) + 0.5) * voxel_size + l * bs for l, h in zip(lo, hi)]
+def tsdf_layer_from_distance(distance_fn, aabb_min, aabb_max, voxel_size, truncation_m):
+    """Scene::generateLayerFromScene (primitives/internal/impl/scene_impl.h:105-140): the blocks touched by the AABB are
+    allocated; every voxel whose centre lies in the AABB gets the ground-truth distance clipped to +-truncation and
+    weight 1, the others stay unset. distance_fn maps (..., 3) float64 points to signed distances.
+    -> (block indices (n, 3) int32, voxels (n, 8, 8, 8) TSDF_DT)."""
+    bs = np.float32(8) * np.float32(voxel_size)
+    lo = [int(np.floor(np.float32(a) / bs)) for a in aabb_min]  # getBlockIndicesTouchedByBoundingBox
+    hi = [int(np.floor(np.float32(a) / bs)) for a in aabb_max]
+    ax = [(np.arange(8 * (h - l + 1)) + 0.5) * float(voxel_size) + l * float(bs) for l, h in zip(lo, hi)]
     P = np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1)
-    D = np.clip(scene.distance(P), -truncation_m, truncation_m).astype(np.float32)
-    inside = np.all((P >= (-5.0, -5.0, 0.0)) & (P <= (5.0, 5.0, 5.0)), axis=-1)  # voxels outside the AABB stay unset
-    idx, vox = [], []
-    for bx in range(hi[0] - lo[0] + 1):
-        for by in range(hi[1] - lo[1] + 1):
-            for bz in range(hi[2] - lo[2] + 1):
-                sl = (slice(8 * bx, 8 * bx + 8), slice(8 * by, 8 * by + 8), slice(8 * bz, 8 * bz + 8))
-                b = np.zeros((8, 8, 8), TSDF_DT)
-                b["distance"] = np.where(inside[sl], D[sl], 0.0)
-                b["weight"] = np.where(inside[sl], 1.0, 0.0)
-                idx.append((bx + lo[0], by + lo[1], bz + lo[2]))
-                vox.append(b)
-    return np.asarray(idx, np.int32), np.stack(vox)
+    D = np.clip(distance_fn(P), -truncation_m, truncation_m).astype(np.float32)
+    inside = np.all((P >= np.asarray(aabb_min, float)) & (P <= np.asarray(aabb_max, float)), axis=-1)
+    D = np.where(inside, D, np.float32(0.0)).astype(np.float32)
+    W = inside.astype(np.float32)
+    n = [h - l + 1 for l, h in zip(lo, hi)]
+    vox = np.zeros((n[0], n[1], n[2], 8, 8, 8), TSDF_DT)
+    vox["distance"] = D.reshape(n[0], 8, n[1], 8, n[2], 8).transpose(0, 2, 4, 1, 3, 5)
+    vox["weight"] = W.reshape(n[0], 8, n[1], 8, n[2], 8).transpose(0, 2, 4, 1, 3, 5)
+    gx, gy, gz = np.meshgrid(np.arange(lo[0], hi[0] + 1), np.arange(lo[1], hi[1] + 1), np.arange(lo[2], hi[2] + 1), indexing="ij")
+    idx = np.stack([gx, gy, gz], axis=-1).reshape(-1, 3).astype(np.int32)
+    return idx, vox.reshape(-1, 8, 8, 8)
+
+
+def sphere_in_box_signed_distance(P):
+    """Scene::getSignedDistanceToPoint for the sphere-in-a-box scene of the reference's tests (ground 0, ceiling 5, walls at
+    +-5 with inward normals, sphere r = 2 at (0, 0, 2)): the minimum of the primitives' signed distances, negative behind
+    a wall and inside the sphere."""
+    P = np.asarray(P, np.float64)
+    x, y, z = P[..., 0], P[..., 1], P[..., 2]
+    d = np.minimum.reduce([z, 5.0 - z, x + 5.0, 5.0 - x, y + 5.0, 5.0 - y])
+    return np.minimum(d, np.linalg.norm(P - (0.0, 0.0, 2.0), axis=-1) - 2.0)
+
+
+def sphere_scene_tsdf_layer(voxel_size=0.05, truncation_m=0.2):
+    return tsdf_layer_from_distance(sphere_in_box_signed_distance, (-5.0, -5.0, 0.0), (5.0, 5.0, 5.0), voxel_size, truncation_m)
+
+
+def spheres_distance(centers, radius):
+    def fn(P):
+        return np.min([np.linalg.norm(P - np.asarray(c, float), axis=-1) - radius for c in centers], axis=0)
+    return fn
+
+
+def points_on_a_sphere(radius, center, points_per_rad=10):
+    """getPointsOnASphere (tests/test_color_integrator.cpp:88-107)."""
+    pts = []
+    for a in range(2 * points_per_rad):
+        for e in range(points_per_rad):
+            az = a * np.pi / points_per_rad - np.pi
+            el = e * np.pi / points_per_rad - np.pi / 2.0
+            pts.append(radius * np.array([np.cos(az) * np.sin(el), np.sin(az) * np.sin(el), np.cos(el)]) + np.asarray(center, float))
+    return np.asarray(pts, np.float32)
+
+
+def voxel_at_position(layer, p, voxel_size):
+    """getVoxelAtPosition on a {block index: (8, 8, 8) array} layer -> the voxel record or None."""
+    bs = np.float32(8) * np.float32(voxel_size)
+    p = np.asarray(p, np.float32)
+    b = np.floor(p / bs).astype(int)
+    v = np.minimum(((p - bs * b.astype(np.float32)) * np.float32(1.0 / (float(bs) / 8))).astype(int), 7)
+    blk = layer.get(tuple(int(c) for c in b))
+    return None if blk is None else blk[v[0], v[1], v[2]]
+
+
+def rotation_y(angle):
+    c, s = np.cos(angle), np.sin(angle)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32)
+    return T
 
 
 def check_sphere_scene_slice(esdf_layer, planar, voxel_size=0.05):
