@@ -58,5 +58,6 @@ class VoxelBlockLayer {
 using TsdfLayer = VoxelBlockLayer<TsdfVoxel>;
 using OccupancyLayer = VoxelBlockLayer<OccupancyVoxel>;
 using FreespaceLayer = VoxelBlockLayer<FreespaceVoxel>;
+using ColorLayer = VoxelBlockLayer<ColorVoxel>;
 using EsdfLayer = VoxelBlockLayer<EsdfVoxel>;
 }  // namespace nvblox

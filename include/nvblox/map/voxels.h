@@ -1,4 +1,4 @@
-// nvblox/map/voxels.h -- TsdfVoxel / OccupancyVoxel / FreespaceVoxel / EsdfVoxel with the reference's layout
+// nvblox/map/voxels.h -- TsdfVoxel / OccupancyVoxel / FreespaceVoxel / ColorVoxel / EsdfVoxel with the reference's layout
 // (nvblox/include/nvblox/map/voxels.h:28-74); these are the bytes stored in HBM.
 #pragma once
 #include <cstdint>
@@ -18,6 +18,23 @@ struct FreespaceVoxel {
   Time consecutive_occupancy_duration_ms = 0;
   bool is_high_confidence_freespace = false;
 };
+// Color (core/color.h:28-68): three bytes, RGB.
+struct Color {
+  uint8_t r = 0, g = 0, b = 0;
+  Color() = default;
+  Color(uint8_t r_, uint8_t g_, uint8_t b_) : r(r_), g(g_), b(b_) {}
+  bool operator==(const Color& o) const { return r == o.r && g == o.g && b == o.b; }
+  static Color Gray() { return Color(127, 127, 127); }
+  static Color Red() { return Color(255, 0, 0); }
+  static Color Green() { return Color(0, 255, 0); }
+  static Color Blue() { return Color(0, 0, 255); }
+  static Color White() { return Color(255, 255, 255); }
+  static Color Black() { return Color(0, 0, 0); }
+};
+struct ColorVoxel {
+  Color color = Color::Gray();
+  float weight = 0.0f;
+};
 struct EsdfVoxel {
   float squared_distance_vox = 0.0f;
   Index3D parent_direction = Index3D::Zero();
@@ -29,4 +46,5 @@ static_assert(sizeof(TsdfVoxel) == 8, "TsdfVoxel layout");
 static_assert(sizeof(OccupancyVoxel) == 4, "OccupancyVoxel layout");
 static_assert(sizeof(FreespaceVoxel) == 24, "FreespaceVoxel layout");
 static_assert(sizeof(EsdfVoxel) == 20, "EsdfVoxel layout");
+static_assert(sizeof(Color) == 3 && sizeof(ColorVoxel) == 8, "ColorVoxel layout");
 }  // namespace nvblox

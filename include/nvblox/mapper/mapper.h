@@ -99,6 +99,28 @@ class ProjectiveOccupancyIntegrator {
   NvbMapper* m_;
 };
 
+// ProjectiveColorIntegrator (integrators/projective_appearance_integrator.h:44-194): parameters; integrateFrame is reached
+// through Mapper::integrateColor (the integrator reads the mapper's TSDF layer and writes its colour layer).
+class ProjectiveColorIntegrator {
+ public:
+  explicit ProjectiveColorIntegrator(NvbMapper* m) : m_(m) {}
+  float max_integration_distance_m() const { return get().max_integration_distance_m; }
+  void max_integration_distance_m(float v) { auto p = get(); p.max_integration_distance_m = v; set(p); }
+  float truncation_distance_vox() const { return get().truncation_distance_vox; }
+  void truncation_distance_vox(float v) { auto p = get(); p.truncation_distance_vox = v; set(p); }
+  float get_truncation_distance_m(float voxel_size) const { return get().truncation_distance_vox * voxel_size; }
+  float max_weight() const { return get().max_weight; }
+  void max_weight(float v) { auto p = get(); p.max_weight = v; set(p); }
+  float measurement_weight() const { return get().measurement_weight; }
+  void measurement_weight(float v) { auto p = get(); p.measurement_weight = v; set(p); }
+  int sphere_tracing_ray_subsampling_factor() const { return get().sphere_tracing_ray_subsampling_factor; }
+  void sphere_tracing_ray_subsampling_factor(int v) { auto p = get(); p.sphere_tracing_ray_subsampling_factor = v; set(p); }
+ private:
+  NvbColorParams get() const { NvbColorParams p; b200_detail::check(nvb_mapper_get_color_params(m_, &p), "color params", nvb_last_error()); return p; }
+  void set(const NvbColorParams& p) { b200_detail::check(nvb_mapper_set_color_params(m_, &p), "color params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+
 // FreespaceIntegrator (integrators/freespace_integrator.h:36-175): parameters + updateFreespaceLayer on a block list.
 class FreespaceIntegrator {
  public:
@@ -244,6 +266,20 @@ class Mapper {
     // Mapper::integrateDepth dispatches on the projective layer type (mapper_impl.h:28-81)
     b200_detail::integrateFrame(m_, depth_frame, T_L_C, camera, nullptr);
   }
+  // Mapper::integrateColor (mapper.h:202-207, mapper_impl.h:104-130)
+  void integrateColor(const ColorImage& color_frame, const Transform& T_L_C, const Camera& camera) {
+    integrateColor(MaskedColorImageConstView(color_frame, kMaskActiveEverywhere), T_L_C, camera);
+  }
+  void integrateColor(const MaskedColorImageConstView& color_frame, const Transform& T_L_C, const Camera& camera) {
+    const MonoImageConstView& mask = color_frame.mask();
+    b200_detail::check(nvb_mapper_integrate_color(m_, reinterpret_cast<const uint8_t*>(color_frame.dataConstPtr()), mask.dataConstPtr(),
+                                                  color_frame.mode() == MaskMode::kInverted ? NVB_MASK_INVERTED : NVB_MASK_NON_INVERTED,
+                                                  color_frame.on_device() ? NVB_MEM_DEVICE : NVB_MEM_HOST, color_frame.rows(),
+                                                  color_frame.cols(), T_L_C.data(), camera.c_abi(), nullptr, 0, nullptr),
+                       "integrateColor", nvb_last_error());
+  }
+  ColorLayer color_layer() const { return ColorLayer(m_, NVB_LAYER_COLOR); }
+  ProjectiveColorIntegrator color_integrator() const { return ProjectiveColorIntegrator(m_); }
   void updateEsdf(UpdateFullLayer full = UpdateFullLayer::kNo) {
     b200_detail::check(nvb_mapper_update_esdf(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdf", nvb_last_error());
   }

@@ -4,6 +4,7 @@
 #include <optional>
 #include <vector>
 #include "nvblox/core/types.h"
+#include "nvblox/map/voxels.h"
 #include "nvblox_b200.h"
 namespace nvblox {
 enum class MaskMode { kNonInverted, kInverted };
@@ -31,6 +32,7 @@ class Image {
 };
 using DepthImage = Image<float>;
 using MonoImage = Image<uint8_t>;
+using ColorImage = Image<Color>;  // 3 bytes per pixel, RGB (sensors/image.h:442)
 
 template <typename T>
 class ImageView {
@@ -49,6 +51,7 @@ class ImageView {
 };
 using DepthImageConstView = ImageView<float>;
 using MonoImageConstView = ImageView<uint8_t>;
+using ColorImageConstView = ImageView<Color>;
 
 class MaskedDepthImageConstView : public DepthImageConstView {
  public:
@@ -61,6 +64,25 @@ class MaskedDepthImageConstView : public DepthImageConstView {
     }
   }
   MaskedDepthImageConstView(const DepthImage& image, std::nullopt_t) : DepthImageConstView(image) {}
+  const MonoImageConstView& mask() const { return mask_; }
+  MaskMode mode() const { return mode_; }
+ private:
+  MonoImageConstView mask_;
+  MaskMode mode_ = MaskMode::kNonInverted;
+};
+
+// MaskedImageView<const Color> (sensors/image.h:389-438)
+class MaskedColorImageConstView : public ColorImageConstView {
+ public:
+  MaskedColorImageConstView(const ColorImageConstView& image, std::optional<MonoImageConstView> mask = std::nullopt,
+                            MaskMode mode = MaskMode::kNonInverted)
+      : ColorImageConstView(image), mode_(mode) {
+    if (mask.has_value()) {
+      if (mask->rows() != image.rows() || mask->cols() != image.cols()) b200_detail::check(-1, "MaskedImageView", "mask/image size mismatch");
+      mask_ = *mask;
+    }
+  }
+  MaskedColorImageConstView(const ColorImage& image, std::nullopt_t) : ColorImageConstView(image) {}
   const MonoImageConstView& mask() const { return mask_; }
   MaskMode mode() const { return mode_; }
  private:

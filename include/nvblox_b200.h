@@ -60,7 +60,7 @@ typedef enum {
 typedef enum { NVB_MEM_HOST = 0, NVB_MEM_DEVICE = 1 } NvbMemory;
 
 /* Layers of the map (C/include/nvblox/map/common_names.h TsdfLayer / EsdfLayer). */
-typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1, NVB_LAYER_OCCUPANCY = 2, NVB_LAYER_FREESPACE = 3 } NvbLayer;
+typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1, NVB_LAYER_OCCUPANCY = 2, NVB_LAYER_FREESPACE = 3, NVB_LAYER_COLOR = 4 } NvbLayer;
 
 /* ProjectiveLayerType of a Mapper (C/include/nvblox/mapper/mapper.h:40-48): which layer integrateDepth feeds. */
 typedef enum {
@@ -147,6 +147,13 @@ typedef struct {
   int64_t consecutive_occupancy_duration_ms;
   uint8_t is_high_confidence_freespace, pad_[7];
 } NvbFreespaceVoxel;
+
+/* ColorVoxel (C/include/nvblox/map/voxels.h:77-83): Color = 3 bytes RGB (core/color.h:28-68), one byte of padding, float weight.
+ * A freshly allocated block holds ColorVoxel() = Color::Gray() (127, 127, 127), weight 0. */
+typedef struct {
+  uint8_t r, g, b, pad_;
+  float weight;
+} NvbColorVoxel;
 
 /* Construction options. capacity = number of 8x8x8 blocks each layer's slab is
  * sized for up front (it grows by doubling, which is a synchronising event;
@@ -269,6 +276,45 @@ NVB_API int32_t nvb_view_raycast(NvbMapper* m, const float* depth, int32_t depth
                                  float max_integration_distance_behind_surface_m,
                                  float max_integration_distance_m, int32_t* out_xyz_host,
                                  int32_t cap, int32_t* out_count);
+
+/* ProjectiveColorIntegrator's parameters (C/include/nvblox/integrators/projective_appearance_integrator.h:96-175,
+ * projective_integrator_params.h:24-75), with those of its SphereTracer (rays/sphere_tracer.h:204-218) and of its own
+ * ViewCalculator's workspace bounds. sphere_tracer_maximum_ray_length_m is a separate field because the reference
+ * copies max_integration_distance_m into the tracer in the constructor only
+ * (src/integrators/projective_appearance_integrator.cu:61). */
+typedef struct {
+  float max_integration_distance_m;                 /* 7.0 */
+  float truncation_distance_vox;                    /* 4.0 */
+  float max_weight;                                 /* 5.0 */
+  float measurement_weight;                         /* 0.8, in (0, 1] */
+  int32_t sphere_tracing_ray_subsampling_factor;    /* 4; must divide the image size */
+  int32_t sphere_tracer_maximum_steps;              /* 100 */
+  float sphere_tracer_maximum_ray_length_m;         /* 7.0 */
+  float sphere_tracer_surface_distance_epsilon_vox; /* 0.1 */
+  int32_t workspace_bounds_type;                    /* NVB_WS_UNBOUNDED */
+  float workspace_min[3], workspace_max[3];
+} NvbColorParams;
+NVB_API void nvb_default_color_params(NvbColorParams* p);
+NVB_API int32_t nvb_mapper_set_color_params(NvbMapper* m, const NvbColorParams* p);
+NVB_API int32_t nvb_mapper_get_color_params(const NvbMapper* m, NvbColorParams* p);
+
+/* Mapper::integrateColor(MaskedColorImageConstView, T_L_C, Camera) (mapper.h:202-207, mapper_impl.h:104-130) =
+ * ProjectiveColorIntegrator::integrateFrame (src/integrators/projective_appearance_integrator.cu:68-165): the TSDF blocks
+ * in the camera's view (ViewCalculator::getBlocksInImageViewProjection) that touch the truncation band get a colour block;
+ * a sphere-traced synthetic depth image of the TSDF layer (SphereTracer::renderImageOnGPU) decides occlusion; visible voxels
+ * blend the bilinearly interpolated pixel in (UpdateAppearanceVoxelFunctor). color = rows * cols * 3 bytes, RGB, row-major;
+ * mask (rows * cols, may be NULL) and mask_mode as for depth. With an occupancy mapper the call does nothing, as in the
+ * reference. updated_xyz_host may be NULL; otherwise it receives up to cap triples of `updated_blocks` (unordered) and
+ * *out_count the full count. */
+NVB_API int32_t nvb_mapper_integrate_color(NvbMapper* m, const uint8_t* color, const uint8_t* mask, int32_t mask_mode,
+                                           int32_t memory, int32_t rows, int32_t cols, const float* T_L_C,
+                                           const NvbCamera* cam, int32_t* updated_xyz_host, int32_t cap, int32_t* out_count);
+/* SphereTracer::renderImageOnGPU(camera, T_L_C, tsdf_layer, truncation_distance_m, &depth, ..., ray_subsampling_factor)
+ * (C/src/rays/sphere_tracer.cu:389-485) with the colour integrator's tracer settings: out_depth_host receives
+ * (height / f) * (width / f) floats, -1 where a ray found no surface. */
+NVB_API int32_t nvb_sphere_tracer_render_depth(NvbMapper* m, const float* T_L_C, const NvbCamera* cam,
+                                               float truncation_distance_m, int32_t ray_subsampling_factor,
+                                               float* out_depth_host);
 
 /* Mapper::integrateDepth(MaskedDepthImageConstView, T_L_C, Camera)
  * (mapper.h:167-172, mapper_impl.h:28-81) =

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnvblox_b200.so")
 
 NVB_OK = 0
 NVB_MEM_HOST, NVB_MEM_DEVICE = 0, 1
-NVB_LAYER_TSDF, NVB_LAYER_ESDF, NVB_LAYER_OCCUPANCY, NVB_LAYER_FREESPACE = 0, 1, 2, 3
+NVB_LAYER_TSDF, NVB_LAYER_ESDF, NVB_LAYER_OCCUPANCY, NVB_LAYER_FREESPACE, NVB_LAYER_COLOR = 0, 1, 2, 3, 4
 NVB_PROJECTIVE_TSDF, NVB_PROJECTIVE_OCCUPANCY, NVB_PROJECTIVE_TSDF_WITH_FREESPACE = 0, 1, 2
 
 # Every symbol include/nvblox_b200.h declares (checked by tests/test_cabi_symbols.py).
@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = [
     "nvb_mapper_get_occupancy_decay_params", "nvb_mapper_decay", "nvb_mapper_decay_exclude_last_view",
     "nvb_default_freespace_params", "nvb_mapper_set_freespace_params", "nvb_mapper_get_freespace_params",
     "nvb_mapper_update_freespace", "nvb_freespace_update_blocks",
+    "nvb_default_color_params", "nvb_mapper_set_color_params", "nvb_mapper_get_color_params",
+    "nvb_mapper_integrate_color", "nvb_sphere_tracer_render_depth",
     "nvb_default_esdf_slice_params", "nvb_mapper_set_esdf_slice_params", "nvb_mapper_get_esdf_slice_params",
     "nvb_mapper_update_esdf_slice", "nvb_esdf_integrate_slice_blocks", "nvb_esdf_slice_distance_image",
     "nvb_mapper_update_esdf_slice_planar", "nvb_esdf_integrate_slice_planar_blocks",
@@ -79,6 +81,14 @@ class NvbOccupancyParams(C.Structure):
 class NvbEsdfSliceParams(C.Structure):
     _fields_ = [("slice_min_height_m", C.c_float), ("slice_max_height_m", C.c_float), ("slice_height_m", C.c_float),
                 ("slice_height_above_plane_m", C.c_float), ("slice_height_thickness_m", C.c_float)]
+
+
+class NvbColorParams(C.Structure):
+    _fields_ = [("max_integration_distance_m", C.c_float), ("truncation_distance_vox", C.c_float),
+                ("max_weight", C.c_float), ("measurement_weight", C.c_float),
+                ("sphere_tracing_ray_subsampling_factor", C.c_int32), ("sphere_tracer_maximum_steps", C.c_int32),
+                ("sphere_tracer_maximum_ray_length_m", C.c_float), ("sphere_tracer_surface_distance_epsilon_vox", C.c_float),
+                ("workspace_bounds_type", C.c_int32), ("workspace_min", C.c_float * 3), ("workspace_max", C.c_float * 3)]
 
 
 class NvbFreespaceParams(C.Structure):
@@ -162,6 +172,12 @@ def load():
     L.nvb_mapper_update_esdf_slice_planar.argtypes = [vp, fp, i32]
     L.nvb_esdf_integrate_slice_planar_blocks.argtypes = [vp, fp, ip, i32]
     L.nvb_esdf_slice_distance_image.argtypes = [vp, f32, f32, fp, fp, C.POINTER(C.c_int8), i32, ip, ip]
+    L.nvb_default_color_params.argtypes = [C.POINTER(NvbColorParams)]
+    L.nvb_default_color_params.restype = None
+    L.nvb_mapper_set_color_params.argtypes = [vp, C.POINTER(NvbColorParams)]
+    L.nvb_mapper_get_color_params.argtypes = [vp, C.POINTER(NvbColorParams)]
+    L.nvb_mapper_integrate_color.argtypes = [vp, vp, vp, i32, i32, i32, i32, fp, C.POINTER(NvbCamera), ip, i32, ip]
+    L.nvb_sphere_tracer_render_depth.argtypes = [vp, fp, C.POINTER(NvbCamera), f32, i32, fp]
     L.nvb_default_freespace_params.argtypes = [C.POINTER(NvbFreespaceParams)]
     L.nvb_default_freespace_params.restype = None
     L.nvb_mapper_set_freespace_params.argtypes = [vp, C.POINTER(NvbFreespaceParams)]

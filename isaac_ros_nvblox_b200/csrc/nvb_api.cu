@@ -69,6 +69,17 @@ struct NvbMapper {
 
   DevLayer tsdf{}, esdf{};
   DevLayer freespace{};    // FreespaceLayer of a NVB_PROJECTIVE_TSDF_WITH_FREESPACE mapper
+  DevLayer color{};        // ColorLayer, created by the first nvb_mapper_integrate_color
+  NvbColorParams cp{};
+  int4* color_work = nullptr;  // blocks of the last colour frame {x, y, z, colour slot}
+  int color_work_cap = 0;
+  float* color_synth = nullptr;  // sphere-traced synthetic depth
+  size_t color_synth_cap = 0;
+  unsigned char* color_stage = nullptr;  // host colour image / mask staged on the device
+  size_t color_stage_cap = 0;
+  unsigned char* color_mask_stage = nullptr;
+  size_t color_mask_stage_cap = 0;
+  int color_last_count = 0;
   NvbFreespaceParams fp;
   NvbEsdfSliceParams sp;
   int esdf_mode = 0;                // EsdfMode: 0 unset, 1 3-D, 2 2-D slice (mapper.h:61, src/mapper/mapper.cpp:408-470)
@@ -328,7 +339,7 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kNumInts = 32 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kColorWorkCount = 31, kNumInts = 32 };
 
 float logOddsFromProbability(float p);
 
@@ -941,6 +952,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   nvb_default_occupancy_decay_params(&m->odp);
   nvb_default_freespace_params(&m->fp);
   nvb_default_esdf_slice_params(&m->sp);
+  nvb_default_color_params(&m->cp);
   m->projective_layer_type = opts->projective_layer_type;
   m->keep_last_view = opts->keep_last_view ? 1 : 0;
   m->esdf_persistent = opts->esdf_persistent;
@@ -1005,6 +1017,8 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaStreamDestroy(m->esdf_stream);
   freeLayer(&m->tsdf), freeLayer(&m->esdf);
   if (m->freespace.blocks) freeLayer(&m->freespace);
+  if (m->color.blocks) freeLayer(&m->color);
+  cudaFree(m->color_work), cudaFree(m->color_synth), cudaFree(m->color_stage), cudaFree(m->color_mask_stage);
   cudaFree(m->dirty_fs), cudaFree(m->todo_fs_slots), cudaFree(m->fs_work), cudaFree(m->colset), cudaFree(m->cols);
   cudaFree(m->bits), cudaFree(m->frame_blocks), cudaFree(m->tile_state), cudaFree(m->ticket);
   for (int k = 0; k < kStagingBuffers; k++) {
@@ -1030,6 +1044,7 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(syncAll(m));
   std::vector<DevLayer*> layers = {&m->tsdf, &m->esdf};
   if (m->freespace.blocks) layers.push_back(&m->freespace);
+  if (m->color.blocks) layers.push_back(&m->color);
   for (DevLayer* L : layers) {
     int count = 0;
     NVB_CUDA(cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1277,6 +1292,10 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
       launchRemoveBlocks(m->freespace, m->dead, a.dead_count, n_dead, m->stream);
       touched.push_back(&m->freespace);
     }
+    if (m->color.blocks) {
+      launchRemoveBlocks(m->color, m->dead, a.dead_count, n_dead, m->stream);
+      touched.push_back(&m->color);
+    }
     for (DevLayer* L : touched) {
       int hw = 0;
       NVB_CUDA(cudaMemcpyAsync(&hw, L->count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -1487,6 +1506,237 @@ int32_t nvb_mapper_integrate_depth_async(NvbMapper* m, const float* depth, const
   const float trunc_m = m->tp.truncation_distance_vox * m->voxel_size;
   return enqueueFrame(m, depth, mask, mask_mode, memory, rows, cols, T_L_C, cam, m->block_size, trunc_m,
                       m->tp.max_integration_distance_m, true);
+}
+
+// ---------------------------------------------------------------------------
+// Colour integration (nvb_color.cu)
+// ---------------------------------------------------------------------------
+void nvb_default_color_params(NvbColorParams* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  // integrators/projective_integrator_params.h:24-75, projective_appearance_integrator.h:164, rays/sphere_tracer.h:216-218
+  p->max_integration_distance_m = 7.0f;
+  p->truncation_distance_vox = 4.0f;
+  p->max_weight = 5.0f;
+  p->measurement_weight = 0.8f;
+  p->sphere_tracing_ray_subsampling_factor = 4;
+  p->sphere_tracer_maximum_steps = 100;
+  p->sphere_tracer_maximum_ray_length_m = 7.0f;
+  p->sphere_tracer_surface_distance_epsilon_vox = 0.1f;
+  p->workspace_bounds_type = NVB_WS_UNBOUNDED;
+}
+int32_t nvb_mapper_set_color_params(NvbMapper* m, const NvbColorParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  // the reference's setters CHECK these (projective_appearance_integrator.cu:168-208, projective_integrator.cpp setters)
+  if (!(p->max_integration_distance_m > 0.0f) || !(p->truncation_distance_vox > 0.0f) || !(p->max_weight > 0.0f) ||
+      !(p->measurement_weight > 0.0f) || !(p->measurement_weight <= 1.0f) || p->sphere_tracing_ray_subsampling_factor <= 0 ||
+      p->sphere_tracer_maximum_steps <= 0 || !(p->sphere_tracer_maximum_ray_length_m > 0.0f) ||
+      !(p->sphere_tracer_surface_distance_epsilon_vox > 0.0f))
+    return fail(NVB_ERR_INVALID_ARGUMENT, "colour integrator parameter out of range");
+  m->cp = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_color_params(const NvbMapper* m, NvbColorParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->cp;
+  return NVB_OK;
+}
+
+namespace {
+// binary32 -> binary16 -> binary32, round to nearest even (__float2half followed by the implicit __half -> float)
+float roundThroughHalf(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = x & 0x80000000u, ax = x & 0x7fffffffu;
+  uint32_t out;
+  if (ax >= 0x7f800000u) {
+    out = ax;
+  } else if (ax >= 0x477ff000u) {
+    out = 0x7f800000u;
+  } else if (ax < 0x38800000u) {
+    const float r = std::nearbyint(std::fabs(f) * 16777216.0f) * (1.0f / 16777216.0f);
+    memcpy(&out, &r, 4);
+  } else {
+    out = (ax + 0x0fffu + ((ax >> 13) & 1u)) & 0xffffe000u;
+  }
+  out |= sign;
+  float r;
+  memcpy(&r, &out, 4);
+  return r;
+}
+
+int ensureColorLayer(NvbMapper* m) {
+  int rc;
+  if (!m->color.blocks) {
+    if ((rc = allocLayer(&m->color, m->tsdf.capacity, kColorBlockBytes, m->stream))) return rc;
+  } else if (m->color.capacity < m->tsdf.capacity) {
+    if ((rc = growLayer(m, &m->color, m->tsdf.capacity))) return rc;
+  }
+  if (m->color_work_cap < m->tsdf.capacity) {
+    NVB_CUDA(syncAll(m));
+    if (m->color_work) cudaFree(m->color_work);
+    NVB_CUDA(cudaMalloc(&m->color_work, (size_t)m->tsdf.capacity * sizeof(int4)));
+    m->color_work_cap = m->tsdf.capacity;
+  }
+  return NVB_OK;
+}
+
+// The tracer's half of ColorArgs + the launch. synth must hold (height / f) * (width / f) floats.
+int fillTracerArgs(NvbMapper* m, ColorArgs* a, const float* T_L_C_cm, const NvbCamera* cam, float trunc_m, int f) {
+  if (f <= 0 || cam->width % f != 0 || cam->height % f != 0)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "the ray subsampling factor must divide the image size");  // CHECK_EQ, sphere_tracer.cu:432-433
+  a->tsdf = m->tsdf;
+  a->T_L_C = rigidFromColMajor(T_L_C_cm);
+  a->T_C_L = invertRigid(a->T_L_C);
+  a->cam = *cam;
+  a->block_size = m->block_size;
+  a->voxel_size = m->block_size * (1.0f / kVps);
+  a->half_voxel_size = m->block_size * (0.5f / kVps);
+  a->voxel_size_inv = (float)(1.0 / (double)(m->block_size * (1.0f / kVps)));  // indexing_impl.h:41
+  a->trunc_m = trunc_m;
+  a->subsample = f;
+  a->drows = cam->height / f, a->dcols = cam->width / f;  // getSubsampledImageSize (sphere_tracer.cu:335-339)
+  a->max_steps = m->cp.sphere_tracer_maximum_steps;
+  a->max_ray_len = m->cp.sphere_tracer_maximum_ray_length_m;
+  a->eps_m = m->cp.sphere_tracer_surface_distance_epsilon_vox * m->voxel_size;
+  const size_t need = (size_t)a->drows * a->dcols;
+  if (m->color_synth_cap < need) {
+    NVB_CUDA(syncAll(m));
+    if (m->color_synth) cudaFree(m->color_synth);
+    NVB_CUDA(cudaMalloc(&m->color_synth, need * sizeof(float)));
+    m->color_synth_cap = need;
+  }
+  a->synth = m->color_synth;
+  return NVB_OK;
+}
+
+int stageBytes(NvbMapper* m, unsigned char** buf, size_t* cap, const unsigned char* host, size_t bytes) {
+  if (*cap < bytes) {
+    NVB_CUDA(syncAll(m));
+    if (*buf) cudaFree(*buf);
+    NVB_CUDA(cudaMalloc(buf, bytes));
+    *cap = bytes;
+  }
+  NVB_CUDA(cudaMemcpyAsync(*buf, host, bytes, cudaMemcpyHostToDevice, m->stream));
+  return NVB_OK;
+}
+}  // namespace
+
+int32_t nvb_sphere_tracer_render_depth(NvbMapper* m, const float* T_L_C, const NvbCamera* cam, float truncation_distance_m,
+                                       int32_t ray_subsampling_factor, float* out_depth_host) {
+  if (!m || !T_L_C || !cam || !out_depth_host) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "the sphere tracer needs a TSDF layer");
+  NVB_CUDA(cudaSetDevice(m->device));
+  ColorArgs a{};
+  int rc = fillTracerArgs(m, &a, T_L_C, cam, truncation_distance_m, ray_subsampling_factor);
+  if (rc) return rc;
+  launchSphereTrace(a, m->stream);
+  m->launches++;
+  NVB_CUDA(cudaMemcpyAsync(out_depth_host, a.synth, (size_t)a.drows * a.dcols * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  return checkDeviceError(m);
+}
+
+int32_t nvb_mapper_integrate_color(NvbMapper* m, const uint8_t* color, const uint8_t* mask, int32_t mask_mode, int32_t memory,
+                                   int32_t rows, int32_t cols, const float* T_L_C, const NvbCamera* cam,
+                                   int32_t* updated_xyz_host, int32_t cap, int32_t* out_count) {
+  if (!m || !color || !T_L_C || !cam) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (rows <= 0 || cols <= 0) return fail(NVB_ERR_INVALID_ARGUMENT, "image must have positive size");
+  if (!(cam->fu != 0.0f) || !(cam->fv != 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "camera focal length is zero");
+  if (out_count) *out_count = 0;
+  m->color_last_count = 0;
+  // "Color is only integrated for Tsdf layers (not for occupancy)" (mapper_impl.h:118-119)
+  if (m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = ensureColorLayer(m))) return rc;
+  const float trunc_m = m->cp.truncation_distance_vox * m->voxel_size;
+  ColorArgs a{};
+  if ((rc = fillTracerArgs(m, &a, T_L_C, cam, trunc_m, m->cp.sphere_tracing_ray_subsampling_factor))) return rc;
+  a.color = m->color;
+  // Camera::getViewAABB(T_L_C, 1e-6, max_integration_distance + truncation) + the integrator's own workspace bounds
+  // (view_calculator_impl.h:47-58)
+  {
+    const float max_distance = m->cp.max_integration_distance_m + trunc_m;
+    const float w = (float)cam->width, h = (float)cam->height;
+    const float ux[4] = {0.0f, w, w, 0.0f}, vy[4] = {0.0f, 0.0f, h, h};
+    Vec3 ray[4];
+    for (int k = 0; k < 4; k++) {
+      float nx = (ux[k] - cam->cu) / cam->fu, ny = (vy[k] - cam->cv) / cam->fv;
+      if (cam->has_distortion) removeDistortion(*cam, nx, ny);
+      ray[k] = Vec3{nx, ny, 1.0f};
+    }
+    const int order[4] = {2, 1, 0, 3};
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int k = 0; k < 8; k++) {
+      const float d = (k < 4) ? 1e-6f : max_distance;
+      const Vec3 r = ray[order[k & 3]];
+      const Vec3 c = transformPoint(a.T_L_C, Vec3{d * r.x, d * r.y, d * r.z});
+      const float cl[3] = {c.x, c.y, c.z};
+      for (int i = 0; i < 3; i++) lo[i] = std::min(lo[i], cl[i]), hi[i] = std::max(hi[i], cl[i]);
+    }
+    if (m->cp.workspace_bounds_type == NVB_WS_HEIGHT_BOUNDS) {
+      lo[2] = std::max(lo[2], m->cp.workspace_min[2]);
+      hi[2] = std::min(hi[2], m->cp.workspace_max[2]);
+    } else if (m->cp.workspace_bounds_type == NVB_WS_BOUNDING_BOX) {
+      for (int i = 0; i < 3; i++) lo[i] = std::max(m->cp.workspace_min[i], lo[i]), hi[i] = std::min(hi[i], m->cp.workspace_max[i]);
+    }
+    if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) return NVB_OK;  // empty workspace intersection: nothing in view
+    a.aabb_lo = blockIndexFromPosition(m->block_size, Vec3{lo[0], lo[1], lo[2]});
+    a.aabb_hi = blockIndexFromPosition(m->block_size, Vec3{hi[0], hi[1], hi[2]});
+    // Camera::getNormalizedViewport(getViewportMargin(height)) (src/sensors/camera.cpp:85-96, view_calculator_impl.h:81-83)
+    const float margin = (float)cam->height / 20.0f;
+    float x0 = (-margin - cam->cu) / cam->fu, y0 = (-margin - cam->cv) / cam->fv;
+    float x1 = (((float)cam->width + margin) - cam->cu) / cam->fu, y1 = (((float)cam->height + margin) - cam->cv) / cam->fv;
+    if (cam->has_distortion) removeDistortion(*cam, x0, y0), removeDistortion(*cam, x1, y1);
+    a.vmin_x = x0, a.vmin_y = y0, a.vmax_x = x1, a.vmax_y = y1;
+  }
+  a.max_integration_distance_m = m->cp.max_integration_distance_m;
+  a.max_weight = m->cp.max_weight;
+  a.measurement_weight = m->cp.measurement_weight;
+  {  // blendTwoArrays (projective_appearance_integrator.cu:287-306)
+    float w_old = 1.0f - m->cp.measurement_weight, w_new = m->cp.measurement_weight;
+    const float total = w_old + w_new;
+    w_old /= total, w_new /= total;
+    a.w_old_h = roundThroughHalf(w_old), a.w_new_h = roundThroughHalf(w_new);
+  }
+  a.work = m->color_work;
+  a.work_count = m->esdf_ints + kColorWorkCount;
+  a.error = m->error_dev;
+  a.rows = rows, a.cols = cols;
+  a.depth_subsample = rows / a.drows;  // projective_integrator_impl.cuh:320
+  if (a.depth_subsample <= 0) return fail(NVB_ERR_INVALID_ARGUMENT, "the colour image is smaller than the synthetic depth image");
+  a.mask_mode = mask_mode;
+  if (memory == NVB_MEM_HOST) {
+    if ((rc = stageBytes(m, &m->color_stage, &m->color_stage_cap, color, (size_t)rows * cols * 3))) return rc;
+    a.color_image = m->color_stage;
+    a.mask = nullptr;
+    if (mask) {
+      if ((rc = stageBytes(m, &m->color_mask_stage, &m->color_mask_stage_cap, mask, (size_t)rows * cols))) return rc;
+      a.mask = m->color_mask_stage;
+    }
+  } else {
+    a.color_image = color, a.mask = mask;
+  }
+  NVB_CUDA(cudaMemsetAsync(a.work_count, 0, sizeof(int), m->stream));
+  launchColorSelect(a, m->num_sms, m->stream);
+  launchSphereTrace(a, m->stream);
+  launchColorIntegrate(a, m->num_sms, m->stream);
+  m->launches += 3;
+  int n = 0;
+  NVB_CUDA(cudaMemcpyAsync(&n, a.work_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));  // also: host colour / mask buffers are free again
+  m->color_last_count = n;
+  if (out_count) *out_count = n;
+  if (updated_xyz_host && cap > 0 && n > 0) {
+    const int k = std::min(n, (int)cap);
+    std::vector<int4> tmp((size_t)k);
+    NVB_CUDA(cudaMemcpy(tmp.data(), m->color_work, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < k; i++)
+      updated_xyz_host[3 * i] = tmp[i].x, updated_xyz_host[3 * i + 1] = tmp[i].y, updated_xyz_host[3 * i + 2] = tmp[i].z;
+  }
+  return checkDeviceError(m);
 }
 
 int32_t nvb_mapper_integrate_depth(NvbMapper* m, const float* depth, const uint8_t* mask, int32_t mask_mode,
@@ -1749,6 +1999,11 @@ void* nvb_mapper_stream(NvbMapper* m) { return m ? (void*)m->stream : nullptr; }
 static DevLayer* layerOf(NvbMapper* m, int layer) {
   if (layer == NVB_LAYER_TSDF) return m->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY ? &m->tsdf : nullptr;
   if (layer == NVB_LAYER_FREESPACE) return m->freespace.blocks ? &m->freespace : nullptr;
+  if (layer == NVB_LAYER_COLOR) {
+    // created on first use (integration or query); an occupancy mapper never has one (mapper_impl.h:118-119)
+    if (!m->color.blocks && m->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY && ensureColorLayer(m)) return nullptr;
+    return m->color.blocks ? &m->color : nullptr;
+  }
   if (layer == NVB_LAYER_OCCUPANCY) return m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? &m->tsdf : nullptr;
   if (layer == NVB_LAYER_ESDF) return &m->esdf;
   return nullptr;
@@ -1759,6 +2014,7 @@ int32_t nvb_layer_block_bytes(int32_t layer) {
   if (layer == NVB_LAYER_ESDF) return kEsdfBlockBytes;
   if (layer == NVB_LAYER_OCCUPANCY) return kOccBlockBytes;
   if (layer == NVB_LAYER_FREESPACE) return kFreespaceBlockBytes;
+  if (layer == NVB_LAYER_COLOR) return kColorBlockBytes;
   return 0;
 }
 

@@ -20,6 +20,7 @@ constexpr int kVpb = kVps * kVps * kVps;
 constexpr int kTsdfBlockBytes = kVpb * 8;   // 4096
 constexpr int kEsdfBlockBytes = kVpb * 20;  // 10240
 constexpr int kEsdfVoxelWords = 5;
+constexpr int kColorBlockBytes = kVpb * 8;  // ColorVoxel{Color (3 bytes) + 1 pad, float weight} (map/voxels.h:77-83)
 constexpr int kOccBlockBytes = kVpb * 4;    // OccupancyVoxel{float log_odds} (map/voxels.h:92-97)
 
 struct Vec3 {
@@ -426,6 +427,32 @@ struct FreespaceArgs {
 void launchFreespaceUpdate(const FreespaceArgs& a, int upper, int num_sms, cudaStream_t stream);
 
 // nvb_tsdf.cu: decay (VoxelDecayer::decay, integrators/internal/cuda/impl/decayer_impl.cuh)
+// Colour integration (nvb_color.cu): one frame's arguments.
+struct ColorArgs {
+  DevLayer tsdf, color;
+  Rigid T_C_L, T_L_C;
+  NvbCamera cam;
+  int3 aabb_lo, aabb_hi;                   // block-index range of the view AABB
+  float vmin_x, vmin_y, vmax_x, vmax_y;    // Camera::getNormalizedViewport(getViewportMargin(height))
+  float block_size, voxel_size, half_voxel_size, voxel_size_inv;
+  float trunc_m, max_integration_distance_m, max_weight, measurement_weight;
+  float w_old_h, w_new_h;                  // blendTwoArrays' normalised weights, rounded through binary16 on the host
+  int4* work;                              // {x, y, z, colour slot} of the blocks in view and in the truncation band
+  int* work_count;
+  int* error;
+  float* synth;                            // sphere-traced depth, drows x dcols
+  int drows, dcols, subsample, depth_subsample;
+  int max_steps;
+  float max_ray_len, eps_m;
+  const unsigned char* color_image;        // rows x cols x 3 (RGB)
+  const unsigned char* mask;
+  int mask_mode;
+  int rows, cols;
+};
+void launchColorSelect(const ColorArgs& a, int num_sms, cudaStream_t stream);
+void launchSphereTrace(const ColorArgs& a, cudaStream_t stream);
+void launchColorIntegrate(const ColorArgs& a, int num_sms, cudaStream_t stream);
+
 struct DecayArgs {
   DevLayer layer;  // the projective layer (TsdfVoxel or OccupancyVoxel blocks)
   int occupancy;

@@ -27,6 +27,7 @@ ESDF_VOXEL_DTYPE = np.dtype(
      ("is_inside", "u1"), ("observed", "u1"), ("is_site", "u1"), ("pad", "u1")])
 
 OCCUPANCY_VOXEL_DTYPE = np.dtype([("log_odds", "<f4")])  # map/voxels.h:51-53
+COLOR_VOXEL_DTYPE = np.dtype([("color", "u1", (3,)), ("pad", "u1"), ("weight", "<f4")])  # ColorVoxel (map/voxels.h:77-83)
 FREESPACE_VOXEL_DTYPE = np.dtype([("last_occupied_timestamp_ms", "<i8"), ("consecutive_occupancy_duration_ms", "<i8"),
                                   ("is_high_confidence_freespace", "u1"), ("pad", "u1", (7,))])  # map/voxels.h:38-52
 
@@ -219,6 +220,32 @@ class _OccupancyIntegrator(_TsdfIntegrator):
             .occupied_region_half_width_m
 
 
+class _ColorIntegrator:
+    """ProjectiveColorIntegrator parameter surface (projective_appearance_integrator.h:96-148) and its SphereTracer."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def params(self, **kw):
+        p = _lib.NvbColorParams()
+        check(self._m._L.nvb_mapper_get_color_params(self._m._h, C.byref(p)))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        if kw:
+            check(self._m._L.nvb_mapper_set_color_params(self._m._h, C.byref(p)))
+        return p
+
+    def render_depth(self, T_L_C, camera, truncation_distance_m, ray_subsampling_factor=1):
+        """SphereTracer::renderImageOnGPU(camera, T_L_C, tsdf_layer, truncation_distance_m, ..., ray_subsampling_factor)
+        -> (height / f, width / f) float32, -1 where a ray found no surface."""
+        f = int(ray_subsampling_factor)
+        out = np.zeros((max(camera.c.height // max(f, 1), 1), max(camera.c.width // max(f, 1), 1)), np.float32)
+        T = colmajor(T_L_C)
+        check(self._m._L.nvb_sphere_tracer_render_depth(self._m._h, _fp(T), C.byref(camera.c), float(truncation_distance_m), f,
+                                                        _fp(out)))
+        return out
+
+
 class _FreespaceIntegrator:
     """FreespaceIntegrator parameter surface (freespace_integrator.h:75-128) + updateFreespaceLayer on a block list."""
 
@@ -395,6 +422,7 @@ class Mapper:
         self._occupancy = _Layer(self, _lib.NVB_LAYER_OCCUPANCY, OCCUPANCY_VOXEL_DTYPE)
         self._freespace = _Layer(self, _lib.NVB_LAYER_FREESPACE, FREESPACE_VOXEL_DTYPE)
         self._esdf = _Layer(self, _lib.NVB_LAYER_ESDF, ESDF_VOXEL_DTYPE)
+        self._color = _Layer(self, _lib.NVB_LAYER_COLOR, COLOR_VOXEL_DTYPE)
         self._keep = []  # host buffers of in-flight async frames
 
     def close(self):
@@ -423,6 +451,36 @@ class Mapper:
 
     def freespace_layer(self):
         return self._freespace
+
+    def color_layer(self):
+        return self._color
+
+    def color_integrator(self):
+        return _ColorIntegrator(self)
+
+    def integrate_color(self, color, T_L_C, camera, mask=None, mask_mode=0, return_blocks=True):
+        """Mapper::integrateColor(color_frame[, mask], T_L_C, camera) (mapper.h:202-207). color: (rows, cols, 3) uint8 RGB.
+        Returns updated_blocks (n, 3) (unordered)."""
+        c = np.ascontiguousarray(color, dtype=np.uint8)
+        if c.ndim != 3 or c.shape[2] != 3:
+            raise ValueError("color must be (rows, cols, 3) uint8")
+        mk = None
+        if mask is not None:
+            mk = np.ascontiguousarray(mask, dtype=np.uint8)
+            if mk.shape != c.shape[:2]:
+                raise ValueError("mask must have the colour image's size")
+        T = colmajor(T_L_C)
+        cap = 1 << 14 if return_blocks else 0
+        n = C.c_int32(0)
+        out = np.empty((max(cap, 1), 3), dtype=np.int32)
+        check(self._L.nvb_mapper_integrate_color(self._h, c.ctypes.data, None if mk is None else mk.ctypes.data, mask_mode,
+                                                 _lib.NVB_MEM_HOST, c.shape[0], c.shape[1], _fp(T), C.byref(camera.c),
+                                                 _ip(out) if return_blocks else None, cap, C.byref(n)))
+        if not return_blocks:
+            return None
+        if n.value > cap:
+            raise RuntimeError("more than %d colour blocks in one frame" % cap)
+        return out[:n.value].copy()
 
     def freespace_integrator(self):
         return _FreespaceIntegrator(self)

@@ -56,6 +56,24 @@ int main() {
     }
   }
   EXPECT(sites > 1000);
+  // colour (test_color_integrator.cpp): a red frame paints the observed surface red, nothing else
+  ColorImage red(480, 640, MemoryType::kUnified);
+  for (int r = 0; r < 480; r++) for (int c = 0; c < 640; c++) red(r, c) = Color::Red();
+  mapper.color_integrator().measurement_weight(0.3f);
+  EXPECT(std::fabs(mapper.color_integrator().measurement_weight() - 0.3f) < 1e-7f);
+  mapper.integrateColor(red, Transform::Identity(), camera);
+  ColorLayer color = mapper.color_layer();
+  EXPECT(color.numBlocks() > 0 && color.numBlocks() <= tsdf.numBlocks());
+  long painted = 0;
+  for (const Index3D& idx : color.getAllBlockIndices()) {
+    auto blk = color.getBlockAtIndexHost(idx);
+    for (int x = 0; x < 8; x++) for (int y = 0; y < 8; y++) for (int z = 0; z < 8; z++) {
+      const ColorVoxel& v = blk->voxels[x][y][z];
+      if (v.weight > 1e-4f) { painted++; EXPECT(v.color == Color::Red()); EXPECT(std::fabs(v.weight - 0.3f) < 1e-6f); }
+      else EXPECT(v.color == Color::Gray());
+    }
+  }
+  EXPECT(painted > 10000);
   // decay (test_tsdf_decay.cpp): the last view is spared, everything decays away without it
   const int blocks_before = tsdf.numBlocks();
   mapper.tsdf_decay_integrator().decay_factor(0.1f);
@@ -65,6 +83,7 @@ int main() {
   for (int i = 0; i < 6 && tsdf.numBlocks() > 0; i++) mapper.decayTsdfAllVoxels();
   EXPECT(tsdf.numBlocks() == 0);
   EXPECT(esdf.numBlocks() == 0);
+  EXPECT(color.numBlocks() == 0);
   std::printf("drop-in C++ API ok: %zu blocks, %ld observed voxels, %ld sites\n", updated.size(), observed, sites);
   return 0;
 }

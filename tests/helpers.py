@@ -217,3 +217,25 @@ def check_sphere_scene_slice(esdf_layer, planar, voxel_size=0.05):
             assert x < (2.0 if planar else 2.0 * np.sqrt(2.0))
             n_inside += 1
     return n_inside
+
+
+def assert_color_equal(gpu_layer, cpu_layer):
+    """ColorLayer parity: same block set, identical colour bytes, bit-identical weights."""
+    assert set(gpu_layer) == set(cpu_layer), (len(gpu_layer), len(cpu_layer), sorted(set(gpu_layer) ^ set(cpu_layer))[:5])
+    for k, g in gpu_layer.items():
+        c = cpu_layer[k]
+        if not np.array_equal(g["color"], c["color"]):
+            bad = np.argwhere(np.any(g["color"] != c["color"], axis=-1))
+            raise AssertionError(("color", k, len(bad), bad[:3], g["color"][tuple(bad[0])], c["color"][tuple(bad[0])]))
+        if not np.array_equal(g["weight"].view(np.uint32), c["weight"].view(np.uint32)):
+            bad = np.argwhere(g["weight"] != c["weight"])
+            raise AssertionError(("weight", k, len(bad), bad[:3], g["weight"][tuple(bad[0])], c["weight"][tuple(bad[0])]))
+
+
+def textured_image(rows, cols, seed=0):
+    """A smooth-plus-noise RGB test image."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:rows, 0:cols]
+    img = np.stack([(x * 255 // max(cols - 1, 1)), (y * 255 // max(rows - 1, 1)), ((x // 16 + y // 16) % 2) * 200 + 20], axis=-1)
+    img = img + rng.integers(-20, 21, size=img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
