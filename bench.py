@@ -314,6 +314,41 @@ def main():
         dist.all_reduce(ta, op=dist.ReduceOp.MAX)
     e2e_async_value = world * F * args.steps / float(ta.item())
 
+    # ---- BASELINE.json configs[1] shape: a colour frame with every depth frame (TSDF + colour + ESDF), device-resident ----
+    with_color = None
+    if world == 1:
+        from isaac_ros_nvblox_b200 import synthetic as syn_mod  # noqa: F401
+        yy, xx = np.mgrid[0:ROWS, 0:COLS]
+        base = np.stack([xx * 255 // (COLS - 1), yy * 255 // (ROWS - 1), ((xx // 16 + yy // 16) % 2) * 200 + 20], axis=-1)
+        color_dev = torch.from_numpy(np.stack([np.roll(base, 7 * i, axis=1) for i in range(F)]).astype(np.uint8)).cuda()
+
+        def step_color():
+            m.clear()
+            for i in range(F):
+                m.integrate_depth_device(depth_dev[i].data_ptr(), ROWS, COLS, poses[i], cam)
+                m.integrate_color_device(color_dev[i].data_ptr(), ROWS, COLS, poses[i], cam)
+                m.update_esdf(sync=False)
+
+        for _ in range(max(args.warmup, 3)):
+            step_color()
+        m.synchronize()
+        barrier()
+        l0 = m.kernel_launches()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(args.steps):
+            step_color()
+        m.join_streams()
+        c1.record(stream)
+        m.synchronize()
+        barrier()
+        cms = c0.elapsed_time(c1)
+        with_color = {"value": F * args.steps / (cms * 1e-3), "unit": "frames/s", "ms_per_step": cms / args.steps,
+                      "gpu_launches": int(m.kernel_launches() - l0), "color_blocks": m.color_layer().num_blocks(),
+                      "workload": "the same sequence with a 640x480 RGB frame integrated after every depth frame "
+                                  "(TSDF + colour + ESDF, BASELINE.json configs[1] shape), frames resident in HBM"}
+        del color_dev
+
     # ---- per-stage device time + algorithmic bytes for the roofline (rank 0, one extra step) ----
     roofline, stages_out, map_stats = None, None, None
     if rank == 0:
@@ -390,7 +425,7 @@ def main():
                                   "api": "nvb_mapper_integrate_depth_async (pinned host depth) + nvb_mapper_update_esdf_async per "
                                          "frame, one nvb_mapper_synchronize + block-index read-back per step"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages_out,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "with_color": with_color,
         }
         print(json.dumps(out))
     m.close()

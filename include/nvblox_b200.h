@@ -309,6 +309,9 @@ NVB_API int32_t nvb_mapper_get_color_params(const NvbMapper* m, NvbColorParams* 
 NVB_API int32_t nvb_mapper_integrate_color(NvbMapper* m, const uint8_t* color, const uint8_t* mask, int32_t mask_mode,
                                            int32_t memory, int32_t rows, int32_t cols, const float* T_L_C,
                                            const NvbCamera* cam, int32_t* updated_xyz_host, int32_t cap, int32_t* out_count);
+/* A call with device-resident images (memory = NVB_MEM_DEVICE) and no output pointers is enqueued without synchronising;
+ * after nvb_mapper_synchronize, this returns the `updated_blocks` of the last colour frame. */
+NVB_API int32_t nvb_mapper_last_color_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_t cap, int32_t* out_count);
 /* SphereTracer::renderImageOnGPU(camera, T_L_C, tsdf_layer, truncation_distance_m, &depth, ..., ray_subsampling_factor)
  * (C/src/rays/sphere_tracer.cu:389-485) with the colour integrator's tracer settings: out_depth_host receives
  * (height / f) * (width / f) floats, -1 where a ray found no surface. */

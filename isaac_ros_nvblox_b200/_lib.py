@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "nvb_default_freespace_params", "nvb_mapper_set_freespace_params", "nvb_mapper_get_freespace_params",
     "nvb_mapper_update_freespace", "nvb_freespace_update_blocks",
     "nvb_default_color_params", "nvb_mapper_set_color_params", "nvb_mapper_get_color_params",
-    "nvb_mapper_integrate_color", "nvb_sphere_tracer_render_depth",
+    "nvb_mapper_integrate_color", "nvb_mapper_last_color_blocks", "nvb_sphere_tracer_render_depth",
     "nvb_default_esdf_slice_params", "nvb_mapper_set_esdf_slice_params", "nvb_mapper_get_esdf_slice_params",
     "nvb_mapper_update_esdf_slice", "nvb_esdf_integrate_slice_blocks", "nvb_esdf_slice_distance_image",
     "nvb_mapper_update_esdf_slice_planar", "nvb_esdf_integrate_slice_planar_blocks",
@@ -177,6 +177,7 @@ def load():
     L.nvb_mapper_set_color_params.argtypes = [vp, C.POINTER(NvbColorParams)]
     L.nvb_mapper_get_color_params.argtypes = [vp, C.POINTER(NvbColorParams)]
     L.nvb_mapper_integrate_color.argtypes = [vp, vp, vp, i32, i32, i32, i32, fp, C.POINTER(NvbCamera), ip, i32, ip]
+    L.nvb_mapper_last_color_blocks.argtypes = [vp, ip, i32, ip]
     L.nvb_sphere_tracer_render_depth.argtypes = [vp, fp, C.POINTER(NvbCamera), f32, i32, fp]
     L.nvb_default_freespace_params.argtypes = [C.POINTER(NvbFreespaceParams)]
     L.nvb_default_freespace_params.restype = None

@@ -79,7 +79,6 @@ struct NvbMapper {
   size_t color_stage_cap = 0;
   unsigned char* color_mask_stage = nullptr;
   size_t color_mask_stage_cap = 0;
-  int color_last_count = 0;
   NvbFreespaceParams fp;
   NvbEsdfSliceParams sp;
   int esdf_mode = 0;                // EsdfMode: 0 unset, 1 3-D, 2 2-D slice (mapper.h:61, src/mapper/mapper.cpp:408-470)
@@ -1645,7 +1644,6 @@ int32_t nvb_mapper_integrate_color(NvbMapper* m, const uint8_t* color, const uin
   if (rows <= 0 || cols <= 0) return fail(NVB_ERR_INVALID_ARGUMENT, "image must have positive size");
   if (!(cam->fu != 0.0f) || !(cam->fv != 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "camera focal length is zero");
   if (out_count) *out_count = 0;
-  m->color_last_count = 0;
   // "Color is only integrated for Tsdf layers (not for occupancy)" (mapper_impl.h:118-119)
   if (m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY) return NVB_OK;
   NVB_CUDA(cudaSetDevice(m->device));
@@ -1724,19 +1722,33 @@ int32_t nvb_mapper_integrate_color(NvbMapper* m, const uint8_t* color, const uin
   launchSphereTrace(a, m->stream);
   launchColorIntegrate(a, m->num_sms, m->stream);
   m->launches += 3;
+  // Device-resident frames with no output requested stay asynchronous (read the list later with
+  // nvb_mapper_last_color_blocks); host buffers must be released and outputs filled, so those calls synchronise.
+  if (memory == NVB_MEM_DEVICE && !updated_xyz_host && !out_count) return NVB_OK;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int rc2 = nvb_mapper_last_color_blocks(m, updated_xyz_host, cap, out_count);
+  if (rc2) return rc2;
+  return checkDeviceError(m);
+}
+
+int32_t nvb_mapper_last_color_blocks(NvbMapper* m, int32_t* out_xyz_host, int32_t cap, int32_t* out_count) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (out_count) *out_count = 0;
+  if (!m->color.blocks || !m->color_work) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
   int n = 0;
-  NVB_CUDA(cudaMemcpyAsync(&n, a.work_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-  NVB_CUDA(cudaStreamSynchronize(m->stream));  // also: host colour / mask buffers are free again
-  m->color_last_count = n;
+  NVB_CUDA(cudaMemcpyAsync(&n, m->esdf_ints + kColorWorkCount, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
   if (out_count) *out_count = n;
-  if (updated_xyz_host && cap > 0 && n > 0) {
+  if (out_xyz_host && cap > 0 && n > 0) {
     const int k = std::min(n, (int)cap);
     std::vector<int4> tmp((size_t)k);
-    NVB_CUDA(cudaMemcpy(tmp.data(), m->color_work, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost));
+    NVB_CUDA(cudaMemcpyAsync(tmp.data(), m->color_work, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
     for (int i = 0; i < k; i++)
-      updated_xyz_host[3 * i] = tmp[i].x, updated_xyz_host[3 * i + 1] = tmp[i].y, updated_xyz_host[3 * i + 2] = tmp[i].z;
+      out_xyz_host[3 * i] = tmp[i].x, out_xyz_host[3 * i + 1] = tmp[i].y, out_xyz_host[3 * i + 2] = tmp[i].z;
   }
-  return checkDeviceError(m);
+  return NVB_OK;
 }
 
 int32_t nvb_mapper_integrate_depth(NvbMapper* m, const float* depth, const uint8_t* mask, int32_t mask_mode,

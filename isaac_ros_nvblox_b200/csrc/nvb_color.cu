@@ -96,13 +96,19 @@ __global__ void __launch_bounds__(128) sphereTraceKernel(const __grid_constant__
   int first = 0;  // 0 not yet known, 1 positive, 2 negative
   float t = 0.0f;
   bool ok = false, done = false;
+  int last_bx = INT32_MIN, last_by = 0, last_bz = 0, last_slot = -1;
   for (int i = 0; (i < a.max_steps) && (t < a.max_ray_len) && !done; i++) {
     const float plx = T.t[0] + t * ux, ply = T.t[1] + t * uy, plz = T.t[2] + t * uz;
     int bx, by, bz, vx, vy, vz;
     blockAndVoxel1D(a.block_size, a.voxel_size_inv, plx, bx, vx);
     blockAndVoxel1D(a.block_size, a.voxel_size_inv, ply, by, vy);
     blockAndVoxel1D(a.block_size, a.voxel_size_inv, plz, bz, vz);
-    const int slot = hashFind(a.tsdf.hash, bx, by, bz);
+    // consecutive samples mostly stay in one block (a step is at most the truncation distance): remember its slot
+    if (bx != last_bx || by != last_by || bz != last_bz) {
+      last_slot = hashFind(a.tsdf.hash, bx, by, bz);
+      last_bx = bx, last_by = by, last_bz = bz;
+    }
+    const int slot = last_slot;
     float dist = 0.0f, wgt = 0.0f;
     if (slot >= 0) {
       const float2 v = *reinterpret_cast<const float2*>(a.tsdf.blocks + (size_t)slot * kTsdfBlockBytes +

@@ -482,6 +482,20 @@ class Mapper:
             raise RuntimeError("more than %d colour blocks in one frame" % cap)
         return out[:n.value].copy()
 
+    def integrate_color_device(self, color_ptr, rows, cols, T_L_C, camera, mask_ptr=0, mask_mode=0):
+        """Same, for an RGB frame already resident in HBM (raw device pointers); enqueued without synchronising."""
+        T = colmajor(T_L_C)
+        check(self._L.nvb_mapper_integrate_color(self._h, color_ptr, mask_ptr or None, mask_mode, _lib.NVB_MEM_DEVICE, rows, cols,
+                                                 _fp(T), C.byref(camera.c), None, 0, None))
+
+    def last_color_blocks(self):
+        """updated_blocks of the last colour frame (after synchronize())."""
+        n = C.c_int32(0)
+        check(self._L.nvb_mapper_last_color_blocks(self._h, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3), dtype=np.int32)
+        check(self._L.nvb_mapper_last_color_blocks(self._h, _ip(out), n.value, C.byref(n)))
+        return out[:n.value].copy()
+
     def freespace_integrator(self):
         return _FreespaceIntegrator(self)
 

@@ -190,3 +190,28 @@ def test_color_parameter_checks(gpu):
     with pytest.raises(Exception):
         m.integrate_color(np.zeros((240, 320), np.uint8), np.eye(4, dtype=np.float32), cam)
     m.close()
+
+
+def test_device_resident_frames_stay_asynchronous_and_match(gpu):
+    """Depth and colour frames already in HBM (raw device pointers): enqueued without a host synchronisation, same result."""
+    import torch
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240, f=160.0)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:5])
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    depth_dev = torch.from_numpy(np.stack([d for d, _ in frames])).cuda()
+    imgs = np.stack([textured_image(240, 320, seed=10 + i) for i in range(len(frames))])
+    color_dev = torch.from_numpy(imgs).cuda()
+    mask = (np.random.default_rng(4).random((240, 320)) < 0.8).astype(np.uint8)
+    mask_dev = torch.from_numpy(mask).cuda()
+    torch.cuda.synchronize()
+    for i, (d, T) in enumerate(frames):
+        m.integrate_depth_device(depth_dev[i].data_ptr(), 240, 320, T, cam)
+        m.integrate_color_device(color_dev[i].data_ptr(), 240, 320, T, cam, mask_ptr=mask_dev.data_ptr() if i == 3 else 0)
+        m.update_esdf(sync=False)
+        o.integrate_depth(d, T, ocam)
+        bc = o.integrate_color(imgs[i], T, ocam, mask=mask if i == 3 else None)
+    m.synchronize()
+    assert _blockset(m.last_color_blocks()) == _blockset(bc)
+    assert_color_equal(m.color_layer().as_dict(), o.color_layer())
+    m.close()
