@@ -1,6 +1,6 @@
 """Small workload that touches every kernel of the library once (for compute-sanitizer): TSDF / occupancy / freespace mappers,
 3-D and 2-D ESDF (four-phase, host loop and gather-replay wavefronts), decay with deallocation and slot reuse, the slicer,
-explicit block lists, layer read-back and growth."""
+explicit block lists, layer read-back and growth, colour integration (with distortion and a mask) and the sphere tracer."""
 import os
 import sys
 
@@ -29,6 +29,9 @@ def main():
                 m.integrate_depth(d, T, dcam if i == 1 else cam, mask=k if i == 2 else None, mask_mode=1)
                 if ltype == nvb.ProjectiveLayerType.kTsdfWithFreespace:
                     m.update_freespace(1000 + 400 * i, depth=d, T_L_C=T, camera=cam)
+                if ltype != nvb.ProjectiveLayerType.kOccupancy:
+                    img = np.full((120, 160, 3), 40 * i + 10, np.uint8)
+                    m.integrate_color(img, T, dcam if i == 1 else cam, mask=k if i == 2 else None)
                 m.update_esdf()
             m.decay_exclude_last_view()
             m.decay()
@@ -36,6 +39,10 @@ def main():
             b = m.integrate_depth(d, T, cam)
             m.update_esdf()
             m.esdf_integrator().integrate_blocks(b[:10])
+            if ltype != nvb.ProjectiveLayerType.kOccupancy:
+                m.integrate_color(np.zeros((120, 160, 3), np.uint8), T, cam)  # reuses deallocated colour slots
+                m.color_integrator().render_depth(T, cam, 0.4, ray_subsampling_factor=2)
+                m.color_layer().as_dict()
             nvb.EsdfSlicer(m).slice_layer_to_distance_image(1.0, with_occupancy_grid=True)
             total += m.esdf_layer().num_blocks()
             m.esdf_layer().as_dict()
