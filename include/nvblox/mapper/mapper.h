@@ -266,6 +266,12 @@ class Mapper {
     // Mapper::integrateDepth dispatches on the projective layer type (mapper_impl.h:28-81)
     b200_detail::integrateFrame(m_, depth_frame, T_L_C, camera, nullptr);
   }
+  // Mapper::markUnobservedTsdfFreeInsideRadius (mapper.h:352-356)
+  void markUnobservedTsdfFreeInsideRadius(const Vector3f& center, float radius) {
+    const float c[3] = {center[0], center[1], center[2]};
+    b200_detail::check(nvb_mapper_mark_unobserved_free_inside_radius(m_, c, radius, nullptr, 0, nullptr),
+                       "markUnobservedTsdfFreeInsideRadius", nvb_last_error());
+  }
   // Mapper::integrateColor (mapper.h:202-207, mapper_impl.h:104-130)
   void integrateColor(const ColorImage& color_frame, const Transform& T_L_C, const Camera& camera) {
     integrateColor(MaskedColorImageConstView(color_frame, kMaskActiveEverywhere), T_L_C, camera);

@@ -277,6 +277,14 @@ NVB_API int32_t nvb_view_raycast(NvbMapper* m, const float* depth, int32_t depth
                                  float max_integration_distance_m, int32_t* out_xyz_host,
                                  int32_t cap, int32_t* out_count);
 
+/* Mapper::markUnobservedTsdfFreeInsideRadius(center, radius) (C/include/nvblox/mapper/mapper.h:352-356, src/mapper/mapper.cpp:494-507)
+ * = Projective{Tsdf,Occupancy}Integrator::markUnobservedFreeInsideRadius (projective_integrator_impl.cuh:408-462): every block
+ * whose box is closer than `radius` to `center` is allocated in the projective layer and its unobserved voxels are set to
+ * slightly observed free space (TSDF: truncation distance, weight 0.1 where weight < 1e-3; occupancy: log odds -2e-4 where
+ * |log odds| < 1e-4); the blocks join the tracker, so the next ESDF update covers them. updated_xyz_host may be NULL; it receives up to cap triples (unordered). */
+NVB_API int32_t nvb_mapper_mark_unobserved_free_inside_radius(NvbMapper* m, const float center[3], float radius,
+                                                              int32_t* updated_xyz_host, int32_t cap, int32_t* out_count);
+
 /* ProjectiveColorIntegrator's parameters (C/include/nvblox/integrators/projective_appearance_integrator.h:96-175,
  * projective_integrator_params.h:24-75), with those of its SphereTracer (rays/sphere_tracer.h:204-218) and of its own
  * ViewCalculator's workspace bounds. sphere_tracer_maximum_ray_length_m is a separate field because the reference

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "nvb_mapper_get_occupancy_decay_params", "nvb_mapper_decay", "nvb_mapper_decay_exclude_last_view",
     "nvb_default_freespace_params", "nvb_mapper_set_freespace_params", "nvb_mapper_get_freespace_params",
     "nvb_mapper_update_freespace", "nvb_freespace_update_blocks",
+    "nvb_mapper_mark_unobserved_free_inside_radius",
     "nvb_default_color_params", "nvb_mapper_set_color_params", "nvb_mapper_get_color_params",
     "nvb_mapper_integrate_color", "nvb_mapper_last_color_blocks", "nvb_sphere_tracer_render_depth",
     "nvb_default_esdf_slice_params", "nvb_mapper_set_esdf_slice_params", "nvb_mapper_get_esdf_slice_params",
@@ -172,6 +173,7 @@ def load():
     L.nvb_mapper_update_esdf_slice_planar.argtypes = [vp, fp, i32]
     L.nvb_esdf_integrate_slice_planar_blocks.argtypes = [vp, fp, ip, i32]
     L.nvb_esdf_slice_distance_image.argtypes = [vp, f32, f32, fp, fp, C.POINTER(C.c_int8), i32, ip, ip]
+    L.nvb_mapper_mark_unobserved_free_inside_radius.argtypes = [vp, fp, f32, ip, i32, ip]
     L.nvb_default_color_params.argtypes = [C.POINTER(NvbColorParams)]
     L.nvb_default_color_params.restype = None
     L.nvb_mapper_set_color_params.argtypes = [vp, C.POINTER(NvbColorParams)]

@@ -1507,6 +1507,61 @@ int32_t nvb_mapper_integrate_depth_async(NvbMapper* m, const float* depth, const
                       m->tp.max_integration_distance_m, true);
 }
 
+int32_t nvb_mapper_mark_unobserved_free_inside_radius(NvbMapper* m, const float center[3], float radius, int32_t* updated_xyz_host,
+                                                      int32_t cap, int32_t* out_count) {
+  if (!m || !center) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (!(radius > 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "radius must be positive");  // CHECK_GT(radius, 0.0f)
+  if (out_count) *out_count = 0;
+  NVB_CUDA(cudaSetDevice(m->device));
+  MarkFreeArgs a{};
+  const Vec3 mn{center[0] - radius, center[1] - radius, center[2] - radius};
+  const Vec3 mx{center[0] + radius, center[1] + radius, center[2] + radius};
+  a.lo = blockIndexFromPosition(m->block_size, mn);
+  const int3 hi = blockIndexFromPosition(m->block_size, mx);
+  a.size = make_int3(hi.x - a.lo.x + 1, hi.y - a.lo.y + 1, hi.z - a.lo.z + 1);
+  const long long cells = (long long)a.size.x * a.size.y * a.size.z;
+  if (cells <= 0 || cells > (1ll << 26)) return fail(NVB_ERR_CAPACITY, "the sphere covers more than 2^26 blocks");
+  if (!indexInRange(a.lo.x, a.lo.y, a.lo.z) || !indexInRange(hi.x, hi.y, hi.z))
+    return fail(NVB_ERR_INDEX_RANGE, "block index outside +-2^20");
+  a.cells = (int)cells;
+  int rc;
+  if ((rc = ensureTsdfCapacity(m, cells))) return rc;
+  m->cells_cum += cells;
+  m->tsdf_count_ub += (int)cells;
+  NVB_CUDA(syncAll(m));  // rare, synchronous call: the ESDF side stream may still be reading the projective layer
+  a.layer = m->tsdf;
+  a.occupancy = m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? 1 : 0;
+  a.cx = center[0], a.cy = center[1], a.cz = center[2];
+  a.radius = radius;
+  a.block_size = m->block_size;
+  a.trunc_m = m->tp.truncation_distance_vox * m->voxel_size;  // get_truncation_distance_m(layer->voxel_size())
+  a.error = m->error_dev;
+  if (m->tracker_initialized) a.dirty = m->dirty, a.todo_slots = m->todo_slots, a.todo_count = m->todo_count;
+  if (m->dirty_fs && m->fs_tracker_initialized)
+    a.dirty2 = m->dirty_fs, a.todo2_slots = m->todo_fs_slots, a.todo2_count = m->esdf_ints + kTodoFsCount;
+  int4* out_dev = nullptr;
+  NVB_CUDA(cudaMalloc(&out_dev, ((size_t)cells + 1) * sizeof(int4)));
+  a.out = out_dev + 1;
+  a.out_count = reinterpret_cast<int*>(out_dev);
+  NVB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(int4), m->stream));
+  launchMarkFreeSphere(a, m->num_sms, m->stream);
+  m->launches++;
+  int n = 0;
+  NVB_CUDA(cudaMemcpyAsync(&n, a.out_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  if (out_count) *out_count = n;
+  if (updated_xyz_host && cap > 0 && n > 0) {
+    const int k = std::min(n, (int)cap);
+    std::vector<int4> tmp((size_t)k);
+    NVB_CUDA(cudaMemcpyAsync(tmp.data(), a.out, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < k; i++)
+      updated_xyz_host[3 * i] = tmp[i].x, updated_xyz_host[3 * i + 1] = tmp[i].y, updated_xyz_host[3 * i + 2] = tmp[i].z;
+  }
+  cudaFree(out_dev);
+  return checkDeviceError(m);
+}
+
 // ---------------------------------------------------------------------------
 // Colour integration (nvb_color.cu)
 // ---------------------------------------------------------------------------

@@ -427,6 +427,21 @@ struct FreespaceArgs {
 void launchFreespaceUpdate(const FreespaceArgs& a, int upper, int num_sms, cudaStream_t stream);
 
 // nvb_tsdf.cu: decay (VoxelDecayer::decay, integrators/internal/cuda/impl/decayer_impl.cuh)
+// Mapper::markUnobservedTsdfFreeInsideRadius (nvb_tsdf.cu)
+struct MarkFreeArgs {
+  DevLayer layer;  // the projective layer
+  int occupancy;
+  int3 lo, size;   // block-index box of center +- radius
+  int cells;
+  float cx, cy, cz, radius, block_size, trunc_m;
+  int4* out;       // {x, y, z, slot} of the blocks inside the radius
+  int* out_count;
+  int* error;
+  int *dirty, *todo_slots, *todo_count;     // ESDF tracker (nullptr before its first query)
+  int *dirty2, *todo2_slots, *todo2_count;  // freespace tracker
+};
+void launchMarkFreeSphere(const MarkFreeArgs& a, int num_sms, cudaStream_t stream);
+
 // Colour integration (nvb_color.cu): one frame's arguments.
 struct ColorArgs {
   DevLayer tsdf, color;

@@ -216,6 +216,60 @@ __global__ void __launch_bounds__(256) tsdfIntegrateKernel(const __grid_constant
   }
 }
 
+// ProjectiveIntegrator::markUnobservedFreeInsideRadiusTemplate (projective_integrator_impl.cuh:408-462): a warp per block of
+// the box around the sphere: exterior distance of the block's box to the centre (getBlocksWithinRadius,
+// src/geometry/bounding_spheres.cpp:24-67), find-or-insert, tracker append, setUnobservedVoxel (:377-392) on its 512 voxels.
+__global__ void __launch_bounds__(256) markFreeSphereKernel(const __grid_constant__ MarkFreeArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float c[3] = {a.cx, a.cy, a.cz};
+  for (int cell = warp; cell < a.cells; cell += nwarps) {
+    const int idx[3] = {a.lo.x + cell / (a.size.y * a.size.z), a.lo.y + (cell / a.size.z) % a.size.y, a.lo.z + cell % a.size.z};
+    float dist2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {  // Eigen AlignedBox::squaredExteriorDistance of getAABBOfBlock
+      const float bmin = (float)idx[k] * a.block_size, bmax = ((float)idx[k] + 1.0f) * a.block_size;
+      if (bmin > c[k]) {
+        const float aux = bmin - c[k];
+        dist2 += aux * aux;
+      } else if (c[k] > bmax) {
+        const float aux = c[k] - bmax;
+        dist2 += aux * aux;
+      }
+    }
+    if (!(sqrtf(dist2) < a.radius)) continue;
+    int slot = -1;
+    if (lane == 0) {
+      bool was_new;
+      slot = hashFindOrInsert(a.layer, idx[0], idx[1], idx[2], a.error, &was_new);
+      if (slot >= 0) {
+        // BlocksToUpdateTracker::addBlocksToUpdate(updated_blocks) (src/mapper/mapper.cpp:506)
+        if (a.dirty != nullptr && atomicExch(a.dirty + slot, 1) == 0) a.todo_slots[atomicAdd(a.todo_count, 1)] = slot;
+        if (a.dirty2 != nullptr && atomicExch(a.dirty2 + slot, 1) == 0) a.todo2_slots[atomicAdd(a.todo2_count, 1)] = slot;
+        a.out[atomicAdd(a.out_count, 1)] = make_int4(idx[0], idx[1], idx[2], slot);
+      }
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < 0) continue;
+    if (a.occupancy) {
+      float* lo = reinterpret_cast<float*>(a.layer.blocks + (size_t)slot * kOccBlockBytes);
+#pragma unroll 4
+      for (int k = 0; k < kVpb / 32; k++) {
+        const float v = lo[lane + 32 * k];
+        if (fabsf(v - 0.0f) < 1e-4f) lo[lane + 32 * k] = -2e-4f;
+      }
+    } else {
+      float2* t = reinterpret_cast<float2*>(a.layer.blocks + (size_t)slot * kTsdfBlockBytes);
+#pragma unroll 4
+      for (int k = 0; k < kVpb / 32; k++) {
+        const float2 v = t[lane + 32 * k];
+        if (v.y < 0.001f) t[lane + 32 * k] = make_float2(a.trunc_m, 0.1f);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -418,6 +472,10 @@ static int projectiveCtasPerSm() {
     if (v < 1 || v > 8) v = 8;
   }
   return v;
+}
+
+void launchMarkFreeSphere(const MarkFreeArgs& a, int num_sms, cudaStream_t stream) {
+  markFreeSphereKernel<<<num_sms * 4, 256, 0, stream>>>(a);
 }
 
 void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* tsdf_blocks,

@@ -452,6 +452,17 @@ class Mapper:
     def freespace_layer(self):
         return self._freespace
 
+    def mark_unobserved_tsdf_free_inside_radius(self, center, radius):
+        """Mapper::markUnobservedTsdfFreeInsideRadius(center, radius) (mapper.h:352-356) -> the blocks inside the radius."""
+        c = np.ascontiguousarray(center, dtype=np.float32).reshape(3)
+        n = C.c_int32(0)
+        cap = 1 << 16
+        out = np.empty((cap, 3), dtype=np.int32)
+        check(self._L.nvb_mapper_mark_unobserved_free_inside_radius(self._h, _fp(c), float(radius), _ip(out), cap, C.byref(n)))
+        if n.value > cap:
+            raise RuntimeError("more than %d blocks inside the radius" % cap)
+        return out[:n.value].copy()
+
     def color_layer(self):
         return self._color
 

@@ -1504,6 +1504,50 @@ int32_t or_esdf_get_block(const OrMap* m, const int32_t xyz[3], OrEsdfVoxel* out
   return 1;
 }
 
+/* ProjectiveIntegrator::markUnobservedFreeInsideRadiusTemplate (projective_integrator_impl.cuh:408-462) behind
+ * Mapper::markUnobservedTsdfFreeInsideRadius (src/mapper/mapper.cpp:494-507): every block whose box is closer than `radius`
+ * to `center` (getBlocksWithinRadius, src/geometry/bounding_spheres.cpp:24-67; Eigen AlignedBox::exteriorDistance) is
+ * allocated, and its unobserved voxels become "slightly observed free": TSDF (truncation distance, weight 0.1) where
+ * weight < 1e-3; occupancy log odds -2e-4 where |log odds| < 1e-4 (setUnobservedVoxel, :377-392). Returns the block count. */
+int32_t or_mark_unobserved_free_inside_radius(OrMap* map, int32_t occupancy, const float center[3], float radius,
+                                              float truncation_distance_m, int32_t* out_xyz, int32_t cap) {
+  const v3 mn = {center[0] - radius, center[1] - radius, center[2] - radius};
+  const v3 mx = {center[0] + radius, center[1] + radius, center[2] + radius};
+  const i3 lo = block_index_from_position(map->block_size, mn), hi = block_index_from_position(map->block_size, mx);
+  List blocks = {0};
+  for (int x = lo.x; x <= hi.x; x++)
+    for (int y = lo.y; y <= hi.y; y++)
+      for (int z = lo.z; z <= hi.z; z++) {
+        const int idx[3] = {x, y, z};
+        float dist2 = 0.0f;
+        for (int k = 0; k < 3; k++) { /* AlignedBox::squaredExteriorDistance of getAABBOfBlock */
+          const float bmin = (float)idx[k] * map->block_size, bmax = ((float)idx[k] + 1.0f) * map->block_size;
+          if (bmin > center[k]) {
+            const float aux = bmin - center[k];
+            dist2 += aux * aux;
+          } else if (center[k] > bmax) {
+            const float aux = center[k] - bmax;
+            dist2 += aux * aux;
+          }
+        }
+        if (!(sqrtf(dist2) < radius)) continue;
+        const i3 k3 = {x, y, z};
+        list_push(&blocks, k3);
+        if (occupancy) {
+          float* lo_v = (float*)layer_block(&map->occ, layer_allocate(&map->occ, k3));
+          for (int v = 0; v < VPB; v++)
+            if (fabsf(lo_v[v] - 0.0f) < 1e-4f) lo_v[v] = -2e-4f;
+        } else {
+          OrTsdfVoxel* t = (OrTsdfVoxel*)layer_block(&map->tsdf, layer_allocate(&map->tsdf, k3));
+          for (int v = 0; v < VPB; v++)
+            if (t[v].weight < 0.001f) t[v].distance = truncation_distance_m, t[v].weight = 0.1f;
+        }
+      }
+  const int32_t n = copy_out(&blocks, out_xyz, cap);
+  list_free(&blocks);
+  return n;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Colour integration (src/integrators/projective_appearance_integrator.cu,  */
 /* src/rays/sphere_tracer.cu)                                                */

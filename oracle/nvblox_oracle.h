@@ -251,6 +251,8 @@ typedef struct {
   int32_t workspace_bounds_type;
   float workspace_min[3], workspace_max[3];
 } OrColorParams;
+int32_t or_mark_unobserved_free_inside_radius(OrMap* map, int32_t occupancy, const float center[3], float radius,
+                                              float truncation_distance_m, int32_t* out_xyz, int32_t cap);
 void or_default_color_params(OrColorParams* p);
 float or_round_through_half(float f);
 int32_t or_sphere_trace_ray(const OrMap* map, const float origin[3], const float direction[3], float truncation_distance_m,

@@ -181,6 +181,8 @@ def lib():
                                                  C.c_float, C.c_float]
     L.or_esdf_integrate_slice_planar.restype = None
     u8p = C.POINTER(C.c_uint8)
+    L.or_mark_unobserved_free_inside_radius.argtypes = [vp, C.c_int32, fp, C.c_float, C.c_float, ip, C.c_int32]
+    L.or_mark_unobserved_free_inside_radius.restype = C.c_int32
     L.or_round_through_half.argtypes = [C.c_float]
     L.or_round_through_half.restype = C.c_float
     L.or_sphere_trace_ray.argtypes = [vp, fp, fp, C.c_float, C.c_int32, C.c_float, C.c_float, fp]
@@ -483,6 +485,17 @@ class OracleMap:
             lib().or_freespace_get_block(self._h, _ip(np.ascontiguousarray(k, dtype=np.int32)), blk.ctypes.data)
             out[tuple(int(c) for c in k)] = blk
         return out
+
+    def mark_unobserved_free_inside_radius(self, center, radius, occupancy=False, truncation_distance_m=None, cap=1 << 20):
+        """Mapper::markUnobservedTsdfFreeInsideRadius(center, radius) -> the blocks inside the radius (all allocated now)."""
+        if truncation_distance_m is None:
+            truncation_distance_m = np.float32(4.0) * np.float32(self.voxel_size)
+        c = np.ascontiguousarray(center, dtype=np.float32).reshape(3)
+        out = np.zeros((cap, 3), dtype=np.int32)
+        n = lib().or_mark_unobserved_free_inside_radius(self._h, 1 if occupancy else 0, _fp(c), float(radius),
+                                                        float(truncation_distance_m), _ip(out), cap)
+        assert n <= cap
+        return out[:n].copy()
 
     def integrate_color(self, color, T_L_C, cam, params=None, mask=None, mask_mode=0, cap=1 << 20):
         """ProjectiveColorIntegrator::integrateFrame(color image (rows, cols, 3) uint8 RGB, T_L_C, camera, tsdf_layer,

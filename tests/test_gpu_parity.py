@@ -536,3 +536,70 @@ def test_distorted_view_raycast_640x480(gpu):
         want = orc.view_raycast(depth, T, ocam, 0.4, 0.2)
         assert np.array_equal(got, want)
     m.close()
+
+
+@pytest.mark.parametrize("mode", ["tsdf", "occupancy", "tsdf_freespace"])
+def test_mark_unobserved_free_inside_radius(gpu, mode):
+    """Mapper::markUnobservedTsdfFreeInsideRadius (tests/test_mapper.cpp GenerateEsdfInFakeObservedAreas): same block set,
+    identical projective voxels, and the ESDF of the following updates (tracker-driven here, explicit lists on the oracle)
+    exact -- before the tracker's first query, after it, and with later frames on top."""
+    import isaac_ros_nvblox_b200 as nvb
+    from oracle import oracle as orc
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:4])
+    ltype = {"tsdf": nvb.ProjectiveLayerType.kTsdf, "occupancy": nvb.ProjectiveLayerType.kOccupancy,
+             "tsdf_freespace": nvb.ProjectiveLayerType.kTsdfWithFreespace}[mode]
+    occ = mode == "occupancy"
+    m, o = nvb.Mapper(0.1, projective_layer_type=ltype), orc.OracleMap(0.1)
+    tp = orc.default_tsdf_params()
+
+    def integrate(d, T):
+        b = m.integrate_depth(d, T, cam)
+        if occ:
+            o.integrate_occupancy(d, T, ocam, tp)
+        else:
+            o.integrate_depth(d, T, ocam)
+        return b
+
+    def esdf(blocks):
+        m.update_esdf()
+        (o.integrate_esdf_occupancy if occ else o.integrate_esdf)(blocks)
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+
+    def proj_equal():
+        if occ:
+            g, c = m.occupancy_layer().as_dict(), o.occupancy_layer()
+            assert set(g) == set(c)
+            for k in g:
+                assert np.array_equal(g[k]["log_odds"].view(np.uint32), np.asarray(c[k]).view(np.uint32)), k
+        else:
+            assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+
+    # 1. before the tracker was ever queried
+    d, T = frames[0]
+    integrate(d, T)
+    center = T[:3, 3] + np.float32(0.123)
+    bg = m.mark_unobserved_tsdf_free_inside_radius(center, 1.7)
+    bc = o.mark_unobserved_free_inside_radius(center, 1.7, occupancy=occ)
+    assert set(map(tuple, bg.tolist())) == set(map(tuple, bc.tolist())) and len(bg) == len(bc) > 50
+    proj_equal()
+    esdf(o.occupancy_block_indices() if occ else o.tsdf_block_indices())
+    # 2. with the tracker running: new frame + a second sphere elsewhere, then an update driven by the tracker
+    d, T = frames[1]
+    b = integrate(d, T)
+    if mode == "tsdf_freespace":
+        m.update_freespace(1000)
+    c2 = np.array([-2.0, 1.0, 0.9], np.float32)
+    bg = m.mark_unobserved_tsdf_free_inside_radius(c2, 2.3)
+    bc = o.mark_unobserved_free_inside_radius(c2, 2.3, occupancy=occ)
+    assert set(map(tuple, bg.tolist())) == set(map(tuple, bc.tolist()))
+    proj_equal()
+    if mode != "tsdf_freespace":  # (the oracle's plain ESDF has no freespace input; the freespace case checks the layers only)
+        esdf(np.vstack([b, bc]))
+        # 3. later frames integrate on top of the slightly observed voxels
+        for d, T in frames[2:]:
+            esdf(integrate(d, T))
+        proj_equal()
+    with pytest.raises(Exception):
+        m.mark_unobserved_tsdf_free_inside_radius(c2, 0.0)
+    m.close()

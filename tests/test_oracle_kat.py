@@ -1133,3 +1133,48 @@ def test_indexing_1d_never_leaves_the_block():
         b, v = int(rng.integers(-1000, 1001)), int(rng.integers(0, 8))
         p = np.float32(b) * bs + np.float32(v) * np.float32(voxel) + np.float32(rng.uniform(0.0, voxel))
         assert orc.block_and_voxel_from_1d(bs, p)[0] in (b, b + (1 if v == 7 else 0))
+
+
+def test_mark_unobserved_free_inside_radius_generates_esdf_in_fake_observed_areas():
+    """GenerateEsdfInFakeObservedAreas (tests/test_mapper.cpp:185-282): a camera at the origin of an 8 m box looks along +x; the
+    space behind it has no blocks until Mapper::markUnobservedTsdfFreeInsideRadius((0, 0, 0), 5) allocates it as free space;
+    the next ESDF update then observes it, and voxels already in the truncation band keep their values."""
+    from helpers import voxel_at_position
+    voxel = 0.1
+    scene = syn.Scene()
+    scene.add_plane(2, -4.0).add_plane(2, 4.0).add_plane(0, -4.0).add_plane(0, 4.0).add_plane(1, -4.0).add_plane(1, 4.0)
+    cs = syn.PinholeCamera(300.0, 300.0, 320.0, 240.0, 640, 480)
+    cam = orc.Camera(300.0, 300.0, 320.0, 240.0, 640, 480)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]], np.float32)  # Quaternionf(0.5, 0.5, 0.5, 0.5)
+    depth = syn.render_depth(scene, cs, T, max_dist=20.0)
+    m = orc.OracleMap(voxel)
+    b = m.integrate_depth(depth, T, cam)
+    m.integrate_esdf(b)
+    tsdf, esdf = m.tsdf_layer(), m.esdf_layer()
+    assert voxel_at_position(tsdf, (1.0, 0.0, 0.0), voxel) is not None and voxel_at_position(tsdf, (-1.0, 0.0, 0.0), voxel) is None
+    assert voxel_at_position(esdf, (1.0, 0.0, 0.0), voxel) is not None and voxel_at_position(esdf, (-1.0, 0.0, 0.0), voxel) is None
+    before = voxel_at_position(tsdf, (4.0, 0.0, 0.0), voxel).copy()
+    marked = m.mark_unobserved_free_inside_radius((0.0, 0.0, 0.0), 5.0)
+    tsdf = m.tsdf_layer()
+    behind = voxel_at_position(tsdf, (-1.0, 0.0, 0.0), voxel)
+    assert behind is not None and behind["weight"] == np.float32(0.1) and behind["distance"] == np.float32(0.4)
+    assert voxel_at_position(m.esdf_layer(), (-1.0, 0.0, 0.0), voxel) is None
+    m.integrate_esdf(marked)  # Mapper::updateEsdf: the marked blocks are in the tracker
+    blk = m.esdf_layer()[(-1, 0, 0)]
+    assert blk["observed"].all() and (blk["squared_distance_vox"] > 0).all()
+    after = voxel_at_position(m.tsdf_layer(), (4.0, 0.0, 0.0), voxel)
+    assert abs(before["weight"] - after["weight"]) < 1e-4 and abs(before["distance"] - after["distance"]) < 1e-4
+    assert before["distance"] < voxel
+    # the block set: exactly the blocks whose box is closer than the radius to the centre
+    for k in map(tuple, marked.tolist()):
+        lo, hi = np.array(k) * 0.8, (np.array(k) + 1) * 0.8
+        assert np.linalg.norm(np.maximum(lo - 0.0, 0) + np.maximum(0.0 - hi, 0)) < 5.0 + 1e-5
+    assert len(marked) > 1200 and (-7, 0, 0) in set(map(tuple, marked.tolist())) and (-8, 0, 0) not in set(map(tuple, marked.tolist()))
+    # occupancy flavour: log odds -2e-4 where unobserved
+    mo = orc.OracleMap(voxel)
+    mo.integrate_occupancy(depth, T, cam)
+    n_before = len(mo.occupancy_block_indices())
+    mo.mark_unobserved_free_inside_radius((0.0, 0.0, 0.0), 2.0, occupancy=True)
+    layer = mo.occupancy_layer()
+    assert len(layer) > n_before and layer[(-1, 0, 0)].max() == np.float32(-2e-4) and layer[(-1, 0, 0)].min() == np.float32(-2e-4)
