@@ -38,3 +38,14 @@ def test_oracle_thread_count_does_not_change_results():
         sums.append((layer_checksum(m.tsdf_layer(), ("distance", "weight")), layer_checksum(m.esdf_layer(), ESDF_FIELDS)))
     orc.set_num_threads(n_threads)
     assert sums[0] == sums[1]
+
+
+def test_oracle_reproduces_the_f_rows_fixture():
+    """tests/golden/f_rows_small.npz (make_golden_f_rows.py): occupancy, colour, decay, freespace, 2-D slice, mark-free."""
+    from golden_f_rows import run_oracle
+    g = np.load(os.path.join(GOLDEN, "c2_small.npz"))
+    want = np.load(os.path.join(GOLDEN, "f_rows_small.npz"))
+    got = run_oracle(g)
+    assert set(got) == set(want.files)
+    for k, v in got.items():
+        assert int(want[k]) == v, k

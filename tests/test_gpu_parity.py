@@ -603,3 +603,14 @@ def test_mark_unobserved_free_inside_radius(gpu, mode):
     with pytest.raises(Exception):
         m.mark_unobserved_tsdf_free_inside_radius(c2, 0.0)
     m.close()
+
+
+def test_golden_fixture_f_rows(gpu):
+    """The CUDA path reproduces tests/golden/f_rows_small.npz (the oracle's checksums of the SURVEY.md 8(f) rows)."""
+    from golden_f_rows import run_gpu
+    g = np.load(os.path.join(GOLDEN, "c2_small.npz"))
+    want = np.load(os.path.join(GOLDEN, "f_rows_small.npz"))
+    got = run_gpu(g)
+    assert set(got) == set(want.files)
+    for k, v in got.items():
+        assert int(want[k]) == v, k
