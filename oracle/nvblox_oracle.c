@@ -1686,18 +1686,17 @@ void or_sphere_trace_image(const OrMap* map, const float* T_L_C, const OrCamera*
 /* ViewCalculator::getBlocksInImageViewProjection (view_calculator_impl.h:29-78) + getVisibleBlocksByProjection<Camera>
  * (src/integrators/view_calculator.cu:380-417), then reduceBlocksToThoseInTruncationBand
  * (projective_appearance_integrator.cu:378-481). */
-static List color_blocks_in_view_and_band(const OrMap* map, const float* T_L_C, const OrCamera* cam, const OrColorParams* P,
-                                          float truncation_distance_m) {
+static List view_projection_blocks(float block_size, const float* T_L_C, const OrCamera* cam, float max_distance,
+                                   int32_t workspace_bounds_type, const float* workspace_min, const float* workspace_max) {
   List out = {0};
-  const float max_distance = P->max_integration_distance_m + truncation_distance_m;
   v3 mn, mx;
   cam_view_aabb(cam, T_L_C, 1e-6f, max_distance, &mn, &mx);
   OrTsdfParams ws;
   memset(&ws, 0, sizeof(ws));
-  ws.workspace_bounds_type = P->workspace_bounds_type;
-  for (int a = 0; a < 3; a++) ws.workspace_min[a] = P->workspace_min[a], ws.workspace_max[a] = P->workspace_max[a];
+  ws.workspace_bounds_type = workspace_bounds_type;
+  for (int a = 0; a < 3; a++) ws.workspace_min[a] = workspace_min[a], ws.workspace_max[a] = workspace_max[a];
   if (!apply_workspace_bounds(&ws, &mn, &mx)) return out;
-  const i3 lo = block_index_from_position(map->block_size, mn), hi = block_index_from_position(map->block_size, mx);
+  const i3 lo = block_index_from_position(block_size, mn), hi = block_index_from_position(block_size, mx);
   float T_C_L[16];
   invert_isometry(T_L_C, T_C_L);
   /* Camera::getNormalizedViewport(getViewportMargin(height)) (src/sensors/camera.cpp:85-96, view_calculator_impl.h:81-83) */
@@ -1708,22 +1707,43 @@ static List color_blocks_in_view_and_band(const OrMap* map, const float* T_L_C, 
     for (int y = lo.y; y <= hi.y; y++)
       for (int z = lo.z; z <= hi.z; z++) { /* getBlockIndicesTouchedByBoundingBox order (bounding_boxes_impl.h:28-53) */
         const i3 k = {x, y, z};
-        const v3 c_L = {map->block_size * ((float)x + 0.5f), map->block_size * ((float)y + 0.5f),
-                        map->block_size * ((float)z + 0.5f)}; /* getCenterPositionFromBlockIndex */
+        const v3 c_L = {block_size * ((float)x + 0.5f), block_size * ((float)y + 0.5f),
+                        block_size * ((float)z + 0.5f)}; /* getCenterPositionFromBlockIndex */
         const v3 p = transform_point(T_C_L, c_L);
         if (!(p.z > 1e-6f)) continue;
         if (!(p.z >= 1e-6f)) continue; /* projectToNormalizedCoordinates (camera_impl.h:65-75) */
         const float un = p.x / p.z, vn = p.y / p.z;
         /* Eigen::AlignedBox::contains: (min <= p).all() && (p <= max).all() */
         if (!(vmin.x <= un && vmin.y <= vn && un <= vmax.x && vn <= vmax.y)) continue;
-        const int32_t slot = hash_find(&map->tsdf.hash, k);
-        if (slot < 0) continue;
-        const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(&map->tsdf, slot);
-        int in_band = 0;
-        for (int v = 0; v < VPB && !in_band; v++)
-          if (t[v].weight > 0.0f && fabsf(t[v].distance) < truncation_distance_m) in_band = 1; /* checkBlocksInTruncationBand */
-        if (in_band) list_push(&out, k);
+        list_push(&out, k);
       }
+  return out;
+}
+/* ViewCalculator::getBlocksInImageViewProjection, exposed for the known-answer tests. */
+int32_t or_view_projection_blocks(float block_size, const float* T_L_C, const OrCamera* cam, float max_distance,
+                                  int32_t* out_xyz, int32_t cap) {
+  const float zero[3] = {0.0f, 0.0f, 0.0f};
+  List l = view_projection_blocks(block_size, T_L_C, cam, max_distance, OR_WS_UNBOUNDED, zero, zero);
+  const int32_t n = copy_out(&l, out_xyz, cap);
+  list_free(&l);
+  return n;
+}
+static List color_blocks_in_view_and_band(const OrMap* map, const float* T_L_C, const OrCamera* cam, const OrColorParams* P,
+                                          float truncation_distance_m) {
+  List in_view = view_projection_blocks(map->block_size, T_L_C, cam, P->max_integration_distance_m + truncation_distance_m,
+                                        P->workspace_bounds_type, P->workspace_min, P->workspace_max);
+  List out = {0};
+  for (int32_t i = 0; i < in_view.n; i++) {
+    const i3 k = in_view.v[i];
+    const int32_t slot = hash_find(&map->tsdf.hash, k);
+    if (slot < 0) continue;
+    const OrTsdfVoxel* t = (const OrTsdfVoxel*)layer_block(&map->tsdf, slot);
+    int in_band = 0;
+    for (int v = 0; v < VPB && !in_band; v++)
+      if (t[v].weight > 0.0f && fabsf(t[v].distance) < truncation_distance_m) in_band = 1; /* checkBlocksInTruncationBand */
+    if (in_band) list_push(&out, k);
+  }
+  list_free(&in_view);
   return out;
 }
 

@@ -183,6 +183,8 @@ def lib():
     u8p = C.POINTER(C.c_uint8)
     L.or_mark_unobserved_free_inside_radius.argtypes = [vp, C.c_int32, fp, C.c_float, C.c_float, ip, C.c_int32]
     L.or_mark_unobserved_free_inside_radius.restype = C.c_int32
+    L.or_view_projection_blocks.argtypes = [C.c_float, fp, C.POINTER(Camera), C.c_float, ip, C.c_int32]
+    L.or_view_projection_blocks.restype = C.c_int32
     L.or_round_through_half.argtypes = [C.c_float]
     L.or_round_through_half.restype = C.c_float
     L.or_sphere_trace_ray.argtypes = [vp, fp, fp, C.c_float, C.c_int32, C.c_float, C.c_float, fp]
@@ -278,6 +280,15 @@ def default_freespace_params(**kw):
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def view_projection_blocks(T_L_C, cam, block_size, max_distance, cap=1 << 20):
+    """ViewCalculator::getBlocksInImageViewProjection(T_L_C, camera, block_size, max_distance) -> (n, 3) block indices."""
+    T = colmajor(T_L_C)
+    out = np.zeros((cap, 3), dtype=np.int32)
+    n = lib().or_view_projection_blocks(float(block_size), _fp(T), C.byref(cam), float(max_distance), _ip(out), cap)
+    assert n <= cap
+    return out[:n].copy()
 
 
 def default_color_params(**kw):

@@ -1178,3 +1178,123 @@ def test_mark_unobserved_free_inside_radius_generates_esdf_in_fake_observed_area
     mo.mark_unobserved_free_inside_radius((0.0, 0.0, 0.0), 2.0, occupancy=True)
     layer = mo.occupancy_layer()
     assert len(layer) > n_before and layer[(-1, 0, 0)].max() == np.float32(-2e-4) and layer[(-1, 0, 0)].min() == np.float32(-2e-4)
+
+
+def _box_room_view():
+    """The 8 m box room seen from its centre along +x (tests/test_mapper.cpp:128-149, 186-207)."""
+    scene = syn.Scene()
+    scene.add_plane(2, -4.0).add_plane(2, 4.0).add_plane(0, -4.0).add_plane(0, 4.0).add_plane(1, -4.0).add_plane(1, 4.0)
+    cs = syn.PinholeCamera(300.0, 300.0, 320.0, 240.0, 640, 480)
+    cam = orc.Camera(300.0, 300.0, 320.0, 240.0, 640, 480)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]], np.float32)  # Quaternionf(0.5, 0.5, 0.5, 0.5)
+    return syn.render_depth(scene, cs, T, max_dist=20.0), T, cam
+
+
+def test_mapper_integrate_depth_with_an_all_zero_mask():
+    """IntegrateDepthWithMask (tests/test_mapper.cpp:127-183): with every pixel masked out (non-inverted mode: 0 = inactive) only
+    free space is carved: every observed voxel sits at the truncation distance."""
+    depth, T, cam = _box_room_view()
+    m = orc.OracleMap(0.1)
+    tp = orc.default_tsdf_params(truncation_distance_vox=2.0)
+    m.integrate_depth(depth, T, cam, tp, mask=np.zeros(depth.shape, np.uint8), mask_mode=0)
+    n = 0
+    for blk in m.tsdf_layer().values():
+        seen = blk["weight"] > 0
+        assert np.all(blk["distance"][seen] >= np.float32(2.0) * np.float32(0.1))
+        n += int(seen.sum())
+    assert n > 0
+
+
+def test_workspace_bounds_check_allocated_blocks():
+    """CheckAllocatedBlocks (tests/test_workspace_bounds.cpp:38-118): a plane 5 m ahead; every allocated block has a voxel
+    (origin) inside the bounds; unbounded > height bounds > bounding box > 0 blocks."""
+    cs = syn.PinholeCamera(300.0, 300.0, 320.0, 240.0, 640, 480)
+    cam = orc.Camera(300.0, 300.0, 320.0, 240.0, 640, 480)
+    scene = syn.Scene()
+    scene.add_plane(2, 5.0)
+    T = np.eye(4, dtype=np.float32)
+    depth = syn.render_depth(scene, cs, T, max_dist=20.0)
+    lo, hi = np.array([-3.0, -3.0, 2.0], np.float32), np.array([3.0, 3.0, 4.0], np.float32)
+    counts = {}
+    for btype in (0, 1, 2):  # kUnbounded, kHeightBounds, kBoundingBox
+        m = orc.OracleMap(0.1)
+        tp = orc.default_tsdf_params(workspace_bounds_type=btype)
+        tp.workspace_min[:], tp.workspace_max[:] = [float(v) for v in lo], [float(v) for v in hi]
+        updated = m.integrate_depth(depth, T, cam, tp)
+        assert len(updated) > 0
+        for k in m.tsdf_layer():
+            x, y, z = np.meshgrid(*[(np.float32(k[a]) * np.float32(0.8) + np.arange(8, dtype=np.float32) * np.float32(0.1))
+                                    for a in range(3)], indexing="ij")
+            if btype == 1:
+                assert ((z >= lo[2]) & (z <= hi[2])).any(), k
+            elif btype == 2:
+                inside = (x >= lo[0]) & (x <= hi[0]) & (y >= lo[1]) & (y <= hi[1]) & (z >= lo[2]) & (z <= hi[2])
+                assert inside.any(), k
+        counts[btype] = len(m.tsdf_layer())
+    assert counts[2] > 0 and counts[1] > counts[2] and counts[0] > counts[2]
+
+
+# ---------------------------------------------------------------------------
+# tests/test_camera.cu, tests/test_frustum.cpp:487-520, MarkUnobservedFree of the two projective integrators
+# ---------------------------------------------------------------------------
+def _test_camera():
+    return orc.Camera(300.0, 300.0, 320.0, 240.0, 640, 480)  # getTestCamera (tests/test_camera.cu:46-55)
+
+
+def test_camera_projection_cases():
+    """PointsInView (:86-103), CenterPixel (:105-119), BehindCamera (:121-138), OutsideImagePlane (:140-173),
+    InvalidPointProjections (:406-448)."""
+    cam = _test_camera()
+    rng = np.random.default_rng(0)
+    for _ in range(1000):
+        u = np.array([rng.uniform(0, 640), rng.uniform(0, 480)], np.float32)
+        ray = orc.camera_vector_from_image_plane(cam, float(u[0]), float(u[1]))
+        p = np.float32(rng.uniform(1.0, 1000.0)) * ray
+        uv = orc.camera_project(cam, p)
+        assert uv is not None and np.all(np.abs(uv - u) < 1e-4 * 10)  # kFloatEpsilon on pixel coordinates up to 640
+        assert orc.camera_project(cam, p * np.array([1, 1, -1], np.float32)) is None  # behind the camera
+    uv = orc.camera_project(cam, np.array([0, 0, rng.uniform(1, 1000)], np.float32))
+    assert np.all(np.abs(uv - (320.0, 240.0)) < 1e-4)
+    for _ in range(1000):
+        du = rng.choice([-1, 1]) * rng.uniform(320.0, 5 * 640.0)
+        dv = rng.choice([-1, 1]) * rng.uniform(240.0, 5 * 480.0)
+        ray = np.array([du / 300.0, dv / 300.0, 1.0], np.float32)
+        assert orc.camera_project(cam, np.float32(rng.uniform(1, 1000)) * ray) is None
+    assert orc.camera_project(cam, np.array([0, 0, 5], np.float32)) is not None
+    for bad in (np.nan, np.inf, -np.inf):
+        for coord in range(3):
+            p = np.array([0, 0, 5], np.float32)
+            p[coord] = bad
+            assert orc.camera_project(cam, p) is None
+    assert orc.camera_project(cam, np.array([1, 1, -1], np.float32)) is None
+    assert orc.camera_project(cam, np.array([1, 1, 0.5e-6], np.float32)) is None  # closer than kDefaultMinProjectionDepth
+    assert orc.camera_project(cam, np.array([0, 0, 1e-6], np.float32)) is not None  # exactly at it
+
+
+def test_view_projection_block_count():
+    """getBlocksInImageViewProjection_specialization (tests/test_frustum.cpp:487-520): identity pose, the test camera, 5 cm voxels,
+    10 m -> exactly 23042 blocks (kExpectedNumBlocks)."""
+    b = orc.view_projection_blocks(np.eye(4, dtype=np.float32), _test_camera(), np.float32(8) * np.float32(0.05), 10.0)
+    assert len(b) == 23042
+    assert len({tuple(r) for r in b.tolist()}) == 23042
+    centers = (b.astype(np.float32) + np.float32(0.5)) * np.float32(0.4)
+    assert (centers[:, 2] > 0).all() and centers[:, 2].max() < 10.0 + 0.4
+
+
+@pytest.mark.parametrize("occupancy", [False, True])
+def test_mark_unobserved_free_on_an_empty_layer(occupancy):
+    """TsdfIntegratorTest.MarkUnobservedFree (tests/test_tsdf_integrator.cpp:336-363) and OccupancyIntegratorTest.MarkUnobservedFree
+    (tests/test_occupancy_integrator.cpp:221-246): radius 1 m around the origin of an empty 10 cm layer."""
+    m = orc.OracleMap(0.1)
+    assert len(m.tsdf_block_indices()) == 0
+    blocks = m.mark_unobserved_free_inside_radius((0.0, 0.0, 0.0), 1.0, occupancy=occupancy)
+    assert len(blocks) > 0
+    if occupancy:
+        layer = m.occupancy_layer()
+        assert len(layer) == len(blocks) and all((v < 0.0).all() for v in layer.values())
+    else:
+        layer = m.tsdf_layer()
+        assert len(layer) == len(blocks)
+        for v in layer.values():
+            assert np.all(np.abs(v["distance"] - np.float32(4.0) * np.float32(0.1)) < 1e-3) and np.all(v["weight"] > 0.0)
