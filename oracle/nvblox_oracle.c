@@ -2157,6 +2157,12 @@ void or_tsdf_set_block(OrMap* m, const int32_t xyz[3], const OrTsdfVoxel* in) {
   memcpy(layer_block(&m->tsdf, s), in, m->tsdf.block_bytes);
 }
 
+void or_freespace_set_block(OrMap* m, const int32_t xyz[3], const OrFreespaceVoxel* in) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = layer_allocate(&m->freespace, k);
+  memcpy(layer_block(&m->freespace, s), in, m->freespace.block_bytes);
+}
+
 void or_occupancy_set_block(OrMap* m, const int32_t xyz[3], const float* in) {
   i3 k = {xyz[0], xyz[1], xyz[2]};
   int32_t s = layer_allocate(&m->occ, k);

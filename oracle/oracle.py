@@ -175,6 +175,8 @@ def lib():
     L.or_esdf_get_block.argtypes = [vp, ip, vp]
     L.or_esdf_get_block.restype = C.c_int32
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
+    L.or_freespace_set_block.argtypes = [vp, ip, vp]
+    L.or_freespace_set_block.restype = None
     L.or_occupancy_set_block.argtypes = [vp, ip, vp]
     L.or_occupancy_set_block.restype = None
     L.or_esdf_integrate_slice_planar.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), fp, C.c_float,
@@ -646,6 +648,11 @@ class OracleMap:
         k = np.asarray(idx, dtype=np.int32)
         v = np.ascontiguousarray(voxels, dtype=TSDF_VOXEL_DTYPE).reshape(8, 8, 8)
         lib().or_tsdf_set_block(self._h, _ip(k), v.ctypes.data)
+
+    def set_freespace_block(self, idx, voxels):
+        k = np.asarray(idx, dtype=np.int32)
+        v = np.ascontiguousarray(voxels, dtype=FREESPACE_VOXEL_DTYPE).reshape(8, 8, 8)
+        lib().or_freespace_set_block(self._h, _ip(k), v.ctypes.data)
 
     def tsdf_layer(self):
         """{(x,y,z): (8,8,8) structured array} for every allocated TSDF block."""

@@ -137,15 +137,21 @@ def check_slicing_sites(esdf_layer, exp):
 def tsdf_layer_from_distance(distance_fn, aabb_min, aabb_max, voxel_size, truncation_m):
     """Scene::generateLayerFromScene (primitives/internal/impl/scene_impl.h:105-140): the blocks touched by the AABB are
     allocated; every voxel whose centre lies in the AABB gets the ground-truth distance clipped to +-truncation and
-    weight 1, the others stay unset. distance_fn maps (..., 3) float64 points to signed distances.
+    weight 1, the others stay unset. distance_fn maps (..., 3) float32 points to signed distances.
     -> (block indices (n, 3) int32, voxels (n, 8, 8, 8) TSDF_DT)."""
     bs = np.float32(8) * np.float32(voxel_size)
     lo = [int(np.floor(np.float32(a) / bs)) for a in aabb_min]  # getBlockIndicesTouchedByBoundingBox
     hi = [int(np.floor(np.float32(a) / bs)) for a in aabb_max]
-    ax = [(np.arange(8 * (h - l + 1)) + 0.5) * float(voxel_size) + l * float(bs) for l, h in zip(lo, hi)]
-    P = np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1)
+    # getCenterPositionFromBlockIndexAndVoxelIndex in binary32, like the reference (indexing_impl.h:51-81)
+    vs32, half32 = bs * np.float32(1.0 / 8), bs * np.float32(0.5 / 8)
+    ax = []
+    for l, h in zip(lo, hi):
+        b = np.repeat(np.arange(l, h + 1), 8).astype(np.float32)
+        v = np.tile(np.arange(8), h - l + 1).astype(np.float32)
+        ax.append((bs * b + vs32 * v) + half32)
+    P = np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1)  # float32
     D = np.clip(distance_fn(P), -truncation_m, truncation_m).astype(np.float32)
-    inside = np.all((P >= np.asarray(aabb_min, float)) & (P <= np.asarray(aabb_max, float)), axis=-1)
+    inside = np.all((P >= np.asarray(aabb_min, np.float32)) & (P <= np.asarray(aabb_max, np.float32)), axis=-1)
     D = np.where(inside, D, np.float32(0.0)).astype(np.float32)
     W = inside.astype(np.float32)
     n = [h - l + 1 for l, h in zip(lo, hi)]
