@@ -675,6 +675,9 @@ static float weighting(int type, float measured, float voxel_depth, float trunc)
   }
 }
 
+/* WeightingFunction::operator(), exposed for the known-answer tests (tests/test_weighting_function.cpp). */
+float or_weighting(int32_t type, float measured, float voxel_depth, float trunc) { return weighting(type, measured, voxel_depth, trunc); }
+
 /* UpdateTsdfVoxelFunctor::operator() (integrators/internal/cuda/impl/
  * projective_tsdf_integrator_impl.cuh:30-90). */
 static void tsdf_update_voxel(float surface_depth, float voxel_depth, int is_active,

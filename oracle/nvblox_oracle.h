@@ -256,6 +256,7 @@ int32_t or_mark_unobserved_free_inside_radius(OrMap* map, int32_t occupancy, con
 int32_t or_view_projection_blocks(float block_size, const float* T_L_C, const OrCamera* cam, float max_distance,
                                   int32_t* out_xyz, int32_t cap);
 void or_freespace_set_block(OrMap* m, const int32_t xyz[3], const OrFreespaceVoxel* in);
+float or_weighting(int32_t type, float measured, float voxel_depth, float trunc);
 void or_default_color_params(OrColorParams* p);
 float or_round_through_half(float f);
 int32_t or_sphere_trace_ray(const OrMap* map, const float origin[3], const float direction[3], float truncation_distance_m,

@@ -187,6 +187,8 @@ def lib():
     L.or_mark_unobserved_free_inside_radius.restype = C.c_int32
     L.or_view_projection_blocks.argtypes = [C.c_float, fp, C.POINTER(Camera), C.c_float, ip, C.c_int32]
     L.or_view_projection_blocks.restype = C.c_int32
+    L.or_weighting.argtypes = [C.c_int32, C.c_float, C.c_float, C.c_float]
+    L.or_weighting.restype = C.c_float
     L.or_round_through_half.argtypes = [C.c_float]
     L.or_round_through_half.restype = C.c_float
     L.or_sphere_trace_ray.argtypes = [vp, fp, fp, C.c_float, C.c_int32, C.c_float, C.c_float, fp]
@@ -299,6 +301,11 @@ def default_color_params(**kw):
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def weighting(wtype, measured, voxel_depth, truncation_distance):
+    """WeightingFunction(type)(measured depth, voxel depth, truncation distance)."""
+    return float(lib().or_weighting(int(wtype), float(measured), float(voxel_depth), float(truncation_distance)))
 
 
 def round_through_half(f):

@@ -1298,3 +1298,18 @@ def test_mark_unobserved_free_on_an_empty_layer(occupancy):
         assert len(layer) == len(blocks)
         for v in layer.values():
             assert np.all(np.abs(v["distance"] - np.float32(4.0) * np.float32(0.1)) < 1e-3) and np.all(v["weight"] > 0.0)
+
+
+def test_weighting_function_unit_cases():
+    """tests/test_weighting_function.cpp: TestConstantWeight (:21-46), TestConstantDropoffWeight (:48-85), TestInverseSquare
+    (:87-118), TestLinearWithMax (:120-150): surface at 10 m, truncation 1 m."""
+    def w(t, voxel_depth):
+        return orc.weighting(t, 10.0, voxel_depth, 1.0)
+    eps = 1e-6
+    assert all(abs(w(0, d) - 1.0) < eps for d in (10.0, 8.0, 11.0))
+    for d, want in ((10.0, 1.0), (8.0, 1.0), (11.0, 0.0), (10.5, 0.5), (0.0, 1.0)):
+        assert abs(w(1, d) - want) < eps
+    for d, want in ((10.0, 0.01), (5.0, 0.04), (11.0, 0.0), (0.0, 1.0)):
+        assert abs(w(2, d) - want) < eps
+    for d, want in ((0.0, 1.0), (0.5, 1.0), (1.0, 1.0), (5.0, 0.2)):
+        assert abs(w(5, d) - want) < eps
