@@ -12,6 +12,7 @@
 #pragma once
 #include <vector>
 #include "nvblox/integrators/weighting_function.h"
+#include "nvblox/geometry/plane.h"
 #include "nvblox/map/layer.h"
 #include "nvblox/sensors/camera.h"
 #include "nvblox/sensors/image.h"
@@ -214,6 +215,15 @@ class EsdfIntegrator {
     for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
     b200_detail::check(nvb_esdf_integrate_slice_blocks(m_, raw.data(), (int32_t)block_indices.size()), "integrateSlice", nvb_last_error());
   }
+  // integrateSlice(layer, block_indices, ground_plane, esdf_layer) (esdf_integrator.h:136-173)
+  template <typename LayerT>
+  void integrateSlice(const LayerT&, const std::vector<Index3D>& block_indices, const Plane& ground_plane, EsdfLayer*) {
+    std::vector<int32_t> raw(block_indices.size() * 3 + 3);
+    for (size_t i = 0; i < block_indices.size(); i++) for (int a = 0; a < 3; a++) raw[3 * i + a] = block_indices[i][a];
+    const float pl[4] = {ground_plane.normal()[0], ground_plane.normal()[1], ground_plane.normal()[2], ground_plane.d()};
+    b200_detail::check(nvb_esdf_integrate_slice_planar_blocks(m_, pl, raw.data(), (int32_t)block_indices.size()), "integrateSlice",
+                       nvb_last_error());
+  }
   float slice_height_above_plane_m() const { return getSlice().slice_height_above_plane_m; }
   void slice_height_above_plane_m(float v) { auto p = getSlice(); p.slice_height_above_plane_m = v; setSlice(p); }
   float slice_height_thickness_m() const { return getSlice().slice_height_thickness_m; }
@@ -292,6 +302,12 @@ class Mapper {
   // Mapper::updateEsdfSlice (mapper.h:343): the 2-D ESDF on the slice layer
   void updateEsdfSlice(UpdateFullLayer full = UpdateFullLayer::kNo) {
     b200_detail::check(nvb_mapper_update_esdf_slice(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdfSlice", nvb_last_error());
+  }
+  // Mapper::updateEsdfSlice(update_full_layer, ground_plane) (mapper.h:338-344): the band follows the ground plane
+  void updateEsdfSlice(UpdateFullLayer full, const Plane& ground_plane) {
+    const float pl[4] = {ground_plane.normal()[0], ground_plane.normal()[1], ground_plane.normal()[2], ground_plane.d()};
+    b200_detail::check(nvb_mapper_update_esdf_slice_planar(m_, pl, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdfSlice",
+                       nvb_last_error());
   }
   void clear() { b200_detail::check(nvb_mapper_clear(m_), "clear", nvb_last_error()); }
   // Mapper::updateFreespace(update_time_ms, T_L_C, camera, depth_frame, update_full_layer) (mapper.h:196-214)

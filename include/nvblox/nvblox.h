@@ -1,6 +1,8 @@
 // Umbrella header of the source-compatible subset (reference: nvblox/include/nvblox/nvblox.h).
 #pragma once
 #include "nvblox/core/types.h"
+#include "nvblox/geometry/plane.h"
+#include "nvblox/integrators/esdf_slicer.h"
 #include "nvblox/integrators/weighting_function.h"
 #include "nvblox/map/blox.h"
 #include "nvblox/map/layer.h"

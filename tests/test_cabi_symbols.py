@@ -62,13 +62,13 @@ def test_fails_loudly_without_a_gpu(built):
     assert "no CPU fallback" in str(ei.value)
 
 
-def _compile_cpp_dropin(tmp_path):
+def _compile_cpp_dropin(tmp_path, name="test_mapper_dropin"):
     import subprocess
     from isaac_ros_nvblox_b200 import _lib
-    exe = str(tmp_path / "test_mapper_dropin")
-    src = os.path.join(ROOT, "tests", "cpp", "test_mapper_dropin.cpp")
+    exe = str(tmp_path / name)
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
     libdir = os.path.dirname(_lib.LIB_PATH)
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
            "-L", libdir, "-lnvblox_b200", "-Wl,-rpath," + libdir]
     subprocess.check_call(cmd)
     return exe
@@ -78,7 +78,8 @@ def test_cpp_mirror_headers_compile_and_link(built, tmp_path):
     """include/nvblox/*.h (the source-compatible subset of the reference's headers) builds with plain g++
     against the C-ABI library; without a GPU the program reports that and exits 77."""
     import subprocess
-    exe = _compile_cpp_dropin(tmp_path)
     from isaac_ros_nvblox_b200 import _lib
-    if _lib.load().nvb_device_count() == 0:
-        assert subprocess.call([exe]) == 77
+    for name in ("test_mapper_dropin", "test_mirror_surface"):  # the second covers Plane, planar slices and EsdfSlicer
+        exe = _compile_cpp_dropin(tmp_path, name)
+        if _lib.load().nvb_device_count() == 0:
+            assert subprocess.call([exe]) == 77
