@@ -83,3 +83,14 @@ def test_cpp_mirror_headers_compile_and_link(built, tmp_path):
         exe = _compile_cpp_dropin(tmp_path, name)
         if _lib.load().nvb_device_count() == 0:
             assert subprocess.call([exe]) == 77
+
+
+def test_header_is_strict_c99(tmp_path):
+    """include/nvblox_b200.h is the FFI boundary (cgo / ctypes / JNI read it as C): it must compile as plain C99."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "nvblox_b200.h"\n'
+                   'int use(void) { NvbColorParams c; NvbTsdfParams t; nvb_default_color_params(&c); nvb_default_tsdf_params(&t);\n'
+                   '  return (int)sizeof(NvbEsdfVoxel) + (int)sizeof(NvbColorVoxel) + (int)sizeof(NvbFreespaceVoxel); }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           str(src)])
