@@ -3,8 +3,9 @@
  *
  * CPU restatement of the reference's depth-integration hot path. Citations are
  * relative to /root/reference/nvblox_ros/nvblox_core/nvblox/ ("C/" in SURVEY.md).
- * Parity: pinned against the reference's known-answer tests only (the reference
- * itself cannot be built in this environment) -- see tests/test_oracle_kat.py.
+ * Parity: "parity unpinned" against a reference binary -- pinned against the reference's
+ * known-answer tests only (the reference itself cannot be built in this environment): see
+ * tests/test_oracle_kat.py, tests/test_oracle_color_kat.py, tests/test_oracle_esdf_scenes_kat.py.
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared
  */

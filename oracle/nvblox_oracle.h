@@ -11,10 +11,11 @@
  * reference legs may load this library. The product path
  * (isaac_ros_nvblox_b200/) never does.
  *
- * Parity status: the reference cannot be built here (Eigen/stdgpu/glog/... are
+ * Parity status: PARITY UNPINNED against a reference binary. The reference cannot be built here (Eigen/stdgpu/glog/... are
  * un-vendored network fetches and there is no GPU), so this oracle is pinned
- * against the reference's own known-answer tests (tests/test_oracle_kat.py)
- * and NOT against a reference binary.
+ * against the reference's own known-answer tests (tests/test_oracle_kat.py,
+ * test_oracle_color_kat.py, test_oracle_esdf_scenes_kat.py) and NOT against a
+ * reference binary.
  *
  * Arithmetic: IEEE binary32, one rounding per operation, no FMA contraction
  * (compile with -ffp-contract=off). 3-term sums use Eigen's unrolled

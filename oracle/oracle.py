@@ -2,6 +2,7 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this module (see oracle/nvblox_oracle.h).
+Parity unpinned against a reference binary (none can be built here): the oracle is pinned to the reference's own tests.
 """
 import ctypes as C
 import os
