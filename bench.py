@@ -133,7 +133,9 @@ def cpu_threads():
 
 def cpu_baseline(frames_np, cam_s, sample_frames, voxel=VOXEL):
     """The reference's algorithm on the host cores (oracle port, OpenMP where the reference's kernels
-    are race-free): TSDF + ESDF on the first `sample_frames` frames of the same sequence."""
+    are race-free): TSDF + ESDF on the first `sample_frames` frames of the same sequence (default: all of them,
+    i.e. the same work as one GPU step). Returns the baseline record and the oracle map (the parity checker of
+    the post-timing check)."""
     from oracle import oracle as orc
     orc.set_num_threads(cpu_threads())
     ocam = orc.Camera(cam_s.fu, cam_s.fv, cam_s.cu, cam_s.cv, cam_s.width, cam_s.height)
@@ -143,14 +145,47 @@ def cpu_baseline(frames_np, cam_s, sample_frames, voxel=VOXEL):
         b = o.integrate_depth(depth, T, ocam)
         o.integrate_esdf(b)
     dt = time.perf_counter() - t0
+    whole = sample_frames == len(frames_np)
     return {"value": sample_frames / dt, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": "first %d frames of the same sequence (raycast+TSDF+ESDF), %.1f s" % (sample_frames, dt)}
+            "sample": ("the whole %d-frame step" if whole else "first %d frames of the same sequence") % sample_frames
+                      + " (raycast+TSDF+ESDF), %.1f s" % dt}, o
+
+
+def layer_checksum(layer, fields):
+    """Order-independent checksum of a {block index: voxels} layer (sum of per-block CRC32s); the same function as
+    tests/helpers.py::layer_checksum."""
+    import zlib
+    total = 0
+    for k in sorted(layer):
+        h = zlib.crc32(np.asarray(k, dtype=np.int32).tobytes())
+        for f in fields:
+            h = zlib.crc32(np.ascontiguousarray(layer[k][f]).tobytes(), h)
+        total = (total + h) & 0xFFFFFFFFFFFF
+    return total
+
+
+ESDF_FIELDS = ("squared_distance_vox", "parent_direction", "is_inside", "observed", "is_site")
+
+
+def parity_check(m, o):
+    """Post-timing check, outside every timed region: the map the benchmarked pipeline just built (device-resident
+    frames, asynchronous calls, ESDF wavefront overlapping the next frame's TSDF chain) against the oracle's map of
+    the same sequence: allocated block sets, TSDF bits, all five EsdfVoxel fields."""
+    t_gpu, e_gpu = m.tsdf_layer().as_dict(), m.esdf_layer().as_dict()
+    t_cpu, e_cpu = o.tsdf_layer(), o.esdf_layer()
+    ok = set(t_gpu) == set(t_cpu) and set(e_gpu) == set(e_cpu)
+    cs = {"tsdf_gpu": layer_checksum(t_gpu, ("distance", "weight")), "tsdf_oracle": layer_checksum(t_cpu, ("distance", "weight")),
+          "esdf_gpu": layer_checksum(e_gpu, ESDF_FIELDS), "esdf_oracle": layer_checksum(e_cpu, ESDF_FIELDS)}
+    ok = ok and cs["tsdf_gpu"] == cs["tsdf_oracle"] and cs["esdf_gpu"] == cs["esdf_oracle"]
+    return bool(ok), {"tsdf_blocks": len(t_gpu), "esdf_blocks": len(e_gpu), "checksums": cs,
+                      "what": "final TSDF + ESDF layers of the device-resident asynchronous pipeline (the timed one) vs the "
+                              "oracle on the same frames: block sets equal, CRC32 of the voxel bytes equal"}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cam_s, frames = make_frames(args.cpu_sample_frames, 0, 1)
+    cam_s, frames = make_frames(min(args.cpu_sample_frames, args.frames), 0, 1)
     from oracle import oracle as orc
     orc.set_num_threads(cpu_threads())
     ocam = orc.Camera(cam_s.fu, cam_s.fv, cam_s.cu, cam_s.cv, cam_s.width, cam_s.height)
@@ -167,12 +202,13 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     value = args.steps * len(frames) / dt
-    sample = "each step = first %d frames of the sequence on the host cores" % len(frames)
+    sample = ("each step = the whole %d-frame sequence on the host cores (same work as one GPU step)" if len(frames) == args.frames
+              else "each step = first %d frames of the sequence on the host cores") % len(frames)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": len(frames)},
+        "config": {"workload": WORKLOAD, "frames_per_step": len(frames), "voxel_size_m": VOXEL},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -186,7 +222,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=80)
-    ap.add_argument("--cpu-sample-frames", type=int, default=12)
+    ap.add_argument("--cpu-sample-frames", type=int, default=80,
+                    help="frames per step of the CPU arm (default: the whole sequence = the same work as a GPU step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--esdf-host-loop", action="store_true", help="reference-like per-ring launches")
     ap.add_argument("--voxel-size", type=float, default=VOXEL,
@@ -229,12 +266,12 @@ def main():
     stream = torch.cuda.ExternalStream(m.cuda_stream(), device=torch.device("cuda", local_rank))
     frame_bytes = ROWS * COLS * 4
 
-    def step_device():
+    def step_device(merge=True):
         m.clear()
         for i in range(F):
             m.integrate_depth_device(depth_dev[i].data_ptr(), ROWS, COLS, poses[i], cam)
             m.update_esdf(sync=False)
-        if world > 1:
+        if world > 1 and merge:
             multi_gpu.merge_updated_blocks(m, stream)
 
     def step_e2e():
@@ -399,9 +436,15 @@ def main():
                      "esdf_swept_per_frame": tot["swept"] / F, "esdf_face_passes_per_frame": tot["face_passes"] / F,
                      "esdf_clear_candidates_per_frame": tot["clear_candidates"] / F}
 
-    cpu = None
+    cpu, parity_ok, parity = None, None, None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(frames, cam_s, min(args.cpu_sample_frames, F), voxel)
+        cpu, omap = cpu_baseline(frames, cam_s, min(args.cpu_sample_frames, F), voxel)
+        if min(args.cpu_sample_frames, F) == F:
+            # the oracle has just built the map of the whole step: check the benchmarked pipeline against it
+            step_device(merge=False)  # rank 0 only: no collective here
+            m.synchronize()
+            parity_ok, parity = parity_check(m, omap)
+        del omap
 
     if rank == 0:
         working_set_mb = (F * frame_bytes + (map_stats["tsdf_blocks"] * 4096 + map_stats["esdf_blocks"] * 10240)) / 1e6
@@ -426,6 +469,7 @@ def main():
                                          "frame, one nvb_mapper_synchronize + block-index read-back per step"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages_out,
             "cpu_baseline": cpu, "with_color": with_color,
+            "parity_checked": parity_ok, "parity": parity,
         }
         print(json.dumps(out))
     m.close()

@@ -258,11 +258,12 @@ class Mapper {
     NvbMapperOptions o;
     nvb_default_mapper_options(&o);
     o.voxel_size_m = voxel_size_m;
-    // kTsdfWithFreespace / kNone are outside this path: nvb_mapper_create rejects them.
     o.keep_last_view = 1;  // Mapper::integrateDepth keeps the last posed depth image for the decay (mapper_impl.h:70-78)
-    o.projective_layer_type = projective_layer_type == ProjectiveLayerType::kTsdf        ? NVB_PROJECTIVE_TSDF
-                              : projective_layer_type == ProjectiveLayerType::kOccupancy ? NVB_PROJECTIVE_OCCUPANCY
-                                                                                         : -1;
+    // ProjectiveLayerType::kNone has no projective layer to integrate into: nvb_mapper_create rejects it (-1).
+    o.projective_layer_type = projective_layer_type == ProjectiveLayerType::kTsdf                 ? NVB_PROJECTIVE_TSDF
+                              : projective_layer_type == ProjectiveLayerType::kOccupancy          ? NVB_PROJECTIVE_OCCUPANCY
+                              : projective_layer_type == ProjectiveLayerType::kTsdfWithFreespace ? NVB_PROJECTIVE_TSDF_WITH_FREESPACE
+                                                                                                  : -1;
     b200_detail::check(nvb_mapper_create(&o, &m_), "Mapper", nvb_last_error());
   }
   ~Mapper() { nvb_mapper_destroy(m_); }

@@ -443,7 +443,8 @@ def test_golden_fixture(gpu):
 
 
 def test_full_sequence_properties(gpu):
-    """80-frame C2 sequence at full size (too long for the oracle in a unit test): properties only."""
+    """Every 4th frame of the C2 sequence at full size: size-independent properties of the result (the bit-for-bit
+    comparison of the whole 80-frame sequence with the oracle is tests/test_gpu_bench_pipeline.py)."""
     nvb = _nvb()
     cs, cam, ocam = cameras()
     frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(80)[::4])
