@@ -226,6 +226,8 @@ def main():
                     help="frames per step of the CPU arm (default: the whole sequence = the same work as a GPU step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--esdf-host-loop", action="store_true", help="reference-like per-ring launches")
+    ap.add_argument("--esdf-mode", type=int, default=3, choices=[1, 2, 3],
+                    help="ESDF wavefront: 3 exchange-slab (default), 1 four-phase, 2 gather-replay")
     ap.add_argument("--voxel-size", type=float, default=VOXEL,
                     help="side study only (e.g. 0.02 = the Redwood-shape config): the headline metric is quoted at 0.05")
     args = ap.parse_args()
@@ -262,7 +264,7 @@ def main():
     poses = [T for _, T in frames]
 
     voxel = args.voxel_size
-    m = nvb.Mapper(voxel, device=local_rank, esdf_persistent=not args.esdf_host_loop)
+    m = nvb.Mapper(voxel, device=local_rank, esdf_persistent=0 if args.esdf_host_loop else args.esdf_mode)
     stream = torch.cuda.ExternalStream(m.cuda_stream(), device=torch.device("cuda", local_rank))
     frame_bytes = ROWS * COLS * 4
 
@@ -420,7 +422,7 @@ def main():
         peak, peak_src = measured_peak_gbs()
         dom_ms, dom_calls = st[dom]
         achieved = (bytes_by_stage[dom] / (dom_ms * 1e-3)) / 1e9
-        kernel_of_stage = {"esdf/integrate/compute": "esdfWaveKernel", "esdf/integrate/mark_sites": "esdfMarkTmaKernel",
+        kernel_of_stage = {"esdf/integrate/compute": {1: "esdfWaveKernel", 2: "esdfWaveGesKernel", 3: "esdfWaveXKernel"}[args.esdf_mode], "esdf/integrate/mark_sites": "esdfMarkTmaKernel",
                            "esdf/integrate/clear": "esdfClearKernel", "tsdf/integrate/update_blocks": "tsdfIntegrateKernel",
                            "tsdf/integrate/allocate_blocks": "compactAllocateKernel",
                            "view_calculator/raycast": "viewRaycastKernel"}
@@ -457,7 +459,7 @@ def main():
                        "parallelism": "%d independent camera streams (one map replica per GPU)" % world,
                        "l2": "no explicit flush: one step touches %.0f MB (depth frames + map), larger than the 126 MB L2"
                              % working_set_mb,
-                       "esdf_driver": "host loop" if args.esdf_host_loop else "persistent cooperative kernel",
+                       "esdf_driver": "host loop" if args.esdf_host_loop else {1: "four-phase wavefront", 2: "gather-replay wavefront", 3: "exchange-slab wavefront"}[args.esdf_mode] + " (one cooperative launch)",
                        "map": map_stats},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes,
                     "d2h_bytes_per_step": int(d2h),

@@ -164,9 +164,11 @@ typedef struct {
   int32_t device;                /* CUDA device ordinal */
   int32_t tsdf_capacity_blocks;
   int32_t esdf_capacity_blocks;
-  int32_t esdf_persistent;       /* 1: whole ESDF wavefront in one cooperative launch (default);
-                                    0: one launch per ring with a host-read counter, like the reference;
-                                    2: gather-replay wavefront (experimental) */
+  int32_t esdf_persistent;       /* how computeEsdf runs. 3 (default): exchange-slab wavefront, whole update in one cooperative
+                                    launch, one grid barrier per ring (adds two ESDF-sized slabs + the candidate records);
+                                    1: four-phase wavefront, one cooperative launch, four barriers per ring;
+                                    2: gather-replay wavefront, two barriers per ring;
+                                    0: one launch per ring phase with a host-read counter, like the reference */
   int32_t projective_layer_type; /* NvbProjectiveLayerType: TSDF (default) or occupancy */
   int32_t keep_last_view;        /* 1: every integrated frame leaves a device copy of its depth image, pose and camera
                                     behind for nvb_mapper_decay_exclude_last_view, like Mapper::integrateDepth does

@@ -137,6 +137,10 @@ struct NvbMapper {
   int* nbr27 = nullptr;
   unsigned char* shadow = nullptr;
   int shadow_cap = 0;
+  unsigned char* xslab = nullptr;  // exchange-slab wavefront (esdf_persistent == 3): 2 x capacity ESDF blocks
+  int* xrec = nullptr;             // ... 2 x CTAs x xseg candidate records of 32 ints ...
+  int xseg = 0;
+  int* xcounts = nullptr;          // ... and 2 x CTAs count pairs
   int* cand_stamp = nullptr;
   // decay integrators
   NvbTsdfDecayParams tdp;
@@ -322,6 +326,22 @@ int allocEsdfScratch(NvbMapper* m, int old_cap, int cap) {
     NVB_CUDA(cudaMalloc(&m->shadow, (size_t)cap * kEsdfBlockBytes));
     m->shadow_cap = cap;
   }
+  if (m->esdf_persistent == 3) {
+    // exchange-slab wavefront: two slabs by ring parity + the candidate records (contents only live inside one launch)
+    NVB_CUDA(syncAll(m));
+    if (m->xslab) cudaFree(m->xslab);
+    if (m->xrec) cudaFree(m->xrec);
+    m->xslab = nullptr, m->xrec = nullptr;
+    NVB_CUDA(cudaMalloc(&m->xslab, 2 * (size_t)cap * kEsdfBlockBytes));
+    // A CTA registers at most 6 candidates per candidate it owns, i.e. <= 6 * ceil(cap / CTAs) < cap / 16 + 64 per ring.
+    const int ctas = std::min(m->num_sms, esdfWaveXMaxCtas());
+    m->xseg = cap / 16 + 64;
+    NVB_CUDA(cudaMalloc(&m->xrec, 2 * (size_t)ctas * m->xseg * 32 * sizeof(int)));
+    if (!m->xcounts) {
+      NVB_CUDA(cudaMalloc(&m->xcounts, esdfWaveXFlagBytes()));
+      NVB_CUDA(cudaMemsetAsync(m->xcounts, 0, esdfWaveXFlagBytes(), m->stream));
+    }
+  }
   return NVB_OK;
 }
 
@@ -338,7 +358,7 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kColorWorkCount = 31, kNumInts = 32 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kColorWorkCount = 31, kXTail = 32, kNumInts = 40 };
 
 float logOddsFromProbability(float p);
 
@@ -360,6 +380,7 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.ring_id = m->esdf_ints + kRingId;
   c.nbr = m->nbr, c.seed_upd = m->seed_upd, c.seed_clr = m->seed_clr;
   c.nbr27 = m->nbr27, c.shadow = m->shadow, c.cand_stamp = m->cand_stamp;
+  c.xslab = m->xslab, c.xrec = m->xrec, c.xtail = m->esdf_ints + kXTail, c.xseg = m->xseg, c.xcounts = m->xcounts;
   c.ges_counts = m->esdf_ints + kGesCounts;
   c.cand_a = m->cand_a, c.cand_b = m->cand_b, c.ges_switch = m->ges_switch;
   c.colset_keys = m->colset, c.colset_mask = m->colset_n ? (unsigned int)(m->colset_n - 1) : 0u;
@@ -843,8 +864,9 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
     m->launches++;
     endStageOn(m, es);
     beginStageOn(m, 5, es);
-    e = m->esdf_persistent == 2 ? launchEsdfComputeGes(c, m->num_sms, es, &launches)
-                                : launchEsdfComputePersistent(c, m->num_sms, es, &launches);
+    e = m->esdf_persistent == 3   ? launchEsdfComputeX(c, m->num_sms, es, &launches)
+        : m->esdf_persistent == 2 ? launchEsdfComputeGes(c, m->num_sms, es, &launches)
+                                  : launchEsdfComputePersistent(c, m->num_sms, es, &launches);
     endStageOn(m, es);
     if (e == cudaSuccess) {
       NVB_CUDA(cudaEventRecord(m->esdf_done, es));
@@ -893,7 +915,7 @@ void nvb_default_mapper_options(NvbMapperOptions* o) {
   o->device = 0;
   o->tsdf_capacity_blocks = kDefaultCapacity;
   o->esdf_capacity_blocks = kDefaultCapacity;
-  o->esdf_persistent = 1;
+  o->esdf_persistent = 3;
   o->projective_layer_type = NVB_PROJECTIVE_TSDF;
   o->keep_last_view = 0;
 }
@@ -960,7 +982,15 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   if (const char* e = getenv("NVB_GES_SWITCH")) m->ges_switch = atoi(e);
   NVB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   NVB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-  NVB_CUDA(cudaStreamCreateWithFlags(&m->esdf_stream, cudaStreamNonBlocking));
+  {
+    // The ESDF chain is the frame's critical path; the next frame's raycast / compaction / TSDF update only has to finish
+    // before the next mark kernel. NVB_ESDF_STREAM_PRIORITY=0 switches the preference off (A/B).
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const char* pe = getenv("NVB_ESDF_STREAM_PRIORITY");
+    const int prio = (pe && atoi(pe) == 0) ? lo : hi;
+    NVB_CUDA(cudaStreamCreateWithPriority(&m->esdf_stream, cudaStreamNonBlocking, prio));
+  }
   NVB_CUDA(cudaEventCreateWithFlags(&m->esdf_ready, cudaEventDisableTiming));
   NVB_CUDA(cudaEventCreateWithFlags(&m->esdf_done, cudaEventDisableTiming));
   NVB_CUDA(cudaEventCreateWithFlags(&m->mark_done, cudaEventDisableTiming));
@@ -1029,6 +1059,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
   cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr);
   cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
+  cudaFree(m->xslab), cudaFree(m->xrec), cudaFree(m->xcounts);
   cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);

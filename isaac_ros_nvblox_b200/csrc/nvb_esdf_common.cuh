@@ -85,7 +85,7 @@ __device__ __forceinline__ void linkNewBlock(const EsdfCtx& c, int slot, int tid
 
 __device__ __forceinline__ long long globalTimerNs() {
   long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
   return t;
 }
 

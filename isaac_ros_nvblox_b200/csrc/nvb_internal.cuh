@@ -349,6 +349,12 @@ struct EsdfCtx {
   int* nbr27;         // 27 ints per ESDF slot: slot of the block at offset (dx,dy,dz), entry (dx+1)*9+(dy+1)*3+(dz+1);
                       // -1 none, < -1 unknown (never linked)
   unsigned char* shadow;  // second ESDF slab (same slot indexing): results of a ring wait here until all reads are done
+  unsigned char* xslab;   // exchange-slab wavefront: two ESDF slabs (ring parity), members' blocks as their neighbours' owners read them
+  int* xtail;             // exchange-slab wavefront: 4 ints, hand-over of a single-CTA tail episode (rings advanced, K, M)
+  int* xrec;              // exchange-slab wavefront: candidate records {slot, 27 neighbour slots, pad}, 32 ints; per ring parity one
+                          // segment of `xseg` records per CTA
+  int xseg;
+  int* xcounts;           // exchange-slab wavefront: barrier flags, per barrier parity and CTA {generation, registrations, changed blocks}
   int slice_mode;  // the ESDF layer is a 2-D slice (EsdfMode::k2D)
   // constant-z slice (2-D ESDF): block / voxel z of the band's bottom and top and of the output layer
   int slice_min_bz, slice_min_vz, slice_max_bz, slice_max_vz, slice_out_bz, slice_out_vz;
@@ -394,6 +400,9 @@ void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaSt
 // Whole wavefront (both computeEsdf calls) in one cooperative launch. Returns cudaError.
 cudaError_t launchEsdfComputeGes(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
 cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
+cudaError_t launchEsdfComputeX(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);  // nvb_esdf_wavex.cu
+int esdfWaveXMaxCtas();
+size_t esdfWaveXFlagBytes();
 // Reference-like driver: one launch per phase, host reads the ring counter.
 cudaError_t runEsdfComputeHostLoop(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
 int esdfPersistentMaxCtas(int num_sms);

@@ -401,7 +401,7 @@ class Mapper:
         return {"barrier_wait_ns_cta0": out[0], "axis_ns_cta0": out[1], "slowest_cta_work_ns": out[2], "barriers": out[3]}
 
     def __init__(self, voxel_size_m, device=0, tsdf_capacity_blocks=0, esdf_capacity_blocks=0,
-                 esdf_persistent=True, projective_layer_type=ProjectiveLayerType.kTsdf, keep_last_view=False):
+                 esdf_persistent=3, projective_layer_type=ProjectiveLayerType.kTsdf, keep_last_view=False):
         self._L = _lib.load()
         o = NvbMapperOptions()
         self._L.nvb_default_mapper_options(C.byref(o))
@@ -411,7 +411,7 @@ class Mapper:
             o.tsdf_capacity_blocks = int(tsdf_capacity_blocks)
         if esdf_capacity_blocks:
             o.esdf_capacity_blocks = int(esdf_capacity_blocks)
-        o.esdf_persistent = int(esdf_persistent)  # 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
+        o.esdf_persistent = 1 if esdf_persistent is True else int(esdf_persistent)  # (True: the four-phase wavefront, as in round 1) 0 host loop, 1 four-phase wavefront, 2 gather-replay wavefront, 3 exchange-slab wavefront
         o.projective_layer_type = int(projective_layer_type)
         o.keep_last_view = 1 if keep_last_view else 0
         self._projective_layer_type = int(projective_layer_type)

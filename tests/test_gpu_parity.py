@@ -279,7 +279,7 @@ def test_block_round_trip_and_device_pointers(gpu):
 # ----------------------------------------------------------------------------------------
 # ESDF
 # ----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("persistent", [1, 0, 3])
 def test_esdf_incremental_sequence(gpu, persistent):
     cs, cam, ocam = cameras(320, 240)
     frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:5])
@@ -304,11 +304,24 @@ def test_esdf_gather_replay_wavefront(gpu, monkeypatch, switch):
     m.close()
 
 
-def test_esdf_gather_replay_640x480_with_growth(gpu):
+@pytest.mark.parametrize("mode", [2, 3])
+def test_esdf_gather_replay_640x480_with_growth(gpu, mode):
     cs, cam, ocam = cameras()
     frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(80)[:5])
     m, _ = _run_pair(0.05, frames, cam, ocam, esdf=True, check_every_frame=False,
-                     mapper_kw=dict(esdf_persistent=2, tsdf_capacity_blocks=1024, esdf_capacity_blocks=1024))
+                     mapper_kw=dict(esdf_persistent=mode, tsdf_capacity_blocks=1024, esdf_capacity_blocks=1024))
+    m.close()
+
+
+def test_esdf_exchange_slab_wavefront_noisy_scene_every_frame(gpu):
+    """esdf_persistent=3 (one barrier per ring: exchange slabs by ring parity, candidate records, single-CTA tail rings):
+    same results and the same per-update statistics as the oracle after every frame of a noisy sequence."""
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:8], noise_sigma_rel=0.005, seed=11)
+    m, o = _run_pair(0.05, frames, cam, ocam, esdf=True, mapper_kw=dict(esdf_persistent=3))
+    s_gpu, s_cpu = m.esdf_integrator().last_stats(), o.esdf_stats()
+    for k in ("marked", "with_sites", "to_clear", "cleared", "swept", "face_passes", "rings"):
+        assert s_gpu[k] == s_cpu[k], (k, s_gpu, s_cpu)
     m.close()
 
 
@@ -343,15 +356,17 @@ def test_esdf_small_grids_exercise_multi_round_paths(gpu, mark_tma):
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
-def test_esdf_gather_replay_2cm_many_candidates(gpu):
-    """2 cm voxels: rings with thousands of candidates (several chunks of 32 per CTA in the gather-replay kernel)."""
+@pytest.mark.parametrize("mode", [2, 3])
+def test_esdf_gather_replay_2cm_many_candidates(gpu, mode):
+    """2 cm voxels: rings with thousands of candidates (several chunks of 32 per CTA in the gather-replay kernel, several
+    candidates per 64-thread group in the exchange-slab kernel)."""
     cs, cam, ocam = cameras(320, 240)
     frames = syn.make_sequence(syn.box_with_cube(), cs, syn.circle_trajectory(80)[:2])
     import os as _os
     _os.environ["NVB_GES_SWITCH"] = "100000"
     try:
         m, o = _run_pair(0.02, frames, cam, ocam, esdf=True, tsdf_kw=dict(max_integration_distance_m=4.0),
-                         mapper_kw=dict(esdf_persistent=2), check_every_frame=False)
+                         mapper_kw=dict(esdf_persistent=mode), check_every_frame=False)
     finally:
         _os.environ.pop("NVB_GES_SWITCH", None)
     assert m.esdf_layer().num_blocks() > 10000
