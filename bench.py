@@ -393,7 +393,7 @@ def main():
     if rank == 0:
         m.clear()
         m.enable_profiling(True)
-        tot = {"N": 0, "marked": 0, "swept": 0, "face_passes": 0, "clear_candidates": 0, "rings": 0}
+        tot = {"N": 0, "marked": 0, "swept": 0, "face_passes": 0, "clear_candidates": 0, "rings": 0, "clear_read": 0}
         for i in range(F):
             m.integrate_depth_device(depth_dev[i].data_ptr(), ROWS, COLS, poses[i], cam)
             m.update_esdf(sync=False)
@@ -402,6 +402,7 @@ def main():
             s = m.esdf_integrator().last_stats()
             for k in ("marked", "swept", "face_passes", "clear_candidates", "rings"):
                 tot[k] += s[k]
+            tot["clear_read"] += m.esdf_integrator().clear_blocks_read()
         st = m.stage_times(reset=True)
         m.enable_profiling(False)
         # algorithmic bytes per stage over the sequence (DESIGN.md "Roofline")
@@ -411,7 +412,7 @@ def main():
             "tsdf/integrate/allocate_blocks": tot["N"] * 16,
             "tsdf/integrate/update_blocks": 8192 * tot["N"] + F * frame_bytes,
             "esdf/integrate/mark_sites": 24576 * tot["marked"],
-            "esdf/integrate/clear": 10240 * tot["clear_candidates"],
+            "esdf/integrate/clear": 10240 * tot["clear_read"] + 4 * tot["clear_candidates"],  # blocks read + the skipped candidates' parent boxes
             "esdf/integrate/compute": 20480 * tot["swept"] + 3840 * tot["face_passes"],
         }
         stages_out = {}
@@ -436,7 +437,8 @@ def main():
         map_stats = {"tsdf_blocks": m.tsdf_layer().num_blocks(), "esdf_blocks": m.esdf_layer().num_blocks(),
                      "blocks_per_frame": tot["N"] / F, "esdf_rings_per_frame": tot["rings"] / F,
                      "esdf_swept_per_frame": tot["swept"] / F, "esdf_face_passes_per_frame": tot["face_passes"] / F,
-                     "esdf_clear_candidates_per_frame": tot["clear_candidates"] / F}
+                     "esdf_clear_candidates_per_frame": tot["clear_candidates"] / F,
+                     "esdf_clear_blocks_read_per_frame": tot["clear_read"] / F}
 
     cpu, parity_ok, parity = None, None, None
     if rank == 0 and not args.no_cpu_baseline:

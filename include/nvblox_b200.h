@@ -477,6 +477,11 @@ NVB_API int32_t nvb_mapper_last_esdf_stats(NvbMapper* m, int64_t out[8]);
  * [1] face-propagation phases, [2] scan + sweep phases, [3] number of grid barriers. Synchronising. */
 NVB_API int32_t nvb_mapper_esdf_time_split(NvbMapper* m, int64_t out[4]);
 
+/* Blocks the clear pass of the last ESDF update actually read (clearAllInvalidKernel's candidates,
+ * nvblox/src/integrators/esdf_integrator.cu:1587-1647, minus those whose parent box holds no to-clear block; the
+ * `clear_candidates` statistic keeps counting the reference's candidates). */
+NVB_API int32_t nvb_mapper_esdf_clear_blocks_read(NvbMapper* m, int64_t* out);
+
 /* Debug: work time (ns) of the slowest CTA in each barrier-delimited phase of the last wavefront. */
 NVB_API int32_t nvb_mapper_debug_phase_max(NvbMapper* m, int64_t* out, int32_t cap);
 

@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "nvb_mapper_stream", "nvb_mapper_join_streams", "nvb_blocks_union",
     "nvb_layer_num_blocks", "nvb_layer_block_indices", "nvb_layer_get_blocks",
     "nvb_layer_set_blocks", "nvb_layer_block_device_ptr", "nvb_layer_block_bytes",
-    "nvb_mapper_last_esdf_stats", "nvb_mapper_esdf_time_split", "nvb_mapper_debug_phase_max", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
+    "nvb_mapper_last_esdf_stats", "nvb_mapper_esdf_time_split", "nvb_mapper_esdf_clear_blocks_read", "nvb_mapper_debug_phase_max", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
     "nvb_mapper_kernel_launches",
 ]
 
@@ -222,6 +222,7 @@ def load():
     L.nvb_layer_block_bytes.argtypes = [i32]
     L.nvb_mapper_last_esdf_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     L.nvb_mapper_esdf_time_split.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.nvb_mapper_esdf_clear_blocks_read.argtypes = [vp, C.POINTER(C.c_int64)]
     L.nvb_mapper_debug_phase_max.argtypes = [vp, C.POINTER(C.c_int64), i32]
     L.nvb_mapper_enable_profiling.argtypes = [vp, i32]
     L.nvb_mapper_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]

@@ -165,6 +165,10 @@ struct NvbMapper {
   int ges_switch = 160;
   int* seed_upd = nullptr;
   int* seed_clr = nullptr;
+  unsigned int* clr_bits = nullptr;  // to-clear bitmap of the current update (2048 words)
+  unsigned int* psum = nullptr;  // per ESDF slot: box of the block offsets its voxels' parents point into (clear-pass pruning)
+  bool prune_default = false;    // esdf_persistent == 3 and not switched off (NVB_CLEAR_PRUNE=0)
+  bool prune_ok = false;         // the summaries are upper bounds for every block (only the exchange-slab wavefront keeps them)
   int update_seq = 0;
   long long* stats = nullptr;
   unsigned int* barrier = nullptr;
@@ -295,6 +299,7 @@ int allocEsdfScratch(NvbMapper* m, int old_cap, int cap) {
   if ((rc = reallocCopy(&m->stamp_b, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
   if ((rc = reallocCopy(&m->seed_upd, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
   if ((rc = reallocCopy(&m->seed_clr, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->psum, 2 * (size_t)old_cap, 2 * (size_t)cap, true, m->stream))) return rc;
   // neighbour table: 0xFE bytes = "unknown" (< -1) for slots that were never linked
   {
     int* q = nullptr;
@@ -379,6 +384,8 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.stamp_a = m->stamp_a, c.stamp_b = m->stamp_b;
   c.ring_id = m->esdf_ints + kRingId;
   c.nbr = m->nbr, c.seed_upd = m->seed_upd, c.seed_clr = m->seed_clr;
+  c.clr_bits = m->clr_bits;
+  c.psum = m->psum, c.prune = (m->prune_ok && m->esdf_persistent == 3) ? 1 : 0;
   c.nbr27 = m->nbr27, c.shadow = m->shadow, c.cand_stamp = m->cand_stamp;
   c.xslab = m->xslab, c.xrec = m->xrec, c.xtail = m->esdf_ints + kXTail, c.xseg = m->xseg, c.xcounts = m->xcounts;
   c.ges_counts = m->esdf_ints + kGesCounts;
@@ -980,6 +987,11 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   // A/B switch for measurements: 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
   if (const char* e = getenv("NVB_ESDF_MODE")) m->esdf_persistent = atoi(e);
   if (const char* e = getenv("NVB_GES_SWITCH")) m->ges_switch = atoi(e);
+  {
+    const char* e = getenv("NVB_CLEAR_PRUNE");
+    m->prune_default = m->esdf_persistent == 3 && !(e && atoi(e) == 0);
+    m->prune_ok = m->prune_default;
+  }
   NVB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   NVB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   {
@@ -1012,6 +1024,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   m->todo_count = m->esdf_ints + kTodoCount;
   m->frame_count = m->esdf_ints + kFrameCount;
   m->error_dev = m->esdf_ints + kError;
+  NVB_CUDA(cudaMalloc(&m->clr_bits, 2048 * sizeof(unsigned int)));
   NVB_CUDA(cudaMalloc(&m->stats, 16 * sizeof(long long)));
   NVB_CUDA(cudaMemsetAsync(m->stats, 0, 16 * sizeof(long long), m->stream));
   NVB_CUDA(cudaMalloc(&m->phase_max, 4000 * sizeof(unsigned long long)));
@@ -1057,10 +1070,11 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->dirty), cudaFree(m->todo_slots);
   cudaFree(m->work), cudaFree(m->esdf_ints), cudaFree(m->upd_list), cudaFree(m->clr_list), cudaFree(m->cleared_list);
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
-  cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr);
+  cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr), cudaFree(m->psum);
   cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
   cudaFree(m->xslab), cudaFree(m->xrec), cudaFree(m->xcounts);
   cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
+  cudaFree(m->clr_bits);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
@@ -1092,6 +1106,8 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kDeadClearedCount, 0, sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->seed_upd, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->seed_clr, 0, (size_t)m->esdf.capacity * sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->psum, 0, 2 * (size_t)m->esdf.capacity * sizeof(int), m->stream));
+  m->prune_ok = m->prune_default;  // an empty layer: every summary is exact again
   NVB_CUDA(cudaMemsetAsync(m->nbr, 0xFE, (size_t)m->esdf.capacity * 6 * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->nbr27, 0xFE, (size_t)m->esdf.capacity * 27 * sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
@@ -1317,6 +1333,9 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
       c.slice_out_bz = (int)std::floor(m->sp.slice_height_m / m->block_size);
     }
     launchEsdfRemoveBlocks(c, m->dead, a.dead_count, n_dead, m->stream);
+    // Voxels of other blocks may keep parents inside the removed blocks: the reference clears them when they happen to be
+    // candidates of a later clear pass, which the per-block parent boxes cannot tell. No pruning from here on.
+    m->prune_ok = false;
     std::vector<DevLayer*> touched = {&m->tsdf, &m->esdf};
     if (m->freespace.blocks) {
       launchRemoveBlocks(m->freespace, m->dead, a.dead_count, n_dead, m->stream);
@@ -2206,6 +2225,7 @@ int32_t nvb_layer_set_blocks(NvbMapper* m, int32_t layer, const int32_t* xyz_hos
   NVB_CUDA(cudaMemcpyAsync(in_dev, in_host, (size_t)n * L->block_bytes, cudaMemcpyHostToDevice, m->stream));
   launchScatterBlocks(*L, xyz_dev, n, in_dev, m->error_dev, m->stream);
   m->launches++;
+  if (layer == NVB_LAYER_ESDF) m->prune_ok = false;  // voxels written from outside: the parent boxes are no longer bounds
   NVB_CUDA(syncAll(m));
   cudaFree(xyz_dev), cudaFree(in_dev);
   if (layer == NVB_LAYER_TSDF) {
@@ -2267,6 +2287,16 @@ int32_t nvb_mapper_esdf_time_split(NvbMapper* m, int64_t out[4]) {
   // [1]+[2] are CTA 0's own work; tmp[4] is the sum over phases of the slowest CTA's work: report it in [1]
   // of a second call convention: keep the API at 4 entries, fold it in as out[2] = slowest-CTA work total.
   out[2] = tmp[4];
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_esdf_clear_blocks_read(NvbMapper* m, int64_t* out) {
+  if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(syncAll(m));
+  long long v = 0;
+  NVB_CUDA(cudaMemcpy(&v, m->stats + 13, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = v;
   return NVB_OK;
 }
 

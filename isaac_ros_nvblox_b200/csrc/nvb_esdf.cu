@@ -30,6 +30,13 @@ namespace nvb {
 
 namespace {
 
+// To-clear bitmap for the clear pass's pruning (esdfClearKernel): 64 x 32 columns x 32 layers of block indices, folded
+// (x mod 64, y mod 32, z mod 32): no origin to agree on, so every mark CTA sets the bits of its own to-clear blocks while it
+// runs; two blocks that alias (25.6 m x 12.8 m x 12.8 m apart at 5 cm voxels) only cost an unnecessary read. Zeroed by the
+// allocate kernel of the update.
+constexpr int kClearBitWords = 2048;
+__device__ __forceinline__ int clearBitWord(int x, int y) { return ((x & 63) << 5) | (y & 31); }
+
 // ---------------------------------------------------------------------------
 // Allocation of the ESDF blocks + per-update counter reset
 // (EsdfIntegrator::allocateBlocksOnCPU, esdf_integrator.cu:391-397).
@@ -51,6 +58,8 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
     for (int k = 0; k < 16; k++) c.stats[k] = 0;
   }
   for (int q = i; q < 4000; q += gridDim.x * blockDim.x) c.phase_max[q] = 0ull;
+  if (c.clr_bits)
+    for (int q = i; q < kClearBitWords; q += gridDim.x * blockDim.x) c.clr_bits[q] = 0u;
   if (i == 0) {
     c.stats[0] = n;
   }
@@ -115,6 +124,7 @@ __device__ __forceinline__ void markLocalRecord(const EsdfCtx& c, MarkLocal& ml,
     const int x = bi[0], y = bi[1], z = bi[2];
     ml.aabb[0] = min(ml.aabb[0], x), ml.aabb[1] = min(ml.aabb[1], y), ml.aabb[2] = min(ml.aabb[2], z);
     ml.aabb[3] = max(ml.aabb[3], x), ml.aabb[4] = max(ml.aabb[4], y), ml.aabb[5] = max(ml.aabb[5], z);
+    if (c.clr_bits) atomicOr(c.clr_bits + clearBitWord(x, y), 1u << (z & 31));
   }
 }
 
@@ -521,19 +531,25 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
   const int nblocks = *c.esdf.count < c.esdf.capacity ? *c.esdf.count : c.esdf.capacity;
   const float bs = c.block_size;
   float amin[3], amax[3];
+  int ia[3], ib[3];  // the to-clear AABB in block indices
 #pragma unroll
   for (int a = 0; a < 3; a++) {
-    amin[a] = (float)c.clr_aabb[a] * bs;
-    amax[a] = ((float)c.clr_aabb[3 + a] + 1.0f) * bs;
+    ia[a] = c.clr_aabb[a], ib[a] = c.clr_aabb[3 + a];
+    amin[a] = (float)ia[a] * bs;
+    amax[a] = ((float)ib[a] + 1.0f) * bs;
   }
-  long long ncand_total = 0;
+  // Pruning (c.prune): a voxel is cleared iff its parent voxel is no longer a site, and sites are only lost in the to-clear
+  // blocks; c.psum[slot] bounds the block offsets the parents of the block's voxels point into. A candidate is only READ if that
+  // box (clipped to the to-clear AABB) contains a to-clear block: tested against the folded bitmap the mark kernel filled.
+  const bool use_bits = c.prune && c.clr_bits != nullptr;
+  long long ncand_total = 0, nread_total = 0;
   // Slots are dealt round-robin over the CTAs (recently allocated = high slots are the likely candidates);
   // one selection round tests 256 of this CTA's slots at once, one thread per slot.
   for (long long first = blockIdx.x; first < nblocks; first += (long long)gridDim.x * kThreads) {
     if (tid == 0) s_ncand = 0, s_ndone = 0;
     __syncthreads();
     const long long slot_ll = first + (long long)tid * gridDim.x;
-    bool is_cand = false;
+    bool is_cand = false, ref_cand = false;
     if (slot_ll < nblocks && c.esdf.block_index[3 * slot_ll] != kDeadSlotX) {
       const int* bi = c.esdf.block_index + 3 * slot_ll;
       const int b3[3] = {bi[0], bi[1], bi[2]};
@@ -551,15 +567,55 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
         }
       }
       is_cand = !(sqrtf(d2) > c.max_esdf_distance_m);
+      if (is_cand && c.prune) {
+        // union of the two half-block boxes (one word per warp of the storing group)
+        const uint2 pw = __ldg(reinterpret_cast<const uint2*>(c.psum) + slot_ll);
+        if (pw.x == 0u && pw.y == 0u) {
+          is_cand = false, ref_cand = true;  // no voxel of the block has a parent
+        } else if (pw.x != 0xffffffffu && pw.y != 0xffffffffu) {
+          ref_cand = true;
+          int lo[3], hi[3];
+          bool hit = true;
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            int l = 99, h = -99;
+            if (pw.x) l = (int)((pw.x >> (10 * a)) & 31u) - 16, h = (int)((pw.x >> (10 * a + 5)) & 31u) - 16;
+            if (pw.y) l = min(l, (int)((pw.y >> (10 * a)) & 31u) - 16), h = max(h, (int)((pw.y >> (10 * a + 5)) & 31u) - 16);
+            lo[a] = b3[a] + l, hi[a] = b3[a] + h;
+            lo[a] = lo[a] > ia[a] ? lo[a] : ia[a], hi[a] = hi[a] < ib[a] ? hi[a] : ib[a];
+            hit = hit && lo[a] <= hi[a];
+          }
+          if (hit && use_bits) {
+            unsigned int zmask = 0xffffffffu;  // z layers lo..hi, folded mod 32
+            if (hi[2] - lo[2] < 31) {
+              const unsigned int m = (1u << (hi[2] - lo[2] + 1)) - 1u;
+              const int sh = lo[2] & 31;
+              zmask = (m << sh) | (sh ? (m >> (32 - sh)) : 0u);
+            }
+            hit = false;
+            for (int x = lo[0]; x <= hi[0] && !hit; x++)
+              for (int y = lo[1]; y <= hi[1]; y++)
+                if (__ldg(c.clr_bits + clearBitWord(x, y)) & zmask) {
+                  hit = true;
+                  break;
+                }
+          }
+          is_cand = hit;
+        }
+      }
+      ref_cand = ref_cand || is_cand;
     }
+    // (the statistics count the reference's candidates; `is_cand` decides what is read)
+    const unsigned int ref_ballot = __ballot_sync(0xffffffffu, ref_cand);
     const unsigned int ballot = __ballot_sync(0xffffffffu, is_cand);
     int wbase = 0;
     if (lane == 0 && ballot) wbase = atomicAdd(&s_ncand, __popc(ballot));
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
     if (is_cand) s_cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = (int)slot_ll;
+    if (lane == 0) ncand_total += __popc(ref_ballot);
     __syncthreads();
     const int ncand = s_ncand;
-    ncand_total += ncand;
+    if (tid == 0) nread_total += ncand;
     // Candidates one after the other; the next one's block and neighbour row are already on their way.
     if (ncand > 0) clearPrefetch(c, s_blk[0], s_nb[0], s_cand[0], tid);
     for (int i = 0; i < ncand; i++) {
@@ -638,7 +694,8 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
     }
     __syncthreads();
   }
-  if (tid == 0 && ncand_total) atomicAdd((unsigned long long*)&c.stats[3], (unsigned long long)ncand_total);
+  if (lane == 0 && ncand_total) atomicAdd((unsigned long long*)&c.stats[3], (unsigned long long)ncand_total);
+  if (tid == 0 && nread_total) atomicAdd((unsigned long long*)&c.stats[13], (unsigned long long)nread_total);
 }
 
 // ---------------------------------------------------------------------------
@@ -984,6 +1041,8 @@ __global__ void esdfSliceAllocateKernel(EsdfCtx c) {
     c.stats[0] = n;
   }
   for (int q = i; q < 4000; q += gridDim.x * blockDim.x) c.phase_max[q] = 0ull;
+  if (c.clr_bits)
+    for (int q = i; q < kClearBitWords; q += gridDim.x * blockDim.x) c.clr_bits[q] = 0u;
   const int stride = gridDim.x * blockDim.x;
   for (int k = i; k < n; k += stride) {
     const int x = c.cols[2 * k], y = c.cols[2 * k + 1];

@@ -104,6 +104,7 @@ struct XCtx {
   int* nbr;
   int* nbr27;
   int* cand_stamp;
+  unsigned int* psum;     // per slot: box of the block offsets the voxels' parents point into (clear-pass pruning)
   int* stamp[2];          // member stamps by ring parity
   unsigned char* X[2];    // exchange slabs by ring parity
   int* recs[2];           // candidate records by ring parity: one segment of `seg` records per CTA
@@ -269,13 +270,17 @@ __device__ __forceinline__ void ownToShared(unsigned int* R, const OwnRegs& o, i
   }
 }
 // inner 8x8x8 of the region -> the block in the layer (if `to_layer`) and its copy in an exchange slab; half a z-row (four
-// voxels = 80 bytes = five 16-byte words) at a time
+// voxels = 80 bytes = five 16-byte words) at a time. On the way the box of the BLOCK OFFSETS the voxels' parents point into is
+// collected and published in c.psum (EsdfCtx::psum; one word per warp of the group, so no barrier is needed): the clear pass of
+// later updates reads a candidate block only if that box contains a to-clear block.
 __device__ __forceinline__ void ownStore(unsigned char* layer_blk, bool to_layer, unsigned char* x_blk, const unsigned int* R,
-                                         int lane64) {
+                                         unsigned int* psum_slot, int lane64) {
   const uint4* A = reinterpret_cast<const uint4*>(R);
-  const int v0 = rvox((lane64 >> 3) + 1, (lane64 & 7) + 1, 1);
+  const int x = lane64 >> 3, y = lane64 & 7;
+  const int v0 = rvox(x + 1, y + 1, 1);
   uint4* dl = reinterpret_cast<uint4*>(layer_blk) + lane64 * 10;
   uint4* dx = reinterpret_cast<uint4*>(x_blk) + lane64 * 10;
+  int lo0 = 99, lo1 = 99, lo2 = 99, hi0 = -99, hi1 = -99, hi2 = -99;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     unsigned int w[20];
@@ -284,12 +289,30 @@ __device__ __forceinline__ void ownStore(unsigned char* layer_blk, bool to_layer
       const uint4 a = A[v0 + 4 * h + z];
       w[5 * z] = a.x, w[5 * z + 1] = a.y, w[5 * z + 2] = a.z, w[5 * z + 3] = a.w;
       w[5 * z + 4] = R[kFlagBase + v0 + 4 * h + z];
+      if ((a.y | a.z | a.w) != 0u) {
+        const int b0 = (x + (int)a.y) >> 3, b1 = (y + (int)a.z) >> 3, b2 = (4 * h + z + (int)a.w) >> 3;  // floor: arithmetic shift
+        lo0 = min(lo0, b0), hi0 = max(hi0, b0), lo1 = min(lo1, b1), hi1 = max(hi1, b1), lo2 = min(lo2, b2), hi2 = max(hi2, b2);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) {
       const uint4 v = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
       if (to_layer) __stcg(dl + 5 * h + i, v);
       __stcg(dx + 5 * h + i, v);
+    }
+  }
+  if (psum_slot) {
+    lo0 = __reduce_min_sync(0xffffffffu, lo0), lo1 = __reduce_min_sync(0xffffffffu, lo1), lo2 = __reduce_min_sync(0xffffffffu, lo2);
+    hi0 = __reduce_max_sync(0xffffffffu, hi0), hi1 = __reduce_max_sync(0xffffffffu, hi1), hi2 = __reduce_max_sync(0xffffffffu, hi2);
+    if ((lane64 & 31) == 0) {
+      unsigned int v = 0u;
+      if (lo0 <= hi0) {
+        const bool fits = lo0 >= -16 && lo1 >= -16 && lo2 >= -16 && hi0 <= 15 && hi1 <= 15 && hi2 <= 15;
+        v = fits ? ((1u << 31) | (unsigned)(lo0 + 16) | ((unsigned)(hi0 + 16) << 5) | ((unsigned)(lo1 + 16) << 10) |
+                    ((unsigned)(hi1 + 16) << 15) | ((unsigned)(lo2 + 16) << 20) | ((unsigned)(hi2 + 16) << 25))
+                 : 0xffffffffu;
+      }
+      psum_slot[lane64 >> 5] = v;
     }
   }
 }
@@ -562,7 +585,7 @@ __device__ __noinline__ void processCandidate(const XCtx& c, const XTables& tab,
     registerClaim(xs, rs, group, lane64, ring + 1);
     groupSync(group);
     X_PROF(4)
-    ownStore(c.blocks + (size_t)slot * kEsdfBlockBytes, true, c.X[ni] + (size_t)slot * kEsdfBlockBytes, R, lane64);
+    ownStore(c.blocks + (size_t)slot * kEsdfBlockBytes, true, c.X[ni] + (size_t)slot * kEsdfBlockBytes, R, c.psum + 2 * (size_t)slot, lane64);
     registerFinish(c, xs, rs, group, lane64, c.segment(ni, cta));
     X_PROF_COUNT(7)
   }
@@ -590,7 +613,8 @@ __device__ __noinline__ void processSeed(const XCtx& c, XShared& xs, unsigned in
   registerClaim(xs, rs, group, lane64, ring);
   if (ch) xs.changed[group] = 1;
   groupSync(group);
-  ownStore(blk, xs.changed[group] != 0, c.X[ci] + (size_t)slot * kEsdfBlockBytes, R, lane64);
+  // (an unchanged block keeps its parent box)
+  ownStore(blk, xs.changed[group] != 0, c.X[ci] + (size_t)slot * kEsdfBlockBytes, R, xs.changed[group] ? c.psum + 2 * (size_t)slot : nullptr, lane64);
   registerFinish(c, xs, rs, group, lane64, c.segment(ci, cta));
   groupSync(group);
 }
@@ -651,7 +675,7 @@ __global__ void __maxnreg__(NVB_WAVEX_MAXREG) esdfWaveXKernel(EsdfCtx c) {
   if (tid == 0) {
     xs.ncand = 0, xs.nchanged = 0, xs.next = 0;
     xc.blocks = c.esdf.blocks, xc.block_index = c.esdf.block_index, xc.hash = c.esdf.hash;
-    xc.nbr = c.nbr, xc.nbr27 = c.nbr27, xc.cand_stamp = c.cand_stamp;
+    xc.nbr = c.nbr, xc.nbr27 = c.nbr27, xc.cand_stamp = c.cand_stamp, xc.psum = c.psum;
     xc.stamp[0] = c.stamp_a, xc.stamp[1] = c.stamp_b;
     xc.X[0] = c.xslab, xc.X[1] = c.xslab + (size_t)c.esdf.capacity * kEsdfBlockBytes;
     xc.recs[0] = c.xrec, xc.recs[1] = c.xrec + (size_t)nctas * c.xseg * kRecInts;

@@ -372,6 +372,12 @@ struct EsdfCtx {
   int ges_switch;     // rings with more members than this run as four-phase rings
   int* cand_stamp;    // per slot: == ring  <=> registered as a candidate (neighbour of a member) of that ring
   int* ges_counts;    // 4 ints: candidate count [2], member count [2] (ping-pong by ring parity)
+  unsigned int* psum; // two words per slot (the two halves of the block, x < 4 and x >= 4): 0 = no voxel has a parent; bit 31 set: box of the BLOCK OFFSETS the voxels' parents
+                      // point into, 5 bits per bound (lo x, hi x, lo y, hi y, lo z, hi z, each + 16); 0xffffffff = unknown.
+                      // An upper bound kept by the exchange-slab wavefront (the only writer of non-zero parents in that mode).
+  unsigned int* clr_bits;  // bitmap of the to-clear blocks over their AABB (2048 words), built by the mark kernel's last CTA
+  int prune;          // clear pass: skip candidates whose parent box holds no to-clear block (exact: a voxel is cleared iff its
+                      // parent voxel lost its site flag, and sites are only lost in to-clear blocks)
   int* seed_upd;      // per slot: == update_seq  <=> block has sites in this update (computeEsdf #1 seeds)
   int* seed_clr;      // per slot: == *cleared_seq <=> member of the persistent cleared list (computeEsdf #2 seeds)
   int* cleared_seq;   // device: update_seq of the last update whose clear pass ran

@@ -368,6 +368,12 @@ class _EsdfIntegrator:
         keys = ("marked", "with_sites", "to_clear", "clear_candidates", "cleared", "swept", "face_passes", "rings")
         return dict(zip(keys, list(out)))
 
+    def clear_blocks_read(self):
+        """Blocks the last clear pass read (<= clear_candidates: candidates whose parents cannot lie in a to-clear block are skipped)."""
+        out = C.c_int64(0)
+        check(self._m._L.nvb_mapper_esdf_clear_blocks_read(self._m._h, C.byref(out)))
+        return int(out.value)
+
 
 class EsdfSlicer:
     """EsdfSlicer (integrators/esdf_slicer.h:36-138): distance-map image and occupancy grid of an ESDF slice."""

@@ -14,9 +14,8 @@ except Exception as e:
     print(sys.argv[1], 'failed', e)
 PY
 done <<'CFG'
-r128 prio||
-r128 noprio||NVB_ESDF_STREAM_PRIORITY=0
-r96 prio|-DNVB_WAVEX_MAXREG=96|
-r96 noprio|-DNVB_WAVEX_MAXREG=96|NVB_ESDF_STREAM_PRIORITY=0
-r112 prio|-DNVB_WAVEX_MAXREG=112|
+prune on||
+prune off||NVB_CLEAR_PRUNE=0
+prune on (2)||
+prune off (2)||NVB_CLEAR_PRUNE=0
 CFG

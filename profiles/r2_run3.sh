@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick loop: mode-3 parity subset + bench + per-ring split of a profiling build
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_occupancy.py tests/test_gpu_bench_pipeline.py -x -q -m gpu -k "(esdf and (3 or exchange)) or (bench_pipeline_async_80 and 3) or growth_mid" > gpurun_out/r2_run3_tests.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_occupancy.py tests/test_gpu_bench_pipeline.py tests/test_gpu_decay.py tests/test_gpu_esdf_slice.py -x -q -m gpu -k "(esdf and (3 or exchange or pruning)) or (bench_pipeline_async_80 and 3) or growth_mid or decay or slice" > gpurun_out/r2_run3_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/r2_run3_tests.log
 tail -4 gpurun_out/r2_run3_tests.log
 NVB_ESDF_MODE=${MODE:-3} timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_run3_bench.json 2> gpurun_out/r2_run3_bench.err

@@ -325,6 +325,37 @@ def test_esdf_exchange_slab_wavefront_noisy_scene_every_frame(gpu):
     m.close()
 
 
+@pytest.mark.parametrize("prune", ["1", "0"])
+def test_esdf_clear_pass_pruning_is_exact(gpu, monkeypatch, prune):
+    """The clear pass only READS candidates whose parent box (per-block bound of where the voxels' parents live, kept by the
+    exchange-slab wavefront) contains a to-clear block. Same layers and statistics as the oracle after every frame with the
+    pruning on and off (NVB_CLEAR_PRUNE=0); `clear_candidates` keeps counting the reference's candidates."""
+    monkeypatch.setenv("NVB_CLEAR_PRUNE", prune)
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:10], noise_sigma_rel=0.005, seed=7)
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    read, cands, cleared = 0, 0, 0
+    for i, (depth, T) in enumerate(frames):
+        b = m.integrate_depth(depth, T, cam)
+        o.integrate_depth(depth, T, ocam)
+        m.update_esdf()
+        o.integrate_esdf(b if i > 0 else o.tsdf_block_indices())
+        s_gpu, s_cpu = m.esdf_integrator().last_stats(), o.esdf_stats()
+        for k in ("to_clear", "clear_candidates", "cleared", "swept", "face_passes", "rings"):
+            assert s_gpu[k] == s_cpu[k], (i, k, s_gpu, s_cpu)
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+        read += m.esdf_integrator().clear_blocks_read()
+        cands += s_gpu["clear_candidates"]
+        cleared += s_gpu["cleared"]
+    assert cleared > 0 and cands > 0
+    if prune == "1":
+        assert cleared <= read < cands / 2, (cleared, read, cands)
+    else:
+        assert read == cands
+    m.close()
+
+
 @pytest.mark.parametrize("mark_tma", ["1", "0"])
 def test_esdf_small_grids_exercise_multi_round_paths(gpu, mark_tma):
     """Runs in a subprocess with NVB_ESDF_GRID_CAP=3 (the cap is read once per process): three CTAs mark ~1000 blocks
