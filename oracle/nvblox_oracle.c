@@ -2161,6 +2161,14 @@ void or_tsdf_set_block(OrMap* m, const int32_t xyz[3], const OrTsdfVoxel* in) {
   memcpy(layer_block(&m->tsdf, s), in, m->tsdf.block_bytes);
 }
 
+/* Test hook (no reference counterpart): place an EsdfBlock with given voxel contents, to start the wavefront from a state that
+ * was written down by hand (tests/test_oracle_esdf_order_kat.py). */
+void or_esdf_set_block(OrMap* m, const int32_t xyz[3], const OrEsdfVoxel* in) {
+  i3 k = {xyz[0], xyz[1], xyz[2]};
+  int32_t s = layer_allocate(&m->esdf, k);
+  memcpy(layer_block(&m->esdf, s), in, m->esdf.block_bytes);
+}
+
 void or_freespace_set_block(OrMap* m, const int32_t xyz[3], const OrFreespaceVoxel* in) {
   i3 k = {xyz[0], xyz[1], xyz[2]};
   int32_t s = layer_allocate(&m->freespace, k);

@@ -300,6 +300,7 @@ int32_t or_tsdf_get_block(const OrMap* map, const int32_t xyz[3], OrTsdfVoxel* o
 int32_t or_esdf_get_block(const OrMap* map, const int32_t xyz[3], OrEsdfVoxel* out);
 /* Test helper: overwrite / create a TSDF block. */
 void or_tsdf_set_block(OrMap* map, const int32_t xyz[3], const OrTsdfVoxel* in);
+void or_esdf_set_block(OrMap* map, const int32_t xyz[3], const OrEsdfVoxel* in); /* test hook */
 
 /* Camera::project / vectorFromImagePlaneCoordinates exposed for the distortion tests. */
 int32_t or_camera_project(const OrCamera* cam, const float p_C[3], float uv[2]);

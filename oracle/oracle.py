@@ -176,6 +176,7 @@ def lib():
     L.or_esdf_get_block.argtypes = [vp, ip, vp]
     L.or_esdf_get_block.restype = C.c_int32
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
+    L.or_esdf_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.restype = None
     L.or_occupancy_set_block.argtypes = [vp, ip, vp]
@@ -656,6 +657,12 @@ class OracleMap:
         k = np.asarray(idx, dtype=np.int32)
         v = np.ascontiguousarray(voxels, dtype=TSDF_VOXEL_DTYPE).reshape(8, 8, 8)
         lib().or_tsdf_set_block(self._h, _ip(k), v.ctypes.data)
+
+    def set_esdf_block(self, idx, voxels):
+        """Test hook: place an EsdfBlock with the given voxels (ESDF_VOXEL_DTYPE, (8, 8, 8))."""
+        k = np.asarray(idx, dtype=np.int32)
+        v = np.ascontiguousarray(voxels, dtype=ESDF_VOXEL_DTYPE).reshape(8, 8, 8)
+        lib().or_esdf_set_block(self._h, _ip(k), v.ctypes.data)
 
     def set_freespace_block(self, idx, voxels):
         k = np.asarray(idx, dtype=np.int32)

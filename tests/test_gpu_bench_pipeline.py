@@ -177,3 +177,33 @@ def test_async_pipeline_with_layer_growth_mid_sequence(c2, mode):
     assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
     assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
     m.close()
+
+
+def test_threedmatch_reference_data_equals_oracle(gpu):
+    """The reference's own real-data fixture (nvblox/tests/data/3dmatch/seq-01; tests/golden/threedmatch_seq01.npz): five real
+    640x480 depth frames (13 % invalid pixels), the colour image of the first, an ESDF update per frame. Per-frame block lists,
+    TSDF bits, colour bytes and all five EsdfVoxel fields equal to the oracle's, and to the committed checksums."""
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    import make_threedmatch_fixture as mk
+    nvb = _nvb()
+    fx = np.load(os.path.join(golden, "threedmatch_seq01.npz"))
+    K = fx["intrinsics"]
+    o, lists = mk.run_oracle(K, fx["depth_u16"], fx["poses"], fx["color0"], float(fx["voxel_size"]))
+    cam = nvb.Camera(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), 640, 480)
+    m = nvb.Mapper(float(fx["voxel_size"]))
+    for i in range(len(fx["depth_u16"])):
+        b = m.integrate_depth(mk.depth_to_float(fx["depth_u16"][i]), fx["poses"][i], cam)
+        assert np.array_equal(b, lists[i]) and np.array_equal(b, fx["blocks_%d" % i]), i
+        if i == 0:
+            m.integrate_color(fx["color0"], fx["poses"][0], cam)
+        m.update_esdf()
+    assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+    assert_color_equal(m.color_layer().as_dict(), o.color_layer())
+    assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+    assert layer_checksum(m.tsdf_layer().as_dict(), ("distance", "weight")) == int(fx["tsdf_checksum"])
+    assert layer_checksum(m.esdf_layer().as_dict(), ESDF_FIELDS) == int(fx["esdf_checksum"])
+    assert layer_checksum(m.color_layer().as_dict(), ("color", "weight")) == int(fx["color_checksum"])
+    m.close()

@@ -325,6 +325,34 @@ def test_esdf_exchange_slab_wavefront_noisy_scene_every_frame(gpu):
     m.close()
 
 
+@pytest.mark.parametrize("mode", [3, 1, 2, 0])
+def test_esdf_hand_derived_order_kats(gpu, mode):
+    """tests/esdf_order_cases.py: known answers written down from the reference's source (the scan's "last taker" rule; the
+    propagation across a block face with its ring statistics), for every wavefront formulation."""
+    from esdf_order_cases import ACROSS_FACE_STATS, across_face_case, check_across_face, check_last_taker, last_taker_case
+    nvb = _nvb()
+    tsdf, esdf, expected = last_taker_case(nvb.TSDF_VOXEL_DTYPE, nvb.ESDF_VOXEL_DTYPE)
+    m = nvb.Mapper(0.05, esdf_persistent=mode)
+    idx = np.array(list(tsdf), np.int32)
+    m.tsdf_layer().set_blocks(idx, np.stack([tsdf[tuple(k)] for k in idx]))
+    m.esdf_layer().set_blocks(idx, np.stack([esdf[tuple(k)] for k in idx]))
+    m.esdf_integrator().integrate_blocks(idx)
+    s = m.esdf_integrator().last_stats()
+    assert s["with_sites"] == 1 and s["to_clear"] == 0 and s["swept"] == 1 and s["rings"] == 1, s
+    check_last_taker(m.esdf_layer().as_dict()[(0, 0, 0)], expected)
+    m.close()
+    tsdf, parents = across_face_case(nvb.TSDF_VOXEL_DTYPE)
+    m = nvb.Mapper(0.05, esdf_persistent=mode)
+    idx = np.array(list(tsdf), np.int32)
+    m.tsdf_layer().set_blocks(idx, np.stack([tsdf[tuple(k)] for k in idx]))
+    m.esdf_integrator().integrate_blocks(idx)
+    s = m.esdf_integrator().last_stats()
+    for k, v in ACROSS_FACE_STATS.items():
+        assert s[k] == v, (k, s)
+    check_across_face(m.esdf_layer().as_dict(), parents)
+    m.close()
+
+
 @pytest.mark.parametrize("prune", ["1", "0"])
 def test_esdf_clear_pass_pruning_is_exact(gpu, monkeypatch, prune):
     """The clear pass only READS candidates whose parent box (per-block bound of where the voxels' parents live, kept by the
