@@ -30,12 +30,19 @@ class VoxelBlockLayer {
     for (int i = 0; i < n; i++) out[i] = Index3D(raw[3 * i], raw[3 * i + 1], raw[3 * i + 2]);
     return out;
   }
-  // Raw device pointer of the block (getBlockAtIndex(idx).get()), nullptr if not allocated.
-  const BlockType* getBlockAtIndex(const Index3D& idx) const {
+  // BlockLayer::getBlockAtIndex (map/layer.h:103-104): a handle whose get() is the block's device address, null if the block
+  // is not allocated.
+  typename BlockType::ConstPtr getBlockAtIndex(const Index3D& idx) const {
     const int32_t k[3] = {idx[0], idx[1], idx[2]};
     void* p = nullptr;
     b200_detail::check(nvb_layer_block_device_ptr(m_, id_, k, &p), "getBlockAtIndex", nvb_last_error());
-    return static_cast<const BlockType*>(p);
+    return typename BlockType::ConstPtr(static_cast<const BlockType*>(p));
+  }
+  typename BlockType::Ptr getBlockAtIndex(const Index3D& idx) {
+    const int32_t k[3] = {idx[0], idx[1], idx[2]};
+    void* p = nullptr;
+    b200_detail::check(nvb_layer_block_device_ptr(m_, id_, k, &p), "getBlockAtIndex", nvb_last_error());
+    return typename BlockType::Ptr(static_cast<BlockType*>(p));
   }
   bool isBlockAllocated(const Index3D& idx) const { return getBlockAtIndex(idx) != nullptr; }
   // Host copy of one block (the reference's tests read kUnified layers directly).

@@ -1,6 +1,6 @@
 // nvblox/mapper/mapper.h -- nvblox::Mapper restricted to the depth-integration path
 // (reference: nvblox/include/nvblox/mapper/mapper.h:107-836), forwarding to libnvblox_b200.so.
-//   Mapper(voxel_size_m)                                   mapper.h:119-124
+//   Mapper(voxel_size_m, BlockMemoryPoolParams, ProjectiveLayerType, shared_ptr<CudaStream>)   mapper.h:119-124
 //   integrateDepth(depth, T_L_C, camera)                   mapper.h:167-172
 //   updateEsdf(UpdateFullLayer)                            mapper.h:326
 //   tsdf_layer() / esdf_layer()                            mapper.h:372,393
@@ -10,7 +10,10 @@
 //   decayTsdfAllVoxels / decayTsdfExcludeLastView / decayOccupancy...   mapper.h:218-233
 //   tsdf_decay_integrator() / occupancy_decay_integrator()  mapper.h:496-504
 #pragma once
+#include <memory>
+#include <type_traits>
 #include <vector>
+#include "nvblox/core/cuda_stream.h"
 #include "nvblox/integrators/weighting_function.h"
 #include "nvblox/geometry/plane.h"
 #include "nvblox/map/layer.h"
@@ -20,6 +23,40 @@
 namespace nvblox {
 
 enum class UpdateFullLayer { kNo, kYes };
+
+// BlockMemoryPoolParams (map/internal/block_memory_pool_params.h:35-45): how the reference's block pools are sized. Here a layer
+// is one slab: num_preallocated_blocks becomes the slabs' initial capacity (0: the library's default),
+// growth is by doubling whatever expansion_factor says, and blocks always live in device memory.
+struct BlockMemoryPoolParams {
+  BlockMemoryPoolParams() = default;
+  BlockMemoryPoolParams(const MemoryType _memory_type) : memory_type(_memory_type) {}  // NOLINT (implicit, like the reference)
+  MemoryType memory_type = MemoryType::kDevice;
+  int num_preallocated_blocks = 0;
+  float expansion_factor = 2.0f;
+};
+
+// MapperParams (mapper/mapper_params.h:46-70), the members this path consumes; applied with Mapper::setMapperParams.
+struct EsdfIntegratorParams {
+  float esdf_integrator_max_distance_m = 2.0f;
+  float esdf_integrator_max_site_distance_vox = 1.0f;
+  float esdf_integrator_min_weight = 1e-4f;
+  float esdf_slice_min_height = 0.0f, esdf_slice_max_height = 1.0f, esdf_slice_height = 1.0f;
+};
+struct ProjectiveIntegratorParams {
+  float projective_integrator_max_integration_distance_m = 7.0f;
+  float projective_integrator_truncation_distance_vox = 4.0f;
+  WeightingFunctionType projective_integrator_weighting_mode = WeightingFunctionType::kInverseSquareWeight;
+  float projective_integrator_max_weight = 5.0f;
+};
+struct OccupancyIntegratorParams {
+  float free_region_occupancy_probability = 0.3f, occupied_region_occupancy_probability = 0.7f;
+  float unobserved_region_occupancy_probability = 0.5f, occupied_region_half_width_m = 0.1f;
+};
+struct MapperParams {
+  EsdfIntegratorParams esdf_integrator_params;
+  ProjectiveIntegratorParams projective_integrator_params;
+  OccupancyIntegratorParams occupancy_integrator_params;
+};
 enum class ProjectiveLayerType { kTsdf, kOccupancy, kTsdfWithFreespace, kNone };
 enum class EsdfMode { k3D, k2D, kUnset };
 
@@ -47,6 +84,25 @@ inline void integrateFrame(NvbMapper* m, const MaskedDepthImageConstView& depth,
 }
 }  // namespace b200_detail
 
+// ViewCalculator's parameter surface (integrators/view_calculator.h:115-190): the workspace bounds and the raycast subsampling.
+enum class WorkspaceBoundsType { kUnbounded, kHeightBounds, kBoundingBox };  // geometry/workspace_bounds.h:24
+class ViewCalculator {
+ public:
+  explicit ViewCalculator(NvbMapper* m) : m_(m) {}
+  WorkspaceBoundsType workspace_bounds_type() const { return (WorkspaceBoundsType)get().workspace_bounds_type; }
+  void workspace_bounds_type(WorkspaceBoundsType t) { auto p = get(); p.workspace_bounds_type = (int)t; set(p); }
+  Vector3f workspace_bounds_min_corner_m() const { auto p = get(); return Vector3f(p.workspace_min[0], p.workspace_min[1], p.workspace_min[2]); }
+  void workspace_bounds_min_corner_m(const Vector3f& v) { auto p = get(); for (int a = 0; a < 3; a++) p.workspace_min[a] = v[a]; set(p); }
+  Vector3f workspace_bounds_max_corner_m() const { auto p = get(); return Vector3f(p.workspace_max[0], p.workspace_max[1], p.workspace_max[2]); }
+  void workspace_bounds_max_corner_m(const Vector3f& v) { auto p = get(); for (int a = 0; a < 3; a++) p.workspace_max[a] = v[a]; set(p); }
+  unsigned int raycast_subsampling_factor() const { return (unsigned int)get().raycast_subsampling; }
+  void raycast_subsampling_factor(unsigned int f) { auto p = get(); p.raycast_subsampling = (int)f; set(p); }
+ private:
+  NvbTsdfParams get() const { NvbTsdfParams p; b200_detail::check(nvb_mapper_get_tsdf_params(m_, &p), "view calculator params", nvb_last_error()); return p; }
+  void set(const NvbTsdfParams& p) { b200_detail::check(nvb_mapper_set_tsdf_params(m_, &p), "view calculator params", nvb_last_error()); }
+  NvbMapper* m_;
+};
+
 // ProjectiveTsdfIntegrator's parameter surface + integrateFrame
 // (integrators/projective_tsdf_integrator.h:48-121, internal/projective_integrator.h:56-85).
 class ProjectiveTsdfIntegrator {
@@ -63,6 +119,7 @@ class ProjectiveTsdfIntegrator {
   WeightingFunctionType weighting_function_type() const { return (WeightingFunctionType)get().weighting_type; }
   void weighting_function_type(WeightingFunctionType t) { auto p = get(); p.weighting_type = (int)t; set(p); }
   float get_truncation_distance_m(float voxel_size) const { return truncation_distance_vox() * voxel_size; }
+  ViewCalculator view_calculator() const { return ViewCalculator(m_); }  // internal/projective_integrator.h:118-119
   // integrateFrame(depth_frame, T_L_C, camera, layer, updated_blocks)
   void integrateFrame(const MaskedDepthImageConstView& depth, const Transform& T_L_C, const Camera& camera,
                       TsdfLayer* /*layer of this mapper*/, std::vector<Index3D>* updated_blocks = nullptr) {
@@ -252,12 +309,18 @@ class EsdfIntegrator {
 
 class Mapper {
  public:
-  explicit Mapper(float voxel_size_m, MemoryType = MemoryType::kDevice,
-                  ProjectiveLayerType projective_layer_type = ProjectiveLayerType::kTsdf)
-      : projective_layer_type_(projective_layer_type) {
+  Mapper() = delete;
+  // Mapper(voxel_size_m, block_memory_pool_params, projective_layer_type, cuda_stream) -- mapper/mapper.h:119-124.
+  // (BlockMemoryPoolParams converts from a MemoryType, so the older Mapper(voxel, MemoryType, layer type) spelling still works.)
+  explicit Mapper(float voxel_size_m, BlockMemoryPoolParams block_memory_pool_params = BlockMemoryPoolParams(),
+                  ProjectiveLayerType projective_layer_type = ProjectiveLayerType::kTsdf,
+                  std::shared_ptr<CudaStream> cuda_stream = std::make_shared<CudaStreamOwning>())
+      : projective_layer_type_(projective_layer_type), cuda_stream_(std::move(cuda_stream)) {
     NvbMapperOptions o;
     nvb_default_mapper_options(&o);
     o.voxel_size_m = voxel_size_m;
+    if (block_memory_pool_params.num_preallocated_blocks > 0)
+      o.tsdf_capacity_blocks = o.esdf_capacity_blocks = block_memory_pool_params.num_preallocated_blocks;
     o.keep_last_view = 1;  // Mapper::integrateDepth keeps the last posed depth image for the decay (mapper_impl.h:70-78)
     // ProjectiveLayerType::kNone has no projective layer to integrate into: nvb_mapper_create rejects it (-1).
     o.projective_layer_type = projective_layer_type == ProjectiveLayerType::kTsdf                 ? NVB_PROJECTIVE_TSDF
@@ -270,13 +333,41 @@ class Mapper {
   Mapper(const Mapper&) = delete;
   Mapper& operator=(const Mapper&) = delete;
 
-  void integrateDepth(const DepthImage& depth_frame, const Transform& T_L_C, const Camera& camera) {
-    integrateDepth(MaskedDepthImageConstView(depth_frame, kMaskActiveEverywhere), T_L_C, camera);
+  // template <typename SensorType> integrateDepth(depth_frame, T_L_C, sensor) -- mapper/mapper.h:167-180, mapper_impl.h:28-81.
+  // SensorType = Camera is built (the Lidar model of sensors/lidar.h is not on this path).
+  template <typename SensorType>
+  void integrateDepth(const DepthImage& depth_frame, const Transform& T_L_C, const SensorType& sensor) {
+    integrateDepth(MaskedDepthImageConstView(depth_frame, kMaskActiveEverywhere), T_L_C, sensor);
   }
-  void integrateDepth(const MaskedDepthImageConstView& depth_frame, const Transform& T_L_C, const Camera& camera) {
+  template <typename SensorType>
+  void integrateDepth(const MaskedDepthImageConstView& depth_frame, const Transform& T_L_C, const SensorType& sensor) {
+    static_assert(std::is_same<SensorType, Camera>::value, "only the Camera sensor model is built on this path");
     // Mapper::integrateDepth dispatches on the projective layer type (mapper_impl.h:28-81)
-    b200_detail::integrateFrame(m_, depth_frame, T_L_C, camera, nullptr);
+    b200_detail::integrateFrame(m_, depth_frame, T_L_C, sensor, nullptr);
   }
+  // Mapper::setMapperParams (mapper/mapper.h:131): the members of MapperParams this path consumes
+  void setMapperParams(const MapperParams& p) {
+    auto ti = tsdf_integrator();
+    ti.max_integration_distance_m(p.projective_integrator_params.projective_integrator_max_integration_distance_m);
+    ti.truncation_distance_vox(p.projective_integrator_params.projective_integrator_truncation_distance_vox);
+    ti.weighting_function_type(p.projective_integrator_params.projective_integrator_weighting_mode);
+    ti.max_weight(p.projective_integrator_params.projective_integrator_max_weight);
+    auto ei = esdf_integrator();
+    ei.max_esdf_distance_m(p.esdf_integrator_params.esdf_integrator_max_distance_m);
+    ei.max_site_distance_vox(p.esdf_integrator_params.esdf_integrator_max_site_distance_vox);
+    ei.min_weight(p.esdf_integrator_params.esdf_integrator_min_weight);
+    ei.esdf_slice_min_height(p.esdf_integrator_params.esdf_slice_min_height);
+    ei.esdf_slice_max_height(p.esdf_integrator_params.esdf_slice_max_height);
+    ei.esdf_slice_height(p.esdf_integrator_params.esdf_slice_height);
+    if (projective_layer_type_ == ProjectiveLayerType::kOccupancy) {
+      auto oi = occupancy_integrator();
+      oi.free_region_occupancy_probability(p.occupancy_integrator_params.free_region_occupancy_probability);
+      oi.occupied_region_occupancy_probability(p.occupancy_integrator_params.occupied_region_occupancy_probability);
+      oi.unobserved_region_occupancy_probability(p.occupancy_integrator_params.unobserved_region_occupancy_probability);
+      oi.occupied_region_half_width_m(p.occupancy_integrator_params.occupied_region_half_width_m);
+    }
+  }
+  std::shared_ptr<CudaStream> cuda_stream() const { return cuda_stream_; }
   // Mapper::markUnobservedTsdfFreeInsideRadius (mapper.h:352-356)
   void markUnobservedTsdfFreeInsideRadius(const Vector3f& center, float radius) {
     const float c[3] = {center[0], center[1], center[2]};
@@ -330,6 +421,11 @@ class Mapper {
   void decayOccupancyAllVoxels() { decayAll(ProjectiveLayerType::kOccupancy); }
   void decayTsdfExcludeLastView() { decayLastView(ProjectiveLayerType::kTsdf); }
   void decayOccupancyExcludeLastView() { decayLastView(ProjectiveLayerType::kOccupancy); }
+  // the reference's spelling (mapper/mapper.h:226-233: the sensor type of the last integrated view)
+  template <typename SensorType>
+  void decayTsdfExcludeLastView() { static_assert(std::is_same<SensorType, Camera>::value, "Camera only"); decayTsdfExcludeLastView(); }
+  template <typename SensorType>
+  void decayOccupancyExcludeLastView() { static_assert(std::is_same<SensorType, Camera>::value, "Camera only"); decayOccupancyExcludeLastView(); }
   TsdfDecayIntegrator tsdf_decay_integrator() const { return TsdfDecayIntegrator(m_); }
   OccupancyDecayIntegrator occupancy_decay_integrator() const { return OccupancyDecayIntegrator(m_); }
   float voxel_size_m() const { return nvb_mapper_voxel_size(m_); }
@@ -358,5 +454,6 @@ class Mapper {
   }
   NvbMapper* m_ = nullptr;
   ProjectiveLayerType projective_layer_type_;
+  std::shared_ptr<CudaStream> cuda_stream_;
 };
 }  // namespace nvblox

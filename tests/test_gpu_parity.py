@@ -551,14 +551,16 @@ def test_full_sequence_properties(gpu):
     m.close()
 
 
-def test_cpp_dropin_program(gpu, tmp_path):
-    """tests/cpp/test_mapper_dropin.cpp: the reference-style C++ test through include/nvblox/mapper/mapper.h."""
+@pytest.mark.parametrize("name,ok", [("test_mapper_dropin", "drop-in C++ API ok"), ("test_multi_mapper_dropin", "MultiMapper drop-in ok")])
+def test_cpp_dropin_program(gpu, tmp_path, name, ok):
+    """tests/cpp/*.cpp: the reference-style C++ tests through include/nvblox/ (Mapper with the reference's constructor
+    signature, occupancy and freespace mappers, MultiMapper as nvblox_ros drives it)."""
     import subprocess
     from test_cabi_symbols import _compile_cpp_dropin
-    exe = _compile_cpp_dropin(tmp_path)
+    exe = _compile_cpp_dropin(tmp_path, name)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "drop-in C++ API ok" in out.stdout
+    assert ok in out.stdout
 
 
 def test_block_list_union_kernel(gpu):
