@@ -441,6 +441,21 @@ NVB_API int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n
                                  const int32_t aabb_max[3], int32_t* out_xyz_dev, int32_t cap,
                                  int32_t* out_count_host);
 
+/* Device-resident merge of the ranks' updated-block lists (multi-GPU; the reference has no counterpart:
+ * it is single-GPU and keeps `updated_blocks` in a host std::vector, C/include/nvblox/mapper/internal/impl/mapper_impl.h:40-60).
+ * A SEGMENT is an int32 device array [count, x0, y0, z0, x1, ...] of capacity cap_entries (1 + 3 * cap_entries ints).
+ *  - nvb_mapper_append_frame_blocks: appends the block list of the last integrated frame to a segment, enqueued on the mapper's
+ *    stream (no host synchronisation; the caller zeroes segment[0] when a batch starts);
+ *  - nvb_blocks_union_segments: sorted unique union (x fastest, then y, then z) of num_segments gathered segments laid out every
+ *    segment_stride_ints ints -- AABB, bitset marking and ordered compaction all sized on the device -- written to
+ *    out_xyz_dev / out_count_dev; enqueued on `stream` (a cudaStream_t; NULL = the mapper's stream), no host synchronisation;
+ *  - nvb_blocks_union_status: synchronises and reports whether a union overflowed its bitset (1) -- a test / debug call. */
+NVB_API int32_t nvb_mapper_append_frame_blocks(NvbMapper* m, int32_t* segment_dev, int32_t cap_entries);
+NVB_API int32_t nvb_blocks_union_segments(NvbMapper* m, const int32_t* segments_dev, int32_t num_segments,
+                                          int32_t segment_stride_ints, int32_t cap_entries, int32_t* out_xyz_dev,
+                                          int32_t out_cap, int32_t* out_count_dev, void* stream);
+NVB_API int32_t nvb_blocks_union_status(NvbMapper* m, int32_t* out_error);
+
 /* Device-side join (no host synchronisation): work enqueued on nvb_mapper_stream() after this
  * call also waits for the ESDF wavefront, which runs on an internal side stream so that it
  * overlaps the next frame's TSDF chain. Needed before recording an event on the mapper's stream. */

@@ -165,6 +165,10 @@ struct NvbMapper {
   int ges_switch = 160;
   int* seed_upd = nullptr;
   int* seed_clr = nullptr;
+  // device-resident merge of block lists (nvb_blocks_union_segments): own scratch, usable on any stream
+  unsigned int* union_bits = nullptr;
+  long long union_bits_cap = 0;      // in bits
+  int* union_state = nullptr;        // AABB, error flag, words in use
   unsigned int* clr_bits = nullptr;  // to-clear bitmap of the current update (2048 words)
   unsigned int* psum = nullptr;  // per ESDF slot: box of the block offsets its voxels' parents point into (clear-pass pruning)
   bool prune_default = false;    // esdf_persistent == 3 and not switched off (NVB_CLEAR_PRUNE=0)
@@ -624,6 +628,7 @@ int checkDeviceError(NvbMapper* m) {
     cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream);
     cudaStreamSynchronize(m->stream);
     if (err & 2) return fail(NVB_ERR_INDEX_RANGE, "a block index does not fit the 21-bit hash key");
+    if (err & 4) return fail(NVB_ERR_CAPACITY, "a block-list segment of the multi-GPU merge overflowed (nvb_mapper_append_frame_blocks)");
     return fail(NVB_ERR_CAPACITY, "a layer slab overflowed on the device");
   }
   return NVB_OK;
@@ -1074,7 +1079,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
   cudaFree(m->xslab), cudaFree(m->xrec), cudaFree(m->xcounts);
   cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
-  cudaFree(m->clr_bits);
+  cudaFree(m->clr_bits), cudaFree(m->union_bits), cudaFree(m->union_state);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
@@ -2098,6 +2103,48 @@ int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n, const 
     NVB_CUDA(cudaMemcpyAsync(m->h_ints, m->frame_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     NVB_CUDA(cudaStreamSynchronize(m->stream));
     *out_count_host = m->h_ints[0];
+  }
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_append_frame_blocks(NvbMapper* m, int32_t* segment_dev, int32_t cap_entries) {
+  if (!m || !segment_dev || cap_entries <= 0) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  if (!m->frame_blocks) return NVB_OK;  // no frame integrated yet
+  launchAppendFrame(m->frame_blocks, m->frame_count, segment_dev, cap_entries, m->error_dev, m->stream);
+  m->launches++;
+  return NVB_OK;
+}
+
+int32_t nvb_blocks_union_segments(NvbMapper* m, const int32_t* segments_dev, int32_t num_segments, int32_t segment_stride_ints,
+                                  int32_t cap_entries, int32_t* out_xyz_dev, int32_t out_cap, int32_t* out_count_dev, void* stream) {
+  if (!m || !segments_dev || !out_xyz_dev || !out_count_dev || num_segments <= 0 || cap_entries <= 0 ||
+      segment_stride_ints < 1 + 3 * cap_entries)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "bad argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  if (!m->union_bits) {
+    // 2^28 cells = 32 MiB of bits: a union AABB of e.g. 1024 x 1024 x 256 blocks (410 m x 410 m x 102 m at 5 cm voxels)
+    m->union_bits_cap = 1ll << 28;
+    NVB_CUDA(cudaMalloc(&m->union_bits, (size_t)(m->union_bits_cap / 8)));
+    NVB_CUDA(cudaMemset(m->union_bits, 0, (size_t)(m->union_bits_cap / 8)));
+    NVB_CUDA(cudaMalloc(&m->union_state, 8 * sizeof(int)));
+    NVB_CUDA(cudaMemset(m->union_state, 0, 8 * sizeof(int)));
+  }
+  launchUnionSegments(segments_dev, num_segments, segment_stride_ints, cap_entries, m->union_state, m->union_bits, m->union_bits_cap,
+                      out_xyz_dev, out_cap, out_count_dev, stream ? (cudaStream_t)stream : m->stream);
+  m->launches += 5;
+  return NVB_OK;
+}
+
+int32_t nvb_blocks_union_status(NvbMapper* m, int32_t* out_error) {
+  if (!m || !out_error) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  NVB_CUDA(cudaSetDevice(m->device));
+  *out_error = 0;
+  if (m->union_state) {
+    NVB_CUDA(cudaDeviceSynchronize());
+    int st[8];
+    NVB_CUDA(cudaMemcpy(st, m->union_state, sizeof(st), cudaMemcpyDeviceToHost));
+    *out_error = st[6];
   }
   return NVB_OK;
 }

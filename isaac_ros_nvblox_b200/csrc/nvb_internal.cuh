@@ -512,6 +512,11 @@ void launchMarkSkipped(const DevLayer& layer, const int* xyz_dev, int n, int* sk
 // nvb_esdf.cu: ESDF side of a deallocation (Mapper::clearBlocksInLayers)
 void launchEsdfRemoveBlocks(const EsdfCtx& c, const int4* dead, const int* dead_count, int upper, cudaStream_t stream);
 
+// nvb_merge.cu: device-resident merge of the ranks' block lists (multi-GPU)
+void launchAppendFrame(const int4* frame, const int* frame_count, int* seg, int cap, int* error, cudaStream_t stream);
+void launchUnionSegments(const int* segs, int num_segments, int stride, int cap, int* state, unsigned int* bits, long long cap_bits,
+                         int* out_xyz, int out_cap, int* out_count, cudaStream_t stream);
+
 // nvb_util.cu
 void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsigned char* out, unsigned char* found,
                         cudaStream_t stream);

@@ -105,6 +105,101 @@ def merge_updated_blocks(mapper, stream=None, group=None):
     return merge_block_lists(torch.from_numpy(np.ascontiguousarray(idx)), group=group)
 
 
+def make_segment(xyz, cap):
+    """(n,3) block indices -> the int32 segment [count, x0, y0, z0, ...] of capacity `cap` the device merge exchanges."""
+    xyz = np.asarray(xyz, np.int32).reshape(-1, 3)
+    seg = np.zeros(1 + 3 * cap, np.int32)
+    n = min(len(xyz), cap)
+    seg[0] = n
+    seg[1:1 + 3 * n] = xyz[:n].reshape(-1)
+    return seg
+
+
+def union_segments_reference(segments, cap):
+    """What nvb_blocks_union_segments computes, in numpy: sorted unique union of the gathered segments, x fastest, then y,
+    then z. `segments`: (world, 1 + 3 * cap) int32."""
+    segments = np.asarray(segments, np.int32).reshape(-1, 1 + 3 * cap)
+    rows = [s[1:1 + 3 * int(min(max(s[0], 0), cap))].reshape(-1, 3) for s in segments]
+    allxyz = np.concatenate(rows) if rows else np.zeros((0, 3), np.int32)
+    if len(allxyz) == 0:
+        return allxyz
+    u = np.unique(allxyz, axis=0)
+    return u[np.lexsort((u[:, 0], u[:, 1], u[:, 2]))]
+
+
+class BatchMerger:
+    """Device-resident merge of the ranks' updated-block lists, one merge per batch of frames.
+
+    Every frame's block list is appended on the device to this rank's segment (no host copy of indices, no count exchange);
+    `merge()` enqueues ONE fixed-size all-gather of the segments and the library's union kernels on a side stream, so the next
+    batch's frames (on the mapper's streams) overlap it; `result()` is the only call that synchronises. Segments are
+    double-buffered: the segment a merge is reading is not the one the next batch appends to.
+    """
+
+    def __init__(self, mapper, cap_entries, group=None):
+        self.m, self.cap, self.group = mapper, int(cap_entries), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.stride = 1 + 3 * self.cap
+        self.local = [torch.zeros(self.stride, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.gathered = torch.zeros(self.world * self.stride, dtype=torch.int32, device=dev)
+        self.out = torch.zeros((self.world * self.cap, 3), dtype=torch.int32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ext = torch.cuda.ExternalStream(mapper.cuda_stream(), device=dev)
+        self.comm = torch.cuda.Stream(device=dev)
+        self.read_done = [None, None]
+        self.cur = 0
+        self.t0 = torch.cuda.Event(enable_timing=True)
+        self.t1 = torch.cuda.Event(enable_timing=True)
+        self.timed = []
+        torch.cuda.synchronize()
+
+    def append_last_frame(self):
+        """Append the block list of the mapper's last integrated frame to this batch's segment (enqueued, no sync)."""
+        from ._lib import check
+        check(self.m._L.nvb_mapper_append_frame_blocks(self.m._h, self.local[self.cur].data_ptr(), self.cap))
+
+    def merge(self, timed=False):
+        """All-gather the segments of this batch and enqueue the union; start the next batch. No host synchronisation."""
+        from ._lib import check
+        seg = self.local[self.cur]
+        self.comm.wait_stream(self.ext)  # the appends of this batch
+        with torch.cuda.stream(self.comm):
+            if timed:
+                self.t0.record(self.comm)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.gathered, seg, group=self.group)
+                src = self.gathered
+            else:
+                src = seg
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+            self.read_done[self.cur] = ev
+            check(self.m._L.nvb_blocks_union_segments(self.m._h, src.data_ptr(), self.world, self.stride, self.cap,
+                                                      self.out.data_ptr(), self.out.shape[0], self.count.data_ptr(),
+                                                      self.comm.cuda_stream))
+            if timed:
+                self.t1.record(self.comm)
+                self.timed.append((self.t0, self.t1))
+                self.t0, self.t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # next batch appends to the other segment, once the merge that last read it is done with it
+        self.cur ^= 1
+        if self.read_done[self.cur] is not None:
+            self.ext.wait_event(self.read_done[self.cur])
+        with torch.cuda.stream(self.ext):
+            self.local[self.cur][:1].zero_()
+
+    def result(self):
+        """The last merge's union as an (n, 3) int32 tensor on the device (synchronises the merge stream)."""
+        self.comm.synchronize()
+        return self.out[:int(self.count.item())]
+
+    def merge_ms(self):
+        """Device time of the timed merges (all-gather + union kernels), in ms each."""
+        self.comm.synchronize()
+        return [a.elapsed_time(b) for a, b in self.timed]
+
+
 def shard_frames(num_frames, rank, world):
     """Frame indices of `rank` when one stream of frames is dealt round-robin over `world` map
     replicas (time-slice sharding)."""

@@ -563,6 +563,62 @@ def test_cpp_dropin_program(gpu, tmp_path, name, ok):
     assert ok in out.stdout
 
 
+def test_device_resident_block_list_merge(gpu):
+    """nvb_mapper_append_frame_blocks + nvb_blocks_union_segments: frame lists appended on the device, gathered segments
+    merged into the sorted unique union (x fastest) with AABB / bitset / compaction sized on the device; BatchMerger's
+    double-buffered batches on one rank."""
+    import ctypes as C
+    import torch
+    nvb = _nvb()
+    from isaac_ros_nvblox_b200 import multi_gpu
+    from isaac_ros_nvblox_b200._lib import check
+    m = nvb.Mapper(0.05)
+    rng = np.random.default_rng(11)
+    cap, world = 2000, 5
+    lists = [rng.integers(-60, 60, size=(n, 3)).astype(np.int32) for n in (700, 0, 2000, 1, 1500)]
+    lists[4][:300] = lists[0][:300]  # overlap between ranks
+    segs = np.stack([multi_gpu.make_segment(l, cap) for l in lists])
+    segs[3, 4:] = 12345  # garbage beyond a segment's count must be ignored
+    want = multi_gpu.union_segments_reference(segs, cap)
+    gathered = torch.from_numpy(segs.reshape(-1)).cuda()
+    out = torch.zeros((world * cap, 3), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(2):  # twice: the bitset is left clean
+        check(m._L.nvb_blocks_union_segments(m._h, gathered.data_ptr(), world, 1 + 3 * cap, cap, out.data_ptr(), out.shape[0],
+                                             cnt.data_ptr(), None))
+        m.synchronize()
+        got = out[:int(cnt.item())].cpu().numpy()
+        assert np.array_equal(got, want)
+    err = C.c_int32(0)
+    check(m._L.nvb_blocks_union_status(m._h, C.byref(err)))
+    assert err.value == 0
+    # all segments empty
+    empty = torch.zeros(world * (1 + 3 * cap), dtype=torch.int32, device="cuda")
+    check(m._L.nvb_blocks_union_segments(m._h, empty.data_ptr(), world, 1 + 3 * cap, cap, out.data_ptr(), out.shape[0], cnt.data_ptr(), None))
+    m.synchronize()
+    assert int(cnt.item()) == 0
+    # frames appended on the device, batch by batch
+    cs, cam, ocam = cameras(320, 240)
+    frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:6])
+    bm = multi_gpu.BatchMerger(m, cap_entries=3 * 4096)
+    per_frame = []
+    for i, (depth, T) in enumerate(frames):
+        per_frame.append(m.integrate_depth(depth, T, cam))
+        bm.append_last_frame()
+        if i % 3 == 2:
+            bm.merge(timed=True)
+            u = np.unique(np.concatenate(per_frame[i - 2:i + 1]), axis=0)
+            assert np.array_equal(bm.result().cpu().numpy(), u[np.lexsort((u[:, 0], u[:, 1], u[:, 2]))])
+    assert len(bm.merge_ms()) == 2 and all(t > 0 for t in bm.merge_ms())
+    # a segment that is too small is reported, not silently truncated
+    small = multi_gpu.BatchMerger(m, cap_entries=100)
+    m.integrate_depth(frames[0][0], frames[0][1], cam)
+    small.append_last_frame()
+    with pytest.raises(Exception):
+        m.synchronize()
+    m.close()
+
+
 def test_block_list_union_kernel(gpu):
     """nvb_blocks_union == sort(unique(concat)) as a set, in x-fastest order, with padding and duplicates."""
     import torch

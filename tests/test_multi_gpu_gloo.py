@@ -80,3 +80,41 @@ def test_shard_frames_partition():
     for world in (1, 2, 4, 8):
         parts = [multi_gpu.shard_frames(80, r, world) for r in range(world)]
         assert sorted(sum(parts, [])) == list(range(80))
+
+
+def _worker_segments(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from isaac_ros_nvblox_b200 import multi_gpu
+    cap = 512
+    rng = np.random.default_rng(7 + rank)
+    n = [300, 0, 512][rank % 3]
+    local = rng.integers(-20, 20, size=(n, 3)).astype(np.int32)
+    seg = torch.from_numpy(multi_gpu.make_segment(local, cap))
+    gathered = torch.zeros(world * (1 + 3 * cap), dtype=torch.int32)
+    dist.all_gather_into_tensor(gathered, seg)  # ONE fixed-size collective: no count exchange
+    union = multi_gpu.union_segments_reference(gathered.numpy(), cap)
+    q.put((rank, local, union))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fixed_size_segment_exchange_world3():
+    """The device merge's protocol (segments [count, xyz...] of fixed capacity, one all-gather, union x fastest) on gloo."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_segments, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    u = np.unique(np.concatenate([r[1] for r in res]), axis=0)
+    want = u[np.lexsort((u[:, 0], u[:, 1], u[:, 2]))]
+    for _, _, union in res:
+        assert np.array_equal(union, want)
