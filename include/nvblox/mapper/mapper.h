@@ -95,6 +95,8 @@ class ViewCalculator {
   void workspace_bounds_min_corner_m(const Vector3f& v) { auto p = get(); for (int a = 0; a < 3; a++) p.workspace_min[a] = v[a]; set(p); }
   Vector3f workspace_bounds_max_corner_m() const { auto p = get(); return Vector3f(p.workspace_max[0], p.workspace_max[1], p.workspace_max[2]); }
   void workspace_bounds_max_corner_m(const Vector3f& v) { auto p = get(); for (int a = 0; a < 3; a++) p.workspace_max[a] = v[a]; set(p); }
+  bool cache_last_viewpoint() const { return nvb_mapper_get_cache_last_viewpoint(m_) != 0; }  // view_calculator.h:146-151
+  void cache_last_viewpoint(bool v) { b200_detail::check(nvb_mapper_set_cache_last_viewpoint(m_, v ? 1 : 0), "cache_last_viewpoint", nvb_last_error()); }
   unsigned int raycast_subsampling_factor() const { return (unsigned int)get().raycast_subsampling; }
   void raycast_subsampling_factor(unsigned int f) { auto p = get(); p.raycast_subsampling = (int)f; set(p); }
  private:

@@ -441,6 +441,12 @@ NVB_API int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n
                                  const int32_t aabb_max[3], int32_t* out_xyz_dev, int32_t cap,
                                  int32_t* out_count_host);
 
+/* ViewCalculator::cache_last_viewpoint (C/include/nvblox/integrators/view_calculator.h:196; C/src/integrators/view_calculator.cu:82-88),
+ * on by default like in the reference: nvb_mapper_integrate_depth* reuses the block list of one of the last two frames whose
+ * pose (1 mm, 0.1 degree) and sensor match -- whatever the depth image holds (ViewpointCache, view_calculator.h:211-244). */
+NVB_API int32_t nvb_mapper_set_cache_last_viewpoint(NvbMapper* m, int32_t enable);
+NVB_API int32_t nvb_mapper_get_cache_last_viewpoint(const NvbMapper* m);
+
 /* Device-resident merge of the ranks' updated-block lists (multi-GPU; the reference has no counterpart:
  * it is single-GPU and keeps `updated_blocks` in a host std::vector, C/include/nvblox/mapper/internal/impl/mapper_impl.h:40-60).
  * A SEGMENT is an int32 device array [count, x0, y0, z0, x1, ...] of capacity cap_entries (1 + 3 * cap_entries ints).

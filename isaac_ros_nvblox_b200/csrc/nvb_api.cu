@@ -95,6 +95,19 @@ struct NvbMapper {
   int tsdf_count_ub = 0;   // host-side upper bound of *tsdf.count
   int esdf_extra_ub = 0;   // blocks submitted to the ESDF through explicit lists
 
+  // ViewpointCache of the projective integrator's ViewCalculator (C/include/nvblox/integrators/view_calculator.h:196,211-244):
+  // up to two (pose, sensor) -> block-list entries, newest first. A list is kept as the view bitset it was compacted from (a
+  // few KB on the device): a hit skips the raycast and replays the compaction + allocation, which yields the same list in the
+  // same order and re-allocates blocks that were deallocated in between, like allocateBlocksWhereRequired does in the reference.
+  int cache_last_viewpoint = 1;
+  int vc_n = 0;
+  float vc_T[2][16];
+  NvbCamera vc_cam[2];
+  ViewGrid vc_grid[2];
+  long long vc_cells[2] = {0, 0};
+  unsigned int* vc_bits[2] = {nullptr, nullptr};
+  size_t vc_bits_cap[2] = {0, 0};
+
   // per-frame scratch
   unsigned int* bits = nullptr;
   size_t bits_words_cap = 0;
@@ -641,6 +654,55 @@ int validateFrameArgs(const NvbMapper* m, const float* depth, int rows, int cols
   return NVB_OK;
 }
 
+// arePosesClose (C/src/geometry/transforms.cpp:20-36) in binary32, Eigen::AngleAxisf(R).angle() through the quaternion.
+bool posesClose(const float* T1, const float* T2, float tol_m, float tol_deg) {
+  auto R_ = [](const float* T, int i, int j) { return T[j * 4 + i]; };
+  float inv[16] = {0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) inv[j * 4 + i] = R_(T1, j, i);
+  for (int i = 0; i < 3; i++) inv[12 + i] = -(inv[0 * 4 + i] * T1[12] + (inv[1 * 4 + i] * T1[13] + inv[2 * 4 + i] * T1[14]));
+  float R[3][3], t[3];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) R[i][j] = (R_(inv, i, 0) * R_(T2, 0, j) + R_(inv, i, 1) * R_(T2, 1, j)) + R_(inv, i, 2) * R_(T2, 2, j);
+    t[i] = ((R_(inv, i, 0) * T2[12] + R_(inv, i, 1) * T2[13]) + R_(inv, i, 2) * T2[14]) + inv[12 + i];
+  }
+  if (std::sqrt(t[0] * t[0] + (t[1] * t[1] + t[2] * t[2])) > tol_m) return false;
+  float w, x, y, z;
+  const float tr = R[0][0] + R[1][1] + R[2][2];
+  if (tr > 0.0f) {
+    float q = std::sqrt(tr + 1.0f);
+    w = 0.5f * q;
+    q = 0.5f / q;
+    x = (R[2][1] - R[1][2]) * q, y = (R[0][2] - R[2][0]) * q, z = (R[1][0] - R[0][1]) * q;
+  } else {
+    int i = 0;
+    if (R[1][1] > R[0][0]) i = 1;
+    if (R[2][2] > R[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    float q = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0f);
+    float v[3];
+    v[i] = 0.5f * q;
+    q = 0.5f / q;
+    w = (R[k][j] - R[j][k]) * q;
+    v[j] = (R[j][i] + R[i][j]) * q;
+    v[k] = (R[k][i] + R[i][k]) * q;
+    x = v[0], y = v[1], z = v[2];
+  }
+  const float n = std::sqrt(x * x + (y * y + z * z));
+  const float angle = n != 0.0f ? 2.0f * std::atan2(n, std::fabs(w)) : 0.0f;
+  const float deg = (float)((double)(angle * 180.0f) / 3.14159265358979323846);
+  return !(std::fabs(deg) > tol_deg);
+}
+// operator==(Camera, Camera) (C/include/nvblox/sensors/internal/impl/camera_impl.h:134-156)
+bool camerasEqual(const NvbCamera& a, const NvbCamera& b) {
+  bool same = std::fabs((double)(a.fu - b.fu)) <= 0.1 && std::fabs((double)(a.fv - b.fv)) <= 0.1 &&
+              std::fabs((double)(a.cu - b.cu)) <= 0.1 && std::fabs((double)(a.cv - b.cv)) <= 0.1 && a.width == b.width &&
+              a.height == b.height && (a.has_distortion != 0) == (b.has_distortion != 0);
+  if (same && a.has_distortion && b.has_distortion)
+    same = a.k1 == b.k1 && a.k2 == b.k2 && a.k3 == b.k3 && a.k4 == b.k4 && a.k5 == b.k5 && a.k6 == b.k6 && a.p1 == b.p1 && a.p2 == b.p2;
+  return same;
+}
+
 // The depth-integration chain for one frame, enqueued on m->stream.
 int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, int mask_mode, int memory, int rows,
                  int cols, const float* T_L_C_cm, const NvbCamera* cam, float block_size, float trunc_m,
@@ -648,7 +710,17 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
   const Rigid T_L_C = rigidFromColMajor(T_L_C_cm);
   ViewGrid grid{};
   long long cells = 0;
-  const bool visible = computeViewGrid(*cam, T_L_C, block_size, max_dist, m->tp, &grid, &cells);
+  // ViewpointCache::getCachedResult (view_calculator_impl.h:120-155): keyed on the pose and the sensor only
+  int cache_hit = -1;
+  if (integrate && m->cache_last_viewpoint)
+    for (int i = 0; i < m->vc_n && cache_hit < 0; i++)
+      if (posesClose(T_L_C_cm, m->vc_T[i], 0.001f, 0.1f) && camerasEqual(*cam, m->vc_cam[i])) cache_hit = i;
+  bool visible;
+  if (cache_hit >= 0) {
+    grid = m->vc_grid[cache_hit], cells = m->vc_cells[cache_hit], visible = true;
+  } else {
+    visible = computeViewGrid(*cam, T_L_C, block_size, max_dist, m->tp, &grid, &cells);
+  }
   if (!visible) {
     if (cells < 0) return fail(NVB_ERR_CAPACITY, "view AABB has more than 2^31 blocks");
     NVB_CUDA(cudaMemsetAsync(m->frame_count, 0, sizeof(int), m->stream));  // empty workspace -> empty list
@@ -693,10 +765,36 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
   }
 
   beginStage(m, 0);
-  launchViewRaycast(depth_dev, rows, cols, T_L_C, *cam, block_size, trunc_m, max_dist, m->tp.raycast_subsampling,
-                    grid, m->bits, m->stream);
+  if (cache_hit >= 0) {
+    // the cached view bitset instead of a raycast
+    NVB_CUDA(cudaMemcpyAsync(m->bits, m->vc_bits[cache_hit], (size_t)grid.num_words * sizeof(unsigned int), cudaMemcpyDeviceToDevice,
+                             m->stream));
+  } else {
+    launchViewRaycast(depth_dev, rows, cols, T_L_C, *cam, block_size, trunc_m, max_dist, m->tp.raycast_subsampling,
+                      grid, m->bits, m->stream);
+    m->launches++;
+    if (integrate && m->cache_last_viewpoint) {
+      // ViewpointCache::storeResultInCache (view_calculator_impl.h:157-174): newest first, the oldest of two is dropped
+      if (m->vc_n == 2) m->vc_n = 1;
+      if (m->vc_n == 1) {
+        std::swap(m->vc_bits[0], m->vc_bits[1]), std::swap(m->vc_bits_cap[0], m->vc_bits_cap[1]);
+        memcpy(m->vc_T[1], m->vc_T[0], sizeof(m->vc_T[0]));
+        m->vc_cam[1] = m->vc_cam[0], m->vc_grid[1] = m->vc_grid[0], m->vc_cells[1] = m->vc_cells[0];
+      }
+      if (m->vc_bits_cap[0] < (size_t)grid.num_words) {
+        NVB_CUDA(syncAll(m));
+        if (m->vc_bits[0]) cudaFree(m->vc_bits[0]);
+        m->vc_bits_cap[0] = (size_t)(1.5 * grid.num_words) + 64;
+        NVB_CUDA(cudaMalloc(&m->vc_bits[0], m->vc_bits_cap[0] * sizeof(unsigned int)));
+      }
+      NVB_CUDA(cudaMemcpyAsync(m->vc_bits[0], m->bits, (size_t)grid.num_words * sizeof(unsigned int), cudaMemcpyDeviceToDevice,
+                               m->stream));
+      memcpy(m->vc_T[0], T_L_C_cm, sizeof(m->vc_T[0]));
+      m->vc_cam[0] = *cam, m->vc_grid[0] = grid, m->vc_cells[0] = cells;
+      m->vc_n++;
+    }
+  }
   endStage(m);
-  m->launches++;
 
   beginStage(m, 1);
   CompactArgs ca{};
@@ -1080,6 +1178,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->xslab), cudaFree(m->xrec), cudaFree(m->xcounts);
   cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
   cudaFree(m->clr_bits), cudaFree(m->union_bits), cudaFree(m->union_state);
+  cudaFree(m->vc_bits[0]), cudaFree(m->vc_bits[1]);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
   cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
@@ -2148,6 +2247,14 @@ int32_t nvb_blocks_union_status(NvbMapper* m, int32_t* out_error) {
   }
   return NVB_OK;
 }
+
+int32_t nvb_mapper_set_cache_last_viewpoint(NvbMapper* m, int32_t enable) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  m->cache_last_viewpoint = enable ? 1 : 0;
+  if (!enable) m->vc_n = 0;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_cache_last_viewpoint(const NvbMapper* m) { return m ? m->cache_last_viewpoint : 0; }
 
 int32_t nvb_mapper_join_streams(NvbMapper* m) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");

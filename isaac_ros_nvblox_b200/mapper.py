@@ -180,6 +180,12 @@ class _TsdfIntegrator:
             self._set(weighting_type=int(v))
         return self._get().weighting_type
 
+    def cache_last_viewpoint(self, v=None):
+        """ViewCalculator::cache_last_viewpoint (view_calculator.h:196): on by default, like the reference."""
+        if v is not None:
+            check(self._m._L.nvb_mapper_set_cache_last_viewpoint(self._m._h, 1 if v else 0))
+        return bool(self._m._L.nvb_mapper_get_cache_last_viewpoint(self._m._h))
+
     def raycast_subsampling_factor(self, v=None):
         if v is not None:
             self._set(raycast_subsampling=int(v))

@@ -484,6 +484,13 @@ struct OrMap {
    * (esdf_integrator.cu:242-257), so its content carries over between calls. */
   List esdf_cleared_persistent;
   int64_t stats[8];
+  /* ViewpointCache of the projective integrator's ViewCalculator (integrators/view_calculator.h:196,211-244): up to
+   * kMaxCacheSize = 2 (pose, sensor, block list) entries, newest first; cache_last_viewpoint_ defaults to true. */
+  int32_t cache_last_viewpoint;
+  int32_t view_cache_n;
+  float view_cache_T[2][16];
+  OrCamera view_cache_cam[2];
+  List view_cache_blocks[2];
 };
 
 void or_default_tsdf_params(OrTsdfParams* p) {
@@ -514,6 +521,7 @@ void or_default_occupancy_params(OrOccupancyParams* p) {
 
 OrMap* or_map_create(float voxel_size_m) {
   OrMap* m = (OrMap*)calloc(1, sizeof(OrMap));
+  m->cache_last_viewpoint = 1;
   m->voxel_size = voxel_size_m;
   m->block_size = voxel_size_m * (float)VPS; /* voxelSizeToBlockSize, indexing_impl.h:22 */
   layer_init(&m->tsdf, sizeof(OrTsdfVoxel) * VPB);
@@ -527,11 +535,13 @@ void or_map_destroy(OrMap* m) {
   if (!m) return;
   layer_free(&m->tsdf), layer_free(&m->esdf), layer_free(&m->occ), layer_free(&m->freespace), layer_free(&m->color);
   list_free(&m->esdf_cleared_persistent);
+  for (int i = 0; i < m->view_cache_n; i++) list_free(&m->view_cache_blocks[i]);
   free(m);
 }
 void or_map_clear(OrMap* m) {
   layer_clear(&m->tsdf), layer_clear(&m->esdf), layer_clear(&m->occ), layer_clear(&m->freespace), layer_clear(&m->color);
   m->esdf_cleared_persistent.n = 0;
+  /* (Mapper::clear does not touch the integrators: the viewpoint cache survives) */
 }
 
 /* ------------------------------------------------------------------------- */
@@ -552,10 +562,12 @@ static void set_index_updated(i3 idx, i3 mn, i3 sz, uint8_t* grid) {
 }
 
 /* Returns a malloc'ed list of block indices in x-fastest order. */
+static int g_view_not_cacheable; /* set when the last view_raycast returned before the cache store (empty workspace) */
 static List view_raycast(const float* depth, int rows, int cols, const float* T_L_C,
                          const OrCamera* cam, float block_size, float trunc_m,
                          const OrTsdfParams* P) {
   List out = {0};
+  g_view_not_cacheable = 1;
   const float max_dist = P->max_integration_distance_m;
   const int f = P->raycast_subsampling;
   /* view_calculator_impl.cuh:137-156 */
@@ -568,6 +580,7 @@ static List view_raycast(const float* depth, int rows, int cols, const float* T_
                    max_index.z - min_index.z + 1};
   const int64_t lin_size = (int64_t)size.x * size.y * size.z;
   if (lin_size <= 0) return out;
+  g_view_not_cacheable = 0; /* from here on the result reaches storeResultInCache (view_calculator_impl.cuh:193-196) */
   uint8_t* grid = (uint8_t*)calloc((size_t)lin_size, 1);
 
   /* getBlocksByRaycastingPixelsAsync launch shape (view_calculator_impl.cuh:200-233). */
@@ -616,6 +629,92 @@ static List view_raycast(const float* depth, int rows, int cols, const float* T_
   free(grid);
   return out;
 }
+
+/* arePosesClose (src/geometry/transforms.cpp:20-36) in binary32: T_B1_B2 = T_A_B1^-1 * T_A_B2, translation norm and the angle of
+ * Eigen::AngleAxisf(R) (via the quaternion: 2 atan2(|vec|, |w|), Eigen/src/Geometry/AngleAxis.h). */
+static int poses_close(const float* T1, const float* T2, float tol_m, float tol_deg) {
+  float inv[16], R[3][3], t[3];
+  invert_isometry(T1, inv);
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) R[i][j] = (Rm(inv, i, 0) * Rm(T2, 0, j) + Rm(inv, i, 1) * Rm(T2, 1, j)) + Rm(inv, i, 2) * Rm(T2, 2, j);
+    t[i] = ((Rm(inv, i, 0) * Tt(T2, 0) + Rm(inv, i, 1) * Tt(T2, 1)) + Rm(inv, i, 2) * Tt(T2, 2)) + Tt(inv, i);
+  }
+  if (sqrtf(t[0] * t[0] + (t[1] * t[1] + t[2] * t[2])) > tol_m) return 0;
+  /* QuaternionBase::operator=(matrix) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl<Other,3,3>) */
+  float w, x, y, z;
+  const float tr = R[0][0] + R[1][1] + R[2][2];
+  if (tr > 0.0f) {
+    float q = sqrtf(tr + 1.0f);
+    w = 0.5f * q;
+    q = 0.5f / q;
+    x = (R[2][1] - R[1][2]) * q, y = (R[0][2] - R[2][0]) * q, z = (R[1][0] - R[0][1]) * q;
+  } else {
+    int i = 0;
+    if (R[1][1] > R[0][0]) i = 1;
+    if (R[2][2] > R[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    float q = sqrtf(R[i][i] - R[j][j] - R[k][k] + 1.0f);
+    float v[3];
+    v[i] = 0.5f * q;
+    q = 0.5f / q;
+    w = (R[k][j] - R[j][k]) * q;
+    v[j] = (R[j][i] + R[i][j]) * q;
+    v[k] = (R[k][i] + R[i][k]) * q;
+    x = v[0], y = v[1], z = v[2];
+  }
+  const float n = sqrtf(x * x + (y * y + z * z));
+  const float angle = n != 0.0f ? 2.0f * atan2f(n, fabsf(w)) : 0.0f;
+  const float deg = (float)((double)(angle * 180.0f) / 3.14159265358979323846); /* float * 180.0f / M_PI (double) -> float */
+  return !(fabsf(deg) > tol_deg);
+}
+/* operator==(Camera, Camera) (sensors/internal/impl/camera_impl.h:134-156) */
+static int cameras_equal(const OrCamera* a, const OrCamera* b) {
+  int same = 1;
+  same &= fabs((double)(a->fu - b->fu)) <= 0.1;
+  same &= fabs((double)(a->fv - b->fv)) <= 0.1;
+  same &= fabs((double)(a->cu - b->cu)) <= 0.1;
+  same &= fabs((double)(a->cv - b->cv)) <= 0.1;
+  same &= a->width == b->width && a->height == b->height;
+  same &= (a->has_distortion != 0) == (b->has_distortion != 0);
+  if (a->has_distortion && b->has_distortion)
+    same &= a->k1 == b->k1 && a->k2 == b->k2 && a->k3 == b->k3 && a->k4 == b->k4 && a->k5 == b->k5 && a->k6 == b->k6 &&
+            a->p1 == b->p1 && a->p2 == b->p2;
+  return same;
+}
+/* getBlocksInImageViewRaycast with its ViewpointCache (view_calculator_impl.cuh:117-197, view_calculator_impl.h:120-174): a
+ * hit is keyed on the pose (1 mm, 0.1 degree) and the sensor ONLY -- not on the depth image, not on the distances. */
+static List view_raycast_cached(OrMap* map, const float* depth, int rows, int cols, const float* T_L_C, const OrCamera* cam,
+                                float block_size, float trunc_m, const OrTsdfParams* P) {
+  if (map->cache_last_viewpoint) {
+    for (int i = 0; i < map->view_cache_n; i++) {
+      if (poses_close(T_L_C, map->view_cache_T[i], 0.001f, 0.1f) && cameras_equal(cam, &map->view_cache_cam[i])) {
+        List out = {0};
+        for (int32_t q = 0; q < map->view_cache_blocks[i].n; q++) list_push(&out, map->view_cache_blocks[i].v[q]);
+        return out;
+      }
+    }
+  }
+  List l = view_raycast(depth, rows, cols, T_L_C, cam, block_size, trunc_m, P);
+  if (map->cache_last_viewpoint && !g_view_not_cacheable) {
+    if (map->view_cache_n == 2) { /* pop_back */
+      list_free(&map->view_cache_blocks[1]);
+      map->view_cache_n = 1;
+    }
+    if (map->view_cache_n == 1) { /* push_front */
+      memcpy(map->view_cache_T[1], map->view_cache_T[0], sizeof(float) * 16);
+      map->view_cache_cam[1] = map->view_cache_cam[0];
+      map->view_cache_blocks[1] = map->view_cache_blocks[0];
+    }
+    memcpy(map->view_cache_T[0], T_L_C, sizeof(float) * 16);
+    map->view_cache_cam[0] = *cam;
+    List copy = {0};
+    for (int32_t q = 0; q < l.n; q++) list_push(&copy, l.v[q]);
+    map->view_cache_blocks[0] = copy;
+    map->view_cache_n++;
+  }
+  return l;
+}
+void or_map_cache_last_viewpoint(OrMap* map, int32_t enable) { map->cache_last_viewpoint = enable; }
 
 static int32_t copy_out(const List* l, int32_t* out_xyz, int32_t cap) {
   for (int32_t i = 0; i < l->n && i < cap; i++)
@@ -808,7 +907,7 @@ int32_t or_tsdf_integrate(OrMap* map, const float* depth, const uint8_t* mask,
                           const float* T_L_C, const OrCamera* cam,
                           const OrTsdfParams* P, int32_t* out_xyz, int32_t cap) {
   const float trunc = P->truncation_distance_vox * map->voxel_size;
-  List blocks = view_raycast(depth, rows, cols, T_L_C, cam, map->block_size, trunc, P);
+  List blocks = view_raycast_cached(map, depth, rows, cols, T_L_C, cam, map->block_size, trunc, P);
   if (blocks.n == 0) {
     list_free(&blocks);
     return 0;
@@ -834,7 +933,7 @@ int32_t or_occupancy_integrate(OrMap* map, const float* depth, const uint8_t* ma
   if (P->truncation_distance_vox * map->voxel_size < f.half_width)
     P->truncation_distance_vox = f.half_width / map->voxel_size; /* persists, like the setter call */
   const float trunc = P->truncation_distance_vox * map->voxel_size;
-  List blocks = view_raycast(depth, rows, cols, T_L_C, cam, map->block_size, trunc, P);
+  List blocks = view_raycast_cached(map, depth, rows, cols, T_L_C, cam, map->block_size, trunc, P);
   if (blocks.n == 0) {
     list_free(&blocks);
     return 0;

@@ -299,6 +299,8 @@ int32_t or_esdf_block_indices(const OrMap* map, int32_t* out_xyz, int32_t cap);
 int32_t or_tsdf_get_block(const OrMap* map, const int32_t xyz[3], OrTsdfVoxel* out);
 int32_t or_esdf_get_block(const OrMap* map, const int32_t xyz[3], OrEsdfVoxel* out);
 /* Test helper: overwrite / create a TSDF block. */
+/* ViewCalculator::cache_last_viewpoint (integrators/view_calculator.h:196; default on) of the map's projective integrator */
+void or_map_cache_last_viewpoint(OrMap* map, int32_t enable);
 void or_tsdf_set_block(OrMap* map, const int32_t xyz[3], const OrTsdfVoxel* in);
 void or_esdf_set_block(OrMap* map, const int32_t xyz[3], const OrEsdfVoxel* in); /* test hook */
 

@@ -176,6 +176,7 @@ def lib():
     L.or_esdf_get_block.argtypes = [vp, ip, vp]
     L.or_esdf_get_block.restype = C.c_int32
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
+    L.or_map_cache_last_viewpoint.argtypes = [vp, C.c_int32]
     L.or_esdf_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.restype = None
@@ -657,6 +658,10 @@ class OracleMap:
         k = np.asarray(idx, dtype=np.int32)
         v = np.ascontiguousarray(voxels, dtype=TSDF_VOXEL_DTYPE).reshape(8, 8, 8)
         lib().or_tsdf_set_block(self._h, _ip(k), v.ctypes.data)
+
+    def cache_last_viewpoint(self, enable):
+        """ViewCalculator::cache_last_viewpoint of the projective integrator (default on, like the reference)."""
+        lib().or_map_cache_last_viewpoint(self._h, 1 if enable else 0)
 
     def set_esdf_block(self, idx, voxels):
         """Test hook: place an EsdfBlock with the given voxels (ESDF_VOXEL_DTYPE, (8, 8, 8))."""

@@ -563,6 +563,58 @@ def test_cpp_dropin_program(gpu, tmp_path, name, ok):
     assert ok in out.stdout
 
 
+def test_viewpoint_cache_matches_oracle(gpu):
+    """ViewpointCache (view_calculator.h:196,211-244), on by default: (1) the reference's InvalidDepthHandling sequence
+    (test_tsdf_integrator.cpp:588-722) -- six all-invalid frames at one pose, a valid one, three invalid ones -- gives the
+    same lists and the same voxels as the oracle's (the valid frame integrates the NaN frame's cached single block, the
+    later invalid frames decay it); (2) hits and misses by pose / sensor tolerance and the two-entry capacity; (3) the cache
+    can be switched off."""
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras()
+    T = np.eye(4, dtype=np.float32)
+    m, o = nvb.Mapper(0.2), orc.OracleMap(0.2)
+    p = orc.default_tsdf_params(invalid_depth_decay_factor=0.8, weighting_type=orc.WEIGHT_CONSTANT)
+    m.tsdf_integrator().params(invalid_depth_decay_factor=0.8, weighting_type=orc.WEIGHT_CONSTANT)
+    for v in (np.nan, np.inf, -np.inf, -1.0, 0.0, -10.0, 2.0, np.inf, -1.0, 0.0):
+        d = np.full((480, 640), v, np.float32)
+        assert np.array_equal(m.integrate_depth(d, T, cam), o.integrate_depth(d, T, ocam, p)), v
+        assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+    w = sum(float(b["weight"].sum(dtype=np.float64)) for b in m.tsdf_layer().as_dict().values())
+    n = sum(int((b["weight"] > 0).sum()) for b in m.tsdf_layer().as_dict().values())
+    assert n > 0 and abs(w - n * 0.8 ** 3) < 1e-3
+    m.close()
+    # keys and capacity, side by side with the oracle
+    m, o = nvb.Mapper(0.2), orc.OracleMap(0.2)
+    p = orc.default_tsdf_params()
+    near, far = np.full((480, 640), 1.0, np.float32), np.full((480, 640), 4.0, np.float32)
+    poses = []
+    for dx in (0.0, 0.0005, 0.002):
+        Tx = np.eye(4, dtype=np.float32)
+        Tx[0, 3] = dx
+        poses.append(Tx)
+    c, s_ = np.float32(np.cos(np.deg2rad(0.05))), np.float32(np.sin(np.deg2rad(0.05)))
+    R = np.eye(4, dtype=np.float32)
+    R[0, 0], R[0, 2], R[2, 0], R[2, 2] = c, s_, -s_, c
+    cs2, cam2, ocam2 = cameras(f=300.2)
+    seq = [(near, poses[0], cam, ocam), (far, poses[1], cam, ocam), (far, poses[2], cam, ocam), (far, R, cam, ocam),
+           (far, poses[0], cam2, ocam2), (far, poses[0], cam, ocam)]
+    counts = []
+    for d, Tq, cg, co in seq:
+        bg, bo = m.integrate_depth(d, Tq, cg), o.integrate_depth(d, Tq, co, p)
+        assert np.array_equal(bg, bo)
+        counts.append(len(bg))
+    assert counts[1] == counts[0] and counts[3] == counts[0] and counts[2] > 2 * counts[0] and counts[5] == counts[2]
+    assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+    # off: every frame raycasts
+    m.tsdf_integrator().cache_last_viewpoint(False)
+    o.cache_last_viewpoint(False)
+    assert not m.tsdf_integrator().cache_last_viewpoint()
+    bg, bo = m.integrate_depth(far, poses[0], cam), o.integrate_depth(far, poses[0], ocam, p)
+    bg, bo = m.integrate_depth(near, poses[0], cam), o.integrate_depth(near, poses[0], ocam, p)
+    assert np.array_equal(bg, bo) and len(bg) == counts[0]
+    m.close()
+
+
 def test_device_resident_block_list_merge(gpu):
     """nvb_mapper_append_frame_blocks + nvb_blocks_union_segments: frame lists appended on the device, gathered segments
     merged into the sorted unique union (x fastest) with AABB / bitset / compaction sized on the device; BatchMerger's

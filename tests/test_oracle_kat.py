@@ -136,30 +136,72 @@ def test_invalid_depth_frames_integrate_nothing(bad):
         assert not after[k]["weight"].any() and not after[k]["distance"].any()
 
 
-def test_invalid_depth_decay_scales_total_weight():
+def test_invalid_depth_handling_reference_sequence():
+    """TsdfIntegratorTestFixture.InvalidDepthHandling (test_tsdf_integrator.cpp:588-722), call for call on ONE integrator:
+    six all-invalid frames at the identity pose (NaN first), a valid frame, three more invalid ones, voxel size 0.2 m, constant
+    weighting, invalid_depth_decay_factor 0.8. The reference's expectations only hold BECAUSE of its ViewpointCache
+    (view_calculator.h:196,211-244; on by default, keyed on pose + sensor, not on the depth image): the NaN frame casts rays
+    (NaN passes `depth <= 0`, view_calculator_impl.cuh:93) that end in the single block the float->int cast maps NaN to; that
+    list is cached, so the valid frame integrates ONLY that block ("some voxels gain weight", each exactly 1), and the invalid
+    frames that follow -- which cast no rays at all -- reuse it and decay its voxels by 0.8 each. Without the cache the valid
+    frame would touch its whole frustum (24 blocks) and the invalid frames none (no decay): the test's third expectation would fail."""
     cam = _cam()
     T = np.eye(4, dtype=np.float32)
-    m = orc.OracleMap(VOXEL)
-    p = orc.default_tsdf_params(invalid_depth_decay_factor=0.8)
-    m.integrate_depth(np.full((480, 640), 3.0, np.float32), T, cam, p)
-    w0 = sum(float(b["weight"].astype(np.float64).sum()) for b in m.tsdf_layer().values())
-    for i in range(3):
-        m.integrate_depth(np.zeros((480, 640), np.float32), T, cam, p)
-        # zeros cast no rays, so re-integrate on the first frame's blocks with the invalid image:
-    # decay needs the blocks in view; drive it through the block-list entry point
-    m2 = orc.OracleMap(VOXEL)
-    blocks = m2.integrate_depth(np.full((480, 640), 3.0, np.float32), T, cam, p)
-    w_start = sum(float(b["weight"].astype(np.float64).sum()) for b in m2.tsdf_layer().values())
-    assert abs(w_start - w0) < 1e-6 * w0
-    total = w_start
-    for i in range(3):
-        m2.integrate_depth_blocks(np.full((480, 640), np.nan, np.float32), T, cam, blocks, p)
-        now = sum(float(b["weight"].astype(np.float64).sum()) for b in m2.tsdf_layer().values())
-        assert 0.0 < now < total
-        total = now
-    # every voxel that projects into the image was scaled by 0.8 per frame
-    k = next(iter(m2.tsdf_layer()))
-    assert total < w_start * 0.8 ** 3 * 1.6  # voxels outside the viewport keep their weight
+    m = orc.OracleMap(0.2)
+    p = orc.default_tsdf_params(invalid_depth_decay_factor=0.8, weighting_type=orc.WEIGHT_CONSTANT)
+
+    def totals():
+        L = m.tsdf_layer()
+        return (sum(int((b["weight"] > 0).sum()) for b in L.values()),
+                float(sum(np.float32(b["weight"].sum(dtype=np.float64)) for b in L.values())))
+
+    for bad in (np.nan, np.inf, -np.inf, -1.0, 0.0, -10.0):
+        m.integrate_depth(np.full((480, 640), bad, np.float32), T, cam, p)
+        assert totals() == (0, 0.0)
+    blocks = m.integrate_depth(np.full((480, 640), 2.0, np.float32), T, cam, p)
+    n_valid, w_valid = totals()
+    assert n_valid > 0 and abs(w_valid - n_valid * 1.0) < 1e-3
+    assert len(blocks) == 1  # the cached list of the NaN frame, not the valid frame's own frustum
+    expect = w_valid
+    for bad in (np.inf, -1.0, 0.0):
+        m.integrate_depth(np.full((480, 640), bad, np.float32), T, cam, p)
+        expect *= 0.8
+        assert abs(totals()[1] - expect) < 1e-3
+    # the same sequence without the cache does what the comment says
+    m2 = orc.OracleMap(0.2)
+    m2.cache_last_viewpoint(False)
+    m2.integrate_depth(np.full((480, 640), np.nan, np.float32), T, cam, p)
+    assert len(m2.integrate_depth(np.full((480, 640), 2.0, np.float32), T, cam, p)) > 10  # 24 blocks of 1.6 m, not 1
+    w = sum(float(b["weight"].sum(dtype=np.float64)) for b in m2.tsdf_layer().values())
+    assert len(m2.integrate_depth(np.zeros((480, 640), np.float32), T, cam, p)) == 0
+    assert sum(float(b["weight"].sum(dtype=np.float64)) for b in m2.tsdf_layer().values()) == w
+
+
+def test_viewpoint_cache_keys_and_capacity():
+    """ViewpointCache (view_calculator_impl.h:120-174, transforms.cpp:20-36, camera_impl.h:134-156): a hit needs the pose within
+    1 mm / 0.1 degree and an equal sensor (focal lengths / centre within 0.1, same size); two entries, the oldest is dropped."""
+    cam = _cam()
+    m = orc.OracleMap(0.2)
+    p = orc.default_tsdf_params()
+    Ts = []
+    for dx in (0.0, 0.0005, 0.002):
+        T = np.eye(4, dtype=np.float32)
+        T[0, 3] = dx
+        Ts.append(T)
+    near = np.full((480, 640), 1.0, np.float32)
+    far = np.full((480, 640), 4.0, np.float32)
+    n_near = len(m.integrate_depth(near, Ts[0], cam, p))
+    n_far_fresh = len(orc.OracleMap(0.2).integrate_depth(far, Ts[0], cam, p))
+    assert n_far_fresh > 2 * n_near
+    assert len(m.integrate_depth(far, Ts[1], cam, p)) == n_near       # 0.5 mm away: hit, the near frame's list
+    assert len(m.integrate_depth(far, Ts[2], cam, p)) == n_far_fresh  # 2 mm away: miss (now cached: [Ts[2], Ts[0]])
+    c = np.cos(np.deg2rad(0.05)).astype(np.float32), np.sin(np.deg2rad(0.05)).astype(np.float32)
+    R = np.eye(4, dtype=np.float32)
+    R[0, 0], R[0, 2], R[2, 0], R[2, 2] = c[0], c[1], -c[1], c[0]
+    assert len(m.integrate_depth(far, R, cam, p)) == n_near           # 0.05 degrees: hit on Ts[0]
+    cam2 = _cam(f=300.2)
+    assert len(m.integrate_depth(far, Ts[0], cam2, p)) != n_near      # another sensor: miss ([cam2@Ts[0], Ts[2]]: Ts[0]/cam dropped)
+    assert len(m.integrate_depth(far, Ts[0], cam, p)) == n_far_fresh  # ... so this one is a miss too
 
 
 # --- test_tsdf_integrator.cpp:512-586 (mask semantics) ----------------------------------
@@ -495,21 +537,29 @@ def test_occupancy_masked_pixels_are_unobserved():
     assert checked > 0 and changed > 0
 
 
-@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf, -1.0, 0.0, -10.0])
-def test_occupancy_invalid_depth_integrates_nothing(bad):
-    """InvalidDepthHandling (test_occupancy_integrator.cpp:306-393)."""
+def test_occupancy_invalid_depth_handling_reference_sequence():
+    """OccupancyIntegratorTestFixture.InvalidDepthHandling (test_occupancy_integrator.cpp:306-393), call for call on one
+    integrator (voxel size 0.1 m): six all-invalid frames change nothing; the valid frame integrates "some" voxels -- the cached
+    block list of the NaN frame (see test_invalid_depth_handling_reference_sequence); an invalid frame afterwards changes
+    nothing (occupancy has no invalid-depth decay)."""
     cam = _cam()
     T = np.eye(4, dtype=np.float32)
     m = orc.OracleMap(0.1)
-    m.integrate_occupancy(np.full((480, 640), bad, np.float32), T, cam)
-    assert all(not (np.abs(b) > 1e-6).any() for b in m.occupancy_layer().values())
+
+    def integrated():
+        return sum(int((np.abs(b) > 1e-6).sum()) for b in m.occupancy_layer().values())
+
+    for bad in (np.nan, np.inf, -np.inf, -1.0, 0.0, -10.0):
+        m.integrate_occupancy(np.full((480, 640), bad, np.float32), T, cam)
+        assert integrated() == 0
     m.integrate_occupancy(np.full((480, 640), 2.0, np.float32), T, cam)
+    assert integrated() > 0
     before = {k: b.copy() for k, b in m.occupancy_layer().items()}
-    assert sum(int((np.abs(b) > 1e-6).sum()) for b in before.values()) > 0
-    m.integrate_occupancy(np.full((480, 640), bad, np.float32), T, cam)
+    m.integrate_occupancy(np.full((480, 640), np.inf, np.float32), T, cam)
     after = m.occupancy_layer()
+    assert set(after) == set(before)
     for k, b in before.items():
-        assert np.array_equal(after[k], b)  # no decay for invalid depth
+        assert np.array_equal(after[k], b)
 
 
 def test_occupancy_truncation_raised_to_half_width():
