@@ -53,6 +53,8 @@ struct OccupancyIntegratorParams {
   float unobserved_region_occupancy_probability = 0.5f, occupied_region_half_width_m = 0.1f;
 };
 struct MapperParams {
+  bool do_depth_preprocessing = false;          // mapper_params.h:33-37
+  int depth_preprocessing_num_dilations = 4;    // mapper_params.h:39-42
   EsdfIntegratorParams esdf_integrator_params;
   ProjectiveIntegratorParams projective_integrator_params;
   OccupancyIntegratorParams occupancy_integrator_params;
@@ -349,6 +351,8 @@ class Mapper {
   }
   // Mapper::setMapperParams (mapper/mapper.h:131): the members of MapperParams this path consumes
   void setMapperParams(const MapperParams& p) {
+    do_depth_preprocessing(p.do_depth_preprocessing);
+    depth_preprocessing_num_dilations(p.depth_preprocessing_num_dilations);
     auto ti = tsdf_integrator();
     ti.max_integration_distance_m(p.projective_integrator_params.projective_integrator_max_integration_distance_m);
     ti.truncation_distance_vox(p.projective_integrator_params.projective_integrator_truncation_distance_vox);
@@ -370,6 +374,26 @@ class Mapper {
     }
   }
   std::shared_ptr<CudaStream> cuda_stream() const { return cuda_stream_; }
+  // Mapper::do_depth_preprocessing / depth_preprocessing_num_dilations (mapper.h; mapper.cpp:335-352): dilation of the
+  // invalid regions of every depth image before it is integrated
+  bool do_depth_preprocessing() const {
+    int32_t en = 0, n = 0;
+    b200_detail::check(nvb_mapper_get_depth_preprocessing(m_, &en, &n), "do_depth_preprocessing", nvb_last_error());
+    return en != 0;
+  }
+  void do_depth_preprocessing(bool v) {
+    b200_detail::check(nvb_mapper_set_depth_preprocessing(m_, v ? 1 : 0, depth_preprocessing_num_dilations()),
+                       "do_depth_preprocessing", nvb_last_error());
+  }
+  int depth_preprocessing_num_dilations() const {
+    int32_t en = 0, n = 0;
+    b200_detail::check(nvb_mapper_get_depth_preprocessing(m_, &en, &n), "depth_preprocessing_num_dilations", nvb_last_error());
+    return n;
+  }
+  void depth_preprocessing_num_dilations(int v) {
+    b200_detail::check(nvb_mapper_set_depth_preprocessing(m_, do_depth_preprocessing() ? 1 : 0, v),
+                       "depth_preprocessing_num_dilations", nvb_last_error());
+  }
   // Mapper::markUnobservedTsdfFreeInsideRadius (mapper.h:352-356)
   void markUnobservedTsdfFreeInsideRadius(const Vector3f& center, float radius) {
     const float c[3] = {center[0], center[1], center[2]};

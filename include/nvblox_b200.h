@@ -447,6 +447,19 @@ NVB_API int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n
 NVB_API int32_t nvb_mapper_set_cache_last_viewpoint(NvbMapper* m, int32_t enable);
 NVB_API int32_t nvb_mapper_get_cache_last_viewpoint(const NvbMapper* m);
 
+/* Mapper::do_depth_preprocessing / depth_preprocessing_num_dilations (C/include/nvblox/mapper/mapper_params.h:33-42, defaults
+ * off / 4; Mapper::preprocessDepthImageAsync, C/src/mapper/mapper.cpp:335-352): when enabled, nvb_mapper_integrate_depth*
+ * integrates (and keeps as the last view) a copy of the depth image whose invalid regions were dilated. */
+NVB_API int32_t nvb_mapper_set_depth_preprocessing(NvbMapper* m, int32_t enable, int32_t num_dilations);
+NVB_API int32_t nvb_mapper_get_depth_preprocessing(const NvbMapper* m, int32_t* enable, int32_t* num_dilations);
+/* DepthPreprocessor::dilateInvalidRegionsAsync (C/src/sensors/depth_preprocessing.cpp; C/include/nvblox/sensors/
+ * depth_preprocessing.h): pixels with depth < invalid_depth_threshold (the class default is 1e-2) are invalid; the invalid
+ * mask is dilated num_dilations times with a 3x3 structuring element (replicated border) and every masked pixel is written
+ * as invalid_depth_value (default 0). Device pointers, rows*cols floats, out_dev must not alias depth_dev; enqueued on the
+ * mapper's stream. */
+NVB_API int32_t nvb_depth_dilate_invalid(NvbMapper* m, const float* depth_dev, float* out_dev, int32_t rows, int32_t cols,
+                                         int32_t num_dilations, float invalid_depth_threshold, float invalid_depth_value);
+
 /* Device-resident merge of the ranks' updated-block lists (multi-GPU; the reference has no counterpart:
  * it is single-GPU and keeps `updated_blocks` in a host std::vector, C/include/nvblox/mapper/internal/impl/mapper_impl.h:40-60).
  * A SEGMENT is an int32 device array [count, x0, y0, z0, x1, ...] of capacity cap_entries (1 + 3 * cap_entries ints).

@@ -100,6 +100,11 @@ struct NvbMapper {
   // few KB on the device): a hit skips the raycast and replays the compaction + allocation, which yields the same list in the
   // same order and re-allocates blocks that were deallocated in between, like allocateBlocksWhereRequired does in the reference.
   int cache_last_viewpoint = 1;
+  // Mapper::do_depth_preprocessing / depth_preprocessing_num_dilations (mapper_params.h:33-42; mapper.cpp:335-352)
+  int do_depth_preprocessing = 0;
+  int depth_preprocessing_num_dilations = 4;
+  float* pre_depth = nullptr;
+  size_t pre_depth_cap = 0;
   int vc_n = 0;
   float vc_T[2][16];
   NvbCamera vc_cam[2];
@@ -703,6 +708,11 @@ bool camerasEqual(const NvbCamera& a, const NvbCamera& b) {
   return same;
 }
 
+// DepthPreprocessor's invalid_depth_threshold_ / invalid_depth_value_ (include/nvblox/sensors/depth_preprocessing.h)
+constexpr float kInvalidDepthThreshold = 1e-2f;
+constexpr float kInvalidDepthValue = 0.0f;
+constexpr int kMaxDilations = 64;
+
 // The depth-integration chain for one frame, enqueued on m->stream.
 int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, int mask_mode, int memory, int rows,
                  int cols, const float* T_L_C_cm, const NvbCamera* cam, float block_size, float trunc_m,
@@ -751,6 +761,24 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
     mask_dev = mask ? m->mask_stage[stage_slot] : nullptr;
   }
   m->frame_seq++;
+  if (integrate && m->do_depth_preprocessing) {
+    // Mapper::preprocessDepthImageAsync (src/mapper/mapper.cpp:335-352): the integrators and the saved last view
+    // both see the dilated copy (mapper_impl.h:38-76)
+    // CHECK_GE(rows, 3), CHECK_GE(cols, 3) (src/sensors/depth_preprocessing.cpp:64-65)
+    if (rows < 3 || cols < 3) return fail(NVB_ERR_INVALID_ARGUMENT, "depth preprocessing needs an image of at least 3x3");
+    const size_t pixels = (size_t)rows * cols;
+    if (m->pre_depth_cap < pixels) {
+      NVB_CUDA(syncAll(m));
+      if (m->pre_depth) cudaFree(m->pre_depth);
+      m->pre_depth = nullptr, m->pre_depth_cap = 0;
+      NVB_CUDA(cudaMalloc(&m->pre_depth, pixels * sizeof(float)));
+      m->pre_depth_cap = pixels;
+    }
+    launchDilateInvalid(depth_dev, m->pre_depth, rows, cols, m->depth_preprocessing_num_dilations, kInvalidDepthThreshold,
+                        kInvalidDepthValue, m->stream);
+    m->launches++;
+    depth_dev = m->pre_depth;
+  }
   if (integrate && m->keep_last_view) {
     const size_t pixels = (size_t)rows * cols;
     if (m->last_depth_cap < pixels) {
@@ -1177,6 +1205,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
   cudaFree(m->xslab), cudaFree(m->xrec), cudaFree(m->xcounts);
   cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
+  cudaFree(m->pre_depth);
   cudaFree(m->clr_bits), cudaFree(m->union_bits), cudaFree(m->union_state);
   cudaFree(m->vc_bits[0]), cudaFree(m->vc_bits[1]);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
@@ -2255,6 +2284,33 @@ int32_t nvb_mapper_set_cache_last_viewpoint(NvbMapper* m, int32_t enable) {
   return NVB_OK;
 }
 int32_t nvb_mapper_get_cache_last_viewpoint(const NvbMapper* m) { return m ? m->cache_last_viewpoint : 0; }
+
+int32_t nvb_mapper_set_depth_preprocessing(NvbMapper* m, int32_t enable, int32_t num_dilations) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (num_dilations < 0 || num_dilations > kMaxDilations)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "depth_preprocessing_num_dilations must be in [0, 64]");
+  m->do_depth_preprocessing = enable ? 1 : 0;
+  m->depth_preprocessing_num_dilations = num_dilations;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_depth_preprocessing(const NvbMapper* m, int32_t* enable, int32_t* num_dilations) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (enable) *enable = m->do_depth_preprocessing;
+  if (num_dilations) *num_dilations = m->depth_preprocessing_num_dilations;
+  return NVB_OK;
+}
+int32_t nvb_depth_dilate_invalid(NvbMapper* m, const float* depth_dev, float* out_dev, int32_t rows, int32_t cols,
+                                 int32_t num_dilations, float invalid_depth_threshold, float invalid_depth_value) {
+  if (!m || !depth_dev || !out_dev) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (rows < 3 || cols < 3) return fail(NVB_ERR_INVALID_ARGUMENT, "rows and cols must be >= 3");
+  if (depth_dev == out_dev) return fail(NVB_ERR_INVALID_ARGUMENT, "the output image must not alias the input");
+  if (num_dilations < 0 || num_dilations > kMaxDilations)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "num_dilations must be in [0, 64]");
+  NVB_CUDA(cudaSetDevice(m->device));
+  launchDilateInvalid(depth_dev, out_dev, rows, cols, num_dilations, invalid_depth_threshold, invalid_depth_value, m->stream);
+  NVB_CUDA(cudaGetLastError());
+  return NVB_OK;
+}
 
 int32_t nvb_mapper_join_streams(NvbMapper* m) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");

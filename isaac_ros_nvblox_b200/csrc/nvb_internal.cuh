@@ -523,6 +523,9 @@ void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsign
 void launchScatterBlocks(const DevLayer& layer, const int* xyz_dev, int n, const unsigned char* in, int* error,
                          cudaStream_t stream);
 void launchFillU64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t stream);
+// DepthPreprocessor::dilateInvalidRegionsAsync (src/sensors/depth_preprocessing.cpp); out must not alias in
+void launchDilateInvalid(const float* in, float* out, int rows, int cols, int num_dilations, float threshold,
+                         float invalid_value, cudaStream_t stream);
 void launchRehash(const DevLayer& layer, int count, cudaStream_t stream);
 // EsdfSlicer (integrators/esdf_slicer.h): AABB of the ESDF blocks at block height zb (min x, min y, max x, max y; int[4]
 // preset to INT_MAX / INT_MIN), and the distance image / occupancy grid over an AABB.

@@ -47,6 +47,40 @@ __global__ void scatterBlocksKernel(DevLayer L, const int* xyz, int n, const uns
   for (int k = threadIdx.x; k < nvec; k += blockDim.x) dst[k] = src[k];
 }
 
+// DepthPreprocessor::dilateInvalidRegionsAsync (src/sensors/depth_preprocessing.cpp): mask = depth < threshold, N x 3x3
+// dilations with a replicated border, masked pixels set to the invalid value. N 3x3 dilations with replicated borders
+// are one (2N+1)^2 maximum over clamped coordinates, and a clamped coordinate never leaves the window, so the out-of-
+// image taps can simply be dropped. Separable in shared memory: rows first, then columns; one pass over the image.
+constexpr int kDilateTileW = 32, kDilateTileH = 8;
+__global__ void dilateInvalidKernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int n,
+                                    float threshold, float invalid_value) {
+  extern __shared__ unsigned char s_flags[];
+  const int tw = kDilateTileW + 2 * n, th = kDilateTileH + 2 * n;
+  unsigned char* s_in = s_flags;             // th x tw : depth < threshold
+  unsigned char* s_row = s_flags + tw * th;  // th x kDilateTileW : OR over the row window
+  const int x0 = blockIdx.x * kDilateTileW - n, y0 = blockIdx.y * kDilateTileH - n;
+  const int tid = threadIdx.y * kDilateTileW + threadIdx.x, nthreads = kDilateTileW * kDilateTileH;
+  for (int i = tid; i < tw * th; i += nthreads) {
+    const int x = x0 + i % tw, y = y0 + i / tw;
+    unsigned char f = 0;
+    if (x >= 0 && x < cols && y >= 0 && y < rows) f = in[(size_t)y * cols + x] < threshold ? 1 : 0;  // NaN compares false
+    s_in[i] = f;
+  }
+  __syncthreads();
+  for (int i = tid; i < kDilateTileW * th; i += nthreads) {
+    const int x = i % kDilateTileW, y = i / kDilateTileW;
+    unsigned char f = 0;
+    for (int k = 0; k <= 2 * n; k++) f |= s_in[y * tw + x + k];
+    s_row[i] = f;
+  }
+  __syncthreads();
+  const int x = blockIdx.x * kDilateTileW + threadIdx.x, y = blockIdx.y * kDilateTileH + threadIdx.y;
+  if (x >= cols || y >= rows) return;
+  unsigned char f = 0;
+  for (int k = 0; k <= 2 * n; k++) f |= s_row[(threadIdx.y + k) * kDilateTileW + threadIdx.x];
+  out[(size_t)y * cols + x] = f ? invalid_value : in[(size_t)y * cols + x];
+}
+
 __global__ void fillU64Kernel(unsigned long long* p, unsigned long long v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -185,6 +219,15 @@ void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsign
 void launchScatterBlocks(const DevLayer& layer, const int* xyz_dev, int n, const unsigned char* in, int* error,
                          cudaStream_t stream) {
   if (n > 0) scatterBlocksKernel<<<n, 128, 0, stream>>>(layer, xyz_dev, n, in, error);
+}
+void launchDilateInvalid(const float* in, float* out, int rows, int cols, int num_dilations, float threshold,
+                         float invalid_value, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return;
+  const int tw = kDilateTileW + 2 * num_dilations, th = kDilateTileH + 2 * num_dilations;
+  const size_t smem = (size_t)tw * th + (size_t)kDilateTileW * th;
+  const dim3 grid((cols + kDilateTileW - 1) / kDilateTileW, (rows + kDilateTileH - 1) / kDilateTileH);
+  dilateInvalidKernel<<<grid, dim3(kDilateTileW, kDilateTileH), smem, stream>>>(in, out, rows, cols, num_dilations, threshold,
+                                                                            invalid_value);
 }
 void launchFillU64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t stream) {
   if (n > 0) fillU64Kernel<<<1184, 256, 0, stream>>>(p, v, n);

@@ -602,6 +602,31 @@ class Mapper:
     def cuda_stream(self):
         return self._L.nvb_mapper_stream(self._h)
 
+    def do_depth_preprocessing(self, v=None):
+        """Mapper::do_depth_preprocessing (mapper.h; mapper_params.h:33-37, default off)."""
+        en, n = C.c_int32(0), C.c_int32(0)
+        check(self._L.nvb_mapper_get_depth_preprocessing(self._h, C.byref(en), C.byref(n)))
+        if v is not None:
+            check(self._L.nvb_mapper_set_depth_preprocessing(self._h, 1 if v else 0, n.value))
+            return bool(v)
+        return bool(en.value)
+
+    def depth_preprocessing_num_dilations(self, v=None):
+        """Mapper::depth_preprocessing_num_dilations (mapper_params.h:39-42, default 4)."""
+        en, n = C.c_int32(0), C.c_int32(0)
+        check(self._L.nvb_mapper_get_depth_preprocessing(self._h, C.byref(en), C.byref(n)))
+        if v is not None:
+            check(self._L.nvb_mapper_set_depth_preprocessing(self._h, en.value, int(v)))
+            return int(v)
+        return int(n.value)
+
+    def dilate_invalid_regions_device(self, depth_ptr, out_ptr, rows, cols, num_dilations, invalid_depth_threshold=1e-2,
+                                      invalid_depth_value=0.0):
+        """DepthPreprocessor::dilateInvalidRegionsAsync (sensors/depth_preprocessing.h:33-38) on device images, enqueued on
+        cuda_stream(); the output must not alias the input."""
+        check(self._L.nvb_depth_dilate_invalid(self._h, depth_ptr, out_ptr, rows, cols, int(num_dilations),
+                                               float(invalid_depth_threshold), float(invalid_depth_value)))
+
     def clear(self):
         check(self._L.nvb_mapper_clear(self._h))
 

@@ -716,6 +716,37 @@ static List view_raycast_cached(OrMap* map, const float* depth, int rows, int co
 }
 void or_map_cache_last_viewpoint(OrMap* map, int32_t enable) { map->cache_last_viewpoint = enable; }
 
+/* DepthPreprocessor::dilateInvalidRegionsAsync (src/sensors/depth_preprocessing.cpp:36-58), step by step like the NPP calls
+ * it is made of (src/sensors/npp_image_operations.cpp): getInvalidDepthMaskAsync = nppiCompareC_32f_C1R(NPP_CMP_LESS)
+ * -> 255 where depth < threshold; num_dilations x nppiDilate3x3Border_8u_C1R(NPP_BORDER_REPLICATE) through a double buffer;
+ * maskedSetAsync = nppiSet_32f_C1MR -> value where the mask is non-zero. */
+void or_depth_dilate_invalid(const float* depth, int32_t rows, int32_t cols, int32_t num_dilations, float threshold,
+                             float value, float* out) {
+  const size_t n = (size_t)rows * cols;
+  uint8_t* a = (uint8_t*)malloc(n);
+  uint8_t* b = (uint8_t*)malloc(n);
+  for (size_t i = 0; i < n; i++) a[i] = depth[i] < threshold ? 255 : 0;
+  for (int32_t it = 0; it < num_dilations; it++) {
+    for (int32_t y = 0; y < rows; y++)
+      for (int32_t x = 0; x < cols; x++) {
+        uint8_t m = 0;
+        for (int32_t dy = -1; dy <= 1; dy++)
+          for (int32_t dx = -1; dx <= 1; dx++) {
+            int32_t yy = y + dy, xx = x + dx; /* replicated border */
+            yy = yy < 0 ? 0 : (yy >= rows ? rows - 1 : yy);
+            xx = xx < 0 ? 0 : (xx >= cols ? cols - 1 : xx);
+            const uint8_t v = a[(size_t)yy * cols + xx];
+            if (v > m) m = v;
+          }
+        b[(size_t)y * cols + x] = m;
+      }
+    uint8_t* t = a;
+    a = b, b = t;
+  }
+  for (size_t i = 0; i < n; i++) out[i] = a[i] ? value : depth[i];
+  free(a), free(b);
+}
+
 static int32_t copy_out(const List* l, int32_t* out_xyz, int32_t cap) {
   for (int32_t i = 0; i < l->n && i < cap; i++)
     out_xyz[3 * i] = l->v[i].x, out_xyz[3 * i + 1] = l->v[i].y, out_xyz[3 * i + 2] = l->v[i].z;

@@ -301,6 +301,10 @@ int32_t or_esdf_get_block(const OrMap* map, const int32_t xyz[3], OrEsdfVoxel* o
 /* Test helper: overwrite / create a TSDF block. */
 /* ViewCalculator::cache_last_viewpoint (integrators/view_calculator.h:196; default on) of the map's projective integrator */
 void or_map_cache_last_viewpoint(OrMap* map, int32_t enable);
+/* DepthPreprocessor::dilateInvalidRegionsAsync (src/sensors/depth_preprocessing.cpp:36-58; the class defaults are
+ * threshold 1e-2, value 0): out = depth with the (depth < threshold) regions dilated num_dilations times by 3x3. */
+void or_depth_dilate_invalid(const float* depth, int32_t rows, int32_t cols, int32_t num_dilations, float threshold,
+                             float value, float* out);
 void or_tsdf_set_block(OrMap* map, const int32_t xyz[3], const OrTsdfVoxel* in);
 void or_esdf_set_block(OrMap* map, const int32_t xyz[3], const OrEsdfVoxel* in); /* test hook */
 

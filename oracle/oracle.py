@@ -177,6 +177,8 @@ def lib():
     L.or_esdf_get_block.restype = C.c_int32
     L.or_tsdf_set_block.argtypes = [vp, ip, vp]
     L.or_map_cache_last_viewpoint.argtypes = [vp, C.c_int32]
+    L.or_depth_dilate_invalid.argtypes = [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.POINTER(C.c_float)]
+    L.or_depth_dilate_invalid.restype = None
     L.or_esdf_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.restype = None
@@ -260,6 +262,15 @@ def _ip(a):
 def colmajor(T):
     """4x4 numpy transform -> 16 float32 in Eigen (column-major) order."""
     return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T).reshape(16)
+
+
+def dilate_invalid(depth, num_dilations, threshold=1e-2, value=0.0):
+    """DepthPreprocessor::dilateInvalidRegionsAsync (src/sensors/depth_preprocessing.cpp:36-58)."""
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    out = np.empty_like(depth)
+    lib().or_depth_dilate_invalid(_fp(depth), depth.shape[0], depth.shape[1], int(num_dilations), float(threshold), float(value),
+                                  _fp(out))
+    return out
 
 
 def default_tsdf_params(**kw):
@@ -373,8 +384,18 @@ class OracleMap:
     def clear(self):
         lib().or_map_clear(self._h)
 
-    def integrate_depth(self, depth, T_L_C, cam, params=None, mask=None, mask_mode=0, cap=1 << 20):
+    def depth_preprocessing(self, enable, num_dilations=4):
+        """Mapper::do_depth_preprocessing / depth_preprocessing_num_dilations (mapper_params.h:33-42; defaults off / 4):
+        integrate_depth / integrate_occupancy then see the dilated image, like Mapper::integrateDepth (mapper_impl.h:38-42)."""
+        self._pre = (bool(enable), int(num_dilations))
+
+    def _preprocessed(self, depth):
         depth = np.ascontiguousarray(depth, dtype=np.float32)
+        pre = getattr(self, "_pre", (False, 4))
+        return dilate_invalid(depth, pre[1]) if pre[0] else depth
+
+    def integrate_depth(self, depth, T_L_C, cam, params=None, mask=None, mask_mode=0, cap=1 << 20):
+        depth = self._preprocessed(depth)
         params = params or default_tsdf_params()
         T = colmajor(T_L_C)
         out = np.zeros((cap, 3), dtype=np.int32)
@@ -404,7 +425,7 @@ class OracleMap:
     def integrate_occupancy(self, depth, T_L_C, cam, params=None, occ_params=None, mask=None, mask_mode=0, cap=1 << 20):
         """ProjectiveOccupancyIntegrator::integrateFrame; `params` (TsdfParams) is updated in place when the
         truncation distance is raised to the occupied half width."""
-        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        depth = self._preprocessed(depth)
         params = params or default_tsdf_params()
         occ_params = occ_params or default_occupancy_params()
         T = colmajor(T_L_C)

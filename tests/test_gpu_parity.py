@@ -799,3 +799,86 @@ def test_golden_fixture_f_rows(gpu):
     assert set(got) == set(want.files)
     for k, v in got.items():
         assert int(want[k]) == v, k
+
+
+def test_depth_preprocessing_matches_oracle(gpu):
+    """Mapper::do_depth_preprocessing (mapper.cpp:335-352; mapper_impl.h:38-76) and DepthPreprocessor::dilateInvalidRegionsAsync
+    (sensors/depth_preprocessing.cpp:36-58): (1) the dilation kernel on the reference-held 3DMatch frame and on random images
+    with ragged sizes, every n, bit for bit; (2) a mapper with preprocessing on against the oracle with preprocessing on --
+    lists, TSDF, ESDF -- through the synchronous host API and the asynchronous device API; (3) the last view kept for the
+    decay exclusion is the dilated image; (4) argument checks."""
+    import os
+    import torch
+    nvb, orc = _nvb(), _orc()
+    m = nvb.Mapper(0.05)
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "threedmatch_seq01.npz"))
+    real = (fx["depth_u16"][0].astype(np.float32) / np.float32(1000.0)).astype(np.float32)
+    rng = np.random.default_rng(5)
+    images = [(real, n) for n in (0, 1, 4, 9)]
+    for (r, c) in ((3, 3), (9, 9), (37, 61), (8, 32), (65, 33)):
+        img = rng.uniform(0.5, 5.0, (r, c)).astype(np.float32)
+        img[rng.random((r, c)) < 0.03] = 0.0
+        img[rng.random((r, c)) < 0.01] = np.nan
+        img[rng.random((r, c)) < 0.01] = -np.inf
+        images += [(img, n) for n in (0, 1, 2, 5, 64)]
+    for img, n in images:
+        d = torch.from_numpy(img).cuda()
+        out = torch.empty_like(d)
+        m.dilate_invalid_regions_device(d.data_ptr(), out.data_ptr(), img.shape[0], img.shape[1], n)
+        m.synchronize()
+        assert np.array_equal(out.cpu().numpy(), orc.dilate_invalid(img, n), equal_nan=True), (img.shape, n)
+    d = torch.from_numpy(real).cuda()
+    out = torch.empty_like(d)
+    m.dilate_invalid_regions_device(d.data_ptr(), out.data_ptr(), 480, 640, 2, invalid_depth_threshold=1.5, invalid_depth_value=-3.0)
+    m.synchronize()
+    assert np.array_equal(out.cpu().numpy(), orc.dilate_invalid(real, 2, threshold=1.5, value=-3.0))
+    with pytest.raises(RuntimeError):
+        m.dilate_invalid_regions_device(d.data_ptr(), d.data_ptr(), 480, 640, 1)
+    with pytest.raises(RuntimeError):
+        m.dilate_invalid_regions_device(d.data_ptr(), out.data_ptr(), 2, 640, 1)
+    with pytest.raises(RuntimeError):
+        m.depth_preprocessing_num_dilations(-1)
+    assert m.do_depth_preprocessing() is False and m.depth_preprocessing_num_dilations() == 4
+    m.close()
+
+    K = fx["intrinsics"]
+    cam = nvb.Camera(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), 640, 480)
+    ocam = orc.Camera(float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), 640, 480)
+    frames = [(fx["depth_u16"][i].astype(np.float32) / np.float32(1000.0)).astype(np.float32) for i in range(3)]
+    o = orc.OracleMap(0.05)
+    o.depth_preprocessing(True, 4)
+    lists = []
+    for i, f in enumerate(frames):
+        lists.append(o.integrate_depth(f, fx["poses"][i], ocam))
+        o.integrate_esdf(lists[-1])
+    plain = orc.OracleMap(0.05)
+    plain.integrate_depth(frames[0], fx["poses"][0], ocam)
+    for api in ("host", "device"):
+        m = nvb.Mapper(0.05)
+        m.do_depth_preprocessing(True)
+        assert m.do_depth_preprocessing() is True and m.depth_preprocessing_num_dilations() == 4
+        dev = torch.from_numpy(np.stack(frames)).cuda()
+        for i, f in enumerate(frames):
+            if api == "host":
+                assert np.array_equal(m.integrate_depth(f, fx["poses"][i], cam), lists[i])
+                m.update_esdf()
+            else:
+                m.integrate_depth_device(dev[i].data_ptr(), 480, 640, fx["poses"][i], cam)
+                m.update_esdf(sync=False)
+        m.synchronize()
+        assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+        assert_esdf_equal(m.esdf_layer().as_dict(), o.esdf_layer())
+        assert np.array_equal(dev[2].cpu().numpy(), frames[2])  # the caller's image is not modified
+        m.close()
+    assert layer_checksum(o.tsdf_layer(), ("distance", "weight")) != layer_checksum(plain.tsdf_layer(), ("distance", "weight"))
+    # the view saved for decayTsdfExcludeLastView is the preprocessed one (mapper_impl.h:60-76)
+    m, o2 = nvb.Mapper(0.05, keep_last_view=True), orc.OracleMap(0.05)
+    m.do_depth_preprocessing(True)
+    m.depth_preprocessing_num_dilations(6)
+    o2.depth_preprocessing(True, 6)
+    m.integrate_depth(frames[0], fx["poses"][0], cam)
+    o2.integrate_depth(frames[0], fx["poses"][0], ocam)
+    m.decay_exclude_last_view()
+    o2.decay_tsdf(depth=orc.dilate_invalid(frames[0], 6), T_L_C=fx["poses"][0], cam=ocam)
+    assert_tsdf_equal(m.tsdf_layer().as_dict(), o2.tsdf_layer())
+    m.close()
