@@ -99,6 +99,7 @@ struct NvbMapper {
   // up to two (pose, sensor) -> block-list entries, newest first. A list is kept as the view bitset it was compacted from (a
   // few KB on the device): a hit skips the raycast and replays the compaction + allocation, which yields the same list in the
   // same order and re-allocates blocks that were deallocated in between, like allocateBlocksWhereRequired does in the reference.
+  BlockTensorMap tsdf_tmap;  // TMA descriptor of the TSDF slab (nvb_tsdf.cu)
   int cache_last_viewpoint = 1;
   // Mapper::do_depth_preprocessing / depth_preprocessing_num_dilations (mapper_params.h:33-42; mapper.cpp:335-352)
   int do_depth_preprocessing = 0;
@@ -876,8 +877,13 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
       launchOccupancyIntegrate(m->frame_blocks, m->frame_count, m->tsdf.blocks, depth_dev, mask_dev, mask_mode, rows,
                                cols, T_C_L, *cam, p, o, m->num_sms, m->bits, grid.num_words, m->stream);
     } else {
+      // the slab's tensor descriptor follows reallocations (growLayer) by being re-encoded when base or capacity changed
+      if (tsdfUseTma() && (m->tsdf_tmap.base != m->tsdf.blocks || m->tsdf_tmap.capacity != m->tsdf.capacity)) {
+        if (encodeBlockTensorMap(&m->tsdf_tmap, m->tsdf.blocks, m->tsdf.capacity, kTsdfBlockBytes))
+          return fail(NVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the TSDF slab");
+      }
       launchTsdfIntegrate(m->frame_blocks, m->frame_count, m->tsdf.blocks, depth_dev, mask_dev, mask_mode, rows, cols,
-                          T_C_L, *cam, p, m->num_sms, m->bits, grid.num_words, m->stream);
+                          T_C_L, *cam, p, m->num_sms, m->bits, grid.num_words, tsdfUseTma() ? &m->tsdf_tmap : nullptr, m->stream);
     }
     endStage(m);
     m->launches++;

@@ -309,10 +309,23 @@ void launchUnpackList(const int4* in, const int* count, int* out, int cap, cudaS
 void launchCompactAllocate(const CompactArgs& args, cudaStream_t stream);
 
 // nvb_tsdf.cu
+// A CUtensorMap (128 bytes, 64-byte aligned) that describes a layer slab to the TMA unit, and what it was encoded for.
+struct alignas(64) TensorMapBytes {
+  unsigned long long opaque[16];
+};
+struct BlockTensorMap {
+  TensorMapBytes desc;
+  const void* base = nullptr;
+  int capacity = 0;
+};
+bool tsdfUseTma();
+// 0 on success; the slab must be viewed as [capacity * block_bytes / 1024][256] 32-bit words
+int encodeBlockTensorMap(BlockTensorMap* out, void* base, int capacity, int block_bytes);
+// tmap == nullptr: the register-prefetch kernel
 void launchTsdfIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* tsdf_blocks,
                          const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,
                          const Rigid& T_C_L, const NvbCamera& cam, const TsdfKernelParams& p, int num_sms,
-                         unsigned int* bits_to_clear, int num_words, cudaStream_t stream);
+                         unsigned int* bits_to_clear, int num_words, const BlockTensorMap* tmap, cudaStream_t stream);
 
 void launchOccupancyIntegrate(const int4* frame_blocks, const int* frame_count, unsigned char* occ_blocks,
                               const float* depth, const unsigned char* mask, int mask_mode, int rows, int cols,

@@ -882,3 +882,47 @@ def test_depth_preprocessing_matches_oracle(gpu):
     o2.decay_tsdf(depth=orc.dilate_invalid(frames[0], 6), T_L_C=fx["poses"][0], cam=ocam)
     assert_tsdf_equal(m.tsdf_layer().as_dict(), o2.tsdf_layer())
     m.close()
+
+
+@pytest.mark.parametrize("variant", ["tma", "tma_1cta_per_sm", "registers"])
+def test_tsdf_kernel_variants_equal_oracle(gpu, variant):
+    """The TSDF update kernel that stages VoxelBlocks with cp.async.bulk.tensor.2d (NVB_TSDF_TMA=1; with 1 CTA per SM every
+    CTA walks ~20+ blocks so the 6-stage tile ring wraps and refills several times), and the register-prefetch kernel
+    (the default): TSDF bits equal to the oracle's over frames with masks, invalid depth, a lens distortion, and a slab that
+    grows (the tensor descriptor is re-encoded). Subprocess: the switches are read once per process."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        from helpers import assert_esdf_equal, assert_tsdf_equal, cameras
+        from isaac_ros_nvblox_b200 import synthetic as syn
+        import isaac_ros_nvblox_b200 as nvb
+        from oracle import oracle as orc
+        cs, cam, ocam = cameras(320, 240)
+        frames = syn.make_sequence(syn.sphere_in_box(), cs, syn.circle_trajectory(40)[:6])
+        rng = np.random.default_rng(3)
+        m, o = nvb.Mapper(0.05, tsdf_capacity_blocks=1024, esdf_capacity_blocks=1024), orc.OracleMap(0.05)
+        for i, (d, T) in enumerate(frames):
+            d = d.copy()
+            d[rng.random(d.shape) < 0.05] = 0.0
+            mask = (rng.random(d.shape) < 0.2).astype(np.uint8) if i %% 2 else None
+            b = m.integrate_depth(d, T, cam, mask=mask)
+            assert np.array_equal(b, o.integrate_depth(d, T, ocam, mask=mask))
+        assert m.tsdf_layer().num_blocks() > 1024
+        assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+        m.close()
+        # a distorted camera (separate instantiation of the kernel) at 2 cm (many blocks per CTA)
+        _, dc, odc = cameras(320, 240, radial=(0.05, -0.02, 0.001, 0.0, 0.0, 0.0), tangential=(0.001, -0.001))
+        m, o = nvb.Mapper(0.02), orc.OracleMap(0.02)
+        for d, T in frames[:2]:
+            assert np.array_equal(m.integrate_depth(d, T, dc), o.integrate_depth(d, T, odc))
+        assert_tsdf_equal(m.tsdf_layer().as_dict(), o.tsdf_layer())
+        m.close()
+        print("ok")
+    """) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, NVB_TSDF_TMA="0" if variant == "registers" else "1")
+    if variant == "tma_1cta_per_sm":
+        env["NVB_TSDF_TMA_CTAS_PER_SM"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
