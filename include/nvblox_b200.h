@@ -60,7 +60,7 @@ typedef enum {
 typedef enum { NVB_MEM_HOST = 0, NVB_MEM_DEVICE = 1 } NvbMemory;
 
 /* Layers of the map (C/include/nvblox/map/common_names.h TsdfLayer / EsdfLayer). */
-typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1, NVB_LAYER_OCCUPANCY = 2, NVB_LAYER_FREESPACE = 3, NVB_LAYER_COLOR = 4 } NvbLayer;
+typedef enum { NVB_LAYER_TSDF = 0, NVB_LAYER_ESDF = 1, NVB_LAYER_OCCUPANCY = 2, NVB_LAYER_FREESPACE = 3, NVB_LAYER_COLOR = 4, NVB_LAYER_MESH = 5 } NvbLayer;
 
 /* ProjectiveLayerType of a Mapper (C/include/nvblox/mapper/mapper.h:40-48): which layer integrateDepth feeds. */
 typedef enum {
@@ -446,6 +446,38 @@ NVB_API int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n
  * pose (1 mm, 0.1 degree) and sensor match -- whatever the depth image holds (ViewpointCache, view_calculator.h:211-244). */
 NVB_API int32_t nvb_mapper_set_cache_last_viewpoint(NvbMapper* m, int32_t enable);
 NVB_API int32_t nvb_mapper_get_cache_last_viewpoint(const NvbMapper* m);
+
+/* ---- Mesh (C/include/nvblox/mesh/mesh_integrator.h:39-162, C/src/mesh/mesh_integrator.cu,
+ * C/src/mesh/mesh_integrator_appearance.cu). The mesh layer holds, per VoxelBlock that has triangles, vertices (3 floats),
+ * flat per-vertex normals (3 floats), triangle indices into the block's vertices (triplets) and -- after a colour update --
+ * one RGBA colour per vertex (MeshBlock, C/include/nvblox/mesh/mesh_block.h:32-83). A block's triangles come out in
+ * x-major voxel order (the reference's order within a block is an atomicAdd race, marching_cubes_impl.cuh:11-29). */
+typedef struct {
+  float min_weight;          /* mesh_integrator_min_weight, 1e-4 (C/include/nvblox/mesh/mesh_integrator_params.h:22-24) */
+  int32_t weld_vertices;     /* mesh_integrator_weld_vertices, true (mesh_integrator_params.h:25-27) */
+  float cutoff_distance_vox; /* MeshIntegrator::cutoff_distance_vox_, 5 (mesh_integrator.h:129) */
+} NvbMeshParams;
+NVB_API void nvb_default_mesh_params(NvbMeshParams* p);
+NVB_API int32_t nvb_mapper_set_mesh_params(NvbMapper* m, const NvbMeshParams* p);
+NVB_API int32_t nvb_mapper_get_mesh_params(const NvbMapper* m, NvbMeshParams* p);
+/* Mapper::updateColorMesh(UpdateFullLayer) (C/src/mapper/mapper.cpp:371-406): re-meshes the blocks touched since the last
+ * call (or every block) and colours them from the colour layer; a no-op for an occupancy mapper. */
+NVB_API int32_t nvb_mapper_update_mesh(NvbMapper* m, int32_t update_full_layer);
+/* MeshIntegrator::integrateBlocksGPU (mesh_integrator.cu:66-108) on an explicit list of block indices (host, triples; the
+ * ones missing from the TSDF layer are skipped), optionally followed by MeshIntegrator::updateAppearance on the same list. */
+NVB_API int32_t nvb_mesh_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks, int32_t update_color);
+/* MeshIntegrator::updateAppearance(colour layer, block list, mesh layer) (mesh_integrator_appearance.cu:71-96,281-380). */
+NVB_API int32_t nvb_mesh_update_color(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks);
+/* Sizes of the listed mesh blocks: sizes_out[3 i ..] = {vertices, triangle indices, colours}, or -1s if block i has no mesh
+ * block. The block indices of the layer: nvb_layer_block_indices(m, NVB_LAYER_MESH, ...). */
+NVB_API int32_t nvb_mesh_block_sizes(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks, int32_t* sizes_out);
+/* The listed mesh blocks packed back to back in list order into host buffers (any of them may be NULL): 3 floats per
+ * vertex / normal, one int32 per triangle index (relative to the block's first vertex), 4 bytes RGBA per colour.
+ * caps = capacities of the buffers in {vertices, triangle indices, colours}. */
+NVB_API int32_t nvb_mesh_get_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks, float* vertices_out,
+                                    float* normals_out, int32_t* triangles_out, uint8_t* colors_out, const int64_t caps[3]);
+/* out = {arena capacity, fill level, vertices emitted by the last update, reserved} in vertices. */
+NVB_API int32_t nvb_mesh_arena_stats(NvbMapper* m, int64_t out[4]);
 
 /* Mapper::do_depth_preprocessing / depth_preprocessing_num_dilations (C/include/nvblox/mapper/mapper_params.h:33-42, defaults
  * off / 4; Mapper::preprocessDepthImageAsync, C/src/mapper/mapper.cpp:335-352): when enabled, nvb_mapper_integrate_depth*

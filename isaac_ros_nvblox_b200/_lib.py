@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnvblox_b200.so")
 
 NVB_OK = 0
 NVB_MEM_HOST, NVB_MEM_DEVICE = 0, 1
-NVB_LAYER_TSDF, NVB_LAYER_ESDF, NVB_LAYER_OCCUPANCY, NVB_LAYER_FREESPACE, NVB_LAYER_COLOR = 0, 1, 2, 3, 4
+NVB_LAYER_TSDF, NVB_LAYER_ESDF, NVB_LAYER_OCCUPANCY, NVB_LAYER_FREESPACE, NVB_LAYER_COLOR, NVB_LAYER_MESH = 0, 1, 2, 3, 4, 5
 NVB_PROJECTIVE_TSDF, NVB_PROJECTIVE_OCCUPANCY, NVB_PROJECTIVE_TSDF_WITH_FREESPACE = 0, 1, 2
 
 # Every symbol include/nvblox_b200.h declares (checked by tests/test_cabi_symbols.py).
@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "nvb_mapper_stream", "nvb_mapper_join_streams", "nvb_blocks_union",
     "nvb_layer_num_blocks", "nvb_layer_block_indices", "nvb_layer_get_blocks",
     "nvb_layer_set_blocks", "nvb_layer_block_device_ptr", "nvb_layer_block_bytes",
-    "nvb_mapper_last_esdf_stats", "nvb_mapper_set_cache_last_viewpoint", "nvb_mapper_get_cache_last_viewpoint", "nvb_mapper_set_depth_preprocessing", "nvb_mapper_get_depth_preprocessing", "nvb_depth_dilate_invalid", "nvb_mapper_append_frame_blocks", "nvb_blocks_union_segments", "nvb_blocks_union_status", "nvb_mapper_esdf_time_split", "nvb_mapper_esdf_clear_blocks_read", "nvb_mapper_debug_phase_max", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
+    "nvb_mapper_last_esdf_stats", "nvb_mapper_set_cache_last_viewpoint", "nvb_mapper_get_cache_last_viewpoint", "nvb_mapper_set_depth_preprocessing", "nvb_mapper_get_depth_preprocessing", "nvb_depth_dilate_invalid", "nvb_default_mesh_params", "nvb_mapper_set_mesh_params", "nvb_mapper_get_mesh_params", "nvb_mapper_update_mesh", "nvb_mesh_integrate_blocks", "nvb_mesh_update_color", "nvb_mesh_block_sizes", "nvb_mesh_get_blocks", "nvb_mesh_arena_stats", "nvb_mapper_append_frame_blocks", "nvb_blocks_union_segments", "nvb_blocks_union_status", "nvb_mapper_esdf_time_split", "nvb_mapper_esdf_clear_blocks_read", "nvb_mapper_debug_phase_max", "nvb_mapper_enable_profiling", "nvb_mapper_stage_times",
     "nvb_mapper_kernel_launches",
 ]
 
@@ -77,6 +77,10 @@ class NvbOccupancyParams(C.Structure):
                 ("occupied_region_occupancy_probability", C.c_float),
                 ("unobserved_region_occupancy_probability", C.c_float),
                 ("occupied_region_half_width_m", C.c_float)]
+
+
+class NvbMeshParams(C.Structure):
+    _fields_ = [("min_weight", C.c_float), ("weld_vertices", C.c_int32), ("cutoff_distance_vox", C.c_float)]
 
 
 class NvbEsdfSliceParams(C.Structure):
@@ -226,6 +230,16 @@ def load():
     L.nvb_mapper_set_depth_preprocessing.argtypes = [vp, C.c_int32, C.c_int32]
     L.nvb_mapper_get_depth_preprocessing.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.nvb_depth_dilate_invalid.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float]
+    L.nvb_default_mesh_params.argtypes = [C.POINTER(NvbMeshParams)]
+    L.nvb_default_mesh_params.restype = None
+    L.nvb_mapper_set_mesh_params.argtypes = [vp, C.POINTER(NvbMeshParams)]
+    L.nvb_mapper_get_mesh_params.argtypes = [vp, C.POINTER(NvbMeshParams)]
+    L.nvb_mapper_update_mesh.argtypes = [vp, C.c_int32]
+    L.nvb_mesh_integrate_blocks.argtypes = [vp, C.POINTER(C.c_int32), C.c_int32, C.c_int32]
+    L.nvb_mesh_update_color.argtypes = [vp, C.POINTER(C.c_int32), C.c_int32]
+    L.nvb_mesh_block_sizes.argtypes = [vp, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
+    L.nvb_mesh_get_blocks.argtypes = [vp, C.POINTER(C.c_int32), C.c_int32, vp, vp, vp, vp, C.POINTER(C.c_int64)]
+    L.nvb_mesh_arena_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     L.nvb_mapper_append_frame_blocks.argtypes = [vp, vp, C.c_int32]
     L.nvb_blocks_union_segments.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp]
     L.nvb_blocks_union_status.argtypes = [vp, C.POINTER(C.c_int32)]

@@ -100,6 +100,24 @@ struct NvbMapper {
   // few KB on the device): a hit skips the raycast and replays the compaction + allocation, which yields the same list in the
   // same order and re-allocates blocks that were deallocated in between, like allocateBlocksWhereRequired does in the reference.
   BlockTensorMap tsdf_tmap;  // TMA descriptor of the TSDF slab (nvb_tsdf.cu)
+
+  // Mesh layer (nvb_mesh.cu): header slab + one arena for vertices / normals / triangle indices / colours
+  DevLayer mesh{};
+  float* mesh_v = nullptr;
+  float* mesh_n = nullptr;
+  int* mesh_t = nullptr;
+  unsigned char* mesh_c = nullptr;
+  long long mesh_arena_cap = 0;  // entries
+  int* mesh_state = nullptr;     // kArena* ints
+  int* mesh_counts = nullptr;
+  int* mesh_offsets = nullptr;
+  int mesh_list_cap = 0;
+  int* mesh_xyz_dev = nullptr;
+  int mesh_xyz_cap = 0;
+  int* dirty_mesh = nullptr;  // the tracker's third consumer (BlocksToUpdateType::kColorMesh)
+  int* todo_mesh_slots = nullptr;
+  bool mesh_tracker_initialized = false;
+  NvbMeshParams mp{1e-4f, 1, 5.0f};
   int cache_last_viewpoint = 1;
   // Mapper::do_depth_preprocessing / depth_preprocessing_num_dilations (mapper_params.h:33-42; mapper.cpp:335-352)
   int do_depth_preprocessing = 0;
@@ -381,12 +399,16 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
     if ((rc = reallocCopy(&m->dirty_fs, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
     if ((rc = reallocCopy(&m->todo_fs_slots, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
   }
+  if (m->dirty_mesh) {
+    if ((rc = reallocCopy(&m->dirty_mesh, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+    if ((rc = reallocCopy(&m->todo_mesh_slots, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
+  }
   return NVB_OK;
 }
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kColorWorkCount = 31, kXTail = 32, kNumInts = 40 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kColorWorkCount = 31, kXTail = 32, kTodoMeshCount = 36, kNumInts = 40 };
 
 float logOddsFromProbability(float p);
 
@@ -844,6 +866,9 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
   ca.dirty2 = (integrate && m->dirty_fs && m->fs_tracker_initialized) ? m->dirty_fs : nullptr;
   ca.todo2_slots = m->todo_fs_slots;
   ca.todo2_count = m->esdf_ints + kTodoFsCount;
+  ca.dirty3 = (integrate && m->dirty_mesh && m->mesh_tracker_initialized) ? m->dirty_mesh : nullptr;
+  ca.todo3_slots = m->todo_mesh_slots;
+  ca.todo3_count = m->esdf_ints + kTodoMeshCount;
   launchCompactAllocate(ca, m->stream);
   if (compactUsesTickets(grid)) m->ticket_base += (unsigned int)compactNumTiles(grid);
   endStage(m);
@@ -1212,6 +1237,9 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->xslab), cudaFree(m->xrec), cudaFree(m->xcounts);
   cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
   cudaFree(m->pre_depth);
+  if (m->mesh.blocks) freeLayer(&m->mesh);
+  cudaFree(m->mesh_v), cudaFree(m->mesh_n), cudaFree(m->mesh_t), cudaFree(m->mesh_c), cudaFree(m->mesh_state);
+  cudaFree(m->mesh_counts), cudaFree(m->mesh_offsets), cudaFree(m->mesh_xyz_dev), cudaFree(m->dirty_mesh), cudaFree(m->todo_mesh_slots);
   cudaFree(m->clr_bits), cudaFree(m->union_bits), cudaFree(m->union_state);
   cudaFree(m->vc_bits[0]), cudaFree(m->vc_bits[1]);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
@@ -1252,6 +1280,16 @@ int32_t nvb_mapper_clear(NvbMapper* m) {
   NVB_CUDA(cudaMemsetAsync(m->error_dev, 0, sizeof(int), m->stream));
   m->tracker_initialized = false;
   m->fs_tracker_initialized = false;
+  m->mesh_tracker_initialized = false;
+  if (m->mesh.blocks) {
+    NVB_CUDA(cudaMemsetAsync(m->mesh.blocks, 0, (size_t)m->mesh.capacity * m->mesh.block_bytes, m->stream));
+    NVB_CUDA(cudaMemsetAsync(m->mesh.count, 0, sizeof(int), m->stream));
+    NVB_CUDA(cudaMemsetAsync(m->mesh.free_count, 0, sizeof(int), m->stream));
+    launchFillU64(m->mesh.hash.keys, kEmptyKey, (size_t)m->mesh.hash.mask + 1, m->stream);
+    NVB_CUDA(cudaMemsetAsync(m->mesh_state, 0, kArenaInts * sizeof(int), m->stream));
+    NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoMeshCount, 0, sizeof(int), m->stream));
+    NVB_CUDA(cudaMemsetAsync(m->dirty_mesh, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
+  }
   m->esdf_mode = 0;
   m->fs_last_update_ms = 0;
   NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoFsCount, 0, sizeof(int), m->stream));
@@ -1484,6 +1522,12 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
       launchRemoveBlocks(m->color, m->dead, a.dead_count, n_dead, m->stream);
       touched.push_back(&m->color);
     }
+    // ColorMeshLayer::clearBlocksAsync (Mapper::clearBlocksInLayers, src/mapper/mapper.cpp:552-557): the arena segments
+    // of the removed headers are no longer referenced and are dropped by the next arena repack
+    if (m->mesh.blocks) {
+      launchRemoveBlocks(m->mesh, m->dead, a.dead_count, n_dead, m->stream);
+      touched.push_back(&m->mesh);
+    }
     for (DevLayer* L : touched) {
       int hw = 0;
       NVB_CUDA(cudaMemcpyAsync(&hw, L->count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -1494,6 +1538,7 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
     }
     m->launches += 6;
     if (m->dirty_fs) NVB_CUDA(cudaMemsetAsync(m->dirty_fs, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
+    if (m->dirty_mesh) NVB_CUDA(cudaMemsetAsync(m->dirty_mesh, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
     if (out_count) *out_count = n_dead;
     if (removed_xyz_host && cap > 0) {
       const int k = std::min(n_dead, (int)cap);
@@ -1507,8 +1552,10 @@ int32_t nvb_mapper_decay(NvbMapper* m, const NvbDecayExclusion* exclusion, const
   // BlocksToUpdateTracker::addAllBlocksToUpdate (mapper_impl.h:208-211): the next ESDF update covers every block
   m->tracker_initialized = false;
   m->fs_tracker_initialized = false;
+  m->mesh_tracker_initialized = false;
   NVB_CUDA(cudaMemsetAsync(m->todo_count, 0, sizeof(int), m->stream));
   NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoFsCount, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoMeshCount, 0, sizeof(int), m->stream));
   NVB_CUDA(syncAll(m));
   return checkDeviceError(m);
 }
@@ -1728,6 +1775,8 @@ int32_t nvb_mapper_mark_unobserved_free_inside_radius(NvbMapper* m, const float 
   if (m->tracker_initialized) a.dirty = m->dirty, a.todo_slots = m->todo_slots, a.todo_count = m->todo_count;
   if (m->dirty_fs && m->fs_tracker_initialized)
     a.dirty2 = m->dirty_fs, a.todo2_slots = m->todo_fs_slots, a.todo2_count = m->esdf_ints + kTodoFsCount;
+  if (m->dirty_mesh && m->mesh_tracker_initialized)
+    a.dirty3 = m->dirty_mesh, a.todo3_slots = m->todo_mesh_slots, a.todo3_count = m->esdf_ints + kTodoMeshCount;
   int4* out_dev = nullptr;
   NVB_CUDA(cudaMalloc(&out_dev, ((size_t)cells + 1) * sizeof(int4)));
   a.out = out_dev + 1;
@@ -2339,6 +2388,7 @@ static DevLayer* layerOf(NvbMapper* m, int layer) {
   }
   if (layer == NVB_LAYER_OCCUPANCY) return m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY ? &m->tsdf : nullptr;
   if (layer == NVB_LAYER_ESDF) return &m->esdf;
+  if (layer == NVB_LAYER_MESH) return m->mesh.blocks ? &m->mesh : nullptr;  // the headers; the geometry: nvb_mesh_get_blocks
   return nullptr;
 }
 
@@ -2548,5 +2598,297 @@ int32_t nvb_mapper_stage_times(NvbMapper* m, double* out_ms, int64_t* out_calls,
 }
 
 int64_t nvb_mapper_kernel_launches(const NvbMapper* m) { return m ? m->launches : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Mesh (nvb_mesh.cu)
+// ---------------------------------------------------------------------------
+namespace {
+
+int ensureMeshLayer(NvbMapper* m) {
+  int rc;
+  if (!m->mesh.blocks) {
+    if ((rc = allocLayer(&m->mesh, m->tsdf.capacity, kMeshHeaderBytes, m->stream))) return rc;
+    NVB_CUDA(cudaMalloc(&m->mesh_state, kArenaInts * sizeof(int)));
+    NVB_CUDA(cudaMemsetAsync(m->mesh_state, 0, kArenaInts * sizeof(int), m->stream));
+    NVB_CUDA(cudaMalloc(&m->dirty_mesh, (size_t)m->tsdf.capacity * sizeof(int)));
+    NVB_CUDA(cudaMemsetAsync(m->dirty_mesh, 0, (size_t)m->tsdf.capacity * sizeof(int), m->stream));
+    NVB_CUDA(cudaMalloc(&m->todo_mesh_slots, (size_t)m->tsdf.capacity * sizeof(int)));
+  } else if (m->mesh.capacity < m->tsdf.capacity) {
+    if ((rc = growLayer(m, &m->mesh, m->tsdf.capacity))) return rc;
+  }
+  return NVB_OK;
+}
+
+MeshCtx makeMeshCtx(NvbMapper* m) {
+  MeshCtx c{};
+  c.tsdf = m->tsdf, c.color = m->color, c.mesh = m->mesh;
+  c.vertices = m->mesh_v, c.normals = m->mesh_n, c.triangles = m->mesh_t, c.colors_raw = m->mesh_c;
+  c.colors = reinterpret_cast<uchar4*>(m->mesh_c);
+  c.arena_state = m->mesh_state;
+  c.counts = m->mesh_counts, c.offsets = m->mesh_offsets;
+  c.block_size = m->block_size, c.voxel_size = m->voxel_size;
+  c.min_weight = m->mp.min_weight, c.cutoff_distance_m = m->mp.cutoff_distance_vox * m->voxel_size;
+  c.weld = m->mp.weld_vertices ? 1 : 0;
+  c.error = m->error_dev;
+  return c;
+}
+
+// Moves the live segments into a fresh arena of at least `need` free entries behind them (growth and garbage collection
+// are the same operation: a segment is live while a header points at it).
+int repackMeshArena(NvbMapper* m, long long need) {
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  int nslots = 0;
+  NVB_CUDA(cudaMemcpy(&nslots, m->mesh.count, sizeof(int), cudaMemcpyDeviceToHost));
+  nslots = std::min(nslots, m->mesh.capacity);
+  int* sizes = nullptr;
+  int* new_off = nullptr;
+  NVB_CUDA(cudaMalloc(&sizes, ((size_t)nslots + 1) * sizeof(int)));
+  NVB_CUDA(cudaMalloc(&new_off, ((size_t)nslots + 1) * sizeof(int)));
+  MeshCtx c = makeMeshCtx(m);
+  launchMeshCompactSizes(c, nslots, sizes, m->stream);
+  std::vector<int> h((size_t)nslots + 1, 0), o((size_t)nslots + 1, 0);
+  NVB_CUDA(cudaMemcpyAsync(h.data(), sizes, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  long long live = 0;
+  for (int i = 0; i < nslots; i++) o[i] = (int)live, live += h[i];
+  long long cap = std::max<long long>(m->mesh_arena_cap, 1 << 18);
+  while (cap < live + need) cap *= 2;
+  if (cap > 0x7fffffffll) {
+    cudaFree(sizes), cudaFree(new_off);
+    return fail(NVB_ERR_CAPACITY, "mesh arena beyond 2^31 vertices");
+  }
+  float *v2 = nullptr, *n2 = nullptr;
+  int* t2 = nullptr;
+  unsigned char* c2 = nullptr;
+  NVB_CUDA(cudaMalloc(&v2, (size_t)cap * 12));
+  NVB_CUDA(cudaMalloc(&n2, (size_t)cap * 12));
+  NVB_CUDA(cudaMalloc(&t2, (size_t)cap * 4));
+  NVB_CUDA(cudaMalloc(&c2, (size_t)cap * 4));
+  NVB_CUDA(cudaMemcpyAsync(new_off, o.data(), (size_t)nslots * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  if (m->mesh_v) launchMeshCompactMove(c, nslots, new_off, v2, n2, t2, c2, m->num_sms, m->stream);
+  const int state[kArenaInts] = {(int)live, 0, (int)live, 0};
+  NVB_CUDA(cudaMemcpyAsync(m->mesh_state, state, sizeof(state), cudaMemcpyHostToDevice, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(m->mesh_v), cudaFree(m->mesh_n), cudaFree(m->mesh_t), cudaFree(m->mesh_c), cudaFree(sizes), cudaFree(new_off);
+  m->mesh_v = v2, m->mesh_n = n2, m->mesh_t = t2, m->mesh_c = c2, m->mesh_arena_cap = cap;
+  m->launches += 2;
+  return NVB_OK;
+}
+
+// One mesh update over a device list (explicit indices, or TSDF slots from the tracker).
+int meshUpdateImpl(NvbMapper* m, const int* xyz_dev, const int* slots_dev, const int* count_dev, int upper, bool color) {
+  int rc;
+  if (upper <= 0) return NVB_OK;
+  if (m->mesh_list_cap < upper) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(m->mesh_counts), cudaFree(m->mesh_offsets);
+    m->mesh_counts = m->mesh_offsets = nullptr;
+    const int cap = std::max(upper, 2 * m->mesh_list_cap);
+    NVB_CUDA(cudaMalloc(&m->mesh_counts, (size_t)cap * sizeof(int)));
+    NVB_CUDA(cudaMalloc(&m->mesh_offsets, (size_t)cap * sizeof(int)));
+    m->mesh_list_cap = cap;
+  }
+  MeshCtx c = makeMeshCtx(m);
+  c.in_xyz = xyz_dev, c.in_slots = slots_dev, c.in_count_dev = count_dev, c.in_count_host = upper;
+  c.tracker_dirty = slots_dev ? m->dirty_mesh : nullptr;
+  launchMeshCount(c, upper, m->num_sms, m->stream);
+  m->launches += 2;
+  // the one number the host needs: does the update fit behind the arena's fill level?
+  int state[kArenaInts];
+  NVB_CUDA(cudaMemcpyAsync(state, m->mesh_state, sizeof(state), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  if ((long long)state[kArenaLastBase] + state[kArenaLastTotal] > m->mesh_arena_cap) {
+    if ((rc = repackMeshArena(m, state[kArenaLastTotal]))) return rc;
+    c = makeMeshCtx(m);
+    c.in_xyz = xyz_dev, c.in_slots = slots_dev, c.in_count_dev = count_dev, c.in_count_host = upper;
+    launchMeshScan(c, m->stream);  // the offsets move with the fill level
+    m->launches++;
+  }
+  launchMeshEmit(c, upper, m->num_sms, m->stream);
+  m->launches += c.weld ? 2 : 1;
+  if (color) {
+    launchMeshColor(c, upper, m->num_sms, m->stream);
+    m->launches++;
+  }
+  return NVB_OK;
+}
+
+int uploadMeshList(NvbMapper* m, const int32_t* xyz_host, int n, int* out_unique) {
+  for (int i = 0; i < n; i++)
+    if (!indexInRange(xyz_host[3 * i], xyz_host[3 * i + 1], xyz_host[3 * i + 2]))
+      return fail(NVB_ERR_INDEX_RANGE, "block index outside +-2^20");
+  // a set, like the tracker's list in the reference (the mesh layer's find-or-insert needs unique keys per launch)
+  struct K3 {
+    int x, y, z;
+  };
+  std::vector<K3> v((size_t)n);
+  memcpy(v.data(), xyz_host, (size_t)n * sizeof(K3));
+  std::sort(v.begin(), v.end(), [](const K3& a, const K3& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); });
+  v.erase(std::unique(v.begin(), v.end(), [](const K3& a, const K3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }), v.end());
+  const int u = (int)v.size();
+  if (m->mesh_xyz_cap < u) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(m->mesh_xyz_dev);
+    m->mesh_xyz_dev = nullptr;
+    const int cap = std::max(u, 2 * m->mesh_xyz_cap);
+    NVB_CUDA(cudaMalloc(&m->mesh_xyz_dev, (size_t)cap * 3 * sizeof(int)));
+    m->mesh_xyz_cap = cap;
+  }
+  NVB_CUDA(cudaMemcpyAsync(m->mesh_xyz_dev, v.data(), (size_t)u * sizeof(K3), cudaMemcpyHostToDevice, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));  // v dies with this scope
+  *out_unique = u;
+  return NVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void nvb_default_mesh_params(NvbMeshParams* p) {
+  if (!p) return;
+  p->min_weight = 1e-4f;          // mesh/mesh_integrator_params.h:22-24
+  p->weld_vertices = 1;           // mesh/mesh_integrator_params.h:25-27
+  p->cutoff_distance_vox = 5.0f;  // MeshIntegrator::cutoff_distance_vox_, mesh/mesh_integrator.h:129
+}
+int32_t nvb_mapper_set_mesh_params(NvbMapper* m, const NvbMeshParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  m->mp = *p;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_mesh_params(const NvbMapper* m, NvbMeshParams* p) {
+  if (!m || !p) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *p = m->mp;
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_update_mesh(NvbMapper* m, int32_t update_full_layer) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  // "Mesh is only updated for Tsdf layers (not for occupancy)" (src/mapper/mapper.cpp:380-383)
+  if (m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = ensureMeshLayer(m))) return rc;
+  pollCounts(m);
+  const int upper = std::min(m->tsdf_count_ub, m->tsdf.capacity);
+  if (!m->mesh_tracker_initialized || update_full_layer) {
+    launchTodoAll(m->tsdf, m->dirty_mesh, m->todo_mesh_slots, m->esdf_ints + kTodoMeshCount, m->stream);
+    m->launches++;
+    m->mesh_tracker_initialized = true;
+  }
+  // integrateBlocksGPU + updateAppearance over the tracker's blocks, then markBlocksAsUpdated (mapper.cpp:385-395)
+  if ((rc = meshUpdateImpl(m, nullptr, m->todo_mesh_slots, m->esdf_ints + kTodoMeshCount, upper, true))) return rc;
+  NVB_CUDA(cudaMemsetAsync(m->esdf_ints + kTodoMeshCount, 0, sizeof(int), m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  return checkDeviceError(m);
+}
+
+int32_t nvb_mesh_integrate_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks, int32_t update_color) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (m->projective_layer_type == NVB_PROJECTIVE_OCCUPANCY) return fail(NVB_ERR_INVALID_ARGUMENT, "the mapper has no TSDF layer");
+  if (num_blocks < 0 || (num_blocks > 0 && !blocks_xyz_host)) return fail(NVB_ERR_INVALID_ARGUMENT, "bad block list");
+  NVB_CUDA(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = ensureMeshLayer(m))) return rc;
+  if (num_blocks == 0) return NVB_OK;  // (:73-75)
+  int u = 0;
+  if ((rc = uploadMeshList(m, blocks_xyz_host, num_blocks, &u))) return rc;
+  if ((rc = meshUpdateImpl(m, m->mesh_xyz_dev, nullptr, nullptr, u, update_color != 0))) return rc;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  return checkDeviceError(m);
+}
+
+int32_t nvb_mesh_update_color(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (num_blocks < 0 || (num_blocks > 0 && !blocks_xyz_host)) return fail(NVB_ERR_INVALID_ARGUMENT, "bad block list");
+  NVB_CUDA(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = ensureMeshLayer(m))) return rc;
+  if (num_blocks == 0 || !m->mesh_v) return NVB_OK;
+  int u = 0;
+  if ((rc = uploadMeshList(m, blocks_xyz_host, num_blocks, &u))) return rc;
+  MeshCtx c = makeMeshCtx(m);
+  c.in_xyz = m->mesh_xyz_dev, c.in_count_host = u;
+  launchMeshColor(c, u, m->num_sms, m->stream);
+  m->launches++;
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  return NVB_OK;
+}
+
+int32_t nvb_mesh_block_sizes(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks, int32_t* sizes_out) {
+  if (!m || (num_blocks > 0 && (!blocks_xyz_host || !sizes_out))) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (num_blocks <= 0) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
+  for (int i = 0; i < 3 * num_blocks; i++) sizes_out[i] = -1;
+  if (!m->mesh.blocks) return NVB_OK;
+  NVB_CUDA(syncAll(m));
+  int* dev = nullptr;
+  NVB_CUDA(cudaMalloc(&dev, (size_t)num_blocks * 7 * sizeof(int)));  // headers[4n] (int4-aligned) | xyz[3n]
+  int* xyz_dev = dev + 4 * (size_t)num_blocks;
+  NVB_CUDA(cudaMemcpy(xyz_dev, blocks_xyz_host, (size_t)num_blocks * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  launchMeshHeaders(makeMeshCtx(m), xyz_dev, num_blocks, dev, m->stream);
+  std::vector<int> h((size_t)num_blocks * 4);
+  NVB_CUDA(cudaMemcpyAsync(h.data(), dev, h.size() * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(dev);
+  for (int i = 0; i < num_blocks; i++)
+    if (h[4 * i] >= 0) sizes_out[3 * i] = h[4 * i + 1], sizes_out[3 * i + 1] = h[4 * i + 2], sizes_out[3 * i + 2] = h[4 * i + 3];
+  return NVB_OK;
+}
+
+int32_t nvb_mesh_get_blocks(NvbMapper* m, const int32_t* blocks_xyz_host, int32_t num_blocks, float* vertices_out,
+                            float* normals_out, int32_t* triangles_out, uint8_t* colors_out, const int64_t caps[3]) {
+  if (!m || !caps || (num_blocks > 0 && !blocks_xyz_host)) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (num_blocks <= 0 || !m->mesh.blocks) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(syncAll(m));
+  const size_t n = (size_t)num_blocks;
+  int* dev = nullptr;  // headers[4n] (int4-aligned) | xyz[3n] | dst[3n]
+  NVB_CUDA(cudaMalloc(&dev, n * 10 * sizeof(int)));
+  NVB_CUDA(cudaMemcpy(dev + 4 * n, blocks_xyz_host, n * 3 * sizeof(int), cudaMemcpyHostToDevice));
+  MeshCtx c = makeMeshCtx(m);
+  launchMeshHeaders(c, dev + 4 * n, num_blocks, dev, m->stream);
+  std::vector<int> h(n * 4), dst(n * 3);
+  NVB_CUDA(cudaMemcpyAsync(h.data(), dev, h.size() * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  long long tv = 0, tt = 0, tc = 0;
+  for (size_t i = 0; i < n; i++) {
+    dst[3 * i] = (int)tv, dst[3 * i + 1] = (int)tt, dst[3 * i + 2] = (int)tc;
+    if (h[4 * i] >= 0) tv += h[4 * i + 1], tt += h[4 * i + 2], tc += h[4 * i + 3];
+  }
+  if (tv > caps[0] || tt > caps[1] || tc > caps[2]) {
+    cudaFree(dev);
+    return fail(NVB_ERR_CAPACITY, "output buffers smaller than the listed mesh blocks");
+  }
+  float *pv = nullptr, *pn = nullptr;
+  int* pt = nullptr;
+  unsigned char* pc = nullptr;
+  NVB_CUDA(cudaMalloc(&pv, std::max<size_t>(1, (size_t)tv * 12)));
+  NVB_CUDA(cudaMalloc(&pn, std::max<size_t>(1, (size_t)tv * 12)));
+  NVB_CUDA(cudaMalloc(&pt, std::max<size_t>(1, (size_t)tt * 4)));
+  NVB_CUDA(cudaMalloc(&pc, std::max<size_t>(1, (size_t)tc * 4)));
+  NVB_CUDA(cudaMemcpyAsync(dev + 7 * n, dst.data(), n * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  launchMeshPack(c, dev, dev + 7 * n, num_blocks, pv, pn, pt, pc, m->num_sms, m->stream);
+  if (vertices_out && tv) NVB_CUDA(cudaMemcpyAsync(vertices_out, pv, (size_t)tv * 12, cudaMemcpyDeviceToHost, m->stream));
+  if (normals_out && tv) NVB_CUDA(cudaMemcpyAsync(normals_out, pn, (size_t)tv * 12, cudaMemcpyDeviceToHost, m->stream));
+  if (triangles_out && tt) NVB_CUDA(cudaMemcpyAsync(triangles_out, pt, (size_t)tt * 4, cudaMemcpyDeviceToHost, m->stream));
+  if (colors_out && tc) NVB_CUDA(cudaMemcpyAsync(colors_out, pc, (size_t)tc * 4, cudaMemcpyDeviceToHost, m->stream));
+  NVB_CUDA(cudaStreamSynchronize(m->stream));
+  cudaFree(dev), cudaFree(pv), cudaFree(pn), cudaFree(pt), cudaFree(pc);
+  return NVB_OK;
+}
+
+int32_t nvb_mesh_arena_stats(NvbMapper* m, int64_t out[4]) {
+  if (!m || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  out[0] = m->mesh_arena_cap, out[1] = out[2] = out[3] = 0;
+  if (!m->mesh.blocks) return NVB_OK;
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(syncAll(m));
+  int state[kArenaInts];
+  NVB_CUDA(cudaMemcpy(state, m->mesh_state, sizeof(state), cudaMemcpyDeviceToHost));
+  out[1] = state[kArenaUsed], out[2] = state[kArenaLastTotal], out[3] = state[kArenaGarbage];
+  return NVB_OK;
+}
 
 }  // extern "C"

@@ -296,6 +296,9 @@ struct CompactArgs {
   int* todo_slots;
   int* todo_count;
   int* dirty2;                     // second consumer of the tracker (freespace; may be null)
+  int* dirty3;                     // third consumer (mesh; may be null)
+  int* todo3_slots;
+  int* todo3_count;
   int* todo2_slots;
   int* todo2_count;
 };
@@ -467,6 +470,7 @@ struct MarkFreeArgs {
   int* error;
   int *dirty, *todo_slots, *todo_count;     // ESDF tracker (nullptr before its first query)
   int *dirty2, *todo2_slots, *todo2_count;  // freespace tracker
+  int *dirty3, *todo3_slots, *todo3_count;  // mesh tracker
 };
 void launchMarkFreeSphere(const MarkFreeArgs& a, int num_sms, cudaStream_t stream);
 
@@ -529,6 +533,46 @@ void launchEsdfRemoveBlocks(const EsdfCtx& c, const int4* dead, const int* dead_
 void launchAppendFrame(const int4* frame, const int* frame_count, int* seg, int cap, int* error, cudaStream_t stream);
 void launchUnionSegments(const int* segs, int num_segments, int stride, int cap, int* state, unsigned int* bits, long long cap_bits,
                          int* out_xyz, int out_cap, int* out_count, cudaStream_t stream);
+
+// nvb_mesh.cu
+// Header of one mesh block in the mesh layer's slab (32 bytes): where its vertices / normals / triangle indices / colours
+// live in the arena. cap = the arena entries reserved for it (its pre-weld vertex count).
+struct MeshHeader {
+  int offset, nv, nt, cap, nc, pad[3];
+};
+constexpr int kMeshHeaderBytes = 32;
+static_assert(sizeof(MeshHeader) == kMeshHeaderBytes, "MeshHeader layout");
+enum { kArenaUsed = 0, kArenaGarbage = 1, kArenaLastBase = 2, kArenaLastTotal = 3, kArenaInts = 4 };
+struct MeshCtx {
+  DevLayer tsdf, color, mesh;  // color.blocks == nullptr: the mapper has no colour layer (yet)
+  float* vertices;
+  float* normals;
+  int* triangles;
+  unsigned char* colors_raw;
+  uchar4* colors;
+  int* arena_state;  // kArena* ints
+  int* counts;       // per list entry: pre-weld vertex count
+  int* offsets;      // per list entry: arena offset
+  const int* in_xyz;       // explicit list (device) or ...
+  const int* in_slots;     // ... TSDF slots from the tracker
+  const int* in_count_dev;
+  int in_count_host;
+  int* tracker_dirty;
+  float block_size, voxel_size, min_weight, cutoff_distance_m;
+  int weld;
+  int* error;
+};
+size_t meshWeldSmemBytes();
+void launchMeshCount(const MeshCtx& c, int upper, int num_sms, cudaStream_t stream);
+void launchMeshScan(const MeshCtx& c, cudaStream_t stream);
+void launchMeshEmit(const MeshCtx& c, int upper, int num_sms, cudaStream_t stream);
+void launchMeshColor(const MeshCtx& c, int upper, int num_sms, cudaStream_t stream);
+void launchMeshHeaders(const MeshCtx& c, const int* xyz_dev, int n, int* out4, cudaStream_t stream);
+void launchMeshPack(const MeshCtx& c, const int* src4, const int* dst3, int n, float* v_out, float* n_out, int* t_out,
+                    unsigned char* c_out, int num_sms, cudaStream_t stream);
+void launchMeshCompactSizes(const MeshCtx& c, int nslots, int* sizes, cudaStream_t stream);
+void launchMeshCompactMove(const MeshCtx& c, int nslots, const int* new_offsets, float* v2, float* n2, int* t2,
+                           unsigned char* c2, int num_sms, cudaStream_t stream);
 
 // nvb_util.cu
 void launchGatherBlocks(const DevLayer& layer, const int* xyz_dev, int n, unsigned char* out, unsigned char* found,

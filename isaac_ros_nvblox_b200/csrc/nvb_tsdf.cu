@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(256) markFreeSphereKernel(const __grid_constan
         // BlocksToUpdateTracker::addBlocksToUpdate(updated_blocks) (src/mapper/mapper.cpp:506)
         if (a.dirty != nullptr && atomicExch(a.dirty + slot, 1) == 0) a.todo_slots[atomicAdd(a.todo_count, 1)] = slot;
         if (a.dirty2 != nullptr && atomicExch(a.dirty2 + slot, 1) == 0) a.todo2_slots[atomicAdd(a.todo2_count, 1)] = slot;
+        if (a.dirty3 != nullptr && atomicExch(a.dirty3 + slot, 1) == 0) a.todo3_slots[atomicAdd(a.todo3_count, 1)] = slot;
         a.out[atomicAdd(a.out_count, 1)] = make_int4(idx[0], idx[1], idx[2], slot);
       }
     }

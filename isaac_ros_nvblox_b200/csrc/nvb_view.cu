@@ -238,6 +238,9 @@ __global__ void __launch_bounds__(kCompactThreads) compactAllocateKernel(Compact
       if (slot >= 0 && a.dirty2 != nullptr) {
         if (atomicExch(a.dirty2 + slot, 1) == 0) a.todo2_slots[atomicAdd(a.todo2_count, 1)] = slot;
       }
+      if (slot >= 0 && a.dirty3 != nullptr) {
+        if (atomicExch(a.dirty3 + slot, 1) == 0) a.todo3_slots[atomicAdd(a.todo3_count, 1)] = slot;
+      }
     }
     s_out[j] = make_int4(x, y, z, slot);
   }

@@ -381,6 +381,108 @@ class _EsdfIntegrator:
         return int(out.value)
 
 
+class _MeshIntegrator:
+    """MeshIntegrator parameters (mesh/mesh_integrator.h:83-87,126-133)."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def params(self, **kw):
+        p = _lib.NvbMeshParams()
+        check(self._m._L.nvb_mapper_get_mesh_params(self._m._h, C.byref(p)))
+        if kw:
+            for k, v in kw.items():
+                setattr(p, k, v)
+            check(self._m._L.nvb_mapper_set_mesh_params(self._m._h, C.byref(p)))
+        return p
+
+    def min_weight(self, v=None):
+        return self.params(**({} if v is None else {"min_weight": float(v)})).min_weight
+
+    def weld_vertices(self, v=None):
+        return bool(self.params(**({} if v is None else {"weld_vertices": 1 if v else 0})).weld_vertices)
+
+    def integrate_blocks(self, blocks, update_color=False):
+        """MeshIntegrator::integrateBlocksGPU(tsdf_layer, block_indices, mesh_layer) [+ updateAppearance]."""
+        b = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        check(self._m._L.nvb_mesh_integrate_blocks(self._m._h, _ip(b), b.shape[0], 1 if update_color else 0))
+
+    def integrate_mesh_from_distance_field(self, update_color=False):
+        """MeshIntegrator::integrateMeshFromDistanceField: every block of the TSDF layer."""
+        self.integrate_blocks(self._m.tsdf_layer().get_all_block_indices(), update_color)
+
+    def update_color(self, blocks=None):
+        """MeshIntegrator::updateAppearance (blocks=None: every mesh block)."""
+        if blocks is None:
+            blocks = self._m.mesh_layer().get_all_block_indices()
+        b = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        check(self._m._L.nvb_mesh_update_color(self._m._h, _ip(b), b.shape[0]))
+
+
+class _MeshLayer:
+    """MeshBlockLayer queries (mesh/mesh_block.h:32-83; map/layer.h) answered from the device arena."""
+
+    def __init__(self, mapper):
+        self._m = mapper
+
+    def num_blocks(self):
+        n = C.c_int32(0)
+        rc = self._m._L.nvb_layer_num_blocks(self._m._h, _lib.NVB_LAYER_MESH, C.byref(n))
+        return n.value if rc == 0 else 0  # no mesh update yet: an empty layer
+
+    def get_all_block_indices(self):
+        n = self.num_blocks()
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        if n:
+            cnt = C.c_int32(0)
+            check(self._m._L.nvb_layer_block_indices(self._m._h, _lib.NVB_LAYER_MESH, _ip(out), n, C.byref(cnt)))
+        return out[:n].copy()
+
+    def block_sizes(self, indices):
+        """(n,3) -> (n,3) int32 {vertices, triangle indices, colours}; -1 where there is no mesh block."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        out = np.full((max(idx.shape[0], 1), 3), -1, dtype=np.int32)
+        check(self._m._L.nvb_mesh_block_sizes(self._m._h, _ip(idx), idx.shape[0], _ip(out)))
+        return out[:idx.shape[0]]
+
+    def get_blocks(self, indices):
+        """(n,3) -> list of {"vertices" (v,3) f32, "normals" (v,3) f32, "triangles" (t,) i32, "colors" (c,4) u8} or None."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 3)
+        sz = self.block_sizes(idx)
+        live = np.maximum(sz, 0).astype(np.int64)
+        tv, tt, tc = (int(x) for x in live.sum(axis=0)) if idx.shape[0] else (0, 0, 0)
+        V, N = np.zeros((max(tv, 1), 3), np.float32), np.zeros((max(tv, 1), 3), np.float32)
+        T, Cc = np.zeros(max(tt, 1), np.int32), np.zeros((max(tc, 1), 4), np.uint8)
+        caps = (C.c_int64 * 3)(tv, tt, tc)
+        check(self._m._L.nvb_mesh_get_blocks(self._m._h, _ip(idx), idx.shape[0], V.ctypes.data, N.ctypes.data, T.ctypes.data,
+                                             Cc.ctypes.data, caps))
+        out, ov, ot, oc = [], 0, 0, 0
+        for i in range(idx.shape[0]):
+            if sz[i, 0] < 0:
+                out.append(None)
+                continue
+            nv, nt, nc = (int(x) for x in sz[i])
+            out.append({"vertices": V[ov:ov + nv].copy(), "normals": N[ov:ov + nv].copy(), "triangles": T[ot:ot + nt].copy(),
+                        "colors": Cc[oc:oc + nc].copy()})
+            ov, ot, oc = ov + nv, ot + nt, oc + nc
+        return out
+
+    def get_block_at_index(self, index):
+        return self.get_blocks(np.asarray(index, dtype=np.int32).reshape(1, 3))[0]
+
+    def is_block_allocated(self, index):
+        return bool(self.block_sizes(np.asarray(index, dtype=np.int32).reshape(1, 3))[0, 0] >= 0)
+
+    def as_dict(self):
+        idx = self.get_all_block_indices()
+        return {tuple(int(c) for c in k): b for k, b in zip(idx, self.get_blocks(idx))}
+
+    def arena_stats(self):
+        out = (C.c_int64 * 4)()
+        check(self._m._L.nvb_mesh_arena_stats(self._m._h, out))
+        return {"capacity": out[0], "used": out[1], "last_update_vertices": out[2]}
+
+
 class EsdfSlicer:
     """EsdfSlicer (integrators/esdf_slicer.h:36-138): distance-map image and occupancy grid of an ESDF slice."""
 
@@ -477,6 +579,18 @@ class Mapper:
 
     def color_layer(self):
         return self._color
+
+    def mesh_layer(self):
+        """Mapper::color_mesh_layer()."""
+        return _MeshLayer(self)
+
+    def mesh_integrator(self):
+        """Mapper::color_mesh_integrator()."""
+        return _MeshIntegrator(self)
+
+    def update_mesh(self, update_full_layer=False):
+        """Mapper::updateColorMesh(UpdateFullLayer) (mapper.h; src/mapper/mapper.cpp:371-406)."""
+        check(self._L.nvb_mapper_update_mesh(self._h, 1 if update_full_layer else 0))
 
     def color_integrator(self):
         return _ColorIntegrator(self)

@@ -474,9 +474,27 @@ static void list_sort_unique(List* l) {
   l->n = w;
 }
 
+/* MeshBlock (mesh/mesh_block.h:32-83): vertices, vertex_normals, vertex_appearances (Color), triangles */
+typedef struct {
+  int32_t nv, nt, nc; /* sizes of vertices (= normals), triangles, colours */
+  float* v;
+  float* nrm;
+  int32_t* tri;
+  uint8_t* col; /* rgba */
+} MeshBlock;
+
+static void mesh_block_release(MeshBlock* b) {
+  free(b->v), free(b->nrm), free(b->tri), free(b->col);
+  memset(b, 0, sizeof(*b));
+}
+static void mesh_layer_release(Layer* l) {
+  for (int32_t s = 0; s < l->n; s++) mesh_block_release((MeshBlock*)layer_block(l, s));
+}
+
 struct OrMap {
   float voxel_size, block_size;
   Layer tsdf, esdf, occ, freespace, color;
+  Layer mesh; /* MeshBlockLayer: one MeshBlock header per slot (the arrays hang off it) */
   int64_t freespace_last_update_time_ms; /* FreespaceIntegrator::last_update_time_ms_ (freespace_integrator.h:171) */
   float slice_min_z, slice_max_z, slice_out_z; /* heights of the last or_esdf_integrate_slice call (for the 2-D clear) */
   /* EsdfIntegrator::cleared_block_indices_device_ (integrators/esdf_integrator.h:389)
@@ -529,17 +547,20 @@ OrMap* or_map_create(float voxel_size_m) {
   layer_init(&m->occ, sizeof(float) * VPB); /* OccupancyVoxel{float log_odds} (map/voxels.h:92-97) */
   layer_init(&m->freespace, sizeof(OrFreespaceVoxel) * VPB);
   layer_init(&m->color, sizeof(OrColorVoxel) * VPB);
+  layer_init(&m->mesh, sizeof(MeshBlock));
   return m;
 }
 void or_map_destroy(OrMap* m) {
   if (!m) return;
   layer_free(&m->tsdf), layer_free(&m->esdf), layer_free(&m->occ), layer_free(&m->freespace), layer_free(&m->color);
+  mesh_layer_release(&m->mesh), layer_free(&m->mesh);
   list_free(&m->esdf_cleared_persistent);
   for (int i = 0; i < m->view_cache_n; i++) list_free(&m->view_cache_blocks[i]);
   free(m);
 }
 void or_map_clear(OrMap* m) {
   layer_clear(&m->tsdf), layer_clear(&m->esdf), layer_clear(&m->occ), layer_clear(&m->freespace), layer_clear(&m->color);
+  mesh_layer_release(&m->mesh), layer_clear(&m->mesh);
   m->esdf_cleared_persistent.n = 0;
   /* (Mapper::clear does not touch the integrators: the viewpoint cache survives) */
 }
@@ -2318,6 +2339,241 @@ int32_t or_camera_project(const OrCamera* cam, const float p_C[3], float uv[2]) 
 void or_camera_vector_from_image_plane(const OrCamera* cam, float u, float v, float out[3]) {
   v3 r = cam_vector_from_image_plane(cam, u, v);
   out[0] = r.x, out[1] = r.y, out[2] = r.z;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Mesh integrator (src/mesh/mesh_integrator.cu, mesh_integrator_appearance.cu) */
+/* ------------------------------------------------------------------------- */
+#include "mc_table.h"
+
+static int mc_hex(char c) { return c <= '9' ? c - '0' : c - 'a' + 10; }
+
+/* One voxel of meshBlocksCalculateTableIndicesKernel (mesh_integrator.cu:335-452): the 8 corner samples of the cube whose
+ * minimum corner is voxel (vx, vy, vz) of `blk`; nb[] = the block and its 7 upper neighbours in
+ * neighborIndexFromDirection order (x << 2 | y << 1 | z, marching_cubes_impl.h:17-19). Returns the table index, or -1
+ * if a corner is missing / unobserved. */
+static int mesh_cube(const OrTsdfVoxel* const nb[8], i3 bidx, float block_size, float voxel_size, float min_weight, int vx,
+                     int vy, int vz, float sdf[8], float pos[8][3]) {
+  const int v[3] = {vx, vy, vz};
+  /* getPositionFromBlockIndex (core/internal/impl/indexing_impl.h): block_size * index */
+  const float bp[3] = {block_size * (float)bidx.x, block_size * (float)bidx.y, block_size * (float)bidx.z};
+  for (int i = 0; i < 8; i++) {
+    int c[3], off[3] = {0, 0, 0};
+    for (int j = 0; j < 3; j++) {
+      c[j] = v[j] + kMcCornerOffsets[i][j];
+      if (c[j] >= VPS) c[j] -= VPS, off[j] = 1;
+    }
+    const OrTsdfVoxel* b = nb[(off[0] << 2) | (off[1] << 1) | off[2]];
+    if (!b) return -1;
+    const OrTsdfVoxel* vox = b + (c[0] * VPS + c[1]) * VPS + c[2];
+    if (vox->weight < min_weight) return -1;
+    sdf[i] = vox->distance;
+    /* block_positions[block] + voxel_size * (corner_index + 0.5 + 8 * block_offset)  (:423-426) */
+    for (int j = 0; j < 3; j++) pos[i][j] = bp[j] + voxel_size * (((float)c[j] + 0.5f) + (float)(VPS * off[j]));
+  }
+  int idx = 0; /* calculateVertexConfiguration (marching_cubes_impl.h:6-15) */
+  for (int i = 0; i < 8; i++)
+    if (sdf[i] < 0) idx |= 1 << i;
+  return idx;
+}
+
+/* interpolateVertex (marching_cubes_impl.h:28-43) */
+static void mc_interpolate(const float a[3], const float b[3], float sa, float sb, float out[3]) {
+  const float diff = sa - sb;
+  if (fabsf(diff) >= 1e-4f) {
+    const float t = sa / diff;
+    for (int j = 0; j < 3; j++) out[j] = a[j] + t * (b[j] - a[j]);
+  } else {
+    for (int j = 0; j < 3; j++) out[j] = 0.5f * (a[j] + b[j]);
+  }
+}
+
+/* calculateVertices (internal/impl/cuda/marching_cubes_impl.cuh:31-70): the triangles of one cube, appended at `next`. */
+static int mc_emit(int table_index, const float sdf[8], float pos[8][3], float* V, float* N, int32_t* T, int next) {
+  const char* row = kMcTriangles[table_index];
+  if (!row[0]) return next;
+  float edge[12][3];
+  memset(edge, 0, sizeof(edge));
+  for (int e = 0; e < 12; e++) { /* interpolateEdgeVertices (marching_cubes_impl.h:45-64) */
+    const int c0 = kMcEdgeCorners[e][0], c1 = kMcEdgeCorners[e][1];
+    if ((sdf[c0] < 0 && sdf[c1] >= 0) || (sdf[c0] >= 0 && sdf[c1] < 0)) mc_interpolate(pos[c0], pos[c1], sdf[c0], sdf[c1], edge[e]);
+  }
+  for (int c = 0; row[c]; c += 3) {
+    const float* p0 = edge[mc_hex(row[c + 2])];
+    const float* p1 = edge[mc_hex(row[c + 1])];
+    const float* p2 = edge[mc_hex(row[c])];
+    memcpy(V + 3 * next, p0, 12), memcpy(V + 3 * (next + 1), p1, 12), memcpy(V + 3 * (next + 2), p2, 12);
+    T[next] = next, T[next + 1] = next + 1, T[next + 2] = next + 2;
+    const float px[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    const float py[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+    /* Eigen cross + normalized(): v / sqrt(squaredNorm) if squaredNorm > 0 */
+    float n[3] = {px[1] * py[2] - px[2] * py[1], px[2] * py[0] - px[0] * py[2], px[0] * py[1] - px[1] * py[0]};
+    const float sq = (n[0] * n[0] + n[1] * n[1]) + n[2] * n[2];
+    if (sq > 0.0f) {
+      const float len = sqrtf(sq);
+      n[0] /= len, n[1] /= len, n[2] /= len;
+    }
+    for (int k = 0; k < 3; k++) memcpy(N + 3 * (next + k), n, 12);
+    next += 3;
+  }
+  return next;
+}
+
+typedef struct {
+  uint64_t key;
+  int32_t idx;
+} WeldKey;
+static int weld_cmp(const void* a, const void* b) {
+  const WeldKey* x = (const WeldKey*)a;
+  const WeldKey* y = (const WeldKey*)b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0); /* the radix sort is stable */
+}
+
+/* weldVerticesCubKernel<128, 20> (mesh_integrator.cu:691-803). */
+static void mesh_weld(MeshBlock* b) {
+  const int n = b->nv;
+  if (n <= 0 || n >= 128 * 20) return; /* too many vertices: the block keeps them all */
+  WeldKey* k = (WeldKey*)malloc(sizeof(WeldKey) * (size_t)n);
+  for (int i = 0; i < n; i++) {
+    /* Index3DHash(Index3D(x * 1000, y * 1000, z * 1000)) (core/hash.h:32-40): float products truncated to int, then
+     * x + y * 17191 + z * 17191^2 in size_t arithmetic */
+    const int32_t x = (int32_t)(b->v[3 * i] * 1000.0f), y = (int32_t)(b->v[3 * i + 1] * 1000.0f), z = (int32_t)(b->v[3 * i + 2] * 1000.0f);
+    const uint64_t sl = 17191ull;
+    k[i].key = (uint64_t)(int64_t)x + (uint64_t)(int64_t)y * sl + (uint64_t)(int64_t)z * (sl * sl);
+    k[i].idx = b->tri[i];
+  }
+  qsort(k, (size_t)n, sizeof(WeldKey), weld_cmp);
+  float* V = (float*)malloc(12 * (size_t)n);
+  float* N = (float*)malloc(12 * (size_t)n);
+  int heads = 0;
+  for (int i = 0; i < n; i++) {
+    if (i == 0 || k[i].key != k[i - 1].key) { /* FlagHeads + InclusiveSum */
+      memcpy(V + 3 * heads, b->v + 3 * k[i].idx, 12), memcpy(N + 3 * heads, b->nrm + 3 * k[i].idx, 12);
+      heads++;
+    }
+    b->tri[k[i].idx] = heads - 1;
+  }
+  memcpy(b->v, V, 12 * (size_t)heads), memcpy(b->nrm, N, 12 * (size_t)heads);
+  b->nv = heads; /* vertices / normals shrink; `triangles` keeps its pre-weld length (:668-686) */
+  free(V), free(N), free(k);
+}
+
+void or_default_mesh_params(OrMeshParams* p) {
+  p->min_weight = 1e-4f;          /* mesh_integrator_params.h:22-24 */
+  p->weld_vertices = 1;           /* mesh_integrator_params.h:25-27 */
+  p->cutoff_distance_vox = 5.0f;  /* mesh_integrator.h:129 */
+}
+
+/* MeshIntegrator::integrateBlocksGPU (mesh_integrator.cu:66-108) with the per-voxel output order made deterministic: the
+ * reference hands out vertex ranges with an atomicAdd per voxel (calculateOutputIndex, marching_cubes_impl.cuh:11-29), so the
+ * order of a block's triangles differs from run to run there; here voxels emit in x-major linear order (the CPU path's
+ * order, :200-233). */
+void or_mesh_integrate_blocks(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, const OrMeshParams* P) {
+  const float block_size = map->block_size, voxel_size = map->voxel_size;
+  /* getIndicesInLayer + "clear all blocks if they exist" (:53-87) */
+  for (int32_t i = 0; i < num_blocks; i++) {
+    const i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], blocks_xyz[3 * i + 2]};
+    if (hash_find(&map->tsdf.hash, k) < 0) continue;
+    const int32_t ms = hash_find(&map->mesh.hash, k);
+    if (ms >= 0) {
+      MeshBlock* mb = (MeshBlock*)layer_block(&map->mesh, ms);
+      mb->nv = mb->nt = mb->nc = 0; /* MeshBlock::clear */
+    }
+  }
+  const float cutoff = P->cutoff_distance_vox * voxel_size;
+  float* V = (float*)malloc(12 * (size_t)VPB * 15);
+  float* N = (float*)malloc(12 * (size_t)VPB * 15);
+  int32_t* T = (int32_t*)malloc(4 * (size_t)VPB * 15);
+  for (int32_t i = 0; i < num_blocks; i++) {
+    const i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], blocks_xyz[3 * i + 2]};
+    const int32_t ts = hash_find(&map->tsdf.hash, k);
+    if (ts < 0) continue;
+    const OrTsdfVoxel* blk = (const OrTsdfVoxel*)layer_block(&map->tsdf, ts);
+    int meshable = 0; /* isBlockMeshableKernel (:313-328) */
+    for (int q = 0; q < VPB && !meshable; q++) meshable = fabsf(blk[q].distance) <= cutoff && blk[q].weight >= P->min_weight;
+    if (!meshable) continue;
+    const OrTsdfVoxel* nb[8];
+    for (int j = 0; j < 8; j++) {
+      const i3 nk = {k.x + ((j >> 2) & 1), k.y + ((j >> 1) & 1), k.z + (j & 1)};
+      const int32_t s = hash_find(&map->tsdf.hash, nk);
+      nb[j] = s >= 0 ? (const OrTsdfVoxel*)layer_block(&map->tsdf, s) : NULL;
+    }
+    int next = 0;
+    for (int vx = 0; vx < VPS; vx++)
+      for (int vy = 0; vy < VPS; vy++)
+        for (int vz = 0; vz < VPS; vz++) {
+          float sdf[8], pos[8][3];
+          const int idx = mesh_cube(nb, k, block_size, voxel_size, P->min_weight, vx, vy, vz, sdf, pos);
+          if (idx < 0) continue;
+          next = mc_emit(idx, sdf, pos, V, N, T, next);
+        }
+    if (next == 0) continue; /* mesh blocks are only allocated for num_vertices > 0 (:603-611) */
+    const int32_t ms = layer_allocate(&map->mesh, k);
+    MeshBlock* mb = (MeshBlock*)layer_block(&map->mesh, ms);
+    free(mb->v), free(mb->nrm), free(mb->tri);
+    mb->v = (float*)malloc(12 * (size_t)next), mb->nrm = (float*)malloc(12 * (size_t)next), mb->tri = (int32_t*)malloc(4 * (size_t)next);
+    memcpy(mb->v, V, 12 * (size_t)next), memcpy(mb->nrm, N, 12 * (size_t)next), memcpy(mb->tri, T, 4 * (size_t)next);
+    mb->nv = next, mb->nt = next, mb->nc = 0;
+    if (P->weld_vertices) mesh_weld(mb);
+  }
+  free(V), free(N), free(T);
+}
+
+/* MeshIntegrator::updateAppearanceGPU (mesh_integrator_appearance.cu:281-380) for ColorVoxel: every requested block that has
+ * a mesh block gets one colour per vertex -- the colour voxel the vertex falls into in the CO-LOCATED colour block
+ * (updateAppearanceBlockByClosestVoxel, :98-147), or Color::Gray() (127, 127, 127, core/color.h:59) if there is none. */
+void or_mesh_update_color(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks) {
+  const float block_size = map->block_size, voxel_size = map->voxel_size;
+  for (int32_t i = 0; i < num_blocks; i++) {
+    const i3 k = {blocks_xyz[3 * i], blocks_xyz[3 * i + 1], blocks_xyz[3 * i + 2]};
+    const int32_t ms = hash_find(&map->mesh.hash, k);
+    if (ms < 0) continue;
+    MeshBlock* mb = (MeshBlock*)layer_block(&map->mesh, ms);
+    free(mb->col);
+    mb->col = (uint8_t*)malloc(4 * (size_t)(mb->nv > 0 ? mb->nv : 1)); /* expandAppearanceToMatchVertices */
+    mb->nc = mb->nv;
+    const int32_t cs = hash_find(&map->color.hash, k);
+    const OrColorVoxel* cb = cs >= 0 ? (const OrColorVoxel*)layer_block(&map->color, cs) : NULL;
+    const float bp[3] = {block_size * (float)k.x, block_size * (float)k.y, block_size * (float)k.z};
+    for (int32_t q = 0; q < mb->nv; q++) {
+      uint8_t* c = mb->col + 4 * q;
+      if (!cb) {
+        c[0] = c[1] = c[2] = 127, c[3] = 255;
+        continue;
+      }
+      int vi[3];
+      for (int j = 0; j < 3; j++) {
+        vi[j] = (int)((mb->v[3 * q + j] - bp[j]) / voxel_size);
+        vi[j] = vi[j] > VPS - 1 ? VPS - 1 : vi[j];
+        vi[j] = vi[j] < 0 ? 0 : vi[j];
+      }
+      const OrColorVoxel* cv = cb + (vi[0] * VPS + vi[1]) * VPS + vi[2];
+      c[0] = cv->r, c[1] = cv->g, c[2] = cv->b, c[3] = 255;
+    }
+  }
+}
+
+int32_t or_mesh_num_blocks(const OrMap* m) { return m->mesh.n; }
+int32_t or_mesh_block_indices(const OrMap* m, int32_t* out, int32_t cap) { return layer_indices(&m->mesh, out, cap); }
+int32_t or_mesh_block_sizes(const OrMap* m, const int32_t xyz[3], int32_t out[3]) {
+  const i3 k = {xyz[0], xyz[1], xyz[2]};
+  const int32_t s = hash_find(&m->mesh.hash, k);
+  if (s < 0) return 0;
+  const MeshBlock* b = (const MeshBlock*)layer_block(&m->mesh, s);
+  out[0] = b->nv, out[1] = b->nt, out[2] = b->nc;
+  return 1;
+}
+int32_t or_mesh_get_block(const OrMap* m, const int32_t xyz[3], float* vertices, float* normals, int32_t* triangles, uint8_t* colors) {
+  const i3 k = {xyz[0], xyz[1], xyz[2]};
+  const int32_t s = hash_find(&m->mesh.hash, k);
+  if (s < 0) return 0;
+  const MeshBlock* b = (const MeshBlock*)layer_block(&m->mesh, s);
+  if (vertices) memcpy(vertices, b->v, 12 * (size_t)b->nv);
+  if (normals) memcpy(normals, b->nrm, 12 * (size_t)b->nv);
+  if (triangles) memcpy(triangles, b->tri, 4 * (size_t)b->nt);
+  if (colors) memcpy(colors, b->col, 4 * (size_t)b->nc);
+  return 1;
 }
 
 int32_t or_num_threads(void) {

@@ -308,6 +308,26 @@ void or_depth_dilate_invalid(const float* depth, int32_t rows, int32_t cols, int
 void or_tsdf_set_block(OrMap* map, const int32_t xyz[3], const OrTsdfVoxel* in);
 void or_esdf_set_block(OrMap* map, const int32_t xyz[3], const OrEsdfVoxel* in); /* test hook */
 
+/* ---- Mesh integrator (mesh/mesh_integrator.h; src/mesh/mesh_integrator.cu, mesh_integrator_appearance.cu) */
+typedef struct {
+  float min_weight;          /* mesh_integrator_params.h:22-24, default 1e-4 */
+  int32_t weld_vertices;     /* mesh_integrator_params.h:25-27, default true */
+  float cutoff_distance_vox; /* MeshIntegrator::cutoff_distance_vox_ (mesh_integrator.h:129), 5 */
+} OrMeshParams;
+void or_default_mesh_params(OrMeshParams* p);
+/* MeshIntegrator::integrateBlocksGPU (mesh_integrator.cu:66-108): re-meshes the listed blocks (those in the TSDF layer).
+ * A block's triangles come out in x-major voxel order (the reference's order is an atomicAdd race). */
+void or_mesh_integrate_blocks(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks, const OrMeshParams* params);
+/* MeshIntegrator::updateAppearanceGPU for the colour layer (mesh_integrator_appearance.cu:281-380) */
+void or_mesh_update_color(OrMap* map, const int32_t* blocks_xyz, int32_t num_blocks);
+int32_t or_mesh_num_blocks(const OrMap* map);
+int32_t or_mesh_block_indices(const OrMap* map, int32_t* out_xyz, int32_t cap);
+/* out = {vertices, triangle indices, colours}; 0 if the block is absent */
+int32_t or_mesh_block_sizes(const OrMap* map, const int32_t xyz[3], int32_t out[3]);
+/* vertices / normals: 3 floats each; triangles: indices into vertices; colours: rgba bytes. Any pointer may be NULL. */
+int32_t or_mesh_get_block(const OrMap* map, const int32_t xyz[3], float* vertices, float* normals, int32_t* triangles,
+                          uint8_t* colors);
+
 /* Camera::project / vectorFromImagePlaneCoordinates exposed for the distortion tests. */
 int32_t or_camera_project(const OrCamera* cam, const float p_C[3], float uv[2]);
 void or_camera_vector_from_image_plane(const OrCamera* cam, float u, float v, float out[3]);

@@ -98,6 +98,11 @@ class ColorParams(C.Structure):
                 ("workspace_bounds_type", C.c_int32), ("workspace_min", C.c_float * 3), ("workspace_max", C.c_float * 3)]
 
 
+class MeshParams(C.Structure):
+    """OrMeshParams: mesh_integrator_params.h:22-27, MeshIntegrator::cutoff_distance_vox_ (mesh_integrator.h:129)."""
+    _fields_ = [("min_weight", C.c_float), ("weld_vertices", C.c_int32), ("cutoff_distance_vox", C.c_float)]
+
+
 class TsdfDecayParams(C.Structure):
     _fields_ = [("decay_factor", C.c_float), ("decayed_weight_threshold", C.c_float),
                 ("set_free_distance_on_decayed", C.c_int32), ("free_distance_vox", C.c_float),
@@ -179,6 +184,14 @@ def lib():
     L.or_map_cache_last_viewpoint.argtypes = [vp, C.c_int32]
     L.or_depth_dilate_invalid.argtypes = [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.POINTER(C.c_float)]
     L.or_depth_dilate_invalid.restype = None
+    L.or_mesh_integrate_blocks.argtypes = [vp, ip, C.c_int32, C.POINTER(MeshParams)]
+    L.or_mesh_integrate_blocks.restype = None
+    L.or_mesh_update_color.argtypes = [vp, ip, C.c_int32]
+    L.or_mesh_update_color.restype = None
+    L.or_mesh_num_blocks.argtypes = [vp]
+    L.or_mesh_block_indices.argtypes = [vp, ip, C.c_int32]
+    L.or_mesh_block_sizes.argtypes = [vp, ip, C.POINTER(C.c_int32 * 3)]
+    L.or_mesh_get_block.argtypes = [vp, ip, fp, fp, ip, u8p]
     L.or_esdf_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.argtypes = [vp, ip, vp]
     L.or_freespace_set_block.restype = None
@@ -597,6 +610,44 @@ class OracleMap:
 
     def color_layer(self):
         return {tuple(int(c) for c in k): self.color_block(k) for k in self.color_block_indices()}
+
+    # ---- mesh (mesh/mesh_integrator.h)
+    def integrate_mesh(self, blocks=None, min_weight=1e-4, weld_vertices=True, cutoff_distance_vox=5.0):
+        """MeshIntegrator::integrateBlocksGPU (blocks) / integrateMeshFromDistanceField (blocks=None: every TSDF block)."""
+        if blocks is None:
+            blocks = self.tsdf_block_indices()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        p = MeshParams(float(min_weight), 1 if weld_vertices else 0, float(cutoff_distance_vox))
+        lib().or_mesh_integrate_blocks(self._h, _ip(blocks), blocks.shape[0], C.byref(p))
+
+    def update_mesh_color(self, blocks=None):
+        """MeshIntegrator::updateAppearance for the colour layer (blocks=None: every mesh block)."""
+        if blocks is None:
+            blocks = self.mesh_block_indices()
+        blocks = np.ascontiguousarray(blocks, dtype=np.int32).reshape(-1, 3)
+        lib().or_mesh_update_color(self._h, _ip(blocks), blocks.shape[0])
+
+    def mesh_block_indices(self):
+        n = lib().or_mesh_num_blocks(self._h)
+        out = np.zeros((max(n, 1), 3), dtype=np.int32)
+        lib().or_mesh_block_indices(self._h, _ip(out), n)
+        return out[:n]
+
+    def mesh_block(self, idx):
+        k = np.ascontiguousarray(idx, dtype=np.int32).reshape(3)
+        sz = (C.c_int32 * 3)()
+        if not lib().or_mesh_block_sizes(self._h, _ip(k), sz):
+            return None
+        v = np.zeros((sz[0], 3), np.float32)
+        nrm = np.zeros((sz[0], 3), np.float32)
+        t = np.zeros(sz[1], np.int32)
+        c = np.zeros((sz[2], 4), np.uint8)
+        lib().or_mesh_get_block(self._h, _ip(k), _fp(v) if sz[0] else None, _fp(nrm) if sz[0] else None, _ip(t) if sz[1] else None,
+                                c.ctypes.data_as(C.POINTER(C.c_uint8)) if sz[2] else None)
+        return {"vertices": v, "normals": nrm, "triangles": t, "colors": c}
+
+    def mesh_layer(self):
+        return {tuple(int(c) for c in k): self.mesh_block(k) for k in self.mesh_block_indices()}
 
     def integrate_esdf_slice(self, blocks, params=None, z_min_m=0.0, z_max_m=1.0, z_output_m=1.0, from_occupancy=False,
                              use_freespace=False):
