@@ -534,6 +534,39 @@ def main():
                                   "(TSDF + colour + ESDF, BASELINE.json configs[1] shape), frames resident in HBM"}
         del color_dev
 
+    # ---- BASELINE.json configs[2] flavour ("Meshing", mesh/integrate): the mesh of the touched blocks after every frame ----
+    with_mesh = None
+    if world == 1 and wl.name == "c2" and not wl.occupancy:
+        def step_mesh():
+            m.clear()
+            for i in range(F):
+                m.integrate_depth_device(depth_dev[i].data_ptr(), ROWS, COLS, poses[i], cam)
+                m.update_esdf(sync=False)
+                m.update_mesh()  # marching cubes + weld + vertex colours of the blocks touched since the last call
+
+        for _ in range(2):
+            step_mesh()
+        m.synchronize()
+        l0 = m.kernel_launches()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(args.steps):
+            step_mesh()
+        m.join_streams()
+        c1.record(stream)
+        m.synchronize()
+        mms = c0.elapsed_time(c1)
+        st = m.mesh_layer().arena_stats()
+        sizes = m.mesh_layer().block_sizes(m.mesh_layer().get_all_block_indices())
+        with_mesh = {"value": F * args.steps / (mms * 1e-3), "unit": "frames/s", "ms_per_step": mms / args.steps,
+                     "mesh_ms_per_frame": (mms / args.steps - ms_max / args.steps) / F,
+                     "gpu_launches": int(m.kernel_launches() - l0), "mesh_blocks": int(len(sizes)),
+                     "vertices": int(np.maximum(sizes[:, 0], 0).sum()), "triangles": int(np.maximum(sizes[:, 1], 0).sum() // 3),
+                     "arena_vertices": int(st["capacity"]),
+                     "workload": "the same sequence with Mapper::updateColorMesh after every depth frame (TSDF + ESDF + incremental "
+                                 "mesh, welded); mesh_ms_per_frame = extra wall time per frame over the TSDF+ESDF step, including "
+                                 "the one host read-back each mesh update makes"}
+
     # ---- per-stage device time + algorithmic bytes for the roofline (rank 0, one extra step) ----
     roofline, stages_out, map_stats = None, None, None
     if rank == 0:
@@ -606,6 +639,13 @@ def main():
             step_device(merge=False)  # rank 0 only: no collective here
             m.synchronize()
             parity_ok, parity = parity_check(m, omap, wl.occupancy)
+            if with_mesh is not None:
+                # the mesh of the final map, GPU vs oracle: same blocks, same vertex / normal / index arrays
+                m.update_mesh(update_full_layer=True)
+                omap.integrate_mesh()
+                gm, om = m.mesh_layer().as_dict(), omap.mesh_layer()
+                with_mesh["parity_checked"] = bool(set(gm) == set(om) and all(
+                    np.array_equal(gm[k][f], om[k][f]) for k in om for f in ("vertices", "normals", "triangles")))
         del omap
 
     if rank == 0:
@@ -632,7 +672,7 @@ def main():
                        "map": map_stats},
             "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages_out,
-            "cpu_baseline": cpu, "with_color": with_color, "merge": merge_info,
+            "cpu_baseline": cpu, "with_color": with_color, "with_mesh": with_mesh, "merge": merge_info,
             "parity_checked": parity_ok, "parity": parity,
         }
         print(json.dumps(out))

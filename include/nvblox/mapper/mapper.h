@@ -17,6 +17,7 @@
 #include "nvblox/integrators/weighting_function.h"
 #include "nvblox/geometry/plane.h"
 #include "nvblox/map/layer.h"
+#include "nvblox/mesh/mesh_integrator.h"
 #include "nvblox/sensors/camera.h"
 #include "nvblox/sensors/image.h"
 #include "nvblox_b200.h"
@@ -53,6 +54,7 @@ struct OccupancyIntegratorParams {
   float unobserved_region_occupancy_probability = 0.5f, occupied_region_half_width_m = 0.1f;
 };
 struct MapperParams {
+  MeshIntegratorParams mesh_integrator_params;  // mapper_params.h:54
   bool do_depth_preprocessing = false;          // mapper_params.h:33-37
   int depth_preprocessing_num_dilations = 4;    // mapper_params.h:39-42
   EsdfIntegratorParams esdf_integrator_params;
@@ -352,6 +354,8 @@ class Mapper {
   // Mapper::setMapperParams (mapper/mapper.h:131): the members of MapperParams this path consumes
   void setMapperParams(const MapperParams& p) {
     do_depth_preprocessing(p.do_depth_preprocessing);
+    color_mesh_integrator().min_weight(p.mesh_integrator_params.mesh_integrator_min_weight);
+    color_mesh_integrator().weld_vertices(p.mesh_integrator_params.mesh_integrator_weld_vertices);
     depth_preprocessing_num_dilations(p.depth_preprocessing_num_dilations);
     auto ti = tsdf_integrator();
     ti.max_integration_distance_m(p.projective_integrator_params.projective_integrator_max_integration_distance_m);
@@ -413,6 +417,12 @@ class Mapper {
                        "integrateColor", nvb_last_error());
   }
   ColorLayer color_layer() const { return ColorLayer(m_, NVB_LAYER_COLOR); }
+  // Mapper::color_mesh_layer / color_mesh_integrator / updateColorMesh (mapper.h; src/mapper/mapper.cpp:371-406)
+  ColorMeshLayer color_mesh_layer() const { return ColorMeshLayer(m_); }
+  ColorMeshIntegrator color_mesh_integrator() const { return ColorMeshIntegrator(m_); }
+  void updateColorMesh(UpdateFullLayer full = UpdateFullLayer::kNo) {
+    b200_detail::check(nvb_mapper_update_mesh(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateColorMesh", nvb_last_error());
+  }
   ProjectiveColorIntegrator color_integrator() const { return ProjectiveColorIntegrator(m_); }
   void updateEsdf(UpdateFullLayer full = UpdateFullLayer::kNo) {
     b200_detail::check(nvb_mapper_update_esdf(m_, full == UpdateFullLayer::kYes ? 1 : 0), "updateEsdf", nvb_last_error());
