@@ -447,6 +447,12 @@ NVB_API int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n
 NVB_API int32_t nvb_mapper_set_cache_last_viewpoint(NvbMapper* m, int32_t enable);
 NVB_API int32_t nvb_mapper_get_cache_last_viewpoint(const NvbMapper* m);
 
+/* Scheduling knob with no counterpart in the reference: the cooperative ESDF wavefront launches num_SMs - reserved_sms CTAs
+ * (default 2), leaving room for the kernels that run concurrently with it -- the next frame's raycast / TSDF chain and, on
+ * a multi-GPU rank, the NCCL all-gather of the block-list merge (4 there). Results do not depend on it. */
+NVB_API int32_t nvb_mapper_set_esdf_reserved_sms(NvbMapper* m, int32_t reserved_sms);
+NVB_API int32_t nvb_mapper_get_esdf_reserved_sms(const NvbMapper* m);
+
 /* ---- Mesh (C/include/nvblox/mesh/mesh_integrator.h:39-162, C/src/mesh/mesh_integrator.cu,
  * C/src/mesh/mesh_integrator_appearance.cu). The mesh layer holds, per VoxelBlock that has triangles, vertices (3 floats),
  * flat per-vertex normals (3 floats), triangle indices into the block's vertices (triplets) and -- after a colour update --

@@ -66,6 +66,7 @@ struct NvbMapper {
   // (ProjectiveLayerType, mapper/mapper.h:52-53).
   int projective_layer_type = 0;
   int esdf_persistent = 1;
+  int esdf_reserved_sms = 2;  // SMs the exchange-slab wavefront leaves to concurrently running kernels (nvb_esdf_wavex.cu)
 
   DevLayer tsdf{}, esdf{};
   DevLayer freespace{};    // FreespaceLayer of a NVB_PROJECTIVE_TSDF_WITH_FREESPACE mapper
@@ -100,6 +101,9 @@ struct NvbMapper {
   // few KB on the device): a hit skips the raycast and replays the compaction + allocation, which yields the same list in the
   // same order and re-allocates blocks that were deallocated in between, like allocateBlocksWhereRequired does in the reference.
   BlockTensorMap tsdf_tmap;  // TMA descriptor of the TSDF slab (nvb_tsdf.cu)
+  int4* union_list = nullptr;  // nvb_blocks_union's own output list
+  int* union_list_count = nullptr;
+  int union_list_cap = 0;
 
   // Mesh layer (nvb_mesh.cu): header slab + one arena for vertices / normals / triangle indices / colours
   DevLayer mesh{};
@@ -165,6 +169,7 @@ struct NvbMapper {
   int* esdf_ints = nullptr;  // small counters block
   int* upd_list = nullptr;
   int* clr_list = nullptr;
+  int* clr_cand = nullptr;  // candidates of the clear pass that survive the pruning (select kernel -> process kernel)
   int* cleared_list = nullptr;
   int* ring_a = nullptr;
   int* ring_b = nullptr;
@@ -333,6 +338,7 @@ int allocEsdfScratch(NvbMapper* m, int old_cap, int cap) {
   if ((rc = reallocCopy(&m->work, 0, (size_t)cap, false, m->stream))) return rc;
   if ((rc = reallocCopy(&m->upd_list, 0, (size_t)cap, false, m->stream))) return rc;
   if ((rc = reallocCopy(&m->clr_list, 0, (size_t)cap, false, m->stream))) return rc;
+  if ((rc = reallocCopy(&m->clr_cand, 0, (size_t)cap, false, m->stream))) return rc;
   if ((rc = reallocCopy(&m->cleared_list, (size_t)old_cap, (size_t)cap, true, m->stream))) return rc;
   if ((rc = reallocCopy(&m->ring_a, 0, (size_t)cap, false, m->stream))) return rc;
   if ((rc = reallocCopy(&m->ring_b, 0, (size_t)cap, false, m->stream))) return rc;
@@ -408,7 +414,7 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
-       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kColorWorkCount = 31, kXTail = 32, kTodoMeshCount = 36, kNumInts = 40 };
+       kTodoCount = 15, kFrameCount = 16, kError = 17, kClearedSeq = 18, kTailState = 20, kDeadCount = 22, kDeadClearedCount = 23, kGesCounts = 24, kTodoFsCount = 28, kFsWorkCount = 29, kColsCount = 30, kColorWorkCount = 31, kXTail = 32, kTodoMeshCount = 36, kClrCandCount = 37, kNumInts = 40 };
 
 float logOddsFromProbability(float p);
 
@@ -421,6 +427,7 @@ EsdfCtx makeEsdfCtx(NvbMapper* m) {
   c.work_count = m->esdf_ints + kWorkCount;
   c.upd_list = m->upd_list, c.upd_count = m->esdf_ints + kUpdCount;
   c.clr_list = m->clr_list, c.clr_count = m->esdf_ints + kClrCount;
+  c.clr_cand = m->clr_cand, c.clr_cand_count = m->esdf_ints + kClrCandCount;
   c.clr_aabb = m->esdf_ints + kClrAabb;
   c.cleared_list = m->cleared_list, c.cleared_count = m->esdf_ints + kClearedCount;
   c.ring_a = m->ring_a, c.ring_b = m->ring_b;
@@ -670,6 +677,20 @@ int checkDeviceError(NvbMapper* m) {
     cudaStreamSynchronize(m->stream);
     if (err & 2) return fail(NVB_ERR_INDEX_RANGE, "a block index does not fit the 21-bit hash key");
     if (err & 4) return fail(NVB_ERR_CAPACITY, "a block-list segment of the multi-GPU merge overflowed (nvb_mapper_append_frame_blocks)");
+    // Roll the overflow back: find-or-insert left the keys it could not serve in the hash (value -1) and the fill level
+    // above the capacity. Clamp the level and rebuild the hashes from the live slots, so that the same indices can be
+    // allocated again once the caller has made room (or after the next growth).
+    syncAll(m);
+    DevLayer* layers[] = {&m->tsdf, &m->esdf, &m->freespace, &m->color, &m->mesh};
+    for (DevLayer* L : layers) {
+      if (!L->blocks) continue;
+      int count = 0;
+      if (cudaMemcpy(&count, L->count, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || count <= L->capacity) continue;
+      cudaMemcpyAsync(L->count, &L->capacity, sizeof(int), cudaMemcpyHostToDevice, m->stream);
+      launchFillU64(L->hash.keys, kEmptyKey, (size_t)L->hash.mask + 1, m->stream);
+      launchRehash(*L, L->capacity, m->stream);
+      cudaStreamSynchronize(m->stream);
+    }
     return fail(NVB_ERR_CAPACITY, "a layer slab overflowed on the device");
   }
   return NVB_OK;
@@ -1029,11 +1050,10 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
     NVB_CUDA(cudaEventRecord(m->mark_done, es));
     NVB_CUDA(cudaStreamWaitEvent(m->stream, m->mark_done, 0));
     beginStageOn(m, 4, es);
-    launchEsdfClear(c, m->esdf.capacity, m->num_sms, es);
-    m->launches++;
+    m->launches += launchEsdfClear(c, m->esdf.capacity, m->num_sms, es);
     endStageOn(m, es);
     beginStageOn(m, 5, es);
-    e = m->esdf_persistent == 3   ? launchEsdfComputeX(c, m->num_sms, es, &launches)
+    e = m->esdf_persistent == 3   ? launchEsdfComputeX(c, m->num_sms, m->esdf_reserved_sms, es, &launches)
         : m->esdf_persistent == 2 ? launchEsdfComputeGes(c, m->num_sms, es, &launches)
                                   : launchEsdfComputePersistent(c, m->num_sms, es, &launches);
     endStageOn(m, es);
@@ -1047,8 +1067,7 @@ int enqueueEsdf(NvbMapper* m, const int* in_xyz_dev, int n_explicit, bool from_t
     allocAndMark(m->stream);
     endStage(m);
     beginStage(m, 4);
-    launchEsdfClear(c, m->esdf.capacity, m->num_sms, m->stream);
-    m->launches++;
+    m->launches += launchEsdfClear(c, m->esdf.capacity, m->num_sms, m->stream);
     endStage(m);
     beginStage(m, 5);
     e = runEsdfComputeHostLoop(c, m->num_sms, m->stream, &launches);
@@ -1115,20 +1134,9 @@ void nvb_default_occupancy_params(NvbOccupancyParams* p) {
   p->occupied_region_half_width_m = 0.1f;
 }
 
-int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
-  if (!opts || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
-  if (!(opts->voxel_size_m > 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "voxel_size_m must be > 0");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    return fail(NVB_ERR_NO_DEVICE, "no CUDA device: the depth-integration path has no CPU fallback");
-  }
-  if (opts->device < 0 || opts->device >= ndev) return fail(NVB_ERR_INVALID_ARGUMENT, "bad device ordinal");
-  if (opts->projective_layer_type != NVB_PROJECTIVE_TSDF && opts->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY &&
-      opts->projective_layer_type != NVB_PROJECTIVE_TSDF_WITH_FREESPACE)
-    return fail(NVB_ERR_INVALID_ARGUMENT, "unknown projective_layer_type");
-  NVB_CUDA(cudaSetDevice(opts->device));
-  NvbMapper* m = new NvbMapper();
+// Everything nvb_mapper_create allocates, on an already constructed object (so that a failure half way can be undone
+// by nvb_mapper_destroy).
+static int createMapperResources(const NvbMapperOptions* opts, NvbMapper* m) {
   m->device = opts->device;
   cudaDeviceProp prop;
   NVB_CUDA(cudaGetDeviceProperties(&prop, opts->device));
@@ -1148,6 +1156,7 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
   m->esdf_persistent = opts->esdf_persistent;
   // A/B switch for measurements: 0 host loop, 1 four-phase wavefront, 2 gather-emulate-sweep wavefront
   if (const char* e = getenv("NVB_ESDF_MODE")) m->esdf_persistent = atoi(e);
+  if (const char* e = getenv("NVB_WAVEX_RESERVED_SMS")) m->esdf_reserved_sms = std::max(0, std::min(64, atoi(e)));
   if (const char* e = getenv("NVB_GES_SWITCH")) m->ges_switch = atoi(e);
   {
     const char* e = getenv("NVB_CLEAR_PRUNE");
@@ -1207,6 +1216,33 @@ int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
     NVB_CUDA(cudaEventCreateWithFlags(&m->stage_consumed[k], cudaEventDisableTiming));
   }
   NVB_CUDA(syncAll(m));
+  return NVB_OK;
+}
+
+int32_t nvb_mapper_create(const NvbMapperOptions* opts, NvbMapper** out) {
+  if (!opts || !out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (!(opts->voxel_size_m > 0.0f)) return fail(NVB_ERR_INVALID_ARGUMENT, "voxel_size_m must be > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(NVB_ERR_NO_DEVICE, "no CUDA device: the depth-integration path has no CPU fallback");
+  }
+  if (opts->device < 0 || opts->device >= ndev) return fail(NVB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+  if (opts->projective_layer_type != NVB_PROJECTIVE_TSDF && opts->projective_layer_type != NVB_PROJECTIVE_OCCUPANCY &&
+      opts->projective_layer_type != NVB_PROJECTIVE_TSDF_WITH_FREESPACE)
+    return fail(NVB_ERR_INVALID_ARGUMENT, "unknown projective_layer_type");
+  NVB_CUDA(cudaSetDevice(opts->device));
+  NvbMapper* m = new NvbMapper();
+  const int rc = createMapperResources(opts, m);
+  if (rc != NVB_OK) {
+    // no leak on a failed create: the partial object goes through the normal destructor (null handles are skipped by
+    // the CUDA runtime with an error code that is cleared here; the message of the original failure is kept)
+    const std::string why = g_last_error;
+    nvb_mapper_destroy(m);
+    cudaGetLastError();
+    g_last_error = why;
+    return rc;
+  }
   *out = m;
   return NVB_OK;
 }
@@ -1230,13 +1266,14 @@ void nvb_mapper_destroy(NvbMapper* m) {
     cudaEventDestroy(m->stage_copied[k]), cudaEventDestroy(m->stage_consumed[k]);
   }
   cudaFree(m->dirty), cudaFree(m->todo_slots);
-  cudaFree(m->work), cudaFree(m->esdf_ints), cudaFree(m->upd_list), cudaFree(m->clr_list), cudaFree(m->cleared_list);
+  cudaFree(m->work), cudaFree(m->esdf_ints), cudaFree(m->upd_list), cudaFree(m->clr_list), cudaFree(m->clr_cand), cudaFree(m->cleared_list);
   cudaFree(m->ring_a), cudaFree(m->ring_b), cudaFree(m->stamp_a), cudaFree(m->stamp_b);
   cudaFree(m->nbr), cudaFree(m->seed_upd), cudaFree(m->seed_clr), cudaFree(m->psum);
   cudaFree(m->nbr27), cudaFree(m->shadow), cudaFree(m->cand_stamp), cudaFree(m->cand_a), cudaFree(m->cand_b);
   cudaFree(m->xslab), cudaFree(m->xrec), cudaFree(m->xcounts);
   cudaFree(m->dead), cudaFree(m->skip_stamp), cudaFree(m->dead_cleared_xyz), cudaFree(m->last_depth);
   cudaFree(m->pre_depth);
+  cudaFree(m->union_list), cudaFree(m->union_list_count);
   if (m->mesh.blocks) freeLayer(&m->mesh);
   cudaFree(m->mesh_v), cudaFree(m->mesh_n), cudaFree(m->mesh_t), cudaFree(m->mesh_c), cudaFree(m->mesh_state);
   cudaFree(m->mesh_counts), cudaFree(m->mesh_offsets), cudaFree(m->mesh_xyz_dev), cudaFree(m->dirty_mesh), cudaFree(m->todo_mesh_slots);
@@ -2263,13 +2300,26 @@ int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n, const 
   g.linear_size = (int)(sx * sy * sz);
   g.num_words = (g.linear_size + 31) / 32;
   int rc;
-  if ((rc = ensureFrameScratch(m, g))) return rc;
+  // the union has its own list: the last frame's block list (nvb_mapper_last_frame_blocks) survives a merge
+  ViewGrid scratch = g;
+  scratch.linear_size = 0;  // bitset + tile state only
+  if ((rc = ensureFrameScratch(m, scratch))) return rc;
+  const int need = std::min(n, g.linear_size);
+  if (need > m->union_list_cap) {
+    NVB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->union_list) cudaFree(m->union_list);
+    m->union_list = nullptr, m->union_list_cap = 0;
+    const int cap2 = (int)std::min<long long>((long long)(1.5 * need) + 64, 0x7fffffff);
+    NVB_CUDA(cudaMalloc(&m->union_list, (size_t)cap2 * sizeof(int4)));
+    m->union_list_cap = cap2;
+  }
+  if (!m->union_list_count) NVB_CUDA(cudaMalloc(&m->union_list_count, sizeof(int)));
   launchMarkList(xyz_dev, n, g, m->bits, m->stream);
   CompactArgs ca{};
   ca.bits = m->bits;
   ca.grid = g;
-  ca.frame_blocks = m->frame_blocks;
-  ca.frame_count = m->frame_count;
+  ca.frame_blocks = m->union_list;
+  ca.frame_count = m->union_list_count;
   ca.tile_state = m->tile_state;
   ca.ticket = m->ticket;
   ca.ticket_base = m->ticket_base;
@@ -2280,10 +2330,10 @@ int32_t nvb_blocks_union(NvbMapper* m, const int32_t* xyz_dev, int32_t n, const 
   launchCompactAllocate(ca, m->stream);
   if (compactUsesTickets(g)) m->ticket_base += (unsigned int)compactNumTiles(g);
   launchClearBits(m->bits, g.num_words, m->stream);
-  if (out_xyz_dev && cap > 0) launchUnpackList(m->frame_blocks, m->frame_count, out_xyz_dev, cap, m->stream);
+  if (out_xyz_dev && cap > 0) launchUnpackList(m->union_list, m->union_list_count, out_xyz_dev, cap, m->stream);
   m->launches += 4;
   if (out_count_host) {
-    NVB_CUDA(cudaMemcpyAsync(m->h_ints, m->frame_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    NVB_CUDA(cudaMemcpyAsync(m->h_ints, m->union_list_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     NVB_CUDA(cudaStreamSynchronize(m->stream));
     *out_count_host = m->h_ints[0];
   }
@@ -2339,6 +2389,14 @@ int32_t nvb_mapper_set_cache_last_viewpoint(NvbMapper* m, int32_t enable) {
   return NVB_OK;
 }
 int32_t nvb_mapper_get_cache_last_viewpoint(const NvbMapper* m) { return m ? m->cache_last_viewpoint : 0; }
+
+int32_t nvb_mapper_set_esdf_reserved_sms(NvbMapper* m, int32_t reserved_sms) {
+  if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
+  if (reserved_sms < 0 || reserved_sms > 64) return fail(NVB_ERR_INVALID_ARGUMENT, "reserved_sms must be in [0, 64]");
+  m->esdf_reserved_sms = reserved_sms;
+  return NVB_OK;
+}
+int32_t nvb_mapper_get_esdf_reserved_sms(const NvbMapper* m) { return m ? m->esdf_reserved_sms : 0; }
 
 int32_t nvb_mapper_set_depth_preprocessing(NvbMapper* m, int32_t enable, int32_t num_dilations) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");

@@ -49,6 +49,7 @@ __global__ void esdfAllocateKernel(EsdfCtx c, const int* in_xyz, const int* in_s
     *c.work_count = n;
     *c.upd_count = 0;
     *c.clr_count = 0;
+    if (c.clr_cand_count) *c.clr_cand_count = 0;
     c.clr_aabb[0] = c.clr_aabb[1] = c.clr_aabb[2] = INT32_MAX;
     c.clr_aabb[3] = c.clr_aabb[4] = c.clr_aabb[5] = INT32_MIN;
     c.ring_count[0] = c.ring_count[1] = 0;
@@ -519,7 +520,12 @@ __device__ __forceinline__ void clearPrefetch(const EsdfCtx& c, unsigned int* sb
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
+// kMode 0: selection and candidate processing in one kernel (a CTA reads the candidates among its own slots: their number
+//         per CTA is Poisson-distributed, ~2 on average and 7-8 on the unluckiest of 1184 CTAs, which sets the kernel's time);
+// kMode 1: selection only -- survivors go to the global candidate list (one atomicAdd per CTA, few large CTAs' worth of slots);
+// kMode 2: processing only -- CTA b takes entries b, b + grid, ... of that list, so every CTA reads ceil(n / grid) blocks.
+template <int kMode>
+__global__ void __launch_bounds__(kThreads) esdfClearKernelT(EsdfCtx c) {
   __shared__ __align__(16) unsigned int s_blk[2][kBlockWords];
   __shared__ int s_nb[2][32];
   __shared__ int s_cand[kClearMaxCand];
@@ -545,12 +551,22 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
   long long ncand_total = 0, nread_total = 0;
   // Slots are dealt round-robin over the CTAs (recently allocated = high slots are the likely candidates);
   // one selection round tests 256 of this CTA's slots at once, one thread per slot.
-  for (long long first = blockIdx.x; first < nblocks; first += (long long)gridDim.x * kThreads) {
+  const long long nwork = kMode == 2 ? (long long)*(volatile int*)c.clr_cand_count : (long long)nblocks;
+  // (the select kernel takes 256 CONSECUTIVE slots per CTA: few CTAs have work, so few of them queue at the list's counter)
+  for (long long first = kMode == 1 ? (long long)blockIdx.x * kThreads : (long long)blockIdx.x; first < nwork;
+       first += (long long)gridDim.x * kThreads) {
     if (tid == 0) s_ncand = 0, s_ndone = 0;
     __syncthreads();
-    const long long slot_ll = first + (long long)tid * gridDim.x;
+    const long long slot_ll = kMode == 1 ? first + tid : first + (long long)tid * gridDim.x;
     bool is_cand = false, ref_cand = false;
-    if (slot_ll < nblocks && c.esdf.block_index[3 * slot_ll] != kDeadSlotX) {
+    if (kMode == 2) {
+      // this CTA's share of the global candidate list, up to 256 entries per round
+      if (slot_ll < nwork) s_cand[tid] = __ldcg(c.clr_cand + slot_ll);
+      if (tid == 0) {
+        const long long mine = (nwork - first + gridDim.x - 1) / gridDim.x;
+        s_ncand = (int)(mine < kThreads ? mine : kThreads);
+      }
+    } else if (slot_ll < nblocks && c.esdf.block_index[3 * slot_ll] != kDeadSlotX) {
       const int* bi = c.esdf.block_index + 3 * slot_ll;
       const int b3[3] = {bi[0], bi[1], bi[2]};
       // AlignedBox::exteriorDistance(box) > radius -> skip
@@ -606,16 +622,27 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernel(EsdfCtx c) {
       ref_cand = ref_cand || is_cand;
     }
     // (the statistics count the reference's candidates; `is_cand` decides what is read)
-    const unsigned int ref_ballot = __ballot_sync(0xffffffffu, ref_cand);
-    const unsigned int ballot = __ballot_sync(0xffffffffu, is_cand);
-    int wbase = 0;
-    if (lane == 0 && ballot) wbase = atomicAdd(&s_ncand, __popc(ballot));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (is_cand) s_cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = (int)slot_ll;
-    if (lane == 0) ncand_total += __popc(ref_ballot);
+    if (kMode != 2) {
+      const unsigned int ref_ballot = __ballot_sync(0xffffffffu, ref_cand);
+      const unsigned int ballot = __ballot_sync(0xffffffffu, is_cand);
+      int wbase = 0;
+      if (lane == 0 && ballot) wbase = atomicAdd(&s_ncand, __popc(ballot));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (is_cand) s_cand[wbase + __popc(ballot & ((1u << lane) - 1u))] = (int)slot_ll;
+      if (lane == 0) ncand_total += __popc(ref_ballot);
+    }
     __syncthreads();
     const int ncand = s_ncand;
-    if (tid == 0) nread_total += ncand;
+    if (tid == 0 && kMode != 2) nread_total += ncand;
+    if (kMode == 1) {
+      // hand the survivors to the global list
+      __shared__ int s_gbase;
+      if (tid == 0 && ncand) s_gbase = atomicAdd(c.clr_cand_count, ncand);
+      __syncthreads();
+      for (int i = tid; i < ncand; i += kThreads) c.clr_cand[s_gbase + i] = s_cand[i];
+      __syncthreads();
+      continue;
+    }
     // Candidates one after the other; the next one's block and neighbour row are already on their way.
     if (ncand > 0) clearPrefetch(c, s_blk[0], s_nb[0], s_cand[0], tid);
     for (int i = 0; i < ncand; i++) {
@@ -1031,6 +1058,7 @@ __global__ void esdfSliceAllocateKernel(EsdfCtx c) {
     *c.work_count = n;
     *c.upd_count = 0;
     *c.clr_count = 0;
+    if (c.clr_cand_count) *c.clr_cand_count = 0;
     c.clr_aabb[0] = c.clr_aabb[1] = c.clr_aabb[2] = INT32_MAX;
     c.clr_aabb[3] = c.clr_aabb[4] = c.clr_aabb[5] = INT32_MIN;
     c.ring_count[0] = c.ring_count[1] = 0;
@@ -1247,11 +1275,32 @@ void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t
   esdfMarkKernel<<<cappedGrid(grid), kThreads, 0, stream>>>(c);
 }
 
-void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream) {
+// NVB_CLEAR_SPLIT=1: selection and processing as two kernels with a balanced candidate list in between (A/B switch; both
+// paths are parity-tested). Measured on the 80-frame C2 bench (profiles/r2_run10.sh): fused 24.2 us per frame, split 29.0 us --
+// the imbalance of the fused kernel's per-CTA candidate counts costs less than the second launch, so the default stays fused.
+static bool clearSplit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NVB_CLEAR_SPLIT");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v != 0;
+}
+int launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream) {
   int grid = num_sms * 8;
   if (esdf_count_upper < grid) grid = esdf_count_upper;
   if (grid < 1) grid = 1;
-  esdfClearKernel<<<cappedGrid(grid), kThreads, 0, stream>>>(c);
+  if (clearSplit() && c.clr_cand != nullptr) {
+    // selection: one slot per thread, one global atomicAdd per CTA -> CTAs of 256 slots; processing: balanced
+    int sgrid = (esdf_count_upper + kThreads - 1) / kThreads;
+    if (sgrid > num_sms * 8) sgrid = num_sms * 8;
+    if (sgrid < 1) sgrid = 1;
+    esdfClearKernelT<1><<<cappedGrid(sgrid), kThreads, 0, stream>>>(c);
+    esdfClearKernelT<2><<<cappedGrid(grid), kThreads, 0, stream>>>(c);
+    return 2;
+  }
+  esdfClearKernelT<0><<<cappedGrid(grid), kThreads, 0, stream>>>(c);
+  return 1;
 }
 
 // One launch per phase; the host reads the ring's block count after every ring,

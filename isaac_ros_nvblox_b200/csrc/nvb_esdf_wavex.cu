@@ -38,6 +38,8 @@
 //   * 512-thread CTAs = 8 groups per SM x 148 SMs: 1 184 candidates in flight at once.
 #include "nvb_esdf_wave_common.cuh"
 
+#include <cstdlib>
+
 namespace nvb {
 
 namespace {
@@ -832,7 +834,7 @@ __global__ void __maxnreg__(NVB_WAVEX_MAXREG) esdfWaveXKernel(EsdfCtx c) {
 int esdfWaveXMaxCtas() { return kMaxCtas; }
 size_t esdfWaveXFlagBytes() { return 2 * (size_t)kMaxCtas * sizeof(int2); }
 
-cudaError_t launchEsdfComputeX(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches) {
+cudaError_t launchEsdfComputeX(const EsdfCtx& c, int num_sms, int reserved_sms, cudaStream_t stream, int* launches) {
   static int per_sm = -1;
   if (per_sm < 0) {
     cudaFuncSetAttribute(esdfWaveXKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmemBytes);
@@ -844,7 +846,13 @@ cudaError_t launchEsdfComputeX(const EsdfCtx& c, int num_sms, cudaStream_t strea
   EsdfCtx cc = c;
   void* args[] = {&cc};
   (*launches)++;
-  const int grid = num_sms < kMaxCtas ? num_sms : kMaxCtas;
+  // `reserved_sms` SMs are left to the other resident kernels: the raycast / compaction / TSDF kernels of the next frame then
+  // run there instead of stealing issue slots from ring-critical CTAs (measured on the 80-frame C2 bench,
+  // profiles/r2_run9.sh: 0 / 2 / 4 / 8 / 16 reserved -> 3069 / 3213 / 3194 / 3198 / 3151 frames/s), and a multi-GPU
+  // rank's NCCL all-gather can start -- and wait for its peers -- while a wavefront is in flight (a cooperative grid
+  // that fills every SM serialises the two: 0.30 ms per merge with 0 reserved, 0.10 ms with 4, profiles/r2_run8.sh).
+  int grid = num_sms < kMaxCtas ? num_sms : kMaxCtas;
+  if (reserved_sms > 0 && grid - reserved_sms >= 8) grid -= reserved_sms;
   return cudaLaunchCooperativeKernel((const void*)esdfWaveXKernel, dim3(grid), dim3(kXT), args, kXSmemBytes, stream);
 }
 

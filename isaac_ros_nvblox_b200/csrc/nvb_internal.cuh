@@ -391,6 +391,8 @@ struct EsdfCtx {
   unsigned int* psum; // two words per slot (the two halves of the block, x < 4 and x >= 4): 0 = no voxel has a parent; bit 31 set: box of the BLOCK OFFSETS the voxels' parents
                       // point into, 5 bits per bound (lo x, hi x, lo y, hi y, lo z, hi z, each + 16); 0xffffffff = unknown.
                       // An upper bound kept by the exchange-slab wavefront (the only writer of non-zero parents in that mode).
+  int* clr_cand;        // clear pass: candidates that survive the pruning, and their count
+  int* clr_cand_count;
   unsigned int* clr_bits;  // bitmap of the to-clear blocks over their AABB (2048 words), built by the mark kernel's last CTA
   int prune;          // clear pass: skip candidates whose parent box holds no to-clear block (exact: a voxel is cleared iff its
                       // parent voxel lost its site flag, and sites are only lost in to-clear blocks)
@@ -418,11 +420,11 @@ void launchEsdfSliceAllocateAndMark(const EsdfCtx& c, const int* in_xyz, const i
 void launchEsdfAllocate(const EsdfCtx& c, const int* in_xyz, const int* in_slots, const int* in_count_dev,
                         int in_count_upper, cudaStream_t stream);
 void launchEsdfMark(const EsdfCtx& c, int count_upper, int num_sms, cudaStream_t stream);
-void launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream);
+int launchEsdfClear(const EsdfCtx& c, int esdf_count_upper, int num_sms, cudaStream_t stream);  // returns the number of launches
 // Whole wavefront (both computeEsdf calls) in one cooperative launch. Returns cudaError.
 cudaError_t launchEsdfComputeGes(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
 cudaError_t launchEsdfComputePersistent(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);
-cudaError_t launchEsdfComputeX(const EsdfCtx& c, int num_sms, cudaStream_t stream, int* launches);  // nvb_esdf_wavex.cu
+cudaError_t launchEsdfComputeX(const EsdfCtx& c, int num_sms, int reserved_sms, cudaStream_t stream, int* launches);  // nvb_esdf_wavex.cu
 int esdfWaveXMaxCtas();
 size_t esdfWaveXFlagBytes();
 // Reference-like driver: one launch per phase, host reads the ring counter.

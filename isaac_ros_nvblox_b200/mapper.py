@@ -716,6 +716,12 @@ class Mapper:
     def cuda_stream(self):
         return self._L.nvb_mapper_stream(self._h)
 
+    def esdf_reserved_sms(self, v=None):
+        """SMs the ESDF wavefront leaves to concurrently running kernels (default 2; 4 on a multi-GPU rank that merges)."""
+        if v is not None:
+            check(self._L.nvb_mapper_set_esdf_reserved_sms(self._h, int(v)))
+        return int(self._L.nvb_mapper_get_esdf_reserved_sms(self._h))
+
     def do_depth_preprocessing(self, v=None):
         """Mapper::do_depth_preprocessing (mapper.h; mapper_params.h:33-37, default off)."""
         en, n = C.c_int32(0), C.c_int32(0)

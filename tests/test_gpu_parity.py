@@ -410,7 +410,8 @@ def test_esdf_small_grids_exercise_multi_round_paths(gpu, mark_tma):
         m.close()
         print("ok")
     """) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    env = dict(os.environ, NVB_ESDF_GRID_CAP="3", NVB_MARK_TMA=mark_tma)
+    # (the second variant also runs the clear pass as two kernels, select + balanced process: NVB_CLEAR_SPLIT=1)
+    env = dict(os.environ, NVB_ESDF_GRID_CAP="3", NVB_MARK_TMA=mark_tma, NVB_CLEAR_SPLIT="0" if mark_tma == "1" else "1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
