@@ -112,6 +112,11 @@ struct NvbMapper {
   int* mesh_t = nullptr;
   unsigned char* mesh_c = nullptr;
   long long mesh_arena_cap = 0;  // entries
+  float* mesh_alt_v = nullptr;   // the spare arena a repack moves the live segments into (then the two swap)
+  float* mesh_alt_n = nullptr;
+  int* mesh_alt_t = nullptr;
+  unsigned char* mesh_alt_c = nullptr;
+  long long mesh_alt_cap = 0;
   int* mesh_state = nullptr;     // kArena* ints
   int* mesh_counts = nullptr;
   int* mesh_offsets = nullptr;
@@ -1276,6 +1281,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->union_list), cudaFree(m->union_list_count);
   if (m->mesh.blocks) freeLayer(&m->mesh);
   cudaFree(m->mesh_v), cudaFree(m->mesh_n), cudaFree(m->mesh_t), cudaFree(m->mesh_c), cudaFree(m->mesh_state);
+  cudaFree(m->mesh_alt_v), cudaFree(m->mesh_alt_n), cudaFree(m->mesh_alt_t), cudaFree(m->mesh_alt_c);
   cudaFree(m->mesh_counts), cudaFree(m->mesh_offsets), cudaFree(m->mesh_xyz_dev), cudaFree(m->dirty_mesh), cudaFree(m->todo_mesh_slots);
   cudaFree(m->clr_bits), cudaFree(m->union_bits), cudaFree(m->union_state);
   cudaFree(m->vc_bits[0]), cudaFree(m->vc_bits[1]);
@@ -2711,26 +2717,32 @@ int repackMeshArena(NvbMapper* m, long long need) {
   NVB_CUDA(cudaStreamSynchronize(m->stream));
   long long live = 0;
   for (int i = 0; i < nslots; i++) o[i] = (int)live, live += h[i];
-  long long cap = std::max<long long>(m->mesh_arena_cap, 1 << 18);
-  while (cap < live + need) cap *= 2;
+  // at least half of the arena is free behind the live data after a repack: with an update re-emitting ~1/5 of the live
+  // vertices, that is several updates between repacks
+  long long cap = std::max<long long>(m->mesh_arena_cap, 1 << 20);
+  while (cap < 2 * (live + need)) cap *= 2;
   if (cap > 0x7fffffffll) {
     cudaFree(sizes), cudaFree(new_off);
     return fail(NVB_ERR_CAPACITY, "mesh arena beyond 2^31 vertices");
   }
-  float *v2 = nullptr, *n2 = nullptr;
-  int* t2 = nullptr;
-  unsigned char* c2 = nullptr;
-  NVB_CUDA(cudaMalloc(&v2, (size_t)cap * 12));
-  NVB_CUDA(cudaMalloc(&n2, (size_t)cap * 12));
-  NVB_CUDA(cudaMalloc(&t2, (size_t)cap * 4));
-  NVB_CUDA(cudaMalloc(&c2, (size_t)cap * 4));
+  // the spare arena of the previous repack is reused when it has the right size (no cudaMalloc in the steady state)
+  if (m->mesh_alt_cap != cap) {
+    cudaFree(m->mesh_alt_v), cudaFree(m->mesh_alt_n), cudaFree(m->mesh_alt_t), cudaFree(m->mesh_alt_c);
+    m->mesh_alt_v = m->mesh_alt_n = nullptr, m->mesh_alt_t = nullptr, m->mesh_alt_c = nullptr, m->mesh_alt_cap = 0;
+    NVB_CUDA(cudaMalloc(&m->mesh_alt_v, (size_t)cap * 12));
+    NVB_CUDA(cudaMalloc(&m->mesh_alt_n, (size_t)cap * 12));
+    NVB_CUDA(cudaMalloc(&m->mesh_alt_t, (size_t)cap * 4));
+    NVB_CUDA(cudaMalloc(&m->mesh_alt_c, (size_t)cap * 4));
+    m->mesh_alt_cap = cap;
+  }
   NVB_CUDA(cudaMemcpyAsync(new_off, o.data(), (size_t)nslots * sizeof(int), cudaMemcpyHostToDevice, m->stream));
-  if (m->mesh_v) launchMeshCompactMove(c, nslots, new_off, v2, n2, t2, c2, m->num_sms, m->stream);
+  if (m->mesh_v) launchMeshCompactMove(c, nslots, new_off, m->mesh_alt_v, m->mesh_alt_n, m->mesh_alt_t, m->mesh_alt_c, m->num_sms, m->stream);
   const int state[kArenaInts] = {(int)live, 0, (int)live, 0};
   NVB_CUDA(cudaMemcpyAsync(m->mesh_state, state, sizeof(state), cudaMemcpyHostToDevice, m->stream));
   NVB_CUDA(cudaStreamSynchronize(m->stream));
-  cudaFree(m->mesh_v), cudaFree(m->mesh_n), cudaFree(m->mesh_t), cudaFree(m->mesh_c), cudaFree(sizes), cudaFree(new_off);
-  m->mesh_v = v2, m->mesh_n = n2, m->mesh_t = t2, m->mesh_c = c2, m->mesh_arena_cap = cap;
+  cudaFree(sizes), cudaFree(new_off);
+  std::swap(m->mesh_v, m->mesh_alt_v), std::swap(m->mesh_n, m->mesh_alt_n), std::swap(m->mesh_t, m->mesh_alt_t);
+  std::swap(m->mesh_c, m->mesh_alt_c), std::swap(m->mesh_arena_cap, m->mesh_alt_cap);
   m->launches += 2;
   return NVB_OK;
 }

@@ -670,18 +670,14 @@ __global__ void __launch_bounds__(kThreads) esdfClearKernelT(EsdfCtx c) {
         if (flagObserved(fl) && !flagSite(fl) && (p[0] != 0 || p[1] != 0 || p[2] != 0)) {
           // getBlockAndVoxelIndexFromOffset (:1498-1520): C++ '/' and '%' truncate toward zero.
           const int vi[3] = {v >> 6, (v >> 3) & 7, v & 7};
+          // The reference splits p with truncating '/' and '%' and then carries nv back into [0, 8): the result is the floor
+          // division of vi + p by 8 (8 nb + nv = vi + p with 0 <= nv < 8 has one solution), i.e. a shift and a mask.
           int nb[3], nv[3];
 #pragma unroll
           for (int a = 0; a < 3; a++) {
-            nb[a] = p[a] / kVps;  // block offset (relative)
-            nv[a] = vi[a] + p[a] % kVps;
-            if (nv[a] >= kVps) {
-              nv[a] -= kVps;
-              nb[a]++;
-            } else if (nv[a] < 0) {
-              nv[a] += kVps;
-              nb[a]--;
-            }
+            const int q = vi[a] + p[a];
+            nb[a] = q >> 3;  // block offset (relative)
+            nv[a] = q & (kVps - 1);
           }
           const int pv = (nv[0] * kVps + nv[1]) * kVps + nv[2];
           bool parent_is_site = false;
