@@ -18,6 +18,7 @@ the NCCL merge of the ranks' updated-block lists (isaac_ros_nvblox_b200/multi_gp
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -225,7 +226,8 @@ def ncu_traffic_by_kernel():
             ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             for n in names:
-                vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if n + "(" in r[ik] or r[ik].endswith(n)]
+                pat = re.compile(re.escape(n) + r"T?(<[^>]*>)?(\(|$)")  # plain, templated (<0>) and ...KernelT<mode> instantiations
+                vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if pat.search(r[ik])]
                 if vals:
                     out[n] = sum(vals) / len(vals)
         except Exception:
@@ -370,6 +372,10 @@ def main():
         # rank 0 must print exactly one line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION) goes there too
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        # The only collective is the all-gather of a few hundred KB of block indices per batch: two NCCL channels are plenty,
+        # and their CTAs then fit the SMs the cooperative ESDF wavefront leaves free (BatchMerger reserves 4), so neither
+        # kernel has to wait for the other to drain (8 GPUs, profiles/r2_scale8_ab.sh: 3 007 -> 3 194 frames/s per GPU).
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = WORKLOADS[args.workload](args, rank, world)
