@@ -3,8 +3,9 @@
 #include "nvblox/core/unified_ptr.h"
 #include "nvblox/map/voxels.h"
 namespace nvblox {
-template <typename VoxelType>
+template <typename _VoxelType>
 struct VoxelBlock {
+  typedef _VoxelType VoxelType;
   static constexpr int kVoxelsPerSide = 8;
   static constexpr int kNumVoxels = 512;
   typedef unified_ptr<VoxelBlock> Ptr;             // map/blox.h:45

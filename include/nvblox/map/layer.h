@@ -12,6 +12,7 @@ class VoxelBlockLayer {
   using BlockType = VoxelBlock<VoxelType>;
   VoxelBlockLayer(NvbMapper* m, int layer_id) : m_(m), id_(layer_id) {}
   NvbMapper* mapper_handle() const { return m_; }  // (not in the reference: the layers here are views of a mapper's device map)
+  int layer_id() const { return id_; }
   float voxel_size() const { return nvb_mapper_voxel_size(m_); }
   float block_size() const { return nvb_mapper_block_size(m_); }
   MemoryType memory_type() const { return MemoryType::kDevice; }

@@ -79,7 +79,7 @@ def test_cpp_mirror_headers_compile_and_link(built, tmp_path):
     against the C-ABI library; without a GPU the program reports that and exits 77."""
     import subprocess
     from isaac_ros_nvblox_b200 import _lib
-    for name in ("test_mapper_dropin", "test_mirror_surface", "test_multi_mapper_dropin", "test_mesh_dropin"):  # the second covers Plane, planar slices and EsdfSlicer; the third MultiMapper + the reference's Mapper constructor
+    for name in ("test_mapper_dropin", "test_mirror_surface", "test_multi_mapper_dropin", "test_mesh_dropin", "test_streamer_dropin"):  # the second covers Plane, planar slices and EsdfSlicer; the third MultiMapper + the reference's Mapper constructor
         exe = _compile_cpp_dropin(tmp_path, name)
         if _lib.load().nvb_device_count() == 0:
             assert subprocess.call([exe]) == 77

@@ -552,7 +552,7 @@ def test_full_sequence_properties(gpu):
     m.close()
 
 
-@pytest.mark.parametrize("name,ok", [("test_mapper_dropin", "drop-in C++ API ok"), ("test_multi_mapper_dropin", "MultiMapper drop-in ok"), ("test_mesh_dropin", "mesh drop-in ok")])
+@pytest.mark.parametrize("name,ok", [("test_mapper_dropin", "drop-in C++ API ok"), ("test_multi_mapper_dropin", "MultiMapper drop-in ok"), ("test_mesh_dropin", "mesh drop-in ok"), ("test_streamer_dropin", "streamer drop-in ok")])
 def test_cpp_dropin_program(gpu, tmp_path, name, ok):
     """tests/cpp/*.cpp: the reference-style C++ tests through include/nvblox/ (Mapper with the reference's constructor
     signature, occupancy and freespace mappers, MultiMapper as nvblox_ros drives it)."""
