@@ -264,3 +264,29 @@ class LayerStreamerOldestBlocks(LayerStreamerBase):
         else:
             num_bytes = int(np.float32(bandwidth_limit_mbps) * np.float32(1.0 / rate) * np.float32(1e6 / 8.0))
         return self.get_n_bytes_of_serialized_blocks(num_bytes, layer, block_exclusion_params)
+
+
+class LayerCakeStreamer:
+    """LayerCakeStreamer (layer_cake_streamer.h:25-98): one LayerStreamerOldestBlocks per layer kind ("tsdf", "esdf", "mesh", ...)
+    behind one object; a request for a kind that was not added does nothing and returns None."""
+
+    def __init__(self, *kinds):
+        self._streamers = {}
+        for k in kinds:
+            self.add(k)
+
+    def add(self, kind):
+        self._streamers.setdefault(kind, LayerStreamerOldestBlocks())  # one of each kind at most
+
+    def get(self, kind):
+        return self._streamers.get(kind)
+
+    def estimate_bandwidth_and_serialize(self, kind, layer, blocks_to_serialize, block_exclusion_params=None, bandwidth_limit_mbps=-1.0,
+                                         now_s=None):
+        s = self._streamers.get(kind)
+        return None if s is None else s.estimate_bandwidth_and_serialize(layer, blocks_to_serialize, block_exclusion_params,
+                                                                         bandwidth_limit_mbps, now_s)
+
+    def serialize_all_blocks(self, kind, layer, block_indices):
+        s = self._streamers.get(kind)
+        return None if s is None else s.serialize_all_blocks(layer, block_indices)

@@ -112,6 +112,18 @@ int main() {
   EXPECT(!h1.empty() && !h2.empty() && h1.size() + h2.size() == mall.size() && ms.numCandidates() == 0);
   auto bw = ms.estimateBandwidthAndSerialize(mesh, mall, "mesh", BlockExclusionParams(), (int)kLayerStreamerUnlimitedBandwidth, CudaStreamOwning());
   EXPECT(bw->block_indices.size() == mall.size());
+  // LayerCakeStreamer (test_layer_cake_streamer.cpp): one streamer per layer type; a type that is not in the cake does nothing
+  LayerCakeStreamer cake = LayerCakeStreamer::create<TsdfLayer, ColorMeshLayer>();
+  EXPECT(cake.getPtr<TsdfLayer>() != nullptr && cake.getPtr<ColorMeshLayer>() != nullptr && cake.getPtr<EsdfLayer>() == nullptr);
+  auto c1 = cake.estimateBandwidthAndSerialize(tsdf, all, "tsdf", BlockExclusionParams(), (int)kLayerStreamerUnlimitedBandwidth, CudaStreamOwning());
+  EXPECT(c1 && c1->block_indices.size() == all.size() && c1->voxels.size() == all.size() * 512);
+  auto c2 = cake.serializeAllBlocks(mesh, mall, CudaStreamOwning());
+  EXPECT(c2 && c2->vertices.size() == sm->vertices.size());
+  EXPECT(cake.getSerializedLayer<ColorMeshLayer>() == c2);
+  EsdfLayer esdf = mapper.esdf_layer();
+  EXPECT(!cake.estimateBandwidthAndSerialize(esdf, all, "esdf", BlockExclusionParams(), -1, CudaStreamOwning()));
+  cake.add<TsdfLayer>();  // already there: ignored
+  EXPECT(cake.get<TsdfLayer>().numCandidates() == 0);
   std::printf("streamer drop-in ok: %zu tsdf blocks, %zu mesh blocks, %zu mesh bytes\n", all.size(), mall.size(), total_bytes);
   return 0;
 }

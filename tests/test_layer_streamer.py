@@ -131,3 +131,16 @@ def test_bandwidth_estimate():
     for i in range(1, 6):
         n.append(len(s.estimate_bandwidth_and_serialize(layer, have, bandwidth_limit_mbps=8.0, now_s=0.1 * i)["block_indices"]))
     assert n[-1] == 24 and s.num_candidates() > 0
+
+
+def test_layer_cake_streamer():
+    """LayerCakeStreamer (nvblox/tests/test_layer_cake_streamer.cpp): a streamer per layer kind; unknown kinds do nothing."""
+    have = np.array([[i, 0, 0] for i in range(20)])
+    layer = FakeLayer(have)
+    cake = st.LayerCakeStreamer("tsdf", "mesh")
+    cake.add("tsdf")  # already there
+    assert cake.get("tsdf") is not None and cake.get("esdf") is None
+    got = cake.estimate_bandwidth_and_serialize("tsdf", layer, have)
+    assert len(got["block_indices"]) == 20 and cake.get("tsdf").num_candidates() == 0
+    assert cake.estimate_bandwidth_and_serialize("esdf", layer, have) is None
+    assert len(cake.serialize_all_blocks("tsdf", layer, have[:3])["block_indices"]) == 3
