@@ -228,7 +228,9 @@ struct NvbMapper {
   int xyz_upload_cap = 0;
 
   // pinned host scratch
-  int* h_ints = nullptr;  // [0] frame count, [1] error, [2..] misc
+  int* h_ints = nullptr;  // [0] frame count, [1] error, [2..] misc, [8], [9] prefetched error words (pinned)
+  int4* h_list = nullptr;  // pinned: the last frame's block list lands here (readFrameList)
+  int last_frame_n = 0;
   int* h_count_ring = nullptr;
   cudaEvent_t count_events[kCountRing];
   bool count_pending[kCountRing];
@@ -416,6 +418,8 @@ int allocTsdfSide(NvbMapper* m, int old_cap, int cap) {
   }
   return NVB_OK;
 }
+
+constexpr int kHostListCap = 1 << 15;  // entries of the pinned frame-list buffer (512 KiB)
 
 // esdf_ints layout
 enum { kWorkCount = 0, kUpdCount = 1, kClrCount = 2, kClrAabb = 3, kClearedCount = 9, kRingCount = 10, kRingId = 14,
@@ -957,16 +961,50 @@ int enqueueFrame(NvbMapper* m, const float* depth, const unsigned char* mask, in
   return NVB_OK;
 }
 
+// The error word, copied to pinned host memory behind everything that is enqueued so far on both streams: after the next
+// syncAll the host knows whether any kernel raised an error without a blocking copy of its own (a 4-byte cudaMemcpy is a
+// full host round trip, ~10 us, and the synchronous API paid two of them per frame).
+constexpr int kHostErrMain = 8, kHostErrEsdf = 9;
+int enqueueErrorCopies(NvbMapper* m) {
+  m->h_ints[kHostErrMain] = 0, m->h_ints[kHostErrEsdf] = 0;
+  NVB_CUDA(cudaMemcpyAsync(m->h_ints + kHostErrMain, m->error_dev, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  if (m->esdf_stream)
+    NVB_CUDA(cudaMemcpyAsync(m->h_ints + kHostErrEsdf, m->error_dev, sizeof(int), cudaMemcpyDeviceToHost, m->esdf_stream));
+  return NVB_OK;
+}
+// After enqueueErrorCopies + syncAll.
+int checkPrefetchedError(NvbMapper* m) {
+  if ((m->h_ints[kHostErrMain] | m->h_ints[kHostErrEsdf]) == 0) return NVB_OK;
+  return checkDeviceError(m);  // slow path: re-reads the word, rolls back, reports
+}
+
+// Count + list of the last frame's blocks with ONE synchronisation: the count, a speculative prefix of the list (sized from
+// the previous frame's count) and the error word travel to pinned host memory behind the frame's kernels.
 int readFrameList(NvbMapper* m, int32_t* out_xyz, int32_t cap, int32_t* out_count) {
+  int want = 0;
+  if (out_xyz && cap > 0 && m->h_list) {
+    want = std::min<long long>(std::min<long long>(cap, kHostListCap), (long long)m->last_frame_n * 3 / 2 + 512);
+    want = std::min(want, m->frame_cap);
+  }
   NVB_CUDA(cudaMemcpyAsync(m->h_ints, m->frame_count, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  if (want > 0)
+    NVB_CUDA(cudaMemcpyAsync(m->h_list, m->frame_blocks, (size_t)want * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
+  int rc = enqueueErrorCopies(m);
+  if (rc) return rc;
   NVB_CUDA(syncAll(m));
   const int n = m->h_ints[0];
+  m->last_frame_n = n;
   if (out_count) *out_count = n;
   if (out_xyz && cap > 0 && n > 0) {
     const int k = std::min(n, cap);
-    std::vector<int4> tmp((size_t)k);
-    NVB_CUDA(cudaMemcpy(tmp.data(), m->frame_blocks, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < k; i++) out_xyz[3 * i] = tmp[i].x, out_xyz[3 * i + 1] = tmp[i].y, out_xyz[3 * i + 2] = tmp[i].z;
+    const int4* src = m->h_list;
+    std::vector<int4> tmp;
+    if (k > want) {  // the frame has more blocks than the speculative prefix: one more copy
+      tmp.resize((size_t)k);
+      NVB_CUDA(cudaMemcpy(tmp.data(), m->frame_blocks, (size_t)k * sizeof(int4), cudaMemcpyDeviceToHost));
+      src = tmp.data();
+    }
+    for (int i = 0; i < k; i++) out_xyz[3 * i] = src[i].x, out_xyz[3 * i + 1] = src[i].y, out_xyz[3 * i + 2] = src[i].z;
   }
   return NVB_OK;
 }
@@ -1210,6 +1248,8 @@ static int createMapperResources(const NvbMapperOptions* opts, NvbMapper* m) {
   NVB_CUDA(cudaMalloc(&m->ticket, 64));
   NVB_CUDA(cudaMemsetAsync(m->ticket, 0, 64, m->stream));
   NVB_CUDA(cudaMallocHost(&m->h_ints, 64 * sizeof(int)));
+  memset(m->h_ints, 0, 64 * sizeof(int));
+  NVB_CUDA(cudaMallocHost(&m->h_list, (size_t)kHostListCap * sizeof(int4)));
   NVB_CUDA(cudaMallocHost(&m->h_count_ring, kCountRing * sizeof(int)));
   for (int k = 0; k < kCountRing; k++) {
     NVB_CUDA(cudaEventCreateWithFlags(&m->count_events[k], cudaEventDisableTiming));
@@ -1286,7 +1326,7 @@ void nvb_mapper_destroy(NvbMapper* m) {
   cudaFree(m->clr_bits), cudaFree(m->union_bits), cudaFree(m->union_state);
   cudaFree(m->vc_bits[0]), cudaFree(m->vc_bits[1]);
   cudaFree(m->stats), cudaFree(m->barrier), cudaFree(m->phase_max), cudaFree(m->xyz_upload);
-  cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring);
+  cudaFreeHost(m->h_ints), cudaFreeHost(m->h_count_ring), cudaFreeHost(m->h_list);
   for (int k = 0; k < kCountRing; k++) cudaEventDestroy(m->count_events[k]);
   cudaStreamDestroy(m->stream), cudaStreamDestroy(m->copy_stream);
   delete m;
@@ -2093,7 +2133,7 @@ int32_t nvb_mapper_integrate_depth(NvbMapper* m, const float* depth, const uint8
   int rc = nvb_mapper_integrate_depth_async(m, depth, mask, mask_mode, memory, rows, cols, T_L_C, cam);
   if (rc) return rc;
   if ((rc = readFrameList(m, updated_xyz_host, cap, out_count))) return rc;
-  return checkDeviceError(m);
+  return checkPrefetchedError(m);
 }
 
 int32_t nvb_mapper_update_esdf_async(NvbMapper* m, int32_t update_full_layer) {
@@ -2271,10 +2311,12 @@ int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float 
 int32_t nvb_mapper_synchronize(NvbMapper* m) {
   if (!m) return fail(NVB_ERR_INVALID_ARGUMENT, "null mapper");
   NVB_CUDA(cudaSetDevice(m->device));
+  int rc = enqueueErrorCopies(m);
+  if (rc) return rc;
   NVB_CUDA(syncAll(m));
   NVB_CUDA(cudaGetLastError());
   collectStages(m);
-  return checkDeviceError(m);
+  return checkPrefetchedError(m);
 }
 
 int32_t nvb_mapper_last_frame_block_count(NvbMapper* m, int32_t* out_count) {
