@@ -35,6 +35,14 @@ class AxisAlignedBoundingBox {
   const Vector3f& min() const { return min_; }
   const Vector3f& max() const { return max_; }
   bool isEmpty() const { return empty_ || min_[0] > max_[0] || min_[1] > max_[1] || min_[2] > max_[2]; }
+  // Eigen::AlignedBox::merged: the box that encloses both (an empty box contributes nothing)
+  AxisAlignedBoundingBox merged(const AxisAlignedBoundingBox& o) const {
+    if (isEmpty()) return o;
+    if (o.isEmpty()) return *this;
+    Vector3f mn, mx;
+    for (int a = 0; a < 3; a++) mn[a] = min_[a] < o.min_[a] ? min_[a] : o.min_[a], mx[a] = max_[a] > o.max_[a] ? max_[a] : o.max_[a];
+    return AxisAlignedBoundingBox(mn, mx);
+  }
 
  private:
   Vector3f min_, max_;

@@ -420,6 +420,15 @@ NVB_API int32_t nvb_esdf_integrate_slice_blocks(NvbMapper* m, const int32_t* blo
 NVB_API int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float unobserved_value,
                                               float aabb_out[6], float* image_host, int8_t* grid_host, int32_t cap_pixels,
                                               int32_t* rows_out, int32_t* cols_out);
+/* EsdfSlicer::getAabbOfLayerAtHeight (C/src/integrators/esdf_slicer.cu:112-147): the box of the ESDF blocks at the slice's z
+ * index; *empty_out = 1 (aabb_out untouched) if there is none. */
+NVB_API int32_t nvb_esdf_slice_aabb(NvbMapper* m, float slice_height_m, float aabb_out[6], int32_t* empty_out);
+/* EsdfSlicer::sliceLayerToDistanceImage(layer, slice_height, unobserved_value, aabb, image) on a GIVEN box (:169-199): the
+ * building block of sliceLayersToCombinedDistanceImage (C/include/nvblox/integrators/esdf_slicer.h:78-118, esdf_slicer.cu:
+ * 201-240), which slices two layers (two mappers here) on the merged box of their slices and takes the element-wise minimum. */
+NVB_API int32_t nvb_esdf_slice_distance_image_in_aabb(NvbMapper* m, float slice_height_m, float unobserved_value, const float aabb[6],
+                                                      float* image_host, int8_t* grid_host, int32_t cap_pixels, int32_t* rows_out,
+                                                      int32_t* cols_out);
 
 /* EsdfIntegrator::integrateBlocks(const TsdfLayer&, const std::vector<Index3D>&, EsdfLayer*)
  * (esdf_integrator.h:56-58, src/integrators/esdf_integrator.cu:220-266) on an

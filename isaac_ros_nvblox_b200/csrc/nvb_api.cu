@@ -2266,11 +2266,9 @@ static int32_t integrateSliceBlocksImpl(NvbMapper* m, const float* plane, const 
   return tightenEsdfBound(m);
 }
 
-int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float unobserved_value, float aabb_out[6],
-                                      float* image_host, int8_t* grid_host, int32_t cap_pixels, int32_t* rows_out,
-                                      int32_t* cols_out) {
-  if (!m || !rows_out || !cols_out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
-  *rows_out = *cols_out = 0;
+int32_t nvb_esdf_slice_aabb(NvbMapper* m, float slice_height_m, float aabb_out[6], int32_t* empty_out) {
+  if (!m || !aabb_out || !empty_out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *empty_out = 1;
   NVB_CUDA(cudaSetDevice(m->device));
   NVB_CUDA(syncAll(m));
   const int zb = (int)std::floor(slice_height_m / m->block_size);
@@ -2282,15 +2280,28 @@ int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float 
   NVB_CUDA(cudaMemcpyAsync(box, box_dev, sizeof(box), cudaMemcpyDeviceToHost, m->stream));
   NVB_CUDA(cudaStreamSynchronize(m->stream));
   NVB_CUDA(cudaMemsetAsync(box_dev, 0, sizeof(box), m->stream));
+  m->launches++;
   if (box[0] > box[2]) return NVB_OK;  // no block at that height: empty AABB (:166-168)
   // getAABBOfBlock: [index * block_size, (index + 1) * block_size]
   const float bs = m->block_size;
-  const float amin[3] = {(float)box[0] * bs, (float)box[1] * bs, (float)zb * bs};
-  const float amax[3] = {((float)box[2] + 1.0f) * bs, ((float)box[3] + 1.0f) * bs, ((float)zb + 1.0f) * bs};
-  if (aabb_out)
-    for (int a = 0; a < 3; a++) aabb_out[a] = amin[a], aabb_out[3 + a] = amax[a];
+  aabb_out[0] = (float)box[0] * bs, aabb_out[1] = (float)box[1] * bs, aabb_out[2] = (float)zb * bs;
+  aabb_out[3] = ((float)box[2] + 1.0f) * bs, aabb_out[4] = ((float)box[3] + 1.0f) * bs, aabb_out[5] = ((float)zb + 1.0f) * bs;
+  *empty_out = 0;
+  return NVB_OK;
+}
+
+int32_t nvb_esdf_slice_distance_image_in_aabb(NvbMapper* m, float slice_height_m, float unobserved_value, const float aabb[6],
+                                              float* image_host, int8_t* grid_host, int32_t cap_pixels, int32_t* rows_out,
+                                              int32_t* cols_out) {
+  if (!m || !aabb || !rows_out || !cols_out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *rows_out = *cols_out = 0;
+  NVB_CUDA(cudaSetDevice(m->device));
+  NVB_CUDA(syncAll(m));
+  const float bs = m->block_size;
   const float voxel_size = bs / (float)kVps;
-  const int cols = (int)std::ceil((amax[0] - amin[0]) / voxel_size), rows = (int)std::ceil((amax[1] - amin[1]) / voxel_size);
+  const float sx = aabb[3] - aabb[0], sy = aabb[4] - aabb[1];
+  if (!(sx > 0.0f) || !(sy > 0.0f)) return NVB_OK;  // aabb.isEmpty() (:175-177)
+  const int cols = (int)std::ceil(sx / voxel_size), rows = (int)std::ceil(sy / voxel_size);
   *rows_out = rows, *cols_out = cols;
   const long long npix = (long long)rows * cols;
   if (npix <= 0 || (!image_host && !grid_host) || cap_pixels <= 0) return NVB_OK;
@@ -2298,14 +2309,29 @@ int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float 
   signed char* grid_dev = nullptr;
   if (image_host) NVB_CUDA(cudaMalloc(&img_dev, (size_t)npix * sizeof(float)));
   if (grid_host) NVB_CUDA(cudaMalloc(&grid_dev, (size_t)npix));
-  launchSliceImage(m->esdf, bs, amin[0], amin[1], slice_height_m, unobserved_value, rows, cols, img_dev, grid_dev, m->stream);
-  m->launches += 2;
+  launchSliceImage(m->esdf, bs, aabb[0], aabb[1], slice_height_m, unobserved_value, rows, cols, img_dev, grid_dev, m->stream);
+  m->launches++;
   const size_t k = (size_t)std::min<long long>(npix, cap_pixels);
   if (image_host) NVB_CUDA(cudaMemcpyAsync(image_host, img_dev, k * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   if (grid_host) NVB_CUDA(cudaMemcpyAsync(grid_host, grid_dev, k, cudaMemcpyDeviceToHost, m->stream));
   NVB_CUDA(cudaStreamSynchronize(m->stream));
   cudaFree(img_dev), cudaFree(grid_dev);
   return NVB_OK;
+}
+
+int32_t nvb_esdf_slice_distance_image(NvbMapper* m, float slice_height_m, float unobserved_value, float aabb_out[6],
+                                      float* image_host, int8_t* grid_host, int32_t cap_pixels, int32_t* rows_out,
+                                      int32_t* cols_out) {
+  if (!m || !rows_out || !cols_out) return fail(NVB_ERR_INVALID_ARGUMENT, "null argument");
+  *rows_out = *cols_out = 0;
+  float box[6];
+  int32_t empty = 1;
+  int rc = nvb_esdf_slice_aabb(m, slice_height_m, box, &empty);
+  if (rc || empty) return rc;
+  if (aabb_out)
+    for (int a = 0; a < 6; a++) aabb_out[a] = box[a];
+  return nvb_esdf_slice_distance_image_in_aabb(m, slice_height_m, unobserved_value, box, image_host, grid_host, cap_pixels, rows_out,
+                                               cols_out);
 }
 
 int32_t nvb_mapper_synchronize(NvbMapper* m) {

@@ -505,6 +505,46 @@ class EsdfSlicer:
         img = img[:r.value, :c.value]
         return (aabb, img, grid[:r.value, :c.value]) if with_occupancy_grid else (aabb, img)
 
+    def get_aabb_of_layer_at_height(self, slice_height):
+        """EsdfSlicer::getAabbOfLayerAtHeight (esdf_slicer.h:29-35) -> (6,) float32, or None for an empty box."""
+        aabb = np.zeros(6, np.float32)
+        empty = C.c_int32(1)
+        check(self._m._L.nvb_esdf_slice_aabb(self._m._h, float(slice_height), _fp(aabb), C.byref(empty)))
+        return None if empty.value else aabb
+
+    def slice_layer_to_distance_image_in_aabb(self, slice_height, aabb, unobserved_value=1000.0):
+        """EsdfSlicer::sliceLayerToDistanceImage(layer, slice_height, unobserved_value, aabb, image): a given box."""
+        L, h = self._m._L, self._m._h
+        box = np.ascontiguousarray(aabb, np.float32).reshape(6)
+        r, c = C.c_int32(0), C.c_int32(0)
+        check(L.nvb_esdf_slice_distance_image_in_aabb(h, float(slice_height), float(unobserved_value), _fp(box), None, None, 0,
+                                                      C.byref(r), C.byref(c)))
+        img = np.zeros((max(r.value, 1), max(c.value, 1)), np.float32)
+        if r.value * c.value > 0:
+            check(L.nvb_esdf_slice_distance_image_in_aabb(h, float(slice_height), float(unobserved_value), _fp(box), _fp(img), None,
+                                                          r.value * c.value, C.byref(r), C.byref(c)))
+        return img[:r.value, :c.value]
+
+    def slice_layers_to_combined_distance_image(self, other_mapper, slice_height_1, slice_height_2, unobserved_value=1000.0,
+                                                with_occupancy_grid=False):
+        """EsdfSlicer::sliceLayersToCombinedDistanceImage (esdf_slicer.h:78-118, src/integrators/esdf_slicer.cu:201-240): this
+        mapper's ESDF layer and another mapper's (e.g. MultiMapper's static and dynamic maps) sliced on the merged box of their
+        slices, element-wise minimum. -> (aabb, image[, grid]); (None, None[, None]) if neither layer has a block there."""
+        other = EsdfSlicer(other_mapper)
+        boxes = [b for b in (self.get_aabb_of_layer_at_height(slice_height_1), other.get_aabb_of_layer_at_height(slice_height_2))
+                 if b is not None]
+        if not boxes:
+            return (None, None, None) if with_occupancy_grid else (None, None)
+        aabb = np.concatenate([np.min([b[:3] for b in boxes], axis=0), np.max([b[3:] for b in boxes], axis=0)]).astype(np.float32)
+        img = np.minimum(self.slice_layer_to_distance_image_in_aabb(slice_height_1, aabb, unobserved_value),
+                         other.slice_layer_to_distance_image_in_aabb(slice_height_2, aabb, unobserved_value))
+        if not with_occupancy_grid:
+            return aabb, img
+        # occupancyGridFromSliceImageKernel (src/integrators/esdf_slicer.cu:78-110)
+        grid = np.where(img < np.float32(1e-2), 100, 0).astype(np.int8)
+        grid[np.abs(img - np.float32(unobserved_value)) < np.float32(1e-2)] = -1
+        return aabb, img, grid
+
 
 class Mapper:
     """nvblox::Mapper(voxel_size_m, projective_layer_type) with a projective (TSDF or occupancy) and an ESDF layer."""

@@ -1557,16 +1557,14 @@ static void esdf_integrate_slice_impl(OrMap* map, int32_t from_occupancy, int32_
   list_free(&blocks), list_free(&updated), list_free(&to_clear);
 }
 
-/* EsdfSlicer::sliceLayerToDistanceImage (src/integrators/esdf_slicer.cu:128-215) + populateSliceFromLayerKernel (:25-67) +
- * occupancyGridFromSliceImageKernel (:78-110). Returns rows * cols (0 if the layer has no block at that height); writes the
- * AABB (min xyz, max xyz), and up to cap pixels of the image / grid (either may be NULL). */
-int32_t or_esdf_slice_image(const OrMap* map, float slice_height, float unobserved_value, float aabb_out[6],
-                            float* image_out, int8_t* grid_out, int32_t cap, int32_t* rows_out, int32_t* cols_out) {
+/* EsdfSlicer::getAabbOfLayerAtHeight (src/integrators/esdf_slicer.cu:112-147): the blocks at the slice's z index. Returns 0 and
+ * leaves aabb_out alone if there is none (an empty AlignedBox in the reference). */
+int32_t or_esdf_slice_aabb(const OrMap* map, float slice_height, float aabb_out[6]) {
   const float bs = map->block_size;
   const int zb = f2i(floorf(slice_height / bs));
   int have = 0;
   int32_t mnx = 0, mny = 0, mxx = 0, mxy = 0;
-  for (int32_t s = 0; s < map->esdf.n; s++) { /* getAabbOfLayerAtHeight (:112-135) */
+  for (int32_t s = 0; s < map->esdf.n; s++) {
     const i3 k = map->esdf.index[s];
     if (k.z != zb) continue;
     if (!have) mnx = mxx = k.x, mny = mxy = k.y, have = 1;
@@ -1575,12 +1573,21 @@ int32_t or_esdf_slice_image(const OrMap* map, float slice_height, float unobserv
     if (k.y < mny) mny = k.y;
     if (k.y > mxy) mxy = k.y;
   }
-  *rows_out = *cols_out = 0;
   if (!have) return 0;
   /* getAABBOfBlock: [index * block_size, (index + 1) * block_size] */
-  const float amin[3] = {(float)mnx * bs, (float)mny * bs, (float)zb * bs};
-  const float amax[3] = {((float)mxx + 1.0f) * bs, ((float)mxy + 1.0f) * bs, ((float)zb + 1.0f) * bs};
-  for (int a = 0; a < 3; a++) aabb_out[a] = amin[a], aabb_out[3 + a] = amax[a];
+  aabb_out[0] = (float)mnx * bs, aabb_out[1] = (float)mny * bs, aabb_out[2] = (float)zb * bs;
+  aabb_out[3] = ((float)mxx + 1.0f) * bs, aabb_out[4] = ((float)mxy + 1.0f) * bs, aabb_out[5] = ((float)zb + 1.0f) * bs;
+  return 1;
+}
+
+/* EsdfSlicer::sliceLayerToDistanceImage(layer, slice_height, unobserved_value, aabb, image) (:169-199) on a GIVEN box +
+ * populateSliceFromLayerKernel (:25-67) + occupancyGridFromSliceImageKernel (:78-110). Returns rows * cols; writes up to cap
+ * pixels of the image / grid (either may be NULL). */
+int32_t or_esdf_slice_image_in_aabb(const OrMap* map, float slice_height, float unobserved_value, const float aabb[6],
+                                    float* image_out, int8_t* grid_out, int32_t cap, int32_t* rows_out, int32_t* cols_out) {
+  const float bs = map->block_size;
+  const float* amin = aabb;
+  const float* amax = aabb + 3;
   const float voxel_size = bs / (float)VPS;
   const int cols = f2i(ceilf((amax[0] - amin[0]) / voxel_size)), rows = f2i(ceilf((amax[1] - amin[1]) / voxel_size));
   *rows_out = rows, *cols_out = cols;
@@ -1617,6 +1624,17 @@ int32_t or_esdf_slice_image(const OrMap* map, float slice_height, float unobserv
       }
     }
   return rows * cols;
+}
+
+/* EsdfSlicer::sliceLayerToDistanceImage(layer, slice_height, unobserved_value, &aabb, image) (:157-167): the layer's own box.
+ * Returns rows * cols (0 if the layer has no block at that height). */
+int32_t or_esdf_slice_image(const OrMap* map, float slice_height, float unobserved_value, float aabb_out[6],
+                            float* image_out, int8_t* grid_out, int32_t cap, int32_t* rows_out, int32_t* cols_out) {
+  *rows_out = *cols_out = 0;
+  float box[6];
+  if (!or_esdf_slice_aabb(map, slice_height, box)) return 0;
+  for (int a = 0; a < 6; a++) aabb_out[a] = box[a];
+  return or_esdf_slice_image_in_aabb(map, slice_height, unobserved_value, box, image_out, grid_out, cap, rows_out, cols_out);
 }
 
 void or_esdf_last_stats(const OrMap* map, int64_t out[8]) { memcpy(out, map->stats, sizeof(map->stats)); }

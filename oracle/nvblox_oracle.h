@@ -283,6 +283,12 @@ void or_esdf_integrate_slice_planar(OrMap* map, int32_t from_occupancy, int32_t 
  * over the AABB of the blocks at that height (aabb_out = min xyz, max xyz); rows follow y, columns x. */
 int32_t or_esdf_slice_image(const OrMap* map, float slice_height, float unobserved_value, float aabb_out[6],
                             float* image_out, int8_t* grid_out, int32_t cap, int32_t* rows_out, int32_t* cols_out);
+/* EsdfSlicer::getAabbOfLayerAtHeight (:112-147); 0 = no block at that height */
+int32_t or_esdf_slice_aabb(const OrMap* map, float slice_height, float aabb_out[6]);
+/* EsdfSlicer::sliceLayerToDistanceImage on a given AABB (:169-199): what sliceLayersToCombinedDistanceImage (:201-240) runs on
+ * each of its two layers with their merged box before the element-wise minimum */
+int32_t or_esdf_slice_image_in_aabb(const OrMap* map, float slice_height, float unobserved_value, const float aabb[6],
+                                    float* image_out, int8_t* grid_out, int32_t cap, int32_t* rows_out, int32_t* cols_out);
 
 /* Statistics of the last or_esdf_integrate call: [0] blocks marked, [1] blocks
  * with sites, [2] blocks to clear, [3] candidate blocks scanned by the clear

@@ -230,6 +230,10 @@ def lib():
     L.or_block_and_voxel_from_1d.restype = None
     L.or_esdf_slice_image.argtypes = [vp, C.c_float, C.c_float, fp, fp, C.POINTER(C.c_int8), C.c_int32, ip, ip]
     L.or_esdf_slice_image.restype = C.c_int32
+    L.or_esdf_slice_aabb.argtypes = [vp, C.c_float, fp]
+    L.or_esdf_slice_aabb.restype = C.c_int32
+    L.or_esdf_slice_image_in_aabb.argtypes = [vp, C.c_float, C.c_float, fp, fp, C.POINTER(C.c_int8), C.c_int32, ip, ip]
+    L.or_esdf_slice_image_in_aabb.restype = C.c_int32
     L.or_esdf_integrate_slice.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, C.POINTER(EsdfParams), C.c_float, C.c_float,
                                           C.c_float]
     L.or_esdf_integrate_slice.restype = None
@@ -284,6 +288,18 @@ def dilate_invalid(depth, num_dilations, threshold=1e-2, value=0.0):
     lib().or_depth_dilate_invalid(_fp(depth), depth.shape[0], depth.shape[1], int(num_dilations), float(threshold), float(value),
                                   _fp(out))
     return out
+
+
+def combined_slice_image(map_1, map_2, slice_height_1, slice_height_2, unobserved_value=1000.0):
+    """EsdfSlicer::sliceLayersToCombinedDistanceImage (src/integrators/esdf_slicer.cu:201-240): both layers sliced on the merged
+    AABB of their slices (getCombinedAabbOfLayersAtHeight, :149-157), element-wise minimum. -> (aabb or None, image or None)."""
+    boxes = [b for b in (map_1.esdf_slice_aabb(slice_height_1), map_2.esdf_slice_aabb(slice_height_2)) if b is not None]
+    if not boxes:
+        return None, None  # empty AABB: the reference returns without touching the output
+    aabb = np.concatenate([np.min([b[:3] for b in boxes], axis=0), np.max([b[3:] for b in boxes], axis=0)]).astype(np.float32)
+    i1 = map_1.esdf_slice_image_in_aabb(slice_height_1, aabb, unobserved_value)
+    i2 = map_2.esdf_slice_image_in_aabb(slice_height_2, aabb, unobserved_value)
+    return aabb, np.minimum(i1, i2)
 
 
 def default_tsdf_params(**kw):
@@ -679,6 +695,23 @@ class OracleMap:
             lib().or_esdf_slice_image(self._h, float(slice_height), float(unobserved_value), _fp(aabb), _fp(img),
                                       grid.ctypes.data_as(C.POINTER(C.c_int8)), n, C.byref(r), C.byref(c))
         return aabb, img[:r.value, :c.value], grid[:r.value, :c.value]
+
+    def esdf_slice_aabb(self, slice_height):
+        """EsdfSlicer::getAabbOfLayerAtHeight -> (6,) float32 or None if the layer has no block at that height."""
+        aabb = np.zeros(6, np.float32)
+        return aabb if lib().or_esdf_slice_aabb(self._h, float(slice_height), _fp(aabb)) else None
+
+    def esdf_slice_image_in_aabb(self, slice_height, aabb, unobserved_value=1000.0):
+        """EsdfSlicer::sliceLayerToDistanceImage on a given AABB -> image (rows, cols)."""
+        box = np.ascontiguousarray(aabb, np.float32).reshape(6)
+        r, c = C.c_int32(0), C.c_int32(0)
+        n = lib().or_esdf_slice_image_in_aabb(self._h, float(slice_height), float(unobserved_value), _fp(box), None, None, 0,
+                                              C.byref(r), C.byref(c))
+        img = np.zeros((max(r.value, 1), max(c.value, 1)), np.float32)
+        if n > 0:
+            lib().or_esdf_slice_image_in_aabb(self._h, float(slice_height), float(unobserved_value), _fp(box), _fp(img), None, n,
+                                              C.byref(r), C.byref(c))
+        return img[:r.value, :c.value]
 
     def integrate_esdf_with_freespace(self, blocks, params=None):
         params = params or default_esdf_params()

@@ -40,6 +40,18 @@ int main() {
   int occupied = 0;
   for (int8_t g : grid) occupied += g == 100;
   EXPECT(occupied > 0);  // the wall 3 m ahead crosses the band
+  {
+    // sliceLayersToCombinedDistanceImage (esdf_slicer.h:78-118): the same layer twice is the layer's own image; the given-box
+    // overload on the layer's own box too
+    AxisAlignedBoundingBox both;
+    Image<float> combined(0, 0), own(0, 0);
+    slicer.sliceLayersToCombinedDistanceImage(esdf, esdf, 1.0f, 1.0f, 1000.0f, &both, &combined);
+    slicer.sliceLayerToDistanceImage(esdf, 1.0f, 1000.0f, aabb, &own);
+    EXPECT(!both.isEmpty() && combined.rows() == image.rows() && combined.cols() == image.cols() && own.rows() == image.rows());
+    for (int r = 0; r < image.rows(); r++)
+      for (int c = 0; c < image.cols(); c++) EXPECT(combined(r, c) == image(r, c) && own(r, c) == image(r, c));
+    EXPECT(slicer.getCombinedAabbOfLayersAtHeight(esdf, esdf, 1.0f, 40.0f).max()[0] == aabb.max()[0]);
+  }
   std::vector<Index3D> blocks = mapper.tsdf_layer().getAllBlockIndices();
   TsdfLayer tsdf = mapper.tsdf_layer();
   mapper.esdf_integrator().integrateSlice(tsdf, blocks, ground, &esdf);

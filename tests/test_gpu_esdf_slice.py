@@ -199,3 +199,34 @@ def test_slicing_sphere_scene(gpu, planar):
     assert check_sphere_scene_slice(layer, planar) > 3000
     assert_esdf_equal(layer, o.esdf_layer())
     m.close()
+
+
+def test_esdf_slicer_combined_image_of_two_mappers(gpu):
+    """EsdfSlicer::sliceLayersToCombinedDistanceImage (esdf_slicer.h:78-118): two mappers (what MultiMapper's static and dynamic
+    maps are), different scenes and slice heights: merged box, image and occupancy grid equal to the oracle's, bit for bit; one
+    empty layer; two empty layers."""
+    nvb, orc = _nvb(), _orc()
+    cs, cam, ocam = cameras(320, 240)
+    poses = syn.circle_trajectory(40)
+    pairs = []
+    for sel, scene in ((poses[:3], syn.sphere_in_box()), (poses[14:17], syn.box_with_cube())):
+        m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+        for i, (d, T) in enumerate(syn.make_sequence(scene, cs, sel)):
+            b = m.integrate_depth(d, T, cam)
+            o.integrate_depth(d, T, ocam)
+            m.update_esdf()
+            o.integrate_esdf(b if i else o.tsdf_block_indices())
+        pairs.append((m, o))
+    (m1, o1), (m2, o2) = pairs
+    for h1, h2 in ((1.0, 1.0), (0.93, 1.7), (1.0, 40.0)):
+        aabb_g, img_g, grid_g = nvb.EsdfSlicer(m1).slice_layers_to_combined_distance_image(m2, h1, h2, 1000.0, with_occupancy_grid=True)
+        aabb_c, img_c = orc.combined_slice_image(o1, o2, h1, h2, 1000.0)
+        assert np.array_equal(aabb_g, aabb_c) and img_g.shape == img_c.shape and img_c.size > 0
+        assert np.array_equal(img_g.view(np.uint32), img_c.view(np.uint32))
+        assert np.array_equal(grid_g == 100, img_c < np.float32(1e-2)) and np.array_equal(grid_g == -1, np.abs(img_c - 1000.0) < 1e-2)
+        box = nvb.EsdfSlicer(m1).get_aabb_of_layer_at_height(h1)
+        assert np.array_equal(box, o1.esdf_slice_aabb(h1))
+    assert nvb.EsdfSlicer(m1).slice_layers_to_combined_distance_image(m2, 40.0, 41.0) == (None, None)
+    assert nvb.EsdfSlicer(m1).get_aabb_of_layer_at_height(40.0) is None
+    for m, _ in pairs:
+        m.close()

@@ -1363,3 +1363,34 @@ def test_weighting_function_unit_cases():
         assert abs(w(2, d) - want) < eps
     for d, want in ((0.0, 1.0), (0.5, 1.0), (1.0, 1.0), (5.0, 0.2)):
         assert abs(w(5, d) - want) < eps
+
+
+def test_esdf_slicer_combined_image_of_two_layers():
+    """EsdfSlicer::sliceLayersToCombinedDistanceImage (esdf_slicer.cu:149-157, 201-240; the reference ships no test of it):
+    both layers sliced on the box that encloses their slices, element-wise minimum. Checked against the definition: every pixel
+    is the smaller of the two layers' single-layer pixels at the same world position (unobserved = 1000 loses against any distance),
+    the box is the union box, and one empty layer leaves the other layer's own image."""
+    voxel = 0.1
+    cs = syn.PinholeCamera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    cam = orc.Camera(150.0, 150.0, 160.0, 120.0, 320, 240)
+    poses = syn.circle_trajectory(16)
+    a, b, empty = orc.OracleMap(voxel), orc.OracleMap(voxel), orc.OracleMap(voxel)
+    for m, sel, scene in ((a, poses[:2], syn.sphere_in_box()), (b, poses[6:8], syn.box_with_cube())):
+        for i, (d, T) in enumerate(syn.make_sequence(scene, cs, sel)):
+            blocks = m.integrate_depth(d, T, cam)
+            m.integrate_esdf(blocks if i else m.tsdf_block_indices())
+    ha, hb = 1.0, 1.3
+    aabb, img = orc.combined_slice_image(a, b, ha, hb)
+    box_a, img_a, _ = a.esdf_slice_image(ha)
+    box_b, img_b, _ = b.esdf_slice_image(hb)
+    assert np.allclose(aabb[:2], np.minimum(box_a[:2], box_b[:2])) and np.allclose(aabb[3:5], np.maximum(box_a[3:5], box_b[3:5]))
+    assert img.shape == (round((aabb[4] - aabb[1]) / voxel), round((aabb[3] - aabb[0]) / voxel))
+    want = np.full(img.shape, 1000.0, np.float32)
+    for box, im in ((box_a, img_a), (box_b, img_b)):
+        r0, c0 = round((box[1] - aabb[1]) / voxel), round((box[0] - aabb[0]) / voxel)
+        want[r0:r0 + im.shape[0], c0:c0 + im.shape[1]] = np.minimum(want[r0:r0 + im.shape[0], c0:c0 + im.shape[1]], im)
+    assert np.array_equal(img, want)
+    assert (img < img_a.max()).any() and (np.abs(img) < 1e-2).any() and (img == 1000.0).any()
+    one_box, one = orc.combined_slice_image(a, empty, ha, hb)
+    assert np.array_equal(one_box, box_a) and np.array_equal(one, img_a)
+    assert orc.combined_slice_image(empty, empty, ha, hb) == (None, None)
