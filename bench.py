@@ -324,7 +324,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl.description, "frames_per_step": len(wl.frames), "voxel_size_m": VOXEL},
+        "config": {"workload": wl.description, "workload_id": wl.name, "frames_per_step": len(wl.frames), "voxel_size_m": VOXEL,
+                   "parallelism": "the reference's algorithm on the host cores of rank 0 (OpenMP), the same frames as one GPU rank"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": orc.num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
