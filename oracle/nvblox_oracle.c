@@ -2171,6 +2171,13 @@ static int32_t decay_layer(OrMap* map, int occupancy, const void* params, const 
     layer_remove_blocks(L, rm.v, rm.n);
     if (clear_esdf == 1) layer_remove_blocks(&map->esdf, rm.v, rm.n);
     if (clear_esdf) layer_remove_blocks(&map->freespace, rm.v, rm.n), layer_remove_blocks(&map->color, rm.v, rm.n);
+    if (clear_esdf && !occupancy) { /* ColorMeshLayer::clearBlocksAsync (src/mapper/mapper.cpp:552-557): TSDF mappers only */
+      for (int32_t i = 0; i < rm.n; i++) {
+        const int32_t ms = hash_find(&map->mesh.hash, rm.v[i]);
+        if (ms >= 0) mesh_block_release((MeshBlock*)layer_block(&map->mesh, ms));
+      }
+      layer_remove_blocks(&map->mesh, rm.v, rm.n);
+    }
     if (clear_esdf == 2) {
       /* 2-D ESDF (src/mapper/mapper.cpp:569-626): a column's slice block goes when no projective block is left in the
        * vertical column within the slice bounds (the projective blocks were removed above) */

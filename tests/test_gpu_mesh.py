@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import mesh_cases as mc
-from helpers import cameras
+from helpers import cameras, sort_rows
 from isaac_ros_nvblox_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
@@ -172,4 +172,26 @@ def test_decay_removes_mesh_blocks_with_their_tsdf_blocks(gpu):
     m.integrate_depth(frames[0][0], frames[0][1], cam)
     m.update_mesh()
     assert 0 < m.mesh_layer().num_blocks() <= before
+    m.close()
+    # a PARTIAL removal, side by side with the oracle: blocks outside a sphere decay away, the mesh blocks of the rest stay as
+    # they are (vertices, normals, indices), later mesh updates reuse the freed header slots and arena space
+    m, o = nvb.Mapper(0.05), orc.OracleMap(0.05)
+    for d, T in frames:
+        assert np.array_equal(m.integrate_depth(d, T, cam), o.integrate_depth(d, T, ocam))
+    m.update_mesh()
+    o.integrate_mesh()
+    dp = orc.default_tsdf_decay_params(decay_factor=1e-6, decayed_weight_threshold=1e-3)
+    m.tsdf_decay_integrator().params(decay_factor=1e-6, decayed_weight_threshold=1e-3)
+    center = tuple(float(c) for c in frames[0][1][:3, 3] + 2.5 * frames[0][1][:3, 2])
+    gone_g = m.decay(exclusion_center=center, exclusion_radius_m=1.2)
+    gone_c = o.decay_tsdf(dp, exclusion_center=center, exclusion_radius_m=1.2)
+    assert len(gone_c) > 0 and np.array_equal(sort_rows(gone_g), sort_rows(gone_c))
+    assert 0 < m.tsdf_layer().num_blocks() == len(o.tsdf_block_indices())
+    assert_mesh_equal(m.mesh_layer().as_dict(), o.mesh_layer())
+    assert 0 < m.mesh_layer().num_blocks() < before
+    b = m.integrate_depth(frames[1][0], frames[1][1], cam)
+    assert np.array_equal(b, o.integrate_depth(frames[1][0], frames[1][1], ocam))
+    m.update_mesh()  # after a deallocation the tracker restarts with every block (like the ESDF's)
+    o.integrate_mesh()
+    assert_mesh_equal(m.mesh_layer().as_dict(), o.mesh_layer())
     m.close()
