@@ -628,6 +628,11 @@ class Mapper:
         """Mapper::color_mesh_integrator()."""
         return _MeshIntegrator(self)
 
+    def save_color_mesh_as_ply(self, filename):
+        """Mapper::saveColorMeshAsPly (src/mapper/mapper.cpp:694-696)."""
+        from . import io as _io
+        return _io.output_color_mesh_layer_to_ply(self.mesh_layer(), filename)
+
     def update_mesh(self, update_full_layer=False):
         """Mapper::updateColorMesh(UpdateFullLayer) (mapper.h; src/mapper/mapper.cpp:371-406)."""
         check(self._L.nvb_mapper_update_mesh(self._h, 1 if update_full_layer else 0))
