@@ -1394,3 +1394,17 @@ def test_esdf_slicer_combined_image_of_two_layers():
     one_box, one = orc.combined_slice_image(a, empty, ha, hb)
     assert np.array_equal(one_box, box_a) and np.array_equal(one, img_a)
     assert orc.combined_slice_image(empty, empty, ha, hb) == (None, None)
+
+
+def test_blocks_within_radius_known_answers():
+    """BoundingSpheresTest.BlocksInside (nvblox/tests/test_bounding_spheres.cpp:56-79) through the oracle's
+    markUnobservedFreeInsideRadius, which selects blocks with the same isBlockWithinRadius test (exterior distance of the block's
+    box to the centre < radius): 1 m blocks around (0.5, 0.5, 0.5): radius 0.45 -> the centre block only; 0.55 -> it and its six
+    face neighbours; sqrt(3)/2 + 0.01 -> the whole 3x3x3 cube. BlocksOutside (:81-104) is the complement: 26 / 20 / 0 of 27."""
+    cube = {(x, y, z) for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)}
+    faces = {(0, 0, 0), (-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)}
+    for radius, want in ((0.45, {(0, 0, 0)}), (0.55, faces), (np.sqrt(3.0) / 2.0 + 0.01, cube)):
+        m = orc.OracleMap(0.125)  # 8 voxels of 12.5 cm: 1 m blocks
+        got = {tuple(int(c) for c in k) for k in m.mark_unobserved_free_inside_radius((0.5, 0.5, 0.5), radius)}
+        assert got == want, radius
+        assert len(cube - got) == 27 - len(want)
